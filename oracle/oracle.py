@@ -1,0 +1,244 @@
+"""ctypes front-end of oracle/sigma_oracle.c (TEST INFRASTRUCTURE, not product).
+
+All index arrays are 1-based int32 numpy arrays laid out exactly as the
+Fortran reference holds them (see the C file's header).  Every wrapper names
+the C function it calls; the C function cites the reference file:line.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libsigma_oracle.so")
+
+CSR, CSC, ELL = 1, 2, 3
+
+__all__ = [
+    "CSR", "CSC", "ELL", "build", "lib", "Matrix", "ll_graph_edges", "cs_graph_build",
+    "ellpack_graph_build", "matvec", "matvec_add", "jacobi_setup", "jacobi_solve",
+    "cg_solve", "bicgstab_solve", "lanczos", "eigensolve", "tridiag_eig",
+    "partition_rows", "halo_build", "cs_set_value", "ell_set_value",
+]
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with oracle/Makefile (gcc, strict fp flags)."""
+    src = os.path.join(_HERE, "sigma_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE])
+    return _SO
+
+
+class _OrcMatrix(C.Structure):
+    _fields_ = [
+        ("format", C.c_int32), ("nrow", C.c_int32), ("ncol", C.c_int32), ("max_d", C.c_int32),
+        ("ptr", C.c_void_p), ("node", C.c_void_p), ("degrees", C.c_void_p), ("val", C.c_void_p),
+    ]
+
+
+_lib = None
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    L = C.CDLL(build())
+    i32, i64, f64, vp = C.c_int32, C.c_int64, C.c_double, C.c_void_p
+    mp = C.POINTER(_OrcMatrix)
+    sig = {
+        "orc_ll_graph_edges": (i64, [i32, i64, _i32p, _i32p, _i32p, _i32p, C.POINTER(i32)]),
+        "orc_cs_graph_build": (i32, [i32, i64, _i32p, _i32p, i32, _i32p, _i32p]),
+        "orc_ellpack_max_degree": (i32, [i32, i64, _i32p, _i32p, i32]),
+        "orc_ellpack_graph_build": (None, [i32, i64, _i32p, _i32p, i32, i32, _i32p, _i32p]),
+        "orc_cs_set_value": (i32, [_i32p, _i32p, _f64p, i32, i32, f64, i32]),
+        "orc_cs_get_value": (f64, [_i32p, _i32p, _f64p, i32, i32]),
+        "orc_ell_set_value": (i32, [i32, _i32p, _i32p, _f64p, i32, i32, f64, i32]),
+        "orc_ell_get_value": (f64, [i32, _i32p, _i32p, _f64p, i32, i32]),
+        "orc_matvec_add": (None, [mp, i32, _f64p, _f64p]),
+        "orc_matvec": (None, [mp, i32, _f64p, _f64p]),
+        "orc_jacobi_setup": (None, [mp, _f64p]),
+        "orc_jacobi_solve": (None, [i32, _f64p, _f64p, _f64p]),
+        "orc_cg_solve": (i64, [mp, _f64p, _f64p, f64, i64, _f64p, C.POINTER(f64), C.POINTER(i32)]),
+        "orc_cg_solve_jacobi": (i64, [mp, _f64p, _f64p, _f64p, f64, i64, _f64p, C.POINTER(f64), C.POINTER(i32)]),
+        "orc_bicgstab_solve": (i64, [mp, _f64p, _f64p, f64, i64, _f64p, C.POINTER(f64), C.POINTER(i32)]),
+        "orc_bicgstab_solve_jacobi": (i64, [mp, _f64p, _f64p, _f64p, f64, i64, _f64p, C.POINTER(f64), C.POINTER(i32)]),
+        "orc_lanczos": (None, [mp, i32, _f64p, _f64p, _f64p, _f64p]),
+        "orc_tridiag_eig": (i32, [i32, _f64p, _f64p, _f64p]),
+        "orc_eigensolve": (i32, [mp, i32, _f64p, _f64p, _f64p]),
+        "orc_partition_rows": (None, [i32, _i32p, i32, _i32p]),
+        "orc_halo_build": (i32, [i32, i32, _i32p, _i32p, _i32p, _i32p]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    _ = vp
+    _lib = L
+    return L
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Matrix:
+    """Host matrix in the reference's own storage.
+
+    CSR/CSC: ``ptr`` (n+1), ``node`` (ne), ``val`` (ne), 1-based.
+    ELL: ``node``/``val`` of shape (nrow, max_d) C-order == Fortran
+    ``node(max_d, nrow)`` column-major; ``degrees`` (nrow).
+    """
+
+    def __init__(self, fmt, nrow, ncol, node, val, ptr=None, degrees=None):
+        self.format, self.nrow, self.ncol = fmt, int(nrow), int(ncol)
+        self.node, self.val = _i32(node), _f64(val)
+        self.ptr = _i32(ptr) if ptr is not None else None
+        self.degrees = _i32(degrees) if degrees is not None else None
+        self.max_d = int(self.node.shape[1]) if fmt == ELL else 0
+        self._c = _OrcMatrix(
+            fmt, self.nrow, self.ncol, self.max_d,
+            self.ptr.ctypes.data if self.ptr is not None else None,
+            self.node.ctypes.data,
+            self.degrees.ctypes.data if self.degrees is not None else None,
+            self.val.ctypes.data,
+        )
+
+    @property
+    def c(self):
+        return C.byref(self._c)
+
+
+def ll_graph_edges(n, ei, ej):
+    """orc_ll_graph_edges: replay add_edge calls, return iteration-order edges."""
+    ei, ej = _i32(ei), _i32(ej)
+    oi, oj = np.empty_like(ei), np.empty_like(ej)
+    md = C.c_int32(0)
+    ne = lib().orc_ll_graph_edges(n, ei.size, ei, ej, oi, oj, C.byref(md))
+    return oi[:ne].copy(), oj[:ne].copy(), md.value
+
+
+def cs_graph_build(n, src_i, src_j, trans=False):
+    """orc_cs_graph_build -> (ptr, node, max_d), 1-based."""
+    src_i, src_j = _i32(src_i), _i32(src_j)
+    ptr = np.empty(n + 1, np.int32)
+    node = np.empty(src_i.size, np.int32)
+    md = lib().orc_cs_graph_build(n, src_i.size, src_i, src_j, int(trans), ptr, node)
+    if md < 0:
+        raise ValueError("edge stream held duplicates")
+    return ptr, node, md
+
+
+def ellpack_graph_build(n, src_i, src_j, trans=False):
+    """orc_ellpack_max_degree + orc_ellpack_graph_build -> (node[n,max_d], degrees)."""
+    src_i, src_j = _i32(src_i), _i32(src_j)
+    md = lib().orc_ellpack_max_degree(n, src_i.size, src_i, src_j, int(trans))
+    node = np.empty((n, md), np.int32)
+    deg = np.empty(n, np.int32)
+    lib().orc_ellpack_graph_build(n, src_i.size, src_i, src_j, int(trans), md, node.reshape(-1), deg)
+    return node, deg
+
+
+def cs_set_value(ptr, node, val, i, j, z, add=False):
+    return lib().orc_cs_set_value(ptr, node, val, i, j, z, int(add))
+
+
+def ell_set_value(node, degrees, val, i, j, z, add=False):
+    return lib().orc_ell_set_value(node.shape[1], node.reshape(-1), degrees, val.reshape(-1), i, j, z, int(add))
+
+
+def matvec(A: Matrix, x, trans=False):
+    y = np.empty(A.ncol if trans else A.nrow)
+    lib().orc_matvec(A.c, int(trans), _f64(x), y)
+    return y
+
+
+def matvec_add(A: Matrix, x, y, trans=False):
+    y = _f64(y).copy()
+    lib().orc_matvec_add(A.c, int(trans), _f64(x), y)
+    return y
+
+
+def jacobi_setup(A: Matrix):
+    idiag = np.empty(A.nrow)
+    lib().orc_jacobi_setup(A.c, idiag)
+    return idiag
+
+
+def jacobi_solve(idiag, b):
+    x = np.empty_like(idiag)
+    lib().orc_jacobi_solve(idiag.size, idiag, x, _f64(b))
+    return x
+
+
+def _solve(fn, A, x0, b, tol, max_iter, nwork, idiag=None):
+    x = _f64(x0).copy()
+    work = np.zeros(nwork * A.nrow)
+    res2, capped = C.c_double(0.0), C.c_int32(0)
+    if idiag is None:
+        it = fn(A.c, x, _f64(b), tol, max_iter, work, C.byref(res2), C.byref(capped))
+    else:
+        it = fn(A.c, x, _f64(b), _f64(idiag), tol, max_iter, work, C.byref(res2), C.byref(capped))
+    return x, int(it), res2.value, bool(capped.value)
+
+
+def cg_solve(A, x0, b, tol=1e-16, max_iter=-1, idiag=None):
+    """orc_cg_solve / orc_cg_solve_jacobi -> (x, iterations, res2, capped)."""
+    L = lib()
+    return _solve(L.orc_cg_solve if idiag is None else L.orc_cg_solve_jacobi, A, x0, b, tol, max_iter, 4, idiag)
+
+
+def bicgstab_solve(A, x0, b, tol=1e-16, max_iter=-1, idiag=None):
+    """orc_bicgstab_solve / orc_bicgstab_solve_jacobi -> (x, iterations, res2, capped)."""
+    L = lib()
+    return _solve(L.orc_bicgstab_solve if idiag is None else L.orc_bicgstab_solve_jacobi, A, x0, b, tol, max_iter, 8, idiag)
+
+
+def lanczos(A, n, q1):
+    """orc_lanczos -> (T[3,n] as in Fortran T(3,n), Q[nrow,n])."""
+    T = np.empty(3 * n)
+    Q = np.empty(A.nrow * n)
+    w = np.empty(A.nrow)
+    lib().orc_lanczos(A.c, n, _f64(q1), T, Q, w)
+    return T.reshape(n, 3).T.copy(), Q.reshape(n, A.nrow).T.copy()
+
+
+def tridiag_eig(d, e):
+    d = _f64(d).copy()
+    n = d.size
+    ee = np.zeros(n)
+    ee[: n - 1] = e
+    Z = np.empty(n * n)
+    info = lib().orc_tridiag_eig(n, d, ee, Z)
+    return info, d, Z.reshape(n, n).T.copy()
+
+
+def eigensolve(A, n, q1):
+    lam = np.empty(n)
+    V = np.empty(A.nrow * n)
+    info = lib().orc_eigensolve(A.c, n, _f64(q1), lam, V)
+    return info, lam, V.reshape(n, A.nrow).T.copy()
+
+
+def partition_rows(ptr, P):
+    part = np.empty(P + 1, np.int32)
+    lib().orc_partition_rows(ptr.size - 1, _i32(ptr), P, part)
+    return part
+
+
+def halo_build(lo, hi, ptr, node):
+    ptr, node = _i32(ptr), _i32(node)
+    cnt = int(ptr[hi] - ptr[lo])
+    halo = np.empty(max(cnt, 1), np.int32)
+    local = np.empty(max(cnt, 1), np.int32)
+    nh = lib().orc_halo_build(lo, hi, ptr, node, halo, local)
+    return halo[:nh].copy(), local[:cnt].copy()
