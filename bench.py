@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the SpMV + CG hot path.
+
+Workload (BASELINE.json configs[1]): fp64 CG on the 2-D Poisson 5-point CSR
+matrix, 4096 x 4096 grid (n = 16 777 216 rows, nnz = 83 869 696), rhs
+b = A x*, x* ~ U[0,1) PCG64(12345), x0 = 0, row-sharded over N GPUs.
+A "step" is ONE CG iteration (SpMV+dot, x/r update+norm, p update).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--grid 4096]
+
+N > 1 is launched by torchrun (one rank per GPU).  Prints ONE JSON line
+(rank 0).  `value` = CG iterations/s with everything resident in HBM;
+`e2e` = the same through the host-pointer C-ABI call (sigb_solver_solve) with
+pinned host buffers, copies inside the timed region; `roofline` = the dominant
+kernel (CSR SpMV + fused dot) timed live with CUDA events against
+MEASURED_PEAKS.json; `cpu_baseline` = the oracle port on one host core.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "CG iters/sec (and SpMV GB/s, % of HBM roofline), 2D Poisson 16.7M rows"
+UNIT = "iters/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ---------------------------------------------------------------------------
+def cpu_cg_rate(N, iters, warm=1):
+    """Times `iters` CG iterations of the oracle (serial restatement of
+    cg_solve, 1 thread) on the full N x N Poisson matrix.  Returns it/s."""
+    import oracle as orc
+    from sigma_b200 import generators as G
+
+    n = N * N
+    ptr, node, val = G.poisson2d_csr(N)
+    b, _ = G.poisson2d_rhs(N)
+    A = orc.Matrix(orc.CSR, n, n, node, val, ptr=ptr)
+    tol = 1e-10 * float(np.linalg.norm(b))
+    if warm:
+        orc.cg_solve(A, np.zeros(n), b, tol, max_iter=warm)
+    # the init part (1 matvec + setup passes) is timed separately and removed
+    t0 = time.perf_counter()
+    orc.cg_solve(A, np.zeros(n), b, tol, max_iter=0)
+    t_init = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    _, it, _, _ = orc.cg_solve(A, np.zeros(n), b, tol, max_iter=iters)
+    t = time.perf_counter() - t0 - t_init
+    return it / t, it, t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N = args.grid
+    # bounded sample: one full-size iteration costs ~0.3-0.6 s on one core
+    steps = min(args.steps, 60)
+    rate, it, t = cpu_cg_rate(N, steps, warm=min(args.warmup, 2))
+    n = N * N
+    out = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": it, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 / rate, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"2D Poisson 5-point CSR {N}x{N} (n={n}), fp64 CG, x0=0, b=A*rand(seed 12345)"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{it} full-size CG iterations of the serial C restatement of cg_solve "
+                                   f"(gcc -O2 -ffp-contract=off), init pass subtracted; reference is serial Fortran, "
+                                   f"no Fortran compiler in the image; host has {os.cpu_count()} cores"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import sigma_b200 as sb
+    from sigma_b200 import generators as G
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}; launch N>1 with torch.distributed.run")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sb.init(local)
+    stream = torch.cuda.Stream(device=dev)
+    sb.set_stream(stream.cuda_stream)
+
+    N = args.grid
+    n = N * N
+    K, W = args.steps, max(args.warmup, 3)
+    hbm_peak, peak_src = peaks()
+
+    if world > 1:
+        from sigma_b200 import distributed as D
+
+        ctx = D.setup_poisson(N, rank, world, dev)
+        A, nloc, nnz_loc, b_host, nnz_glob = ctx.A, ctx.nloc, ctx.nnz_loc, ctx.b, ctx.nnz_glob
+    else:
+        ptr, node, val = G.poisson2d_csr(N)
+        b_host, _ = G.poisson2d_rhs(N)
+        A = sb.csr_matrix(n, n, ptr, node, val)
+        nloc, nnz_loc, nnz_glob = n, int(node.size), int(node.size)
+        del ptr, node, val
+
+    bnorm2 = float(np.dot(b_host, b_host))
+    if world > 1:
+        t = torch.tensor([bnorm2], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        bnorm2 = float(t.item())
+    tol = 1e-10 * np.sqrt(bnorm2)
+
+    b_pin = torch.from_numpy(b_host).pin_memory()
+    x_pin = torch.zeros(nloc, dtype=torch.float64).pin_memory()
+    with torch.cuda.stream(stream):
+        b_dev = b_pin.to(dev, non_blocking=True)
+        x_dev = torch.zeros(nloc, dtype=torch.float64, device=dev)
+        y_dev = torch.empty(nloc, dtype=torch.float64, device=dev)
+    stream.synchronize()
+
+    solver = sb.cg(tol)
+    solver.setup(A)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    def timed(fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+        e1.synchronize()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- warm-up: W CG iterations + a few SpMVs ---------------------------
+    solver.set_max_iterations(W)
+    with torch.cuda.stream(stream):
+        x_dev.zero_()
+    solver.solve_dev(A, x_dev, b_dev)
+    for _ in range(3):
+        A.matvec_dot_dev(b_dev, y_dev, fetch=False)
+
+    # ---- value: K CG iterations, device-resident --------------------------
+    solver.set_max_iterations(K)
+    solver.setup(A)
+    with torch.cuda.stream(stream):
+        x_dev.zero_()
+    launches0 = sb.launch_count()
+    with ClockSampler(local) as clk:
+        ms_cg = timed(lambda: solver.solve_dev(A, x_dev, b_dev))
+        # dominant kernel, live: CSR SpMV + fused dot (q = A p, p.q)
+        reps = max(20, min(K, 200))
+
+        def spmv_loop():
+            for _ in range(reps):
+                A.matvec_dev(b_dev, y_dev)
+
+        def spmv_dot_loop():
+            for _ in range(reps):
+                A.matvec_dot_dev(b_dev, y_dev, fetch=False)
+
+        ms_spmv = timed(spmv_loop) / reps
+        ms_spmv_dot = timed(spmv_dot_loop) / reps
+    launches = sb.launch_count() - launches0
+    it_done, res2, capped = solver.info()
+    assert it_done == K, (it_done, K)
+    cg_rate = K / (ms_cg * 1e-3)
+
+    # ---- e2e: host buffers through sigb_solver_solve ----------------------
+    solver.setup(A)
+    x_pin.zero_()
+    from sigma_b200._capi import check, lib
+
+    def e2e_call():
+        check(lib().sigb_solver_solve(solver._h, A._h, x_pin.data_ptr(), b_pin.data_ptr(), None))
+
+    barrier()
+    t0 = time.perf_counter()
+    e2e_call()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    t_e2e = max_over_ranks(t_e2e * 1e3) * 1e-3
+    e2e_rate = K / t_e2e
+    res_e2e = float(np.sqrt(solver.info()[1]))
+
+    # ---- roofline of the dominant kernel ----------------------------------
+    # algorithmic bytes of one CSR SpMV: 12 B/entry + 20 B/row + 4;
+    # per rank, max over ranks timing -> use the largest shard
+    bytes_spmv = 12 * nnz_loc + 20 * nloc + 4
+    achieved = bytes_spmv / (ms_spmv_dot * 1e-3) / 1e9
+    bytes_cg_glob = 12 * nnz_glob + 92 * n + 4
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tfile):
+        try:
+            traffic = json.load(open(tfile)).get("csr_stream_kernel_dot_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    out = None
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": cg_rate, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_cg / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"2D Poisson 5-point CSR {N}x{N} (n={n}, nnz={nnz_glob}), fp64 CG, x0=0, "
+                                   f"b=A*rand(seed 12345), tol=1e-10*|b|",
+                       "sharding": f"contiguous row blocks over {world} GPU(s)",
+                       "l2": "inputs larger than L2 (matrix 1.0 GB + 5 vectors of 134 MB per solve)",
+                       "step": "one CG iteration (3 kernels)"},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_rate, "unit": UNIT, "h2d_bytes_per_step": 16 * nloc / K,
+                    "d2h_bytes_per_step": 8 * nloc / K,
+                    "note": f"sigb_solver_solve with pinned host x,b: H2D x0+b, {K} iterations, D2H x; "
+                            f"final |r| = {res_e2e:.3e}"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": traffic,
+                         "kernel": "csr_stream_kernel<MODE_SET,NDOT=1> (q = A p fused with p.q)",
+                         "bytes_per_launch": bytes_spmv, "us_per_launch": ms_spmv_dot * 1e3,
+                         "peak_source": peak_src},
+            "spmv": {"gbs": bytes_spmv / (ms_spmv * 1e-3) / 1e9 * (world if world > 1 else 1),
+                     "per_s": 1e3 / ms_spmv, "us": ms_spmv * 1e3,
+                     "frac_of_measured_hbm": bytes_spmv / (ms_spmv * 1e-3) / 1e9 / hbm_peak,
+                     "frac_of_nominal_8TBs": bytes_spmv / (ms_spmv * 1e-3) / 1e9 / 8000.0},
+            "cg": {"algorithmic_bytes_per_iteration": bytes_cg_glob,
+                   "gbs": bytes_cg_glob * cg_rate / 1e9,
+                   "frac_of_measured_hbm": bytes_cg_glob * cg_rate / 1e9 / (hbm_peak * world),
+                   "final_res_norm": float(np.sqrt(res2)), "capped": bool(capped)},
+        }
+        if world == 1 and not args.no_cpu:
+            rate, it, t = cpu_cg_rate(N, args.cpu_iters)
+            out["cpu_baseline"] = {
+                "value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"{it} full-size CG iterations of the serial C restatement of cg_solve in {t:.1f} s "
+                          f"(init pass subtracted); host has {os.cpu_count()} cores"}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=4096)
+    ap.add_argument("--cpu-iters", type=int, default=30)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,267 @@
+/*
+ * sigma_b200.h -- C-ABI of the B200-native SpMV + Krylov hot path of SiGMA
+ * (danshapero/sigma).
+ *
+ * The reference is Fortran 2003 and has no FFI for this path (its only C
+ * header, include/graphs.h, is dead code that covers graphs alone; SURVEY.md
+ * F4).  The seams this ABI sits behind are therefore the reference's
+ * type-bound procedures; every entry point below names the reference
+ * procedure whose BODY it replaces (file:line relative to the reference
+ * root).  fortran/sigma_b200_shim.f90 holds the iso_c_binding stubs a
+ * maintainer adds.
+ *
+ * Conventions
+ *  - plain C, no C++/torch types; every function returns an int status
+ *    (SIGB_OK = 0).  The reference's error convention is
+ *    `print *, ...; call exit(1)` (e.g. src/solver/cg_solvers.f90:61-65): the
+ *    shim prints sigb_last_error() and exits 1 on a non-zero status.
+ *  - all reals are IEEE fp64 (dp = kind(0.d0), src/types.f90:5); all indices
+ *    are int32 and 1-BASED, passed exactly as the Fortran arrays hold them
+ *    (cs_graph: ptr(n+1), node(ne), src/graph/formats/cs_graphs.f90:16;
+ *    ellpack_graph: node(max_d, n) column-major + degrees(n),
+ *    src/graph/formats/ellpack_graphs.f90:10-20).
+ *  - pointers are HOST pointers unless the function name ends in _dev.
+ *  - not thread-safe, like the reference (solvers are stateful,
+ *    src/solver/cg_solvers.f90:13).  One process drives one GPU; multi-GPU
+ *    runs use one process per GPU joined through a sigb_comm_t.
+ *  - there is no CPU fallback: every compute entry fails with
+ *    SIGB_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef SIGMA_B200_H
+#define SIGMA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIGB_API __attribute__((visibility("default")))
+
+/* ---- status codes ------------------------------------------------------ */
+enum {
+    SIGB_OK            = 0,
+    SIGB_ERR_ARG       = 1,  /* bad argument (null handle, size mismatch ...) */
+    SIGB_ERR_CUDA      = 2,  /* CUDA runtime failure / no usable device       */
+    SIGB_ERR_STATE     = 3,  /* call order (solve before setup ...)           */
+    SIGB_ERR_NONSQUARE = 4,  /* cg_setup/bicgstab_setup/jacobi_setup on a
+                                non-square operator (cg_solvers.f90:61-65)     */
+    SIGB_ERR_ISOLATED  = 5,  /* ELLPACK row with no edge: the reference would
+                                read x(0) (README.md:71-73); rejected here     */
+    SIGB_ERR_COMM      = 6,  /* NCCL / peer-memory failure                    */
+    SIGB_ERR_UNSUPPORTED = 7
+};
+
+/* storage order of a compressed-sparse graph */
+enum { SIGB_ROW = 0 /* csr_matrix */, SIGB_COL = 1 /* csc_matrix */ };
+
+typedef struct sigb_graph_s  *sigb_graph_t;   /* device mirror of cs_graph / ellpack_graph */
+typedef struct sigb_matrix_s *sigb_matrix_t;  /* device mirror of cs_matrix / ellpack_matrix */
+typedef struct sigb_solver_s *sigb_solver_t;  /* cg_solver / bicgstab_solver / jacobi_solver */
+typedef struct sigb_comm_s   *sigb_comm_t;    /* multi-GPU communicator */
+
+/* ---- runtime ----------------------------------------------------------- */
+
+/* Select the CUDA device this process drives and create the library stream.
+ * device < 0: use LOCAL_RANK from the environment, else 0. */
+SIGB_API int sigb_init(int device);
+SIGB_API int sigb_finalize(void);
+/* Message of the last failing call on this thread ("" if none). */
+SIGB_API const char *sigb_last_error(void);
+/* Library version string. */
+SIGB_API const char *sigb_version(void);
+/* Use an existing cudaStream_t for every launch (NULL restores the library's
+ * own stream).  Lets a host time the library's kernels with its own events. */
+SIGB_API int sigb_set_stream(void *cuda_stream);
+SIGB_API int sigb_synchronize(void);
+/* Number of kernels this library has launched since sigb_init (diagnostic). */
+SIGB_API int64_t sigb_launch_count(void);
+
+/* Device buffers (so a C / Fortran host needs no other CUDA binding). */
+SIGB_API int sigb_dev_alloc(int64_t bytes, void **ptr_dev);
+SIGB_API int sigb_dev_free(void *ptr_dev);
+SIGB_API int sigb_copy_h2d(void *dst_dev, const void *src, int64_t bytes);
+SIGB_API int sigb_copy_d2h(void *dst, const void *src_dev, int64_t bytes);
+
+/* ---- graphs (sparsity patterns) ---------------------------------------- */
+
+/* Mirror a cs_graph (src/graph/formats/cs_graphs.f90:11-60).
+ *  n      : g%n  (rows for SIGB_ROW, columns for SIGB_COL)
+ *  m      : g%m
+ *  ptr1   : g%ptr(1:n+1), 1-based;  node1 : g%node(1:ne), 1-based, UNSORTED,
+ *           stored order is preserved on the device.
+ * For SIGB_COL the library also builds, once and on the device, the stable
+ * transpose to CSR (row i's entries in ascending source column), which makes
+ * the CSR kernel accumulate into each y(i) in exactly the order
+ * csc_matvec_add does (src/matrix/formats/cs_matrices.f90:627-647). */
+SIGB_API int sigb_cs_graph_create(int32_t n, int32_t m, const int32_t *ptr1,
+                                  const int32_t *node1, int order,
+                                  sigb_graph_t *g);
+
+/* Mirror an ellpack_graph (src/graph/formats/ellpack_graphs.f90:10-61).
+ *  node_cm : g%node(max_d, n) as stored (slot index fastest), padding slots
+ *            included (copies of the row's last neighbour, :164);
+ *  degrees : g%degrees(n).  Rows with degree 0 -> SIGB_ERR_ISOLATED.
+ * The device copy is re-laid out slot-major (slot k of all rows contiguous). */
+SIGB_API int sigb_ell_graph_create(int32_t n, int32_t m, int32_t max_d,
+                                   const int32_t *node_cm,
+                                   const int32_t *degrees, sigb_graph_t *g);
+
+/* Reference counting like graph_interface add_reference/remove_reference
+ * (src/graph/graph_interfaces.f90:345-363).  create returns refcount 1. */
+SIGB_API int sigb_graph_retain(sigb_graph_t g);
+SIGB_API int sigb_graph_release(sigb_graph_t g);
+
+/* Read back the device-built transpose of a cs graph (index parity checks):
+ * ptr_t1 has (other dimension)+1 entries, node_t1 has ne entries, 1-based.
+ * Either may be NULL.  For SIGB_COL graphs this is the CSR form used by
+ * matvec; for SIGB_ROW graphs it is the form used by matvec_t. */
+SIGB_API int sigb_cs_graph_get_transpose(sigb_graph_t g, int32_t *ptr_t1,
+                                         int32_t *node_t1);
+
+/* ---- matrices ---------------------------------------------------------- */
+
+/* A%set_graph(g): share the pattern, values zero
+ * (cs_matrix_set_graph src/matrix/formats/cs_matrices.f90:259-289,
+ *  ellpack_matrix_set_graph src/matrix/formats/ellpack_matrices.f90:141-164). */
+SIGB_API int sigb_matrix_create(sigb_graph_t g, sigb_matrix_t *A);
+/* Upload / refresh A%val (cs: ne doubles in node order; ellpack:
+ * val(max_d, n) as stored, padding zeros included).  This is what the shim
+ * calls when a host mutator (set_value/add_value/zero/scalar_multiply/...,
+ * cs_matrices.f90:448-490,840-1099) has marked the mirror dirty. */
+SIGB_API int sigb_matrix_set_values(sigb_matrix_t A, const double *val,
+                                    int64_t count);
+SIGB_API int sigb_matrix_destroy(sigb_matrix_t A);
+SIGB_API int sigb_matrix_get_dims(sigb_matrix_t A, int32_t *nrow, int32_t *ncol,
+                                  int64_t *nnz);
+/* Values of the device-built transpose, in sigb_cs_graph_get_transpose order. */
+SIGB_API int sigb_matrix_get_transpose_values(sigb_matrix_t A, double *val_t);
+
+/* ---- matvec ------------------------------------------------------------ */
+
+/* linear_operator%matvec / matvec_t
+ * (src/linear_operator/linear_operator_interface.f90:185-208): y = op(A) x.
+ * trans = 0: A, trans = 1: A^T.  The zero-fill pass is fused away. */
+SIGB_API int sigb_matvec(sigb_matrix_t A, int trans, const double *x, double *y);
+/* matvec_add / matvec_t_add seam: y = y + op(A) x
+ * (csr_matvec_add cs_matrices.f90:600-622, csc_matvec_add :627-647,
+ *  ellpack_matvec_add ellpack_matrices.f90:640-665, _t_add :670-693). */
+SIGB_API int sigb_matvec_add(sigb_matrix_t A, int trans, const double *x,
+                             double *y);
+/* Same with device-resident vectors (add != 0 selects matvec_add). */
+SIGB_API int sigb_matvec_dev(sigb_matrix_t A, int trans, const double *x_dev,
+                             double *y_dev, int add);
+/* Fused y = A x and *dot = x . y (the CG hot pair cg_solvers.f90:134-135),
+ * device vectors, result copied to the host scalar (dot may be NULL: nothing
+ * is copied and the call stays asynchronous). */
+SIGB_API int sigb_matvec_dot_dev(sigb_matrix_t A, const double *x_dev,
+                                 double *y_dev, double *dot);
+
+/* ---- solvers ----------------------------------------------------------- */
+
+/* cg(tolerance) (src/solver/cg_solvers.f90:36-47); tolerance < 0 selects the
+ * reference default 1e-16 (cg_set_params :95-111). */
+SIGB_API int sigb_cg_create(double tolerance, sigb_solver_t *s);
+/* bicgstab(tolerance) (src/solver/bicgstab_solvers.f90:36-47). */
+SIGB_API int sigb_bicgstab_create(double tolerance, sigb_solver_t *s);
+/* jacobi() (src/solver/jacobi_solvers.f90:26-32). */
+SIGB_API int sigb_jacobi_create(sigb_solver_t *s);
+
+/* solver%setup(A): cg_setup cg_solvers.f90:52-90, bicgstab_setup
+ * bicgstab_solvers.f90:52-100 (allocate + zero work vectors, iterations = 0),
+ * jacobi_setup jacobi_solvers.f90:37-63 (idiag(i) = 1 / A(i,i)). */
+SIGB_API int sigb_solver_setup(sigb_solver_t s, sigb_matrix_t A);
+/* set_params (cg_solvers.f90:95-111): tolerance < 0 -> 1e-16. */
+SIGB_API int sigb_solver_set_params(sigb_solver_t s, double tolerance);
+/* NOT in the reference: a safety cap on iterations per solve call (the
+ * reference loops `do while (dsqrt(res2) > tolerance)` with no cap,
+ * cg_solvers.f90:133).  cap < 0 (default) = no cap.  A capped solve still
+ * returns SIGB_OK; query it with sigb_solver_get_info. */
+SIGB_API int sigb_solver_set_max_iterations(sigb_solver_t s, int64_t cap);
+
+/* solver%solve(A, x, b [, pc]): linear_solve / linear_solve_pc
+ * (cg_solve cg_solvers.f90:116-150, cg_solve_pc :155-194, bicgstab_solve
+ * bicgstab_solvers.f90:124-177, bicgstab_solve_pc :182-237, jacobi_solve
+ * jacobi_solvers.f90:68-81).  x is the initial guess on entry and the
+ * solution on return.  pc may be NULL; the only device preconditioner is
+ * jacobi (anything else is SIGB_ERR_UNSUPPORTED).  The whole iteration runs
+ * on the device; the loop stops at the same test as the reference,
+ * evaluated every iteration. */
+SIGB_API int sigb_solver_solve(sigb_solver_t s, sigb_matrix_t A, double *x,
+                               const double *b, sigb_solver_t pc);
+SIGB_API int sigb_solver_solve_dev(sigb_solver_t s, sigb_matrix_t A,
+                                   double *x_dev, const double *b_dev,
+                                   sigb_solver_t pc);
+/* iterations: solver%iterations, accumulated over solve calls since the last
+ * setup (cg_solvers.f90:72,145).  res2: last value of the stopping quantity
+ * squared.  capped: 1 if the last solve hit the safety cap. */
+SIGB_API int sigb_solver_get_info(sigb_solver_t s, int64_t *iterations,
+                                  double *res2, int *capped);
+/* Copy a work vector back (diagnostics / parity): name is one of
+ * "p","q","r","z","r0","v","s","t","idiag". */
+SIGB_API int sigb_solver_get_vector(sigb_solver_t s, const char *name,
+                                    double *out);
+SIGB_API int sigb_solver_destroy(sigb_solver_t s);
+
+/* ---- eigensolver ------------------------------------------------------- */
+
+/* lanczos(A, T, Q) (src/eigensolver.f90:27-90): n = size(T, 2) steps.
+ *  q1 : un-normalised start vector (nrow).  The reference draws it from a
+ *       time-seeded RNG (:47-50); pass NULL to have the library draw one
+ *       from `seed` (splitmix64 -> uniform [-1, 1)), else it is used as is
+ *       and normalised as :51 does.
+ *  T  : T(3, n) column-major;  Q : Q(nrow, n) column-major. */
+SIGB_API int sigb_lanczos(sigb_matrix_t A, int32_t n, const double *q1,
+                          uint64_t seed, double *T, double *Q);
+/* eigensolve(A, lambda, V) (src/eigensolver.f90:160-184): lanczos, symmetric
+ * tridiagonal eigen-solve (stands in for LAPACK dstev, :174), V = V*Q on the
+ * device, sign normalisation (:178-180).  lambda ascending. */
+SIGB_API int sigb_eigensolve(sigb_matrix_t A, int32_t n, const double *q1,
+                             uint64_t seed, double *lambda, double *V);
+
+/* ---- multi-GPU: row-sharded operators ----------------------------------
+ * Not in the reference (serial).  The seam is the block-row loop of
+ * composite_matvec_add (src/matrix/sparse_matrix_composites.f90:1076-1100,
+ * "This loop can be parallelized" :1086).  One process per GPU. */
+
+/* Host-only index work (no GPU needed; bit-exact contract with
+ * oracle/sigma_oracle.c orc_partition_rows / orc_halo_build). */
+SIGB_API int sigb_partition_rows(int32_t n, const int32_t *ptr1, int32_t nparts,
+                                 int32_t *part /* nparts+1, 0-based */);
+/* For rows [lo, hi) (0-based) given that block's own ptr (hi-lo+1 entries,
+ * 1-based, may start above 1) and GLOBAL 1-based column ids:
+ *  halo       : out, sorted unique global columns outside the block
+ *               (capacity = entries in the block); *nhalo its length;
+ *  local_node : out, columns renumbered 1-based into [owned | halo]. */
+SIGB_API int sigb_halo_build(int32_t lo, int32_t hi, const int32_t *ptr_blk1,
+                             const int32_t *node_glob1, int32_t *halo,
+                             int32_t *nhalo, int32_t *local_node);
+
+/* Communicator.  unique_id is SIGB_UNIQUE_ID_BYTES bytes produced by
+ * sigb_comm_unique_id on rank 0 and broadcast by the host (torch.distributed,
+ * MPI, a file ...). */
+#define SIGB_UNIQUE_ID_BYTES 128
+SIGB_API int sigb_comm_unique_id(void *unique_id);
+SIGB_API int sigb_comm_create(const void *unique_id, int rank, int nranks,
+                              sigb_comm_t *comm);
+SIGB_API int sigb_comm_destroy(sigb_comm_t comm);
+SIGB_API int sigb_comm_info(sigb_comm_t comm, int *rank, int *nranks,
+                            int *peer_access);
+
+/* Row block [part[rank], part[rank+1]) of a global n x n CSR matrix.
+ *  ptr_blk1  : the block's slice of the global ptr (nloc+1 entries, 1-based)
+ *  node_glob1: GLOBAL 1-based column ids of the block's entries, stored order
+ * The library derives halo and send lists (graph-derived, exchanged over the
+ * communicator), splits rows into interior / boundary, and mirrors the
+ * renumbered local CSR on the device. */
+SIGB_API int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global,
+                                  const int32_t *part, const int32_t *ptr_blk1,
+                                  const int32_t *node_glob1,
+                                  sigb_matrix_t *A);
+/* Halo / send lists of a distributed matrix (index parity checks). */
+SIGB_API int sigb_dist_get_halo(sigb_matrix_t A, int32_t *nhalo, int32_t *halo);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIGMA_B200_H */

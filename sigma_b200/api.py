@@ -1,0 +1,267 @@
+"""Host-side mirror of the reference's operator / solver interface for the hot
+path, as a thin layer over the C-ABI (include/sigma_b200.h).
+
+Names and call shapes follow the Fortran API so the parity tests read like the
+reference's own test programs:
+
+    reference (Fortran)                              here
+    ----------------------------------------------   -----------------------------------
+    call A%matvec(x, y) / matvec_t / matvec_add      y = A.matvec(x) / A.matvec_t(x) / A.matvec_add(x, y)
+    solver => cg(1.d-16); call solver%setup(A)       solver = cg(1e-16); solver.setup(A)
+    call solver%solve(A, u, f [, pc])                u = solver.solve(A, u, f, pc)
+    pc => jacobi(); call pc%setup(A)                 pc = jacobi(); pc.setup(A)
+    call lanczos(A, T, Q)                            T, Q = lanczos(A, n, q1)
+    call eigensolve(A, lambda, V)                    lam, V = eigensolve(A, n, q1)
+
+(linear_operator_interface.f90:185-233, cg_solvers.f90:36-194,
+bicgstab_solvers.f90:36-237, jacobi_solvers.f90:26-81, eigensolver.f90:27-184.)
+Errors raise SigmaError where the reference prints and calls exit(1).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import ROW, COL, SigmaError, as_f64, as_i32, check, lib, ptr
+
+__all__ = ["init", "Graph", "Matrix", "Solver", "cg", "bicgstab", "jacobi", "lanczos", "eigensolve",
+           "csr_matrix", "csc_matrix", "ellpack_matrix", "SigmaError", "launch_count", "set_stream",
+           "synchronize"]
+
+
+def init(device: int = -1):
+    check(lib().sigb_init(device))
+
+
+def launch_count() -> int:
+    return int(lib().sigb_launch_count())
+
+
+def set_stream(stream_ptr):
+    check(lib().sigb_set_stream(stream_ptr))
+
+
+def synchronize():
+    check(lib().sigb_synchronize())
+
+
+class Graph:
+    """Device mirror of a cs_graph / ellpack_graph (refcounted like the reference)."""
+
+    def __init__(self, handle, kind, n, m):
+        self._h, self.kind, self.n, self.m = handle, kind, n, m
+
+    @classmethod
+    def cs(cls, n, m, ptr1, node1, order=ROW):
+        ptr1, node1 = as_i32(ptr1), as_i32(node1)
+        if ptr1.size != n + 1:
+            raise SigmaError(_capi.ERR_ARG, "ptr must have n+1 entries")
+        h = C.c_void_p()
+        check(lib().sigb_cs_graph_create(n, m, ptr(ptr1), ptr(node1), order, C.byref(h)))
+        return cls(h, "csr" if order == ROW else "csc", n, m)
+
+    @classmethod
+    def ellpack(cls, n, m, node, degrees):
+        """node: (n, max_d) C-order == Fortran node(max_d, n)."""
+        node, degrees = as_i32(node), as_i32(degrees)
+        h = C.c_void_p()
+        check(lib().sigb_ell_graph_create(n, m, node.shape[1], ptr(node), ptr(degrees), C.byref(h)))
+        g = cls(h, "ellpack", n, m)
+        g.max_d = node.shape[1]
+        return g
+
+    def transpose_arrays(self, other_dim, ne):
+        ptr_t = np.empty(other_dim + 1, np.int32)
+        node_t = np.empty(ne, np.int32)
+        check(lib().sigb_cs_graph_get_transpose(self._h, ptr(ptr_t), ptr(node_t)))
+        return ptr_t, node_t
+
+    def release(self):
+        if self._h:
+            check(lib().sigb_graph_release(self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class Matrix:
+    """Device mirror of csr_matrix / csc_matrix / ellpack_matrix (a linear_operator)."""
+
+    def __init__(self, graph: Graph, handle=None):
+        self.g = graph
+        if handle is None:
+            handle = C.c_void_p()
+            check(lib().sigb_matrix_create(graph._h, C.byref(handle)))
+        self._h = handle
+        nrow, ncol, nnz = C.c_int32(), C.c_int32(), C.c_int64()
+        check(lib().sigb_matrix_get_dims(self._h, C.byref(nrow), C.byref(ncol), C.byref(nnz)))
+        self.nrow, self.ncol, self.nnz = nrow.value, ncol.value, nnz.value
+
+    def set_values(self, val):
+        val = as_f64(val)
+        check(lib().sigb_matrix_set_values(self._h, ptr(val), val.size))
+        return self
+
+    # -- linear_operator interface ------------------------------------------
+    def matvec(self, x, trans=False):
+        x = as_f64(x)
+        y = np.empty(self.ncol if trans else self.nrow)
+        check(lib().sigb_matvec(self._h, int(trans), ptr(x), ptr(y)))
+        return y
+
+    def matvec_t(self, x):
+        return self.matvec(x, trans=True)
+
+    def matvec_add(self, x, y, trans=False):
+        x, y = as_f64(x), as_f64(y).copy()
+        check(lib().sigb_matvec_add(self._h, int(trans), ptr(x), ptr(y)))
+        return y
+
+    def matvec_t_add(self, x, y):
+        return self.matvec_add(x, y, trans=True)
+
+    # -- device-resident variants (torch tensors or raw addresses) ----------
+    def matvec_dev(self, x_dev, y_dev, trans=False, add=False):
+        check(lib().sigb_matvec_dev(self._h, int(trans), ptr(x_dev), ptr(y_dev), int(add)))
+
+    def matvec_dot_dev(self, x_dev, y_dev, fetch=True):
+        if not fetch:
+            check(lib().sigb_matvec_dot_dev(self._h, ptr(x_dev), ptr(y_dev), None))
+            return None
+        d = C.c_double()
+        check(lib().sigb_matvec_dot_dev(self._h, ptr(x_dev), ptr(y_dev), C.byref(d)))
+        return d.value
+
+    def transpose_values(self):
+        out = np.empty(self.g_ne_transposed())
+        check(lib().sigb_matrix_get_transpose_values(self._h, ptr(out)))
+        return out
+
+    def g_ne_transposed(self):
+        if self.g.kind == "ellpack":
+            return self.g.n * self.g.max_d
+        return self.nnz
+
+    def destroy(self):
+        if self._h:
+            check(lib().sigb_matrix_destroy(self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def csr_matrix(n, m, ptr1, node1, val):
+    """type(csr_matrix): A%init(n, m); A%set_graph(g); values as stored."""
+    return Matrix(Graph.cs(n, m, ptr1, node1, ROW)).set_values(val)
+
+
+def csc_matrix(nrow, ncol, ptr1, node1, val):
+    """type(csc_matrix): ptr over the ncol columns, node = row ids."""
+    return Matrix(Graph.cs(ncol, nrow, ptr1, node1, COL)).set_values(val)
+
+
+def ellpack_matrix(n, m, node, degrees, val):
+    """type(ellpack_matrix): node/val (n, max_d) C-order == Fortran (max_d, n)."""
+    return Matrix(Graph.ellpack(n, m, node, degrees)).set_values(np.asarray(val).reshape(-1))
+
+
+class Solver:
+    """linear_solver: cg_solver / bicgstab_solver / jacobi_solver."""
+
+    def __init__(self, kind, tolerance=None):
+        h = C.c_void_p()
+        tol = -1.0 if tolerance is None else float(tolerance)
+        if kind == "cg":
+            check(lib().sigb_cg_create(tol, C.byref(h)))
+        elif kind == "bicgstab":
+            check(lib().sigb_bicgstab_create(tol, C.byref(h)))
+        elif kind == "jacobi":
+            check(lib().sigb_jacobi_create(C.byref(h)))
+        else:
+            raise ValueError(kind)
+        self.kind, self._h = kind, h
+
+    def setup(self, A: Matrix):
+        check(lib().sigb_solver_setup(self._h, A._h))
+        self.nn = A.nrow
+        return self
+
+    def set_params(self, tolerance=None):
+        check(lib().sigb_solver_set_params(self._h, -1.0 if tolerance is None else float(tolerance)))
+
+    def set_max_iterations(self, cap: int):
+        check(lib().sigb_solver_set_max_iterations(self._h, int(cap)))
+
+    def solve(self, A: Matrix, x, b, pc: "Solver | None" = None):
+        """call solver%solve(A, x, b [, pc]); x is the initial guess, returns the solution."""
+        x, b = as_f64(x).copy(), as_f64(b)
+        check(lib().sigb_solver_solve(self._h, A._h, ptr(x), ptr(b), pc._h if pc else None))
+        return x
+
+    def solve_dev(self, A: Matrix, x_dev, b_dev, pc: "Solver | None" = None):
+        check(lib().sigb_solver_solve_dev(self._h, A._h, ptr(x_dev), ptr(b_dev), pc._h if pc else None))
+
+    def info(self):
+        it, r2, cp = C.c_int64(), C.c_double(), C.c_int()
+        check(lib().sigb_solver_get_info(self._h, C.byref(it), C.byref(r2), C.byref(cp)))
+        return it.value, r2.value, bool(cp.value)
+
+    @property
+    def iterations(self):
+        return self.info()[0]
+
+    def vector(self, name):
+        out = np.empty(self.nn)
+        check(lib().sigb_solver_get_vector(self._h, name.encode(), ptr(out)))
+        return out
+
+    def destroy(self):
+        if self._h:
+            check(lib().sigb_solver_destroy(self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def cg(tolerance=None):
+    return Solver("cg", tolerance)
+
+
+def bicgstab(tolerance=None):
+    return Solver("bicgstab", tolerance)
+
+
+def jacobi():
+    return Solver("jacobi")
+
+
+def lanczos(A: Matrix, n: int, q1=None, seed: int = 0):
+    """call lanczos(A, T, Q) -> T[3, n] (T(1,:), T(2,:), T(3,:)), Q[nrow, n]."""
+    T = np.empty(3 * n)
+    Q = np.empty(A.nrow * n)
+    q1a = as_f64(q1) if q1 is not None else None
+    check(lib().sigb_lanczos(A._h, n, ptr(q1a), seed, ptr(T), ptr(Q)))
+    return T.reshape(n, 3).T.copy(), Q.reshape(n, A.nrow).T.copy()
+
+
+def eigensolve(A: Matrix, n: int, q1=None, seed: int = 0):
+    """call eigensolve(A, lambda, V) -> lambda[n] ascending, V[nrow, n]."""
+    lam = np.empty(n)
+    V = np.empty(A.nrow * n)
+    q1a = as_f64(q1) if q1 is not None else None
+    check(lib().sigb_eigensolve(A._h, n, ptr(q1a), seed, ptr(lam), ptr(V)))
+    return lam, V.reshape(n, A.nrow).T.copy()

@@ -1,0 +1,755 @@
+// api.cu -- the C-ABI of include/sigma_b200.h: runtime, graph / matrix
+// mirrors, matvec dispatch and the solver / eigensolver entry points.
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "dist.h"
+#include "internal.h"
+#include "solvers.h"
+
+namespace sigb {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    set_error("CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+    return SIGB_ERR_CUDA;
+}
+
+Ctx &ctx()
+{
+    static Ctx c;
+    return c;
+}
+
+int require_init()
+{
+    if (!ctx().inited) return sigb_init(-1);
+    return SIGB_OK;
+}
+
+template <typename T>
+static int dev_alloc(T **p, size_t count)
+{
+    SIGB_CUDA(cudaMalloc((void **)p, sizeof(T) * (count > 0 ? count : 1)));
+    return SIGB_OK;
+}
+
+// upload the tile table of a CSR view
+static int upload_tiles(CsrView &v, const std::vector<int32_t> &tile_row)
+{
+    v.ntiles = (int32_t)tile_row.size() - 1;
+    SIGB_CHECK(dev_alloc(&v.tile_row, tile_row.size()));
+    SIGB_CUDA(cudaMemcpyAsync(v.tile_row, tile_row.data(), sizeof(int32_t) * tile_row.size(),
+                              cudaMemcpyHostToDevice, ctx().stream));
+    SIGB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return SIGB_OK;
+}
+
+static void free_view(CsrView &v)
+{
+    cudaFree(v.ptr);
+    cudaFree(v.node);
+    cudaFree(v.tile_row);
+    cudaFree(v.tiles_interior);
+    cudaFree(v.tiles_boundary);
+    v = CsrView();
+}
+
+// Build the stable transpose of a cs / ell graph on the device (once).
+static int ensure_graph_transposed(sigb_graph_t g)
+{
+    if (g->has_transposed) return SIGB_OK;
+    int32_t *ptr_t = nullptr, *node_t = nullptr, *perm = nullptr;
+    int32_t ntargets;
+    int64_t ne;
+    if (g->kind == G_ELL) {
+        ntargets = g->m;
+        ne = (int64_t)g->n * g->max_d;
+        SIGB_CHECK(device_transpose_ell(g->ell_node, g->n, g->n_pad, g->max_d, ntargets, &ptr_t,
+                                        &node_t, &perm));
+    } else {
+        ntargets = g->m;
+        ne = g->ne;
+        SIGB_CHECK(device_transpose_cs(g->stored.ptr, g->stored.node, g->n, ntargets, ne, &ptr_t,
+                                       &node_t, &perm));
+    }
+    CsrView &t = g->transposed;
+    t.nrows = ntargets;
+    t.ncols = g->n;
+    t.nnz = ne;
+    t.ptr = ptr_t;
+    t.node = node_t;
+    g->perm_t = perm;
+    g->host_ptr_t.resize((size_t)ntargets + 1);
+    SIGB_CUDA(cudaMemcpy(g->host_ptr_t.data(), ptr_t, sizeof(int32_t) * ((size_t)ntargets + 1),
+                         cudaMemcpyDeviceToHost));
+    std::vector<int32_t> tiles;
+    build_tiles_host(g->host_ptr_t.data(), ntargets, tiles);
+    SIGB_CHECK(upload_tiles(t, tiles));
+    g->has_transposed = true;
+    return SIGB_OK;
+}
+
+int ensure_transposed(sigb_matrix_t A)
+{
+    sigb_graph_t g = A->g;
+    SIGB_CHECK(ensure_graph_transposed(g));
+    if (A->val_t_valid) return SIGB_OK;
+    const int64_t ne = g->transposed.nnz;
+    if (!A->val_t) {
+        SIGB_CHECK(dev_alloc(&A->val_t, (size_t)ne + 8));
+        SIGB_CHECK(fill_f64(A->val_t + ne, 8, 0.0));
+    }
+    if (g->kind == G_ELL)
+        SIGB_CHECK(gather_values_ell(A->val, g->perm_t, ne, g->n_pad, g->max_d, A->val_t));
+    else
+        SIGB_CHECK(gather_values(A->val, g->perm_t, ne, A->val_t));
+    A->val_t_valid = true;
+    return SIGB_OK;
+}
+
+// y = op(A) x or y += op(A) x on device vectors, reproducing the reference's
+// accumulation order per format (see SpmvMode).
+int matvec_dev(sigb_matrix_t A, int trans, const double *x, double *y, SpmvMode, bool add,
+               const DotSpec &dot)
+{
+    sigb_graph_t g = A->g;
+    if (A->dist) {
+        SIGB_REQUIRE(!trans, SIGB_ERR_UNSUPPORTED, "matvec_t on a row-sharded operator");
+        return dist_matvec(A, x, y, add, dot, /*x_has_halo=*/false);
+    }
+    if (g->kind == G_ELL) {
+        if (!trans)
+            return launch_ell_spmv(g->n, g->n_pad, g->max_d, g->ell_node, A->val, x, y,
+                                   add ? MODE_ADD_AFTER : MODE_SET, dot);
+        // ellpack_matvec_t_add scatters y(i) += val*z line by line
+        SIGB_CHECK(ensure_transposed(A));
+        return launch_csr_spmv(g->transposed, A->val_t, x, y, add ? MODE_ACC_INIT : MODE_SET, dot);
+    }
+    // line-wise kernel on the stored arrays: csr & !trans, csc & trans
+    const bool stored_is_rowwise = (g->kind == G_CSR) != (trans != 0);
+    if (stored_is_rowwise)
+        return launch_csr_spmv(g->stored, A->val, x, y, add ? MODE_ADD_AFTER : MODE_SET, dot);
+    SIGB_CHECK(ensure_transposed(A));
+    return launch_csr_spmv(g->transposed, A->val_t, x, y, add ? MODE_ACC_INIT : MODE_SET, dot);
+}
+
+int solver_matvec(sigb_matrix_t A, const double *x, double *y, const DotSpec &dot, bool x_has_halo)
+{
+    if (A->dist) return dist_matvec(A, x, y, false, dot, x_has_halo);
+    return matvec_dev(A, 0, x, y, MODE_SET, false, dot);
+}
+
+static int ensure_xb(sigb_solver_t s, int64_t len)
+{
+    if (s->xb_len >= len) return SIGB_OK;
+    cudaFree(s->xb);
+    s->xb = nullptr;
+    SIGB_CHECK(dev_alloc(&s->xb, (size_t)len));
+    s->xb_len = len;
+    return SIGB_OK;
+}
+
+}  // namespace sigb
+
+using namespace sigb;
+
+// ===========================================================================
+// runtime
+// ===========================================================================
+extern "C" {
+
+const char *sigb_last_error(void) { return g_err; }
+const char *sigb_version(void) { return "sigma_b200 0.1 (sm_100a)"; }
+
+int sigb_init(int device)
+{
+    Ctx &c = ctx();
+    if (c.inited) return SIGB_OK;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("sigb_init: no CUDA device is usable (%s); this library has no CPU path",
+                  cudaGetErrorString(e));
+        return SIGB_ERR_CUDA;
+    }
+    if (device < 0) {
+        const char *lr = getenv("LOCAL_RANK");
+        device = lr ? atoi(lr) % count : 0;
+    }
+    SIGB_REQUIRE(device < count, SIGB_ERR_ARG, "sigb_init: device %d of %d", device, count);
+    SIGB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SIGB_CUDA(cudaGetDeviceProperties(&prop, device));
+    SIGB_REQUIRE(prop.major >= 10, SIGB_ERR_CUDA,
+                 "sigb_init: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                 prop.major, prop.minor);
+    c.device = device;
+    c.num_sms = prop.multiProcessorCount;
+    SIGB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+    SIGB_CUDA(cudaStreamCreateWithFlags(&c.aux_stream, cudaStreamNonBlocking));
+    c.stream = c.own_stream;
+    SIGB_CUDA(cudaMalloc(&c.partials, sizeof(double) * kMaxGrid * kMaxDots * kNumTickets));
+    SIGB_CUDA(cudaMalloc(&c.tickets, sizeof(unsigned) * kNumTickets));
+    SIGB_CUDA(cudaMemset(c.tickets, 0, sizeof(unsigned) * kNumTickets));
+    c.pinned_bytes = 1 << 16;
+    SIGB_CUDA(cudaMallocHost(&c.pinned, c.pinned_bytes));
+    c.launches = 0;
+    c.inited = true;
+    return SIGB_OK;
+}
+
+int sigb_finalize(void)
+{
+    Ctx &c = ctx();
+    if (!c.inited) return SIGB_OK;
+    cudaDeviceSynchronize();
+    cudaFree(c.partials);
+    cudaFree(c.tickets);
+    cudaFreeHost(c.pinned);
+    cudaStreamDestroy(c.own_stream);
+    cudaStreamDestroy(c.aux_stream);
+    c = Ctx();
+    return SIGB_OK;
+}
+
+int sigb_set_stream(void *cuda_stream)
+{
+    SIGB_CHECK(require_init());
+    ctx().stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx().own_stream;
+    return SIGB_OK;
+}
+
+int sigb_synchronize(void)
+{
+    SIGB_CHECK(require_init());
+    SIGB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return SIGB_OK;
+}
+
+int64_t sigb_launch_count(void) { return ctx().launches; }
+
+int sigb_dev_alloc(int64_t bytes, void **ptr_dev)
+{
+    SIGB_CHECK(require_init());
+    SIGB_REQUIRE(ptr_dev && bytes >= 0, SIGB_ERR_ARG, "sigb_dev_alloc: bad argument");
+    SIGB_CUDA(cudaMalloc(ptr_dev, (size_t)(bytes > 0 ? bytes : 1)));
+    return SIGB_OK;
+}
+
+int sigb_dev_free(void *ptr_dev)
+{
+    SIGB_CUDA(cudaFree(ptr_dev));
+    return SIGB_OK;
+}
+
+int sigb_copy_h2d(void *dst_dev, const void *src, int64_t bytes)
+{
+    SIGB_CHECK(require_init());
+    SIGB_CUDA(cudaMemcpyAsync(dst_dev, src, (size_t)bytes, cudaMemcpyHostToDevice, ctx().stream));
+    SIGB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return SIGB_OK;
+}
+
+int sigb_copy_d2h(void *dst, const void *src_dev, int64_t bytes)
+{
+    SIGB_CHECK(require_init());
+    SIGB_CUDA(cudaMemcpyAsync(dst, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, ctx().stream));
+    SIGB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return SIGB_OK;
+}
+
+// ===========================================================================
+// graphs
+// ===========================================================================
+
+int sigb_cs_graph_create(int32_t n, int32_t m, const int32_t *ptr1, const int32_t *node1, int order,
+                         sigb_graph_t *out)
+{
+    SIGB_CHECK(require_init());
+    SIGB_REQUIRE(out && ptr1 && n >= 0 && m >= 0, SIGB_ERR_ARG, "sigb_cs_graph_create: bad argument");
+    SIGB_REQUIRE(order == SIGB_ROW || order == SIGB_COL, SIGB_ERR_ARG,
+                 "sigb_cs_graph_create: order must be SIGB_ROW or SIGB_COL");
+    SIGB_REQUIRE(ptr1[0] == 1, SIGB_ERR_ARG, "sigb_cs_graph_create: ptr must be 1-based (ptr(1) = %d)",
+                 ptr1[0]);
+    const int64_t ne = (int64_t)ptr1[n] - 1;
+    SIGB_REQUIRE(ne >= 0 && (ne == 0 || node1), SIGB_ERR_ARG, "sigb_cs_graph_create: bad ptr/node");
+    int32_t max_d = 0;
+    for (int32_t i = 0; i < n; i++) {
+        const int32_t d = ptr1[i + 1] - ptr1[i];
+        SIGB_REQUIRE(d >= 0, SIGB_ERR_ARG, "sigb_cs_graph_create: ptr not monotone at line %d", i + 1);
+        max_d = std::max(max_d, d);
+    }
+    for (int64_t k = 0; k < ne; k++)
+        SIGB_REQUIRE(node1[k] >= 1 && node1[k] <= m, SIGB_ERR_ARG,
+                     "sigb_cs_graph_create: node(%lld) = %d outside 1..%d", (long long)k + 1,
+                     node1[k], m);
+
+    sigb_graph_t g = new sigb_graph_s();
+    g->kind = (order == SIGB_ROW) ? G_CSR : G_CSC;
+    g->n = n;
+    g->m = m;
+    g->ne = ne;
+    g->max_d = max_d;
+    CsrView &v = g->stored;
+    v.nrows = n;
+    v.ncols = m;
+    v.nnz = ne;
+    cudaStream_t st = ctx().stream;
+    SIGB_CHECK(dev_alloc(&v.ptr, (size_t)n + 1));
+    SIGB_CHECK(dev_alloc(&v.node, (size_t)ne + 8));
+    SIGB_CUDA(cudaMemcpyAsync(v.ptr, ptr1, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+    if (ne > 0)
+        SIGB_CUDA(cudaMemcpyAsync(v.node, node1, sizeof(int32_t) * (size_t)ne, cudaMemcpyHostToDevice, st));
+    SIGB_CHECK(fill_i32(v.node + ne, 8, 1));
+    std::vector<int32_t> tiles;
+    build_tiles_host(ptr1, n, tiles);
+    SIGB_CHECK(upload_tiles(v, tiles));
+    if (g->kind == G_CSC) SIGB_CHECK(ensure_graph_transposed(g));
+    *out = g;
+    return SIGB_OK;
+}
+
+int sigb_ell_graph_create(int32_t n, int32_t m, int32_t max_d, const int32_t *node_cm,
+                          const int32_t *degrees, sigb_graph_t *out)
+{
+    SIGB_CHECK(require_init());
+    SIGB_REQUIRE(out && node_cm && degrees && n >= 0 && m >= 0 && max_d >= 1, SIGB_ERR_ARG,
+                 "sigb_ell_graph_create: bad argument");
+    int64_t ne = 0;
+    for (int32_t i = 0; i < n; i++) {
+        SIGB_REQUIRE(degrees[i] >= 1, SIGB_ERR_ISOLATED,
+                     "sigb_ell_graph_create: row %d has no edge; the reference would read x(0) "
+                     "(README.md:71-73)", i + 1);
+        SIGB_REQUIRE(degrees[i] <= max_d, SIGB_ERR_ARG, "sigb_ell_graph_create: degrees(%d) > max_d", i + 1);
+        ne += degrees[i];
+        for (int32_t k = 0; k < max_d; k++) {
+            const int32_t c = node_cm[(size_t)i * max_d + k];
+            SIGB_REQUIRE(c >= 1 && c <= m, SIGB_ERR_ARG,
+                         "sigb_ell_graph_create: node(%d,%d) = %d outside 1..%d", k + 1, i + 1, c, m);
+        }
+    }
+    sigb_graph_t g = new sigb_graph_s();
+    g->kind = G_ELL;
+    g->n = n;
+    g->m = m;
+    g->ne = ne;
+    g->max_d = max_d;
+    g->n_pad = (n + 63) & ~63;
+    cudaStream_t st = ctx().stream;
+    int32_t *tmp = nullptr;
+    SIGB_CHECK(dev_alloc(&tmp, (size_t)n * max_d));
+    SIGB_CUDA(cudaMemcpyAsync(tmp, node_cm, sizeof(int32_t) * (size_t)n * max_d, cudaMemcpyHostToDevice, st));
+    SIGB_CHECK(dev_alloc(&g->ell_node, (size_t)g->n_pad * max_d));
+    SIGB_CHECK(ell_relayout_node(tmp, n, g->n_pad, max_d, g->ell_node));
+    SIGB_CHECK(dev_alloc(&g->ell_degrees, (size_t)n));
+    SIGB_CUDA(cudaMemcpyAsync(g->ell_degrees, degrees, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    SIGB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(tmp);
+    *out = g;
+    return SIGB_OK;
+}
+
+int sigb_graph_retain(sigb_graph_t g)
+{
+    SIGB_REQUIRE(g, SIGB_ERR_ARG, "sigb_graph_retain: null graph");
+    g->refcount++;
+    return SIGB_OK;
+}
+
+int sigb_graph_release(sigb_graph_t g)
+{
+    SIGB_REQUIRE(g, SIGB_ERR_ARG, "sigb_graph_release: null graph");
+    if (--g->refcount > 0) return SIGB_OK;
+    free_view(g->stored);
+    free_view(g->transposed);
+    cudaFree(g->perm_t);
+    cudaFree(g->ell_node);
+    cudaFree(g->ell_degrees);
+    delete g;
+    return SIGB_OK;
+}
+
+int sigb_cs_graph_get_transpose(sigb_graph_t g, int32_t *ptr_t1, int32_t *node_t1)
+{
+    SIGB_REQUIRE(g, SIGB_ERR_ARG, "sigb_cs_graph_get_transpose: null graph");
+    SIGB_CHECK(ensure_graph_transposed(g));
+    const CsrView &t = g->transposed;
+    if (ptr_t1)
+        SIGB_CUDA(cudaMemcpy(ptr_t1, t.ptr, sizeof(int32_t) * ((size_t)t.nrows + 1), cudaMemcpyDeviceToHost));
+    if (node_t1 && t.nnz > 0)
+        SIGB_CUDA(cudaMemcpy(node_t1, t.node, sizeof(int32_t) * (size_t)t.nnz, cudaMemcpyDeviceToHost));
+    return SIGB_OK;
+}
+
+// ===========================================================================
+// matrices
+// ===========================================================================
+
+int sigb_matrix_create(sigb_graph_t g, sigb_matrix_t *out)
+{
+    SIGB_CHECK(require_init());
+    SIGB_REQUIRE(g && out, SIGB_ERR_ARG, "sigb_matrix_create: bad argument");
+    sigb_matrix_t A = new sigb_matrix_s();
+    A->g = g;
+    g->refcount++;
+    if (g->kind == G_CSC) { A->nrow = g->m; A->ncol = g->n; }
+    else { A->nrow = g->n; A->ncol = g->m; }
+    const size_t len = (g->kind == G_ELL) ? (size_t)g->n_pad * g->max_d : (size_t)g->ne + 8;
+    SIGB_CHECK(dev_alloc(&A->val, len));
+    SIGB_CUDA(cudaMemsetAsync(A->val, 0, sizeof(double) * len, ctx().stream));  // A%val = 0
+    *out = A;
+    return SIGB_OK;
+}
+
+int sigb_matrix_set_values(sigb_matrix_t A, const double *val, int64_t count)
+{
+    SIGB_REQUIRE(A && val, SIGB_ERR_ARG, "sigb_matrix_set_values: bad argument");
+    sigb_graph_t g = A->g;
+    cudaStream_t st = ctx().stream;
+    if (g->kind == G_ELL) {
+        const int64_t want = (int64_t)g->n * g->max_d;
+        SIGB_REQUIRE(count == want, SIGB_ERR_ARG, "sigb_matrix_set_values: got %lld values, val(max_d,n) has %lld",
+                     (long long)count, (long long)want);
+        double *tmp = nullptr;
+        SIGB_CHECK(dev_alloc(&tmp, (size_t)want));
+        SIGB_CUDA(cudaMemcpyAsync(tmp, val, sizeof(double) * (size_t)want, cudaMemcpyHostToDevice, st));
+        SIGB_CHECK(ell_relayout_val(tmp, g->n, g->n_pad, g->max_d, A->val));
+        SIGB_CUDA(cudaStreamSynchronize(st));
+        cudaFree(tmp);
+    } else {
+        SIGB_REQUIRE(count == g->ne, SIGB_ERR_ARG, "sigb_matrix_set_values: got %lld values, graph has %lld edges",
+                     (long long)count, (long long)g->ne);
+        if (count > 0)
+            SIGB_CUDA(cudaMemcpyAsync(A->val, val, sizeof(double) * (size_t)count, cudaMemcpyHostToDevice, st));
+        SIGB_CUDA(cudaStreamSynchronize(st));
+    }
+    A->val_t_valid = false;
+    if (g->kind == G_CSC) SIGB_CHECK(ensure_transposed(A));
+    return SIGB_OK;
+}
+
+int sigb_matrix_destroy(sigb_matrix_t A)
+{
+    if (!A) return SIGB_OK;
+    cudaFree(A->val);
+    cudaFree(A->val_t);
+    if (A->dist) dist_destroy(A);
+    sigb_graph_release(A->g);
+    delete A;
+    return SIGB_OK;
+}
+
+int sigb_matrix_get_dims(sigb_matrix_t A, int32_t *nrow, int32_t *ncol, int64_t *nnz)
+{
+    SIGB_REQUIRE(A, SIGB_ERR_ARG, "sigb_matrix_get_dims: null matrix");
+    if (nrow) *nrow = A->nrow;
+    if (ncol) *ncol = A->ncol;
+    if (nnz) *nnz = A->g->ne;
+    return SIGB_OK;
+}
+
+int sigb_matrix_get_transpose_values(sigb_matrix_t A, double *val_t)
+{
+    SIGB_REQUIRE(A && val_t, SIGB_ERR_ARG, "sigb_matrix_get_transpose_values: bad argument");
+    SIGB_CHECK(ensure_transposed(A));
+    SIGB_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (A->g->transposed.nnz > 0)
+        SIGB_CUDA(cudaMemcpy(val_t, A->val_t, sizeof(double) * (size_t)A->g->transposed.nnz, cudaMemcpyDeviceToHost));
+    return SIGB_OK;
+}
+
+// ===========================================================================
+// matvec
+// ===========================================================================
+
+static int host_matvec(sigb_matrix_t A, int trans, const double *x, double *y, bool add)
+{
+    SIGB_REQUIRE(A && x && y, SIGB_ERR_ARG, "sigb_matvec: bad argument");
+    const int64_t nx = trans ? A->nrow : A->ncol, ny = trans ? A->ncol : A->nrow;
+    cudaStream_t st = ctx().stream;
+    double *xd = nullptr, *yd = nullptr;
+    SIGB_CHECK(dev_alloc(&xd, (size_t)nx));
+    SIGB_CHECK(dev_alloc(&yd, (size_t)ny));
+    SIGB_CUDA(cudaMemcpyAsync(xd, x, sizeof(double) * (size_t)nx, cudaMemcpyHostToDevice, st));
+    if (add) SIGB_CUDA(cudaMemcpyAsync(yd, y, sizeof(double) * (size_t)ny, cudaMemcpyHostToDevice, st));
+    DotSpec none;
+    int rc = matvec_dev(A, trans, xd, yd, MODE_SET, add, none);
+    if (rc == SIGB_OK) {
+        cudaError_t e = cudaMemcpyAsync(y, yd, sizeof(double) * (size_t)ny, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "matvec copy-back", __FILE__, __LINE__);
+    }
+    cudaFree(xd);
+    cudaFree(yd);
+    return rc;
+}
+
+int sigb_matvec(sigb_matrix_t A, int trans, const double *x, double *y)
+{
+    return host_matvec(A, trans, x, y, false);
+}
+
+int sigb_matvec_add(sigb_matrix_t A, int trans, const double *x, double *y)
+{
+    return host_matvec(A, trans, x, y, true);
+}
+
+int sigb_matvec_dev(sigb_matrix_t A, int trans, const double *x_dev, double *y_dev, int add)
+{
+    SIGB_REQUIRE(A && x_dev && y_dev, SIGB_ERR_ARG, "sigb_matvec_dev: bad argument");
+    DotSpec none;
+    return matvec_dev(A, trans, x_dev, y_dev, MODE_SET, add != 0, none);
+}
+
+int sigb_matvec_dot_dev(sigb_matrix_t A, const double *x_dev, double *y_dev, double *dot)
+{
+    SIGB_REQUIRE(A && x_dev && y_dev, SIGB_ERR_ARG, "sigb_matvec_dot_dev: bad argument");
+    SIGB_REQUIRE(A->nrow == A->ncol, SIGB_ERR_NONSQUARE, "sigb_matvec_dot_dev: operator is not square");
+    double *slot = ctx().partials + (size_t)kMaxGrid * kMaxDots * (kNumTickets - 1);
+    DotSpec d;
+    d.ndot = 1;
+    d.u = x_dev;
+    d.out[0] = slot;
+    SIGB_CHECK(solver_matvec(A, x_dev, y_dev, d, false));
+    SIGB_CHECK(dist_allreduce(A, slot, 1));
+    if (dot) {  // dot == NULL: leave everything asynchronous (timing loops)
+        SIGB_CUDA(cudaMemcpyAsync(dot, slot, sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+        SIGB_CUDA(cudaStreamSynchronize(ctx().stream));
+    }
+    return SIGB_OK;
+}
+
+// ===========================================================================
+// solvers
+// ===========================================================================
+
+static int make_solver(int kind, double tol, sigb_solver_t *out)
+{
+    SIGB_CHECK(require_init());
+    SIGB_REQUIRE(out, SIGB_ERR_ARG, "solver create: null output");
+    sigb_solver_t s = new sigb_solver_s();
+    s->kind = kind;
+    s->tol = (tol < 0.0) ? 1e-16 : tol;
+    s->params_set = true;
+    *out = s;
+    return SIGB_OK;
+}
+
+int sigb_cg_create(double tolerance, sigb_solver_t *s) { return make_solver(S_CG, tolerance, s); }
+int sigb_bicgstab_create(double tolerance, sigb_solver_t *s) { return make_solver(S_BICGSTAB, tolerance, s); }
+int sigb_jacobi_create(sigb_solver_t *s) { return make_solver(S_JACOBI, -1.0, s); }
+
+int sigb_solver_set_params(sigb_solver_t s, double tolerance)
+{
+    SIGB_REQUIRE(s, SIGB_ERR_ARG, "sigb_solver_set_params: null solver");
+    s->tol = (tolerance < 0.0) ? 1e-16 : tolerance;
+    s->params_set = true;
+    return SIGB_OK;
+}
+
+int sigb_solver_set_max_iterations(sigb_solver_t s, int64_t cap)
+{
+    SIGB_REQUIRE(s, SIGB_ERR_ARG, "sigb_solver_set_max_iterations: null solver");
+    s->cap = cap;
+    return SIGB_OK;
+}
+
+int sigb_solver_setup(sigb_solver_t s, sigb_matrix_t A)
+{
+    SIGB_REQUIRE(s && A, SIGB_ERR_ARG, "sigb_solver_setup: bad argument");
+    const int64_t nglob_rows = A->dist ? dist_global_n(A) : A->nrow;
+    const int64_t nglob_cols = A->dist ? dist_global_n(A) : A->ncol;
+    if (nglob_rows != nglob_cols) {
+        const char *what = s->kind == S_CG ? "CG" : (s->kind == S_BICGSTAB ? "BiCG-Stab" : "Jacobi");
+        set_error("Cannot make a %s solver for a non-square matrix", what);
+        return SIGB_ERR_NONSQUARE;
+    }
+    const int nwork = s->kind == S_CG ? 4 : (s->kind == S_BICGSTAB ? 8 : 1);
+    const int64_t nvec = (int64_t)A->nrow + dist_halo_len(A);
+    if (s->initialized && (s->nvec != nvec || s->nwork != nwork)) {
+        cudaFree(s->work);
+        s->work = nullptr;
+        s->initialized = false;
+    }
+    s->nn = A->nrow;
+    s->nvec = nvec;
+    s->nwork = nwork;
+    s->iterations = 0;
+    s->A = A;
+    if (!s->initialized) {
+        SIGB_CHECK(dev_alloc(&s->work, (size_t)nvec * nwork));
+        if (!s->state) {
+            SIGB_CUDA(cudaMalloc((void **)&s->state, kstate_bytes()));
+            SIGB_CUDA(cudaMallocHost((void **)&s->state_host, kstate_bytes()));
+        }
+        s->initialized = true;
+    }
+    if (s->kind == S_JACOBI) return jacobi_setup_dev(s, A);
+    SIGB_CUDA(cudaMemsetAsync(s->work, 0, sizeof(double) * (size_t)nvec * nwork, ctx().stream));
+    return SIGB_OK;
+}
+
+int sigb_solver_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x_dev, const double *b_dev,
+                          sigb_solver_t pc)
+{
+    SIGB_REQUIRE(s && A && x_dev && b_dev, SIGB_ERR_ARG, "sigb_solver_solve: bad argument");
+    SIGB_REQUIRE(s->initialized, SIGB_ERR_STATE, "sigb_solver_solve: solver%%setup(A) has not been called");
+    SIGB_REQUIRE(s->nn == A->nrow, SIGB_ERR_ARG, "sigb_solver_solve: solver was set up for nn = %d, operator has %d rows",
+                 s->nn, A->nrow);
+    if (pc) {
+        SIGB_REQUIRE(pc->kind == S_JACOBI, SIGB_ERR_UNSUPPORTED,
+                     "sigb_solver_solve: the only device preconditioner is jacobi");
+        SIGB_REQUIRE(pc->initialized && pc->nn == s->nn, SIGB_ERR_STATE,
+                     "sigb_solver_solve: pc%%setup(A) has not been called");
+    }
+    switch (s->kind) {
+    case S_CG: return cg_solve_dev(s, A, x_dev, b_dev, pc);
+    case S_BICGSTAB: return bicgstab_solve_dev(s, A, x_dev, b_dev, pc);
+    default:
+        // jacobi has no linear_solve_pc override: the default ignores pc
+        // (linear_operator_interface.f90:238-254)
+        return jacobi_apply_dev(s, x_dev, b_dev);
+    }
+}
+
+int sigb_solver_solve(sigb_solver_t s, sigb_matrix_t A, double *x, const double *b, sigb_solver_t pc)
+{
+    SIGB_REQUIRE(s && A && x && b, SIGB_ERR_ARG, "sigb_solver_solve: bad argument");
+    SIGB_REQUIRE(s->initialized, SIGB_ERR_STATE, "sigb_solver_solve: solver%%setup(A) has not been called");
+    const int64_t n = s->nn;
+    SIGB_CHECK(ensure_xb(s, 2 * n));
+    cudaStream_t st = ctx().stream;
+    double *xd = s->xb, *bd = s->xb + n;
+    SIGB_CUDA(cudaMemcpyAsync(xd, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+    SIGB_CUDA(cudaMemcpyAsync(bd, b, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+    SIGB_CHECK(sigb_solver_solve_dev(s, A, xd, bd, pc));
+    SIGB_CUDA(cudaMemcpyAsync(x, xd, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    SIGB_CUDA(cudaStreamSynchronize(st));
+    return SIGB_OK;
+}
+
+int sigb_solver_get_info(sigb_solver_t s, int64_t *iterations, double *res2, int *capped)
+{
+    SIGB_REQUIRE(s, SIGB_ERR_ARG, "sigb_solver_get_info: null solver");
+    if (iterations) *iterations = s->iterations;
+    if (res2) *res2 = s->res2;
+    if (capped) *capped = s->capped;
+    return SIGB_OK;
+}
+
+int sigb_solver_get_vector(sigb_solver_t s, const char *name, double *out)
+{
+    SIGB_REQUIRE(s && name && out && s->initialized, SIGB_ERR_ARG, "sigb_solver_get_vector: bad argument");
+    static const char *cg_names[] = {"p", "q", "r", "z"};
+    static const char *bi_names[] = {"p", "q", "r", "r0", "v", "s", "t", "z"};
+    int idx = -1;
+    if (s->kind == S_JACOBI && !strcmp(name, "idiag")) idx = 0;
+    if (s->kind == S_CG)
+        for (int k = 0; k < 4; k++) if (!strcmp(name, cg_names[k])) idx = k;
+    if (s->kind == S_BICGSTAB)
+        for (int k = 0; k < 8; k++) if (!strcmp(name, bi_names[k])) idx = k;
+    SIGB_REQUIRE(idx >= 0, SIGB_ERR_ARG, "sigb_solver_get_vector: no work vector '%s'", name);
+    SIGB_CUDA(cudaStreamSynchronize(ctx().stream));
+    SIGB_CUDA(cudaMemcpy(out, s->work + (size_t)idx * s->nvec, sizeof(double) * (size_t)s->nn, cudaMemcpyDeviceToHost));
+    return SIGB_OK;
+}
+
+int sigb_solver_destroy(sigb_solver_t s)
+{
+    if (!s) return SIGB_OK;
+    cudaFree(s->work);
+    cudaFree(s->state);
+    cudaFreeHost(s->state_host);
+    cudaFree(s->xb);
+    delete s;
+    return SIGB_OK;
+}
+
+// ===========================================================================
+// eigensolver
+// ===========================================================================
+
+static int lanczos_common(sigb_matrix_t A, int32_t n, const double *q1, uint64_t seed, double *T,
+                          double *Q, double *lambda, bool ritz)
+{
+    SIGB_REQUIRE(A && n >= 1, SIGB_ERR_ARG, "lanczos: bad argument");
+    const int64_t nglob = A->dist ? dist_global_n(A) : A->ncol;
+    SIGB_REQUIRE((A->dist ? dist_global_n(A) : A->nrow) == nglob, SIGB_ERR_NONSQUARE, "lanczos: operator is not square");
+    const int64_t nr = A->nrow;
+    cudaStream_t st = ctx().stream;
+    double *Qd = nullptr, *Td = nullptr, *w = nullptr, *q1d = nullptr, *V2 = nullptr, *small = nullptr;
+    void *kst = nullptr;
+    int rc = SIGB_OK;
+    auto cleanup = [&]() {
+        cudaFree(Qd); cudaFree(Td); cudaFree(w); cudaFree(q1d); cudaFree(V2); cudaFree(small); cudaFree(kst);
+    };
+#define LZ_TRY(expr) do { rc = (expr); if (rc != SIGB_OK) { cleanup(); return rc; } } while (0)
+#define LZ_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cleanup(); return cuda_fail(e_, #expr, __FILE__, __LINE__); } } while (0)
+    LZ_TRY(dev_alloc(&Qd, (size_t)nr * n));
+    LZ_TRY(dev_alloc(&Td, (size_t)3 * n));
+    LZ_TRY(dev_alloc(&w, (size_t)nr));
+    LZ_CUDA(cudaMalloc(&kst, kstate_bytes()));
+    LZ_CUDA(cudaMemsetAsync(kst, 0, kstate_bytes(), st));
+    if (q1) {
+        LZ_TRY(dev_alloc(&q1d, (size_t)nr));
+        LZ_CUDA(cudaMemcpyAsync(q1d, q1, sizeof(double) * (size_t)nr, cudaMemcpyHostToDevice, st));
+    }
+    LZ_TRY(lanczos_dev(A, n, q1d, seed, A->dist ? dist_row_offset(A) : 0, Td, Qd, w, (KState *)kst));
+    std::vector<double> Th((size_t)3 * n);
+    LZ_CUDA(cudaMemcpyAsync(Th.data(), Td, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    LZ_CUDA(cudaStreamSynchronize(st));
+    if (T) memcpy(T, Th.data(), sizeof(double) * 3 * (size_t)n);
+    if (ritz) {
+        std::vector<double> d(n), e(n), Z((size_t)n * n);
+        for (int i = 0; i < n; i++) d[i] = Th[3 * (size_t)i + 1];
+        for (int i = 0; i < n - 1; i++) e[i] = Th[3 * (size_t)i + 2];
+        const int info = tridiag_eig_host(n, d.data(), e.data(), Z.data());
+        if (info != 0) {
+            cleanup();
+            set_error("eigensolve: tridiagonal QL did not converge");
+            return SIGB_ERR_STATE;
+        }
+        LZ_TRY(dev_alloc(&V2, (size_t)nr * n));
+        LZ_TRY(dev_alloc(&small, (size_t)n * n + n));
+        LZ_CUDA(cudaMemcpyAsync(small, Z.data(), sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, st));
+        LZ_TRY(ritz_vectors_dev(Qd, V2, small, nr, n, small + (size_t)n * n));
+        if (lambda) memcpy(lambda, d.data(), sizeof(double) * (size_t)n);
+    }
+    if (Q) LZ_CUDA(cudaMemcpyAsync(Q, Qd, sizeof(double) * (size_t)nr * n, cudaMemcpyDeviceToHost, st));
+    LZ_CUDA(cudaStreamSynchronize(st));
+    cleanup();
+#undef LZ_TRY
+#undef LZ_CUDA
+    return SIGB_OK;
+}
+
+int sigb_lanczos(sigb_matrix_t A, int32_t n, const double *q1, uint64_t seed, double *T, double *Q)
+{
+    SIGB_REQUIRE(T && Q, SIGB_ERR_ARG, "sigb_lanczos: T and Q are required");
+    return lanczos_common(A, n, q1, seed, T, Q, nullptr, false);
+}
+
+int sigb_eigensolve(sigb_matrix_t A, int32_t n, const double *q1, uint64_t seed, double *lambda, double *V)
+{
+    SIGB_REQUIRE(lambda && V, SIGB_ERR_ARG, "sigb_eigensolve: lambda and V are required");
+    SIGB_REQUIRE(!(A && A->dist), SIGB_ERR_UNSUPPORTED, "sigb_eigensolve on a row-sharded operator");
+    return lanczos_common(A, n, q1, seed, nullptr, V, lambda, true);
+}
+
+}  // extern "C"

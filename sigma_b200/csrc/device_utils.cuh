@@ -1,0 +1,130 @@
+// device_utils.cuh -- device helpers shared by the sm_100a kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "internal.h"
+
+namespace sigb {
+
+// The reference is compiled without FMA contraction (default gfortran on
+// x86-64): a*b is rounded, then added.  Every floating-point statement of the
+// hot path is written with these two so nvcc can never contract them.
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+
+// Streaming (read-once) 128-bit loads: keep the matrix arrays out of L1 so the
+// gathered x lines stay resident.
+__device__ __forceinline__ int4 ld_stream_i4(const int32_t *p)
+{
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ int2 ld_stream_i2(const int32_t *p)
+{
+    int2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];"
+                 : "=r"(r.x), "=r"(r.y)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double2 ld_stream_d2(const double *p)
+{
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+                 : "=d"(r.x), "=d"(r.y)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double ld_stream_d(const double *p)
+{
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+
+// ---------------------------------------------------------------------------
+// Deterministic grid reduction.
+//
+// Each thread brings ND partial sums.  They are combined with a fixed shuffle
+// tree inside the warp, a fixed order across the CTA's warps, and the CTA
+// partial is parked in `partials`.  The CTA that takes the last ticket then
+// adds the CTA partials in a fixed order and writes the totals.  For a given
+// (grid, n) the summation tree is therefore identical from run to run.
+// ---------------------------------------------------------------------------
+template <int ND>
+__device__ __forceinline__ void warp_tree(double (&v)[ND])
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int d = 0; d < ND; d++)
+            v[d] = add(v[d], __shfl_down_sync(0xffffffffu, v[d], off));
+    }
+}
+
+template <int ND>
+__device__ __forceinline__ void block_tree(double (&v)[ND], double (*sm)[kThreads / 32])
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    warp_tree<ND>(v);
+    if (lane == 0) {
+#pragma unroll
+        for (int d = 0; d < ND; d++) sm[d][warp] = v[d];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int d = 0; d < ND; d++) v[d] = (lane < kThreads / 32) ? sm[d][lane] : 0.0;
+#pragma unroll
+        for (int off = (kThreads / 64); off > 0; off >>= 1) {
+#pragma unroll
+            for (int d = 0; d < ND; d++)
+                v[d] = add(v[d], __shfl_down_sync(0xffffffffu, v[d], off));
+        }
+    }
+    __syncthreads();
+}
+
+// out[d] receive the grid totals (device pointers).  All threads of all CTAs
+// must call this.  `ticket` must be zero on entry and is zero again on exit.
+template <int ND>
+__device__ __forceinline__ void grid_reduce(double (&acc)[ND], double *partials,
+                                            unsigned *ticket, double *const (&out)[ND])
+{
+    __shared__ double sm[ND][kThreads / 32];
+    __shared__ bool is_last;
+    block_tree<ND>(acc, sm);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int d = 0; d < ND; d++) partials[(size_t)blockIdx.x * ND + d] = acc[d];
+        __threadfence();
+        unsigned t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double v[ND];
+#pragma unroll
+        for (int d = 0; d < ND; d++) v[d] = 0.0;
+        for (unsigned j = threadIdx.x; j < gridDim.x; j += kThreads) {
+#pragma unroll
+            for (int d = 0; d < ND; d++)
+                v[d] = add(v[d], __ldcg(&partials[(size_t)j * ND + d]));
+        }
+        block_tree<ND>(v, sm);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int d = 0; d < ND; d++) *out[d] = v[d];
+            *ticket = 0u;
+        }
+    }
+}
+
+}  // namespace sigb

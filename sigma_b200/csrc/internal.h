@@ -1,0 +1,191 @@
+// internal.h -- private declarations shared by the sigma_b200 CUDA sources.
+// Nothing here is part of the C-ABI (include/sigma_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/sigma_b200.h"
+
+namespace sigb {
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define SIGB_CUDA(call)                                                       \
+    do {                                                                      \
+        cudaError_t e__ = (call);                                             \
+        if (e__ != cudaSuccess)                                               \
+            return ::sigb::cuda_fail(e__, #call, __FILE__, __LINE__);         \
+    } while (0)
+
+#define SIGB_CHECK(call)                                                      \
+    do {                                                                      \
+        int s__ = (call);                                                     \
+        if (s__ != SIGB_OK) return s__;                                       \
+    } while (0)
+
+#define SIGB_REQUIRE(cond, code, ...)                                         \
+    do {                                                                      \
+        if (!(cond)) {                                                        \
+            ::sigb::set_error(__VA_ARGS__);                                   \
+            return (code);                                                    \
+        }                                                                     \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// runtime context (one per process: one process drives one GPU)
+// ---------------------------------------------------------------------------
+struct Ctx {
+    bool inited = false;
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;    // stream every launch goes to
+    cudaStream_t aux_stream = nullptr;  // halo packing / exchange overlap
+    int64_t launches = 0;
+    // scratch for grid reductions
+    double *partials = nullptr;       // kMaxGrid * kMaxDots doubles
+    unsigned *tickets = nullptr;      // kNumTickets counters, zero between kernels
+    void *pinned = nullptr;           // small pinned host staging area
+    size_t pinned_bytes = 0;
+};
+Ctx &ctx();
+int require_init();
+
+constexpr int kThreads = 256;          // every kernel in this library uses 256-thread CTAs
+constexpr int kMaxGrid = 148 * 16;     // upper bound on persistent grid sizes
+constexpr int kMaxDots = 4;
+constexpr int kNumTickets = 8;
+
+inline void count_launch(int n = 1) { ctx().launches += n; }
+
+// ---------------------------------------------------------------------------
+// device-side sparse structures
+// ---------------------------------------------------------------------------
+
+// How the row sum z meets y; reproduces the reference's accumulation order.
+enum SpmvMode {
+    MODE_SET = 0,        // y(i) = z                 (matvec: y was zero-filled)
+    MODE_ADD_AFTER = 1,  // y(i) = y(i) + z, z from 0 (csr_matvec_add order)
+    MODE_ACC_INIT = 2    // z starts from y(i)       (csc_matvec_add order)
+};
+
+// CSR arrays exactly as the reference stores them (1-based) plus the row
+// tiling used by the streaming kernel.
+struct CsrView {
+    int32_t nrows = 0, ncols = 0;
+    int64_t nnz = 0;
+    int32_t *ptr = nullptr;       // nrows + 1, 1-based
+    int32_t *node = nullptr;      // nnz (+ pad), 1-based column ids, stored order
+    int32_t *tile_row = nullptr;  // ntiles + 1 row offsets (0-based)
+    int32_t ntiles = 0;
+    // optional tile subsets (row-sharded operators): interior tiles touch no
+    // halo column, boundary tiles do.
+    int32_t *tiles_interior = nullptr, *tiles_boundary = nullptr;
+    int32_t n_interior = 0, n_boundary = 0;
+};
+
+constexpr int kTileNnz = 2048;   // products staged per tile (16 KB of shared memory)
+// A tile's entry range is widened down to a 4-entry boundary so the node slice
+// can be read with aligned 128-bit loads; capping tiles at kTileNnz - 3 entries
+// keeps the widened range within kTileNnz.
+constexpr int kTileCap = kTileNnz - 3;
+constexpr int kTileRowsMax = 4096;
+
+enum GraphKind { G_CSR = 0, G_CSC = 1, G_ELL = 2 };
+
+struct DistInfo;  // comm.cu
+
+}  // namespace sigb
+
+struct sigb_graph_s {
+    int kind = 0;
+    int refcount = 1;
+    int32_t n = 0, m = 0;       // as in the reference graph (n lines of m possible ids)
+    int64_t ne = 0;
+    int32_t max_d = 0;
+    // compressed sparse: arrays as stored, and the stable transpose
+    sigb::CsrView stored;
+    sigb::CsrView transposed;
+    bool has_transposed = false;
+    int32_t *perm_t = nullptr;  // transposed position -> stored entry index (0-based)
+    // ellpack, slot-major on the device: node_sm[k * n_pad + i]
+    int32_t *ell_node = nullptr;
+    int32_t *ell_degrees = nullptr;  // degrees(n), as stored
+    int32_t n_pad = 0;
+    std::vector<int32_t> host_ptr_t;  // transposed ptr kept on the host for tiling
+};
+
+struct sigb_matrix_s {
+    sigb_graph_t g = nullptr;
+    double *val = nullptr;      // cs: ne (+pad) in stored order; ell: slot-major [max_d][n_pad]
+    double *val_t = nullptr;    // values in transposed order (cs: perm gather; ell: from slots)
+    bool val_t_valid = false;
+    int32_t nrow = 0, ncol = 0;
+    sigb::DistInfo *dist = nullptr;  // non-null for row-sharded operators
+};
+
+namespace sigb {
+
+// ---------------------------------------------------------------------------
+// kernels_spmv.cu
+// ---------------------------------------------------------------------------
+struct DotSpec {
+    int ndot = 0;                 // 0, 1 (u . y) or 2 (u . y and y . y)
+    const double *u = nullptr;    // vector dotted with the result rows
+    double *out[2] = {nullptr, nullptr};  // device scalars receiving the sums
+    const int *skip_flag = nullptr;       // if non-null and *skip_flag != 0 the kernel is a no-op
+    const double *row_scale = nullptr;    // y(i) = row_scale(i) * z (fused jacobi_solve), MODE_SET only
+};
+
+// which: 0 = all tiles, 1 = interior subset, 2 = boundary subset
+int launch_csr_spmv(const CsrView &A, const double *val, const double *x,
+                    double *y, SpmvMode mode, const DotSpec &dot, int which = 0,
+                    cudaStream_t stream = nullptr, int ticket = 0);
+int launch_ell_spmv(int32_t n, int32_t n_pad, int32_t max_d,
+                    const int32_t *node_sm, const double *val_sm,
+                    const double *x, double *y, SpmvMode mode,
+                    const DotSpec &dot);
+int build_tiles_host(const int32_t *ptr1, int32_t nrows,
+                     std::vector<int32_t> &tile_row);
+
+// ---------------------------------------------------------------------------
+// transpose.cu
+// ---------------------------------------------------------------------------
+// Stable transpose of `ne` entries living in `nlines` lines (cs: ptr-delimited,
+// ell: fixed width) into a CSR over `ntargets` rows.  Output arrays are
+// allocated here.  perm[pos] = source entry index (0-based, ascending within a
+// row => reference accumulation order).
+int device_transpose_cs(const int32_t *ptr1, const int32_t *node1, int32_t nlines,
+                        int32_t ntargets, int64_t ne, int32_t **ptr_t,
+                        int32_t **node_t, int32_t **perm);
+int device_transpose_ell(const int32_t *node_sm, int32_t n, int32_t n_pad,
+                         int32_t max_d, int32_t ntargets, int32_t **ptr_t,
+                         int32_t **node_t, int32_t **perm);
+int gather_values(const double *val, const int32_t *perm, int64_t ne, double *val_t);
+int ell_relayout_node(const int32_t *node_cm_dev, int32_t n, int32_t n_pad,
+                      int32_t max_d, int32_t *node_sm);
+int ell_relayout_val(const double *val_cm_dev, int32_t n, int32_t n_pad,
+                     int32_t max_d, double *val_sm);
+// transposed ell values: perm indexes the (line-major) stored layout
+int gather_values_ell(const double *val_sm, const int32_t *perm, int64_t ne,
+                      int32_t n_pad, int32_t max_d, double *val_t);
+int fill_i32(int32_t *p, int64_t n, int32_t v);
+int fill_f64(double *p, int64_t n, double v);
+
+// ---------------------------------------------------------------------------
+// matrix-level dispatch (api.cu)
+// ---------------------------------------------------------------------------
+int ensure_transposed(sigb_matrix_t A);
+// y = op(A) x with device vectors; the single entry every solver goes through
+int matvec_dev(sigb_matrix_t A, int trans, const double *x, double *y,
+               SpmvMode mode_csr_like, bool add, const DotSpec &dot);
+
+}  // namespace sigb

@@ -1,0 +1,768 @@
+// solvers.cu -- device-resident CG, BiCGSTAB, Jacobi and Lanczos.
+//
+// Replaces the bodies of
+//   cg_solve / cg_solve_pc               src/solver/cg_solvers.f90:116-194
+//   bicgstab_solve / bicgstab_solve_pc   src/solver/bicgstab_solvers.f90:124-237
+//   jacobi_setup / jacobi_solve          src/solver/jacobi_solvers.f90:37-81
+//   lanczos / eigensolve                 src/eigensolver.f90:27-90,160-184
+// keeping their stopping rules, work-vector sets and iteration counters.
+#include <math.h>
+#include <string.h>
+
+#include "krylov.cuh"
+#include "solvers.h"
+
+namespace sigb {
+
+// ===========================================================================
+// CG kernels
+// ===========================================================================
+
+// r = b - q ; p = r (or: z = idiag*r ; p = z) ; res2 = r.r (or r.z)
+// cg_solvers.f90:129-131 / :169-172
+struct CgInitOp {
+    static constexpr int ND = 1;
+    const double *__restrict__ b, *__restrict__ q, *__restrict__ idiag;
+    double *__restrict__ r, *__restrict__ p, *__restrict__ z;
+    KState *st;
+    __device__ bool begin() { return true; }
+    __device__ void apply(int64_t i, double *acc)
+    {
+        const double ri = sub(b[i], q[i]);
+        r[i] = ri;
+        double zi = ri;
+        if (idiag) { zi = mul(idiag[i], ri); z[i] = zi; }
+        p[i] = zi;
+        acc[0] = add(acc[0], mul(ri, zi));
+    }
+    __device__ double *out(int) { return &st->rr[0]; }
+};
+
+// latch of the first loop test (cg_solvers.f90:133 before the first pass)
+__global__ void latch0_kernel(KState *st)
+{
+    st->iters = 0;
+    st->capped = 0;
+    const bool go = sqrt(st->rr[0]) > st->tol;
+    int done = go ? 0 : 1;
+    if (go && st->cap == 0) { done = 1; st->capped = 1; }
+    st->done[0] = done;
+    st->done[1] = done;
+    st->final_res2 = st->rr[0];
+}
+
+// x = x + alpha p ; r = r - alpha q ; [z = idiag r] ; dpr = r.r (r.z)
+// cg_solvers.f90:136-140 / :178-183
+struct CgUpdateOp {
+    static constexpr int ND = 1;
+    const double *__restrict__ p, *__restrict__ q, *__restrict__ idiag;
+    double *__restrict__ x, *__restrict__ r, *__restrict__ z;
+    KState *st;
+    int par;
+    double alpha;
+    __device__ bool begin()
+    {
+        if (st->done[par]) return false;
+        alpha = st->rr[par] / st->pq;   // alpha = res2 / dpr
+        return true;
+    }
+    __device__ void apply(int64_t i, double *acc)
+    {
+        x[i] = add(x[i], mul(alpha, p[i]));
+        const double ri = sub(r[i], mul(alpha, q[i]));
+        r[i] = ri;
+        double zi = ri;
+        if (idiag) { zi = mul(idiag[i], ri); z[i] = zi; }
+        acc[0] = add(acc[0], mul(ri, zi));
+    }
+    __device__ double *out(int) { return &st->rr[par ^ 1]; }
+};
+
+// beta = dpr / res2 ; p = r + beta p (p = z + beta p) ; res2 = dpr ;
+// iterations += 1 ; evaluate the loop test for the next pass.
+// cg_solvers.f90:141-145 / :184-189
+struct CgDirectionOp {
+    static constexpr int ND = 0;
+    const double *__restrict__ rz;  // r, or z when preconditioned
+    double *__restrict__ p;
+    KState *st;
+    int par;
+    double beta;
+    __device__ bool begin()
+    {
+        if (st->done[par]) {
+            if (first_thread()) st->done[par ^ 1] = 1;
+            return false;
+        }
+        const double dpr = st->rr[par ^ 1];
+        beta = dpr / st->rr[par];
+        if (first_thread()) {
+            const long long it = st->iters + 1;
+            st->iters = it;
+            st->final_res2 = dpr;
+            int done = (sqrt(dpr) > st->tol) ? 0 : 1;
+            if (!done && st->cap >= 0 && it >= st->cap) { done = 1; st->capped = 1; }
+            st->done[par ^ 1] = done;
+        }
+        return true;
+    }
+    __device__ void apply(int64_t i, double *) { p[i] = add(rz[i], mul(beta, p[i])); }
+    __device__ double *out(int) { return nullptr; }
+};
+
+// ===========================================================================
+// BiCGSTAB kernels
+// ===========================================================================
+
+// r0 = b - q (or idiag*(b - q)) ; r = r0 ; v = 0 ; p = 0 ; res2 = r.r ; rho = r0.r
+// bicgstab_solvers.f90:141-152 / :200-212
+struct BicgInitOp {
+    static constexpr int ND = 2;
+    const double *__restrict__ b, *__restrict__ q, *__restrict__ idiag;
+    double *__restrict__ r, *__restrict__ r0, *__restrict__ v, *__restrict__ p, *__restrict__ z;
+    KState *st;
+    __device__ bool begin() { return true; }
+    __device__ void apply(int64_t i, double *acc)
+    {
+        double ri = sub(b[i], q[i]);
+        if (idiag) { z[i] = ri; ri = mul(idiag[i], ri); }
+        r0[i] = ri;
+        r[i] = ri;
+        v[i] = 0.0;
+        p[i] = 0.0;
+        acc[0] = add(acc[0], mul(ri, ri));
+        acc[1] = add(acc[1], mul(ri, ri));
+    }
+    __device__ double *out(int d) { return d == 0 ? &st->rr[0] : &st->rho[0]; }
+};
+
+__global__ void bicg_latch0_kernel(KState *st)
+{
+    st->iters = 0;
+    st->capped = 0;
+    // rho_old = alpha = omega = 1 (bicgstab_solvers.f90:144-147) live in the
+    // "previous iteration" slots
+    st->rho[1] = 1.0;
+    st->alpha[1] = 1.0;
+    st->omega[1] = 1.0;
+    const bool go = sqrt(st->rr[0]) > st->tol;
+    int done = go ? 0 : 1;
+    if (go && st->cap == 0) { done = 1; st->capped = 1; }
+    // done[1] plays "previous iteration not finished" for the first direction
+    // update; done[0] is written by that update
+    st->done[1] = done;
+    st->done[0] = done;
+    st->itc[0] = 0;
+    st->itc[1] = 0;
+    st->final_res2 = st->rr[0];
+}
+
+// Closes iteration `par^1`... see BicgDirectionOp::begin: evaluates the loop
+// test on rr[cur], then beta = rho/rho_old*alpha/omega ;
+// p = r + beta*(p - omega*v)   (bicgstab_solvers.f90:154-157)
+struct BicgDirectionOp {
+    static constexpr int ND = 0;
+    const double *__restrict__ r, *__restrict__ v;
+    double *__restrict__ p;
+    KState *st;
+    int cur;      // parity of the iteration this p belongs to
+    int initial;  // 1: first direction of a solve (no iteration to close)
+    double beta, omega_old;
+    __device__ bool begin()
+    {
+        const int prev = cur ^ 1;
+        if (initial) {
+            if (st->done[cur]) return false;
+        } else {
+            if (st->done[prev]) {
+                if (first_thread()) st->done[cur] = 1;
+                return false;
+            }
+            const double res2 = st->rr[cur];
+            int done = (sqrt(res2) > st->tol) ? 0 : 1;
+            int capped = 0;
+            // the counter is parity-indexed so that no thread reads a word
+            // another thread of this grid writes
+            const long long it = st->itc[prev] + 1;
+            if (!done && st->cap >= 0 && it >= st->cap) { done = 1; capped = 1; }
+            if (first_thread()) {
+                st->itc[cur] = it;
+                st->iters = it;
+                st->final_res2 = res2;
+                if (capped) st->capped = 1;
+                st->done[cur] = done;
+            }
+            if (done) return false;
+        }
+        omega_old = st->omega[prev];
+        beta = st->rho[cur] / st->rho[prev] * st->alpha[prev] / omega_old;
+        return true;
+    }
+    __device__ void apply(int64_t i, double *)
+    {
+        p[i] = add(r[i], mul(beta, sub(p[i], mul(omega_old, v[i]))));
+    }
+    __device__ double *out(int) { return nullptr; }
+};
+
+// alpha = rho / (r0.v) ; s = r - alpha v     (bicgstab_solvers.f90:160-161)
+struct BicgSOp {
+    static constexpr int ND = 0;
+    const double *__restrict__ r, *__restrict__ v;
+    double *__restrict__ s;
+    KState *st;
+    int par;
+    double alpha;
+    __device__ bool begin()
+    {
+        if (st->done[par]) return false;
+        alpha = st->rho[par] / st->pq;
+        if (first_thread()) st->alpha[par] = alpha;
+        return true;
+    }
+    __device__ void apply(int64_t i, double *) { s[i] = sub(r[i], mul(alpha, v[i])); }
+    __device__ double *out(int) { return nullptr; }
+};
+
+// omega = (s.t)/(t.t) [isnan -> 0] ; x = x + alpha p + omega s ; r = s - omega t ;
+// res2 = r.r ; (next) rho = r0.r         (bicgstab_solvers.f90:164-169,155)
+struct BicgUpdateOp {
+    static constexpr int ND = 2;
+    const double *__restrict__ p, *__restrict__ s, *__restrict__ t, *__restrict__ r0;
+    double *__restrict__ x, *__restrict__ r;
+    KState *st;
+    int par;
+    int nan_guard;  // unpreconditioned solver only (bicgstab_solvers.f90:165)
+    double alpha, omega;
+    __device__ bool begin()
+    {
+        if (st->done[par]) return false;
+        alpha = st->alpha[par];
+        omega = st->st / st->tt;
+        if (nan_guard && isnan(omega)) omega = 0.0;
+        if (first_thread()) st->omega[par] = omega;
+        return true;
+    }
+    __device__ void apply(int64_t i, double *acc)
+    {
+        const double si = s[i];
+        x[i] = add(add(x[i], mul(alpha, p[i])), mul(omega, si));
+        const double ri = sub(si, mul(omega, t[i]));
+        r[i] = ri;
+        acc[0] = add(acc[0], mul(ri, ri));
+        acc[1] = add(acc[1], mul(r0[i], ri));
+    }
+    __device__ double *out(int d) { return d == 0 ? &st->rr[par ^ 1] : &st->rho[par ^ 1]; }
+};
+
+// ===========================================================================
+// Jacobi
+// ===========================================================================
+
+// x = idiag * b   (jacobi_solvers.f90:77)
+struct JacobiApplyOp {
+    static constexpr int ND = 0;
+    const double *__restrict__ idiag, *__restrict__ b;
+    double *__restrict__ x;
+    __device__ bool begin() { return true; }
+    __device__ void apply(int64_t i, double *) { x[i] = mul(idiag[i], b[i]); }
+    __device__ double *out(int) { return nullptr; }
+};
+
+// idiag(i) = 1 / A%get_value(i, i): scan line i of the stored arrays for id i,
+// last hit wins, 0 when absent (csr_matrix_get_value cs_matrices.f90:709-724,
+// csc_matrix_get_value :729-744).
+__global__ void __launch_bounds__(kThreads)
+jacobi_setup_cs_kernel(const int32_t *__restrict__ ptr1, const int32_t *__restrict__ node1,
+                       const double *__restrict__ val, int32_t n, double *__restrict__ idiag)
+{
+    for (int32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+        double z = 0.0;
+        for (int32_t k = ptr1[i] - 1; k < ptr1[i + 1] - 1; k++)
+            if (node1[k] == i + 1) z = val[k];
+        idiag[i] = 1.0 / z;
+    }
+}
+
+// ellpack_matrix_get_value ellpack_matrices.f90:220-237: first degrees(i) slots
+__global__ void __launch_bounds__(kThreads)
+jacobi_setup_ell_kernel(const int32_t *__restrict__ node_sm, const double *__restrict__ val_sm,
+                        const int32_t *__restrict__ degrees, int32_t n, int32_t n_pad,
+                        double *__restrict__ idiag)
+{
+    for (int32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+        double z = 0.0;
+        const int32_t d = degrees[i];
+        for (int32_t k = 0; k < d; k++)
+            if (node_sm[(size_t)k * n_pad + i] == i + 1) z = val_sm[(size_t)k * n_pad + i];
+        idiag[i] = 1.0 / z;
+    }
+}
+
+// ===========================================================================
+// Lanczos kernels
+// ===========================================================================
+
+// dot(a, b) -> *out
+struct DotOp {
+    static constexpr int ND = 1;
+    const double *__restrict__ a, *__restrict__ b;
+    double *o;
+    __device__ bool begin() { return true; }
+    __device__ void apply(int64_t i, double *acc) { acc[0] = add(acc[0], mul(a[i], b[i])); }
+    __device__ double *out(int) { return o; }
+};
+
+// dst = src / sqrt(*norm2)  (eigensolver.f90:52 ; :59,:79 with beta = sqrt(w.w))
+// optionally records alpha / beta into T(:, col)  (:60-62, :80-82)
+struct ScaleOp {
+    static constexpr int ND = 0;
+    const double *src;  // may alias dst
+    double *dst;
+    const double *norm2;
+    const double *alpha;  // may be null
+    double *Tcol;         // T(1:3, col) or null
+    double *beta_out;     // where beta is kept for the next step, or null
+    double d;
+    __device__ bool begin()
+    {
+        d = sqrt(*norm2);
+        if (first_thread()) {
+            if (Tcol) { Tcol[1] = *alpha; Tcol[2] = d; Tcol[0] = d; }
+            if (beta_out) *beta_out = d;
+        }
+        return true;
+    }
+    __device__ void apply(int64_t i, double *) { dst[i] = src[i] / d; }
+    __device__ double *out(int) { return nullptr; }
+};
+
+// w = w - alpha*qi [- beta*qim1] ; then dot(w, nxt or w) -> *o
+// eigensolver.f90:57-58 / :70 (+ the first dot of the sweep :75 or of :78)
+struct LanczosRecurOp {
+    static constexpr int ND = 1;
+    double *__restrict__ w;
+    const double *__restrict__ qi, *__restrict__ qim1;  // qim1 may be null
+    const double *__restrict__ nxt;                     // null => w.w
+    const double *alpha_p, *beta_p;
+    double *o;
+    double alpha, beta;
+    __device__ bool begin()
+    {
+        alpha = *alpha_p;
+        beta = qim1 ? *beta_p : 0.0;
+        return true;
+    }
+    __device__ void apply(int64_t i, double *acc)
+    {
+        double wi = sub(w[i], mul(alpha, qi[i]));
+        if (qim1) wi = sub(wi, mul(beta, qim1[i]));
+        w[i] = wi;
+        acc[0] = add(acc[0], mul(nxt ? nxt[i] : wi, wi));
+    }
+    __device__ double *out(int) { return o; }
+};
+
+// w = w - c*qk ; then dot(nxt or w, w) -> *o     (eigensolver.f90:75)
+struct LanczosOrthoOp {
+    static constexpr int ND = 1;
+    double *__restrict__ w;
+    const double *__restrict__ qk, *__restrict__ nxt;
+    const double *c_p;
+    double *o;
+    double c;
+    __device__ bool begin() { c = *c_p; return true; }
+    __device__ void apply(int64_t i, double *acc)
+    {
+        const double wi = sub(w[i], mul(c, qk[i]));
+        w[i] = wi;
+        acc[0] = add(acc[0], mul(nxt ? nxt[i] : wi, wi));
+    }
+    __device__ double *out(int) { return o; }
+};
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+// random_number(Q(:,1)) ; Q(:,1) = 2*Q(:,1) - 1   (eigensolver.f90:50-51);
+// counter-based so the vector does not depend on the launch shape or sharding
+struct RandomOp {
+    static constexpr int ND = 0;
+    double *__restrict__ q;
+    uint64_t seed;
+    int64_t offset;  // global index of element 0
+    __device__ bool begin() { return true; }
+    __device__ void apply(int64_t i, double *)
+    {
+        const uint64_t h = splitmix64(seed ^ splitmix64((uint64_t)(i + offset)));
+        const double u = (double)(h >> 11) * (1.0 / 9007199254740992.0);
+        q[i] = sub(mul(2.0, u), 1.0);
+    }
+    __device__ double *out(int) { return nullptr; }
+};
+
+// V2(l, j) = sum_k V(l, k) * Qm(k, j)   (V = matmul(V, Q), eigensolver.f90:176)
+__global__ void __launch_bounds__(kThreads)
+ritz_kernel(const double *__restrict__ V, const double *__restrict__ Qm, int64_t nr, int32_t n,
+            double *__restrict__ V2)
+{
+    extern __shared__ double qs[];  // Qm, n*n
+    for (int k = threadIdx.x; k < n * n; k += kThreads) qs[k] = Qm[k];
+    __syncthreads();
+    for (int64_t l = blockIdx.x * (int64_t)kThreads + threadIdx.x; l < nr;
+         l += (int64_t)gridDim.x * kThreads) {
+        for (int j = 0; j < n; j++) {
+            double s = 0.0;
+            for (int k = 0; k < n; k++) s = add(s, mul(V[(size_t)k * nr + l], qs[(size_t)j * n + k]));
+            V2[(size_t)j * nr + l] = s;
+        }
+    }
+}
+
+// V(:, i) = V(1, i)/|V(1, i)| * V(:, i)   (eigensolver.f90:178-180)
+__global__ void __launch_bounds__(kThreads)
+sign_kernel(double *__restrict__ V, int64_t nr, int32_t n, const double *__restrict__ first_row)
+{
+    for (int j = 0; j < n; j++) {
+        const double f = first_row[j];
+        const double sg = f / fabs(f);
+        for (int64_t l = blockIdx.x * (int64_t)kThreads + threadIdx.x; l < nr;
+             l += (int64_t)gridDim.x * kThreads)
+            V[(size_t)j * nr + l] = mul(sg, V[(size_t)j * nr + l]);
+    }
+}
+
+__global__ void grab_first_row_kernel(const double *V, int64_t nr, int32_t n, double *first_row)
+{
+    for (int j = threadIdx.x; j < n; j += blockDim.x) first_row[j] = V[(size_t)j * nr];
+}
+
+// ===========================================================================
+// host drivers
+// ===========================================================================
+
+static int sync_state(sigb_solver_t s)
+{
+    SIGB_CUDA(cudaMemcpyAsync(s->state_host, s->state, sizeof(KState), cudaMemcpyDeviceToHost,
+                              ctx().stream));
+    SIGB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return SIGB_OK;
+}
+
+static int push_state(sigb_solver_t s)
+{
+    memset(s->state_host, 0, sizeof(KState));
+    s->state_host->tol = s->tol;
+    s->state_host->cap = s->cap;
+    SIGB_CUDA(cudaMemcpyAsync(s->state, s->state_host, sizeof(KState), cudaMemcpyHostToDevice,
+                              ctx().stream));
+    return SIGB_OK;
+}
+
+int jacobi_setup_dev(sigb_solver_t s, sigb_matrix_t A)
+{
+    sigb_graph_t g = A->g;
+    const int32_t n = A->nrow;
+    cudaStream_t st = ctx().stream;
+    const int grid = ew_grid(n);
+    if (g->kind == G_ELL) {
+        jacobi_setup_ell_kernel<<<grid, kThreads, 0, st>>>(g->ell_node, A->val, g->ell_degrees, n,
+                                                          g->n_pad, s->work);
+    } else {
+        jacobi_setup_cs_kernel<<<grid, kThreads, 0, st>>>(g->stored.ptr, g->stored.node, A->val, n,
+                                                         s->work);
+    }
+    count_launch();
+    SIGB_CUDA(cudaGetLastError());
+    return SIGB_OK;
+}
+
+int jacobi_apply_dev(sigb_solver_t s, double *x, const double *b)
+{
+    JacobiApplyOp op{s->work, b, x};
+    return launch_ew(op, s->nn);
+}
+
+static int finish_solve(sigb_solver_t s)
+{
+    SIGB_CHECK(sync_state(s));
+    s->iterations += s->state_host->iters;
+    s->res2 = s->state_host->final_res2;
+    s->capped = s->state_host->capped;
+    return SIGB_OK;
+}
+
+// iterations launched between two looks at the device state
+static int batch_size(int64_t n)
+{
+    if (n < (1 << 16)) return 64;
+    if (n < (1 << 20)) return 32;
+    return 16;
+}
+
+int cg_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x, const double *b, sigb_solver_t pc)
+{
+    const int64_t n = s->nn, nv = s->nvec;
+    double *p = s->work, *q = p + nv, *r = q + nv, *z = r + nv;
+    const double *idiag = pc ? pc->work : nullptr;
+    KState *st = s->state;
+    SIGB_CHECK(push_state(s));
+
+    DotSpec none;
+    // q = A x ; r = b - q ; [z = M r] ; p = r|z ; res2 = r.r | r.z
+    SIGB_CHECK(solver_matvec(A, x, q, none, /*x_has_halo=*/false));
+    CgInitOp init{b, q, idiag, r, p, z, st};
+    SIGB_CHECK(launch_ew(init, n));
+    SIGB_CHECK(dist_allreduce(A, &st->rr[0], 1));
+    latch0_kernel<<<1, 1, 0, ctx().stream>>>(st);
+    count_launch();
+
+    const int nb = batch_size(n);
+    int par = 0;
+    for (;;) {
+        for (int it = 0; it < nb; it++) {
+            DotSpec d;
+            d.ndot = 1;
+            d.u = p;
+            d.out[0] = &st->pq;
+            d.skip_flag = &st->done[par];
+            SIGB_CHECK(solver_matvec(A, p, q, d, /*x_has_halo=*/true));   // q = A p ; dpr = p.q
+            SIGB_CHECK(dist_allreduce(A, &st->pq, 1));
+            CgUpdateOp up{p, q, idiag, x, r, z, st, par, 0.0};
+            SIGB_CHECK(launch_ew(up, n));
+            SIGB_CHECK(dist_allreduce(A, &st->rr[par ^ 1], 1));
+            CgDirectionOp dir{idiag ? z : r, p, st, par, 0.0};
+            SIGB_CHECK(launch_ew(dir, n));
+            par ^= 1;
+        }
+        SIGB_CHECK(sync_state(s));
+        if (s->state_host->done[par]) break;
+    }
+    return finish_solve(s);
+}
+
+int bicgstab_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x, const double *b,
+                       sigb_solver_t pc)
+{
+    const int64_t n = s->nn, nv = s->nvec;
+    double *p = s->work, *q = p + nv, *r = q + nv, *r0 = r + nv, *v = r0 + nv, *sv = v + nv,
+           *t = sv + nv, *z = t + nv;
+    const double *idiag = pc ? pc->work : nullptr;
+    KState *st = s->state;
+    SIGB_CHECK(push_state(s));
+
+    DotSpec none;
+    SIGB_CHECK(solver_matvec(A, x, q, none, false));
+    BicgInitOp init{b, q, idiag, r, r0, v, p, z, st};
+    SIGB_CHECK(launch_ew(init, n));
+    SIGB_CHECK(dist_allreduce(A, &st->rr[0], 3));  // rr[0], rr[1], rho[0] are contiguous
+    bicg_latch0_kernel<<<1, 1, 0, ctx().stream>>>(st);
+    count_launch();
+    {
+        BicgDirectionOp dir{r, v, p, st, 0, 1, 0.0, 0.0};
+        SIGB_CHECK(launch_ew(dir, n));
+    }
+
+    const int nb = batch_size(n);
+    int par = 0;
+    for (;;) {
+        for (int it = 0; it < nb; it++) {
+            DotSpec d1;                      // v = [M] A p ; r0.v
+            d1.ndot = 1;
+            d1.u = r0;
+            d1.out[0] = &st->pq;
+            d1.skip_flag = &st->done[par];
+            d1.row_scale = idiag;
+            SIGB_CHECK(solver_matvec(A, p, v, d1, true));
+            SIGB_CHECK(dist_allreduce(A, &st->pq, 1));
+            BicgSOp sop{r, v, sv, st, par, 0.0};
+            SIGB_CHECK(launch_ew(sop, n));
+            DotSpec d2;                      // t = [M] A s ; s.t, t.t
+            d2.ndot = 2;
+            d2.u = sv;
+            d2.out[0] = &st->st;
+            d2.out[1] = &st->tt;
+            d2.skip_flag = &st->done[par];
+            d2.row_scale = idiag;
+            SIGB_CHECK(solver_matvec(A, sv, t, d2, true));
+            SIGB_CHECK(dist_allreduce(A, &st->st, 2));
+            BicgUpdateOp up{p, sv, t, r0, x, r, st, par, pc ? 0 : 1, 0.0, 0.0};
+            SIGB_CHECK(launch_ew(up, n));
+            SIGB_CHECK(dist_allreduce2(A, &st->rr[par ^ 1], &st->rho[par ^ 1]));
+            BicgDirectionOp dir{r, v, p, st, par ^ 1, 0, 0.0, 0.0};
+            SIGB_CHECK(launch_ew(dir, n));
+            par ^= 1;
+        }
+        SIGB_CHECK(sync_state(s));
+        if (s->state_host->done[par]) break;
+    }
+    return finish_solve(s);
+}
+
+// n-step Lanczos on device arrays: Q is nr x n column-major (ld = nr), T is 3 x n.
+int lanczos_dev(sigb_matrix_t A, int32_t n, const double *q1, uint64_t seed, int64_t row_offset,
+                double *T, double *Q, double *w, KState *st)
+{
+    const int64_t nr = A->nrow;
+    cudaStream_t stream = ctx().stream;
+    SIGB_CUDA(cudaMemsetAsync(T, 0, sizeof(double) * 3 * (size_t)n, stream));
+    SIGB_CUDA(cudaMemsetAsync(Q, 0, sizeof(double) * (size_t)nr * n, stream));
+    SIGB_CUDA(cudaMemsetAsync(w, 0, sizeof(double) * (size_t)nr, stream));
+    auto col = [&](int c) { return Q + (size_t)(c - 1) * nr; };  // 1-based column
+
+    if (q1) {
+        SIGB_CUDA(cudaMemcpyAsync(col(1), q1, sizeof(double) * (size_t)nr, cudaMemcpyDeviceToDevice, stream));
+    } else {
+        RandomOp rnd{col(1), seed, row_offset};
+        SIGB_CHECK(launch_ew(rnd, nr));
+    }
+    // Q(:,1) = Q(:,1) / dsqrt(sum(Q(:,1)*Q(:,1)))          :52
+    {
+        DotOp d{col(1), col(1), &st->lz[2]};
+        SIGB_CHECK(launch_ew(d, nr));
+        SIGB_CHECK(dist_allreduce(A, &st->lz[2], 1));
+        ScaleOp sc{col(1), col(1), &st->lz[2], nullptr, nullptr, nullptr, 0.0};
+        SIGB_CHECK(launch_ew(sc, nr));
+    }
+    if (n == 1) {
+        DotSpec d;
+        d.ndot = 1; d.u = col(1); d.out[0] = &T[1];
+        SIGB_CHECK(solver_matvec(A, col(1), w, d, false));
+        SIGB_CHECK(dist_allreduce(A, &T[1], 1));
+        return SIGB_OK;
+    }
+    for (int i = 1; i <= n - 1; i++) {
+        // w = A q_i ; alpha = q_i . w                         :55-56 / :68-69
+        DotSpec d;
+        d.ndot = 1; d.u = col(i); d.out[0] = &st->lz[0];
+        SIGB_CHECK(solver_matvec(A, col(i), w, d, false));
+        SIGB_CHECK(dist_allreduce(A, &st->lz[0], 1));
+        // w = w - alpha q_i - beta q_{i-1}, fused with the next dot  :57 / :70
+        const int nsweep = i - 2;  // re-orthogonalise against q_1 .. q_{i-2}   :74
+        int slot = 3;
+        {
+            LanczosRecurOp op{w, col(i), i >= 2 ? col(i - 1) : nullptr, nsweep >= 1 ? col(1) : nullptr,
+                              &st->lz[0], &st->lz[1], nsweep >= 1 ? &st->lz[slot] : &st->lz[2], 0.0, 0.0};
+            SIGB_CHECK(launch_ew(op, nr));
+            SIGB_CHECK(dist_allreduce(A, nsweep >= 1 ? &st->lz[slot] : &st->lz[2], 1));
+        }
+        for (int k = 1; k <= nsweep; k++) {
+            const bool last = (k == nsweep);
+            const int nslot = (slot == 3) ? 4 : 3;
+            LanczosOrthoOp op{w, col(k), last ? nullptr : col(k + 1), &st->lz[slot],
+                              last ? &st->lz[2] : &st->lz[nslot], 0.0};
+            SIGB_CHECK(launch_ew(op, nr));
+            SIGB_CHECK(dist_allreduce(A, last ? &st->lz[2] : &st->lz[nslot], 1));
+            slot = nslot;
+        }
+        // beta = sqrt(w.w) ; q_{i+1} = w / beta ; T(:, i)     :58-62 / :78-82
+        ScaleOp sc{w, col(i + 1), &st->lz[2], &st->lz[0], T + 3 * (size_t)(i - 1), &st->lz[1], 0.0};
+        SIGB_CHECK(launch_ew(sc, nr));
+    }
+    // T(2, n) = q_n . (A q_n)                                 :87-88
+    DotSpec d;
+    d.ndot = 1; d.u = col(n); d.out[0] = &T[3 * (size_t)(n - 1) + 1];
+    SIGB_CHECK(solver_matvec(A, col(n), w, d, false));
+    SIGB_CHECK(dist_allreduce(A, &T[3 * (size_t)(n - 1) + 1], 1));
+    return SIGB_OK;
+}
+
+// Symmetric tridiagonal eigen-solve standing in for LAPACK dstev('V')
+// (eigensolver.f90:174; LAPACK is not vendored by the reference).  Implicit QL
+// with Wilkinson shifts; eigenvalues ascending, eigenvectors in the columns of
+// Z (column-major n x n).  Runs on the host: n is the number of Lanczos steps.
+int tridiag_eig_host(int n, double *d, double *e, double *Z)
+{
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) Z[(size_t)j * n + i] = (i == j) ? 1.0 : 0.0;
+    if (n == 1) return 0;
+    e[n - 1] = 0.0;
+    const double eps = 2.220446049250313e-16;
+    for (int l = 0; l < n; l++) {
+        int iter = 0, m;
+        do {
+            for (m = l; m < n - 1; m++) {
+                const double dd = fabs(d[m]) + fabs(d[m + 1]);
+                if (fabs(e[m]) <= eps * dd) break;
+            }
+            if (m != l) {
+                if (iter++ == 60) return 1;
+                double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+                double r = hypot(g, 1.0);
+                g = d[m] - d[l] + e[l] / (g + copysign(r, g));
+                double s = 1.0, c = 1.0, p = 0.0;
+                int i;
+                for (i = m - 1; i >= l; i--) {
+                    double f = s * e[i];
+                    const double b = c * e[i];
+                    r = hypot(f, g);
+                    e[i + 1] = r;
+                    if (r == 0.0) {
+                        d[i + 1] -= p;
+                        e[m] = 0.0;
+                        break;
+                    }
+                    s = f / r;
+                    c = g / r;
+                    g = d[i + 1] - p;
+                    r = (d[i] - g) * s + 2.0 * c * b;
+                    p = s * r;
+                    d[i + 1] = g + p;
+                    g = c * r - b;
+                    for (int k = 0; k < n; k++) {
+                        double *zi1 = Z + (size_t)(i + 1) * n + k, *zi = Z + (size_t)i * n + k;
+                        f = *zi1;
+                        *zi1 = s * (*zi) + c * f;
+                        *zi = c * (*zi) - s * f;
+                    }
+                }
+                if (r == 0.0 && i >= l) continue;
+                d[l] -= p;
+                e[l] = g;
+                e[m] = 0.0;
+            }
+        } while (m != l);
+    }
+    for (int i = 0; i < n - 1; i++) {
+        int k = i;
+        double p = d[i];
+        for (int j = i + 1; j < n; j++)
+            if (d[j] < p) { k = j; p = d[j]; }
+        if (k != i) {
+            d[k] = d[i];
+            d[i] = p;
+            for (int j = 0; j < n; j++) {
+                const double tmp = Z[(size_t)i * n + j];
+                Z[(size_t)i * n + j] = Z[(size_t)k * n + j];
+                Z[(size_t)k * n + j] = tmp;
+            }
+        }
+    }
+    return 0;
+}
+
+size_t kstate_bytes() { return sizeof(KState); }
+
+int ritz_vectors_dev(double *V, double *V2, const double *Qm_dev, int64_t nr, int32_t n,
+                     double *first_row_dev)
+{
+    cudaStream_t st = ctx().stream;
+    const size_t smem = sizeof(double) * (size_t)n * n;
+    SIGB_REQUIRE(smem <= 200 * 1024, SIGB_ERR_UNSUPPORTED,
+                 "eigensolve: %d Lanczos steps exceed the on-chip Ritz-matrix budget", n);
+    SIGB_CUDA(cudaFuncSetAttribute(ritz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ritz_kernel<<<ew_grid(nr), kThreads, smem, st>>>(V, Qm_dev, nr, n, V2);
+    SIGB_CUDA(cudaMemcpyAsync(V, V2, sizeof(double) * (size_t)nr * n, cudaMemcpyDeviceToDevice, st));
+    grab_first_row_kernel<<<1, 128, 0, st>>>(V, nr, n, first_row_dev);
+    sign_kernel<<<ew_grid(nr), kThreads, 0, st>>>(V, nr, n, first_row_dev);
+    count_launch(3);
+    SIGB_CUDA(cudaGetLastError());
+    return SIGB_OK;
+}
+
+}  // namespace sigb

@@ -1,0 +1,57 @@
+// solvers.h -- solver handle and the driver entry points shared by
+// solvers.cu, api.cu and comm.cu.
+#pragma once
+
+#include "internal.h"
+
+namespace sigb {
+struct KState;
+enum SolverKind { S_CG = 0, S_BICGSTAB = 1, S_JACOBI = 2 };
+}  // namespace sigb
+
+struct sigb_solver_s {
+    int kind = 0;
+    double tol = 1e-16;        // cg_set_params default, cg_solvers.f90:106
+    bool params_set = false;
+    bool initialized = false;  // work vectors allocated (cg_setup :78-81)
+    int64_t cap = -1;          // safety cap per solve (not in the reference)
+    int32_t nn = 0;            // solver%nn: owned rows
+    int64_t nvec = 0;          // allocated length of each work vector (nn + halo room)
+    int64_t iterations = 0;    // solver%iterations (accumulates until the next setup)
+    double res2 = 0.0;
+    int capped = 0;
+    double *work = nullptr;    // cg: p,q,r,z ; bicgstab: p,q,r,r0,v,s,t,z ; jacobi: idiag
+    int nwork = 0;
+    sigb::KState *state = nullptr;       // device
+    sigb::KState *state_host = nullptr;  // pinned
+    double *xb = nullptr;      // device staging for host-pointer solves (x | b)
+    int64_t xb_len = 0;
+    sigb_matrix_t A = nullptr; // operator given to setup
+};
+
+namespace sigb {
+
+int jacobi_setup_dev(sigb_solver_t s, sigb_matrix_t A);
+int jacobi_apply_dev(sigb_solver_t s, double *x, const double *b);
+int cg_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x, const double *b, sigb_solver_t pc);
+int bicgstab_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x, const double *b,
+                       sigb_solver_t pc);
+int lanczos_dev(sigb_matrix_t A, int32_t n, const double *q1, uint64_t seed, int64_t row_offset,
+                double *T, double *Q, double *w, KState *st);
+int tridiag_eig_host(int n, double *d, double *e, double *Z);
+int ritz_vectors_dev(double *V, double *V2, const double *Qm_dev, int64_t nr, int32_t n,
+                     double *first_row_dev);
+size_t kstate_bytes();
+
+// y = A x (MODE_SET) with fused dots.  For row-sharded operators this also
+// performs the halo exchange; x_has_halo says x has room for (and may receive)
+// the halo entries behind its owned part.
+int solver_matvec(sigb_matrix_t A, const double *x, double *y, const DotSpec &dot,
+                  bool x_has_halo);
+// Sum `count` contiguous device doubles over all ranks (no-op on one GPU).
+int dist_allreduce(sigb_matrix_t A, double *vals, int count);
+int dist_allreduce2(sigb_matrix_t A, double *a, double *b);
+// extra elements a work vector needs behind its owned part (0 on one GPU)
+int64_t dist_halo_len(sigb_matrix_t A);
+
+}  // namespace sigb

@@ -1,0 +1,288 @@
+"""Deterministic synthetic inputs for the hot path, in the reference's storage.
+
+Every generator returns arrays laid out exactly as the reference would hold
+them after building the matrix the way its tests do: build an ``ll_graph`` with
+``add_edge`` (insertion order kept per row, src/graph/formats/ll_graphs.f90:355-371),
+convert to compressed-sparse / ellpack (first-free-slot insertion,
+src/graph/formats/cs_graphs.f90:163-183; last-neighbour padding,
+src/graph/formats/ellpack_graphs.f90:164), then ``set_value``.  Columns are
+therefore NOT sorted in general.  The large cases are produced with vectorised
+numpy that yields the same arrays as that build order; tests/test_generators.py
+proves the equality against the oracle's restatement of the builders on small
+sizes.
+
+Indices are 1-based int32, values fp64.  Nothing here touches the GPU or the
+oracle.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+__all__ = [
+    "tridiag_add_edge_calls", "tridiag_csr", "tridiag_ell", "poisson2d_add_edge_calls",
+    "poisson2d_csr", "poisson2d_rhs", "csr_to_ell", "csr_transpose", "erdos_renyi_csr",
+    "erdos_renyi_add_edge_calls", "fem_p1_csr", "dense_from_csr",
+]
+
+
+# --------------------------------------------------------------------------
+# 1-D three-point operators (test/solver_test_diffusion_1d.f90:55-76,
+# test/solver_test_advection_diffusion_1d.f90:58-82)
+# --------------------------------------------------------------------------
+def tridiag_add_edge_calls(nn):
+    """The (i, j) sequence of g%add_edge calls of both 1-D tests (:60-65)."""
+    i = np.arange(1, nn, dtype=np.int32)
+    ei = np.stack([i, i, i + 1], 1).reshape(-1)
+    ej = np.stack([i, i + 1, i], 1).reshape(-1)
+    return np.append(ei, np.int32(nn)), np.append(ej, np.int32(nn))
+
+
+def tridiag_csr(nn, diag=2.0, upper=-1.0, lower=-1.0):
+    """CSR arrays of tridiag(lower, diag, upper): row i holds [i-1, i, i+1]."""
+    k = np.arange(1, nn + 1, dtype=np.int32)
+    cand = np.stack([k - 1, k, k + 1], 1)
+    vals = np.broadcast_to(np.array([lower, diag, upper]), (nn, 3))
+    valid = np.stack([k > 1, np.ones(nn, bool), k < nn], 1)
+    ptr = np.concatenate([[1], 1 + np.cumsum(valid.sum(1))]).astype(np.int32)
+    return ptr, cand[valid].astype(np.int32), vals[valid].astype(np.float64)
+
+
+def tridiag_ell(nn, diag=2.0, upper=-1.0, lower=-1.0):
+    """ELLPACK arrays (node[nn,3], degrees, val[nn,3]) of the same operator.
+    Row 1 = [1,2,2], row nn = [nn-1,nn,nn]; padding values are 0."""
+    ptr, node, val = tridiag_csr(nn, diag, upper, lower)
+    return csr_to_ell(ptr, node, val)
+
+
+# --------------------------------------------------------------------------
+# 2-D five-point Poisson on an N x N grid, Dirichlet (BASELINE config 2)
+# --------------------------------------------------------------------------
+def poisson2d_add_edge_calls(N):
+    """add_edge sequence in the reference idiom (cf. apps/regular_graphs.f90:22-34,
+    test/solver_test_diffusion_1d.f90:60-65): loop vertices k = N*(ix-1)+iy,
+    add (k,k), then (k,k+1),(k+1,k) if iy<N, then (k,k+N),(k+N,k) if ix<N."""
+    ei, ej = [], []
+    for ix in range(1, N + 1):
+        for iy in range(1, N + 1):
+            k = N * (ix - 1) + iy
+            ei.append(k); ej.append(k)
+            if iy < N:
+                ei += [k, k + 1]; ej += [k + 1, k]
+            if ix < N:
+                ei += [k, k + N]; ej += [k + N, k]
+    return np.array(ei, np.int32), np.array(ej, np.int32)
+
+
+def poisson2d_csr(N, row_lo=0, row_hi=None, diag=4.0, off=-1.0):
+    """Rows [row_lo, row_hi) (0-based) of the N^2 x N^2 five-point matrix.
+
+    Interior row k (1-based) is stored as [k-N, k-1, k, k+1, k+N] -- the order
+    the build above produces.  Returns (ptr, node, val) with ptr 1-based and
+    starting at 1 for the block, node holding GLOBAL 1-based column ids.
+    """
+    n = N * N
+    row_hi = n if row_hi is None else row_hi
+    k0 = np.arange(row_lo, row_hi, dtype=np.int64)
+    ix, iy = k0 // N, k0 % N
+    cand = np.stack([k0 - N, k0 - 1, k0, k0 + 1, k0 + N], 1) + 1
+    valid = np.stack([ix > 0, iy > 0, np.ones(k0.size, bool), iy < N - 1, ix < N - 1], 1)
+    vals = np.broadcast_to(np.array([off, off, diag, off, off]), cand.shape)
+    ptr = np.concatenate([[1], 1 + np.cumsum(valid.sum(1))]).astype(np.int32)
+    return ptr, cand[valid].astype(np.int32), vals[valid].astype(np.float64)
+
+
+def poisson2d_rhs(N, seed=12345, row_lo=0, row_hi=None, diag=4.0, off=-1.0):
+    """b = A x*, x* ~ U[0,1) from PCG64(seed); returns
+    (b[row_lo:row_hi], x*[row_lo:row_hi]).  b is evaluated with the stencil in
+    the stored entry order, without FMA (numpy never contracts)."""
+    n = N * N
+    row_hi = n if row_hi is None else row_hi
+    xs = np.random.Generator(np.random.PCG64(seed)).random(n)
+    g = xs.reshape(N, N)
+    z = np.zeros((N, N))
+    z[1:, :] += off * g[:-1, :]       # k - N
+    z[:, 1:] += off * g[:, :-1]       # k - 1
+    z += diag * g                     # k
+    z[:, :-1] += off * g[:, 1:]       # k + 1
+    z[:-1, :] += off * g[1:, :]       # k + N
+    return z.reshape(-1)[row_lo:row_hi].copy(), xs[row_lo:row_hi].copy()
+
+
+# --------------------------------------------------------------------------
+# format conversions in the reference's own semantics
+# --------------------------------------------------------------------------
+def csr_to_ell(ptr, node, val):
+    """convert_graph_type(g, "ellpack") + values: slots in stored order, the
+    rest of each row filled with the row's last neighbour
+    (ellpack_graphs.f90:164) and val = 0 (ellpack_matrices.f90:132)."""
+    ptr = np.asarray(ptr, np.int64)
+    n = ptr.size - 1
+    deg = np.diff(ptr).astype(np.int32)
+    w = int(deg.max()) if n else 0
+    slot = np.arange(w)[None, :]
+    idx = (ptr[:-1, None] - 1) + np.minimum(slot, np.maximum(deg[:, None] - 1, 0))
+    ell_node = np.asarray(node)[idx].astype(np.int32)
+    ell_val = np.where(slot < deg[:, None], np.asarray(val)[idx], 0.0)
+    if (deg == 0).any():
+        ell_node[deg == 0] = 0
+    return ell_node, deg, ell_val.astype(np.float64)
+
+
+def csr_transpose(n, m, ptr, node, val):
+    """Arrays of the transposed copy the reference builds (cs_graph_build with
+    trans, cs_graphs.f90:122-183): line j holds the source rows in ascending
+    order.  This is also the CSC storage of the same matrix."""
+    ptr = np.asarray(ptr, np.int64)
+    rows = np.repeat(np.arange(1, n + 1, dtype=np.int32), np.diff(ptr))
+    order = np.argsort(np.asarray(node), kind="stable")
+    cnt = np.bincount(np.asarray(node) - 1, minlength=m)
+    ptr_t = np.concatenate([[1], 1 + np.cumsum(cnt)]).astype(np.int32)
+    return ptr_t, rows[order].astype(np.int32), np.asarray(val)[order].astype(np.float64)
+
+
+def dense_from_csr(n, m, ptr, node, val):
+    B = np.zeros((n, m))
+    rows = np.repeat(np.arange(n), np.diff(ptr))
+    B[rows, np.asarray(node) - 1] = val
+    return B
+
+
+# --------------------------------------------------------------------------
+# Erdos-Renyi graph Laplacians (test/solver_test_jacobi.f90:60-128,240-254,
+# test/eigensolver_test_lanczos.f90:58-110, apps/random_graphs.f90:33-42)
+# --------------------------------------------------------------------------
+def _er_pairs(n, p, rng):
+    """Upper-triangle pairs (i<j) of G(n, p) by geometric skipping (the
+    reference's O(n^2) double loop is infeasible at 2e7 vertices)."""
+    total = n * (n - 1) // 2
+    expected = total * p
+    chunk = int(expected * 1.1 + 1000)
+    pos = []
+    cur = -1
+    while True:
+        gaps = rng.geometric(p, size=chunk).astype(np.int64)
+        cs = cur + np.cumsum(gaps)
+        keep = cs < total
+        pos.append(cs[keep])
+        if not keep.all():
+            break
+        cur = int(cs[-1])
+    pos = np.concatenate(pos)
+    # linear index -> (i, j), rows enumerated i = 0..n-2 with n-1-i entries each
+    # i = floor(((2n-1) - sqrt((2n-1)^2 - 8 pos)) / 2)
+    b = 2.0 * n - 1.0
+    i = np.floor((b - np.sqrt(b * b - 8.0 * pos)) / 2.0).astype(np.int64)
+    start = i * (2 * n - i - 1) // 2
+    fix = pos < start
+    i[fix] -= 1
+    start = i * (2 * n - i - 1) // 2
+    fix = pos >= start + (n - 1 - i)
+    i[fix] += 1
+    start = i * (2 * n - i - 1) // 2
+    j = pos - start + i + 1
+    return i, j
+
+
+def erdos_renyi_add_edge_calls(n, i, j):
+    """add_edge sequence of the reference tests for given upper pairs (0-based
+    i<j, sorted by (i, j)): for each i: (i,i), then (i,j),(j,i) per neighbour."""
+    ei, ej = [], []
+    order = np.lexsort((j, i))
+    i, j = i[order], j[order]
+    k = 0
+    for v in range(n):
+        ei.append(v + 1); ej.append(v + 1)
+        while k < i.size and i[k] == v:
+            ei += [v + 1, j[k] + 1]; ej += [j[k] + 1, v + 1]
+            k += 1
+    return np.array(ei, np.int32), np.array(ej, np.int32)
+
+
+def erdos_renyi_csr(n, p=None, seed=7, shift=1.0, skew=False, weights="unit", return_pairs=False):
+    """A = L + shift*I on G(n, p) (p defaults to log2(n)/n).
+
+    weights="unit": L = D - Adj (test/eigensolver_test_lanczos.f90:100-110);
+    weights="random": edge weight z ~ U[0,1): A(i,j) = -z, A(i,i) += z
+    (test/solver_test_jacobi.f90:111-128, diagonal starts at `shift`).
+    skew=True adds the skew-symmetric perturbation +-(2z-1)/16 per edge
+    (:240-254) -> nonsymmetric operator for BiCGSTAB.
+    The build order of the tests makes every row's columns ascending
+    (smaller neighbours, the diagonal, larger neighbours).
+    """
+    rng = np.random.Generator(np.random.PCG64(seed))
+    if p is None:
+        p = np.log2(n) / n
+    i, j = _er_pairs(n, p, rng)
+    ne = i.size
+    w = np.ones(ne) if weights == "unit" else rng.random(ne)
+    rows = np.concatenate([i, j, np.arange(n)])
+    cols = np.concatenate([j, i, np.arange(n)])
+    deg_w = np.bincount(i, w, n) + np.bincount(j, w, n)
+    vals = np.concatenate([-w, -w, shift + deg_w])
+    if skew:
+        s = (2.0 * rng.random(ne) - 1.0) / 16.0
+        vals[:ne] += s
+        vals[ne:2 * ne] -= s
+    order = np.lexsort((cols, rows))
+    rows, cols, vals = rows[order], cols[order], vals[order]
+    ptr = np.concatenate([[1], 1 + np.cumsum(np.bincount(rows, minlength=n))]).astype(np.int32)
+    out = (ptr, (cols + 1).astype(np.int32), vals.astype(np.float64))
+    return out + ((i, j),) if return_pairs else out
+
+
+# --------------------------------------------------------------------------
+# P1 finite-element Laplacian on a perturbed structured triangulation
+# (BASELINE config 4; element matrices per examples/fem.f90:28-49)
+# --------------------------------------------------------------------------
+def fem_p1_csr(N, seed=2024, jitter=0.25):
+    """Stiffness matrix of -Laplace on an N x N vertex grid, each cell split
+    into two triangles along a seeded random diagonal, interior vertices
+    jittered by <= jitter*h; Dirichlet rows/columns replaced by identity.
+
+    Graph build order: loop elements n, add_edge(ele(i,n), ele(j,n)) for
+    j = 1..3, i = 1..3 (the same nesting as the assembly loop fem.f90:43-47);
+    values accumulated in that element order.  Returns (ptr, node, val).
+    """
+    rng = np.random.Generator(np.random.PCG64(seed))
+    h = 1.0 / (N - 1)
+    gx, gy = np.meshgrid(np.arange(N) * h, np.arange(N) * h, indexing="ij")
+    interior = np.zeros((N, N), bool)
+    interior[1:-1, 1:-1] = True
+    gx = gx + np.where(interior, (2 * rng.random((N, N)) - 1) * jitter * h, 0.0)
+    gy = gy + np.where(interior, (2 * rng.random((N, N)) - 1) * jitter * h, 0.0)
+    x = np.stack([gx.reshape(-1), gy.reshape(-1)])          # x(2, nv)
+    vid = np.arange(N * N).reshape(N, N)
+    a, b, c, d = vid[:-1, :-1].ravel(), vid[1:, :-1].ravel(), vid[1:, 1:].ravel(), vid[:-1, 1:].ravel()
+    flip = rng.random(a.size) < 0.5
+    t1 = np.where(flip[:, None], np.stack([a, b, d], 1), np.stack([a, b, c], 1))
+    t2 = np.where(flip[:, None], np.stack([b, c, d], 1), np.stack([a, c, d], 1))
+    ele = np.stack([t1, t2], 1).reshape(-1, 3)               # cell-major, 2 triangles each
+    # element matrices (fem.f90:31-41)
+    jj = ele[:, [1, 2, 0]]
+    kk = ele[:, [2, 0, 1]]
+    V1 = x[1, jj] - x[1, kk]
+    V2 = x[0, kk] - x[0, jj]
+    det = V1[:, 0] * V2[:, 1] - V2[:, 0] * V1[:, 1]
+    area = np.abs(det) / 2.0
+    AE = (0.25 / area)[:, None, None] * (V1[:, :, None] * V1[:, None, :] + V2[:, :, None] * V2[:, None, :])
+    # entry stream in assembly order: element n, j outer, i inner
+    I = ele[:, None, :].repeat(3, 1)        # [n, j, i] -> ele(i)
+    J = ele[:, :, None].repeat(3, 2)        # [n, j, i] -> ele(j)
+    Vv = AE.transpose(0, 2, 1)              # [n, j, i] -> AE(i, j)
+    I, J, Vv = I.reshape(-1), J.reshape(-1), Vv.reshape(-1)
+    nv = N * N
+    bnd = ~interior.reshape(-1)
+    # first-occurrence order per row == ll_graph insertion order
+    key = I.astype(np.int64) * nv + J
+    uniq, first, inv = np.unique(key, return_index=True, return_inverse=True)
+    order = np.lexsort((first, uniq // nv))                  # rows ascending, then first appearance
+    rank = np.empty_like(order)
+    rank[order] = np.arange(order.size)
+    vals = np.zeros(uniq.size)
+    np.add.at(vals, rank[inv], Vv)                           # sequential, element order
+    rows = (uniq // nv)[order]
+    cols = (uniq % nv)[order]
+    # Dirichlet: identity rows/columns on the boundary
+    vals = np.where(bnd[rows] | bnd[cols], np.where(rows == cols, 1.0, 0.0), vals)
+    ptr = np.concatenate([[1], 1 + np.cumsum(np.bincount(rows, minlength=nv))]).astype(np.int32)
+    return ptr, (cols + 1).astype(np.int32), vals.astype(np.float64)
