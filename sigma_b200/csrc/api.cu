@@ -50,11 +50,11 @@ static int dev_alloc(T **p, size_t count)
 }
 
 // upload the tile table of a CSR view
-static int upload_tiles(CsrView &v, const std::vector<int32_t> &tile_row)
+static int upload_tiles(CsrView &v, const std::vector<TileDesc> &tiles)
 {
-    v.ntiles = (int32_t)tile_row.size() - 1;
-    SIGB_CHECK(dev_alloc(&v.tile_row, tile_row.size()));
-    SIGB_CUDA(cudaMemcpyAsync(v.tile_row, tile_row.data(), sizeof(int32_t) * tile_row.size(),
+    v.ntiles = (int32_t)tiles.size();
+    SIGB_CHECK(dev_alloc(&v.tiles, tiles.size()));
+    SIGB_CUDA(cudaMemcpyAsync(v.tiles, tiles.data(), sizeof(TileDesc) * tiles.size(),
                               cudaMemcpyHostToDevice, ctx().stream));
     SIGB_CUDA(cudaStreamSynchronize(ctx().stream));
     return SIGB_OK;
@@ -64,7 +64,7 @@ static void free_view(CsrView &v)
 {
     cudaFree(v.ptr);
     cudaFree(v.node);
-    cudaFree(v.tile_row);
+    cudaFree(v.tiles);
     cudaFree(v.tiles_interior);
     cudaFree(v.tiles_boundary);
     v = CsrView();
@@ -98,7 +98,7 @@ static int ensure_graph_transposed(sigb_graph_t g)
     g->host_ptr_t.resize((size_t)ntargets + 1);
     SIGB_CUDA(cudaMemcpy(g->host_ptr_t.data(), ptr_t, sizeof(int32_t) * ((size_t)ntargets + 1),
                          cudaMemcpyDeviceToHost));
-    std::vector<int32_t> tiles;
+    std::vector<TileDesc> tiles;
     build_tiles_host(g->host_ptr_t.data(), ntargets, tiles);
     SIGB_CHECK(upload_tiles(t, tiles));
     g->has_transposed = true;
@@ -311,13 +311,14 @@ int sigb_cs_graph_create(int32_t n, int32_t m, const int32_t *ptr1, const int32_
     v.ncols = m;
     v.nnz = ne;
     cudaStream_t st = ctx().stream;
-    SIGB_CHECK(dev_alloc(&v.ptr, (size_t)n + 1));
-    SIGB_CHECK(dev_alloc(&v.node, (size_t)ne + 8));
+    SIGB_CHECK(dev_alloc(&v.ptr, (size_t)n + 1 + kPad));
+    SIGB_CHECK(fill_i32(v.ptr + n + 1, kPad, 1));
+    SIGB_CHECK(dev_alloc(&v.node, (size_t)ne + kPad));
     SIGB_CUDA(cudaMemcpyAsync(v.ptr, ptr1, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
     if (ne > 0)
         SIGB_CUDA(cudaMemcpyAsync(v.node, node1, sizeof(int32_t) * (size_t)ne, cudaMemcpyHostToDevice, st));
-    SIGB_CHECK(fill_i32(v.node + ne, 8, 1));
-    std::vector<int32_t> tiles;
+    SIGB_CHECK(fill_i32(v.node + ne, kPad, 1));
+    std::vector<TileDesc> tiles;
     build_tiles_host(ptr1, n, tiles);
     SIGB_CHECK(upload_tiles(v, tiles));
     if (g->kind == G_CSC) SIGB_CHECK(ensure_graph_transposed(g));

@@ -77,27 +77,36 @@ enum SpmvMode {
     MODE_ACC_INIT = 2    // z starts from y(i)       (csc_matvec_add order)
 };
 
+// One row tile of the streaming CSR kernel: rows [rs, re) and their stored
+// entries [ks, ke), all 0-based.  Tiles are built once on the host so the
+// kernel finds everything it needs about a tile in ONE 16-byte load instead of
+// chasing tile_row -> ptr -> data.
+struct TileDesc {
+    int32_t rs, re, ks, ke;
+};
+
 // CSR arrays exactly as the reference stores them (1-based) plus the row
 // tiling used by the streaming kernel.
 struct CsrView {
     int32_t nrows = 0, ncols = 0;
     int64_t nnz = 0;
-    int32_t *ptr = nullptr;       // nrows + 1, 1-based
+    int32_t *ptr = nullptr;       // nrows + 1 (+ pad), 1-based
     int32_t *node = nullptr;      // nnz (+ pad), 1-based column ids, stored order
-    int32_t *tile_row = nullptr;  // ntiles + 1 row offsets (0-based)
+    TileDesc *tiles = nullptr;    // ntiles descriptors
     int32_t ntiles = 0;
     // optional tile subsets (row-sharded operators): interior tiles touch no
     // halo column, boundary tiles do.
-    int32_t *tiles_interior = nullptr, *tiles_boundary = nullptr;
+    TileDesc *tiles_interior = nullptr, *tiles_boundary = nullptr;
     int32_t n_interior = 0, n_boundary = 0;
 };
 
-constexpr int kTileNnz = 2048;   // products staged per tile (16 KB of shared memory)
-// A tile's entry range is widened down to a 4-entry boundary so the node slice
-// can be read with aligned 128-bit loads; capping tiles at kTileNnz - 3 entries
-// keeps the widened range within kTileNnz.
+constexpr int kTileNnz = 2048;   // entries staged per tile
+// A tile's entry range is widened down to a 4-entry boundary so the slices
+// can be moved with aligned 16-byte transfers; capping tiles at kTileNnz - 3
+// entries keeps the widened range within kTileNnz.
 constexpr int kTileCap = kTileNnz - 3;
-constexpr int kTileRowsMax = 4096;
+constexpr int kTileRows = 512;   // rows per tile (their ptr slice is staged too)
+constexpr int kPad = 8;          // slack entries behind ptr / node / val arrays
 
 enum GraphKind { G_CSR = 0, G_CSC = 1, G_ELL = 2 };
 
@@ -153,8 +162,8 @@ int launch_ell_spmv(int32_t n, int32_t n_pad, int32_t max_d,
                     const int32_t *node_sm, const double *val_sm,
                     const double *x, double *y, SpmvMode mode,
                     const DotSpec &dot);
-int build_tiles_host(const int32_t *ptr1, int32_t nrows,
-                     std::vector<int32_t> &tile_row);
+int build_tiles_host(const int32_t *ptr1, int32_t nrows, std::vector<TileDesc> &tiles);
+int spmv_variant();  // SIGB_SPMV_VARIANT: 2 = TMA bulk-copy pipeline (default), 1 = register path
 
 // ---------------------------------------------------------------------------
 // transpose.cu

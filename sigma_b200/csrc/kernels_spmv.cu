@@ -11,11 +11,15 @@
 // bicgstab_solvers.f90:159-160,163-164, eigensolver.f90:68-69).
 //
 // CSR kernel ("stream" layout).  Rows are grouped on the host into tiles of at
-// most kTileNnz stored entries.  A CTA walks tiles round-robin; per tile
-//   phase 1: the tile's slice of node/val is read with 128-bit streaming loads
-//            (perfectly coalesced, independent of row lengths), each entry is
-//            multiplied with its gathered x and the ROUNDED product is parked
-//            in shared memory;
+// most kTileCap stored entries and kTileRows rows.  A persistent CTA walks its
+// tiles round-robin; per tile
+//   stage  : the tile's slices of val / node / ptr are brought into shared
+//            memory by the TMA engine (cp.async.bulk, 1-D, completion on an
+//            mbarrier), double-buffered: the copy of tile t+1 is in flight
+//            while tile t is processed, and no register or thread is tied up
+//            by the HBM stream;
+//   phase 1: every entry is multiplied with its gathered x (L1/L2 hits) and
+//            the ROUNDED product replaces the value in shared memory;
 //   phase 2: one thread per row adds that row's products in STORED order.
 // Because the product is rounded before it is added and the adds run in stored
 // order, every y(i) is bit-identical to the reference's serial loop
@@ -26,6 +30,11 @@
 // HBM traffic per SpMV = 12 B/entry + 4 B/row (ptr) + 8 B/row (x, compulsory)
 // + 8 B/row (y) -- the algorithmic minimum; x re-reads
 // are served by L1/L2.
+//
+// SIGB_SPMV_VARIANT=1 selects the older register-staged kernel (128-bit
+// ld.global.nc loads into registers) kept for A/B measurements.
+#include <stdlib.h>
+
 #include "device_utils.cuh"
 
 namespace sigb {
@@ -33,12 +42,11 @@ namespace sigb {
 namespace {
 
 struct CsrKernelArgs {
-    const int32_t *ptr;       // 1-based, nrows + 1
-    const int32_t *node;      // 1-based
-    const double *val;
-    const int32_t *tile_row;  // ntiles + 1
-    const int32_t *tile_list; // optional indirection (subset launch) or null
-    int32_t ntiles;           // tiles this launch covers
+    const int32_t *ptr;       // 1-based, nrows + 1 (+ pad)
+    const int32_t *node;      // 1-based (+ pad)
+    const double *val;        // (+ pad)
+    const TileDesc *tiles;
+    int32_t ntiles;
     const double *x1;         // x - 1 : indexable by 1-based column id
     double *y;
     const double *u;          // dot vector
@@ -49,6 +57,214 @@ struct CsrKernelArgs {
     const double *scale;      // optional per-row scaling of the result
 };
 
+__device__ __forceinline__ int4 load_desc(const TileDesc *t)
+{
+    return __ldg(reinterpret_cast<const int4 *>(t));
+}
+
+// ---- mbarrier / bulk-copy (TMA) primitives ---------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// shared-memory stage: val | node | ptr slices of one tile
+constexpr int kStageVal = kTileNnz * 8;
+constexpr int kStageNode = kTileNnz * 4;
+constexpr int kStagePtr = (kTileRows + 8) * 4;
+constexpr int kStageBytes = (kStageVal + kStageNode + kStagePtr + 127) & ~127;
+
+__device__ __forceinline__ bool tile_staged(const int4 &d)
+{
+    return (d.w - d.z) <= kTileCap;  // else: one long row, streamed directly
+}
+
+template <int MODE, int NDOT>
+__device__ __forceinline__ void emit_row(const CsrKernelArgs &a, int r, double z, double *acc)
+{
+    if (MODE == MODE_ADD_AFTER) z = add(a.y[r], z);
+    if (MODE == MODE_SET && a.scale) z = mul(a.scale[r], z);
+    a.y[r] = z;
+    if (NDOT >= 1) acc[0] = add(acc[0], mul(a.u[r], z));
+    if (NDOT >= 2) acc[NDOT > 1 ? 1 : 0] = add(acc[NDOT > 1 ? 1 : 0], mul(z, z));
+}
+
+// one row longer than a tile: CTA-wide fixed-tree reduction, direct loads
+template <int MODE, int NDOT>
+__device__ __forceinline__ void long_row(const CsrKernelArgs &a, const int4 &d, double *acc)
+{
+    __shared__ double smr[1][kThreads / 32];
+    double s[1] = {0.0};
+    for (int k = d.z + threadIdx.x; k < d.w; k += kThreads)
+        s[0] = add(s[0], mul(a.val[k], __ldg(a.x1 + a.node[k])));
+    block_tree<1>(s, smr);
+    if (threadIdx.x == 0) {
+        double z = s[0];
+        if (MODE == MODE_ACC_INIT) z = add(a.y[d.x], z);
+        emit_row<MODE, NDOT>(a, d.x, z, acc);
+    }
+    __syncthreads();
+}
+
+template <int NDOT>
+__device__ __forceinline__ void finish_dots(const CsrKernelArgs &a, double *acc)
+{
+    if (NDOT == 1) {
+        double *const out[1] = {a.out0};
+        double v[1] = {acc[0]};
+        grid_reduce<1>(v, a.partials, a.ticket, out);
+    } else if (NDOT == 2) {
+        double *const out[2] = {a.out0, a.out1};
+        double v[2] = {acc[0], acc[NDOT > 1 ? 1 : 0]};
+        grid_reduce<2>(v, a.partials, a.ticket, out);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// variant 2 (default): TMA bulk-copy, double-buffered
+// ---------------------------------------------------------------------------
+template <int MODE, int NDOT>
+__global__ void __launch_bounds__(kThreads)
+csr_tma_kernel(const CsrKernelArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t mbar[2];
+    if (a.skip_flag != nullptr && *a.skip_flag != 0) return;
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    double acc[NDOT > 0 ? NDOT : 1];
+#pragma unroll
+    for (int d = 0; d < (NDOT > 0 ? NDOT : 1); d++) acc[d] = 0.0;
+
+    // thread 0 is the producer: it programs the TMA engine for one tile
+    auto issue = [&](int stage, const int4 &d) {
+        unsigned char *base = smem + stage * kStageBytes;
+        const int ka = d.z & ~3, ra = d.x & ~3;
+        const uint32_t cnt = (uint32_t)((d.w - ka + 3) & ~3);
+        const uint32_t rcnt = (uint32_t)((d.y + 1 - ra + 3) & ~3);
+        mbar_expect_tx(&mbar[stage], cnt * 12u + rcnt * 4u);
+        bulk_g2s(base, a.val + ka, cnt * 8u, &mbar[stage]);
+        bulk_g2s(base + kStageVal, a.node + ka, cnt * 4u, &mbar[stage]);
+        bulk_g2s(base + kStageVal + kStageNode, a.ptr + ra, rcnt * 4u, &mbar[stage]);
+    };
+
+    int t = blockIdx.x;
+    int4 d_cur = make_int4(0, 0, 0, 0), d_next = make_int4(0, 0, 0, 0);
+    if (t < a.ntiles) d_cur = load_desc(a.tiles + t);
+    if (t + (int)gridDim.x < a.ntiles) d_next = load_desc(a.tiles + t + gridDim.x);
+    unsigned sidx = 0;  // staged tiles consumed so far (identical in all threads)
+    if (tid == 0 && t < a.ntiles && tile_staged(d_cur)) issue(0, d_cur);
+
+    for (; t < a.ntiles; t += gridDim.x) {
+        const int tn = t + gridDim.x, tnn = tn + gridDim.x;
+        const bool have_next = tn < a.ntiles;
+        int4 d_next2 = make_int4(0, 0, 0, 0);
+        if (tnn < a.ntiles) d_next2 = load_desc(a.tiles + tnn);  // two tiles ahead, off the critical path
+        const bool staged = tile_staged(d_cur);
+        const unsigned sidx_after = sidx + (staged ? 1u : 0u);
+        if (tid == 0 && have_next && tile_staged(d_next)) issue((int)(sidx_after & 1u), d_next);
+
+        if (staged) {
+            const int stage = (int)(sidx & 1u);
+            unsigned char *base = smem + stage * kStageBytes;
+            double *sval = reinterpret_cast<double *>(base);
+            const int32_t *snode = reinterpret_cast<const int32_t *>(base + kStageVal);
+            const int32_t *sptr = reinterpret_cast<const int32_t *>(base + kStageVal + kStageNode);
+            const int rs = d_cur.x, re = d_cur.y, ks = d_cur.z, ke = d_cur.w;
+            const int ka = ks & ~3, ra = rs & ~3;
+            mbar_wait(&mbar[stage], (sidx >> 1) & 1u);
+            // ---- phase 1: products, in place --------------------------------
+            // (entries before ks belong to the previous tile and hold valid
+            // columns, so every gather below is in range)
+            const int cnt = ke - ka;
+            int c[kTileNnz / kThreads];
+            double v[kTileNnz / kThreads];
+#pragma unroll
+            for (int i = 0; i < kTileNnz / kThreads; i++) {
+                const int k = tid + i * kThreads;
+                c[i] = (k < cnt) ? snode[k] : 1;
+                v[i] = (k < cnt) ? sval[k] : 0.0;
+            }
+            double xv[kTileNnz / kThreads];
+#pragma unroll
+            for (int i = 0; i < kTileNnz / kThreads; i++) xv[i] = __ldg(a.x1 + c[i]);
+#pragma unroll
+            for (int i = 0; i < kTileNnz / kThreads; i++) {
+                const int k = tid + i * kThreads;
+                if (k < cnt) sval[k] = mul(v[i], xv[i]);
+            }
+            __syncthreads();
+            // ---- phase 2: per-row sums in stored order ----------------------
+            for (int r = rs + tid; r < re; r += kThreads) {
+                const int b = sptr[r - ra] - 1 - ka, e = sptr[r + 1 - ra] - 1 - ka;
+                double z = (MODE == MODE_ACC_INIT) ? a.y[r] : 0.0;
+                for (int k = b; k < e; k++) z = add(z, sval[k]);
+                emit_row<MODE, NDOT>(a, r, z, acc);
+            }
+            // the stage is overwritten by the async proxy next: order our
+            // generic-proxy accesses before it
+            fence_proxy_async();
+            __syncthreads();
+        } else {
+            long_row<MODE, NDOT>(a, d_cur, acc);
+        }
+        sidx = sidx_after;
+        d_cur = d_next;
+        d_next = d_next2;
+    }
+    finish_dots<NDOT>(a, acc);
+}
+
+// ---------------------------------------------------------------------------
+// variant 1: register-staged 128-bit streaming loads
+// ---------------------------------------------------------------------------
 template <int MODE, int NDOT>
 __global__ void __launch_bounds__(kThreads)
 csr_stream_kernel(const CsrKernelArgs a)
@@ -61,73 +277,71 @@ csr_stream_kernel(const CsrKernelArgs a)
 #pragma unroll
     for (int d = 0; d < (NDOT > 0 ? NDOT : 1); d++) acc[d] = 0.0;
 
-    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
-        const int tile = a.tile_list ? a.tile_list[t] : t;
-        const int rs = a.tile_row[tile], re = a.tile_row[tile + 1];
-        const int ks = a.ptr[rs] - 1, ke = a.ptr[re] - 1;  // 0-based entry range
-        const int len = ke - ks;
-
-        if (len <= kTileCap) {
-            // ---- phase 1: stream the tile, stage rounded products ----------
-            const int ka = ks & ~3;  // 16-byte aligned start of the node slice
+    int t = blockIdx.x;
+    int4 d_cur = make_int4(0, 0, 0, 0);
+    if (t < a.ntiles) d_cur = load_desc(a.tiles + t);
+    for (; t < a.ntiles; t += gridDim.x) {
+        int4 d_next = make_int4(0, 0, 0, 0);
+        if (t + (int)gridDim.x < a.ntiles) d_next = load_desc(a.tiles + t + gridDim.x);
+        const int rs = d_cur.x, re = d_cur.y, ks = d_cur.z, ke = d_cur.w;
+        if (tile_staged(d_cur)) {
+            const int ka = ks & ~3;
+            constexpr int NIT = kTileNnz / (4 * kThreads);
+            // row extents for phase 2, requested before the big loads
+            int pb[2], pe[2];
 #pragma unroll
-            for (int it = 0; it < kTileNnz / (4 * kThreads); it++) {
+            for (int i = 0; i < 2; i++) {
+                const int r = rs + tid + i * kThreads;
+                pb[i] = (r < re) ? a.ptr[r] : 1;
+                pe[i] = (r < re) ? a.ptr[r + 1] : 1;
+            }
+            int4 c[NIT];
+            double2 v01[NIT], v23[NIT];
+#pragma unroll
+            for (int it = 0; it < NIT; it++) {
                 const int j = ka + 4 * (tid + it * kThreads);
                 if (j < ke) {
-                    const int4 c = ld_stream_i4(a.node + j);
-                    const double2 v01 = ld_stream_d2(a.val + j);
-                    const double2 v23 = ld_stream_d2(a.val + j + 2);
-                    double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
-                    if (j >= ks) p0 = mul(v01.x, __ldg(a.x1 + c.x));
-                    if (j + 1 >= ks && j + 1 < ke) p1 = mul(v01.y, __ldg(a.x1 + c.y));
-                    if (j + 2 >= ks && j + 2 < ke) p2 = mul(v23.x, __ldg(a.x1 + c.z));
-                    if (j + 3 >= ks && j + 3 < ke) p3 = mul(v23.y, __ldg(a.x1 + c.w));
+                    c[it] = ld_stream_i4(a.node + j);
+                    v01[it] = ld_stream_d2(a.val + j);
+                    v23[it] = ld_stream_d2(a.val + j + 2);
+                } else {
+                    c[it] = make_int4(1, 1, 1, 1);
+                    v01[it] = make_double2(0.0, 0.0);
+                    v23[it] = make_double2(0.0, 0.0);
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < NIT; it++) {
+                const int j = ka + 4 * (tid + it * kThreads);
+                if (j < ke) {
+                    // entries before ks belong to the previous tile (valid columns);
+                    // entries past ke are padding (column 1): all gathers are safe
+                    const double p0 = mul(v01[it].x, __ldg(a.x1 + c[it].x));
+                    const double p1 = mul(v01[it].y, __ldg(a.x1 + c[it].y));
+                    const double p2 = mul(v23[it].x, __ldg(a.x1 + c[it].z));
+                    const double p3 = mul(v23[it].y, __ldg(a.x1 + c[it].w));
                     double2 *dst = reinterpret_cast<double2 *>(prod + (j - ka));
                     dst[0] = make_double2(p0, p1);
                     dst[1] = make_double2(p2, p3);
                 }
             }
             __syncthreads();
-            // ---- phase 2: per-row sums in stored order ----------------------
-            for (int r = rs + tid; r < re; r += kThreads) {
-                const int b = a.ptr[r] - 1 - ka, e = a.ptr[r + 1] - 1 - ka;
-                double z = (MODE == MODE_ACC_INIT) ? a.y[r] : 0.0;
-                for (int k = b; k < e; k++) z = add(z, prod[k]);
-                if (MODE == MODE_ADD_AFTER) z = add(a.y[r], z);
-                if (MODE == MODE_SET && a.scale) z = mul(a.scale[r], z);
-                a.y[r] = z;
-                if (NDOT >= 1) acc[0] = add(acc[0], mul(a.u[r], z));
-                if (NDOT >= 2) acc[NDOT > 1 ? 1 : 0] = add(acc[NDOT > 1 ? 1 : 0], mul(z, z));
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const int r = rs + tid + i * kThreads;
+                if (r < re) {
+                    double z = (MODE == MODE_ACC_INIT) ? a.y[r] : 0.0;
+                    for (int k = pb[i] - 1 - ka; k < pe[i] - 1 - ka; k++) z = add(z, prod[k]);
+                    emit_row<MODE, NDOT>(a, r, z, acc);
+                }
             }
             __syncthreads();
         } else {
-            // ---- one long row: CTA-wide fixed-tree reduction -----------------
-            __shared__ double smr[1][kThreads / 32];
-            double s[1] = {0.0};
-            for (int k = ks + tid; k < ke; k += kThreads)
-                s[0] = add(s[0], mul(a.val[k], __ldg(a.x1 + a.node[k])));
-            block_tree<1>(s, smr);
-            if (tid == 0) {
-                double z = s[0];
-                if (MODE == MODE_ACC_INIT || MODE == MODE_ADD_AFTER) z = add(a.y[rs], z);
-                if (MODE == MODE_SET && a.scale) z = mul(a.scale[rs], z);
-                a.y[rs] = z;
-                if (NDOT >= 1) acc[0] = add(acc[0], mul(a.u[rs], z));
-                if (NDOT >= 2) acc[NDOT > 1 ? 1 : 0] = add(acc[NDOT > 1 ? 1 : 0], mul(z, z));
-            }
-            __syncthreads();
+            long_row<MODE, NDOT>(a, d_cur, acc);
         }
+        d_cur = d_next;
     }
-
-    if (NDOT == 1) {
-        double *const out[1] = {a.out0};
-        double v[1] = {acc[0]};
-        grid_reduce<1>(v, a.partials, a.ticket, out);
-    } else if (NDOT == 2) {
-        double *const out[2] = {a.out0, a.out1};
-        double v[2] = {acc[0], acc[NDOT > 1 ? 1 : 0]};
-        grid_reduce<2>(v, a.partials, a.ticket, out);
-    }
+    finish_dots<NDOT>(a, acc);
 }
 
 // ---------------------------------------------------------------------------
@@ -174,10 +388,16 @@ ell_kernel(const EllKernelArgs a)
                 c[k] = ld_stream_i2(a.node + (size_t)k * a.n_pad + i);
                 v[k] = ld_stream_d2(a.val + (size_t)k * a.n_pad + i);
             }
+            double x0[W > 0 ? W : 1], x1v[W > 0 ? W : 1];
 #pragma unroll
             for (int k = 0; k < W; k++) {
-                z0 = add(z0, mul(v[k].x, __ldg(a.x1 + c[k].x)));
-                z1 = add(z1, mul(v[k].y, __ldg(a.x1 + c[k].y)));
+                x0[k] = __ldg(a.x1 + c[k].x);
+                x1v[k] = __ldg(a.x1 + c[k].y);
+            }
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                z0 = add(z0, mul(v[k].x, x0[k]));
+                z1 = add(z1, mul(v[k].y, x1v[k]));
             }
         } else {
             for (int k = 0; k < a.max_d; k++) {
@@ -234,12 +454,20 @@ int occupancy_grid(K kernel, size_t smem, int *grid_out)
 template <int MODE, int NDOT>
 int launch_csr_t(const CsrKernelArgs &a, cudaStream_t st)
 {
-    const size_t smem = (size_t)kTileNnz * sizeof(double);
     int grid = 0;
-    SIGB_CHECK(occupancy_grid(csr_stream_kernel<MODE, NDOT>, smem, &grid));
-    if (a.ntiles < grid) grid = a.ntiles;
-    if (grid < 1) grid = 1;
-    csr_stream_kernel<MODE, NDOT><<<grid, kThreads, smem, st>>>(a);
+    if (spmv_variant() == 1) {
+        const size_t smem = (size_t)kTileNnz * sizeof(double);
+        SIGB_CHECK(occupancy_grid(csr_stream_kernel<MODE, NDOT>, smem, &grid));
+        if (a.ntiles < grid) grid = a.ntiles;
+        if (grid < 1) grid = 1;
+        csr_stream_kernel<MODE, NDOT><<<grid, kThreads, smem, st>>>(a);
+    } else {
+        const size_t smem = 2 * (size_t)kStageBytes;
+        SIGB_CHECK(occupancy_grid(csr_tma_kernel<MODE, NDOT>, smem, &grid));
+        if (a.ntiles < grid) grid = a.ntiles;
+        if (grid < 1) grid = 1;
+        csr_tma_kernel<MODE, NDOT><<<grid, kThreads, smem, st>>>(a);
+    }
     count_launch();
     SIGB_CUDA(cudaGetLastError());
     return SIGB_OK;
@@ -277,18 +505,32 @@ int launch_ell_w(const EllKernelArgs &a, cudaStream_t st)
 
 }  // namespace
 
-// Greedy row tiling: consecutive rows while the tile holds <= kTileCap entries
-// and <= kTileRowsMax rows; a longer row gets a tile of its own.
-int build_tiles_host(const int32_t *ptr1, int32_t nrows, std::vector<int32_t> &tile_row)
+int spmv_variant()
 {
-    tile_row.clear();
-    tile_row.push_back(0);
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SIGB_SPMV_VARIANT");
+        v = (e && atoi(e) == 1) ? 1 : 2;
+    }
+    return v;
+}
+
+// Greedy row tiling: consecutive rows while the tile holds <= kTileCap entries
+// and <= kTileRows rows; a longer row gets a tile of its own.
+int build_tiles_host(const int32_t *ptr1, int32_t nrows, std::vector<TileDesc> &tiles)
+{
+    tiles.clear();
     int32_t s = 0;
     while (s < nrows) {
         int32_t e = s + 1;
         const int64_t base = ptr1[s];
-        while (e < nrows && (int64_t)ptr1[e + 1] - base <= kTileCap && e - s < kTileRowsMax) e++;
-        tile_row.push_back(e);
+        while (e < nrows && (int64_t)ptr1[e + 1] - base <= kTileCap && e - s < kTileRows) e++;
+        TileDesc d;
+        d.rs = s;
+        d.re = e;
+        d.ks = ptr1[s] - 1;
+        d.ke = ptr1[e] - 1;
+        tiles.push_back(d);
         s = e;
     }
     return SIGB_OK;
@@ -302,11 +544,10 @@ int launch_csr_spmv(const CsrView &A, const double *val, const double *x, double
     a.ptr = A.ptr;
     a.node = A.node;
     a.val = val;
-    a.tile_row = A.tile_row;
-    a.tile_list = nullptr;
+    a.tiles = A.tiles;
     a.ntiles = A.ntiles;
-    if (which == 1) { a.tile_list = A.tiles_interior; a.ntiles = A.n_interior; }
-    if (which == 2) { a.tile_list = A.tiles_boundary; a.ntiles = A.n_boundary; }
+    if (which == 1) { a.tiles = A.tiles_interior; a.ntiles = A.n_interior; }
+    if (which == 2) { a.tiles = A.tiles_boundary; a.ntiles = A.n_boundary; }
     a.x1 = x - 1;
     a.y = y;
     a.u = dot.u;

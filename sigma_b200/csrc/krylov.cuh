@@ -39,24 +39,42 @@ struct KState {
 
 // ---------------------------------------------------------------------------
 // generic fused element-wise kernel: Op supplies
-//   static constexpr int ND            number of dot products produced
+//   static constexpr int ND, NIN       dot products produced / values read per element
 //   __device__ bool begin()            scalar prologue; false => whole grid exits
-//   __device__ void apply(i, acc)      element i
+//   __device__ void load(i, in)        read element i's inputs (no stores)
+//   __device__ void compute(i, in, acc) arithmetic + stores + dot contributions
 //   __device__ double *out(d)          where dot d goes
+// Loads of kUnroll elements are issued back to back before any arithmetic or
+// store, so each thread keeps kUnroll * NIN independent 8-byte requests in
+// flight (every request is a fully coalesced 256-byte warp access).
 // ---------------------------------------------------------------------------
+constexpr int kUnroll = 4;
+
 template <class Op>
 __global__ void __launch_bounds__(kThreads)
 ew_kernel(Op op, int64_t n, double *partials, unsigned *ticket)
 {
     if (!op.begin()) return;
     constexpr int ND = Op::ND;
+    constexpr int NIN = Op::NIN > 0 ? Op::NIN : 1;
     double acc[ND > 0 ? ND : 1];
 #pragma unroll
     for (int d = 0; d < (ND > 0 ? ND : 1); d++) acc[d] = 0.0;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
-#pragma unroll 4
-    for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += stride)
-        op.apply(i, acc);
+    for (int64_t base = blockIdx.x * (int64_t)kThreads + threadIdx.x; base < n;
+         base += stride * kUnroll) {
+        double in[kUnroll][NIN];
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const int64_t i = base + u * stride;
+            if (i < n) op.load(i, in[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const int64_t i = base + u * stride;
+            if (i < n) op.compute(i, in[u], acc);
+        }
+    }
     if constexpr (ND == 1) {
         double *const out[1] = {op.out(0)};
         double v[1] = {acc[0]};

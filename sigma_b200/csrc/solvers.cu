@@ -25,13 +25,20 @@ struct CgInitOp {
     const double *__restrict__ b, *__restrict__ q, *__restrict__ idiag;
     double *__restrict__ r, *__restrict__ p, *__restrict__ z;
     KState *st;
+    static constexpr int NIN = 3;
     __device__ bool begin() { return true; }
-    __device__ void apply(int64_t i, double *acc)
+    __device__ void load(int64_t i, double *in)
     {
-        const double ri = sub(b[i], q[i]);
+        in[0] = b[i];
+        in[1] = q[i];
+        if (idiag) in[2] = idiag[i];
+    }
+    __device__ void compute(int64_t i, const double *in, double *acc)
+    {
+        const double ri = sub(in[0], in[1]);
         r[i] = ri;
         double zi = ri;
-        if (idiag) { zi = mul(idiag[i], ri); z[i] = zi; }
+        if (idiag) { zi = mul(in[2], ri); z[i] = zi; }
         p[i] = zi;
         acc[0] = add(acc[0], mul(ri, zi));
     }
@@ -66,13 +73,22 @@ struct CgUpdateOp {
         alpha = st->rr[par] / st->pq;   // alpha = res2 / dpr
         return true;
     }
-    __device__ void apply(int64_t i, double *acc)
+    static constexpr int NIN = 5;
+    __device__ void load(int64_t i, double *in)
     {
-        x[i] = add(x[i], mul(alpha, p[i]));
-        const double ri = sub(r[i], mul(alpha, q[i]));
+        in[0] = x[i];
+        in[1] = p[i];
+        in[2] = r[i];
+        in[3] = q[i];
+        if (idiag) in[4] = idiag[i];
+    }
+    __device__ void compute(int64_t i, const double *in, double *acc)
+    {
+        x[i] = add(in[0], mul(alpha, in[1]));
+        const double ri = sub(in[2], mul(alpha, in[3]));
         r[i] = ri;
         double zi = ri;
-        if (idiag) { zi = mul(idiag[i], ri); z[i] = zi; }
+        if (idiag) { zi = mul(in[4], ri); z[i] = zi; }
         acc[0] = add(acc[0], mul(ri, zi));
     }
     __device__ double *out(int) { return &st->rr[par ^ 1]; }
@@ -106,7 +122,9 @@ struct CgDirectionOp {
         }
         return true;
     }
-    __device__ void apply(int64_t i, double *) { p[i] = add(rz[i], mul(beta, p[i])); }
+    static constexpr int NIN = 2;
+    __device__ void load(int64_t i, double *in) { in[0] = rz[i]; in[1] = p[i]; }
+    __device__ void compute(int64_t i, const double *in, double *) { p[i] = add(in[0], mul(beta, in[1])); }
     __device__ double *out(int) { return nullptr; }
 };
 
@@ -121,11 +139,18 @@ struct BicgInitOp {
     const double *__restrict__ b, *__restrict__ q, *__restrict__ idiag;
     double *__restrict__ r, *__restrict__ r0, *__restrict__ v, *__restrict__ p, *__restrict__ z;
     KState *st;
+    static constexpr int NIN = 3;
     __device__ bool begin() { return true; }
-    __device__ void apply(int64_t i, double *acc)
+    __device__ void load(int64_t i, double *in)
     {
-        double ri = sub(b[i], q[i]);
-        if (idiag) { z[i] = ri; ri = mul(idiag[i], ri); }
+        in[0] = b[i];
+        in[1] = q[i];
+        if (idiag) in[2] = idiag[i];
+    }
+    __device__ void compute(int64_t i, const double *in, double *acc)
+    {
+        double ri = sub(in[0], in[1]);
+        if (idiag) { z[i] = ri; ri = mul(in[2], ri); }
         r0[i] = ri;
         r[i] = ri;
         v[i] = 0.0;
@@ -198,9 +223,11 @@ struct BicgDirectionOp {
         beta = st->rho[cur] / st->rho[prev] * st->alpha[prev] / omega_old;
         return true;
     }
-    __device__ void apply(int64_t i, double *)
+    static constexpr int NIN = 3;
+    __device__ void load(int64_t i, double *in) { in[0] = r[i]; in[1] = p[i]; in[2] = v[i]; }
+    __device__ void compute(int64_t i, const double *in, double *)
     {
-        p[i] = add(r[i], mul(beta, sub(p[i], mul(omega_old, v[i]))));
+        p[i] = add(in[0], mul(beta, sub(in[1], mul(omega_old, in[2]))));
     }
     __device__ double *out(int) { return nullptr; }
 };
@@ -220,7 +247,9 @@ struct BicgSOp {
         if (first_thread()) st->alpha[par] = alpha;
         return true;
     }
-    __device__ void apply(int64_t i, double *) { s[i] = sub(r[i], mul(alpha, v[i])); }
+    static constexpr int NIN = 2;
+    __device__ void load(int64_t i, double *in) { in[0] = r[i]; in[1] = v[i]; }
+    __device__ void compute(int64_t i, const double *in, double *) { s[i] = sub(in[0], mul(alpha, in[1])); }
     __device__ double *out(int) { return nullptr; }
 };
 
@@ -243,14 +272,23 @@ struct BicgUpdateOp {
         if (first_thread()) st->omega[par] = omega;
         return true;
     }
-    __device__ void apply(int64_t i, double *acc)
+    static constexpr int NIN = 5;
+    __device__ void load(int64_t i, double *in)
     {
-        const double si = s[i];
-        x[i] = add(add(x[i], mul(alpha, p[i])), mul(omega, si));
-        const double ri = sub(si, mul(omega, t[i]));
+        in[0] = s[i];
+        in[1] = x[i];
+        in[2] = p[i];
+        in[3] = t[i];
+        in[4] = r0[i];
+    }
+    __device__ void compute(int64_t i, const double *in, double *acc)
+    {
+        const double si = in[0];
+        x[i] = add(add(in[1], mul(alpha, in[2])), mul(omega, si));
+        const double ri = sub(si, mul(omega, in[3]));
         r[i] = ri;
         acc[0] = add(acc[0], mul(ri, ri));
-        acc[1] = add(acc[1], mul(r0[i], ri));
+        acc[1] = add(acc[1], mul(in[4], ri));
     }
     __device__ double *out(int d) { return d == 0 ? &st->rr[par ^ 1] : &st->rho[par ^ 1]; }
 };
@@ -264,8 +302,10 @@ struct JacobiApplyOp {
     static constexpr int ND = 0;
     const double *__restrict__ idiag, *__restrict__ b;
     double *__restrict__ x;
+    static constexpr int NIN = 2;
     __device__ bool begin() { return true; }
-    __device__ void apply(int64_t i, double *) { x[i] = mul(idiag[i], b[i]); }
+    __device__ void load(int64_t i, double *in) { in[0] = idiag[i]; in[1] = b[i]; }
+    __device__ void compute(int64_t i, const double *in, double *) { x[i] = mul(in[0], in[1]); }
     __device__ double *out(int) { return nullptr; }
 };
 
@@ -308,8 +348,10 @@ struct DotOp {
     static constexpr int ND = 1;
     const double *__restrict__ a, *__restrict__ b;
     double *o;
+    static constexpr int NIN = 2;
     __device__ bool begin() { return true; }
-    __device__ void apply(int64_t i, double *acc) { acc[0] = add(acc[0], mul(a[i], b[i])); }
+    __device__ void load(int64_t i, double *in) { in[0] = a[i]; in[1] = b[i]; }
+    __device__ void compute(int64_t, const double *in, double *acc) { acc[0] = add(acc[0], mul(in[0], in[1])); }
     __device__ double *out(int) { return o; }
 };
 
@@ -333,7 +375,9 @@ struct ScaleOp {
         }
         return true;
     }
-    __device__ void apply(int64_t i, double *) { dst[i] = src[i] / d; }
+    static constexpr int NIN = 1;
+    __device__ void load(int64_t i, double *in) { in[0] = src[i]; }
+    __device__ void compute(int64_t i, const double *in, double *) { dst[i] = in[0] / d; }
     __device__ double *out(int) { return nullptr; }
 };
 
@@ -353,12 +397,20 @@ struct LanczosRecurOp {
         beta = qim1 ? *beta_p : 0.0;
         return true;
     }
-    __device__ void apply(int64_t i, double *acc)
+    static constexpr int NIN = 4;
+    __device__ void load(int64_t i, double *in)
     {
-        double wi = sub(w[i], mul(alpha, qi[i]));
-        if (qim1) wi = sub(wi, mul(beta, qim1[i]));
+        in[0] = w[i];
+        in[1] = qi[i];
+        if (qim1) in[2] = qim1[i];
+        if (nxt) in[3] = nxt[i];
+    }
+    __device__ void compute(int64_t i, const double *in, double *acc)
+    {
+        double wi = sub(in[0], mul(alpha, in[1]));
+        if (qim1) wi = sub(wi, mul(beta, in[2]));
         w[i] = wi;
-        acc[0] = add(acc[0], mul(nxt ? nxt[i] : wi, wi));
+        acc[0] = add(acc[0], mul(nxt ? in[3] : wi, wi));
     }
     __device__ double *out(int) { return o; }
 };
@@ -372,11 +424,18 @@ struct LanczosOrthoOp {
     double *o;
     double c;
     __device__ bool begin() { c = *c_p; return true; }
-    __device__ void apply(int64_t i, double *acc)
+    static constexpr int NIN = 3;
+    __device__ void load(int64_t i, double *in)
     {
-        const double wi = sub(w[i], mul(c, qk[i]));
+        in[0] = w[i];
+        in[1] = qk[i];
+        if (nxt) in[2] = nxt[i];
+    }
+    __device__ void compute(int64_t i, const double *in, double *acc)
+    {
+        const double wi = sub(in[0], mul(c, in[1]));
         w[i] = wi;
-        acc[0] = add(acc[0], mul(nxt ? nxt[i] : wi, wi));
+        acc[0] = add(acc[0], mul(nxt ? in[2] : wi, wi));
     }
     __device__ double *out(int) { return o; }
 };
@@ -396,8 +455,10 @@ struct RandomOp {
     double *__restrict__ q;
     uint64_t seed;
     int64_t offset;  // global index of element 0
+    static constexpr int NIN = 0;
     __device__ bool begin() { return true; }
-    __device__ void apply(int64_t i, double *)
+    __device__ void load(int64_t, double *) {}
+    __device__ void compute(int64_t i, const double *, double *)
     {
         const uint64_t h = splitmix64(seed ^ splitmix64((uint64_t)(i + offset)));
         const double u = (double)(h >> 11) * (1.0 / 9007199254740992.0);

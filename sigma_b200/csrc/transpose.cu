@@ -320,7 +320,8 @@ int device_transpose_cs(const int32_t *ptr1, const int32_t *node1, int32_t nline
     cudaStream_t st = ctx().stream;
     int32_t *cnt = nullptr, *ptr_t = nullptr, *node_t = nullptr, *perm = nullptr;
     SIGB_CUDA(cudaMalloc(&cnt, sizeof(int32_t) * ((size_t)ntargets + 1)));
-    SIGB_CUDA(cudaMalloc(&ptr_t, sizeof(int32_t) * ((size_t)ntargets + 1)));
+    SIGB_CUDA(cudaMalloc(&ptr_t, sizeof(int32_t) * ((size_t)ntargets + 1 + kPad)));
+    SIGB_CHECK(fill_i32(ptr_t + ntargets + 1, kPad, 1));
     SIGB_CUDA(cudaMalloc(&node_t, sizeof(int32_t) * ((size_t)ne + 8)));
     SIGB_CUDA(cudaMalloc(&perm, sizeof(int32_t) * ((size_t)ne + 8)));
     SIGB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * ((size_t)ntargets + 1), st));
@@ -356,7 +357,8 @@ int device_transpose_ell(const int32_t *node_sm, int32_t n, int32_t n_pad, int32
     const int64_t ne = (int64_t)n * max_d;
     int32_t *cnt = nullptr, *ptr_t = nullptr, *node_t = nullptr, *perm = nullptr;
     SIGB_CUDA(cudaMalloc(&cnt, sizeof(int32_t) * ((size_t)ntargets + 1)));
-    SIGB_CUDA(cudaMalloc(&ptr_t, sizeof(int32_t) * ((size_t)ntargets + 1)));
+    SIGB_CUDA(cudaMalloc(&ptr_t, sizeof(int32_t) * ((size_t)ntargets + 1 + kPad)));
+    SIGB_CHECK(fill_i32(ptr_t + ntargets + 1, kPad, 1));
     SIGB_CUDA(cudaMalloc(&node_t, sizeof(int32_t) * ((size_t)ne + 8)));
     SIGB_CUDA(cudaMalloc(&perm, sizeof(int32_t) * ((size_t)ne + 8)));
     SIGB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * ((size_t)ntargets + 1), st));
