@@ -127,4 +127,24 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[ND], double *partials,
     }
 }
 
+// Persistent grid = resident CTAs per SM x SMs, queried once per kernel.  The
+// kernel is a template VALUE parameter: kernels sharing a signature must not
+// share the cache (their register counts, hence residency, differ).
+template <auto Kernel>
+int occupancy_grid(size_t smem, int *grid_out)
+{
+    static int cached = 0;
+    if (cached == 0) {
+        int per_sm = 0;
+        SIGB_CUDA(cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SIGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, Kernel, kThreads, smem));
+        if (per_sm < 1) per_sm = 1;
+        int g = per_sm * ctx().num_sms;
+        if (g > kMaxGrid) g = (kMaxGrid / ctx().num_sms) * ctx().num_sms;
+        cached = g;
+    }
+    *grid_out = cached;
+    return SIGB_OK;
+}
+
 }  // namespace sigb

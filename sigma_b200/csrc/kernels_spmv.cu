@@ -434,36 +434,19 @@ ell_kernel(const EllKernelArgs a)
     }
 }
 
-template <typename K>
-int occupancy_grid(K kernel, size_t smem, int *grid_out)
-{
-    static int cached = 0;  // one per template instantiation
-    if (cached == 0) {
-        int per_sm = 0;
-        SIGB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SIGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
-        if (per_sm < 1) per_sm = 1;
-        int g = per_sm * ctx().num_sms;
-        if (g > kMaxGrid) g = (kMaxGrid / ctx().num_sms) * ctx().num_sms;
-        cached = g;
-    }
-    *grid_out = cached;
-    return SIGB_OK;
-}
-
 template <int MODE, int NDOT>
 int launch_csr_t(const CsrKernelArgs &a, cudaStream_t st)
 {
     int grid = 0;
     if (spmv_variant() == 1) {
         const size_t smem = (size_t)kTileNnz * sizeof(double);
-        SIGB_CHECK(occupancy_grid(csr_stream_kernel<MODE, NDOT>, smem, &grid));
+        SIGB_CHECK((occupancy_grid<csr_stream_kernel<MODE, NDOT>>(smem, &grid)));
         if (a.ntiles < grid) grid = a.ntiles;
         if (grid < 1) grid = 1;
         csr_stream_kernel<MODE, NDOT><<<grid, kThreads, smem, st>>>(a);
     } else {
         const size_t smem = 2 * (size_t)kStageBytes;
-        SIGB_CHECK(occupancy_grid(csr_tma_kernel<MODE, NDOT>, smem, &grid));
+        SIGB_CHECK((occupancy_grid<csr_tma_kernel<MODE, NDOT>>(smem, &grid)));
         if (a.ntiles < grid) grid = a.ntiles;
         if (grid < 1) grid = 1;
         csr_tma_kernel<MODE, NDOT><<<grid, kThreads, smem, st>>>(a);
@@ -477,7 +460,7 @@ template <int MODE, int NDOT, int W>
 int launch_ell_t(const EllKernelArgs &a, cudaStream_t st)
 {
     int grid = 0;
-    SIGB_CHECK(occupancy_grid(ell_kernel<MODE, NDOT, W>, 0, &grid));
+    SIGB_CHECK((occupancy_grid<ell_kernel<MODE, NDOT, W>>(0, &grid)));
     const int need = ((a.n_pad >> 1) + kThreads - 1) / kThreads;
     if (need < grid) grid = need;
     if (grid < 1) grid = 1;

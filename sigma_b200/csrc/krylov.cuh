@@ -98,8 +98,12 @@ inline int ew_grid(int64_t n)
 template <class Op>
 int launch_ew(const Op &op, int64_t n, cudaStream_t st = nullptr)
 {
-    ew_kernel<Op><<<ew_grid(n), kThreads, 0, st ? st : ctx().stream>>>(
-        op, n, ctx().partials, ctx().tickets);
+    // one persistent wave: resident CTAs x SMs (register use differs per Op)
+    int grid = 0;
+    SIGB_CHECK((occupancy_grid<ew_kernel<Op>>(0, &grid)));
+    const int need = ew_grid(n);
+    if (need < grid) grid = need;
+    ew_kernel<Op><<<grid, kThreads, 0, st ? st : ctx().stream>>>(op, n, ctx().partials, ctx().tickets);
     count_launch();
     SIGB_CUDA(cudaGetLastError());
     return SIGB_OK;
