@@ -249,15 +249,24 @@ SIGB_API int sigb_comm_info(sigb_comm_t comm, int *rank, int *nranks,
                             int *peer_access);
 
 /* Row block [part[rank], part[rank+1]) of a global n x n CSR matrix.
- *  ptr_blk1  : the block's slice of the global ptr (nloc+1 entries, 1-based)
- *  node_glob1: GLOBAL 1-based column ids of the block's entries, stored order
- * The library derives halo and send lists (graph-derived, exchanged over the
- * communicator), splits rows into interior / boundary, and mirrors the
- * renumbered local CSR on the device. */
+ *  ptr_blk1   : the block's slice of the global ptr (nloc+1 entries, 1-based,
+ *               may start above 1)
+ *  node_glob1 : GLOBAL 1-based column ids of the block's entries, stored order
+ *  send_counts: nranks entries, how many owned rows rank q needs from us
+ *  send_rows1 : those rows as 1-based LOCAL row ids, grouped by destination
+ *               rank ascending, each group in ascending order
+ * The halo list (what we need) is derived here from node_glob1 with
+ * sigb_halo_build; the send lists are its mirror image on the owners, which
+ * the host obtains with one all-to-all of the halo lists (torch.distributed,
+ * MPI_Alltoallv ...; sigma_b200/distributed.py shows it) -- "graph-derived"
+ * index work, no values involved.  The library splits the rows into interior
+ * and boundary tiles and mirrors the renumbered local CSR on the device.
+ * Values are uploaded with sigb_matrix_set_values (the block's val slice). */
 SIGB_API int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global,
                                   const int32_t *part, const int32_t *ptr_blk1,
                                   const int32_t *node_glob1,
-                                  sigb_matrix_t *A);
+                                  const int32_t *send_counts,
+                                  const int32_t *send_rows1, sigb_matrix_t *A);
 /* Halo / send lists of a distributed matrix (index parity checks). */
 SIGB_API int sigb_dist_get_halo(sigb_matrix_t A, int32_t *nhalo, int32_t *halo);
 

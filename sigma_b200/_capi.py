@@ -78,7 +78,7 @@ PROTOTYPES = {
     "sigb_comm_create": (C.c_int, [_vp, C.c_int, C.c_int, _pvp]),
     "sigb_comm_destroy": (C.c_int, [_vp]),
     "sigb_comm_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
-    "sigb_dist_csr_create": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _pvp]),
+    "sigb_dist_csr_create": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _pvp]),
     "sigb_dist_get_halo": (C.c_int, [_vp, _pi32, _vp]),
 }
 

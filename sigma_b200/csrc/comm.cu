@@ -1,32 +1,323 @@
-// comm.cu -- multi-GPU communicator and row-sharded operators (placeholder:
-// the single-GPU path is complete; the sharded path lands next).
+// comm.cu -- multi-GPU communicator and row-sharded (distributed) operators.
+//
+// Not in the reference, which is serial; the seam is the block-row loop of
+// composite_matvec_add (src/matrix/sparse_matrix_composites.f90:1076-1100,
+// "This loop can be parallelized" :1086) with its x(j1:j2) / y(i1:i2) slices.
+//
+// One process per GPU.  Rank r owns the contiguous rows [part[r], part[r+1]) of
+// a square global operator; its block is stored as a local CSR whose columns
+// are renumbered [owned | halo] (partition.cpp).  One SpMV is
+//     pack owned entries other ranks need  ->  exchange  (aux stream)
+//     interior tiles (no halo column)                    (main stream, overlapped)
+//     boundary tiles, gathering halo columns from the landing buffer
+// and every Krylov dot product is completed by an all-reduce of 1-3 doubles.
+// Transport: NCCL (ncclSend/ncclRecv grouped per SpMV, ncclAllReduce per dot)
+// over NVLink/NVSwitch.
+#include <nccl.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "device_utils.cuh"
 #include "dist.h"
 #include "solvers.h"
 
+struct sigb_comm_s {
+    ncclComm_t nccl = nullptr;
+    int rank = 0, nranks = 1;
+    cudaStream_t stream = nullptr;   // halo exchange stream
+    cudaEvent_t ev_pack = nullptr, ev_halo = nullptr;
+};
+
 namespace sigb {
 
-struct DistInfo { int dummy; };
+#define SIGB_NCCL(call)                                                                  \
+    do {                                                                                 \
+        ncclResult_t r__ = (call);                                                       \
+        if (r__ != ncclSuccess) {                                                        \
+            set_error("NCCL error %d (%s) in %s at %s:%d", (int)r__, ncclGetErrorString(r__), #call, \
+                      __FILE__, __LINE__);                                               \
+            return SIGB_ERR_COMM;                                                        \
+        }                                                                                \
+    } while (0)
 
-int dist_matvec(sigb_matrix_t, const double *, double *, bool, const DotSpec &, bool)
+struct DistInfo {
+    sigb_comm_t comm = nullptr;
+    int32_t n_global = 0, lo = 0, hi = 0, nloc = 0, nhalo = 0;
+    std::vector<int32_t> halo_host;              // sorted unique global column ids (1-based)
+    std::vector<int> send_cnt, send_off, recv_cnt, recv_off;
+    int total_send = 0;
+    int32_t *send_rows = nullptr;   // device, 1-based local rows, grouped by destination
+    double *sendbuf = nullptr;      // device, packed values
+    double *halo = nullptr;         // device, landing buffer (nhalo)
+    double *dot_tmp = nullptr;      // device, 2 doubles: interior partial sums
+};
+
+namespace {
+
+__global__ void __launch_bounds__(kThreads)
+pack_kernel(const double *__restrict__ x, const int32_t *__restrict__ rows1, int n,
+            double *__restrict__ out, const int *skip_flag)
 {
-    set_error("row-sharded operators are not built yet");
-    return SIGB_ERR_UNSUPPORTED;
+    if (skip_flag != nullptr && *skip_flag != 0) return;
+    for (int k = blockIdx.x * kThreads + threadIdx.x; k < n; k += gridDim.x * kThreads)
+        out[k] = x[rows1[k] - 1];
 }
-int dist_destroy(sigb_matrix_t) { return SIGB_OK; }
-int64_t dist_global_n(sigb_matrix_t A) { return A->nrow; }
-int64_t dist_row_offset(sigb_matrix_t) { return 0; }
-int64_t dist_halo_len(sigb_matrix_t) { return 0; }
-int dist_allreduce(sigb_matrix_t, double *, int) { return SIGB_OK; }
-int dist_allreduce2(sigb_matrix_t, double *, double *) { return SIGB_OK; }
+
+}  // namespace
+
+int64_t dist_global_n(sigb_matrix_t A) { return A->dist ? A->dist->n_global : A->nrow; }
+int64_t dist_row_offset(sigb_matrix_t A) { return A->dist ? A->dist->lo : 0; }
+int64_t dist_halo_len(sigb_matrix_t) { return 0; }  // halos land in the operator's own buffer
+
+int dist_destroy(sigb_matrix_t A)
+{
+    DistInfo *D = A->dist;
+    if (!D) return SIGB_OK;
+    cudaFree(D->send_rows);
+    cudaFree(D->sendbuf);
+    cudaFree(D->halo);
+    cudaFree(D->dot_tmp);
+    delete D;
+    A->dist = nullptr;
+    return SIGB_OK;
+}
+
+int dist_allreduce(sigb_matrix_t A, double *vals, int count)
+{
+    DistInfo *D = A->dist;
+    if (!D || D->comm->nranks == 1) return SIGB_OK;
+    SIGB_NCCL(ncclAllReduce(vals, vals, (size_t)count, ncclDouble, ncclSum, D->comm->nccl, ctx().stream));
+    return SIGB_OK;
+}
+
+int dist_allreduce2(sigb_matrix_t A, double *a, double *b)
+{
+    DistInfo *D = A->dist;
+    if (!D || D->comm->nranks == 1) return SIGB_OK;
+    SIGB_NCCL(ncclGroupStart());
+    SIGB_NCCL(ncclAllReduce(a, a, 1, ncclDouble, ncclSum, D->comm->nccl, ctx().stream));
+    SIGB_NCCL(ncclAllReduce(b, b, 1, ncclDouble, ncclSum, D->comm->nccl, ctx().stream));
+    SIGB_NCCL(ncclGroupEnd());
+    return SIGB_OK;
+}
+
+// y = A x (or y += A x) for the local row block; x holds the owned entries.
+int dist_matvec(sigb_matrix_t A, const double *x, double *y, bool add, const DotSpec &dot_in, bool)
+{
+    DistInfo *D = A->dist;
+    sigb_comm_t C = D->comm;
+    const CsrView &V = A->g->stored;
+    const SpmvMode mode = add ? MODE_ADD_AFTER : MODE_SET;
+    cudaStream_t main = ctx().stream;
+    DotSpec dot = dot_in;
+    dot.nloc = D->nloc;
+
+    const bool exchange = C->nranks > 1 && (D->total_send > 0 || D->nhalo > 0);
+    if (exchange) {
+        if (D->total_send > 0) {
+            int grid = (D->total_send + kThreads - 1) / kThreads;
+            grid = std::min(grid, ctx().num_sms * 4);
+            pack_kernel<<<grid, kThreads, 0, main>>>(x, D->send_rows, D->total_send, D->sendbuf, dot.skip_flag);
+            count_launch();
+            SIGB_CUDA(cudaGetLastError());
+        }
+        SIGB_CUDA(cudaEventRecord(C->ev_pack, main));
+        SIGB_CUDA(cudaStreamWaitEvent(C->stream, C->ev_pack, 0));
+        SIGB_NCCL(ncclGroupStart());
+        for (int q = 0; q < C->nranks; q++) {
+            if (D->send_cnt[q] > 0)
+                SIGB_NCCL(ncclSend(D->sendbuf + D->send_off[q], (size_t)D->send_cnt[q], ncclDouble, q, C->nccl, C->stream));
+            if (D->recv_cnt[q] > 0)
+                SIGB_NCCL(ncclRecv(D->halo + D->recv_off[q], (size_t)D->recv_cnt[q], ncclDouble, q, C->nccl, C->stream));
+        }
+        SIGB_NCCL(ncclGroupEnd());
+        SIGB_CUDA(cudaEventRecord(C->ev_halo, C->stream));
+    }
+
+    if (V.n_boundary == 0) {
+        // nothing depends on the halo: one launch over the interior list
+        if (exchange) SIGB_CUDA(cudaStreamWaitEvent(main, C->ev_halo, 0));
+        return launch_csr_spmv(V, A->val, x, y, mode, dot, 1, main, 0);
+    }
+    // interior tiles overlap the exchange; their dot partials wait in dot_tmp
+    DotSpec di = dot;
+    if (dot.ndot > 0) {
+        di.out[0] = D->dot_tmp;
+        di.out[1] = D->dot_tmp + 1;
+    }
+    if (V.n_interior > 0 || dot.ndot > 0)
+        SIGB_CHECK(launch_csr_spmv(V, A->val, x, y, mode, di, 1, main, 0));
+    if (exchange) SIGB_CUDA(cudaStreamWaitEvent(main, C->ev_halo, 0));
+    DotSpec db = dot;
+    db.halo = D->halo;
+    if (dot.ndot > 0) {
+        db.addend[0] = D->dot_tmp;
+        db.addend[1] = dot.ndot > 1 ? D->dot_tmp + 1 : nullptr;
+    }
+    return launch_csr_spmv(V, A->val, x, y, mode, db, 2, main, 0);
+}
 
 }  // namespace sigb
 
 using namespace sigb;
+
 extern "C" {
-int sigb_comm_unique_id(void *) { set_error("not built yet"); return SIGB_ERR_UNSUPPORTED; }
-int sigb_comm_create(const void *, int, int, sigb_comm_t *) { set_error("not built yet"); return SIGB_ERR_UNSUPPORTED; }
-int sigb_comm_destroy(sigb_comm_t) { return SIGB_OK; }
-int sigb_comm_info(sigb_comm_t, int *, int *, int *) { set_error("not built yet"); return SIGB_ERR_UNSUPPORTED; }
-int sigb_dist_csr_create(sigb_comm_t, int32_t, const int32_t *, const int32_t *, const int32_t *, sigb_matrix_t *) { set_error("not built yet"); return SIGB_ERR_UNSUPPORTED; }
-int sigb_dist_get_halo(sigb_matrix_t, int32_t *, int32_t *) { set_error("not built yet"); return SIGB_ERR_UNSUPPORTED; }
+
+int sigb_comm_unique_id(void *unique_id)
+{
+    SIGB_REQUIRE(unique_id, SIGB_ERR_ARG, "sigb_comm_unique_id: null buffer");
+    static_assert(sizeof(ncclUniqueId) <= SIGB_UNIQUE_ID_BYTES, "unique id size");
+    ncclUniqueId id;
+    SIGB_NCCL(ncclGetUniqueId(&id));
+    memset(unique_id, 0, SIGB_UNIQUE_ID_BYTES);
+    memcpy(unique_id, &id, sizeof(id));
+    return SIGB_OK;
 }
+
+int sigb_comm_create(const void *unique_id, int rank, int nranks, sigb_comm_t *out)
+{
+    SIGB_CHECK(require_init());
+    SIGB_REQUIRE(unique_id && out && nranks >= 1 && rank >= 0 && rank < nranks, SIGB_ERR_ARG,
+                 "sigb_comm_create: bad argument");
+    sigb_comm_t c = new sigb_comm_s();
+    c->rank = rank;
+    c->nranks = nranks;
+    ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof(id));
+    SIGB_NCCL(ncclCommInitRank(&c->nccl, nranks, id, rank));
+    SIGB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    SIGB_CUDA(cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming));
+    SIGB_CUDA(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+    *out = c;
+    return SIGB_OK;
+}
+
+int sigb_comm_destroy(sigb_comm_t c)
+{
+    if (!c) return SIGB_OK;
+    cudaDeviceSynchronize();
+    if (c->nccl) ncclCommDestroy(c->nccl);
+    cudaStreamDestroy(c->stream);
+    cudaEventDestroy(c->ev_pack);
+    cudaEventDestroy(c->ev_halo);
+    delete c;
+    return SIGB_OK;
+}
+
+int sigb_comm_info(sigb_comm_t c, int *rank, int *nranks, int *peer_access)
+{
+    SIGB_REQUIRE(c, SIGB_ERR_ARG, "sigb_comm_info: null communicator");
+    if (rank) *rank = c->rank;
+    if (nranks) *nranks = c->nranks;
+    if (peer_access) *peer_access = 0;
+    return SIGB_OK;
+}
+
+int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global, const int32_t *part,
+                         const int32_t *ptr_blk1, const int32_t *node_glob1,
+                         const int32_t *send_counts, const int32_t *send_rows1, sigb_matrix_t *out)
+{
+    SIGB_CHECK(require_init());
+    SIGB_REQUIRE(comm && part && ptr_blk1 && out && send_counts, SIGB_ERR_ARG, "sigb_dist_csr_create: bad argument");
+    const int P = comm->nranks, me = comm->rank;
+    SIGB_REQUIRE(part[0] == 0 && part[P] == n_global, SIGB_ERR_ARG, "sigb_dist_csr_create: part must span 0..n_global");
+    const int32_t lo = part[me], hi = part[me + 1], nloc = hi - lo;
+    const int64_t ne = (int64_t)ptr_blk1[nloc] - ptr_blk1[0];
+    SIGB_REQUIRE(ne == 0 || node_glob1, SIGB_ERR_ARG, "sigb_dist_csr_create: null node array");
+
+    DistInfo *D = new DistInfo();
+    D->comm = comm;
+    D->n_global = n_global;
+    D->lo = lo;
+    D->hi = hi;
+    D->nloc = nloc;
+
+    // halo list + local numbering (bit-exact index work, partition.cpp)
+    std::vector<int32_t> halo((size_t)std::max<int64_t>(ne, 1)), local((size_t)std::max<int64_t>(ne, 1));
+    int32_t nhalo = 0;
+    int rc = sigb_halo_build(lo, hi, ptr_blk1, node_glob1, halo.data(), &nhalo, local.data());
+    if (rc != SIGB_OK) { delete D; return rc; }
+    halo.resize((size_t)nhalo);
+    D->nhalo = nhalo;
+    D->halo_host = halo;
+    D->recv_cnt.assign(P, 0);
+    D->recv_off.assign(P, 0);
+    D->send_cnt.assign(P, 0);
+    D->send_off.assign(P, 0);
+    for (int32_t h = 0, q = 0; h < nhalo; h++) {
+        while (halo[h] > part[q + 1]) q++;   // owner of 1-based column c: part[q] < c <= part[q+1]
+        D->recv_cnt[q]++;
+    }
+    for (int q = 1; q < P; q++) D->recv_off[q] = D->recv_off[q - 1] + D->recv_cnt[q - 1];
+    int total_send = 0;
+    for (int q = 0; q < P; q++) {
+        SIGB_REQUIRE(send_counts[q] >= 0 && (q != me || send_counts[q] == 0), SIGB_ERR_ARG,
+                     "sigb_dist_csr_create: bad send count for rank %d", q);
+        D->send_cnt[q] = send_counts[q];
+        D->send_off[q] = total_send;
+        total_send += send_counts[q];
+    }
+    D->total_send = total_send;
+    SIGB_REQUIRE(total_send == 0 || send_rows1, SIGB_ERR_ARG, "sigb_dist_csr_create: null send list");
+    for (int k = 0; k < total_send; k++)
+        SIGB_REQUIRE(send_rows1[k] >= 1 && send_rows1[k] <= nloc, SIGB_ERR_ARG,
+                     "sigb_dist_csr_create: send row %d outside the owned block", send_rows1[k]);
+
+    // local CSR mirror: ptr rebased to 1, columns in [owned | halo] numbering
+    std::vector<int32_t> ptr((size_t)nloc + 1);
+    for (int32_t i = 0; i <= nloc; i++) ptr[i] = ptr_blk1[i] - ptr_blk1[0] + 1;
+    sigb_graph_t g = nullptr;
+    rc = sigb_cs_graph_create(nloc, nloc + nhalo, ptr.data(), local.data(), SIGB_ROW, &g);
+    if (rc != SIGB_OK) { delete D; return rc; }
+
+    // interior / boundary tile lists
+    std::vector<TileDesc> tiles, ti, tb;
+    build_tiles_host(ptr.data(), nloc, tiles);
+    for (const TileDesc &t : tiles) {
+        bool boundary = false;
+        for (int32_t k = t.ks; k < t.ke && !boundary; k++) boundary = local[k] > nloc;
+        (boundary ? tb : ti).push_back(t);
+    }
+    CsrView &V = g->stored;
+    V.n_interior = (int32_t)ti.size();
+    V.n_boundary = (int32_t)tb.size();
+    cudaStream_t st = ctx().stream;
+    SIGB_CUDA(cudaMalloc((void **)&V.tiles_interior, sizeof(TileDesc) * std::max<size_t>(ti.size(), 1)));
+    SIGB_CUDA(cudaMalloc((void **)&V.tiles_boundary, sizeof(TileDesc) * std::max<size_t>(tb.size(), 1)));
+    if (!ti.empty())
+        SIGB_CUDA(cudaMemcpyAsync(V.tiles_interior, ti.data(), sizeof(TileDesc) * ti.size(), cudaMemcpyHostToDevice, st));
+    if (!tb.empty())
+        SIGB_CUDA(cudaMemcpyAsync(V.tiles_boundary, tb.data(), sizeof(TileDesc) * tb.size(), cudaMemcpyHostToDevice, st));
+
+    SIGB_CUDA(cudaMalloc((void **)&D->send_rows, sizeof(int32_t) * std::max(total_send, 1)));
+    SIGB_CUDA(cudaMalloc((void **)&D->sendbuf, sizeof(double) * std::max(total_send, 1)));
+    SIGB_CUDA(cudaMalloc((void **)&D->halo, sizeof(double) * std::max(nhalo, 1)));
+    SIGB_CUDA(cudaMalloc((void **)&D->dot_tmp, sizeof(double) * 2));
+    SIGB_CUDA(cudaMemsetAsync(D->halo, 0, sizeof(double) * std::max(nhalo, 1), st));
+    SIGB_CUDA(cudaMemsetAsync(D->dot_tmp, 0, sizeof(double) * 2, st));
+    if (total_send > 0)
+        SIGB_CUDA(cudaMemcpyAsync(D->send_rows, send_rows1, sizeof(int32_t) * total_send, cudaMemcpyHostToDevice, st));
+    SIGB_CUDA(cudaStreamSynchronize(st));
+
+    sigb_matrix_t A = nullptr;
+    rc = sigb_matrix_create(g, &A);
+    sigb_graph_release(g);   // the matrix holds its own reference
+    if (rc != SIGB_OK) { delete D; return rc; }
+    A->dist = D;
+    A->nrow = nloc;
+    A->ncol = nloc;   // owned columns; the halo is internal
+    *out = A;
+    return SIGB_OK;
+}
+
+int sigb_dist_get_halo(sigb_matrix_t A, int32_t *nhalo, int32_t *halo)
+{
+    SIGB_REQUIRE(A && A->dist, SIGB_ERR_ARG, "sigb_dist_get_halo: not a row-sharded operator");
+    if (nhalo) *nhalo = A->dist->nhalo;
+    if (halo)
+        for (int32_t i = 0; i < A->dist->nhalo; i++) halo[i] = A->dist->halo_host[i];
+    return SIGB_OK;
+}
+
+}  // extern "C"

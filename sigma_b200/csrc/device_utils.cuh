@@ -91,11 +91,17 @@ __device__ __forceinline__ void block_tree(double (&v)[ND], double (*sm)[kThread
     __syncthreads();
 }
 
-// out[d] receive the grid totals (device pointers).  All threads of all CTAs
-// must call this.  `ticket` must be zero on entry and is zero again on exit.
+// out[d] receive the grid totals (device pointers), plus *addend[d] when that
+// pointer is non-null (a partial sum left by an earlier launch).  All threads
+// of all CTAs must call this.  `ticket` must be zero on entry and is zero
+// again on exit.
 template <int ND>
 __device__ __forceinline__ void grid_reduce(double (&acc)[ND], double *partials,
-                                            unsigned *ticket, double *const (&out)[ND])
+                                            unsigned *ticket, double *const (&out)[ND]);
+template <int ND>
+__device__ __forceinline__ void grid_reduce(double (&acc)[ND], double *partials,
+                                            unsigned *ticket, double *const (&out)[ND],
+                                            const double *const (&addend)[ND])
 {
     __shared__ double sm[ND][kThreads / 32];
     __shared__ bool is_last;
@@ -121,10 +127,22 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[ND], double *partials,
         block_tree<ND>(v, sm);
         if (threadIdx.x == 0) {
 #pragma unroll
-            for (int d = 0; d < ND; d++) *out[d] = v[d];
+            for (int d = 0; d < ND; d++)
+                *out[d] = addend[d] ? add(__ldcg(addend[d]), v[d]) : v[d];
             *ticket = 0u;
         }
     }
+}
+
+template <int ND>
+__device__ __forceinline__ void grid_reduce(double (&acc)[ND], double *partials,
+                                            unsigned *ticket, double *const (&out)[ND])
+{
+    const double *addend[ND];
+#pragma unroll
+    for (int d = 0; d < ND; d++) addend[d] = nullptr;
+    const double *const(&ref)[ND] = addend;
+    grid_reduce<ND>(acc, partials, ticket, out, ref);
 }
 
 // Persistent grid = resident CTAs per SM x SMs, queried once per kernel.  The

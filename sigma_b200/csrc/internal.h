@@ -152,6 +152,9 @@ struct DotSpec {
     double *out[2] = {nullptr, nullptr};  // device scalars receiving the sums
     const int *skip_flag = nullptr;       // if non-null and *skip_flag != 0 the kernel is a no-op
     const double *row_scale = nullptr;    // y(i) = row_scale(i) * z (fused jacobi_solve), MODE_SET only
+    const double *addend[2] = {nullptr, nullptr};  // partial sums of an earlier launch, added to the totals
+    const double *halo = nullptr;         // row-sharded: values of columns nloc+1.. (halo landing buffer)
+    int32_t nloc = 0;                     // row-sharded: number of owned columns
 };
 
 // which: 0 = all tiles, 1 = interior subset, 2 = boundary subset
@@ -163,7 +166,6 @@ int launch_ell_spmv(int32_t n, int32_t n_pad, int32_t max_d,
                     const double *x, double *y, SpmvMode mode,
                     const DotSpec &dot);
 int build_tiles_host(const int32_t *ptr1, int32_t nrows, std::vector<TileDesc> &tiles);
-int spmv_variant();  // SIGB_SPMV_VARIANT: 2 = TMA bulk-copy pipeline (default), 1 = register path
 
 // ---------------------------------------------------------------------------
 // transpose.cu

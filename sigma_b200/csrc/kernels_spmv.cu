@@ -31,8 +31,14 @@
 // + 8 B/row (y) -- the algorithmic minimum; x re-reads
 // are served by L1/L2.
 //
-// SIGB_SPMV_VARIANT=1 selects the older register-staged kernel (128-bit
-// ld.global.nc loads into registers) kept for A/B measurements.
+// (Round-1 A/B, profiles/r1_bench_1gpu*.json: a register-staged variant with
+// 128-bit ld.global.nc loads reached 234.6 us per SpMV and 278 us fused with the
+// dot on the 4096^2 Poisson matrix; this TMA pipeline 229 us / 246 us.  The
+// register variant was removed.)
+//
+// Row-sharded operators (comm.cu) run the same kernel twice per SpMV: interior
+// tiles while the halo is in flight, then boundary tiles, whose gathers take
+// columns beyond the owned range from the halo landing buffer (HALO = true).
 #include <stdlib.h>
 
 #include "device_utils.cuh"
@@ -55,6 +61,9 @@ struct CsrKernelArgs {
     unsigned *ticket;
     const int *skip_flag;
     const double *scale;      // optional per-row scaling of the result
+    const double *h1;         // halo - (nloc + 1): indexable by column ids > nloc
+    int32_t nloc;             // owned columns (HALO kernels)
+    const double *add0, *add1;  // optional addends folded into the dot totals
 };
 
 __device__ __forceinline__ int4 load_desc(const TileDesc *t)
@@ -120,28 +129,31 @@ __device__ __forceinline__ bool tile_staged(const int4 &d)
 }
 
 template <int MODE, int NDOT>
-__device__ __forceinline__ void emit_row(const CsrKernelArgs &a, int r, double z, double *acc)
+__device__ __forceinline__ void emit_row(const CsrKernelArgs &a, int r, double z, double ur, double *acc)
 {
     if (MODE == MODE_ADD_AFTER) z = add(a.y[r], z);
     if (MODE == MODE_SET && a.scale) z = mul(a.scale[r], z);
     a.y[r] = z;
-    if (NDOT >= 1) acc[0] = add(acc[0], mul(a.u[r], z));
+    if (NDOT >= 1) acc[0] = add(acc[0], mul(ur, z));
     if (NDOT >= 2) acc[NDOT > 1 ? 1 : 0] = add(acc[NDOT > 1 ? 1 : 0], mul(z, z));
 }
 
 // one row longer than a tile: CTA-wide fixed-tree reduction, direct loads
-template <int MODE, int NDOT>
+template <int MODE, int NDOT, bool HALO>
 __device__ __forceinline__ void long_row(const CsrKernelArgs &a, const int4 &d, double *acc)
 {
     __shared__ double smr[1][kThreads / 32];
     double s[1] = {0.0};
-    for (int k = d.z + threadIdx.x; k < d.w; k += kThreads)
-        s[0] = add(s[0], mul(a.val[k], __ldg(a.x1 + a.node[k])));
+    for (int k = d.z + threadIdx.x; k < d.w; k += kThreads) {
+        const int c = a.node[k];
+        const double xv = (HALO && c > a.nloc) ? __ldcg(a.h1 + c) : __ldg(a.x1 + c);
+        s[0] = add(s[0], mul(a.val[k], xv));
+    }
     block_tree<1>(s, smr);
     if (threadIdx.x == 0) {
         double z = s[0];
         if (MODE == MODE_ACC_INIT) z = add(a.y[d.x], z);
-        emit_row<MODE, NDOT>(a, d.x, z, acc);
+        emit_row<MODE, NDOT>(a, d.x, z, NDOT >= 1 ? a.u[d.x] : 0.0, acc);
     }
     __syncthreads();
 }
@@ -151,19 +163,21 @@ __device__ __forceinline__ void finish_dots(const CsrKernelArgs &a, double *acc)
 {
     if (NDOT == 1) {
         double *const out[1] = {a.out0};
+        const double *const addend[1] = {a.add0};
         double v[1] = {acc[0]};
-        grid_reduce<1>(v, a.partials, a.ticket, out);
+        grid_reduce<1>(v, a.partials, a.ticket, out, addend);
     } else if (NDOT == 2) {
         double *const out[2] = {a.out0, a.out1};
+        const double *const addend[2] = {a.add0, a.add1};
         double v[2] = {acc[0], acc[NDOT > 1 ? 1 : 0]};
-        grid_reduce<2>(v, a.partials, a.ticket, out);
+        grid_reduce<2>(v, a.partials, a.ticket, out, addend);
     }
 }
 
 // ---------------------------------------------------------------------------
-// variant 2 (default): TMA bulk-copy, double-buffered
+// TMA bulk-copy, double-buffered
 // ---------------------------------------------------------------------------
-template <int MODE, int NDOT>
+template <int MODE, int NDOT, bool HALO>
 __global__ void __launch_bounds__(kThreads)
 csr_tma_kernel(const CsrKernelArgs a)
 {
@@ -219,6 +233,15 @@ csr_tma_kernel(const CsrKernelArgs a)
             const int32_t *sptr = reinterpret_cast<const int32_t *>(base + kStageVal + kStageNode);
             const int rs = d_cur.x, re = d_cur.y, ks = d_cur.z, ke = d_cur.w;
             const int ka = ks & ~3, ra = rs & ~3;
+            // operands of the fused dot: requested before the wait, used in phase 2
+            double upre[kTileRows / kThreads];
+            if (NDOT >= 1) {
+#pragma unroll
+                for (int i = 0; i < kTileRows / kThreads; i++) {
+                    const int r = rs + tid + i * kThreads;
+                    upre[i] = (r < re) ? a.u[r] : 0.0;
+                }
+            }
             mbar_wait(&mbar[stage], (sidx >> 1) & 1u);
             // ---- phase 1: products, in place --------------------------------
             // (entries before ks belong to the previous tile and hold valid
@@ -234,7 +257,10 @@ csr_tma_kernel(const CsrKernelArgs a)
             }
             double xv[kTileNnz / kThreads];
 #pragma unroll
-            for (int i = 0; i < kTileNnz / kThreads; i++) xv[i] = __ldg(a.x1 + c[i]);
+            for (int i = 0; i < kTileNnz / kThreads; i++) {
+                if (HALO && c[i] > a.nloc) xv[i] = __ldcg(a.h1 + c[i]);   // written by peers: not via the nc path
+                else xv[i] = __ldg(a.x1 + c[i]);
+            }
 #pragma unroll
             for (int i = 0; i < kTileNnz / kThreads; i++) {
                 const int k = tid + i * kThreads;
@@ -242,104 +268,26 @@ csr_tma_kernel(const CsrKernelArgs a)
             }
             __syncthreads();
             // ---- phase 2: per-row sums in stored order ----------------------
-            for (int r = rs + tid; r < re; r += kThreads) {
-                const int b = sptr[r - ra] - 1 - ka, e = sptr[r + 1 - ra] - 1 - ka;
-                double z = (MODE == MODE_ACC_INIT) ? a.y[r] : 0.0;
-                for (int k = b; k < e; k++) z = add(z, sval[k]);
-                emit_row<MODE, NDOT>(a, r, z, acc);
+#pragma unroll
+            for (int i = 0; i < kTileRows / kThreads; i++) {
+                const int r = rs + tid + i * kThreads;
+                if (r < re) {
+                    const int b = sptr[r - ra] - 1 - ka, e = sptr[r + 1 - ra] - 1 - ka;
+                    double z = (MODE == MODE_ACC_INIT) ? a.y[r] : 0.0;
+                    for (int k = b; k < e; k++) z = add(z, sval[k]);
+                    emit_row<MODE, NDOT>(a, r, z, NDOT >= 1 ? upre[i] : 0.0, acc);
+                }
             }
             // the stage is overwritten by the async proxy next: order our
             // generic-proxy accesses before it
             fence_proxy_async();
             __syncthreads();
         } else {
-            long_row<MODE, NDOT>(a, d_cur, acc);
+            long_row<MODE, NDOT, HALO>(a, d_cur, acc);
         }
         sidx = sidx_after;
         d_cur = d_next;
         d_next = d_next2;
-    }
-    finish_dots<NDOT>(a, acc);
-}
-
-// ---------------------------------------------------------------------------
-// variant 1: register-staged 128-bit streaming loads
-// ---------------------------------------------------------------------------
-template <int MODE, int NDOT>
-__global__ void __launch_bounds__(kThreads)
-csr_stream_kernel(const CsrKernelArgs a)
-{
-    extern __shared__ __align__(16) double prod[];  // kTileNnz rounded products
-    if (a.skip_flag != nullptr && *a.skip_flag != 0) return;
-
-    const int tid = threadIdx.x;
-    double acc[NDOT > 0 ? NDOT : 1];
-#pragma unroll
-    for (int d = 0; d < (NDOT > 0 ? NDOT : 1); d++) acc[d] = 0.0;
-
-    int t = blockIdx.x;
-    int4 d_cur = make_int4(0, 0, 0, 0);
-    if (t < a.ntiles) d_cur = load_desc(a.tiles + t);
-    for (; t < a.ntiles; t += gridDim.x) {
-        int4 d_next = make_int4(0, 0, 0, 0);
-        if (t + (int)gridDim.x < a.ntiles) d_next = load_desc(a.tiles + t + gridDim.x);
-        const int rs = d_cur.x, re = d_cur.y, ks = d_cur.z, ke = d_cur.w;
-        if (tile_staged(d_cur)) {
-            const int ka = ks & ~3;
-            constexpr int NIT = kTileNnz / (4 * kThreads);
-            // row extents for phase 2, requested before the big loads
-            int pb[2], pe[2];
-#pragma unroll
-            for (int i = 0; i < 2; i++) {
-                const int r = rs + tid + i * kThreads;
-                pb[i] = (r < re) ? a.ptr[r] : 1;
-                pe[i] = (r < re) ? a.ptr[r + 1] : 1;
-            }
-            int4 c[NIT];
-            double2 v01[NIT], v23[NIT];
-#pragma unroll
-            for (int it = 0; it < NIT; it++) {
-                const int j = ka + 4 * (tid + it * kThreads);
-                if (j < ke) {
-                    c[it] = ld_stream_i4(a.node + j);
-                    v01[it] = ld_stream_d2(a.val + j);
-                    v23[it] = ld_stream_d2(a.val + j + 2);
-                } else {
-                    c[it] = make_int4(1, 1, 1, 1);
-                    v01[it] = make_double2(0.0, 0.0);
-                    v23[it] = make_double2(0.0, 0.0);
-                }
-            }
-#pragma unroll
-            for (int it = 0; it < NIT; it++) {
-                const int j = ka + 4 * (tid + it * kThreads);
-                if (j < ke) {
-                    // entries before ks belong to the previous tile (valid columns);
-                    // entries past ke are padding (column 1): all gathers are safe
-                    const double p0 = mul(v01[it].x, __ldg(a.x1 + c[it].x));
-                    const double p1 = mul(v01[it].y, __ldg(a.x1 + c[it].y));
-                    const double p2 = mul(v23[it].x, __ldg(a.x1 + c[it].z));
-                    const double p3 = mul(v23[it].y, __ldg(a.x1 + c[it].w));
-                    double2 *dst = reinterpret_cast<double2 *>(prod + (j - ka));
-                    dst[0] = make_double2(p0, p1);
-                    dst[1] = make_double2(p2, p3);
-                }
-            }
-            __syncthreads();
-#pragma unroll
-            for (int i = 0; i < 2; i++) {
-                const int r = rs + tid + i * kThreads;
-                if (r < re) {
-                    double z = (MODE == MODE_ACC_INIT) ? a.y[r] : 0.0;
-                    for (int k = pb[i] - 1 - ka; k < pe[i] - 1 - ka; k++) z = add(z, prod[k]);
-                    emit_row<MODE, NDOT>(a, r, z, acc);
-                }
-            }
-            __syncthreads();
-        } else {
-            long_row<MODE, NDOT>(a, d_cur, acc);
-        }
-        d_cur = d_next;
     }
     finish_dots<NDOT>(a, acc);
 }
@@ -434,23 +382,15 @@ ell_kernel(const EllKernelArgs a)
     }
 }
 
-template <int MODE, int NDOT>
+template <int MODE, int NDOT, bool HALO>
 int launch_csr_t(const CsrKernelArgs &a, cudaStream_t st)
 {
     int grid = 0;
-    if (spmv_variant() == 1) {
-        const size_t smem = (size_t)kTileNnz * sizeof(double);
-        SIGB_CHECK((occupancy_grid<csr_stream_kernel<MODE, NDOT>>(smem, &grid)));
-        if (a.ntiles < grid) grid = a.ntiles;
-        if (grid < 1) grid = 1;
-        csr_stream_kernel<MODE, NDOT><<<grid, kThreads, smem, st>>>(a);
-    } else {
-        const size_t smem = 2 * (size_t)kStageBytes;
-        SIGB_CHECK((occupancy_grid<csr_tma_kernel<MODE, NDOT>>(smem, &grid)));
-        if (a.ntiles < grid) grid = a.ntiles;
-        if (grid < 1) grid = 1;
-        csr_tma_kernel<MODE, NDOT><<<grid, kThreads, smem, st>>>(a);
-    }
+    const size_t smem = 2 * (size_t)kStageBytes;
+    SIGB_CHECK((occupancy_grid<csr_tma_kernel<MODE, NDOT, HALO>>(smem, &grid)));
+    if (a.ntiles < grid) grid = a.ntiles;
+    if (grid < 1) grid = 1;
+    csr_tma_kernel<MODE, NDOT, HALO><<<grid, kThreads, smem, st>>>(a);
     count_launch();
     SIGB_CUDA(cudaGetLastError());
     return SIGB_OK;
@@ -487,16 +427,6 @@ int launch_ell_w(const EllKernelArgs &a, cudaStream_t st)
 }
 
 }  // namespace
-
-int spmv_variant()
-{
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("SIGB_SPMV_VARIANT");
-        v = (e && atoi(e) == 1) ? 1 : 2;
-    }
-    return v;
-}
 
 // Greedy row tiling: consecutive rows while the tile holds <= kTileCap entries
 // and <= kTileRows rows; a longer row gets a tile of its own.
@@ -540,14 +470,19 @@ int launch_csr_spmv(const CsrView &A, const double *val, const double *x, double
     a.ticket = ctx().tickets + ticket;
     a.skip_flag = dot.skip_flag;
     a.scale = dot.row_scale;
+    a.add0 = dot.addend[0];
+    a.add1 = dot.addend[1];
+    a.nloc = dot.nloc;
+    a.h1 = dot.halo ? dot.halo - (dot.nloc + 1) : nullptr;
+    const bool halo = dot.halo != nullptr;
     cudaStream_t st = stream ? stream : ctx().stream;
     if (a.ntiles == 0 && dot.ndot == 0) return SIGB_OK;
 
-#define SIGB_DISPATCH(M)                                                   \
-    switch (dot.ndot) {                                                    \
-    case 0: return launch_csr_t<M, 0>(a, st);                              \
-    case 1: return launch_csr_t<M, 1>(a, st);                              \
-    default: return launch_csr_t<M, 2>(a, st);                             \
+#define SIGB_DISPATCH(M)                                                            \
+    switch (dot.ndot) {                                                             \
+    case 0: return halo ? launch_csr_t<M, 0, true>(a, st) : launch_csr_t<M, 0, false>(a, st);  \
+    case 1: return halo ? launch_csr_t<M, 1, true>(a, st) : launch_csr_t<M, 1, false>(a, st);  \
+    default: return halo ? launch_csr_t<M, 2, true>(a, st) : launch_csr_t<M, 2, false>(a, st); \
     }
     switch (mode) {
     case MODE_SET: SIGB_DISPATCH(MODE_SET)
