@@ -172,7 +172,9 @@ def run_ours(args):
 
         ctx = D.setup_poisson(N, rank, world, dev)
         A, nloc, nnz_loc, b_host, nnz_glob = ctx.A, ctx.nloc, ctx.nnz_loc, ctx.b, ctx.nnz_glob
+        transport = ctx.comm.transport
     else:
+        transport = "none"
         ptr, node, val = G.poisson2d_csr(N)
         b_host, _ = G.poisson2d_rhs(N)
         A = sb.csr_matrix(n, n, ptr, node, val)
@@ -292,7 +294,7 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"2D Poisson 5-point CSR {N}x{N} (n={n}, nnz={nnz_glob}), fp64 CG, x0=0, "
                                    f"b=A*rand(seed 12345), tol=1e-10*|b|",
-                       "sharding": f"contiguous row blocks over {world} GPU(s)",
+                       "sharding": f"contiguous row blocks over {world} GPU(s), halo + dot all-reduce transport: {transport}",
                        "l2": "inputs larger than L2 (matrix 1.0 GB + 5 vectors of 134 MB per solve)",
                        "step": "one CG iteration (3 kernels)"},
             "clocks": clk.summary(),

@@ -7,13 +7,27 @@
 // One process per GPU.  Rank r owns the contiguous rows [part[r], part[r+1]) of
 // a square global operator; its block is stored as a local CSR whose columns
 // are renumbered [owned | halo] (partition.cpp).  One SpMV is
-//     pack owned entries other ranks need  ->  exchange  (aux stream)
-//     interior tiles (no halo column)                    (main stream, overlapped)
+//     publish the owned entries other ranks need
+//     interior tiles (no halo column)          -- overlaps the transfer
 //     boundary tiles, gathering halo columns from the landing buffer
 // and every Krylov dot product is completed by an all-reduce of 1-3 doubles.
-// Transport: NCCL (ncclSend/ncclRecv grouped per SpMV, ncclAllReduce per dot)
-// over NVLink/NVSwitch.
+//
+// Two transports:
+//  * peer memory (default): every rank exposes a small window through CUDA IPC;
+//    NVLink/NVSwitch makes it load/store addressable by all peers.  The push
+//    kernel stores halo entries straight into the consumers' landing buffers
+//    and publishes a sequence number; the boundary SpMV kernel itself waits on
+//    those flags (kernels_spmv.cu) and acknowledges consumption.  All-reduces
+//    are one warp: store the partial into every peer's inbox, wait for the P
+//    inbox entries, add them in rank order -- every rank gets bit-identical
+//    sums, so all ranks take the same stopping decision.  A few microseconds
+//    per collective instead of a library launch per message.
+//  * NCCL (SIGB_TRANSPORT=nccl, or when IPC mapping is unavailable): grouped
+//    ncclSend/ncclRecv on an auxiliary stream + ncclAllReduce.
+// NCCL is always used for bootstrap (exchanging IPC handles and layouts).
 #include <nccl.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <vector>
@@ -22,11 +36,30 @@
 #include "dist.h"
 #include "solvers.h"
 
+namespace sigb {
+
+struct RedEntry {
+    double v[3];
+    unsigned long long seq;
+};
+constexpr int kRedSlots = 4;
+struct RedWin {
+    RedEntry red[kRedSlots][kMaxRanks];  // [slot][source rank], written by the peers
+    unsigned long long red_seq;          // local: reductions completed
+};
+
+}  // namespace sigb
+
 struct sigb_comm_s {
     ncclComm_t nccl = nullptr;
     int rank = 0, nranks = 1;
-    cudaStream_t stream = nullptr;   // halo exchange stream
+    cudaStream_t stream = nullptr;   // NCCL halo exchange stream
     cudaEvent_t ev_pack = nullptr, ev_halo = nullptr;
+    bool p2p = false;
+    sigb::RedWin *red = nullptr;                     // this rank's inbox
+    sigb::RedWin *peer_red[sigb::kMaxRanks] = {};    // peers' inboxes (peer-mapped)
+    char *stage = nullptr;                           // device staging for bootstrap all-gathers
+    size_t stage_bytes = 0;
 };
 
 namespace sigb {
@@ -48,13 +81,97 @@ struct DistInfo {
     std::vector<int> send_cnt, send_off, recv_cnt, recv_off;
     int total_send = 0;
     int32_t *send_rows = nullptr;   // device, 1-based local rows, grouped by destination
-    double *sendbuf = nullptr;      // device, packed values
-    double *halo = nullptr;         // device, landing buffer (nhalo)
+    double *sendbuf = nullptr;      // device, packed values (NCCL transport)
+    double *halo = nullptr;         // device, landing buffer (NCCL transport)
     double *dot_tmp = nullptr;      // device, 2 doubles: interior partial sums
+    // peer-memory transport
+    HaloWin *win = nullptr;         // our window (flags + two landing buffers)
+    int64_t stride = 0;             // doubles between the two landing buffers
+    HaloSync sync;                  // what boundary launches need
+    struct PushPlan {
+        int send_off[kMaxRanks + 1];
+        double *dst[kMaxRanks];      // peer landing buffer 0, already offset to our slice
+        int64_t dst_stride[kMaxRanks];
+        HaloWin *peer[kMaxRanks];
+        uint32_t dst_mask;
+        int me, nranks;
+    } push;
 };
 
 namespace {
 
+// ---- bootstrap: all-gather of a few bytes per rank over NCCL ---------------
+int allgather_bytes(sigb_comm_t c, const void *mine, size_t bytes, void *all)
+{
+    const size_t need = bytes * (size_t)(c->nranks + 1);
+    if (c->stage_bytes < need) {
+        cudaFree(c->stage);
+        SIGB_CUDA(cudaMalloc((void **)&c->stage, need));
+        c->stage_bytes = need;
+    }
+    cudaStream_t st = ctx().stream;
+    char *send = c->stage, *recv = c->stage + bytes;
+    SIGB_CUDA(cudaMemcpyAsync(send, mine, bytes, cudaMemcpyHostToDevice, st));
+    SIGB_NCCL(ncclAllGather(send, recv, bytes, ncclChar, c->nccl, st));
+    SIGB_CUDA(cudaMemcpyAsync(all, recv, bytes * c->nranks, cudaMemcpyDeviceToHost, st));
+    SIGB_CUDA(cudaStreamSynchronize(st));
+    return SIGB_OK;
+}
+
+// Expose `ptr` (a cudaMalloc allocation) to all ranks; peers[q] receives the
+// address it is mapped at in this process.  Collective.
+int share_window(sigb_comm_t c, void *ptr, void **peers)
+{
+    cudaIpcMemHandle_t mine;
+    SIGB_CUDA(cudaIpcGetMemHandle(&mine, ptr));
+    std::vector<cudaIpcMemHandle_t> all((size_t)c->nranks);
+    SIGB_CHECK(allgather_bytes(c, &mine, sizeof(mine), all.data()));
+    for (int q = 0; q < c->nranks; q++) {
+        if (q == c->rank) {
+            peers[q] = ptr;
+        } else {
+            SIGB_CUDA(cudaIpcOpenMemHandle(&peers[q], all[q], cudaIpcMemLazyEnablePeerAccess));
+        }
+    }
+    return SIGB_OK;
+}
+
+// ---- peer-memory all-reduce: one warp -----------------------------------------
+struct RedArgs {
+    double *vals[3];
+    int count;
+    RedWin *win;
+    RedWin *peer[kMaxRanks];
+    int me, nranks;
+    const int *skip_flag;
+};
+
+__global__ void red_kernel(const RedArgs a)
+{
+    if (a.skip_flag != nullptr && *a.skip_flag != 0) return;
+    const int lane = threadIdx.x;
+    const unsigned long long s = a.win->red_seq + 1;
+    const int slot = (int)(s & (kRedSlots - 1));
+    if (lane < a.nranks) {
+        RedEntry *e = &a.peer[lane]->red[slot][a.me];
+        for (int c = 0; c < a.count; c++) e->v[c] = *a.vals[c];
+        __threadfence_system();
+        st_release_sys(&e->seq, s);
+        // wait for the entry rank `lane` wrote into OUR inbox
+        while (ld_acquire_sys(&a.win->red[slot][lane].seq) != s) {}
+    }
+    __syncwarp();
+    if (lane < a.count) {
+        double v = 0.0;
+        for (int q = 0; q < a.nranks; q++)   // rank order: identical result on every rank
+            v = add(v, *reinterpret_cast<volatile double *>(&a.win->red[slot][q].v[lane]));
+        *a.vals[lane] = v;
+    }
+    __syncwarp();
+    if (lane == 0) a.win->red_seq = s;
+}
+
+// ---- NCCL transport: pack into a contiguous send buffer -----------------------
 __global__ void __launch_bounds__(kThreads)
 pack_kernel(const double *__restrict__ x, const int32_t *__restrict__ rows1, int n,
             double *__restrict__ out, const int *skip_flag)
@@ -64,16 +181,67 @@ pack_kernel(const double *__restrict__ x, const int32_t *__restrict__ rows1, int
         out[k] = x[rows1[k] - 1];
 }
 
+// ---- peer-memory transport: store halo entries into the consumers' buffers ---
+__global__ void __launch_bounds__(kThreads)
+push_kernel(const double *__restrict__ x, const int32_t *__restrict__ rows1, int n,
+            HaloWin *win, const DistInfo::PushPlan p, const int *skip_flag)
+{
+    if (skip_flag != nullptr && *skip_flag != 0) return;
+    __shared__ unsigned long long s_seq;
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+        const unsigned long long s = *reinterpret_cast<volatile unsigned long long *>(&win->halo_seq) + 1;
+        // landing buffer (s & 1) was last used by SpMV s-2: wait until every
+        // consumer has acknowledged it
+        if (s > 2)
+            for (int q = 0; q < p.nranks; q++)
+                if (p.dst_mask & (1u << q))
+                    while (ld_acquire_sys(&win->ack[q]) < s - 2) {}
+        s_seq = s;
+    }
+    __syncthreads();
+    const unsigned long long s = s_seq;
+    const int buf = (int)(s & 1);
+    for (int k = blockIdx.x * kThreads + threadIdx.x; k < n; k += gridDim.x * kThreads) {
+        int q = 0;
+        while (k >= p.send_off[q + 1]) q++;
+        p.dst[q][buf * p.dst_stride[q] + (k - p.send_off[q])] = x[rows1[k] - 1];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(&win->push_ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        if (threadIdx.x < p.nranks && (p.dst_mask & (1u << threadIdx.x))) {
+            __threadfence_system();
+            st_release_sys(&p.peer[threadIdx.x]->hflag[buf][p.me], s);
+        }
+        if (threadIdx.x == 0) {
+            win->push_ticket = 0u;
+            *reinterpret_cast<volatile unsigned long long *>(&win->halo_seq) = s;
+        }
+    }
+}
+
 }  // namespace
 
 int64_t dist_global_n(sigb_matrix_t A) { return A->dist ? A->dist->n_global : A->nrow; }
 int64_t dist_row_offset(sigb_matrix_t A) { return A->dist ? A->dist->lo : 0; }
-int64_t dist_halo_len(sigb_matrix_t) { return 0; }  // halos land in the operator's own buffer
+int64_t dist_halo_len(sigb_matrix_t) { return 0; }  // halos land in the operator's own buffers
 
 int dist_destroy(sigb_matrix_t A)
 {
     DistInfo *D = A->dist;
     if (!D) return SIGB_OK;
+    cudaDeviceSynchronize();
+    if (D->win) {
+        for (int q = 0; q < D->comm->nranks; q++)
+            if (q != D->comm->rank && D->sync.peer[q]) cudaIpcCloseMemHandle(D->sync.peer[q]);
+        cudaFree(D->win);
+    }
     cudaFree(D->send_rows);
     cudaFree(D->sendbuf);
     cudaFree(D->halo);
@@ -83,23 +251,43 @@ int dist_destroy(sigb_matrix_t A)
     return SIGB_OK;
 }
 
-int dist_allreduce(sigb_matrix_t A, double *vals, int count)
+static int allreduce_ptrs(sigb_comm_t C, double *const *vals, int count, const int *skip_flag)
 {
-    DistInfo *D = A->dist;
-    if (!D || D->comm->nranks == 1) return SIGB_OK;
-    SIGB_NCCL(ncclAllReduce(vals, vals, (size_t)count, ncclDouble, ncclSum, D->comm->nccl, ctx().stream));
+    if (C->p2p) {
+        RedArgs a;
+        for (int c = 0; c < 3; c++) a.vals[c] = c < count ? vals[c] : nullptr;
+        a.count = count;
+        a.win = C->red;
+        for (int q = 0; q < kMaxRanks; q++) a.peer[q] = C->peer_red[q];
+        a.me = C->rank;
+        a.nranks = C->nranks;
+        a.skip_flag = skip_flag;
+        red_kernel<<<1, 32, 0, ctx().stream>>>(a);
+        count_launch();
+        SIGB_CUDA(cudaGetLastError());
+        return SIGB_OK;
+    }
+    if (count > 1) SIGB_NCCL(ncclGroupStart());
+    for (int c = 0; c < count; c++)
+        SIGB_NCCL(ncclAllReduce(vals[c], vals[c], 1, ncclDouble, ncclSum, C->nccl, ctx().stream));
+    if (count > 1) SIGB_NCCL(ncclGroupEnd());
     return SIGB_OK;
 }
 
-int dist_allreduce2(sigb_matrix_t A, double *a, double *b)
+int dist_allreduce(sigb_matrix_t A, double *vals, int count, const int *skip_flag)
 {
     DistInfo *D = A->dist;
     if (!D || D->comm->nranks == 1) return SIGB_OK;
-    SIGB_NCCL(ncclGroupStart());
-    SIGB_NCCL(ncclAllReduce(a, a, 1, ncclDouble, ncclSum, D->comm->nccl, ctx().stream));
-    SIGB_NCCL(ncclAllReduce(b, b, 1, ncclDouble, ncclSum, D->comm->nccl, ctx().stream));
-    SIGB_NCCL(ncclGroupEnd());
-    return SIGB_OK;
+    double *ptrs[3] = {vals, vals + 1, vals + 2};
+    return allreduce_ptrs(D->comm, ptrs, count, skip_flag);
+}
+
+int dist_allreduce2(sigb_matrix_t A, double *a, double *b, const int *skip_flag)
+{
+    DistInfo *D = A->dist;
+    if (!D || D->comm->nranks == 1) return SIGB_OK;
+    double *ptrs[3] = {a, b, nullptr};
+    return allreduce_ptrs(D->comm, ptrs, 2, skip_flag);
 }
 
 // y = A x (or y += A x) for the local row block; x holds the owned entries.
@@ -114,7 +302,14 @@ int dist_matvec(sigb_matrix_t A, const double *x, double *y, bool add, const Dot
     dot.nloc = D->nloc;
 
     const bool exchange = C->nranks > 1 && (D->total_send > 0 || D->nhalo > 0);
-    if (exchange) {
+    const bool p2p = exchange && C->p2p;
+    if (p2p) {
+        int grid = (D->total_send + kThreads - 1) / kThreads;
+        grid = std::max(1, std::min(grid, ctx().num_sms * 2));
+        push_kernel<<<grid, kThreads, 0, main>>>(x, D->send_rows, D->total_send, D->win, D->push, dot.skip_flag);
+        count_launch();
+        SIGB_CUDA(cudaGetLastError());
+    } else if (exchange) {
         if (D->total_send > 0) {
             int grid = (D->total_send + kThreads - 1) / kThreads;
             grid = std::min(grid, ctx().num_sms * 4);
@@ -136,11 +331,11 @@ int dist_matvec(sigb_matrix_t A, const double *x, double *y, bool add, const Dot
     }
 
     if (V.n_boundary == 0) {
-        // nothing depends on the halo: one launch over the interior list
-        if (exchange) SIGB_CUDA(cudaStreamWaitEvent(main, C->ev_halo, 0));
+        // nothing here depends on a halo: one launch over the interior list
+        if (exchange && !p2p) SIGB_CUDA(cudaStreamWaitEvent(main, C->ev_halo, 0));
         return launch_csr_spmv(V, A->val, x, y, mode, dot, 1, main, 0);
     }
-    // interior tiles overlap the exchange; their dot partials wait in dot_tmp
+    // interior tiles overlap the transfer; their dot partials wait in dot_tmp
     DotSpec di = dot;
     if (dot.ndot > 0) {
         di.out[0] = D->dot_tmp;
@@ -148,9 +343,13 @@ int dist_matvec(sigb_matrix_t A, const double *x, double *y, bool add, const Dot
     }
     if (V.n_interior > 0 || dot.ndot > 0)
         SIGB_CHECK(launch_csr_spmv(V, A->val, x, y, mode, di, 1, main, 0));
-    if (exchange) SIGB_CUDA(cudaStreamWaitEvent(main, C->ev_halo, 0));
     DotSpec db = dot;
-    db.halo = D->halo;
+    if (p2p) {
+        db.sync = &D->sync;           // the kernel waits on the flags itself
+    } else {
+        if (exchange) SIGB_CUDA(cudaStreamWaitEvent(main, C->ev_halo, 0));
+        db.halo = D->halo;
+    }
     if (dot.ndot > 0) {
         db.addend[0] = D->dot_tmp;
         db.addend[1] = dot.ndot > 1 ? D->dot_tmp + 1 : nullptr;
@@ -180,6 +379,7 @@ int sigb_comm_create(const void *unique_id, int rank, int nranks, sigb_comm_t *o
     SIGB_CHECK(require_init());
     SIGB_REQUIRE(unique_id && out && nranks >= 1 && rank >= 0 && rank < nranks, SIGB_ERR_ARG,
                  "sigb_comm_create: bad argument");
+    SIGB_REQUIRE(nranks <= kMaxRanks, SIGB_ERR_UNSUPPORTED, "sigb_comm_create: at most %d ranks (one box)", kMaxRanks);
     sigb_comm_t c = new sigb_comm_s();
     c->rank = rank;
     c->nranks = nranks;
@@ -189,6 +389,25 @@ int sigb_comm_create(const void *unique_id, int rank, int nranks, sigb_comm_t *o
     SIGB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SIGB_CUDA(cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming));
     SIGB_CUDA(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+
+    // peer-memory transport: share the all-reduce inbox; every rank must succeed
+    const char *tr = getenv("SIGB_TRANSPORT");
+    int want = (nranks > 1 && !(tr && !strcmp(tr, "nccl"))) ? 1 : 0;
+    if (want) {
+        int ok = 1;
+        if (cudaMalloc((void **)&c->red, sizeof(RedWin)) != cudaSuccess) ok = 0;
+        if (ok) cudaMemset(c->red, 0, sizeof(RedWin));
+        void *peers[kMaxRanks] = {};
+        if (ok && share_window(c, c->red, peers) != SIGB_OK) ok = 0;
+        cudaGetLastError();
+        std::vector<int> oks((size_t)nranks);
+        SIGB_CHECK(allgather_bytes(c, &ok, sizeof(int), oks.data()));
+        for (int q = 0; q < nranks; q++) ok = ok && oks[q];
+        if (ok) {
+            for (int q = 0; q < nranks; q++) c->peer_red[q] = (RedWin *)peers[q];
+            c->p2p = true;
+        }
+    }
     *out = c;
     return SIGB_OK;
 }
@@ -197,6 +416,12 @@ int sigb_comm_destroy(sigb_comm_t c)
 {
     if (!c) return SIGB_OK;
     cudaDeviceSynchronize();
+    if (c->red) {
+        for (int q = 0; q < c->nranks; q++)
+            if (q != c->rank && c->peer_red[q]) cudaIpcCloseMemHandle(c->peer_red[q]);
+        cudaFree(c->red);
+    }
+    cudaFree(c->stage);
     if (c->nccl) ncclCommDestroy(c->nccl);
     cudaStreamDestroy(c->stream);
     cudaEventDestroy(c->ev_pack);
@@ -210,7 +435,7 @@ int sigb_comm_info(sigb_comm_t c, int *rank, int *nranks, int *peer_access)
     SIGB_REQUIRE(c, SIGB_ERR_ARG, "sigb_comm_info: null communicator");
     if (rank) *rank = c->rank;
     if (nranks) *nranks = c->nranks;
-    if (peer_access) *peer_access = 0;
+    if (peer_access) *peer_access = c->p2p ? 1 : 0;
     return SIGB_OK;
 }
 
@@ -291,13 +516,57 @@ int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global, const int32_t *part
         SIGB_CUDA(cudaMemcpyAsync(V.tiles_boundary, tb.data(), sizeof(TileDesc) * tb.size(), cudaMemcpyHostToDevice, st));
 
     SIGB_CUDA(cudaMalloc((void **)&D->send_rows, sizeof(int32_t) * std::max(total_send, 1)));
-    SIGB_CUDA(cudaMalloc((void **)&D->sendbuf, sizeof(double) * std::max(total_send, 1)));
-    SIGB_CUDA(cudaMalloc((void **)&D->halo, sizeof(double) * std::max(nhalo, 1)));
     SIGB_CUDA(cudaMalloc((void **)&D->dot_tmp, sizeof(double) * 2));
-    SIGB_CUDA(cudaMemsetAsync(D->halo, 0, sizeof(double) * std::max(nhalo, 1), st));
     SIGB_CUDA(cudaMemsetAsync(D->dot_tmp, 0, sizeof(double) * 2, st));
     if (total_send > 0)
         SIGB_CUDA(cudaMemcpyAsync(D->send_rows, send_rows1, sizeof(int32_t) * total_send, cudaMemcpyHostToDevice, st));
+
+    if (comm->p2p) {
+        // window = flags + two landing buffers; tell every rank where our slice
+        // of ITS landing buffer starts (its recv offset for us) and its stride
+        D->stride = ((int64_t)nhalo + 15) & ~15LL;
+        const size_t bytes = sizeof(HaloWin) + sizeof(double) * 2 * (size_t)std::max<int64_t>(D->stride, 16);
+        SIGB_CUDA(cudaMalloc((void **)&D->win, bytes));
+        SIGB_CUDA(cudaMemsetAsync(D->win, 0, bytes, st));
+        SIGB_CUDA(cudaStreamSynchronize(st));
+        void *peers[kMaxRanks] = {};
+        SIGB_CHECK(share_window(comm, D->win, peers));
+        struct Layout { int64_t stride; int32_t recv_off[kMaxRanks]; int32_t recv_cnt[kMaxRanks]; } mine{}, all[kMaxRanks];
+        mine.stride = D->stride;
+        for (int q = 0; q < P; q++) { mine.recv_off[q] = D->recv_off[q]; mine.recv_cnt[q] = D->recv_cnt[q]; }
+        SIGB_CHECK(allgather_bytes(comm, &mine, sizeof(Layout), all));
+        D->sync.win = D->win;
+        D->sync.me = me;
+        D->sync.halo_base = reinterpret_cast<const double *>(D->win + 1);
+        D->sync.halo_stride = D->stride;
+        D->push.me = me;
+        D->push.nranks = P;
+        D->push.dst_mask = 0;
+        for (int q = 0; q < kMaxRanks; q++) {
+            D->sync.peer[q] = q < P ? (HaloWin *)peers[q] : nullptr;
+            D->push.peer[q] = D->sync.peer[q];
+            D->push.dst[q] = nullptr;
+            D->push.dst_stride[q] = 0;
+            D->push.send_off[q] = q < P ? D->send_off[q] : total_send;
+        }
+        D->push.send_off[kMaxRanks] = total_send;
+        for (int q = P; q <= kMaxRanks; q++) D->push.send_off[q] = total_send;
+        for (int q = 0; q < P; q++) {
+            if (D->recv_cnt[q] > 0) D->sync.src_mask |= 1u << q;
+            if (D->send_cnt[q] > 0) {
+                SIGB_REQUIRE(all[q].recv_cnt[me] == D->send_cnt[q], SIGB_ERR_ARG,
+                             "sigb_dist_csr_create: rank %d expects %d entries from rank %d, send list has %d", q,
+                             all[q].recv_cnt[me], me, D->send_cnt[q]);
+                D->push.dst_mask |= 1u << q;
+                D->push.dst[q] = reinterpret_cast<double *>((HaloWin *)peers[q] + 1) + all[q].recv_off[me];
+                D->push.dst_stride[q] = all[q].stride;
+            }
+        }
+    } else {
+        SIGB_CUDA(cudaMalloc((void **)&D->sendbuf, sizeof(double) * std::max(total_send, 1)));
+        SIGB_CUDA(cudaMalloc((void **)&D->halo, sizeof(double) * std::max(nhalo, 1)));
+        SIGB_CUDA(cudaMemsetAsync(D->halo, 0, sizeof(double) * std::max(nhalo, 1), st));
+    }
     SIGB_CUDA(cudaStreamSynchronize(st));
 
     sigb_matrix_t A = nullptr;

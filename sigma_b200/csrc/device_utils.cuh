@@ -49,6 +49,33 @@ __device__ __forceinline__ double ld_stream_d(const double *p)
 }
 
 // ---------------------------------------------------------------------------
+// System-scope flag accesses for the peer-memory (NVLink) transport.  Data is
+// written with plain stores, then published with a release store of a
+// sequence number; consumers spin on an acquire load.  Peer-written data is
+// read with ld.global.cg (L2 is the coherence point; L1 may be stale).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Window of a row-sharded operator: everything peers write into this rank.
+struct HaloWin {
+    unsigned long long hflag[2][kMaxRanks];  // [buffer][source]: sequence number of the halo it holds
+    unsigned long long ack[kMaxRanks];       // [consumer]: last sequence that consumer finished reading
+    unsigned long long halo_seq;             // local: sequence of the current SpMV
+    unsigned int push_ticket, done_ticket;   // local: last-CTA detection
+    unsigned long long pad_[4];
+    // followed by the two landing buffers
+};
+
+// ---------------------------------------------------------------------------
 // Deterministic grid reduction.
 //
 // Each thread brings ND partial sums.  They are combined with a fixed shuffle

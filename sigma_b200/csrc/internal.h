@@ -155,6 +155,19 @@ struct DotSpec {
     const double *addend[2] = {nullptr, nullptr};  // partial sums of an earlier launch, added to the totals
     const double *halo = nullptr;         // row-sharded: values of columns nloc+1.. (halo landing buffer)
     int32_t nloc = 0;                     // row-sharded: number of owned columns
+    const struct HaloSync *sync = nullptr;  // peer-memory transport: flags to wait on / acknowledge
+};
+
+// Peer-memory halo synchronisation handed to a boundary launch (comm.cu).
+constexpr int kMaxRanks = 8;
+struct HaloWin;  // device-resident, IPC-shared (comm.cu)
+struct HaloSync {
+    HaloWin *win = nullptr;               // this rank's window
+    HaloWin *peer[kMaxRanks] = {};        // the peers' windows (peer-mapped)
+    uint32_t src_mask = 0;                // ranks we receive halo entries from
+    int me = 0;
+    const double *halo_base = nullptr;    // two landing buffers, halo_stride apart
+    int64_t halo_stride = 0;
 };
 
 // which: 0 = all tiles, 1 = interior subset, 2 = boundary subset

@@ -64,6 +64,7 @@ struct CsrKernelArgs {
     const double *h1;         // halo - (nloc + 1): indexable by column ids > nloc
     int32_t nloc;             // owned columns (HALO kernels)
     const double *add0, *add1;  // optional addends folded into the dot totals
+    HaloSync sync;            // peer-memory transport (sync.win == nullptr: none)
 };
 
 __device__ __forceinline__ int4 load_desc(const TileDesc *t)
@@ -140,13 +141,13 @@ __device__ __forceinline__ void emit_row(const CsrKernelArgs &a, int r, double z
 
 // one row longer than a tile: CTA-wide fixed-tree reduction, direct loads
 template <int MODE, int NDOT, bool HALO>
-__device__ __forceinline__ void long_row(const CsrKernelArgs &a, const int4 &d, double *acc)
+__device__ __forceinline__ void long_row(const CsrKernelArgs &a, const int4 &d, const double *h1, double *acc)
 {
     __shared__ double smr[1][kThreads / 32];
     double s[1] = {0.0};
     for (int k = d.z + threadIdx.x; k < d.w; k += kThreads) {
         const int c = a.node[k];
-        const double xv = (HALO && c > a.nloc) ? __ldcg(a.h1 + c) : __ldg(a.x1 + c);
+        const double xv = (HALO && c > a.nloc) ? __ldcg(h1 + c) : __ldg(a.x1 + c);
         s[0] = add(s[0], mul(a.val[k], xv));
     }
     block_tree<1>(s, smr);
@@ -196,6 +197,24 @@ csr_tma_kernel(const CsrKernelArgs a)
     double acc[NDOT > 0 ? NDOT : 1];
 #pragma unroll
     for (int d = 0; d < (NDOT > 0 ? NDOT : 1); d++) acc[d] = 0.0;
+
+    // peer-memory transport: wait until every source rank has published the
+    // halo of this SpMV (sequence number written by our own push kernel)
+    const double *h1 = a.h1;
+    unsigned long long hseq = 0;
+    if (HALO && a.sync.win != nullptr) {
+        __shared__ unsigned long long s_seq;
+        if (tid == 0) {
+            const unsigned long long s = *reinterpret_cast<volatile unsigned long long *>(&a.sync.win->halo_seq);
+            for (int q = 0; q < kMaxRanks; q++)
+                if (a.sync.src_mask & (1u << q))
+                    while (ld_acquire_sys(&a.sync.win->hflag[s & 1][q]) < s) {}
+            s_seq = s;
+        }
+        __syncthreads();
+        hseq = s_seq;
+        h1 = a.sync.halo_base + (hseq & 1) * a.sync.halo_stride - (a.nloc + 1);
+    }
 
     // thread 0 is the producer: it programs the TMA engine for one tile
     auto issue = [&](int stage, const int4 &d) {
@@ -258,7 +277,7 @@ csr_tma_kernel(const CsrKernelArgs a)
             double xv[kTileNnz / kThreads];
 #pragma unroll
             for (int i = 0; i < kTileNnz / kThreads; i++) {
-                if (HALO && c[i] > a.nloc) xv[i] = __ldcg(a.h1 + c[i]);   // written by peers: not via the nc path
+                if (HALO && c[i] > a.nloc) xv[i] = __ldcg(h1 + c[i]);   // written by peers: not via the nc path
                 else xv[i] = __ldg(a.x1 + c[i]);
             }
 #pragma unroll
@@ -283,13 +302,28 @@ csr_tma_kernel(const CsrKernelArgs a)
             fence_proxy_async();
             __syncthreads();
         } else {
-            long_row<MODE, NDOT, HALO>(a, d_cur, acc);
+            long_row<MODE, NDOT, HALO>(a, d_cur, h1, acc);
         }
         sidx = sidx_after;
         d_cur = d_next;
         d_next = d_next2;
     }
     finish_dots<NDOT>(a, acc);
+
+    // peer-memory transport: the last CTA tells every source rank that this
+    // landing buffer has been consumed
+    if (HALO && a.sync.win != nullptr) {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            const unsigned t2 = atomicAdd(&a.sync.win->done_ticket, 1u);
+            if (t2 == gridDim.x - 1) {
+                a.sync.win->done_ticket = 0u;
+                for (int q = 0; q < kMaxRanks; q++)
+                    if (a.sync.src_mask & (1u << q)) st_release_sys(&a.sync.peer[q]->ack[a.sync.me], hseq);
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -474,7 +508,8 @@ int launch_csr_spmv(const CsrView &A, const double *val, const double *x, double
     a.add1 = dot.addend[1];
     a.nloc = dot.nloc;
     a.h1 = dot.halo ? dot.halo - (dot.nloc + 1) : nullptr;
-    const bool halo = dot.halo != nullptr;
+    if (dot.sync) a.sync = *dot.sync;
+    const bool halo = dot.halo != nullptr || dot.sync != nullptr;
     cudaStream_t st = stream ? stream : ctx().stream;
     if (a.ntiles == 0 && dot.ndot == 0) return SIGB_OK;
 

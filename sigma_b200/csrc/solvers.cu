@@ -593,10 +593,10 @@ int cg_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x, const double *b, s
             d.out[0] = &st->pq;
             d.skip_flag = &st->done[par];
             SIGB_CHECK(solver_matvec(A, p, q, d, /*x_has_halo=*/true));   // q = A p ; dpr = p.q
-            SIGB_CHECK(dist_allreduce(A, &st->pq, 1));
+            SIGB_CHECK(dist_allreduce(A, &st->pq, 1, &st->done[par]));
             CgUpdateOp up{p, q, idiag, x, r, z, st, par, 0.0};
             SIGB_CHECK(launch_ew(up, n));
-            SIGB_CHECK(dist_allreduce(A, &st->rr[par ^ 1], 1));
+            SIGB_CHECK(dist_allreduce(A, &st->rr[par ^ 1], 1, &st->done[par]));
             CgDirectionOp dir{idiag ? z : r, p, st, par, 0.0};
             SIGB_CHECK(launch_ew(dir, n));
             par ^= 1;
@@ -640,7 +640,7 @@ int bicgstab_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x, const double
             d1.skip_flag = &st->done[par];
             d1.row_scale = idiag;
             SIGB_CHECK(solver_matvec(A, p, v, d1, true));
-            SIGB_CHECK(dist_allreduce(A, &st->pq, 1));
+            SIGB_CHECK(dist_allreduce(A, &st->pq, 1, &st->done[par]));
             BicgSOp sop{r, v, sv, st, par, 0.0};
             SIGB_CHECK(launch_ew(sop, n));
             DotSpec d2;                      // t = [M] A s ; s.t, t.t
@@ -651,10 +651,10 @@ int bicgstab_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x, const double
             d2.skip_flag = &st->done[par];
             d2.row_scale = idiag;
             SIGB_CHECK(solver_matvec(A, sv, t, d2, true));
-            SIGB_CHECK(dist_allreduce(A, &st->st, 2));
+            SIGB_CHECK(dist_allreduce(A, &st->st, 2, &st->done[par]));
             BicgUpdateOp up{p, sv, t, r0, x, r, st, par, pc ? 0 : 1, 0.0, 0.0};
             SIGB_CHECK(launch_ew(up, n));
-            SIGB_CHECK(dist_allreduce2(A, &st->rr[par ^ 1], &st->rho[par ^ 1]));
+            SIGB_CHECK(dist_allreduce2(A, &st->rr[par ^ 1], &st->rho[par ^ 1], &st->done[par]));
             BicgDirectionOp dir{r, v, p, st, par ^ 1, 0, 0.0, 0.0};
             SIGB_CHECK(launch_ew(dir, n));
             par ^= 1;

@@ -49,8 +49,10 @@ size_t kstate_bytes();
 int solver_matvec(sigb_matrix_t A, const double *x, double *y, const DotSpec &dot,
                   bool x_has_halo);
 // Sum `count` contiguous device doubles over all ranks (no-op on one GPU).
-int dist_allreduce(sigb_matrix_t A, double *vals, int count);
-int dist_allreduce2(sigb_matrix_t A, double *a, double *b);
+// skip_flag: device int; when non-zero at execution time the reduction is a
+// no-op (iterations launched past the stopping test), on every rank alike.
+int dist_allreduce(sigb_matrix_t A, double *vals, int count, const int *skip_flag = nullptr);
+int dist_allreduce2(sigb_matrix_t A, double *a, double *b, const int *skip_flag = nullptr);
 // extra elements a work vector needs behind its owned part (0 on one GPU)
 int64_t dist_halo_len(sigb_matrix_t A);
 

@@ -53,6 +53,13 @@ class Comm:
         check(lib().sigb_comm_create(ptr(uid), rank, world, C.byref(h)))
         return cls(h, rank, world)
 
+    @property
+    def transport(self):
+        """'peer-memory' (IPC windows over NVLink) or 'nccl'."""
+        r, n, p = C.c_int(), C.c_int(), C.c_int()
+        check(lib().sigb_comm_info(self._h, C.byref(r), C.byref(n), C.byref(p)))
+        return "peer-memory" if p.value else "nccl"
+
     def destroy(self):
         if self._h:
             check(lib().sigb_comm_destroy(self._h))

@@ -145,7 +145,7 @@ def main():
         np.save("/tmp/sigb_lanczos_q1.npy", V1)
     dist.barrier()
     if rank == 0:
-        print(f"dist gpu ok (world {world}, launches {sb.launch_count()})")
+        print(f"dist gpu ok (world {world}, transport {comm.transport}, launches {sb.launch_count()})")
     dist.destroy_process_group()
 
 

@@ -20,8 +20,9 @@ def free_port():
     return p
 
 
+@pytest.mark.parametrize("transport", ["p2p", "nccl"])
 @pytest.mark.parametrize("world", [1, 2, 4])
-def test_row_sharded_parity(world):
+def test_row_sharded_parity(world, transport):
     import torch
 
     if torch.cuda.device_count() < world:
@@ -29,6 +30,15 @@ def test_row_sharded_parity(world):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
            os.path.join(ROOT, "tests", "dist_gpu_worker.py")]
-    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    if world == 1 and transport == "nccl":
+        pytest.skip("one rank exchanges nothing")
+    env = dict(os.environ)
+    if transport == "nccl":
+        env["SIGB_TRANSPORT"] = "nccl"
+    else:
+        env.pop("SIGB_TRANSPORT", None)
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
     assert "dist gpu ok" in r.stdout
+    if world > 1:
+        assert f"transport {'peer-memory' if transport == 'p2p' else 'nccl'}" in r.stdout, r.stdout[-500:]
