@@ -21,3 +21,10 @@ for n in 1 2 4 8; do
     cat $OUT/bench_n$n.json | tee -a $OUT/summary.txt; tail -8 $OUT/bench_n$n.err | tee -a $OUT/summary.txt
   fi
 done
+if [ "${NCU:-0}" = "1" ]; then
+  echo "== ncu full: csr_tma (1 NDOT=0 + 2 NDOT=1 active launches) and CG vector kernels" | tee -a $OUT/summary.txt
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:csr_tma -s 20 -c 3 -f -o $OUT/prof_csr \
+      python bench.py --steps 48 --warmup 3 --no-cpu > $OUT/ncu_csr.log 2>&1; echo "rc=$?" | tee -a $OUT/summary.txt
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"CgUpdateOp|CgDirectionOp" -s 40 -c 2 -f -o $OUT/prof_ew \
+      python bench.py --steps 48 --warmup 3 --no-cpu > $OUT/ncu_ew.log 2>&1; echo "rc=$?" | tee -a $OUT/summary.txt
+fi

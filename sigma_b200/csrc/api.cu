@@ -64,9 +64,7 @@ static void free_view(CsrView &v)
 {
     cudaFree(v.ptr);
     cudaFree(v.node);
-    cudaFree(v.tiles);
-    cudaFree(v.tiles_interior);
-    cudaFree(v.tiles_boundary);
+    cudaFree(v.tiles);   // tiles_interior / tiles_boundary are views into it
     v = CsrView();
 }
 

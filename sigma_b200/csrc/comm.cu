@@ -331,11 +331,18 @@ int dist_matvec(sigb_matrix_t A, const double *x, double *y, bool add, const Dot
     }
 
     if (V.n_boundary == 0) {
-        // nothing here depends on a halo: one launch over the interior list
+        // nothing here depends on a halo: one launch over all tiles
         if (exchange && !p2p) SIGB_CUDA(cudaStreamWaitEvent(main, C->ev_halo, 0));
-        return launch_csr_spmv(V, A->val, x, y, mode, dot, 1, main, 0);
+        return launch_csr_spmv(V, A->val, x, y, mode, dot, 0, main, 0);
     }
-    // interior tiles overlap the transfer; their dot partials wait in dot_tmp
+    if (p2p) {
+        // ONE launch: tiles are stored interior first, boundary last; each CTA
+        // waits on the peers' flags only when it reaches its first boundary tile
+        DotSpec db = dot;
+        db.sync = &D->sync;
+        return launch_csr_spmv(V, A->val, x, y, mode, db, 0, main, 0);
+    }
+    // NCCL: interior tiles overlap the exchange; their dot partials wait in dot_tmp
     DotSpec di = dot;
     if (dot.ndot > 0) {
         di.out[0] = D->dot_tmp;
@@ -343,13 +350,9 @@ int dist_matvec(sigb_matrix_t A, const double *x, double *y, bool add, const Dot
     }
     if (V.n_interior > 0 || dot.ndot > 0)
         SIGB_CHECK(launch_csr_spmv(V, A->val, x, y, mode, di, 1, main, 0));
+    if (exchange) SIGB_CUDA(cudaStreamWaitEvent(main, C->ev_halo, 0));
     DotSpec db = dot;
-    if (p2p) {
-        db.sync = &D->sync;           // the kernel waits on the flags itself
-    } else {
-        if (exchange) SIGB_CUDA(cudaStreamWaitEvent(main, C->ev_halo, 0));
-        db.halo = D->halo;
-    }
+    db.halo = D->halo;
     if (dot.ndot > 0) {
         db.addend[0] = D->dot_tmp;
         db.addend[1] = dot.ndot > 1 ? D->dot_tmp + 1 : nullptr;
@@ -504,17 +507,18 @@ int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global, const int32_t *part
         for (int32_t k = t.ks; k < t.ke && !boundary; k++) boundary = local[k] > nloc;
         (boundary ? tb : ti).push_back(t);
     }
+    // the device tile table is re-ordered: interior tiles first, boundary last
     CsrView &V = g->stored;
     V.n_interior = (int32_t)ti.size();
     V.n_boundary = (int32_t)tb.size();
     cudaStream_t st = ctx().stream;
-    SIGB_CUDA(cudaMalloc((void **)&V.tiles_interior, sizeof(TileDesc) * std::max<size_t>(ti.size(), 1)));
-    SIGB_CUDA(cudaMalloc((void **)&V.tiles_boundary, sizeof(TileDesc) * std::max<size_t>(tb.size(), 1)));
-    if (!ti.empty())
-        SIGB_CUDA(cudaMemcpyAsync(V.tiles_interior, ti.data(), sizeof(TileDesc) * ti.size(), cudaMemcpyHostToDevice, st));
-    if (!tb.empty())
-        SIGB_CUDA(cudaMemcpyAsync(V.tiles_boundary, tb.data(), sizeof(TileDesc) * tb.size(), cudaMemcpyHostToDevice, st));
-
+    std::vector<TileDesc> ordered(ti);
+    ordered.insert(ordered.end(), tb.begin(), tb.end());
+    if (!ordered.empty())
+        SIGB_CUDA(cudaMemcpyAsync(V.tiles, ordered.data(), sizeof(TileDesc) * ordered.size(), cudaMemcpyHostToDevice, st));
+    SIGB_CUDA(cudaStreamSynchronize(st));
+    V.tiles_interior = V.tiles;                  // views into the same table
+    V.tiles_boundary = V.tiles + V.n_interior;
     SIGB_CUDA(cudaMalloc((void **)&D->send_rows, sizeof(int32_t) * std::max(total_send, 1)));
     SIGB_CUDA(cudaMalloc((void **)&D->dot_tmp, sizeof(double) * 2));
     SIGB_CUDA(cudaMemsetAsync(D->dot_tmp, 0, sizeof(double) * 2, st));

@@ -65,6 +65,7 @@ struct CsrKernelArgs {
     int32_t nloc;             // owned columns (HALO kernels)
     const double *add0, *add1;  // optional addends folded into the dot totals
     HaloSync sync;            // peer-memory transport (sync.win == nullptr: none)
+    int32_t first_halo_tile;  // tiles from this index on read halo columns
 };
 
 __device__ __forceinline__ int4 load_desc(const TileDesc *t)
@@ -198,23 +199,14 @@ csr_tma_kernel(const CsrKernelArgs a)
 #pragma unroll
     for (int d = 0; d < (NDOT > 0 ? NDOT : 1); d++) acc[d] = 0.0;
 
-    // peer-memory transport: wait until every source rank has published the
-    // halo of this SpMV (sequence number written by our own push kernel)
+    // peer-memory transport: tiles [first_halo_tile, ntiles) read halo columns.
+    // A CTA walks its tiles in ascending order, so it reaches them last and
+    // only then waits until every source rank has published the halo of this
+    // SpMV (sequence number left by our own push kernel) -- by which time the
+    // transfer has long been overlapped by the interior tiles.
     const double *h1 = a.h1;
-    unsigned long long hseq = 0;
-    if (HALO && a.sync.win != nullptr) {
-        __shared__ unsigned long long s_seq;
-        if (tid == 0) {
-            const unsigned long long s = *reinterpret_cast<volatile unsigned long long *>(&a.sync.win->halo_seq);
-            for (int q = 0; q < kMaxRanks; q++)
-                if (a.sync.src_mask & (1u << q))
-                    while (ld_acquire_sys(&a.sync.win->hflag[s & 1][q]) < s) {}
-            s_seq = s;
-        }
-        __syncthreads();
-        hseq = s_seq;
-        h1 = a.sync.halo_base + (hseq & 1) * a.sync.halo_stride - (a.nloc + 1);
-    }
+    bool halo_ready = !(HALO && a.sync.win != nullptr);
+    __shared__ unsigned long long s_seq;
 
     // thread 0 is the producer: it programs the TMA engine for one tile
     auto issue = [&](int stage, const int4 &d) {
@@ -243,6 +235,19 @@ csr_tma_kernel(const CsrKernelArgs a)
         const bool staged = tile_staged(d_cur);
         const unsigned sidx_after = sidx + (staged ? 1u : 0u);
         if (tid == 0 && have_next && tile_staged(d_next)) issue((int)(sidx_after & 1u), d_next);
+
+        if (HALO && !halo_ready && t >= a.first_halo_tile) {   // CTA-uniform
+            if (tid == 0) {
+                const unsigned long long s = *reinterpret_cast<volatile unsigned long long *>(&a.sync.win->halo_seq);
+                for (int q = 0; q < kMaxRanks; q++)
+                    if (a.sync.src_mask & (1u << q))
+                        while (ld_acquire_sys(&a.sync.win->hflag[s & 1][q]) < s) {}
+                s_seq = s;
+            }
+            __syncthreads();
+            h1 = a.sync.halo_base + (s_seq & 1) * a.sync.halo_stride - (a.nloc + 1);
+            halo_ready = true;
+        }
 
         if (staged) {
             const int stage = (int)(sidx & 1u);
@@ -319,6 +324,8 @@ csr_tma_kernel(const CsrKernelArgs a)
             const unsigned t2 = atomicAdd(&a.sync.win->done_ticket, 1u);
             if (t2 == gridDim.x - 1) {
                 a.sync.win->done_ticket = 0u;
+                const unsigned long long hseq =
+                    *reinterpret_cast<volatile unsigned long long *>(&a.sync.win->halo_seq);
                 for (int q = 0; q < kMaxRanks; q++)
                     if (a.sync.src_mask & (1u << q)) st_release_sys(&a.sync.peer[q]->ack[a.sync.me], hseq);
             }
@@ -509,6 +516,7 @@ int launch_csr_spmv(const CsrView &A, const double *val, const double *x, double
     a.nloc = dot.nloc;
     a.h1 = dot.halo ? dot.halo - (dot.nloc + 1) : nullptr;
     if (dot.sync) a.sync = *dot.sync;
+    a.first_halo_tile = (which == 0 && dot.sync) ? A.n_interior : 0;
     const bool halo = dot.halo != nullptr || dot.sync != nullptr;
     cudaStream_t st = stream ? stream : ctx().stream;
     if (a.ntiles == 0 && dot.ndot == 0) return SIGB_OK;
