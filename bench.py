@@ -255,6 +255,17 @@ def run_ours(args):
     assert it_done == K, (it_done, K)
     cg_rate = K / (ms_cg * 1e-3)
 
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"variant": os.environ.get("SIGB_LIB_VARIANT", ""), "n_gpus": world,
+                              "cg_it_s": cg_rate, "ms_per_iter": ms_cg / K, "spmv_us": ms_spmv * 1e3,
+                              "spmv_dot_us": ms_spmv_dot * 1e3,
+                              "spmv_frac": (12 * nnz_loc + 20 * nloc + 4) / (ms_spmv * 1e-3) / 1e9 / hbm_peak}), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return None
+
     # ---- e2e: host buffers through sigb_solver_solve ----------------------
     solver.setup(A)
     x_pin.zero_()
@@ -339,6 +350,7 @@ def main():
     ap.add_argument("--grid", type=int, default=4096)
     ap.add_argument("--cpu-iters", type=int, default=30)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="kernel A/B runs: print a short line, skip e2e and the CPU leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsigma_b200.so")
+# SIGB_LIB_VARIANT selects an experimental build (csrc/Makefile VARIANT=...); default: the product library
+LIB_PATH = os.path.join(_HERE, "lib", "libsigma_b200%s.so" % os.environ.get("SIGB_LIB_VARIANT", ""))
 
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NONSQUARE, ERR_ISOLATED, ERR_COMM, ERR_UNSUPPORTED = range(8)
 ROW, COL = 0, 1

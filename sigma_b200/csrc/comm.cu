@@ -38,14 +38,18 @@
 
 namespace sigb {
 
+// One fp64 value in flight, "LL" style: each 8-byte word carries 32 payload
+// bits and a 32-bit sequence flag.  An aligned 8-byte store is delivered as a
+// unit, so a word is either old or complete: no fence between payload and
+// flag, one NVLink store latency per all-reduce.
 struct RedEntry {
-    double v[3];
-    unsigned long long seq;
+    unsigned int lo, flag_lo, hi, flag_hi;
 };
 constexpr int kRedSlots = 4;
+constexpr int kRedVals = 3;
 struct RedWin {
-    RedEntry red[kRedSlots][kMaxRanks];  // [slot][source rank], written by the peers
-    unsigned long long red_seq;          // local: reductions completed
+    RedEntry red[kRedSlots][kMaxRanks][kRedVals];  // [slot][source rank][value], written by the peers
+    unsigned long long red_seq;                    // local: reductions completed
 };
 
 }  // namespace sigb
@@ -88,14 +92,6 @@ struct DistInfo {
     HaloWin *win = nullptr;         // our window (flags + two landing buffers)
     int64_t stride = 0;             // doubles between the two landing buffers
     HaloSync sync;                  // what boundary launches need
-    struct PushPlan {
-        int send_off[kMaxRanks + 1];
-        double *dst[kMaxRanks];      // peer landing buffer 0, already offset to our slice
-        int64_t dst_stride[kMaxRanks];
-        HaloWin *peer[kMaxRanks];
-        uint32_t dst_mask;
-        int me, nranks;
-    } push;
 };
 
 namespace {
@@ -146,25 +142,48 @@ struct RedArgs {
     const int *skip_flag;
 };
 
+__device__ __forceinline__ void st_word(unsigned int *p, unsigned int payload, unsigned int flag)
+{
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(flag) : "memory");
+}
+__device__ __forceinline__ uint2 ld_word(const unsigned int *p)
+{
+    uint2 r;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+    return r;
+}
+
+// One warp.  Lane q < nranks stores this rank's partial sums into rank q's
+// inbox and then polls the entry rank q stored into ours; lanes c < count add
+// the nranks contributions in rank order, so every rank computes bit-identical
+// totals and all ranks take the same stopping decision.  A slot is reused every
+// kRedSlots reductions; an all-reduce is a full barrier, so no rank can be that
+// far ahead.
 __global__ void red_kernel(const RedArgs a)
 {
     if (a.skip_flag != nullptr && *a.skip_flag != 0) return;
     const int lane = threadIdx.x;
     const unsigned long long s = a.win->red_seq + 1;
     const int slot = (int)(s & (kRedSlots - 1));
+    const unsigned int flag = (unsigned int)s;
     if (lane < a.nranks) {
-        RedEntry *e = &a.peer[lane]->red[slot][a.me];
-        for (int c = 0; c < a.count; c++) e->v[c] = *a.vals[c];
-        __threadfence_system();
-        st_release_sys(&e->seq, s);
-        // wait for the entry rank `lane` wrote into OUR inbox
-        while (ld_acquire_sys(&a.win->red[slot][lane].seq) != s) {}
+        RedEntry *e = a.peer[lane]->red[slot][a.me];
+        for (int c = 0; c < a.count; c++) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(*a.vals[c]);
+            st_word(&e[c].lo, (unsigned int)bits, flag);
+            st_word(&e[c].hi, (unsigned int)(bits >> 32), flag);
+        }
     }
     __syncwarp();
     if (lane < a.count) {
         double v = 0.0;
-        for (int q = 0; q < a.nranks; q++)   // rank order: identical result on every rank
-            v = add(v, *reinterpret_cast<volatile double *>(&a.win->red[slot][q].v[lane]));
+        for (int q = 0; q < a.nranks; q++) {   // rank order
+            const RedEntry *e = &a.win->red[slot][q][lane];
+            uint2 lo, hi;
+            do { lo = ld_word(&e->lo); } while (lo.y != flag);
+            do { hi = ld_word(&e->hi); } while (hi.y != flag);
+            v = add(v, __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | lo.x)));
+        }
         *a.vals[lane] = v;
     }
     __syncwarp();
@@ -179,51 +198,6 @@ pack_kernel(const double *__restrict__ x, const int32_t *__restrict__ rows1, int
     if (skip_flag != nullptr && *skip_flag != 0) return;
     for (int k = blockIdx.x * kThreads + threadIdx.x; k < n; k += gridDim.x * kThreads)
         out[k] = x[rows1[k] - 1];
-}
-
-// ---- peer-memory transport: store halo entries into the consumers' buffers ---
-__global__ void __launch_bounds__(kThreads)
-push_kernel(const double *__restrict__ x, const int32_t *__restrict__ rows1, int n,
-            HaloWin *win, const DistInfo::PushPlan p, const int *skip_flag)
-{
-    if (skip_flag != nullptr && *skip_flag != 0) return;
-    __shared__ unsigned long long s_seq;
-    __shared__ bool is_last;
-    if (threadIdx.x == 0) {
-        const unsigned long long s = *reinterpret_cast<volatile unsigned long long *>(&win->halo_seq) + 1;
-        // landing buffer (s & 1) was last used by SpMV s-2: wait until every
-        // consumer has acknowledged it
-        if (s > 2)
-            for (int q = 0; q < p.nranks; q++)
-                if (p.dst_mask & (1u << q))
-                    while (ld_acquire_sys(&win->ack[q]) < s - 2) {}
-        s_seq = s;
-    }
-    __syncthreads();
-    const unsigned long long s = s_seq;
-    const int buf = (int)(s & 1);
-    for (int k = blockIdx.x * kThreads + threadIdx.x; k < n; k += gridDim.x * kThreads) {
-        int q = 0;
-        while (k >= p.send_off[q + 1]) q++;
-        p.dst[q][buf * p.dst_stride[q] + (k - p.send_off[q])] = x[rows1[k] - 1];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned t = atomicAdd(&win->push_ticket, 1u);
-        is_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (is_last) {
-        if (threadIdx.x < p.nranks && (p.dst_mask & (1u << threadIdx.x))) {
-            __threadfence_system();
-            st_release_sys(&p.peer[threadIdx.x]->hflag[buf][p.me], s);
-        }
-        if (threadIdx.x == 0) {
-            win->push_ticket = 0u;
-            *reinterpret_cast<volatile unsigned long long *>(&win->halo_seq) = s;
-        }
-    }
 }
 
 }  // namespace
@@ -304,11 +278,10 @@ int dist_matvec(sigb_matrix_t A, const double *x, double *y, bool add, const Dot
     const bool exchange = C->nranks > 1 && (D->total_send > 0 || D->nhalo > 0);
     const bool p2p = exchange && C->p2p;
     if (p2p) {
-        int grid = (D->total_send + kThreads - 1) / kThreads;
-        grid = std::max(1, std::min(grid, ctx().num_sms * 2));
-        push_kernel<<<grid, kThreads, 0, main>>>(x, D->send_rows, D->total_send, D->win, D->push, dot.skip_flag);
-        count_launch();
-        SIGB_CUDA(cudaGetLastError());
+        // ONE kernel does push + interior + (wait) + boundary + acknowledge
+        DotSpec db = dot;
+        db.sync = &D->sync;
+        return launch_csr_spmv(V, A->val, x, y, mode, db, 0, main, 0);
     } else if (exchange) {
         if (D->total_send > 0) {
             int grid = (D->total_send + kThreads - 1) / kThreads;
@@ -332,15 +305,8 @@ int dist_matvec(sigb_matrix_t A, const double *x, double *y, bool add, const Dot
 
     if (V.n_boundary == 0) {
         // nothing here depends on a halo: one launch over all tiles
-        if (exchange && !p2p) SIGB_CUDA(cudaStreamWaitEvent(main, C->ev_halo, 0));
+        if (exchange) SIGB_CUDA(cudaStreamWaitEvent(main, C->ev_halo, 0));
         return launch_csr_spmv(V, A->val, x, y, mode, dot, 0, main, 0);
-    }
-    if (p2p) {
-        // ONE launch: tiles are stored interior first, boundary last; each CTA
-        // waits on the peers' flags only when it reaches its first boundary tile
-        DotSpec db = dot;
-        db.sync = &D->sync;
-        return launch_csr_spmv(V, A->val, x, y, mode, db, 0, main, 0);
     }
     // NCCL: interior tiles overlap the exchange; their dot partials wait in dot_tmp
     DotSpec di = dot;
@@ -543,27 +509,23 @@ int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global, const int32_t *part
         D->sync.me = me;
         D->sync.halo_base = reinterpret_cast<const double *>(D->win + 1);
         D->sync.halo_stride = D->stride;
-        D->push.me = me;
-        D->push.nranks = P;
-        D->push.dst_mask = 0;
+        D->sync.send_rows = D->send_rows;
+        D->sync.total_send = total_send;
         for (int q = 0; q < kMaxRanks; q++) {
             D->sync.peer[q] = q < P ? (HaloWin *)peers[q] : nullptr;
-            D->push.peer[q] = D->sync.peer[q];
-            D->push.dst[q] = nullptr;
-            D->push.dst_stride[q] = 0;
-            D->push.send_off[q] = q < P ? D->send_off[q] : total_send;
+            D->sync.dst[q] = nullptr;
+            D->sync.dst_stride[q] = 0;
         }
-        D->push.send_off[kMaxRanks] = total_send;
-        for (int q = P; q <= kMaxRanks; q++) D->push.send_off[q] = total_send;
+        for (int q = 0; q <= kMaxRanks; q++) D->sync.send_off[q] = q < P ? D->send_off[q] : total_send;
         for (int q = 0; q < P; q++) {
             if (D->recv_cnt[q] > 0) D->sync.src_mask |= 1u << q;
             if (D->send_cnt[q] > 0) {
                 SIGB_REQUIRE(all[q].recv_cnt[me] == D->send_cnt[q], SIGB_ERR_ARG,
                              "sigb_dist_csr_create: rank %d expects %d entries from rank %d, send list has %d", q,
                              all[q].recv_cnt[me], me, D->send_cnt[q]);
-                D->push.dst_mask |= 1u << q;
-                D->push.dst[q] = reinterpret_cast<double *>((HaloWin *)peers[q] + 1) + all[q].recv_off[me];
-                D->push.dst_stride[q] = all[q].stride;
+                D->sync.dst_mask |= 1u << q;
+                D->sync.dst[q] = reinterpret_cast<double *>((HaloWin *)peers[q] + 1) + all[q].recv_off[me];
+                D->sync.dst_stride[q] = all[q].stride;
             }
         }
     } else {

@@ -69,7 +69,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 struct HaloWin {
     unsigned long long hflag[2][kMaxRanks];  // [buffer][source]: sequence number of the halo it holds
     unsigned long long ack[kMaxRanks];       // [consumer]: last sequence that consumer finished reading
-    unsigned long long halo_seq;             // local: sequence of the current SpMV
+    unsigned long long halo_seq;             // local: SpMVs completed (written by the last CTA)
     unsigned int push_ticket, done_ticket;   // local: last-CTA detection
     unsigned long long pad_[4];
     // followed by the two landing buffers

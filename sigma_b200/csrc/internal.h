@@ -100,12 +100,21 @@ struct CsrView {
     int32_t n_interior = 0, n_boundary = 0;
 };
 
-constexpr int kTileNnz = 2048;   // entries staged per tile
+#ifndef SIGB_TILE_NNZ
+#define SIGB_TILE_NNZ 2048
+#endif
+#ifndef SIGB_TILE_ROWS
+#define SIGB_TILE_ROWS 512
+#endif
+#ifndef SIGB_ROWDIRECT
+#define SIGB_ROWDIRECT 0
+#endif
+constexpr int kTileNnz = SIGB_TILE_NNZ;   // entries staged per tile
 // A tile's entry range is widened down to a 4-entry boundary so the slices
 // can be moved with aligned 16-byte transfers; capping tiles at kTileNnz - 3
 // entries keeps the widened range within kTileNnz.
 constexpr int kTileCap = kTileNnz - 3;
-constexpr int kTileRows = 512;   // rows per tile (their ptr slice is staged too)
+constexpr int kTileRows = SIGB_TILE_ROWS;   // rows per tile (their ptr slice is staged too)
 constexpr int kPad = 8;          // slack entries behind ptr / node / val arrays
 
 enum GraphKind { G_CSR = 0, G_CSC = 1, G_ELL = 2 };
@@ -158,16 +167,28 @@ struct DotSpec {
     const struct HaloSync *sync = nullptr;  // peer-memory transport: flags to wait on / acknowledge
 };
 
-// Peer-memory halo synchronisation handed to a boundary launch (comm.cu).
+// Peer-memory halo exchange, fused into the SpMV kernel (comm.cu builds it).
+// Producer side: the first push_ctas CTAs store the owned entries other ranks
+// need straight into those ranks' landing buffers and publish a sequence
+// number.  Consumer side: a CTA waits for the peers' sequence numbers when it
+// reaches its first boundary tile; the last CTA acknowledges consumption.
 constexpr int kMaxRanks = 8;
-struct HaloWin;  // device-resident, IPC-shared (comm.cu)
+struct HaloWin;  // device-resident, IPC-shared (device_utils.cuh)
 struct HaloSync {
     HaloWin *win = nullptr;               // this rank's window
     HaloWin *peer[kMaxRanks] = {};        // the peers' windows (peer-mapped)
     uint32_t src_mask = 0;                // ranks we receive halo entries from
+    uint32_t dst_mask = 0;                // ranks we send entries to
     int me = 0;
     const double *halo_base = nullptr;    // two landing buffers, halo_stride apart
     int64_t halo_stride = 0;
+    // push plan
+    const int32_t *send_rows = nullptr;   // 1-based owned rows, grouped by destination
+    int32_t total_send = 0;
+    int32_t push_ctas = 0;
+    int32_t send_off[kMaxRanks + 1] = {};
+    double *dst[kMaxRanks] = {};          // peer landing buffer 0, offset to our slice
+    int64_t dst_stride[kMaxRanks] = {};
 };
 
 // which: 0 = all tiles, 1 = interior subset, 2 = boundary subset

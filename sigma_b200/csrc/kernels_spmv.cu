@@ -36,10 +36,16 @@
 // dot on the 4096^2 Poisson matrix; this TMA pipeline 229 us / 246 us.  The
 // register variant was removed.)
 //
-// Row-sharded operators (comm.cu) run the same kernel twice per SpMV: interior
-// tiles while the halo is in flight, then boundary tiles, whose gathers take
-// columns beyond the owned range from the halo landing buffer (HALO = true).
+// Row-sharded operators (comm.cu, HALO = true) use the same kernel as a fused
+// compute + exchange step over NVLink peer memory: in its prologue the first few
+// CTAs store the owned x entries other ranks need straight into those ranks'
+// landing buffers and publish a sequence number; tiles are ordered interior
+// first, so the transfer overlaps the bulk of the work, and a CTA only waits on
+// its peers' sequence numbers when it reaches its first boundary tile, whose
+// gathers take columns beyond the owned range from the landing buffer.
 #include <stdlib.h>
+
+#include <algorithm>
 
 #include "device_utils.cuh"
 
@@ -199,14 +205,44 @@ csr_tma_kernel(const CsrKernelArgs a)
 #pragma unroll
     for (int d = 0; d < (NDOT > 0 ? NDOT : 1); d++) acc[d] = 0.0;
 
-    // peer-memory transport: tiles [first_halo_tile, ntiles) read halo columns.
-    // A CTA walks its tiles in ascending order, so it reaches them last and
-    // only then waits until every source rank has published the halo of this
-    // SpMV (sequence number left by our own push kernel) -- by which time the
-    // transfer has long been overlapped by the interior tiles.
+    // ---- peer-memory halo exchange, producer side ------------------------
+    // tiles [first_halo_tile, ntiles) read halo columns.  This SpMV has
+    // sequence number hseq; halo_seq is only advanced by the last CTA to
+    // finish, so every CTA reads the same value here.
     const double *h1 = a.h1;
     bool halo_ready = !(HALO && a.sync.win != nullptr);
-    __shared__ unsigned long long s_seq;
+    unsigned long long hseq = 0;
+    if (HALO && a.sync.win != nullptr) {
+        hseq = *reinterpret_cast<volatile unsigned long long *>(&a.sync.win->halo_seq) + 1;
+        if ((int)blockIdx.x < a.sync.push_ctas) {
+            const int buf = (int)(hseq & 1);
+            // landing buffer `buf` was last filled for SpMV hseq-2: wait until
+            // every consumer has acknowledged reading it
+            if (tid == 0 && hseq > 2)
+                for (int q = 0; q < kMaxRanks; q++)
+                    if (a.sync.dst_mask & (1u << q))
+                        while (ld_acquire_sys(&a.sync.win->ack[q]) < hseq - 2) {}
+            __syncthreads();
+            for (int k = blockIdx.x * kThreads + tid; k < a.sync.total_send; k += a.sync.push_ctas * kThreads) {
+                int q = 0;
+                while (k >= a.sync.send_off[q + 1]) q++;
+                a.sync.dst[q][buf * a.sync.dst_stride[q] + (k - a.sync.send_off[q])] =
+                    a.x1[a.sync.send_rows[k]];
+            }
+            __syncthreads();   // the CTA's stores happen-before thread 0's fence (cumulative)
+            if (tid == 0) {
+                __threadfence_system();
+                const unsigned t0 = atomicAdd(&a.sync.win->push_ticket, 1u);
+                if (t0 == (unsigned)a.sync.push_ctas - 1) {
+                    a.sync.win->push_ticket = 0u;
+                    __threadfence_system();
+                    for (int q = 0; q < kMaxRanks; q++)
+                        if (a.sync.dst_mask & (1u << q))
+                            *reinterpret_cast<volatile unsigned long long *>(&a.sync.peer[q]->hflag[buf][a.sync.me]) = hseq;
+                }
+            }
+        }
+    }
 
     // thread 0 is the producer: it programs the TMA engine for one tile
     auto issue = [&](int stage, const int4 &d) {
@@ -238,14 +274,12 @@ csr_tma_kernel(const CsrKernelArgs a)
 
         if (HALO && !halo_ready && t >= a.first_halo_tile) {   // CTA-uniform
             if (tid == 0) {
-                const unsigned long long s = *reinterpret_cast<volatile unsigned long long *>(&a.sync.win->halo_seq);
                 for (int q = 0; q < kMaxRanks; q++)
                     if (a.sync.src_mask & (1u << q))
-                        while (ld_acquire_sys(&a.sync.win->hflag[s & 1][q]) < s) {}
-                s_seq = s;
+                        while (ld_acquire_sys(&a.sync.win->hflag[hseq & 1][q]) < hseq) {}
             }
             __syncthreads();
-            h1 = a.sync.halo_base + (s_seq & 1) * a.sync.halo_stride - (a.nloc + 1);
+            h1 = a.sync.halo_base + (hseq & 1) * a.sync.halo_stride - (a.nloc + 1);
             halo_ready = true;
         }
 
@@ -257,16 +291,46 @@ csr_tma_kernel(const CsrKernelArgs a)
             const int32_t *sptr = reinterpret_cast<const int32_t *>(base + kStageVal + kStageNode);
             const int rs = d_cur.x, re = d_cur.y, ks = d_cur.z, ke = d_cur.w;
             const int ka = ks & ~3, ra = rs & ~3;
-            // operands of the fused dot: requested before the wait, used in phase 2
-            double upre[kTileRows / kThreads];
-            if (NDOT >= 1) {
+            mbar_wait(&mbar[stage], (sidx >> 1) & 1u);
+#if SIGB_ROWDIRECT
+            // ---- one thread per row, straight from the staged slices: the
+            // row's entries are multiplied and added in stored order; lanes are
+            // consecutive rows, so for banded matrices slot j of a warp's rows
+            // gathers consecutive x entries (one or two lines per request)
 #pragma unroll
-                for (int i = 0; i < kTileRows / kThreads; i++) {
-                    const int r = rs + tid + i * kThreads;
-                    upre[i] = (r < re) ? a.u[r] : 0.0;
+            for (int i = 0; i < kTileRows / kThreads; i++) {
+                const int r = rs + tid + i * kThreads;
+                if (r < re) {
+                    const int b = sptr[r - ra] - 1 - ka, e = sptr[r + 1 - ra] - 1 - ka;
+                    double ur = 0.0;
+                    if (NDOT >= 1) ur = __ldg(a.u + r);
+                    double z = (MODE == MODE_ACC_INIT) ? a.y[r] : 0.0;
+                    for (int k0 = b; k0 < e; k0 += 8) {
+                        int c[8];
+                        double v[8], xv[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const bool ok = k0 + j < e;
+                            c[j] = ok ? snode[k0 + j] : 1;
+                            v[j] = ok ? sval[k0 + j] : 0.0;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            if (k0 + j < e) {
+                                if (HALO && c[j] > a.nloc) xv[j] = __ldcg(h1 + c[j]);
+                                else xv[j] = __ldg(a.x1 + c[j]);
+                            } else {
+                                xv[j] = 0.0;
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                            if (k0 + j < e) z = add(z, mul(v[j], xv[j]));
+                    }
+                    emit_row<MODE, NDOT>(a, r, z, ur, acc);
                 }
             }
-            mbar_wait(&mbar[stage], (sidx >> 1) & 1u);
+#else
             // ---- phase 1: products, in place --------------------------------
             // (entries before ks belong to the previous tile and hold valid
             // columns, so every gather below is in range)
@@ -292,6 +356,14 @@ csr_tma_kernel(const CsrKernelArgs a)
             }
             __syncthreads();
             // ---- phase 2: per-row sums in stored order ----------------------
+            // operands of the fused dot go through the same read-only path as
+            // the gathers, so rows with a (near-)diagonal entry hit L1
+            double ur[kTileRows / kThreads];
+#pragma unroll
+            for (int i = 0; i < kTileRows / kThreads; i++) {
+                const int r = rs + tid + i * kThreads;
+                ur[i] = (NDOT >= 1 && r < re) ? __ldg(a.u + r) : 0.0;
+            }
 #pragma unroll
             for (int i = 0; i < kTileRows / kThreads; i++) {
                 const int r = rs + tid + i * kThreads;
@@ -299,9 +371,10 @@ csr_tma_kernel(const CsrKernelArgs a)
                     const int b = sptr[r - ra] - 1 - ka, e = sptr[r + 1 - ra] - 1 - ka;
                     double z = (MODE == MODE_ACC_INIT) ? a.y[r] : 0.0;
                     for (int k = b; k < e; k++) z = add(z, sval[k]);
-                    emit_row<MODE, NDOT>(a, r, z, NDOT >= 1 ? upre[i] : 0.0, acc);
+                    emit_row<MODE, NDOT>(a, r, z, ur[i], acc);
                 }
             }
+#endif
             // the stage is overwritten by the async proxy next: order our
             // generic-proxy accesses before it
             fence_proxy_async();
@@ -324,10 +397,11 @@ csr_tma_kernel(const CsrKernelArgs a)
             const unsigned t2 = atomicAdd(&a.sync.win->done_ticket, 1u);
             if (t2 == gridDim.x - 1) {
                 a.sync.win->done_ticket = 0u;
-                const unsigned long long hseq =
-                    *reinterpret_cast<volatile unsigned long long *>(&a.sync.win->halo_seq);
+                *reinterpret_cast<volatile unsigned long long *>(&a.sync.win->halo_seq) = hseq;
+                if (a.sync.src_mask) __threadfence_system();
                 for (int q = 0; q < kMaxRanks; q++)
-                    if (a.sync.src_mask & (1u << q)) st_release_sys(&a.sync.peer[q]->ack[a.sync.me], hseq);
+                    if (a.sync.src_mask & (1u << q))
+                        *reinterpret_cast<volatile unsigned long long *>(&a.sync.peer[q]->ack[a.sync.me]) = hseq;
             }
         }
     }
@@ -431,7 +505,14 @@ int launch_csr_t(const CsrKernelArgs &a, cudaStream_t st)
     SIGB_CHECK((occupancy_grid<csr_tma_kernel<MODE, NDOT, HALO>>(smem, &grid)));
     if (a.ntiles < grid) grid = a.ntiles;
     if (grid < 1) grid = 1;
-    csr_tma_kernel<MODE, NDOT, HALO><<<grid, kThreads, smem, st>>>(a);
+    if (HALO && a.sync.win != nullptr) {
+        CsrKernelArgs b = a;
+        int pc = (a.sync.total_send + 2 * kThreads - 1) / (2 * kThreads);   // ~2 entries per thread
+        b.sync.push_ctas = a.sync.total_send > 0 ? std::max(1, std::min(pc, grid)) : 0;
+        csr_tma_kernel<MODE, NDOT, HALO><<<grid, kThreads, smem, st>>>(b);
+    } else {
+        csr_tma_kernel<MODE, NDOT, HALO><<<grid, kThreads, smem, st>>>(a);
+    }
     count_launch();
     SIGB_CUDA(cudaGetLastError());
     return SIGB_OK;
