@@ -1,0 +1,336 @@
+!==========================================================================!
+!==========================================================================!
+module sigma_b200_shim                                                     !
+!==========================================================================!
+!==========================================================================!
+!==== iso_c_binding interface to libsigma_b200.so (include/sigma_b200.h) ==!
+!==== and the marshalling helpers the SiGMA procedure bodies call.      ====!
+!====                                                                  ====!
+!==== Not compiled in this repository's image (it has no Fortran        ====!
+!==== compiler); every behavioural decision lives on the C side, where  ====!
+!==== it is tested.  tests/cxx/*.cpp make exactly the calls below from   ====!
+!==== C++ (sigma_b200/host/sigma.hpp) and are run on the GPU.            ====!
+!====                                                                  ====!
+!==== INTEGRATION.md shows, procedure by procedure, which reference     ====!
+!==== body is replaced by which call of this module.                    ====!
+!==========================================================================!
+!==========================================================================!
+
+use iso_c_binding
+
+implicit none
+
+integer(c_int), parameter :: SIGB_OK = 0, SIGB_ROW = 0, SIGB_COL = 1
+
+
+!--------------------------------------------------------------------------!
+interface                                                                  !
+!--------------------------------------------------------------------------!
+    ! runtime
+    function sigb_init(device) bind(c, name='sigb_init') result(stat)
+        import :: c_int
+        integer(c_int), value :: device
+        integer(c_int) :: stat
+    end function
+
+    function sigb_last_error() bind(c, name='sigb_last_error') result(msg)
+        import :: c_ptr
+        type(c_ptr) :: msg
+    end function
+
+    ! graphs
+    function sigb_cs_graph_create(n, m, ptr1, node1, order, g) &
+            & bind(c, name='sigb_cs_graph_create') result(stat)
+        import :: c_int, c_int32_t, c_ptr
+        integer(c_int32_t), value :: n, m
+        integer(c_int32_t), intent(in) :: ptr1(*), node1(*)
+        integer(c_int), value :: order
+        type(c_ptr), intent(out) :: g
+        integer(c_int) :: stat
+    end function
+
+    function sigb_ell_graph_create(n, m, max_d, node_cm, degrees, g) &
+            & bind(c, name='sigb_ell_graph_create') result(stat)
+        import :: c_int, c_int32_t, c_ptr
+        integer(c_int32_t), value :: n, m, max_d
+        integer(c_int32_t), intent(in) :: node_cm(*), degrees(*)
+        type(c_ptr), intent(out) :: g
+        integer(c_int) :: stat
+    end function
+
+    function sigb_graph_retain(g) bind(c, name='sigb_graph_retain') result(stat)
+        import :: c_int, c_ptr
+        type(c_ptr), value :: g
+        integer(c_int) :: stat
+    end function
+
+    function sigb_graph_release(g) bind(c, name='sigb_graph_release') result(stat)
+        import :: c_int, c_ptr
+        type(c_ptr), value :: g
+        integer(c_int) :: stat
+    end function
+
+    ! matrices
+    function sigb_matrix_create(g, A) bind(c, name='sigb_matrix_create') result(stat)
+        import :: c_int, c_ptr
+        type(c_ptr), value :: g
+        type(c_ptr), intent(out) :: A
+        integer(c_int) :: stat
+    end function
+
+    function sigb_matrix_set_values(A, val, count) &
+            & bind(c, name='sigb_matrix_set_values') result(stat)
+        import :: c_int, c_int64_t, c_double, c_ptr
+        type(c_ptr), value :: A
+        real(c_double), intent(in) :: val(*)
+        integer(c_int64_t), value :: count
+        integer(c_int) :: stat
+    end function
+
+    function sigb_matrix_destroy(A) bind(c, name='sigb_matrix_destroy') result(stat)
+        import :: c_int, c_ptr
+        type(c_ptr), value :: A
+        integer(c_int) :: stat
+    end function
+
+    ! matvec
+    function sigb_matvec(A, trans, x, y) bind(c, name='sigb_matvec') result(stat)
+        import :: c_int, c_double, c_ptr
+        type(c_ptr), value :: A
+        integer(c_int), value :: trans
+        real(c_double), intent(in) :: x(*)
+        real(c_double), intent(out) :: y(*)
+        integer(c_int) :: stat
+    end function
+
+    function sigb_matvec_add(A, trans, x, y) bind(c, name='sigb_matvec_add') result(stat)
+        import :: c_int, c_double, c_ptr
+        type(c_ptr), value :: A
+        integer(c_int), value :: trans
+        real(c_double), intent(in) :: x(*)
+        real(c_double), intent(inout) :: y(*)
+        integer(c_int) :: stat
+    end function
+
+    ! solvers
+    function sigb_cg_create(tolerance, s) bind(c, name='sigb_cg_create') result(stat)
+        import :: c_int, c_double, c_ptr
+        real(c_double), value :: tolerance
+        type(c_ptr), intent(out) :: s
+        integer(c_int) :: stat
+    end function
+
+    function sigb_bicgstab_create(tolerance, s) bind(c, name='sigb_bicgstab_create') result(stat)
+        import :: c_int, c_double, c_ptr
+        real(c_double), value :: tolerance
+        type(c_ptr), intent(out) :: s
+        integer(c_int) :: stat
+    end function
+
+    function sigb_jacobi_create(s) bind(c, name='sigb_jacobi_create') result(stat)
+        import :: c_int, c_ptr
+        type(c_ptr), intent(out) :: s
+        integer(c_int) :: stat
+    end function
+
+    function sigb_solver_setup(s, A) bind(c, name='sigb_solver_setup') result(stat)
+        import :: c_int, c_ptr
+        type(c_ptr), value :: s, A
+        integer(c_int) :: stat
+    end function
+
+    function sigb_solver_set_params(s, tolerance) &
+            & bind(c, name='sigb_solver_set_params') result(stat)
+        import :: c_int, c_double, c_ptr
+        type(c_ptr), value :: s
+        real(c_double), value :: tolerance
+        integer(c_int) :: stat
+    end function
+
+    function sigb_solver_solve(s, A, x, b, pc) bind(c, name='sigb_solver_solve') result(stat)
+        import :: c_int, c_double, c_ptr
+        type(c_ptr), value :: s, A, pc          ! pc = c_null_ptr: unpreconditioned
+        real(c_double), intent(inout) :: x(*)
+        real(c_double), intent(in) :: b(*)
+        integer(c_int) :: stat
+    end function
+
+    function sigb_solver_get_info(s, iterations, res2, capped) &
+            & bind(c, name='sigb_solver_get_info') result(stat)
+        import :: c_int, c_int64_t, c_double, c_ptr
+        type(c_ptr), value :: s
+        integer(c_int64_t), intent(out) :: iterations
+        real(c_double), intent(out) :: res2
+        integer(c_int), intent(out) :: capped
+        integer(c_int) :: stat
+    end function
+
+    function sigb_solver_destroy(s) bind(c, name='sigb_solver_destroy') result(stat)
+        import :: c_int, c_ptr
+        type(c_ptr), value :: s
+        integer(c_int) :: stat
+    end function
+
+    ! eigensolver
+    function sigb_lanczos(A, n, q1, seed, T, Q) bind(c, name='sigb_lanczos') result(stat)
+        import :: c_int, c_int32_t, c_int64_t, c_double, c_ptr
+        type(c_ptr), value :: A
+        integer(c_int32_t), value :: n
+        type(c_ptr), value :: q1                ! c_null_ptr: library draws the start vector
+        integer(c_int64_t), value :: seed
+        real(c_double), intent(out) :: T(3, *), Q(*)
+        integer(c_int) :: stat
+    end function
+
+    function sigb_eigensolve(A, n, q1, seed, lambda, V) &
+            & bind(c, name='sigb_eigensolve') result(stat)
+        import :: c_int, c_int32_t, c_int64_t, c_double, c_ptr
+        type(c_ptr), value :: A
+        integer(c_int32_t), value :: n
+        type(c_ptr), value :: q1
+        integer(c_int64_t), value :: seed
+        real(c_double), intent(out) :: lambda(*), V(*)
+        integer(c_int) :: stat
+    end function
+
+    function c_strlen(s) bind(c, name='strlen') result(n)
+        import :: c_ptr, c_size_t
+        type(c_ptr), value :: s
+        integer(c_size_t) :: n
+    end function
+end interface
+
+
+contains
+
+
+!--------------------------------------------------------------------------!
+subroutine sigb_check(stat)                                                !
+!--------------------------------------------------------------------------!
+! The reference's error convention: print a message and `call exit(1)`     !
+! (e.g. src/solver/cg_solvers.f90:61-65).                                   !
+!--------------------------------------------------------------------------!
+    integer(c_int), intent(in) :: stat
+    character(kind=c_char), pointer :: msg(:)
+    type(c_ptr) :: cmsg
+
+    if (stat /= SIGB_OK) then
+        cmsg = sigb_last_error()
+        call c_f_pointer(cmsg, msg, [c_strlen(cmsg)])
+        print *, msg
+        print *, 'Terminating.'
+        call exit(1)
+    endif
+
+end subroutine sigb_check
+
+
+end module sigma_b200_shim
+
+
+
+!==========================================================================!
+!==== How the reference's procedure BODIES change (signatures do not).  ====!
+!==== Shown as comments because they are edits to reference files; see  ====!
+!==== INTEGRATION.md for the full list.                                  ====!
+!==========================================================================!
+!
+! --- src/graph/formats/cs_graphs.f90, type cs_graph (:11-60) gains
+!         type(c_ptr), private :: mirror = c_null_ptr      ! device pattern
+!         logical, private :: mirror_is_col = .false.
+!     every mutator (add_edge :400, delete_edge, left/right_permute :499-571,
+!     build :109) ends with       call g%drop_mirror()
+!     (sigb_graph_release + mirror = c_null_ptr).
+!
+! --- src/matrix/formats/cs_matrices.f90, type cs_matrix (:32-107) gains
+!         type(c_ptr), private :: mirror = c_null_ptr      ! device values
+!         logical, private :: dirty = .true.
+!     every mutator (set_value/add_value :840-947, zero, scalar_multiply
+!     :448-490, permutes :972-1099) sets A%dirty = .true.
+!
+!     subroutine cs_matvec_add(A, x, y)                     ! :500-508
+!         class(cs_matrix), intent(in) :: A
+!         real(dp), intent(in)    :: x(:)
+!         real(dp), intent(inout) :: y(:)
+!         call A%sync_mirror()
+!         call sigb_check( sigb_matvec_add(A%mirror, 0_c_int, x, y) )
+!     end subroutine
+!
+!     subroutine cs_matvec_t_add(A, x, y)                   ! :513-521
+!         call A%sync_mirror()
+!         call sigb_check( sigb_matvec_add(A%mirror, 1_c_int, x, y) )
+!     end subroutine
+!
+!     subroutine sync_mirror(A)                             ! new, private
+!         class(cs_matrix), intent(inout) :: A
+!         integer(c_int) :: order
+!         if (.not. c_associated(A%g%mirror)) then
+!             order = SIGB_ROW
+!             if (A%get_col_is_fast) order = SIGB_COL       ! csc_matrix
+!             call sigb_check( sigb_cs_graph_create(A%g%n, A%g%m, A%g%ptr, &
+!                                         & A%g%node, order, A%g%mirror) )
+!         endif
+!         if (.not. c_associated(A%mirror)) then
+!             call sigb_check( sigb_matrix_create(A%g%mirror, A%mirror) )
+!             A%dirty = .true.
+!         endif
+!         if (A%dirty) then
+!             call sigb_check( sigb_matrix_set_values(A%mirror, A%val, &
+!                                         & size(A%val, kind=c_int64_t)) )
+!             A%dirty = .false.
+!         endif
+!     end subroutine
+!
+! --- src/linear_operator/linear_operator_interface.f90
+!     linear_operator_matvec (:185-194) keeps `y = 0; call A%matvec_add(x, y)`
+!     for operators without a mirror; cs_matrix / ellpack_matrix override
+!     matvec / matvec_t with sigb_matvec (zero-fill fused on the device).
+!
+! --- src/matrix/formats/ellpack_matrices.f90: same pattern with
+!     sigb_ell_graph_create(g%n, g%m, g%max_d, g%node, g%degrees, g%mirror)
+!     and sigb_matrix_set_values(A%mirror, A%val, size(A%val)) -- the Fortran
+!     arrays node(max_d, n) / val(max_d, n) are passed as they are.
+!
+! --- src/solver/cg_solvers.f90, type cg_solver (:10-28) gains
+!         type(c_ptr), private :: dev = c_null_ptr
+!
+!     subroutine cg_setup(solver, A)                        ! :52-90
+!         ... unchanged checks (non-square -> print + exit(1)) ...
+!         if (.not. c_associated(solver%dev)) &
+!             call sigb_check( sigb_cg_create(solver%tolerance, solver%dev) )
+!         select type(A)
+!             class is (cs_matrix)                          ! or ellpack_matrix
+!                 call A%sync_mirror()
+!                 call sigb_check( sigb_solver_setup(solver%dev, A%mirror) )
+!         end select
+!         solver%iterations = 0
+!     end subroutine
+!
+!     subroutine cg_solve(solver, A, x, b)                  ! :116-150
+!         integer(c_int64_t) :: it ; real(c_double) :: res2 ; integer(c_int) :: capped
+!         call A%sync_mirror()
+!         call sigb_check( sigb_solver_solve(solver%dev, A%mirror, x, b, c_null_ptr) )
+!         call sigb_check( sigb_solver_get_info(solver%dev, it, res2, capped) )
+!         solver%iterations = int(it)       ! accumulates across solves, like :145
+!     end subroutine
+!
+!     subroutine cg_solve_pc(solver, A, x, b, pc)           ! :155-194
+!         select type(pc)
+!             type is (jacobi_solver)
+!                 call sigb_check( sigb_solver_solve(solver%dev, A%mirror, x, b, pc%dev) )
+!             class default
+!                 ... the reference's host loop, unchanged (matvec through the mirror) ...
+!         end select
+!     end subroutine
+!
+!     bicgstab_solvers.f90 (:124-237) and jacobi_solvers.f90 (:37-81) follow
+!     the same pattern with sigb_bicgstab_create / sigb_jacobi_create.
+!
+! --- src/eigensolver.f90
+!     subroutine lanczos(A, T, Q)                           ! :27-90
+!         call init_seed() ; call random_number(Q(:,1)) ; Q(:,1) = 2 * Q(:,1) - 1
+!         call sigb_check( sigb_lanczos(A%mirror, size(T, 2), c_loc(Q(1,1)), &
+!                                     & 0_c_int64_t, T, Q) )
+!     end subroutine
+!     (the library normalises the start vector as :52 does; passing
+!      c_null_ptr instead lets it draw the vector from `seed`.)

@@ -14,16 +14,13 @@ tail -3 $OUT/smoke.log | tee -a $OUT/summary.txt
 echo "== bench" | tee -a $OUT/summary.txt
 timeout 600 python bench.py --steps 200 --warmup 5 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" | tee -a $OUT/summary.txt
 cat $OUT/bench.json | tee -a $OUT/summary.txt; tail -5 $OUT/bench.err | tee -a $OUT/summary.txt
-echo "== bench variant 1 (register-staged SpMV)" | tee -a $OUT/summary.txt
-SIGB_SPMV_VARIANT=1 timeout 600 python bench.py --steps 200 --warmup 5 --no-cpu > $OUT/bench_v1.json 2> $OUT/bench_v1.err; echo "bench v1 rc=$?" | tee -a $OUT/summary.txt
-cat $OUT/bench_v1.json | tee -a $OUT/summary.txt; tail -5 $OUT/bench_v1.err | tee -a $OUT/summary.txt
 echo "== ncu launch list" | tee -a $OUT/summary.txt
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 32 --warmup 3 --no-cpu > $OUT/bench_under_ncu.log 2>&1; echo "ncu list rc=$?" | tee -a $OUT/summary.txt
 echo "== ncu full (csr_stream)" | tee -a $OUT/summary.txt
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:csr_ -s 12 -c 2 -f -o $OUT/prof_csr \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:csr_tma -s 20 -c 3 -f -o $OUT/prof_csr \
     python bench.py --steps 48 --warmup 3 --no-cpu > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?" | tee -a $OUT/summary.txt
 echo "== ncu full (CgUpdate)" | tee -a $OUT/summary.txt
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:CgUpdateOp -s 8 -c 1 -f -o $OUT/prof_update \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"CgUpdateOp|CgDirectionOp" -s 34 -c 2 -f -o $OUT/prof_update \
     python bench.py --steps 48 --warmup 3 --no-cpu > $OUT/ncu_full2.log 2>&1; echo "ncu full2 rc=$?" | tee -a $OUT/summary.txt
 ls -la $OUT | tee -a $OUT/summary.txt

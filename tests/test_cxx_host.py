@@ -1,0 +1,30 @@
+"""The C++ host mirror (sigma_b200/host/sigma.hpp) compiles on CPU; on a GPU its
+restatements of the reference's test programs pass with exit code 0, exactly
+how the reference's CTest registers them (test/CMakeLists.txt:27-32)."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CXX = os.path.join(ROOT, "tests", "cxx")
+PROGS = ["solver_test_diffusion_1d", "solver_test_advection_diffusion_1d", "solver_test_jacobi",
+         "eigensolver_test_lanczos", "matrix_test_basics"]
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", CXX])
+
+
+def test_cxx_programs_compile_and_link():
+    build()
+    for p in PROGS:
+        assert os.path.exists(os.path.join(CXX, "_build", p))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prog", PROGS)
+def test_reference_test_program(prog):
+    build()
+    r = subprocess.run([os.path.join(CXX, "_build", prog), "-v"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
