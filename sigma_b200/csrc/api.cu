@@ -676,6 +676,8 @@ int sigb_solver_destroy(sigb_solver_t s)
     cudaFree(s->state);
     cudaFreeHost(s->state_host);
     cudaFree(s->xb);
+    cudaFree(s->bar);
+    cudaFree(s->pers_partials);
     delete s;
     return SIGB_OK;
 }

@@ -38,20 +38,6 @@
 
 namespace sigb {
 
-// One fp64 value in flight, "LL" style: each 8-byte word carries 32 payload
-// bits and a 32-bit sequence flag.  An aligned 8-byte store is delivered as a
-// unit, so a word is either old or complete: no fence between payload and
-// flag, one NVLink store latency per all-reduce.
-struct RedEntry {
-    unsigned int lo, flag_lo, hi, flag_hi;
-};
-constexpr int kRedSlots = 4;
-constexpr int kRedVals = 3;
-struct RedWin {
-    RedEntry red[kRedSlots][kMaxRanks][kRedVals];  // [slot][source rank][value], written by the peers
-    unsigned long long red_seq;                    // local: reductions completed
-};
-
 }  // namespace sigb
 
 struct sigb_comm_s {
@@ -142,17 +128,6 @@ struct RedArgs {
     const int *skip_flag;
 };
 
-__device__ __forceinline__ void st_word(unsigned int *p, unsigned int payload, unsigned int flag)
-{
-    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(flag) : "memory");
-}
-__device__ __forceinline__ uint2 ld_word(const unsigned int *p)
-{
-    uint2 r;
-    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
-    return r;
-}
-
 // One warp.  Lane q < nranks stores this rank's partial sums into rank q's
 // inbox and then polls the entry rank q stored into ours; lanes c < count add
 // the nranks contributions in rank order, so every rank computes bit-identical
@@ -180,8 +155,9 @@ __global__ void red_kernel(const RedArgs a)
         for (int q = 0; q < a.nranks; q++) {   // rank order
             const RedEntry *e = &a.win->red[slot][q][lane];
             uint2 lo, hi;
-            do { lo = ld_word(&e->lo); } while (lo.y != flag);
-            do { hi = ld_word(&e->hi); } while (hi.y != flag);
+            unsigned spins = 0;
+            do { lo = ld_word(&e->lo); } while (lo.y != flag && ++spins < kSpinLimit);
+            do { hi = ld_word(&e->hi); } while (hi.y != flag && ++spins < kSpinLimit);
             v = add(v, __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | lo.x)));
         }
         *a.vals[lane] = v;
@@ -205,6 +181,25 @@ pack_kernel(const double *__restrict__ x, const int32_t *__restrict__ rows1, int
 int64_t dist_global_n(sigb_matrix_t A) { return A->dist ? A->dist->n_global : A->nrow; }
 int64_t dist_row_offset(sigb_matrix_t A) { return A->dist ? A->dist->lo : 0; }
 int64_t dist_halo_len(sigb_matrix_t) { return 0; }  // halos land in the operator's own buffers
+
+int dist_persist_info(sigb_matrix_t A, PersistComm *pc, DotSpec *halo, bool *eligible)
+{
+    *pc = PersistComm();
+    *halo = DotSpec();
+    *eligible = true;
+    DistInfo *D = A->dist;
+    if (!D) return SIGB_OK;
+    sigb_comm_t C = D->comm;
+    halo->nloc = D->nloc;
+    if (C->nranks == 1) return SIGB_OK;
+    if (!C->p2p) { *eligible = false; return SIGB_OK; }   // NCCL transport: host-driven kernels only
+    pc->red = C->red;
+    for (int q = 0; q < kMaxRanks; q++) pc->peer_red[q] = C->peer_red[q];
+    pc->me = C->rank;
+    pc->nranks = C->nranks;
+    if (D->total_send > 0 || D->nhalo > 0) halo->sync = &D->sync;
+    return SIGB_OK;
+}
 
 int dist_destroy(sigb_matrix_t A)
 {

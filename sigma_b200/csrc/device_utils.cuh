@@ -65,6 +65,36 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
+// One fp64 value in flight, "LL" style: each 8-byte word carries 32 payload
+// bits and a 32-bit sequence flag.  An aligned 8-byte store is delivered as a
+// unit, so a word is either old or complete: no fence between payload and
+// flag, one NVLink store latency per all-reduce.
+struct RedEntry {
+    unsigned int lo, flag_lo, hi, flag_hi;
+};
+constexpr int kRedSlots = 4;
+constexpr int kRedVals = 3;
+struct RedWin {
+    RedEntry red[kRedSlots][kMaxRanks][kRedVals];  // [slot][source rank][value], written by the peers
+    unsigned long long red_seq;                    // local: reductions completed
+};
+
+__device__ __forceinline__ void st_word(unsigned int *p, unsigned int payload, unsigned int flag)
+{
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(flag) : "memory");
+}
+__device__ __forceinline__ uint2 ld_word(const unsigned int *p)
+{
+    uint2 r;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+    return r;
+}
+
+// Bounded spinning: a peer that never answers must not hang the GPU (a hung
+// box is worse than a wrong answer that the host then reports).  ~1e8 polls of
+// an L2-resident word is several seconds.
+constexpr unsigned kSpinLimit = 1u << 27;
+
 // Window of a row-sharded operator: everything peers write into this rank.
 struct HaloWin {
     unsigned long long hflag[2][kMaxRanks];  // [buffer][source]: sequence number of the halo it holds

@@ -106,9 +106,6 @@ struct CsrView {
 #ifndef SIGB_TILE_ROWS
 #define SIGB_TILE_ROWS 512
 #endif
-#ifndef SIGB_ROWDIRECT
-#define SIGB_ROWDIRECT 0
-#endif
 constexpr int kTileNnz = SIGB_TILE_NNZ;   // entries staged per tile
 // A tile's entry range is widened down to a 4-entry boundary so the slices
 // can be moved with aligned 16-byte transfers; capping tiles at kTileNnz - 3

@@ -7,6 +7,7 @@
 //   lanczos / eigensolve                 src/eigensolver.f90:27-90,160-184
 // keeping their stopping rules, work-vector sets and iteration counters.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "krylov.cuh"
@@ -558,6 +559,16 @@ static int finish_solve(sigb_solver_t s)
     return SIGB_OK;
 }
 
+static bool persistent_enabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SIGB_CG_PERSISTENT");
+        v = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return v != 0;
+}
+
 // iterations launched between two looks at the device state
 static int batch_size(int64_t n)
 {
@@ -582,6 +593,41 @@ int cg_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x, const double *b, s
     SIGB_CHECK(dist_allreduce(A, &st->rr[0], 1));
     latch0_kernel<<<1, 1, 0, ctx().stream>>>(st);
     count_launch();
+
+    // ---- the whole loop as one persistent cooperative kernel ---------------
+    // (CSR-shaped operators; SIGB_CG_PERSISTENT=0 selects the kernel-per-phase
+    // path below, which is also what ELLPACK and the NCCL transport use)
+    {
+        const CsrView *V = nullptr;
+        const double *val = nullptr;
+        PersistComm pcomm;
+        DotSpec halo;
+        bool eligible = persistent_enabled();
+        if (eligible) SIGB_CHECK(dist_persist_info(A, &pcomm, &halo, &eligible));
+        if (eligible) {
+            sigb_graph_t g = A->g;
+            if (g->kind == G_CSR) {
+                V = &g->stored;
+                val = A->val;
+            } else if (g->kind == G_CSC) {
+                SIGB_CHECK(ensure_transposed(A));
+                V = &g->transposed;
+                val = A->val_t;
+            }
+        }
+        if (V != nullptr) {
+            if (!s->bar) {
+                SIGB_CUDA(cudaMalloc((void **)&s->bar, sizeof(unsigned long long)));
+                SIGB_CUDA(cudaMalloc((void **)&s->pers_partials, sizeof(double) * 2 * kMaxGrid));
+            }
+            for (;;) {
+                SIGB_CHECK(cg_persistent_run(s, *V, val, halo, x, p, q, r, z, idiag, n, 0, pcomm, 4096));
+                SIGB_CHECK(sync_state(s));
+                if (s->state_host->done[0]) break;
+            }
+            return finish_solve(s);
+        }
+    }
 
     const int nb = batch_size(n);
     int par = 0;

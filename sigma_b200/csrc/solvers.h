@@ -27,6 +27,9 @@ struct sigb_solver_s {
     double *xb = nullptr;      // device staging for host-pointer solves (x | b)
     int64_t xb_len = 0;
     sigb_matrix_t A = nullptr; // operator given to setup
+    // persistent CG kernel (cg_persistent.cu)
+    unsigned long long *bar = nullptr;   // grid barrier counter
+    double *pers_partials = nullptr;     // 2 x kMaxGrid CTA partial sums
 };
 
 namespace sigb {
@@ -42,6 +45,21 @@ int tridiag_eig_host(int n, double *d, double *e, double *Z);
 int ritz_vectors_dev(double *V, double *V2, const double *Qm_dev, int64_t nr, int32_t n,
                      double *first_row_dev);
 size_t kstate_bytes();
+
+// ---- persistent cooperative CG kernel (cg_persistent.cu) -------------------
+struct PersistComm {          // all-reduce endpoints of a row-sharded operator
+    void *red = nullptr;      // RedWin* of this rank
+    void *peer_red[kMaxRanks] = {};
+    int me = 0, nranks = 1;
+};
+struct CsrKernelArgs;
+int cg_persistent_run(sigb_solver_t s, const CsrView &V, const double *val, const DotSpec &halo, double *x,
+                      double *p, double *q, double *r, double *z, const double *idiag, int64_t n, int grid_hint,
+                      const PersistComm &pcomm, long long max_iters);
+// Row-sharded operators: fills the all-reduce endpoints and the halo spec the
+// persistent kernel needs; *eligible = false when the operator uses a transport
+// the kernel cannot drive (NCCL).
+int dist_persist_info(sigb_matrix_t A, PersistComm *pc, DotSpec *halo, bool *eligible);
 
 // y = A x (MODE_SET) with fused dots.  For row-sharded operators this also
 // performs the halo exchange; x_has_halo says x has room for (and may receive)

@@ -1,0 +1,334 @@
+// spmv_device.cuh -- device side of the streaming CSR SpMV: argument block,
+// TMA / mbarrier primitives and the per-CTA tile pass, shared by the stand-alone
+// kernel (kernels_spmv.cu) and the persistent CG kernel (cg_persistent.cu).
+#pragma once
+
+#include <algorithm>
+
+#include "device_utils.cuh"
+
+namespace sigb {
+
+struct CsrKernelArgs {
+    const int32_t *ptr;       // 1-based, nrows + 1 (+ pad)
+    const int32_t *node;      // 1-based (+ pad)
+    const double *val;        // (+ pad)
+    const TileDesc *tiles;
+    int32_t ntiles;
+    const double *x1;         // x - 1 : indexable by 1-based column id
+    double *y;
+    const double *u;          // dot vector
+    double *out0, *out1;
+    double *partials;
+    unsigned *ticket;
+    const int *skip_flag;
+    const double *scale;      // optional per-row scaling of the result
+    const double *h1;         // halo - (nloc + 1): indexable by column ids > nloc
+    int32_t nloc;             // owned columns (HALO kernels)
+    const double *add0, *add1;  // optional addends folded into the dot totals
+    HaloSync sync;            // peer-memory transport (sync.win == nullptr: none)
+    int32_t first_halo_tile;  // tiles from this index on read halo columns
+};
+
+__device__ __forceinline__ int4 load_desc(const TileDesc *t)
+{
+    return __ldg(reinterpret_cast<const int4 *>(t));
+}
+
+// ---- mbarrier / bulk-copy (TMA) primitives ---------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+// The matrix arrays are read exactly once per SpMV: evict-first keeps them from
+// displacing the vectors, which are re-read by the following kernels and fit
+// in the 126 MB L2 once the operator is sharded.
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar,
+                                         uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// shared-memory stage: val | node | ptr slices of one tile
+constexpr int kStageVal = kTileNnz * 8;
+constexpr int kStageNode = kTileNnz * 4;
+constexpr int kStagePtr = (kTileRows + 8) * 4;
+constexpr int kStageBytes = (kStageVal + kStageNode + kStagePtr + 127) & ~127;
+
+__device__ __forceinline__ bool tile_staged(const int4 &d)
+{
+    return (d.w - d.z) <= kTileCap;  // else: one long row, streamed directly
+}
+
+template <int MODE, int NDOT>
+__device__ __forceinline__ void emit_row(const CsrKernelArgs &a, int r, double z, double ur, double *acc)
+{
+    if (MODE == MODE_ADD_AFTER) z = add(a.y[r], z);
+    if (MODE == MODE_SET && a.scale) z = mul(a.scale[r], z);
+    a.y[r] = z;
+    if (NDOT >= 1) acc[0] = add(acc[0], mul(ur, z));
+    if (NDOT >= 2) acc[NDOT > 1 ? 1 : 0] = add(acc[NDOT > 1 ? 1 : 0], mul(z, z));
+}
+
+// one row longer than a tile: CTA-wide fixed-tree reduction, direct loads
+// XNC: x (and the dot operand u) may be read through the non-coherent read-only
+// path.  True for stand-alone launches, where the vectors are constant for the
+// kernel's lifetime; false inside the persistent CG kernel, which rewrites them
+// between grid barriers and must use coherent loads.
+template <bool XNC>
+__device__ __forceinline__ double ld_x(const double *p)
+{
+    return XNC ? __ldg(p) : *p;
+}
+
+template <int MODE, int NDOT, bool HALO, bool XNC>
+__device__ __forceinline__ void long_row(const CsrKernelArgs &a, const int4 &d, const double *h1, double *acc)
+{
+    __shared__ double smr[1][kThreads / 32];
+    double s[1] = {0.0};
+    for (int k = d.z + threadIdx.x; k < d.w; k += kThreads) {
+        const int c = a.node[k];
+        const double xv = (HALO && c > a.nloc) ? __ldcg(h1 + c) : ld_x<XNC>(a.x1 + c);
+        s[0] = add(s[0], mul(a.val[k], xv));
+    }
+    block_tree<1>(s, smr);
+    if (threadIdx.x == 0) {
+        double z = s[0];
+        if (MODE == MODE_ACC_INIT) z = add(a.y[d.x], z);
+        emit_row<MODE, NDOT>(a, d.x, z, NDOT >= 1 ? ld_x<XNC>(a.u + d.x) : 0.0, acc);
+    }
+    __syncthreads();
+}
+
+template <int NDOT>
+__device__ __forceinline__ void finish_dots(const CsrKernelArgs &a, double *acc)
+{
+    if (NDOT == 1) {
+        double *const out[1] = {a.out0};
+        const double *const addend[1] = {a.add0};
+        double v[1] = {acc[0]};
+        grid_reduce<1>(v, a.partials, a.ticket, out, addend);
+    } else if (NDOT == 2) {
+        double *const out[2] = {a.out0, a.out1};
+        const double *const addend[2] = {a.add0, a.add1};
+        double v[2] = {acc[0], acc[NDOT > 1 ? 1 : 0]};
+        grid_reduce<2>(v, a.partials, a.ticket, out, addend);
+    }
+}
+
+// Per-CTA state of the double-buffered TMA pipeline, carried across calls.
+struct TilePipe {
+    unsigned sidx = 0;     // staged tiles consumed so far: stage = sidx & 1, mbarrier parity = (sidx >> 1) & 1
+    bool primed = false;   // the first tile of the next pass has already been issued
+};
+
+// One SpMV pass of this CTA over its tiles (round-robin), including -- for
+// row-sharded operators on the peer-memory transport -- the halo push in the
+// prologue and the lazy wait before the first boundary tile.  hseq is the
+// sequence number of this SpMV (HALO only).  Dot partials accumulate in acc.
+template <int MODE, int NDOT, bool HALO, bool XNC>
+__device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char *smem, uint64_t *mbar,
+                                           TilePipe &pipe, double *acc, unsigned long long hseq,
+                                           bool prime_next)
+{
+    // ---- peer-memory halo exchange, producer side ------------------------
+    // tiles [first_halo_tile, ntiles) read halo columns.  This SpMV has
+    // sequence number hseq; halo_seq is only advanced by the last CTA to
+    // finish, so every CTA reads the same value here.
+    const int tid = threadIdx.x;
+    const double *h1 = a.h1;
+    bool halo_ready = !(HALO && a.sync.win != nullptr);
+    if (HALO && a.sync.win != nullptr) {
+        if ((int)blockIdx.x < a.sync.push_ctas) {
+            const int buf = (int)(hseq & 1);
+            // landing buffer `buf` was last filled for SpMV hseq-2: wait until
+            // every consumer has acknowledged reading it
+            if (tid == 0 && hseq > 2)
+                for (int q = 0; q < kMaxRanks; q++)
+                    if (a.sync.dst_mask & (1u << q)) {
+                        unsigned spins = 0;
+                        while (ld_acquire_sys(&a.sync.win->ack[q]) < hseq - 2 && ++spins < kSpinLimit) {}
+                    }
+            __syncthreads();
+            for (int k = blockIdx.x * kThreads + tid; k < a.sync.total_send; k += a.sync.push_ctas * kThreads) {
+                int q = 0;
+                while (k >= a.sync.send_off[q + 1]) q++;
+                a.sync.dst[q][buf * a.sync.dst_stride[q] + (k - a.sync.send_off[q])] =
+                    ld_x<XNC>(a.x1 + a.sync.send_rows[k]);
+            }
+            __syncthreads();   // the CTA's stores happen-before thread 0's fence (cumulative)
+            if (tid == 0) {
+                __threadfence_system();
+                const unsigned t0 = atomicAdd(&a.sync.win->push_ticket, 1u);
+                if (t0 == (unsigned)a.sync.push_ctas - 1) {
+                    a.sync.win->push_ticket = 0u;
+                    __threadfence_system();
+                    for (int q = 0; q < kMaxRanks; q++)
+                        if (a.sync.dst_mask & (1u << q))
+                            *reinterpret_cast<volatile unsigned long long *>(&a.sync.peer[q]->hflag[buf][a.sync.me]) = hseq;
+                }
+            }
+        }
+    }
+
+    // thread 0 is the producer: it programs the TMA engine for one tile
+    const uint64_t stream_policy = policy_evict_first();
+    auto issue = [&](int stage, const int4 &d) {
+        unsigned char *base = smem + stage * kStageBytes;
+        const int ka = d.z & ~3, ra = d.x & ~3;
+        const uint32_t cnt = (uint32_t)((d.w - ka + 3) & ~3);
+        const uint32_t rcnt = (uint32_t)((d.y + 1 - ra + 3) & ~3);
+        mbar_expect_tx(&mbar[stage], cnt * 12u + rcnt * 4u);
+        bulk_g2s(base, a.val + ka, cnt * 8u, &mbar[stage], stream_policy);
+        bulk_g2s(base + kStageVal, a.node + ka, cnt * 4u, &mbar[stage], stream_policy);
+        bulk_g2s(base + kStageVal + kStageNode, a.ptr + ra, rcnt * 4u, &mbar[stage], stream_policy);
+    };
+
+    int t = blockIdx.x;
+    int4 d_cur = make_int4(0, 0, 0, 0), d_next = make_int4(0, 0, 0, 0);
+    if (t < a.ntiles) d_cur = load_desc(a.tiles + t);
+    if (t + (int)gridDim.x < a.ntiles) d_next = load_desc(a.tiles + t + gridDim.x);
+    unsigned sidx = pipe.sidx;  // staged tiles consumed so far (identical in all threads)
+    if (!pipe.primed && tid == 0 && t < a.ntiles && tile_staged(d_cur)) issue((int)(sidx & 1u), d_cur);
+    pipe.primed = false;
+
+    for (; t < a.ntiles; t += gridDim.x) {
+        const int tn = t + gridDim.x, tnn = tn + gridDim.x;
+        const bool have_next = tn < a.ntiles;
+        int4 d_next2 = make_int4(0, 0, 0, 0);
+        if (tnn < a.ntiles) d_next2 = load_desc(a.tiles + tnn);  // two tiles ahead, off the critical path
+        const bool staged = tile_staged(d_cur);
+        const unsigned sidx_after = sidx + (staged ? 1u : 0u);
+        if (tid == 0 && have_next && tile_staged(d_next)) issue((int)(sidx_after & 1u), d_next);
+
+        if (HALO && !halo_ready && t >= a.first_halo_tile) {   // CTA-uniform
+            if (tid == 0) {
+                for (int q = 0; q < kMaxRanks; q++)
+                    if (a.sync.src_mask & (1u << q)) {
+                        unsigned spins = 0;
+                        while (ld_acquire_sys(&a.sync.win->hflag[hseq & 1][q]) < hseq && ++spins < kSpinLimit) {}
+                    }
+            }
+            __syncthreads();
+            h1 = a.sync.halo_base + (hseq & 1) * a.sync.halo_stride - (a.nloc + 1);
+            halo_ready = true;
+        }
+
+        if (staged) {
+            const int stage = (int)(sidx & 1u);
+            unsigned char *base = smem + stage * kStageBytes;
+            double *sval = reinterpret_cast<double *>(base);
+            const int32_t *snode = reinterpret_cast<const int32_t *>(base + kStageVal);
+            const int32_t *sptr = reinterpret_cast<const int32_t *>(base + kStageVal + kStageNode);
+            const int rs = d_cur.x, re = d_cur.y, ks = d_cur.z, ke = d_cur.w;
+            const int ka = ks & ~3, ra = rs & ~3;
+            mbar_wait(&mbar[stage], (sidx >> 1) & 1u);
+            // ---- phase 1: products, in place --------------------------------
+            // (entries before ks belong to the previous tile and hold valid
+            // columns, so every gather below is in range)
+            const int cnt = ke - ka;
+            int c[kTileNnz / kThreads];
+            double v[kTileNnz / kThreads];
+#pragma unroll
+            for (int i = 0; i < kTileNnz / kThreads; i++) {
+                const int k = tid + i * kThreads;
+                c[i] = (k < cnt) ? snode[k] : 1;
+                v[i] = (k < cnt) ? sval[k] : 0.0;
+            }
+            double xv[kTileNnz / kThreads];
+#pragma unroll
+            for (int i = 0; i < kTileNnz / kThreads; i++) {
+                if (HALO && c[i] > a.nloc) xv[i] = __ldcg(h1 + c[i]);   // written by peers: not via the nc path
+                else xv[i] = ld_x<XNC>(a.x1 + c[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < kTileNnz / kThreads; i++) {
+                const int k = tid + i * kThreads;
+                if (k < cnt) sval[k] = mul(v[i], xv[i]);
+            }
+            __syncthreads();
+            // ---- phase 2: per-row sums in stored order ----------------------
+            // operands of the fused dot go through the same read-only path as
+            // the gathers, so rows with a (near-)diagonal entry hit L1
+            double ur[kTileRows / kThreads];
+#pragma unroll
+            for (int i = 0; i < kTileRows / kThreads; i++) {
+                const int r = rs + tid + i * kThreads;
+                ur[i] = (NDOT >= 1 && r < re) ? ld_x<XNC>(a.u + r) : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < kTileRows / kThreads; i++) {
+                const int r = rs + tid + i * kThreads;
+                if (r < re) {
+                    const int b = sptr[r - ra] - 1 - ka, e = sptr[r + 1 - ra] - 1 - ka;
+                    double z = (MODE == MODE_ACC_INIT) ? a.y[r] : 0.0;
+                    for (int k = b; k < e; k++) z = add(z, sval[k]);
+                    emit_row<MODE, NDOT>(a, r, z, ur[i], acc);
+                }
+            }
+            // the stage is overwritten by the async proxy next: order our
+            // generic-proxy accesses before it
+            fence_proxy_async();
+            __syncthreads();
+        } else {
+            long_row<MODE, NDOT, HALO, XNC>(a, d_cur, h1, acc);
+        }
+        sidx = sidx_after;
+        d_cur = d_next;
+        d_next = d_next2;
+    }
+    pipe.sidx = sidx;
+    // persistent callers: the matrix does not change between SpMVs, so the first
+    // tile of the NEXT pass can already be in flight while other phases run
+    if (prime_next) {
+        if (blockIdx.x < (unsigned)a.ntiles) {
+            const int4 d0 = load_desc(a.tiles + blockIdx.x);
+            if (tid == 0 && tile_staged(d0)) issue((int)(sidx & 1u), d0);
+        }
+        pipe.primed = true;
+    }
+}
+
+}  // namespace sigb
