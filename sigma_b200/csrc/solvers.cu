@@ -559,14 +559,21 @@ static int finish_solve(sigb_solver_t s)
     return SIGB_OK;
 }
 
-static bool persistent_enabled()
+// The persistent kernel removes kernel boundaries and runs the all-reduces
+// in-kernel, which wins when an iteration is short (sharded operators); its
+// vector phases run at 4 CTAs/SM with a 64-register cap and stream a little
+// slower than the dedicated kernels, which wins when an iteration is long.
+// Measured cross-over on B200 (profiles/r1_size_sweep_persistent.jsonl): ~3 M
+// rows per GPU.  SIGB_CG_PERSISTENT=1 / 0 forces one or the other.
+static bool persistent_enabled(int64_t n_local)
 {
-    static int v = -1;
-    if (v < 0) {
+    static int v = -2;
+    if (v == -2) {
         const char *e = getenv("SIGB_CG_PERSISTENT");
-        v = (e && atoi(e) == 0) ? 0 : 1;
+        v = e ? (atoi(e) != 0 ? 1 : 0) : -1;
     }
-    return v != 0;
+    if (v >= 0) return v != 0;
+    return n_local <= 3000000;
 }
 
 // iterations launched between two looks at the device state
@@ -602,7 +609,7 @@ int cg_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x, const double *b, s
         const double *val = nullptr;
         PersistComm pcomm;
         DotSpec halo;
-        bool eligible = persistent_enabled();
+        bool eligible = persistent_enabled(n);
         if (eligible) SIGB_CHECK(dist_persist_info(A, &pcomm, &halo, &eligible));
         if (eligible) {
             sigb_graph_t g = A->g;
