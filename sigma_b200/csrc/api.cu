@@ -580,7 +580,8 @@ int sigb_solver_setup(sigb_solver_t s, sigb_matrix_t A)
         return SIGB_ERR_NONSQUARE;
     }
     const int nwork = s->kind == S_CG ? 4 : (s->kind == S_BICGSTAB ? 8 : 1);
-    const int64_t nvec = (int64_t)A->nrow + dist_halo_len(A);
+    // work vectors start on 256-byte boundaries (128-bit accesses in the vector phases)
+    const int64_t nvec = (((int64_t)A->nrow + dist_halo_len(A)) + 31) & ~31LL;
     if (s->initialized && (s->nvec != nvec || s->nwork != nwork)) {
         cudaFree(s->work);
         s->work = nullptr;
