@@ -54,6 +54,10 @@ struct Sync {
     int *abort_flag;
 };
 
+__device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p)
 {
     unsigned long long v;
@@ -62,7 +66,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long
 }
 
 // Grid-wide barrier with release/acquire semantics (the scheme cooperative
-// groups uses): bar.sync ; thread 0: fence, arrive, spin, fence ; bar.sync.
+// groups uses: bar.sync ; thread 0: fence, arrive, wait, fence ; bar.sync), with
+// arrival and release on different words: CTAs arrive with an atomic on bar[0];
+// the last one to arrive publishes the epoch in bar[1], which is what everybody
+// else polls -- the pollers do not compete with the arrival atomics.
 // The trailing fence also drops stale L1 lines, so ordinary loads issued after
 // the barrier observe what other SMs wrote before it.
 __device__ __forceinline__ void grid_barrier(Sync &s)
@@ -71,10 +78,13 @@ __device__ __forceinline__ void grid_barrier(Sync &s)
     s.epoch++;
     if (threadIdx.x == 0) {
         __threadfence();
-        atomicAdd(s.bar, 1ull);
-        const unsigned long long target = s.epoch * gridDim.x;
-        unsigned spins = 0;
-        while (ld_acquire_gpu(s.bar) < target && ++spins < kSpinLimit) {}
+        const unsigned long long arrived = atomicAdd(s.bar, 1ull) + 1;
+        if (arrived == s.epoch * gridDim.x) {
+            st_release_gpu(s.bar + 1, s.epoch);
+        } else {
+            unsigned spins = 0;
+            while (ld_acquire_gpu(s.bar + 1) < s.epoch && ++spins < kSpinLimit) {}
+        }
         __threadfence();
     }
     __syncthreads();
@@ -299,7 +309,7 @@ int cg_persistent_run(sigb_solver_t s, const CsrView &V, const double *val, cons
     a.me = pcomm.me;
     a.nranks = pcomm.nranks;
     cudaStream_t st = ctx().stream;
-    SIGB_CUDA(cudaMemsetAsync(s->bar, 0, sizeof(unsigned long long), st));
+    SIGB_CUDA(cudaMemsetAsync(s->bar, 0, 2 * sizeof(unsigned long long), st));
     const bool halo_on = halo.sync != nullptr;
     if (halo_on) return idiag ? launch_persistent<true, true>(a, st) : launch_persistent<true, false>(a, st);
     return idiag ? launch_persistent<false, true>(a, st) : launch_persistent<false, false>(a, st);

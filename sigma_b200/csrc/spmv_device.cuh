@@ -180,6 +180,7 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
     const int tid = threadIdx.x;
     const double *h1 = a.h1;
     bool halo_ready = !(HALO && a.sync.win != nullptr);
+    bool push_pending = false;
     if (HALO && a.sync.win != nullptr) {
         if ((int)blockIdx.x < a.sync.push_ctas) {
             const int buf = (int)(hseq & 1);
@@ -198,20 +199,31 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
                 a.sync.dst[q][buf * a.sync.dst_stride[q] + (k - a.sync.send_off[q])] =
                     ld_x<XNC>(a.x1 + a.sync.send_rows[k]);
             }
-            __syncthreads();   // the CTA's stores happen-before thread 0's fence (cumulative)
-            if (tid == 0) {
-                __threadfence_system();
-                const unsigned t0 = atomicAdd(&a.sync.win->push_ticket, 1u);
-                if (t0 == (unsigned)a.sync.push_ctas - 1) {
-                    a.sync.win->push_ticket = 0u;
-                    __threadfence_system();
-                    for (int q = 0; q < kMaxRanks; q++)
-                        if (a.sync.dst_mask & (1u << q))
-                            *reinterpret_cast<volatile unsigned long long *>(&a.sync.peer[q]->hflag[buf][a.sync.me]) = hseq;
-                }
-            }
+            push_pending = true;   // published after the first tile, see below
         }
     }
+    // The stores above need a system-scope fence before the sequence number may
+    // be published.  Issued right away that fence costs the pushing CTAs a few
+    // microseconds of NVLink round trip before they touch their first tile (and
+    // the whole grid waits for them at the end); issued after the first tile the
+    // stores have long landed and the fence is cheap.  Consumers only look at
+    // the flags when they reach their boundary tiles, at the END of their pass.
+    auto publish_push = [&]() {
+        __syncthreads();   // the CTA's stores happen-before thread 0's fence (cumulative)
+        if (tid == 0) {
+            const int buf = (int)(hseq & 1);
+            __threadfence_system();
+            const unsigned t0 = atomicAdd(&a.sync.win->push_ticket, 1u);
+            if (t0 == (unsigned)a.sync.push_ctas - 1) {
+                a.sync.win->push_ticket = 0u;
+                __threadfence_system();
+                for (int q = 0; q < kMaxRanks; q++)
+                    if (a.sync.dst_mask & (1u << q))
+                        *reinterpret_cast<volatile unsigned long long *>(&a.sync.peer[q]->hflag[buf][a.sync.me]) = hseq;
+            }
+        }
+        push_pending = false;
+    };
 
     // thread 0 is the producer: it programs the TMA engine for one tile
     const uint64_t stream_policy = policy_evict_first();
@@ -244,6 +256,9 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
         if (tid == 0 && have_next && tile_staged(d_next)) issue((int)(sidx_after & 1u), d_next);
 
         if (HALO && !halo_ready && t >= a.first_halo_tile) {   // CTA-uniform
+            // never wait on peers while our own push is unpublished (two ranks
+            // whose pushing CTAs start on a boundary tile would wait forever)
+            if (push_pending) publish_push();
             if (tid == 0) {
                 for (int q = 0; q < kMaxRanks; q++)
                     if (a.sync.src_mask & (1u << q)) {
@@ -318,7 +333,9 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
         sidx = sidx_after;
         d_cur = d_next;
         d_next = d_next2;
+        if (HALO && push_pending) publish_push();
     }
+    if (HALO && push_pending) publish_push();   // a CTA without tiles
     pipe.sidx = sidx;
     // persistent callers: the matrix does not change between SpMVs, so the first
     // tile of the NEXT pass can already be in flight while other phases run
