@@ -569,7 +569,7 @@ static int finish_solve(sigb_solver_t s)
 // slower than the dedicated kernels, which wins when an iteration is long.
 // Measured cross-over on B200 (profiles/r1_size_sweep_persistent.jsonl): ~3 M
 // rows per GPU.  SIGB_CG_PERSISTENT=1 / 0 forces one or the other.
-static bool persistent_enabled(int64_t n_local)
+static bool persistent_enabled(int64_t n_local, int nranks)
 {
     static int v = -2;
     if (v == -2) {
@@ -577,7 +577,9 @@ static bool persistent_enabled(int64_t n_local)
         v = e ? (atoi(e) != 0 ? 1 : 0) : -1;
     }
     if (v >= 0) return v != 0;
-    return n_local <= 3000000;
+    // sharded: every all-reduce of the kernel-per-phase path is two more kernel
+    // boundaries, so the cross-over moves up
+    return nranks > 1 ? n_local <= 6300000 : n_local <= 3000000;
 }
 
 // L2 persistence for the solver's work vectors (north_star: "x-vector reuse
@@ -674,8 +676,9 @@ static int cg_solve_body(sigb_solver_t s, sigb_matrix_t A, double *x, const doub
         const double *val = nullptr;
         PersistComm pcomm;
         DotSpec halo;
-        bool eligible = persistent_enabled(n);
-        if (eligible) SIGB_CHECK(dist_persist_info(A, &pcomm, &halo, &eligible));
+        bool eligible = true;
+        SIGB_CHECK(dist_persist_info(A, &pcomm, &halo, &eligible));
+        eligible = eligible && persistent_enabled(n, pcomm.nranks);
         if (eligible) {
             sigb_graph_t g = A->g;
             if (g->kind == G_CSR) {
