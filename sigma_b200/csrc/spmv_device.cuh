@@ -293,10 +293,20 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
                 v[i] = (k < cnt) ? sval[k] : 0.0;
             }
             double xv[kTileNnz / kThreads];
+            // Only boundary tiles can hold halo columns, and whether a tile is one
+            // is uniform over the CTA: interior tiles take the plain gather; in
+            // boundary tiles the address is selected (no divergent branch between
+            // the gathers, which would serialise them) and everything is read at
+            // L2 -- halo entries are written by peers, so L1 must not serve them.
+            if (HALO && t >= a.first_halo_tile) {
 #pragma unroll
-            for (int i = 0; i < kTileNnz / kThreads; i++) {
-                if (HALO && c[i] > a.nloc) xv[i] = __ldcg(h1 + c[i]);   // written by peers: not via the nc path
-                else xv[i] = ld_x<XNC>(a.x1 + c[i]);
+                for (int i = 0; i < kTileNnz / kThreads; i++) {
+                    const double *src = (c[i] > a.nloc) ? h1 + c[i] : a.x1 + c[i];
+                    xv[i] = __ldcg(src);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < kTileNnz / kThreads; i++) xv[i] = ld_x<XNC>(a.x1 + c[i]);
             }
 #pragma unroll
             for (int i = 0; i < kTileNnz / kThreads; i++) {
@@ -311,7 +321,7 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
 #pragma unroll
             for (int i = 0; i < kTileRows / kThreads; i++) {
                 const int r = rs + tid + i * kThreads;
-                ur[i] = (NDOT >= 1 && r < re) ? ld_x<XNC>(a.u + r) : 0.0;
+                ur[i] = (NDOT >= 1 && r < re && a.u != nullptr) ? ld_x<XNC>(a.u + r) : 1.0;
             }
 #pragma unroll
             for (int i = 0; i < kTileRows / kThreads; i++) {
