@@ -526,8 +526,7 @@ int sigb_matvec_dot_dev(sigb_matrix_t A, const double *x_dev, double *y_dev, dou
     d.u = x_dev;
     d.out[0] = slot;
     SIGB_CHECK(solver_matvec(A, x_dev, y_dev, d, false));
-    static const bool no_red = getenv("SIGB_DEBUG_NO_RED") != nullptr;   // timing experiments only
-    if (!no_red) SIGB_CHECK(dist_allreduce(A, slot, 1));
+    SIGB_CHECK(dist_allreduce(A, slot, 1));
     if (dot) {  // dot == NULL: leave everything asynchronous (timing loops)
         SIGB_CUDA(cudaMemcpyAsync(dot, slot, sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
         SIGB_CUDA(cudaStreamSynchronize(ctx().stream));

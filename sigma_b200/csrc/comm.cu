@@ -276,9 +276,6 @@ int dist_matvec(sigb_matrix_t A, const double *x, double *y, bool add, const Dot
         // ONE kernel does push + interior + (wait) + boundary + acknowledge
         DotSpec db = dot;
         db.sync = &D->sync;
-        static const char *dbg = getenv("SIGB_DEBUG_DIST");   // timing experiments only
-        if (dbg && dbg[0] == 'g') db.out[0] = nullptr;         // dot partials without the grid reduction
-        if (dbg && dbg[0] == 's') db.sync = nullptr;           // no exchange (wrong halo values)
         return launch_csr_spmv(V, A->val, x, y, mode, db, 0, main, 0);
     } else if (exchange) {
         if (D->total_send > 0) {

@@ -577,9 +577,8 @@ static bool persistent_enabled(int64_t n_local, int nranks)
         v = e ? (atoi(e) != 0 ? 1 : 0) : -1;
     }
     if (v >= 0) return v != 0;
-    // sharded: every all-reduce of the kernel-per-phase path is two more kernel
-    // boundaries, so the cross-over moves up
-    return nranks > 1 ? n_local <= 6300000 : n_local <= 3000000;
+    (void)nranks;   // same cross-over measured at 1, 4 and 8 ranks (profiles/README.md)
+    return n_local <= 3000000;
 }
 
 // L2 persistence for the solver's work vectors (north_star: "x-vector reuse

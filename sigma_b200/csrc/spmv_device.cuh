@@ -321,7 +321,7 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
 #pragma unroll
             for (int i = 0; i < kTileRows / kThreads; i++) {
                 const int r = rs + tid + i * kThreads;
-                ur[i] = (NDOT >= 1 && r < re && a.u != nullptr) ? ld_x<XNC>(a.u + r) : 1.0;
+                ur[i] = (NDOT >= 1 && r < re) ? ld_x<XNC>(a.u + r) : 0.0;
             }
 #pragma unroll
             for (int i = 0; i < kTileRows / kThreads; i++) {

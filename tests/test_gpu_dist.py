@@ -21,7 +21,7 @@ def free_port():
 
 
 @pytest.mark.parametrize("transport", ["p2p", "nccl"])
-@pytest.mark.parametrize("world", [1, 2, 4])
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
 def test_row_sharded_parity(world, transport):
     import torch
 
