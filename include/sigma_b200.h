@@ -219,6 +219,24 @@ SIGB_API int sigb_lanczos(sigb_matrix_t A, int32_t n, const double *q1,
 SIGB_API int sigb_eigensolve(sigb_matrix_t A, int32_t n, const double *q1,
                              uint64_t seed, double *lambda, double *V);
 
+/* generalized_lanczos(A, B, T, Q) (src/eigensolver.f90:95-155) for
+ * A x = lambda B x.  Every step runs `call B%solve(w, v)` (:134): b_solver is
+ * the solver attached with B%set_solver (set up on B; the reference test uses
+ * cg(1.0d-15), test/eigensolver_test_generalized_lanczos.f90:150) and b_pc the
+ * optional preconditioner attached with B%set_preconditioner (NULL if none).
+ * The solve runs on the device with w = A q_i as its initial guess, like the
+ * reference facade (linear_operator_interface.f90:213-233). */
+SIGB_API int sigb_generalized_lanczos(sigb_matrix_t A, sigb_matrix_t B,
+                                      sigb_solver_t b_solver, sigb_solver_t b_pc,
+                                      int32_t n, const double *q1, uint64_t seed,
+                                      double *T, double *Q);
+/* generalized_eigensolve(A, B, lambda, V) (src/eigensolver.f90:189-208):
+ * generalized_lanczos, tridiagonal eigen-solve, V = V*Q (no sign fix). */
+SIGB_API int sigb_generalized_eigensolve(sigb_matrix_t A, sigb_matrix_t B,
+                                         sigb_solver_t b_solver, sigb_solver_t b_pc,
+                                         int32_t n, const double *q1, uint64_t seed,
+                                         double *lambda, double *V);
+
 /* ---- multi-GPU: row-sharded operators ----------------------------------
  * Not in the reference (serial).  The seam is the block-row loop of
  * composite_matvec_add (src/matrix/sparse_matrix_composites.f90:1076-1100,

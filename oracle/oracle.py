@@ -20,7 +20,7 @@ CSR, CSC, ELL = 1, 2, 3
 __all__ = [
     "CSR", "CSC", "ELL", "build", "lib", "Matrix", "ll_graph_edges", "cs_graph_build",
     "ellpack_graph_build", "matvec", "matvec_add", "jacobi_setup", "jacobi_solve",
-    "cg_solve", "bicgstab_solve", "lanczos", "eigensolve", "tridiag_eig",
+    "cg_solve", "bicgstab_solve", "lanczos", "generalized_lanczos", "eigensolve", "tridiag_eig",
     "partition_rows", "halo_build", "cs_set_value", "ell_set_value",
 ]
 
@@ -70,6 +70,7 @@ def lib():
         "orc_bicgstab_solve": (i64, [mp, _f64p, _f64p, f64, i64, _f64p, C.POINTER(f64), C.POINTER(i32)]),
         "orc_bicgstab_solve_jacobi": (i64, [mp, _f64p, _f64p, _f64p, f64, i64, _f64p, C.POINTER(f64), C.POINTER(i32)]),
         "orc_lanczos": (None, [mp, i32, _f64p, _f64p, _f64p, _f64p]),
+        "orc_generalized_lanczos": (i64, [mp, mp, i32, _f64p, f64, i64, _f64p, _f64p]),
         "orc_tridiag_eig": (i32, [i32, _f64p, _f64p, _f64p]),
         "orc_eigensolve": (i32, [mp, i32, _f64p, _f64p, _f64p]),
         "orc_partition_rows": (None, [i32, _i32p, i32, _i32p]),
@@ -210,6 +211,14 @@ def lanczos(A, n, q1):
     w = np.empty(A.nrow)
     lib().orc_lanczos(A.c, n, _f64(q1), T, Q, w)
     return T.reshape(n, 3).T.copy(), Q.reshape(n, A.nrow).T.copy()
+
+
+def generalized_lanczos(A, B, n, q1, cg_tol=1e-15, cg_max_iter=-1):
+    """orc_generalized_lanczos -> (T[3,n], Q[nrow,n], inner CG iterations)."""
+    T = np.empty(3 * n)
+    Q = np.empty(A.nrow * n)
+    inner = lib().orc_generalized_lanczos(A.c, B.c, n, _f64(q1), cg_tol, cg_max_iter, T, Q)
+    return T.reshape(n, 3).T.copy(), Q.reshape(n, A.nrow).T.copy(), int(inner)
 
 
 def tridiag_eig(d, e):

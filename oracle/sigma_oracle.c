@@ -795,6 +795,65 @@ ORC_API int32_t orc_eigensolve(const orc_matrix *A, int32_t n,
     return info;
 }
 
+/*
+ * generalized_lanczos, src/eigensolver.f90:95-155, for A x = lambda B x, with
+ * `call B%solve(w, v)` resolved as the reference test sets it up
+ * (test/eigensolver_test_generalized_lanczos.f90:150: B%set_solver(cg(tol)),
+ * no preconditioner): linear_operator_solve
+ * (src/linear_operator/linear_operator_interface.f90:213-233) -> cg_solve with
+ * w (= A q_i at that point) as the initial guess.  q1 is the un-normalised
+ * start vector (the reference draws it from the time-seeded RNG, :119-120).
+ * T(3, n), Q(nrow, n) column-major like orc_lanczos.  The z(:, 0:n) array of the
+ * reference (:108, deliberately indexed from 0, :112,136) is kept as is.
+ * Returns the total number of inner CG iterations.
+ */
+ORC_API int64_t orc_generalized_lanczos(const orc_matrix *A, const orc_matrix *B, int32_t n,
+                                        const double *q1, double cg_tol, int64_t cg_max_iter,
+                                        double *T, double *Q)
+{
+    const int64_t nr = A->nrow;
+    double *w = calloc((size_t)nr, sizeof(double)), *v = calloc((size_t)nr, sizeof(double));
+    double *z = calloc((size_t)nr * (n + 1), sizeof(double));   /* z(:, 0:n) */
+    double *work = calloc((size_t)nr * 4, sizeof(double));     /* cg_setup: p,q,r,z zeroed */
+    double alpha = 0.0, beta = 0.0, d;
+    int64_t l, inner = 0;
+    int32_t i;
+#define QC(c) (Q + (int64_t)((c) - 1) * nr)
+#define ZC(c) (z + (int64_t)(c) * nr)
+
+    for (l = 0; l < 3 * (int64_t)n; l++) T[l] = 0.0;
+    for (l = 0; l < nr * n; l++) Q[l] = 0.0;
+
+    for (l = 0; l < nr; l++) QC(1)[l] = q1[l];                 /* :119-120 */
+    orc_matvec(B, 0, QC(1), w);                                /* :121 */
+    d = sqrt(dot(w, QC(1), (int32_t)nr));                      /* :122 */
+    for (l = 0; l < nr; l++) QC(1)[l] = QC(1)[l] / d;
+    orc_matvec(B, 0, QC(1), ZC(1));                            /* :123 */
+
+    for (i = 1; i <= n - 1; i++) {                             /* :128 */
+        orc_matvec(A, 0, QC(i), w);                            /* :129 */
+        for (l = 0; l < nr; l++) v[l] = w[l] - beta * ZC(i - 1)[l];   /* :130 */
+        alpha = dot(v, QC(i), (int32_t)nr);                    /* :131 */
+        for (l = 0; l < nr; l++) v[l] = v[l] - alpha * ZC(i)[l];      /* :132 */
+
+        inner += orc_cg_solve(B, w, v, cg_tol, cg_max_iter, work, NULL, NULL);   /* :134 */
+
+        beta = sqrt(dot(w, v, (int32_t)nr));                   /* :136 */
+        for (l = 0; l < nr; l++) QC(i + 1)[l] = w[l] / beta;   /* :137 */
+        for (l = 0; l < nr; l++) ZC(i + 1)[l] = v[l] / beta;   /* :138 */
+        T[3 * (i - 1) + 1] = alpha;                            /* :140-142 */
+        T[3 * (i - 1) + 2] = beta;
+        T[3 * (i - 1) + 0] = beta;
+    }
+    orc_matvec(A, 0, QC(n), v);                                /* :145 */
+    for (l = 0; l < nr; l++) v[l] = v[l] - beta * ZC(n)[l];    /* :146 */
+    T[3 * (n - 1) + 1] = dot(QC(n), v, (int32_t)nr);           /* :147 (i == n after the loop) */
+#undef QC
+#undef ZC
+    free(w); free(v); free(z); free(work);
+    return inner;
+}
+
 /* ------------------------------------------------------------------------ */
 /* Row-block partition + halo lists (index work for the multi-GPU path).     */
 /* Not in the reference (it is serial); the single source of truth the       */

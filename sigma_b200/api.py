@@ -27,6 +27,7 @@ from . import _capi
 from ._capi import ROW, COL, SigmaError, as_f64, as_i32, check, lib, ptr
 
 __all__ = ["init", "Graph", "Matrix", "Solver", "cg", "bicgstab", "jacobi", "lanczos", "eigensolve",
+           "generalized_lanczos", "generalized_eigensolve",
            "csr_matrix", "csc_matrix", "ellpack_matrix", "SigmaError", "launch_count", "set_stream",
            "synchronize"]
 
@@ -264,4 +265,25 @@ def eigensolve(A: Matrix, n: int, q1=None, seed: int = 0):
     V = np.empty(A.nrow * n)
     q1a = as_f64(q1) if q1 is not None else None
     check(lib().sigb_eigensolve(A._h, n, ptr(q1a), seed, ptr(lam), ptr(V)))
+    return lam, V.reshape(n, A.nrow).T.copy()
+
+
+def generalized_lanczos(A: Matrix, B: Matrix, b_solver: Solver, n: int, q1=None, seed: int = 0, b_pc: "Solver | None" = None):
+    """call B%set_solver(b_solver); call generalized_lanczos(A, B, T, Q) -> T[3, n], Q[nrow, n]."""
+    T = np.empty(3 * n)
+    Q = np.empty(A.nrow * n)
+    q1a = as_f64(q1) if q1 is not None else None
+    check(lib().sigb_generalized_lanczos(A._h, B._h, b_solver._h, b_pc._h if b_pc else None, n, ptr(q1a), seed,
+                                         ptr(T), ptr(Q)))
+    return T.reshape(n, 3).T.copy(), Q.reshape(n, A.nrow).T.copy()
+
+
+def generalized_eigensolve(A: Matrix, B: Matrix, b_solver: Solver, n: int, q1=None, seed: int = 0,
+                           b_pc: "Solver | None" = None):
+    """call generalized_eigensolve(A, B, lambda, V) -> lambda[n] ascending, V[nrow, n]."""
+    lam = np.empty(n)
+    V = np.empty(A.nrow * n)
+    q1a = as_f64(q1) if q1 is not None else None
+    check(lib().sigb_generalized_eigensolve(A._h, B._h, b_solver._h, b_pc._h if b_pc else None, n, ptr(q1a), seed,
+                                            ptr(lam), ptr(V)))
     return lam, V.reshape(n, A.nrow).T.copy()

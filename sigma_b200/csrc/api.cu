@@ -687,19 +687,29 @@ int sigb_solver_destroy(sigb_solver_t s)
 // eigensolver
 // ===========================================================================
 
+// B == nullptr: lanczos / eigensolve; else generalized_lanczos / generalized_eigensolve
+// with `bs` (+ optional `bpc`) as the solver attached to B.
 static int lanczos_common(sigb_matrix_t A, int32_t n, const double *q1, uint64_t seed, double *T,
-                          double *Q, double *lambda, bool ritz)
+                          double *Q, double *lambda, bool ritz, sigb_matrix_t B = nullptr,
+                          sigb_solver_t bs = nullptr, sigb_solver_t bpc = nullptr)
 {
     SIGB_REQUIRE(A && n >= 1, SIGB_ERR_ARG, "lanczos: bad argument");
+    if (B) {
+        SIGB_REQUIRE(bs && bs->initialized && bs->nn == B->nrow, SIGB_ERR_STATE,
+                     "generalized_lanczos: B has no solver set up (call B%%set_solver first)");
+        SIGB_REQUIRE(B->nrow == A->nrow && B->ncol == A->ncol, SIGB_ERR_ARG, "generalized_lanczos: A and B differ in shape");
+    }
     const int64_t nglob = A->dist ? dist_global_n(A) : A->ncol;
     SIGB_REQUIRE((A->dist ? dist_global_n(A) : A->nrow) == nglob, SIGB_ERR_NONSQUARE, "lanczos: operator is not square");
     const int64_t nr = A->nrow;
     cudaStream_t st = ctx().stream;
     double *Qd = nullptr, *Td = nullptr, *w = nullptr, *q1d = nullptr, *V2 = nullptr, *small = nullptr;
+    double *gv = nullptr, *gz = nullptr;
     void *kst = nullptr;
     int rc = SIGB_OK;
     auto cleanup = [&]() {
         cudaFree(Qd); cudaFree(Td); cudaFree(w); cudaFree(q1d); cudaFree(V2); cudaFree(small); cudaFree(kst);
+        cudaFree(gv); cudaFree(gz);
     };
 #define LZ_TRY(expr) do { rc = (expr); if (rc != SIGB_OK) { cleanup(); return rc; } } while (0)
 #define LZ_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cleanup(); return cuda_fail(e_, #expr, __FILE__, __LINE__); } } while (0)
@@ -712,7 +722,14 @@ static int lanczos_common(sigb_matrix_t A, int32_t n, const double *q1, uint64_t
         LZ_TRY(dev_alloc(&q1d, (size_t)nr));
         LZ_CUDA(cudaMemcpyAsync(q1d, q1, sizeof(double) * (size_t)nr, cudaMemcpyHostToDevice, st));
     }
-    LZ_TRY(lanczos_dev(A, n, q1d, seed, A->dist ? dist_row_offset(A) : 0, Td, Qd, w, (KState *)kst));
+    if (B) {
+        LZ_TRY(dev_alloc(&gv, (size_t)nr));
+        LZ_TRY(dev_alloc(&gz, (size_t)3 * nr));
+        LZ_TRY(generalized_lanczos_dev(A, B, bs, bpc, n, q1d, seed, A->dist ? dist_row_offset(A) : 0, Td, Qd, w, gv,
+                                       gz, (KState *)kst));
+    } else {
+        LZ_TRY(lanczos_dev(A, n, q1d, seed, A->dist ? dist_row_offset(A) : 0, Td, Qd, w, (KState *)kst));
+    }
     std::vector<double> Th((size_t)3 * n);
     LZ_CUDA(cudaMemcpyAsync(Th.data(), Td, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, st));
     LZ_CUDA(cudaStreamSynchronize(st));
@@ -730,7 +747,7 @@ static int lanczos_common(sigb_matrix_t A, int32_t n, const double *q1, uint64_t
         LZ_TRY(dev_alloc(&V2, (size_t)nr * n));
         LZ_TRY(dev_alloc(&small, (size_t)n * n + n));
         LZ_CUDA(cudaMemcpyAsync(small, Z.data(), sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, st));
-        LZ_TRY(ritz_vectors_dev(Qd, V2, small, nr, n, small + (size_t)n * n));
+        LZ_TRY(ritz_vectors_dev(Qd, V2, small, nr, n, B ? nullptr : small + (size_t)n * n));
         if (lambda) memcpy(lambda, d.data(), sizeof(double) * (size_t)n);
     }
     if (Q) LZ_CUDA(cudaMemcpyAsync(Q, Qd, sizeof(double) * (size_t)nr * n, cudaMemcpyDeviceToHost, st));
@@ -752,6 +769,21 @@ int sigb_eigensolve(sigb_matrix_t A, int32_t n, const double *q1, uint64_t seed,
     SIGB_REQUIRE(lambda && V, SIGB_ERR_ARG, "sigb_eigensolve: lambda and V are required");
     SIGB_REQUIRE(!(A && A->dist), SIGB_ERR_UNSUPPORTED, "sigb_eigensolve on a row-sharded operator");
     return lanczos_common(A, n, q1, seed, nullptr, V, lambda, true);
+}
+
+int sigb_generalized_lanczos(sigb_matrix_t A, sigb_matrix_t B, sigb_solver_t b_solver, sigb_solver_t b_pc,
+                             int32_t n, const double *q1, uint64_t seed, double *T, double *Q)
+{
+    SIGB_REQUIRE(B && T && Q, SIGB_ERR_ARG, "sigb_generalized_lanczos: B, T and Q are required");
+    return lanczos_common(A, n, q1, seed, T, Q, nullptr, false, B, b_solver, b_pc);
+}
+
+int sigb_generalized_eigensolve(sigb_matrix_t A, sigb_matrix_t B, sigb_solver_t b_solver, sigb_solver_t b_pc,
+                                int32_t n, const double *q1, uint64_t seed, double *lambda, double *V)
+{
+    SIGB_REQUIRE(B && lambda && V, SIGB_ERR_ARG, "sigb_generalized_eigensolve: B, lambda and V are required");
+    SIGB_REQUIRE(!(A && A->dist), SIGB_ERR_UNSUPPORTED, "sigb_generalized_eigensolve on a row-sharded operator");
+    return lanczos_common(A, n, q1, seed, nullptr, V, lambda, true, B, b_solver, b_pc);
 }
 
 }  // extern "C"

@@ -109,7 +109,9 @@ __device__ __forceinline__ double grid_allreduce(double v, const CgPersistArgs &
         red_seq++;
         const int slot = (int)(red_seq & (kRedSlots - 1));
         const unsigned flag = (unsigned)red_seq;
-        if (blockIdx.x == 0 && threadIdx.x < 32) {
+        // published by the LAST CTA: CTA 0 also pushes halo entries and would be
+        // the latest to get here
+        if (blockIdx.x == gridDim.x - 1 && threadIdx.x < 32) {
             const double local = __shfl_sync(0xffffffffu, t[0], 0);
             if ((int)threadIdx.x < a.nranks) {
                 RedEntry *e = a.peer_red[threadIdx.x]->red[slot][a.me];
@@ -180,12 +182,11 @@ cg_persistent_kernel(const CgPersistArgs a)
         hseq++;
         spmv_phase<MODE_SET, 1, HALO, false>(a.A, smem, mbar, pipe, acc, hseq, true);
         const double pq = grid_allreduce(acc[0], a, s, pbuf, red_seq, sm_red, &s_bcast);
-        if (HALO && a.A.sync.win != nullptr && blockIdx.x == 0 && tid == 0 && a.A.sync.src_mask) {
-            // every CTA is past the barrier: this landing buffer has been consumed
-            __threadfence_system();
-            for (int q = 0; q < kMaxRanks; q++)
-                if (a.A.sync.src_mask & (1u << q))
-                    *reinterpret_cast<volatile unsigned long long *>(&a.A.sync.peer[q]->ack[a.A.sync.me]) = hseq;
+        if (HALO && a.A.sync.win != nullptr && blockIdx.x == gridDim.x - 1 && tid < kMaxRanks &&
+            (a.A.sync.src_mask & (1u << tid))) {
+            // every CTA is past the barrier, i.e. has consumed this landing buffer
+            // (its loads have completed); one lane per source rank acknowledges
+            *reinterpret_cast<volatile unsigned long long *>(&a.A.sync.peer[tid]->ack[a.A.sync.me]) = hseq;
         }
         const double alpha = rr / pq;                                   // cg_solvers.f90:136
 

@@ -445,6 +445,64 @@ struct LanczosOrthoOp {
     __device__ double *out(int) { return o; }
 };
 
+// generalized Lanczos (eigensolver.f90:130-131 / :146-147):
+// v = w - beta*zprev ; dot(v, q) -> *o
+struct GenLanczosVOp {
+    static constexpr int ND = 1;
+    const double *__restrict__ w, *__restrict__ zprev, *__restrict__ q;
+    double *__restrict__ v;
+    const double *beta_p;
+    double *o;
+    double beta;
+    __device__ bool begin() { beta = *beta_p; return true; }
+    static constexpr int NIN = 3;
+    __device__ void load(int64_t i, double *in) { in[0] = w[i]; in[1] = zprev[i]; in[2] = q[i]; }
+    __device__ void compute(int64_t i, const double *in, double *acc)
+    {
+        const double vi = sub(in[0], mul(beta, in[1]));
+        v[i] = vi;
+        acc[0] = add(acc[0], mul(vi, in[2]));
+    }
+    __device__ double *out(int) { return o; }
+};
+
+// v = v - alpha*z   (eigensolver.f90:132)
+struct GenLanczosAxpyOp {
+    static constexpr int ND = 0;
+    double *__restrict__ v;
+    const double *__restrict__ z;
+    const double *alpha_p;
+    double alpha;
+    __device__ bool begin() { alpha = *alpha_p; return true; }
+    static constexpr int NIN = 2;
+    __device__ void load(int64_t i, double *in) { in[0] = v[i]; in[1] = z[i]; }
+    __device__ void compute(int64_t i, const double *in, double *) { v[i] = sub(in[0], mul(alpha, in[1])); }
+    __device__ double *out(int) { return nullptr; }
+};
+
+// beta = sqrt(w.v) ; q_next = w / beta ; z_next = v / beta ; T(:, i)   (eigensolver.f90:136-142)
+struct GenLanczosScaleOp {
+    static constexpr int ND = 0;
+    const double *__restrict__ w, *__restrict__ v;
+    double *__restrict__ qn, *__restrict__ zn;
+    const double *norm2, *alpha;
+    double *Tcol, *beta_out;
+    double d;
+    __device__ bool begin()
+    {
+        d = sqrt(*norm2);
+        if (first_thread()) {
+            Tcol[1] = *alpha; Tcol[2] = d; Tcol[0] = d;
+            *beta_out = d;
+        }
+        return true;
+    }
+    static constexpr int NIN = 2;
+    __device__ void load(int64_t i, double *in) { in[0] = w[i]; in[1] = v[i]; }
+    __device__ void compute(int64_t i, const double *in, double *) { qn[i] = in[0] / d; zn[i] = in[1] / d; }
+    __device__ double *out(int) { return nullptr; }
+};
+
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
 {
     x += 0x9E3779B97F4A7C15ull;
@@ -853,6 +911,65 @@ int lanczos_dev(sigb_matrix_t A, int32_t n, const double *q1, uint64_t seed, int
     return SIGB_OK;
 }
 
+// n-step generalized Lanczos for A x = lambda B x (eigensolver.f90:95-155) on
+// device arrays.  `call B%solve(w, v)` (:134) runs the attached solver -- the
+// device CG / PCG -- with w (= A q_i) as the initial guess, exactly like the
+// reference's facade (linear_operator_interface.f90:213-233).  Only z_{i-1},
+// z_i, z_{i+1} are live, so three rotating buffers replace the reference's
+// z(:, 0:n).  zbuf: 3*nr doubles, w and v: nr each.
+int generalized_lanczos_dev(sigb_matrix_t A, sigb_matrix_t B, sigb_solver_t bs, sigb_solver_t bpc, int32_t n,
+                            const double *q1, uint64_t seed, int64_t row_offset, double *T, double *Q, double *w,
+                            double *v, double *zbuf, KState *st)
+{
+    const int64_t nr = A->nrow;
+    cudaStream_t stream = ctx().stream;
+    SIGB_CUDA(cudaMemsetAsync(T, 0, sizeof(double) * 3 * (size_t)n, stream));
+    SIGB_CUDA(cudaMemsetAsync(Q, 0, sizeof(double) * (size_t)nr * n, stream));
+    SIGB_CUDA(cudaMemsetAsync(zbuf, 0, sizeof(double) * 3 * (size_t)nr, stream));
+    SIGB_CUDA(cudaMemsetAsync(st, 0, sizeof(KState), stream));     // alpha = beta = 0 (:125-126)
+    auto col = [&](int c) { return Q + (size_t)(c - 1) * nr; };    // 1-based column
+    auto zc = [&](int c) { return zbuf + (size_t)(((c % 3) + 3) % 3) * nr; };   // z(:, c), c = 0..n
+
+    if (q1) {
+        SIGB_CUDA(cudaMemcpyAsync(col(1), q1, sizeof(double) * (size_t)nr, cudaMemcpyDeviceToDevice, stream));
+    } else {
+        RandomOp rnd{col(1), seed, row_offset};
+        SIGB_CHECK(launch_ew(rnd, nr));
+    }
+    {   // w = B q1 ; q1 = q1 / sqrt(w.q1) ; z(:,1) = B q1           :121-123
+        DotSpec d;
+        d.ndot = 1; d.u = col(1); d.out[0] = &st->lz[2];
+        SIGB_CHECK(solver_matvec(B, col(1), w, d, false));
+        SIGB_CHECK(dist_allreduce(B, &st->lz[2], 1));
+        ScaleOp sc{col(1), col(1), &st->lz[2], nullptr, nullptr, nullptr, 0.0};
+        SIGB_CHECK(launch_ew(sc, nr));
+        DotSpec none;
+        SIGB_CHECK(solver_matvec(B, col(1), zc(1), none, false));
+    }
+    DotSpec none;
+    for (int i = 1; i <= n - 1; i++) {
+        SIGB_CHECK(solver_matvec(A, col(i), w, none, false));                       // :129
+        GenLanczosVOp vop{w, zc(i - 1), col(i), v, &st->lz[1], &st->lz[0], 0.0};      // :130-131
+        SIGB_CHECK(launch_ew(vop, nr));
+        SIGB_CHECK(dist_allreduce(A, &st->lz[0], 1));
+        GenLanczosAxpyOp ax{v, zc(i), &st->lz[0], 0.0};                               // :132
+        SIGB_CHECK(launch_ew(ax, nr));
+        SIGB_CHECK(sigb_solver_solve_dev(bs, B, w, v, bpc));                          // :134
+        DotOp dop{w, v, &st->lz[2]};                                                  // :136
+        SIGB_CHECK(launch_ew(dop, nr));
+        SIGB_CHECK(dist_allreduce(A, &st->lz[2], 1));
+        GenLanczosScaleOp sc{w, v, col(i + 1), zc(i + 1), &st->lz[2], &st->lz[0], T + 3 * (size_t)(i - 1),
+                             &st->lz[1], 0.0};                                         // :137-142
+        SIGB_CHECK(launch_ew(sc, nr));
+    }
+    // v = A q_n - beta z(:,n) ; T(2,n) = q_n . v                                    :145-147
+    SIGB_CHECK(solver_matvec(A, col(n), w, none, false));
+    GenLanczosVOp vop{w, zc(n), col(n), v, &st->lz[1], &T[3 * (size_t)(n - 1) + 1], 0.0};
+    SIGB_CHECK(launch_ew(vop, nr));
+    SIGB_CHECK(dist_allreduce(A, &T[3 * (size_t)(n - 1) + 1], 1));
+    return SIGB_OK;
+}
+
 // Symmetric tridiagonal eigen-solve standing in for LAPACK dstev('V')
 // (eigensolver.f90:174; LAPACK is not vendored by the reference).  Implicit QL
 // with Wilkinson shifts; eigenvalues ascending, eigenvectors in the columns of
@@ -939,9 +1056,12 @@ int ritz_vectors_dev(double *V, double *V2, const double *Qm_dev, int64_t nr, in
     SIGB_CUDA(cudaFuncSetAttribute(ritz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ritz_kernel<<<ew_grid(nr), kThreads, smem, st>>>(V, Qm_dev, nr, n, V2);
     SIGB_CUDA(cudaMemcpyAsync(V, V2, sizeof(double) * (size_t)nr * n, cudaMemcpyDeviceToDevice, st));
-    grab_first_row_kernel<<<1, 128, 0, st>>>(V, nr, n, first_row_dev);
-    sign_kernel<<<ew_grid(nr), kThreads, 0, st>>>(V, nr, n, first_row_dev);
-    count_launch(3);
+    count_launch(1);
+    if (first_row_dev) {   // sign normalisation of eigensolve (:178-180); generalized_eigensolve has none
+        grab_first_row_kernel<<<1, 128, 0, st>>>(V, nr, n, first_row_dev);
+        sign_kernel<<<ew_grid(nr), kThreads, 0, st>>>(V, nr, n, first_row_dev);
+        count_launch(2);
+    }
     SIGB_CUDA(cudaGetLastError());
     return SIGB_OK;
 }

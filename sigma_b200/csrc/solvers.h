@@ -41,6 +41,9 @@ int bicgstab_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x, const double
                        sigb_solver_t pc);
 int lanczos_dev(sigb_matrix_t A, int32_t n, const double *q1, uint64_t seed, int64_t row_offset,
                 double *T, double *Q, double *w, KState *st);
+int generalized_lanczos_dev(sigb_matrix_t A, sigb_matrix_t B, sigb_solver_t bs, sigb_solver_t bpc, int32_t n,
+                            const double *q1, uint64_t seed, int64_t row_offset, double *T, double *Q, double *w,
+                            double *v, double *zbuf, KState *st);
 int tridiag_eig_host(int n, double *d, double *e, double *Z);
 int ritz_vectors_dev(double *V, double *V2, const double *Qm_dev, int64_t nr, int32_t n,
                      double *first_row_dev);

@@ -21,7 +21,7 @@ import numpy as np
 __all__ = [
     "tridiag_add_edge_calls", "tridiag_csr", "tridiag_ell", "poisson2d_add_edge_calls",
     "poisson2d_csr", "poisson2d_rhs", "csr_to_ell", "csr_transpose", "erdos_renyi_csr",
-    "erdos_renyi_add_edge_calls", "fem_p1_csr", "dense_from_csr",
+    "erdos_renyi_add_edge_calls", "fem_p1_csr", "dense_from_csr", "periodic_p1_grid",
 ]
 
 
@@ -286,3 +286,53 @@ def fem_p1_csr(N, seed=2024, jitter=0.25):
     vals = np.where(bnd[rows] | bnd[cols], np.where(rows == cols, 1.0, 0.0), vals)
     ptr = np.concatenate([[1], 1 + np.cumsum(np.bincount(rows, minlength=nv))]).astype(np.int32)
     return ptr, (cols + 1).astype(np.int32), vals.astype(np.float64)
+
+
+# --------------------------------------------------------------------------
+# Stiffness and mass matrices of the generalized-Lanczos test
+# (test/eigensolver_test_generalized_lanczos.f90:59-133): periodic nx x ny grid of
+# right triangles, built with the test's own add_edge / A%add call order.
+# --------------------------------------------------------------------------
+def periodic_p1_grid(nx=48, ny=32):
+    """Returns (ptr, node, valA, valB): both matrices share the CSR pattern."""
+    nn = nx * ny
+
+    def indx(i, j):          # 1-based (i, j) -> 1-based vertex, :203-209
+        return ny * (j - 1) + i
+
+    lists = [[] for _ in range(nn)]
+
+    def add_edge(a, b):
+        if b not in lists[a - 1]:
+            lists[a - 1].append(b)
+
+    for i in range(1, ny + 1):
+        for j in range(1, nx + 1):
+            k = indx(i, j)
+            add_edge(k, k)
+            for l in (indx(i % ny + 1, j), indx(i, j % nx + 1), indx(i % ny + 1, j % nx + 1)):
+                add_edge(k, l)
+                add_edge(l, k)
+    ptr = np.concatenate([[1], 1 + np.cumsum([len(l) for l in lists])]).astype(np.int32)
+    node = np.array([c for l in lists for c in l], np.int32)
+    pos = [{c: ptr[r] - 1 + t for t, c in enumerate(l)} for r, l in enumerate(lists)]
+    area = 0.5
+    BE = np.full((3, 3), area / 12.0)
+    BE[np.arange(3), np.arange(3)] = area / 6.0
+    AE = np.array([[area, -area, 0.0], [-area, 2 * area, -area], [0.0, -area, area]])
+    valA, valB = np.zeros(node.size), np.zeros(node.size)
+
+    def add(elem):           # A%add(elem, elem, AE): k outer, l inner (cs_matrices.f90:934-967)
+        for k in range(3):
+            for l in range(3):
+                p = pos[elem[k] - 1][elem[l]]
+                valA[p] += AE[k, l]
+                valB[p] += BE[k, l]
+
+    for i in range(1, ny + 1):
+        for j in range(1, nx + 1):
+            e = [indx(i, j), indx(i, j % nx + 1), indx(i % ny + 1, j % nx + 1)]
+            add(e)
+            e[1] = indx(i % ny + 1, j)
+            add(e)
+    return ptr, node, valA, valB

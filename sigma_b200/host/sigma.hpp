@@ -421,4 +421,30 @@ inline void eigensolve(linear_operator &A, int n, dp *lambda, dp *V, bool use_q1
     sigb_check(sigb_eigensolve(M.mirror, n, use_q1 ? q1.data() : nullptr, seed, lambda, V));
 }
 
+// call B%set_solver(...) first; call generalized_lanczos(A, B, T, Q)   (eigensolver.f90:95-155)
+inline void generalized_lanczos(linear_operator &A, linear_operator &B, int n, dp *T, dp *Q, bool use_q1 = false,
+                                uint64_t seed = 0)
+{
+    device_matrix &MA = linear_solver::mirrored(A), &MB = linear_solver::mirrored(B);
+    if (!B.solver) { std::printf(" generalized_lanczos: B has no solver set\n Terminating.\n"); std::exit(1); }
+    MA.sync_mirror();
+    MB.sync_mirror();
+    std::vector<dp> q1;
+    if (use_q1) q1.assign(Q, Q + A.nrow);
+    sigb_check(sigb_generalized_lanczos(MA.mirror, MB.mirror, B.solver->dev, B.pc ? B.pc->dev : nullptr, n,
+                                        use_q1 ? q1.data() : nullptr, seed, T, Q));
+}
+inline void generalized_eigensolve(linear_operator &A, linear_operator &B, int n, dp *lambda, dp *V,
+                                   bool use_q1 = false, uint64_t seed = 0)
+{
+    device_matrix &MA = linear_solver::mirrored(A), &MB = linear_solver::mirrored(B);
+    if (!B.solver) { std::printf(" generalized_eigensolve: B has no solver set\n Terminating.\n"); std::exit(1); }
+    MA.sync_mirror();
+    MB.sync_mirror();
+    std::vector<dp> q1;
+    if (use_q1) q1.assign(V, V + A.nrow);
+    sigb_check(sigb_generalized_eigensolve(MA.mirror, MB.mirror, B.solver->dev, B.pc ? B.pc->dev : nullptr, n,
+                                           use_q1 ? q1.data() : nullptr, seed, lambda, V));
+}
+
 }  // namespace sigma

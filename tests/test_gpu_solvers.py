@@ -287,3 +287,37 @@ def test_full_size_cg_residual_consistency(sb):
     r = b - A.matvec(x)
     assert abs(np.sqrt(res2) - np.linalg.norm(r)) <= 1e-9 * np.linalg.norm(b)
     assert np.linalg.norm(r) < np.linalg.norm(b)
+
+
+def test_generalized_lanczos_like_reference_test(sb, orc):
+    """test/eigensolver_test_generalized_lanczos.f90:59-200 on the device: the
+    reference's own stiffness / mass matrices, B%set_solver(cg(1.0d-15)), nq = 48;
+    the identities the test checks (1e-14) and T against the oracle."""
+    ptr, node, vA, vB = G.periodic_p1_grid()
+    nn, nq = 48 * 32, 48
+    A = sb.csr_matrix(nn, nn, ptr, node, vA)
+    B = sb.csr_matrix(nn, nn, ptr, node, vB)
+    bs = sb.cg(1e-15)
+    bs.setup(B)                       # call B%set_solver(cg(1.0d-15))
+    bs.set_max_iterations(5000)
+    q1 = 2 * np.random.default_rng(0).random(nn) - 1
+    T, V = sb.generalized_lanczos(A, B, bs, nq, q1)
+    assert not bs.info()[2] and bs.iterations > 0
+    U = np.stack([B.matvec(V[:, i]) for i in range(nq)], 1)
+    for i in range(1, nq - 1):
+        w = A.matvec(V[:, i])
+        z = T[1, i] * U[:, i] + T[0, i - 1] * U[:, i - 1] + T[2, i] * U[:, i + 1]
+        assert np.sqrt(((w - z) ** 2).sum() / (w * w).sum()) <= 1e-14
+    Qm = V.T @ U - np.eye(nq)
+    assert np.sqrt((Qm**2).sum()) / nq <= 1e-14
+    OA = orc.Matrix(orc.CSR, nn, nn, node, vA, ptr=ptr)
+    OB = orc.Matrix(orc.CSR, nn, nn, node, vB, ptr=ptr)
+    To, Vo, _ = orc.generalized_lanczos(OA, OB, nq, q1, 1e-15, 5000)
+    assert np.allclose(T[:, :8], To[:, :8], rtol=1e-9, atol=1e-11)
+    assert np.allclose(V[:, :4], Vo[:, :4], atol=1e-11)
+    # generalized_eigensolve: Ritz values of (A, B) from the same T
+    lam, W = sb.generalized_eigensolve(A, B, bs, nq, q1)
+    ref = np.linalg.eigvalsh(np.diag(T[1]) + np.diag(T[2, :-1], 1) + np.diag(T[2, :-1], -1))
+    assert np.allclose(lam, ref, rtol=1e-8, atol=1e-8)
+    # the smallest Ritz value approximates the zero eigenvalue of the periodic stiffness matrix
+    assert abs(lam[0]) < 1e-6

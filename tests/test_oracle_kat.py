@@ -204,3 +204,25 @@ def test_lanczos_identities(orc):
     assert info == 0
     ref = np.linalg.eigvalsh(np.diag(T[1]) + np.diag(T[2, :-1], 1) + np.diag(T[2, :-1], -1))
     assert np.allclose(lam, ref, rtol=1e-12, atol=1e-12)
+
+
+def test_generalized_lanczos_reference_test(orc):
+    """test/eigensolver_test_generalized_lanczos.f90 with its own deterministic
+    matrices (48 x 32 periodic P1 grid, stiffness A and mass B, B%set_solver(cg(1e-15)),
+    nq = 48): three-term recurrence A v_i = alpha_i B v_i + beta_{i-1} B v_{i-1} +
+    beta_i B v_{i+1} and B-orthogonality, both 1e-14 (:168-171,197-200)."""
+    ptr, node, vA, vB = G.periodic_p1_grid()
+    nn, nq = 48 * 32, 48
+    assert np.diff(ptr).max() == 7
+    A = orc.Matrix(orc.CSR, nn, nn, node, vA, ptr=ptr)
+    B = orc.Matrix(orc.CSR, nn, nn, node, vB, ptr=ptr)
+    q1 = 2 * np.random.default_rng(0).random(nn) - 1
+    T, V, inner = orc.generalized_lanczos(A, B, nq, q1, 1e-15, 10000)
+    assert inner > 0
+    U = np.stack([orc.matvec(B, V[:, i]) for i in range(nq)], 1)
+    for i in range(1, nq - 1):
+        w = orc.matvec(A, V[:, i])
+        z = T[1, i] * U[:, i] + T[0, i - 1] * U[:, i - 1] + T[2, i] * U[:, i + 1]
+        assert np.sqrt(((w - z) ** 2).sum() / (w * w).sum()) <= 1e-14
+    Qm = V.T @ U - np.eye(nq)
+    assert np.sqrt((Qm**2).sum()) / nq <= 1e-14
