@@ -10,8 +10,3 @@ for n in 1 2 4 8; do
   fi
   echo "N=$n rc=$?"; cat $OUT/bench_n$n.json; tail -2 $OUT/bench_n$n.err | grep -v "^\*\|OMP"
 done
-# which CG driver wins at N=4 (4.2 M rows per GPU)?
-for p in 0 1; do
-  SIGB_CG_PERSISTENT=$p timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 \
-    bench.py --gpus 4 --steps $STEPS --warmup 5 --quick 2>/dev/null | sed "s/^{/{\"persistent\": $p, /" | tee -a $OUT/n4_ab.jsonl
-done
