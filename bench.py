@@ -43,51 +43,75 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """SM clock and throttle reasons DURING the timed region, polled through NVML
+    every 10 ms from a thread (an nvidia-smi subprocess takes longer to start than
+    a sharded run takes to finish); falls back to one nvidia-smi query."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
-
-    def __enter__(self):
+        self.index, self.sm, self.mask, self.max_sm = index, [], 0, None
+        self._stop = threading.Event()
+        self._thr = None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
-                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
-        return self
+            self.nv = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def __exit__(self, *a):
-        if self.proc:
-            time.sleep(0.15)
-            self.proc.terminate()
-            self.t.join(timeout=2)
-
-    def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+    def _poll_once(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for nme, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nme)
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
             except Exception:
                 pass
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self._poll_once()
+            except Exception:
+                break
+            self._stop.wait(0.01)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        if self._thr is not None:
+            try:
+                self._poll_once()          # at least one sample right at the end of the region
+            except Exception:
+                pass
+            self._stop.set()
+            self._thr.join(timeout=2)
+        elif not self.sm:
+            try:
+                out = subprocess.check_output(
+                    ["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits", "-i",
+                     str(self.index)], text=True, timeout=10)
+                a_, b_ = out.strip().split(",")
+                self.sm.append(float(a_)); self.max_sm = float(b_)
+            except Exception:
+                pass
+
+    def summary(self):
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": [], "samples": 0}
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "samples": len(self.sm)}
 
 
 # ---------------------------------------------------------------------------
