@@ -157,6 +157,49 @@ SIGB_API int sigb_matvec_dev(sigb_matrix_t A, int trans, const double *x_dev,
 SIGB_API int sigb_matvec_dot_dev(sigb_matrix_t A, const double *x_dev,
                                  double *y_dev, double *dot);
 
+/* ---- operator expressions ----------------------------------------------
+ * In the reference every sparse matrix IS a linear_operator, and operators
+ * compose lazily: `A + B`, `A * B`, `adjoint(A)` and the block composite
+ * `sparse_matrix`.  Here an expression is again a sigb_matrix_t: it can be
+ * passed to sigb_matvec*, sigb_solver_setup / _solve (cg, bicgstab; jacobi
+ * where get_value is defined, i.e. not on products), sigb_lanczos*, and to
+ * these constructors again.  Intermediate vectors stay on the device and every
+ * leaf keeps the reference's accumulation order.  Each constructor takes a
+ * reference on its operands (add_reference); sigb_matrix_destroy on an
+ * expression drops them again (operator_sum_destroy
+ * linear_operator_sums.f90:136-159).  Row-sharded operators cannot be
+ * operands. */
+typedef sigb_matrix_t sigb_operator_t;   /* readability only: same handle */
+
+/* C = A + B: add_operators (src/linear_operator/linear_operator_sums.f90:38-72);
+ * matvec_add runs the summands in order into the same y (:100-131). */
+SIGB_API int sigb_operator_sum(sigb_operator_t A, sigb_operator_t B,
+                               sigb_operator_t *C);
+/* C = A * B: multiply_operators
+ * (src/linear_operator/linear_operator_products.f90:39-73); the scratch vectors
+ * z1, z2 of temp_vec_size doubles (:60-61) live on the device;
+ * matvec_add: last factor first, y = y + z2 (:78-114); matvec_t_add: first
+ * factor first, transposed (:119-150). */
+SIGB_API int sigb_operator_product(sigb_operator_t A, sigb_operator_t B,
+                                   sigb_operator_t *C);
+/* B = adjoint(A) (src/linear_operator/linear_operator_adjoints.f90:28-44):
+ * matvec_add <-> matvec_t_add of A (:62-86). */
+SIGB_API int sigb_operator_adjoint(sigb_operator_t A, sigb_operator_t *B);
+/* type(sparse_matrix) as a composite of num_row_mats x num_col_mats blocks
+ * (src/matrix/sparse_matrix_composites.f90:41-49): set_block_sizes(rows, cols)
+ * (:226-262) + set_submatrix(it, jt, blocks[(it-1)*num_col_mats + (jt-1)])
+ * (:1031-1065).  Every block must be given and match its slot's dimensions
+ * ("Inconsistent dimensions for sub-matrix").  matvec_add is the block-row
+ * loop of composite_matvec_add (:1076-1100), matvec_t_add the block-column
+ * loop (:1105-1129), on offset slices of the device vectors. */
+SIGB_API int sigb_composite_create(int32_t num_row_mats, int32_t num_col_mats,
+                                   const int32_t *rows, const int32_t *cols,
+                                   const sigb_operator_t *blocks,
+                                   sigb_operator_t *A);
+/* add_reference (linear_operator_interface.f90:285-291); undone by
+ * sigb_matrix_destroy, which frees the mirror when the count reaches zero. */
+SIGB_API int sigb_matrix_retain(sigb_operator_t A);
+
 /* ---- solvers ----------------------------------------------------------- */
 
 /* cg(tolerance) (src/solver/cg_solvers.f90:36-47); tolerance < 0 selects the

@@ -16,12 +16,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libsigma_oracle.so")
 
 CSR, CSC, ELL = 1, 2, 3
+SUM, PRODUCT, ADJOINT, COMPOSITE = 4, 5, 6, 7
 
 __all__ = [
     "CSR", "CSC", "ELL", "build", "lib", "Matrix", "ll_graph_edges", "cs_graph_build",
     "ellpack_graph_build", "matvec", "matvec_add", "jacobi_setup", "jacobi_solve",
     "cg_solve", "bicgstab_solve", "lanczos", "generalized_lanczos", "eigensolve", "tridiag_eig",
     "partition_rows", "halo_build", "cs_set_value", "ell_set_value",
+    "SUM", "PRODUCT", "ADJOINT", "COMPOSITE", "operator_sum", "operator_product", "adjoint",
+    "composite", "get_value",
 ]
 
 
@@ -37,6 +40,11 @@ class _OrcMatrix(C.Structure):
     _fields_ = [
         ("format", C.c_int32), ("nrow", C.c_int32), ("ncol", C.c_int32), ("max_d", C.c_int32),
         ("ptr", C.c_void_p), ("node", C.c_void_p), ("degrees", C.c_void_p), ("val", C.c_void_p),
+        # operator expressions (orc_matrix in sigma_oracle.c)
+        ("nkids", C.c_int32), ("num_row_mats", C.c_int32), ("num_col_mats", C.c_int32),
+        ("temp_vec_size", C.c_int32),
+        ("kids", C.c_void_p), ("row_ptr", C.c_void_p), ("col_ptr", C.c_void_p),
+        ("z1", C.c_void_p), ("z2", C.c_void_p),
     ]
 
 
@@ -63,6 +71,7 @@ def lib():
         "orc_ell_get_value": (f64, [i32, _i32p, _i32p, _f64p, i32, i32]),
         "orc_matvec_add": (None, [mp, i32, _f64p, _f64p]),
         "orc_matvec": (None, [mp, i32, _f64p, _f64p]),
+        "orc_get_value": (f64, [mp, i32, i32]),
         "orc_jacobi_setup": (None, [mp, _f64p]),
         "orc_jacobi_solve": (None, [i32, _f64p, _f64p, _f64p]),
         "orc_cg_solve": (i64, [mp, _f64p, _f64p, f64, i64, _f64p, C.POINTER(f64), C.POINTER(i32)]),
@@ -117,6 +126,79 @@ class Matrix:
     @property
     def c(self):
         return C.byref(self._c)
+
+
+class Operator:
+    """An operator expression over host matrices: operator_sum, operator_product,
+    operator_adjoint (src/linear_operator/linear_operator_{sums,products,adjoints}.f90)
+    or a block composite sparse_matrix (src/matrix/sparse_matrix_composites.f90).
+    Usable wherever a Matrix is (matvec, get_value, jacobi_setup, the solvers)."""
+
+    def __init__(self, fmt, nrow, ncol, kids, row_ptr=None, col_ptr=None):
+        self.format, self.nrow, self.ncol = fmt, int(nrow), int(ncol)
+        self.kids = list(kids)
+        self._kid_arr = (C.c_void_p * len(self.kids))(*[C.addressof(k._c) for k in self.kids])
+        self.row_ptr = _i32(row_ptr) if row_ptr is not None else None
+        self.col_ptr = _i32(col_ptr) if col_ptr is not None else None
+        tvs = 0
+        self._z1 = self._z2 = None
+        if fmt == PRODUCT:
+            tvs = max(max(k.nrow, k.ncol) for k in self.kids)
+            self._z1, self._z2 = np.zeros(tvs), np.zeros(tvs)
+        self._c = _OrcMatrix(
+            fmt, self.nrow, self.ncol, 0, None, None, None, None,
+            len(self.kids),
+            (self.row_ptr.size - 1) if self.row_ptr is not None else 0,
+            (self.col_ptr.size - 1) if self.col_ptr is not None else 0,
+            tvs,
+            C.cast(self._kid_arr, C.c_void_p),
+            self.row_ptr.ctypes.data if self.row_ptr is not None else None,
+            self.col_ptr.ctypes.data if self.col_ptr is not None else None,
+            self._z1.ctypes.data if self._z1 is not None else None,
+            self._z2.ctypes.data if self._z2 is not None else None,
+        )
+
+    @property
+    def c(self):
+        return C.byref(self._c)
+
+
+def operator_sum(A, B):
+    """add_operators, linear_operator_sums.f90:38-72."""
+    if A.nrow != B.nrow or A.ncol != B.ncol:
+        raise ValueError("Dimensions of operators to be summed are not consistent")
+    return Operator(SUM, A.nrow, A.ncol, [A, B])
+
+
+def operator_product(A, B):
+    """multiply_operators, linear_operator_products.f90:39-73."""
+    if A.ncol != B.nrow:
+        raise ValueError("Dimensions of operators to be multiplied are inconsistent")
+    return Operator(PRODUCT, A.nrow, B.ncol, [A, B])
+
+
+def adjoint(A):
+    """adjoint, linear_operator_adjoints.f90:28-44."""
+    return Operator(ADJOINT, A.ncol, A.nrow, [A])
+
+
+def composite(rows, cols, blocks):
+    """sparse_matrix with set_block_sizes(rows, cols) (sparse_matrix_composites.f90:226-262)
+    and set_submatrix(it, jt, blocks[it][jt]) (:1031-1065)."""
+    row_ptr = np.concatenate([[1], 1 + np.cumsum(rows)]).astype(np.int32)
+    col_ptr = np.concatenate([[1], 1 + np.cumsum(cols)]).astype(np.int32)
+    kids = [blocks[it][jt] for it in range(len(rows)) for jt in range(len(cols))]
+    for it in range(len(rows)):
+        for jt in range(len(cols)):
+            b = blocks[it][jt]
+            if b.nrow != rows[it] or b.ncol != cols[jt]:
+                raise ValueError("Inconsistent dimensions for sub-matrix")
+    return Operator(COMPOSITE, int(sum(rows)), int(sum(cols)), kids, row_ptr, col_ptr)
+
+
+def get_value(A, i, j):
+    """orc_get_value: A%get_value(i, j), 1-based."""
+    return float(lib().orc_get_value(A.c, int(i), int(j)))
 
 
 def ll_graph_edges(n, ei, ej):

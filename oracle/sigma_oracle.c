@@ -334,27 +334,55 @@ ORC_API void orc_ellpack_matvec_t_add(int32_t n, int32_t max_d,
 /* linear_operator dispatch                                                  */
 /* ------------------------------------------------------------------------ */
 
-enum { ORC_CSR = 1, ORC_CSC = 2, ORC_ELL = 3 };
+/* Leaf formats, then the operator expressions of
+ * src/linear_operator/linear_operator_{sums,products,adjoints}.f90 and the
+ * block composite of src/matrix/sparse_matrix_composites.f90. */
+enum { ORC_CSR = 1, ORC_CSC = 2, ORC_ELL = 3,
+       ORC_SUM = 4, ORC_PRODUCT = 5, ORC_ADJOINT = 6, ORC_COMPOSITE = 7 };
 
-typedef struct {
-    int32_t format;        /* ORC_CSR / ORC_CSC / ORC_ELL                    */
+typedef struct orc_matrix_s {
+    int32_t format;        /* ORC_CSR ... ORC_COMPOSITE                      */
     int32_t nrow, ncol;
     int32_t max_d;         /* ELL width                                      */
     const int32_t *ptr;    /* cs: n+1 (n = nrow for CSR, ncol for CSC)       */
     const int32_t *node;   /* cs: ne ; ell: max_d*nrow column-major          */
     const int32_t *degrees;/* ell only: degrees(nrow)                        */
     const double *val;
+    /* ---- operator expressions (unused by the leaf formats) -------------- */
+    int32_t nkids;         /* num_summands / num_products / 1 / #blocks      */
+    int32_t num_row_mats, num_col_mats;   /* composite                      */
+    int32_t temp_vec_size; /* product: maxval([A%nrow,A%ncol,B%nrow,B%ncol]) */
+    const struct orc_matrix_s *const *kids;
+                           /* sum: summands(:) ; product: products(:) ;
+                              adjoint: op ; composite: sub_mats(it, jt) at
+                              [(it-1)*num_col_mats + (jt-1)]                 */
+    const int32_t *row_ptr;/* composite: row_ptr(num_row_mats+1), 1-based    */
+    const int32_t *col_ptr;/* composite: col_ptr(num_col_mats+1), 1-based    */
+    double *z1, *z2;       /* product scratch, temp_vec_size doubles each    */
 } orc_matrix;
 
 static void zero(double *y, int32_t n) { int32_t i; for (i = 0; i < n; i++) y[i] = 0.0; }
 
-/* matvec_add / matvec_t_add dispatch: cs_matvec_add / cs_matvec_t_add,
+ORC_API void orc_matvec(const orc_matrix *A, int32_t trans, const double *x,
+                        double *y);
+
+/* matvec_add / matvec_t_add dispatch.
+ * Leaves: cs_matvec_add / cs_matvec_t_add,
  * src/matrix/formats/cs_matrices.f90:500-521 with the slot bindings at
  * :148-149 (CSR) and :192-193 (CSC); ellpack binds directly
- * (src/matrix/formats/ellpack_matrices.f90:78-79). */
+ * (src/matrix/formats/ellpack_matrices.f90:78-79).
+ * Expressions: operator_sum_matvec_add / _t_add
+ * (src/linear_operator/linear_operator_sums.f90:100-131),
+ * operator_product_matvec_add / _t_add
+ * (src/linear_operator/linear_operator_products.f90:78-150),
+ * operator_adjoint_matvec_add / _t_add
+ * (src/linear_operator/linear_operator_adjoints.f90:62-86),
+ * composite_matvec_add / _t_add
+ * (src/matrix/sparse_matrix_composites.f90:1076-1129). */
 ORC_API void orc_matvec_add(const orc_matrix *A, int32_t trans,
                             const double *x, double *y)
 {
+    int32_t i, k, it, jt;
     switch (A->format) {
     case ORC_CSR:
         if (!trans) orc_csr_matvec_add(A->nrow, A->ptr, A->node, A->val, x, y);
@@ -364,9 +392,70 @@ ORC_API void orc_matvec_add(const orc_matrix *A, int32_t trans,
         if (!trans) orc_csc_matvec_add(A->ncol, A->ptr, A->node, A->val, x, y);
         else        orc_csr_matvec_add(A->ncol, A->ptr, A->node, A->val, x, y);
         break;
-    default:
+    case ORC_ELL:
         if (!trans) orc_ellpack_matvec_add(A->nrow, A->max_d, A->node, A->val, x, y);
         else        orc_ellpack_matvec_t_add(A->nrow, A->max_d, A->node, A->val, x, y);
+        break;
+    case ORC_SUM:
+        /* do k = 1, num_summands: call summands(k)%ap%matvec_add(x, y)  :108-110 */
+        for (k = 0; k < A->nkids; k++) orc_matvec_add(A->kids[k], trans, x, y);
+        break;
+    case ORC_ADJOINT:
+        /* call A%op%matvec_t_add(x, y) / matvec_add(x, y)   :69, :82 */
+        orc_matvec_add(A->kids[0], !trans, x, y);
+        break;
+    case ORC_PRODUCT: {
+        double *z1 = A->z1, *z2 = A->z2;
+        /* z1(1:A%ncol) = x(1:A%ncol) ; z2(:) = 0   :93-94 / :128-129.  (The
+         * transposed form copies A%ncol entries of an x that has A%nrow of
+         * them -- the same thing for the square operators the reference
+         * tests; the input length is used here.) */
+        const int32_t nin = trans ? A->nrow : A->ncol;
+        const int32_t nout = trans ? A->ncol : A->nrow;
+        for (i = 0; i < nin; i++) z1[i] = x[i];
+        zero(z2, A->temp_vec_size);
+        if (!trans) {
+            /* last factor first  :97-108 */
+            for (k = A->nkids - 1; k >= 0; k--) {
+                const orc_matrix *P = A->kids[k];
+                zero(z2, A->temp_vec_size);          /* matvec zeroes all of z2 (:187 of the interface) */
+                orc_matvec_add(P, 0, z1, z2);
+                for (i = 0; i < P->nrow; i++) z1[i] = z2[i];
+            }
+        } else {
+            /* first factor first, transposed  :132-143 */
+            for (k = 0; k < A->nkids; k++) {
+                const orc_matrix *P = A->kids[k];
+                zero(z2, A->temp_vec_size);
+                orc_matvec_add(P, 1, z1, z2);
+                for (i = 0; i < P->ncol; i++) z1[i] = z2[i];
+            }
+        }
+        for (i = 0; i < nout; i++) y[i] = y[i] + z2[i];   /* y = y + z2  :109 / :146 */
+        zero(z1, A->temp_vec_size);                       /* :111-112 */
+        zero(z2, A->temp_vec_size);
+        break;
+    }
+    default: /* ORC_COMPOSITE */
+        if (!trans) {
+            for (it = 1; it <= A->num_row_mats; it++) {              /* :1086 */
+                const int32_t i1 = A->row_ptr[it - 1];
+                for (jt = 1; jt <= A->num_col_mats; jt++) {          /* :1090 */
+                    const int32_t j1 = A->col_ptr[jt - 1];
+                    const orc_matrix *Cm = A->kids[(it - 1) * A->num_col_mats + (jt - 1)];
+                    orc_matvec_add(Cm, 0, x + (j1 - 1), y + (i1 - 1));   /* :1096 */
+                }
+            }
+        } else {
+            for (jt = 1; jt <= A->num_col_mats; jt++) {              /* :1115 */
+                const int32_t j1 = A->col_ptr[jt - 1];
+                for (it = 1; it <= A->num_row_mats; it++) {          /* :1119 */
+                    const int32_t i1 = A->row_ptr[it - 1];
+                    const orc_matrix *Cm = A->kids[(it - 1) * A->num_col_mats + (jt - 1)];
+                    orc_matvec_add(Cm, 1, x + (i1 - 1), y + (j1 - 1));   /* :1125 */
+                }
+            }
+        }
     }
 }
 
@@ -378,6 +467,49 @@ ORC_API void orc_matvec(const orc_matrix *A, int32_t trans, const double *x,
 {
     zero(y, trans ? A->ncol : A->nrow);
     orc_matvec_add(A, trans, x, y);
+}
+
+/* A%get_value(i, j) for any operator.
+ * csr_matrix_get_value cs_matrices.f90:709-724, csc_matrix_get_value :729-744
+ * (scans column j for row i), ellpack_matrix_get_value
+ * ellpack_matrices.f90:220-237, operator_sum_get_value
+ * linear_operator_sums.f90:79-95, operator_adjoint_get_value
+ * linear_operator_adjoints.f90:49-57, composite_mat_get_value
+ * sparse_matrix_composites.f90:465-485 with get_owning_row/column_matrix
+ * :1235-1262.  operator_product has no override: the default
+ * linear_operator_get_value (linear_operator_interface.f90:168-181) multiplies
+ * a vector that is uninitialised except for x(j) = 1 -- restated here with the
+ * unit vector it evidently intends. */
+ORC_API double orc_get_value(const orc_matrix *A, int32_t i, int32_t j)
+{
+    double z = 0.0;
+    int32_t k, it, jt;
+    switch (A->format) {
+    case ORC_CSR: return orc_cs_get_value(A->ptr, A->node, A->val, i, j);
+    case ORC_CSC: return orc_cs_get_value(A->ptr, A->node, A->val, j, i);
+    case ORC_ELL: return orc_ell_get_value(A->max_d, A->node, A->degrees, A->val, i, j);
+    case ORC_SUM:
+        for (k = 0; k < A->nkids; k++) z = z + orc_get_value(A->kids[k], i, j);
+        return z;
+    case ORC_ADJOINT: return orc_get_value(A->kids[0], j, i);
+    case ORC_COMPOSITE:
+        for (it = 1; it <= A->num_row_mats; it++)
+            if (A->row_ptr[it - 1] <= i && A->row_ptr[it] > i) break;
+        for (jt = 1; jt <= A->num_col_mats; jt++)
+            if (A->col_ptr[jt - 1] <= j && A->col_ptr[jt] > j) break;
+        return orc_get_value(A->kids[(it - 1) * A->num_col_mats + (jt - 1)],
+                             i - A->row_ptr[it - 1] + 1, j - A->col_ptr[jt - 1] + 1);
+    default: {
+        double *x = calloc((size_t)A->ncol, sizeof(double));
+        double *y = calloc((size_t)A->nrow, sizeof(double));
+        x[j - 1] = 1.0;
+        orc_matvec(A, 0, x, y);
+        z = y[i - 1];
+        free(x);
+        free(y);
+        return z;
+    }
+    }
 }
 
 /* dot_product(a, b) / sum(a * b) as a non-fast-math gfortran evaluates them:
@@ -399,18 +531,7 @@ static double dot(const double *a, const double *b, int32_t n)
 ORC_API void orc_jacobi_setup(const orc_matrix *A, double *idiag)
 {
     int32_t i;
-    for (i = 1; i <= A->nrow; i++) {
-        double z = 0.0;
-        if (A->format == ORC_ELL) {
-            /* ellpack_matrix_get_value ellpack_matrices.f90:220-237 */
-            z = orc_ell_get_value(A->max_d, A->node, A->degrees, A->val, i, i);
-        } else {
-            /* csr_matrix_get_value cs_matrices.f90:709-724 /
-             * csc_matrix_get_value :729-744 both scan line i for index i */
-            z = orc_cs_get_value(A->ptr, A->node, A->val, i, i);
-        }
-        idiag[i - 1] = 1.0 / z;
-    }
+    for (i = 1; i <= A->nrow; i++) idiag[i - 1] = 1.0 / orc_get_value(A, i, i);
 }
 
 /* jacobi_solve, src/solver/jacobi_solvers.f90:68-81: x = idiag * b */

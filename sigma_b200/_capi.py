@@ -60,6 +60,11 @@ PROTOTYPES = {
     "sigb_matvec_add": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "sigb_matvec_dev": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int]),
     "sigb_matvec_dot_dev": (C.c_int, [_vp, _vp, _vp, _pf64]),
+    "sigb_operator_sum": (C.c_int, [_vp, _vp, _pvp]),
+    "sigb_operator_product": (C.c_int, [_vp, _vp, _pvp]),
+    "sigb_operator_adjoint": (C.c_int, [_vp, _pvp]),
+    "sigb_composite_create": (C.c_int, [_i32, _i32, _vp, _vp, _pvp, _pvp]),
+    "sigb_matrix_retain": (C.c_int, [_vp]),
     "sigb_cg_create": (C.c_int, [_f64, _pvp]),
     "sigb_bicgstab_create": (C.c_int, [_f64, _pvp]),
     "sigb_jacobi_create": (C.c_int, [_pvp]),

@@ -12,9 +12,14 @@ reference's own test programs:
     pc => jacobi(); call pc%setup(A)                 pc = jacobi(); pc.setup(A)
     call lanczos(A, T, Q)                            T, Q = lanczos(A, n, q1)
     call eigensolve(A, lambda, V)                    lam, V = eigensolve(A, n, q1)
+    L = A + B ; L = A * B ; L = adjoint(A)           L = A + B ; L = A * B ; L = adjoint(A)
+    type(sparse_matrix): set_block_sizes(rows, cols) S = sparse_matrix(rows, cols, blocks)
+      + set_submatrix(it, jt, C)
 
 (linear_operator_interface.f90:185-233, cg_solvers.f90:36-194,
-bicgstab_solvers.f90:36-237, jacobi_solvers.f90:26-81, eigensolver.f90:27-184.)
+bicgstab_solvers.f90:36-237, jacobi_solvers.f90:26-81, eigensolver.f90:27-184,
+linear_operator_sums.f90:38-72, linear_operator_products.f90:39-73,
+linear_operator_adjoints.f90:28-44, sparse_matrix_composites.f90:226-262,1031-1129.)
 Errors raise SigmaError where the reference prints and calls exit(1).
 """
 from __future__ import annotations
@@ -29,7 +34,7 @@ from ._capi import ROW, COL, SigmaError, as_f64, as_i32, check, lib, ptr
 __all__ = ["init", "Graph", "Matrix", "Solver", "cg", "bicgstab", "jacobi", "lanczos", "eigensolve",
            "generalized_lanczos", "generalized_eigensolve",
            "csr_matrix", "csc_matrix", "ellpack_matrix", "SigmaError", "launch_count", "set_stream",
-           "synchronize"]
+           "synchronize", "Expression", "operator_sum", "operator_product", "adjoint", "sparse_matrix"]
 
 
 def init(device: int = -1):
@@ -94,7 +99,7 @@ class Graph:
 class Matrix:
     """Device mirror of csr_matrix / csc_matrix / ellpack_matrix (a linear_operator)."""
 
-    def __init__(self, graph: Graph, handle=None):
+    def __init__(self, graph: "Graph | None", handle=None):
         self.g = graph
         if handle is None:
             handle = C.c_void_p()
@@ -149,6 +154,13 @@ class Matrix:
             return self.g.n * self.g.max_d
         return self.nnz
 
+    # -- operator algebra: interface operator(+) / operator(*) ----------------
+    def __add__(self, other):
+        return operator_sum(self, other)
+
+    def __mul__(self, other):
+        return operator_product(self, other)
+
     def destroy(self):
         if self._h:
             check(lib().sigb_matrix_destroy(self._h))
@@ -159,6 +171,52 @@ class Matrix:
             self.destroy()
         except Exception:
             pass
+
+
+class Expression(Matrix):
+    """A lazy operator expression (operator_sum / operator_product / operator_adjoint) or a
+    block composite sparse_matrix.  It is a linear_operator like any matrix: matvec, the
+    solvers and the Lanczos loops take it unchanged; the device library holds references on
+    its operands."""
+
+    def __init__(self, handle, kind, operands):
+        super().__init__(None, handle)
+        self.kind, self.operands = kind, list(operands)
+
+    def set_values(self, val):
+        raise SigmaError(_capi.ERR_UNSUPPORTED, "an operator expression has no values of its own")
+
+
+def operator_sum(A: Matrix, B: Matrix) -> Expression:
+    """L = A + B (add_operators, linear_operator_sums.f90:38-72)."""
+    h = C.c_void_p()
+    check(lib().sigb_operator_sum(A._h, B._h, C.byref(h)))
+    return Expression(h, "sum", [A, B])
+
+
+def operator_product(A: Matrix, B: Matrix) -> Expression:
+    """L = A * B (multiply_operators, linear_operator_products.f90:39-73)."""
+    h = C.c_void_p()
+    check(lib().sigb_operator_product(A._h, B._h, C.byref(h)))
+    return Expression(h, "product", [A, B])
+
+
+def adjoint(A: Matrix) -> Expression:
+    """L = adjoint(A) (linear_operator_adjoints.f90:28-44)."""
+    h = C.c_void_p()
+    check(lib().sigb_operator_adjoint(A._h, C.byref(h)))
+    return Expression(h, "adjoint", [A])
+
+
+def sparse_matrix(rows, cols, blocks) -> Expression:
+    """type(sparse_matrix) composite: A%set_block_sizes(rows, cols) then
+    A%set_submatrix(it, jt, blocks[it][jt]) (sparse_matrix_composites.f90:226-262,1031-1065)."""
+    rows, cols = as_i32(rows), as_i32(cols)
+    flat = [blocks[it][jt] for it in range(rows.size) for jt in range(cols.size)]
+    arr = (C.c_void_p * len(flat))(*[b._h for b in flat])
+    h = C.c_void_p()
+    check(lib().sigb_composite_create(rows.size, cols.size, ptr(rows), ptr(cols), arr, C.byref(h)))
+    return Expression(h, "composite", flat)
 
 
 def csr_matrix(n, m, ptr1, node1, val):

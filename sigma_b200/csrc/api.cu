@@ -126,6 +126,7 @@ int ensure_transposed(sigb_matrix_t A)
 int matvec_dev(sigb_matrix_t A, int trans, const double *x, double *y, SpmvMode, bool add,
                const DotSpec &dot)
 {
+    if (A->op) return op_matvec(A, trans, x, y, add, dot);
     sigb_graph_t g = A->g;
     if (A->dist) {
         SIGB_REQUIRE(!trans, SIGB_ERR_UNSUPPORTED, "matvec_t on a row-sharded operator");
@@ -419,6 +420,7 @@ int sigb_matrix_create(sigb_graph_t g, sigb_matrix_t *out)
 int sigb_matrix_set_values(sigb_matrix_t A, const double *val, int64_t count)
 {
     SIGB_REQUIRE(A && val, SIGB_ERR_ARG, "sigb_matrix_set_values: bad argument");
+    SIGB_REQUIRE(!A->op, SIGB_ERR_UNSUPPORTED, "sigb_matrix_set_values: an operator expression has no values of its own");
     sigb_graph_t g = A->g;
     cudaStream_t st = ctx().stream;
     if (g->kind == G_ELL) {
@@ -446,10 +448,14 @@ int sigb_matrix_set_values(sigb_matrix_t A, const double *val, int64_t count)
 int sigb_matrix_destroy(sigb_matrix_t A)
 {
     if (!A) return SIGB_OK;
+    // remove_reference; the mirror goes away with its last owner (an expression
+    // that still points at this operator keeps it alive)
+    if (--A->refcount > 0) return SIGB_OK;
     cudaFree(A->val);
     cudaFree(A->val_t);
     if (A->dist) dist_destroy(A);
-    sigb_graph_release(A->g);
+    if (A->op) op_destroy(A);
+    if (A->g) sigb_graph_release(A->g);
     delete A;
     return SIGB_OK;
 }
@@ -459,13 +465,29 @@ int sigb_matrix_get_dims(sigb_matrix_t A, int32_t *nrow, int32_t *ncol, int64_t 
     SIGB_REQUIRE(A, SIGB_ERR_ARG, "sigb_matrix_get_dims: null matrix");
     if (nrow) *nrow = A->nrow;
     if (ncol) *ncol = A->ncol;
-    if (nnz) *nnz = A->g->ne;
+    if (nnz) {
+        // composite_mat_get_nnz sums its blocks (sparse_matrix_composites.f90:445-460);
+        // the lazy expressions hold no entries of their own
+        int64_t total = 0;
+        if (A->op) {
+            if (A->op->kind == OP_COMPOSITE)
+                for (sigb_matrix_t k : A->op->kids) {
+                    int64_t sub = 0;
+                    SIGB_CHECK(sigb_matrix_get_dims(k, nullptr, nullptr, &sub));
+                    total += sub;
+                }
+        } else {
+            total = A->g->ne;
+        }
+        *nnz = total;
+    }
     return SIGB_OK;
 }
 
 int sigb_matrix_get_transpose_values(sigb_matrix_t A, double *val_t)
 {
     SIGB_REQUIRE(A && val_t, SIGB_ERR_ARG, "sigb_matrix_get_transpose_values: bad argument");
+    SIGB_REQUIRE(!A->op, SIGB_ERR_UNSUPPORTED, "sigb_matrix_get_transpose_values: not a stored matrix");
     SIGB_CHECK(ensure_transposed(A));
     SIGB_CUDA(cudaStreamSynchronize(ctx().stream));
     if (A->g->transposed.nnz > 0)

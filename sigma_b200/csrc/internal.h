@@ -118,6 +118,20 @@ enum GraphKind { G_CSR = 0, G_CSC = 1, G_ELL = 2 };
 
 struct DistInfo;  // comm.cu
 
+// An operator expression over other operators (operators.cu): operator_sum,
+// operator_product, operator_adjoint (src/linear_operator/linear_operator_
+// {sums,products,adjoints}.f90) or the block composite sparse_matrix
+// (src/matrix/sparse_matrix_composites.f90:41-49).
+enum OpKind { OP_SUM = 1, OP_PRODUCT = 2, OP_ADJOINT = 3, OP_COMPOSITE = 4 };
+struct OpInfo {
+    int kind = 0;
+    std::vector<sigb_matrix_s *> kids;       // summands / products / op / sub_mats(it, jt) row-major
+    int32_t num_row_mats = 0, num_col_mats = 0;
+    std::vector<int32_t> row_ptr, col_ptr;   // composite block offsets, 1-based like the reference
+    int64_t temp_vec_size = 0;               // operator_product%temp_vec_size
+    double *z1 = nullptr, *z2 = nullptr;     // operator_product%z1, z2 (device)
+};
+
 }  // namespace sigb
 
 struct sigb_graph_s {
@@ -139,12 +153,14 @@ struct sigb_graph_s {
 };
 
 struct sigb_matrix_s {
-    sigb_graph_t g = nullptr;
+    int refcount = 1;           // linear_operator%reference_count (linear_operator_interface.f90:285-302)
+    sigb_graph_t g = nullptr;   // null for operator expressions
     double *val = nullptr;      // cs: ne (+pad) in stored order; ell: slot-major [max_d][n_pad]
     double *val_t = nullptr;    // values in transposed order (cs: perm gather; ell: from slots)
     bool val_t_valid = false;
     int32_t nrow = 0, ncol = 0;
     sigb::DistInfo *dist = nullptr;  // non-null for row-sharded operators
+    sigb::OpInfo *op = nullptr;      // non-null for operator expressions (no graph, no values of their own)
 };
 
 namespace sigb {
@@ -229,5 +245,12 @@ int ensure_transposed(sigb_matrix_t A);
 // y = op(A) x with device vectors; the single entry every solver goes through
 int matvec_dev(sigb_matrix_t A, int trans, const double *x, double *y,
                SpmvMode mode_csr_like, bool add, const DotSpec &dot);
+
+// ---------------------------------------------------------------------------
+// operators.cu: operator expressions
+// ---------------------------------------------------------------------------
+int op_matvec(sigb_matrix_t A, int trans, const double *x, double *y, bool add_to_y, const DotSpec &dot);
+int op_jacobi_setup(sigb_matrix_t A, double *idiag);
+void op_destroy(sigb_matrix_t A);
 
 }  // namespace sigb

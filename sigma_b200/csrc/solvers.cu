@@ -590,6 +590,7 @@ static int push_state(sigb_solver_t s)
 
 int jacobi_setup_dev(sigb_solver_t s, sigb_matrix_t A)
 {
+    if (A->op) return op_jacobi_setup(A, s->work);
     sigb_graph_t g = A->g;
     const int32_t n = A->nrow;
     cudaStream_t st = ctx().stream;
@@ -736,7 +737,7 @@ static int cg_solve_body(sigb_solver_t s, sigb_matrix_t A, double *x, const doub
         bool eligible = true;
         SIGB_CHECK(dist_persist_info(A, &pcomm, &halo, &eligible));
         eligible = eligible && persistent_enabled(n, pcomm.nranks);
-        if (eligible) {
+        if (eligible && !A->op) {   // operator expressions run kernel-per-phase
             sigb_graph_t g = A->g;
             if (g->kind == G_CSR) {
                 V = &g->stored;

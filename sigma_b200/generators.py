@@ -231,6 +231,53 @@ def erdos_renyi_csr(n, p=None, seed=7, shift=1.0, skew=False, weights="unit", re
 
 
 # --------------------------------------------------------------------------
+# Two-field block system of test/matrix_test_composite.f90:104-219
+# --------------------------------------------------------------------------
+def _er_laplacian_blocks(n, p, rng):
+    """erdos_renyi_graph(g, n, n, p, symmetric=.true.) (:560-590) followed by
+    erdos_renyi_matrix (:595-620): every vertex carries its self-edge; for each
+    stored edge (i, j): A(i,j) += -1, A(i,i) += +1.  Rows come out ascending
+    (smaller neighbours, the diagonal, larger neighbours)."""
+    upper = np.triu(rng.random((n, n)) < p, k=1)
+    adj = upper | upper.T | np.eye(n, dtype=bool)
+    rows, cols = np.nonzero(adj)                       # row-major => ascending columns
+    deg = adj.sum(axis=1)
+    val = np.where(rows == cols, deg[rows] - 1.0, -1.0)
+    ptr = np.concatenate([[1], 1 + np.cumsum(deg)]).astype(np.int32)
+    return ptr, (cols + 1).astype(np.int32), val.astype(np.float64), adj
+
+
+def composite_er_blocks(nn1=768, nn2=512, seed=11):
+    """The 2 x 2 block matrix of test/matrix_test_composite.f90: random weighted
+    Laplacians on the diagonal (CSR), the coupling graph h (nn1 x nn2, p = 6/nn1,
+    only j > i, :171-174) as the CSR (1,2) block and -- the SAME graph object --
+    as the CSC (2,1) block, coupling values -1 and +1 on both diagonals per
+    coupling edge (:204-217).
+
+    Returns dict(b11=(ptr, node, val), b22=(...), h=(ptr, node), v12, v21,
+    adj1, adj2, adjh) with 1-based int32 index arrays."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    p1 = np.log2(nn1) / nn1
+    p2 = np.log2(nn2) / nn2
+    ptr1, node1, val1, adj1 = _er_laplacian_blocks(nn1, p1, rng)
+    ptr2, node2, val2, adj2 = _er_laplacian_blocks(nn2, p2, rng)
+    adjh = rng.random((nn1, nn2)) < 6.0 / nn1
+    adjh &= np.arange(nn2)[None, :] > np.arange(nn1)[:, None]
+    hr, hc = np.nonzero(adjh)
+    hdeg, htdeg = adjh.sum(axis=1), adjh.sum(axis=0)
+    ptrh = np.concatenate([[1], 1 + np.cumsum(hdeg)]).astype(np.int32)
+    nodeh = (hc + 1).astype(np.int32)
+    # A%add(1, 1, i, i, +1) and A%add(2, 2, j, j, +1) once per coupling edge
+    r1 = np.repeat(np.arange(nn1), np.diff(ptr1))
+    val1 = val1 + np.where(r1 == node1 - 1, hdeg[r1].astype(np.float64), 0.0)
+    r2 = np.repeat(np.arange(nn2), np.diff(ptr2))
+    val2 = val2 + np.where(r2 == node2 - 1, htdeg[r2].astype(np.float64), 0.0)
+    ne_h = nodeh.size
+    return dict(b11=(ptr1, node1, val1), b22=(ptr2, node2, val2), h=(ptrh, nodeh),
+                v12=np.full(ne_h, -1.0), v21=np.full(ne_h, -1.0), adj1=adj1, adj2=adj2, adjh=adjh)
+
+
+# --------------------------------------------------------------------------
 # P1 finite-element Laplacian on a perturbed structured triangulation
 # (BASELINE config 4; element matrices per examples/fem.f90:28-49)
 # --------------------------------------------------------------------------
