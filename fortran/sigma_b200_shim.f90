@@ -193,6 +193,56 @@ interface                                                                  !
         integer(c_int) :: stat
     end function
 
+    function sigb_generalized_lanczos(A, B, b_solver, b_pc, n, q1, seed, T, Q) &
+            & bind(c, name='sigb_generalized_lanczos') result(stat)
+        import :: c_int, c_int32_t, c_int64_t, c_double, c_ptr
+        type(c_ptr), value :: A, B, b_solver, b_pc   ! b_pc = c_null_ptr: none attached
+        integer(c_int32_t), value :: n
+        type(c_ptr), value :: q1
+        integer(c_int64_t), value :: seed
+        real(c_double), intent(out) :: T(3, *), Q(*)
+        integer(c_int) :: stat
+    end function
+
+    ! operator expressions: every constructor returns another operator handle
+    ! that sigb_matvec*, sigb_solver_* and sigb_lanczos* accept unchanged
+    function sigb_operator_sum(A, B, C) bind(c, name='sigb_operator_sum') result(stat)
+        import :: c_int, c_ptr
+        type(c_ptr), value :: A, B
+        type(c_ptr), intent(out) :: C
+        integer(c_int) :: stat
+    end function
+
+    function sigb_operator_product(A, B, C) bind(c, name='sigb_operator_product') result(stat)
+        import :: c_int, c_ptr
+        type(c_ptr), value :: A, B
+        type(c_ptr), intent(out) :: C
+        integer(c_int) :: stat
+    end function
+
+    function sigb_operator_adjoint(A, B) bind(c, name='sigb_operator_adjoint') result(stat)
+        import :: c_int, c_ptr
+        type(c_ptr), value :: A
+        type(c_ptr), intent(out) :: B
+        integer(c_int) :: stat
+    end function
+
+    function sigb_composite_create(num_row_mats, num_col_mats, rows, cols, blocks, A) &
+            & bind(c, name='sigb_composite_create') result(stat)
+        import :: c_int, c_int32_t, c_ptr
+        integer(c_int32_t), value :: num_row_mats, num_col_mats
+        integer(c_int32_t), intent(in) :: rows(*), cols(*)
+        type(c_ptr), intent(in) :: blocks(*)     ! sub_mats(it, jt) at (it-1)*num_col_mats + jt
+        type(c_ptr), intent(out) :: A
+        integer(c_int) :: stat
+    end function
+
+    function sigb_matrix_retain(A) bind(c, name='sigb_matrix_retain') result(stat)
+        import :: c_int, c_ptr
+        type(c_ptr), value :: A
+        integer(c_int) :: stat
+    end function
+
     function c_strlen(s) bind(c, name='strlen') result(n)
         import :: c_ptr, c_size_t
         type(c_ptr), value :: s
@@ -334,3 +384,65 @@ end module sigma_b200_shim
 !     end subroutine
 !     (the library normalises the start vector as :52 does; passing
 !      c_null_ptr instead lets it draw the vector from `seed`.)
+!
+! --- src/linear_operator/linear_operator_interface.f90, type linear_operator
+!     (:18-45) gains a deferred-with-default accessor every operator answers:
+!         procedure :: device_handle => linear_operator_no_mirror   ! c_null_ptr
+!     cs_matrix / ellpack_matrix override it with `call A%sync_mirror();
+!     h = A%mirror`.  The solvers' `select type(A)` above then becomes
+!         h = A%device_handle()
+!         if (c_associated(h)) then ; call sigb_check( sigb_solver_setup(solver%dev, h) ) ...
+!     so that ANY operator with a device mirror -- a stored matrix or one of
+!     the expressions below -- drives the device-resident loops.
+!
+! --- src/linear_operator/linear_operator_sums.f90, type operator_sum (:11-20)
+!     gains  type(c_ptr), private :: mirror = c_null_ptr
+!
+!     function operator_sum_device_handle(A) result(h)      ! new
+!         hA = A%summands(1)%ap%device_handle()              ! refreshes dirty values
+!         hB = A%summands(2)%ap%device_handle()
+!         if (.not. c_associated(A%mirror)) &
+!             call sigb_check( sigb_operator_sum(hA, hB, A%mirror) )
+!         h = A%mirror
+!     end function
+!
+!     subroutine operator_sum_matvec_add(A, x, y)           ! :100-114
+!         h = A%device_handle()
+!         if (c_associated(h)) then
+!             call sigb_check( sigb_matvec_add(h, 0_c_int, x, y) )
+!         else
+!             ... the reference loop over summands, unchanged ...
+!         endif
+!     end subroutine
+!     (matvec_t_add :117-131 with trans = 1; operator_sum_destroy :136-159
+!      additionally calls sigb_matrix_destroy(A%mirror).)
+!
+!     linear_operator_products.f90 (:39-150) and linear_operator_adjoints.f90
+!     (:28-86) follow the same pattern with sigb_operator_product /
+!     sigb_operator_adjoint; the host scratch vectors z1, z2 (:15,61) are no
+!     longer touched when the product has a device mirror.
+!
+! --- src/matrix/sparse_matrix_composites.f90, type sparse_matrix (:41-49)
+!     gains  type(c_ptr), private :: mirror = c_null_ptr ; set_submatrix
+!     (:1031-1065) and set_matrix_type (:267-307) drop it.
+!
+!     function composite_mat_device_handle(A) result(h)     ! new
+!         type(c_ptr) :: blocks(A%num_row_mats * A%num_col_mats)
+!         do it = 1, A%num_row_mats ; do jt = 1, A%num_col_mats
+!             blocks((it - 1) * A%num_col_mats + jt) = A%sub_mats(it, jt)%mat%device_handle()
+!         enddo ; enddo
+!         if (.not. c_associated(A%mirror)) call sigb_check( sigb_composite_create( &
+!                 & A%num_row_mats, A%num_col_mats, &
+!                 & A%row_ptr(2:) - A%row_ptr(:A%num_row_mats), &
+!                 & A%col_ptr(2:) - A%col_ptr(:A%num_col_mats), blocks, A%mirror) )
+!         h = A%mirror
+!     end function
+!
+!     composite_matvec_add (:1076-1100) / composite_matvec_t_add (:1105-1129)
+!     become one sigb_matvec_add call on that handle: the block loops run on
+!     the device over offset slices of x and y, no host round trip per block.
+!
+! --- src/eigensolver.f90, generalized_lanczos (:95-155):
+!         call sigb_check( sigb_generalized_lanczos(A%device_handle(), B%device_handle(), &
+!                 & B%solver%dev, pc_or_null, size(T, 2), c_loc(Q(1,1)), 0_c_int64_t, T, Q) )
+!     where B%solver is what `call B%set_solver(...)` attached (:134 runs it).

@@ -19,6 +19,9 @@
 //   cg(tol), bicgstab(tol), jacobi()                same names -> linear_solver*
 //   solver%setup / solve(A,x,b[,pc]) / destroy      same names
 //   lanczos(A,T,Q), eigensolve(A,lambda,V)          same names
+//   L = A + B, L = A * B, L = adjoint(A)            same (operator_sum/_product/_adjoint)
+//   type(sparse_matrix) composite: set_dimensions,  sparse_matrix, same names
+//   set_block_sizes, set_submatrix, set/add/get
 //
 // Host mutators mark the device mirror dirty; the next matvec / solve re-uploads
 // the values.  Index arrays are 1-based int32 exactly as the
@@ -95,7 +98,10 @@ struct graph_mirror {
 struct cs_graph {
     int n = 0, m = 0, ne = 0, max_d = 0;
     std::vector<int32_t> ptr, node;            // ptr(n+1), node(ne), 1-based
-    std::shared_ptr<graph_mirror> mirror;      // dropped by every mutator
+    // device mirrors, dropped by every mutator: [0] as the row pattern of a
+    // csr_matrix, [1] as the column pattern of a csc_matrix (one graph object can
+    // serve both at once: test/matrix_test_composite.f90:176-186)
+    std::shared_ptr<graph_mirror> mirror[2];
 
     // g%copy(h, trans) -> cs_graph_build :109-197: count, 1-based prefix sum,
     // first-free-slot insertion in the source iteration order (never sorted)
@@ -118,7 +124,8 @@ struct cs_graph {
             }
         max_d = 0;
         for (int i = 0; i < n; i++) max_d = std::max(max_d, ptr[(size_t)i + 1] - ptr[(size_t)i]);
-        mirror.reset();
+        mirror[0].reset();
+        mirror[1].reset();
     }
     int find_edge(int i, int j) const   // 0-based position in node, -1 if absent
     {
@@ -162,21 +169,30 @@ struct linear_solver;
 // src/linear_operator/linear_operator_interface.f90:18-45
 struct linear_operator {
     int nrow = 0, ncol = 0;
+    int reference_count = 0;                     // :285-302
     linear_solver *solver = nullptr, *pc = nullptr;
     virtual ~linear_operator() {}
-    virtual void matvec_add(const dp *x, dp *y) = 0;
-    virtual void matvec_t_add(const dp *x, dp *y) = 0;
-    virtual void matvec(const dp *x, dp *y)      // :185-194: y = 0 ; matvec_add
+    // The device mirror of this operator, brought up to date (values re-uploaded
+    // after host mutations).  Every operator of this header has one: a stored
+    // matrix mirrors its arrays, an expression is built from its operands' mirrors.
+    virtual sigb_matrix_t device_handle() = 0;
+    // matvec_add / matvec_t_add (deferred in the reference, :35-36) and the
+    // non-overridable matvec / matvec_t (:185-208; the zero-fill is fused away)
+    virtual void matvec_add(const dp *x, dp *y) { sigb_check(sigb_matvec_add(device_handle(), 0, x, y)); }
+    virtual void matvec_t_add(const dp *x, dp *y) { sigb_check(sigb_matvec_add(device_handle(), 1, x, y)); }
+    virtual void matvec(const dp *x, dp *y) { sigb_check(sigb_matvec(device_handle(), 0, x, y)); }
+    virtual void matvec_t(const dp *x, dp *y) { sigb_check(sigb_matvec(device_handle(), 1, x, y)); }
+    // default get_value (:168-181): column j of the operator through a matvec
+    virtual dp get_value(int i, int j)
     {
-        for (int i = 0; i < nrow; i++) y[i] = 0.0;
-        matvec_add(x, y);
+        std::vector<dp> x((size_t)ncol, 0.0), y((size_t)nrow, 0.0);
+        x[(size_t)j - 1] = 1.0;
+        matvec(x.data(), y.data());
+        return y[(size_t)i - 1];
     }
-    virtual void matvec_t(const dp *x, dp *y)    // :199-208
-    {
-        for (int i = 0; i < ncol; i++) y[i] = 0.0;
-        matvec_t_add(x, y);
-    }
-    virtual dp get_value(int, int) { return 0.0; }
+    void add_reference() { reference_count++; }
+    void remove_reference() { reference_count--; }
+    virtual void destroy() {}
     inline void set_solver(linear_solver *s);          // :259-267
     inline void set_preconditioner(linear_solver *p);  // :272-280
     inline void solve(dp *x, const dp *b);             // :213-233
@@ -189,10 +205,9 @@ struct device_matrix : linear_operator {
     std::vector<dp> val;
     ~device_matrix() override { if (mirror) sigb_matrix_destroy(mirror); }
     virtual void sync_mirror() = 0;
-    void matvec_add(const dp *x, dp *y) override { sync_mirror(); sigb_check(sigb_matvec_add(mirror, 0, x, y)); }
-    void matvec_t_add(const dp *x, dp *y) override { sync_mirror(); sigb_check(sigb_matvec_add(mirror, 1, x, y)); }
-    void matvec(const dp *x, dp *y) override { sync_mirror(); sigb_check(sigb_matvec(mirror, 0, x, y)); }
-    void matvec_t(const dp *x, dp *y) override { sync_mirror(); sigb_check(sigb_matvec(mirror, 1, x, y)); }
+    sigb_matrix_t device_handle() override { sync_mirror(); return mirror; }
+    virtual void set_value(int i, int j, dp z) = 0;
+    virtual void add_value(int i, int j, dp z) = 0;
     void zero() { for (dp &v : val) v = 0.0; dirty = true; }
     void scalar_multiply(dp alpha) { for (dp &v : val) v *= alpha; dirty = true; }
     void upload()
@@ -237,19 +252,20 @@ struct cs_matrix : device_matrix {
         std::printf(" entry (%d,%d) is not in the sparsity pattern; the reallocation path of set_value is not part of this mirror\n Terminating.\n", i, j);
         std::exit(1);
     }
-    void set_value(int i, int j, dp z) { const int k = slot(i, j); if (k < 0) missing(i, j); val[(size_t)k] = z; dirty = true; }
-    void add_value(int i, int j, dp z) { const int k = slot(i, j); if (k < 0) missing(i, j); val[(size_t)k] += z; dirty = true; }
+    void set_value(int i, int j, dp z) override { const int k = slot(i, j); if (k < 0) missing(i, j); val[(size_t)k] = z; dirty = true; }
+    void add_value(int i, int j, dp z) override { const int k = slot(i, j); if (k < 0) missing(i, j); val[(size_t)k] += z; dirty = true; }
     dp get_value(int i, int j) override { const int k = slot(i, j); return k < 0 ? 0.0 : val[(size_t)k]; }
 
     void sync_mirror() override
     {
-        if (!g->mirror) {
-            g->mirror = std::make_shared<graph_mirror>();
+        std::shared_ptr<graph_mirror> &gm = g->mirror[COL ? 1 : 0];
+        if (!gm) {
+            gm = std::make_shared<graph_mirror>();
             sigb_check(sigb_cs_graph_create(g->n, g->m, g->ptr.data(), g->node.data(), COL ? SIGB_COL : SIGB_ROW,
-                                            &g->mirror->h));
+                                            &gm->h));
         }
         if (!mirror) {
-            sigb_check(sigb_matrix_create(g->mirror->h, &mirror));
+            sigb_check(sigb_matrix_create(gm->h, &mirror));
             dirty = true;
         }
         upload();
@@ -284,14 +300,14 @@ struct ellpack_matrix : device_matrix {
             if (g->node[(size_t)(i - 1) * g->max_d + k] == j) found = (i - 1) * g->max_d + k;
         return found;
     }
-    void set_value(int i, int j, dp z)
+    void set_value(int i, int j, dp z) override
     {
         const int k = slot(i, j);
         if (k < 0) { std::printf(" entry (%d,%d) is not in the sparsity pattern\n Terminating.\n", i, j); std::exit(1); }
         val[(size_t)k] = z;
         dirty = true;
     }
-    void add_value(int i, int j, dp z)
+    void add_value(int i, int j, dp z) override
     {
         const int k = slot(i, j);
         if (k < 0) { std::printf(" entry (%d,%d) is not in the sparsity pattern\n Terminating.\n", i, j); std::exit(1); }
@@ -315,6 +331,176 @@ struct ellpack_matrix : device_matrix {
 };
 
 // ---------------------------------------------------------------------------
+// operator expressions (src/linear_operator/linear_operator_{sums,products,
+// adjoints}.f90) and the block composite (src/matrix/sparse_matrix_composites.f90)
+// ---------------------------------------------------------------------------
+// Common part: the device expression is (re)built from the operands' current
+// mirrors whenever one of them has been replaced (set_graph drops a mirror);
+// refreshing the operands' values is all that is needed otherwise.
+struct operator_expression : linear_operator {
+    std::vector<linear_operator *> operands;
+    std::vector<sigb_matrix_t> built_from;
+    sigb_matrix_t handle = nullptr;
+    ~operator_expression() override { if (handle) sigb_matrix_destroy(handle); }
+    virtual void build(const std::vector<sigb_matrix_t> &h) = 0;
+    sigb_matrix_t device_handle() override
+    {
+        std::vector<sigb_matrix_t> h;
+        for (linear_operator *op : operands) h.push_back(op->device_handle());
+        if (!handle || h != built_from) {
+            if (handle) sigb_matrix_destroy(handle);
+            handle = nullptr;
+            build(h);
+            built_from = h;
+        }
+        return handle;
+    }
+    // operator_sum_destroy linear_operator_sums.f90:136-159 (same for the others):
+    // drop the references; an operand nobody else holds is destroyed with us
+    void destroy() override
+    {
+        if (handle) { sigb_matrix_destroy(handle); handle = nullptr; }
+        for (linear_operator *op : operands) {
+            op->remove_reference();
+            if (op->reference_count <= 0) { op->destroy(); delete op; }
+        }
+        operands.clear();
+        built_from.clear();
+        reference_count = 0;
+    }
+    void adopt(linear_operator &A) { operands.push_back(&A); A.add_reference(); }
+};
+
+struct operator_sum : operator_expression {
+    void build(const std::vector<sigb_matrix_t> &h) override { sigb_check(sigb_operator_sum(h[0], h[1], &handle)); }
+    dp get_value(int i, int j) override   // :79-95
+    {
+        dp z = 0.0;
+        for (linear_operator *op : operands) z = z + op->get_value(i, j);
+        return z;
+    }
+};
+struct operator_product : operator_expression {
+    void build(const std::vector<sigb_matrix_t> &h) override { sigb_check(sigb_operator_product(h[0], h[1], &handle)); }
+};
+struct operator_adjoint : operator_expression {
+    void build(const std::vector<sigb_matrix_t> &h) override { sigb_check(sigb_operator_adjoint(h[0], &handle)); }
+    dp get_value(int i, int j) override { return operands[0]->get_value(j, i); }   // :49-57
+};
+
+// add_operators (linear_operator_sums.f90:38-72), multiply_operators
+// (linear_operator_products.f90:39-73), adjoint (linear_operator_adjoints.f90:28-44).
+// Stack objects handed in as operands must carry a reference of their own
+// (call A.add_reference() first) or destroy() would try to delete them.
+inline linear_operator *add_operators(linear_operator &A, linear_operator &B)
+{
+    if (A.nrow != B.nrow || A.ncol != B.ncol) {
+        std::printf(" Dimensions of operators to be summed are not consistent\n");
+        std::exit(1);
+    }
+    auto *C = new operator_sum();
+    C->nrow = A.nrow;
+    C->ncol = A.ncol;
+    C->adopt(A);
+    C->adopt(B);
+    return C;
+}
+inline linear_operator *multiply_operators(linear_operator &A, linear_operator &B)
+{
+    if (A.ncol != B.nrow) {
+        std::printf(" Dimensions of operators to be multiplied are inconsistent\n");
+        std::exit(1);
+    }
+    auto *C = new operator_product();
+    C->nrow = A.nrow;
+    C->ncol = B.ncol;
+    C->adopt(A);
+    C->adopt(B);
+    return C;
+}
+inline linear_operator *adjoint(linear_operator &A)
+{
+    auto *B = new operator_adjoint();
+    B->nrow = A.ncol;
+    B->ncol = A.nrow;
+    B->adopt(A);
+    return B;
+}
+inline linear_operator *operator+(linear_operator &A, linear_operator &B) { return add_operators(A, B); }
+inline linear_operator *operator*(linear_operator &A, linear_operator &B) { return multiply_operators(A, B); }
+
+// type(sparse_matrix) as a composite of sub-matrices
+// (sparse_matrix_composites.f90:41-49); every block is set with set_submatrix
+struct sparse_matrix : operator_expression {
+    int num_row_mats = 0, num_col_mats = 0;
+    std::vector<int> row_ptr, col_ptr;     // 1-based block offsets, as in the reference
+
+    void set_dimensions(int nrow_, int ncol_) { nrow = nrow_; ncol = ncol_; }     // :181-198
+    void set_block_sizes(const std::vector<int> &rows, const std::vector<int> &cols)   // :226-262
+    {
+        num_row_mats = (int)rows.size();
+        num_col_mats = (int)cols.size();
+        row_ptr.assign(rows.size() + 1, 1);
+        col_ptr.assign(cols.size() + 1, 1);
+        for (size_t it = 0; it < rows.size(); it++) row_ptr[it + 1] = row_ptr[it] + rows[it];
+        for (size_t jt = 0; jt < cols.size(); jt++) col_ptr[jt + 1] = col_ptr[jt] + cols[jt];
+        operands.assign(rows.size() * cols.size(), nullptr);
+    }
+    linear_operator *&sub(int it, int jt) { return operands[(size_t)(it - 1) * num_col_mats + (jt - 1)]; }
+    void set_submatrix(int it, int jt, linear_operator &B)   // :1031-1065
+    {
+        const int r = row_ptr[(size_t)it] - row_ptr[(size_t)it - 1], c = col_ptr[(size_t)jt] - col_ptr[(size_t)jt - 1];
+        if (B.nrow != r || B.ncol != c) {
+            std::printf(" Inconsistent dimensions for sub-matrix\n");
+            std::exit(1);
+        }
+        sub(it, jt) = &B;
+        B.add_reference();
+    }
+    int get_owning_row_matrix(int i) const      // :1235-1246
+    {
+        int it = 1;
+        for (; it <= num_row_mats; it++)
+            if (row_ptr[(size_t)it - 1] <= i && row_ptr[(size_t)it] > i) break;
+        return it;
+    }
+    int get_owning_column_matrix(int j) const   // :1251-1262
+    {
+        int jt = 1;
+        for (; jt <= num_col_mats; jt++)
+            if (col_ptr[(size_t)jt - 1] <= j && col_ptr[(size_t)jt] > j) break;
+        return jt;
+    }
+    dp get_value(int i, int j) override         // :465-485
+    {
+        const int it = get_owning_row_matrix(i), jt = get_owning_column_matrix(j);
+        return sub(it, jt)->get_value(i - row_ptr[(size_t)it - 1] + 1, j - col_ptr[(size_t)jt - 1] + 1);
+    }
+    dp get(int it, int jt, int i, int j) { return sub(it, jt)->get_value(i, j); }   // get_submat_value :490-498
+    device_matrix &leaf(int it, int jt)
+    {
+        auto *M = dynamic_cast<device_matrix *>(sub(it, jt));
+        if (!M) { std::printf(" sub-matrix (%d,%d) is not a stored matrix\n Terminating.\n", it, jt); std::exit(1); }
+        return *M;
+    }
+    void set(int it, int jt, int i, int j, dp z) { leaf(it, jt).set_value(i, j, z); }   // set_submat_value :904-912
+    void add(int it, int jt, int i, int j, dp z) { leaf(it, jt).add_value(i, j, z); }   // add_submat_value :917-925
+    sigb_matrix_t device_handle() override
+    {
+        for (linear_operator *op : operands)
+            if (!op) { std::printf(" composite matrix has an unset sub-matrix\n Terminating.\n"); std::exit(1); }
+        return operator_expression::device_handle();
+    }
+    void build(const std::vector<sigb_matrix_t> &h) override
+    {
+        std::vector<int32_t> rows((size_t)num_row_mats), cols((size_t)num_col_mats);
+        for (int it = 0; it < num_row_mats; it++) rows[(size_t)it] = row_ptr[(size_t)it + 1] - row_ptr[(size_t)it];
+        for (int jt = 0; jt < num_col_mats; jt++) cols[(size_t)jt] = col_ptr[(size_t)jt + 1] - col_ptr[(size_t)jt];
+        sigb_check(sigb_composite_create(num_row_mats, num_col_mats, rows.data(), cols.data(), h.data(), &handle));
+    }
+};
+
+// ---------------------------------------------------------------------------
 // solvers (src/solver/*.f90)
 // ---------------------------------------------------------------------------
 struct linear_solver {
@@ -324,19 +510,11 @@ struct linear_solver {
     sigb_solver_t dev = nullptr;
     virtual ~linear_solver() { destroy(); }
 
-    static device_matrix &mirrored(linear_operator &A)
-    {
-        auto *M = dynamic_cast<device_matrix *>(&A);
-        if (!M) { std::printf(" this solver needs a csr/csc/ellpack matrix\n Terminating.\n"); std::exit(1); }
-        return *M;
-    }
     // solver%setup(A): the non-square check and its message live in the library
     // (cg_solvers.f90:61-65 -> SIGB_ERR_NONSQUARE -> print + exit(1))
     virtual void setup(linear_operator &A)
     {
-        device_matrix &M = mirrored(A);
-        M.sync_mirror();
-        sigb_check(sigb_solver_setup(dev, M.mirror));
+        sigb_check(sigb_solver_setup(dev, A.device_handle()));
         nn = A.nrow;
         initialized = true;
         iterations = 0;
@@ -344,9 +522,7 @@ struct linear_solver {
     // call solver%solve(A, x, b [, pc])
     virtual void solve(linear_operator &A, dp *x, const dp *b, linear_solver *pc = nullptr)
     {
-        device_matrix &M = mirrored(A);
-        M.sync_mirror();
-        sigb_check(sigb_solver_solve(dev, M.mirror, x, b, pc ? pc->dev : nullptr));
+        sigb_check(sigb_solver_solve(dev, A.device_handle(), x, b, pc ? pc->dev : nullptr));
         int64_t it = 0;
         sigb_check(sigb_solver_get_info(dev, &it, nullptr, nullptr));
         iterations = (int)it;
@@ -406,44 +582,34 @@ inline void linear_operator::solve(dp *x, const dp *b) { solver->solve(*this, x,
 // draws it from `seed` (the reference uses a time-seeded RNG, :47-50).
 inline void lanczos(linear_operator &A, int n, dp *T, dp *Q, bool use_q1 = false, uint64_t seed = 0)
 {
-    device_matrix &M = linear_solver::mirrored(A);
-    M.sync_mirror();
     std::vector<dp> q1;
     if (use_q1) q1.assign(Q, Q + A.nrow);
-    sigb_check(sigb_lanczos(M.mirror, n, use_q1 ? q1.data() : nullptr, seed, T, Q));
+    sigb_check(sigb_lanczos(A.device_handle(), n, use_q1 ? q1.data() : nullptr, seed, T, Q));
 }
 inline void eigensolve(linear_operator &A, int n, dp *lambda, dp *V, bool use_q1 = false, uint64_t seed = 0)
 {
-    device_matrix &M = linear_solver::mirrored(A);
-    M.sync_mirror();
     std::vector<dp> q1;
     if (use_q1) q1.assign(V, V + A.nrow);
-    sigb_check(sigb_eigensolve(M.mirror, n, use_q1 ? q1.data() : nullptr, seed, lambda, V));
+    sigb_check(sigb_eigensolve(A.device_handle(), n, use_q1 ? q1.data() : nullptr, seed, lambda, V));
 }
 
 // call B%set_solver(...) first; call generalized_lanczos(A, B, T, Q)   (eigensolver.f90:95-155)
 inline void generalized_lanczos(linear_operator &A, linear_operator &B, int n, dp *T, dp *Q, bool use_q1 = false,
                                 uint64_t seed = 0)
 {
-    device_matrix &MA = linear_solver::mirrored(A), &MB = linear_solver::mirrored(B);
     if (!B.solver) { std::printf(" generalized_lanczos: B has no solver set\n Terminating.\n"); std::exit(1); }
-    MA.sync_mirror();
-    MB.sync_mirror();
     std::vector<dp> q1;
     if (use_q1) q1.assign(Q, Q + A.nrow);
-    sigb_check(sigb_generalized_lanczos(MA.mirror, MB.mirror, B.solver->dev, B.pc ? B.pc->dev : nullptr, n,
+    sigb_check(sigb_generalized_lanczos(A.device_handle(), B.device_handle(), B.solver->dev, B.pc ? B.pc->dev : nullptr, n,
                                         use_q1 ? q1.data() : nullptr, seed, T, Q));
 }
 inline void generalized_eigensolve(linear_operator &A, linear_operator &B, int n, dp *lambda, dp *V,
                                    bool use_q1 = false, uint64_t seed = 0)
 {
-    device_matrix &MA = linear_solver::mirrored(A), &MB = linear_solver::mirrored(B);
     if (!B.solver) { std::printf(" generalized_eigensolve: B has no solver set\n Terminating.\n"); std::exit(1); }
-    MA.sync_mirror();
-    MB.sync_mirror();
     std::vector<dp> q1;
     if (use_q1) q1.assign(V, V + A.nrow);
-    sigb_check(sigb_generalized_eigensolve(MA.mirror, MB.mirror, B.solver->dev, B.pc ? B.pc->dev : nullptr, n,
+    sigb_check(sigb_generalized_eigensolve(A.device_handle(), B.device_handle(), B.solver->dev, B.pc ? B.pc->dev : nullptr, n,
                                            use_q1 ? q1.data() : nullptr, seed, lambda, V));
 }
 
