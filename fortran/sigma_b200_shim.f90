@@ -237,6 +237,34 @@ interface                                                                  !
         integer(c_int) :: stat
     end function
 
+    ! matrix copy / format conversion on the device
+    function sigb_matrix_copy(A, frmt, trans, B) bind(c, name='sigb_matrix_copy') result(stat)
+        import :: c_int, c_ptr
+        type(c_ptr), value :: A
+        integer(c_int), value :: frmt, trans     ! frmt: 1 csr, 2 csc, 3 ellpack
+        type(c_ptr), intent(out) :: B
+        integer(c_int) :: stat
+    end function
+
+    function sigb_matrix_get_format(A, frmt, n_lines, n_ids, ne, max_d) &
+            & bind(c, name='sigb_matrix_get_format') result(stat)
+        import :: c_int, c_int32_t, c_int64_t, c_ptr
+        type(c_ptr), value :: A
+        integer(c_int), intent(out) :: frmt
+        integer(c_int32_t), intent(out) :: n_lines, n_ids, max_d
+        integer(c_int64_t), intent(out) :: ne
+        integer(c_int) :: stat
+    end function
+
+    function sigb_matrix_get_arrays(A, ptr_or_degrees, node, val) &
+            & bind(c, name='sigb_matrix_get_arrays') result(stat)
+        import :: c_int, c_int32_t, c_double, c_ptr
+        type(c_ptr), value :: A
+        integer(c_int32_t), intent(out) :: ptr_or_degrees(*), node(*)
+        real(c_double), intent(out) :: val(*)
+        integer(c_int) :: stat
+    end function
+
     function sigb_matrix_retain(A) bind(c, name='sigb_matrix_retain') result(stat)
         import :: c_int, c_ptr
         type(c_ptr), value :: A
@@ -446,3 +474,19 @@ end module sigma_b200_shim
 !         call sigb_check( sigb_generalized_lanczos(A%device_handle(), B%device_handle(), &
 !                 & B%solver%dev, pc_or_null, size(T, 2), c_loc(Q(1,1)), 0_c_int64_t, T, Q) )
 !     where B%solver is what `call B%set_solver(...)` attached (:134 runs it).
+!
+! --- src/matrix/formats/cs_matrices.f90, cs_matrix_copy_matrix (:294-322):
+!         h = B%device_handle()
+!         if (c_associated(h)) then
+!             frmt = 1 ; if (A%get_col_is_fast) frmt = 2
+!             call sigb_check( sigb_matrix_copy(h, frmt, merge(1, 0, tr), A%mirror) )
+!             call sigb_check( sigb_matrix_get_format(A%mirror, frmt, n, m, ne, max_d) )
+!             allocate(A%g) ; A%g%n = n ; A%g%m = m ; A%g%ne = ne ; A%g%max_d = max_d
+!             allocate(A%g%ptr(n + 1), A%g%node(ne), A%val(ne))
+!             call sigb_check( sigb_matrix_get_arrays(A%mirror, A%g%ptr, A%g%node, A%val) )
+!             A%dirty = .false. ; A%graph_set = .true.
+!         else
+!             ... build_graph_from_matrix + copy_matrix_values, unchanged ...
+!         endif
+!     ellpack_matrix_copy_matrix (ellpack_matrices.f90:169-198) likewise with
+!     frmt = 3 and A%g%degrees(n), A%g%node(max_d, n), A%val(max_d, n).

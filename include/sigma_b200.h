@@ -137,6 +137,38 @@ SIGB_API int sigb_matrix_get_dims(sigb_matrix_t A, int32_t *nrow, int32_t *ncol,
 /* Values of the device-built transpose, in sigb_cs_graph_get_transpose order. */
 SIGB_API int sigb_matrix_get_transpose_values(sigb_matrix_t A, double *val_t);
 
+/* ---- matrix copy / format conversion on the device -----------------------
+ * The step before the hot path: today an O(ne * d) host
+ * scan per copy (cs_graph_build, src/graph/formats/cs_graphs.f90:163-183). */
+enum { SIGB_FMT_CSR = 1, SIGB_FMT_CSC = 2, SIGB_FMT_ELLPACK = 3 };
+
+/* call B%copy_matrix(A, trans) with B of the given format:
+ * cs_matrix_copy_matrix (src/matrix/formats/cs_matrices.f90:294-322) /
+ * ellpack_matrix_copy_matrix (src/matrix/formats/ellpack_matrices.f90:169-198)
+ * = build_graph_from_matrix + copy_matrix_values
+ * (src/matrix/sparse_matrix_interfaces.f90:692-772).  B gets its own graph,
+ * whose arrays equal what the reference's builders produce bit for bit: every
+ * target line holds its entries in the source's iteration order (first-free-
+ * slot insertion, cs_graphs.f90:163-183; ellpack_graphs.f90:150-168 with
+ * last-neighbour padding and val = 0 in the padding).  trans != 0 copies the
+ * transpose.  An ellpack target with an empty row -> SIGB_ERR_ISOLATED.
+ * A must be a stored csr / csc / ellpack matrix without duplicate edges. */
+SIGB_API int sigb_matrix_copy(sigb_matrix_t A, int format, int trans,
+                              sigb_matrix_t *B);
+/* Shape of a stored matrix's arrays: n_lines = g%n, n_ids = g%m, ne = g%ne,
+ * max_d = g%max_d (any pointer may be NULL). */
+SIGB_API int sigb_matrix_get_format(sigb_matrix_t A, int *format,
+                                    int32_t *n_lines, int32_t *n_ids,
+                                    int64_t *ne, int32_t *max_d);
+/* Read the arrays back so the host object can be filled in (or checked):
+ *  csr / csc : ptr_or_degrees = g%ptr(n_lines+1), node = g%node(ne),
+ *              val = A%val(ne), all 1-based as the Fortran holds them;
+ *  ellpack   : ptr_or_degrees = g%degrees(n_lines), node = g%node(max_d, n),
+ *              val = A%val(max_d, n) (slot index fastest).
+ * Any pointer may be NULL. */
+SIGB_API int sigb_matrix_get_arrays(sigb_matrix_t A, int32_t *ptr_or_degrees,
+                                    int32_t *node, double *val);
+
 /* ---- matvec ------------------------------------------------------------ */
 
 /* linear_operator%matvec / matvec_t

@@ -24,7 +24,7 @@ __all__ = [
     "cg_solve", "bicgstab_solve", "lanczos", "generalized_lanczos", "eigensolve", "tridiag_eig",
     "partition_rows", "halo_build", "cs_set_value", "ell_set_value",
     "SUM", "PRODUCT", "ADJOINT", "COMPOSITE", "operator_sum", "operator_product", "adjoint",
-    "composite", "get_value",
+    "composite", "get_value", "matrix_entries", "copy_matrix",
 ]
 
 
@@ -69,6 +69,7 @@ def lib():
         "orc_cs_get_value": (f64, [_i32p, _i32p, _f64p, i32, i32]),
         "orc_ell_set_value": (i32, [i32, _i32p, _i32p, _f64p, i32, i32, f64, i32]),
         "orc_ell_get_value": (f64, [i32, _i32p, _i32p, _f64p, i32, i32]),
+        "orc_copy_matrix_values": (i64, [i32, i32, vp, _i32p, vp, _f64p, i64, _i32p, _i32p, _f64p, i32]),
         "orc_matvec_add": (None, [mp, i32, _f64p, _f64p]),
         "orc_matvec": (None, [mp, i32, _f64p, _f64p]),
         "orc_get_value": (f64, [mp, i32, i32]),
@@ -237,6 +238,44 @@ def cs_set_value(ptr, node, val, i, j, z, add=False):
 
 def ell_set_value(node, degrees, val, i, j, z, add=False):
     return lib().orc_ell_set_value(node.shape[1], node.reshape(-1), degrees, val.reshape(-1), i, j, z, int(add))
+
+
+def matrix_entries(A: Matrix):
+    """The (i, j, value) stream of A's entry iterator, in iteration order:
+    cs_matrix_get_entries (cs_matrices.f90:415-438; a csc_matrix swaps the pair,
+    :793-806) walks the stored arrays line by line; ellpack_matrix_get_entries
+    (ellpack_matrices.f90:381-434) walks each row's first degrees(i) slots."""
+    if A.format == ELL:
+        k = np.arange(A.max_d)[None, :] < A.degrees[:, None]
+        i = np.nonzero(k)[0].astype(np.int32) + 1
+        return i, A.node[k].astype(np.int32), A.val.reshape(A.nrow, A.max_d)[k]
+    line = np.repeat(np.arange(1, A.ptr.size, dtype=np.int32), np.diff(A.ptr))
+    return (line, A.node.copy(), A.val.copy()) if A.format == CSR else (A.node.copy(), line, A.val.copy())
+
+
+def copy_matrix(B: Matrix, fmt, trans=False) -> Matrix:
+    """A%copy_matrix(B, trans) for a target A of format `fmt`:
+    cs_matrix_copy_matrix (cs_matrices.f90:294-322) / ellpack_matrix_copy_matrix
+    (ellpack_matrices.f90:169-198) = build_graph_from_matrix + copy_matrix_values
+    (sparse_matrix_interfaces.f90:692-772)."""
+    si, sj, sv = matrix_entries(B)
+    nrow, ncol = (B.ncol, B.nrow) if trans else (B.nrow, B.ncol)
+    if fmt == ELL:
+        node, deg = ellpack_graph_build(nrow, si, sj, trans=trans)
+        val = np.zeros(node.shape)
+        miss = lib().orc_copy_matrix_values(ELL, node.shape[1], None, node.reshape(-1), deg.ctypes.data,
+                                            val.reshape(-1), si.size, _i32(si), _i32(sj), _f64(sv), int(trans))
+        assert miss == 0
+        return Matrix(ELL, nrow, ncol, node, val, degrees=deg)
+    # the graph of a csc_matrix holds the columns: built with trans flipped (:311)
+    t = (fmt == CSC) != bool(trans)
+    nlines = ncol if fmt == CSC else nrow
+    ptr, node, _ = cs_graph_build(nlines, si, sj, trans=t)
+    val = np.zeros(node.size)
+    miss = lib().orc_copy_matrix_values(fmt, 0, ptr.ctypes.data, node, None, val, si.size, _i32(si), _i32(sj),
+                                        _f64(sv), int(trans))
+    assert miss == 0
+    return Matrix(fmt, nrow, ncol, node, val, ptr=ptr)
 
 
 def matvec(A: Matrix, x, trans=False):

@@ -261,6 +261,44 @@ ORC_API double orc_ell_get_value(int32_t max_d, const int32_t *node,
 }
 
 /* ------------------------------------------------------------------------ */
+/* matrix copy / format conversion                                           */
+/* ------------------------------------------------------------------------ */
+
+/*
+ * copy_matrix_values, src/matrix/sparse_matrix_interfaces.f90:740-772: walk
+ * the entries (si[k], sj[k], sv[k]) of the source in its iteration order and
+ * `call A%set(i, j, z)` on the target, with (i, j) swapped when trans.  The
+ * target graph was built beforehand from the same stream
+ * (build_graph_from_matrix :692-735 -> orc_cs_graph_build /
+ * orc_ellpack_graph_build).
+ *
+ * target_format: ORC_CSR (1): csr_matrix_set_value cs_matrices.f90:840-863
+ *                ORC_CSC (2): csc_matrix_set_value :896-919 (scans column j)
+ *                ORC_ELL (3): ellpack_matrix_set_value ellpack_matrices.f90:444-466
+ * Returns the number of entries that were not found in the target pattern
+ * (0 when the graph was built from the same stream).
+ */
+ORC_API int64_t orc_copy_matrix_values(int32_t target_format, int32_t max_d,
+                                       const int32_t *ptr, const int32_t *node,
+                                       const int32_t *degrees, double *val,
+                                       int64_t ne, const int32_t *si,
+                                       const int32_t *sj, const double *sv,
+                                       int32_t trans)
+{
+    int64_t k, missing = 0;
+    for (k = 0; k < ne; k++) {
+        const int32_t i = trans ? sj[k] : si[k];
+        const int32_t j = trans ? si[k] : sj[k];
+        int32_t found;
+        if (target_format == 1)      found = orc_cs_set_value(ptr, node, val, i, j, sv[k], 0);
+        else if (target_format == 2) found = orc_cs_set_value(ptr, node, val, j, i, sv[k], 0);
+        else                         found = orc_ell_set_value(max_d, node, degrees, val, i, j, sv[k], 0);
+        if (!found) missing++;
+    }
+    return missing;
+}
+
+/* ------------------------------------------------------------------------ */
 /* matvec kernels                                                            */
 /* ------------------------------------------------------------------------ */
 

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsigma_b200%s.so" % os.environ.get("SIG
 
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NONSQUARE, ERR_ISOLATED, ERR_COMM, ERR_UNSUPPORTED = range(8)
 ROW, COL = 0, 1
+FMT_CSR, FMT_CSC, FMT_ELLPACK = 1, 2, 3
 UNIQUE_ID_BYTES = 128
 
 
@@ -56,6 +57,9 @@ PROTOTYPES = {
     "sigb_matrix_destroy": (C.c_int, [_vp]),
     "sigb_matrix_get_dims": (C.c_int, [_vp, _pi32, _pi32, _pi64]),
     "sigb_matrix_get_transpose_values": (C.c_int, [_vp, _vp]),
+    "sigb_matrix_copy": (C.c_int, [_vp, C.c_int, C.c_int, _pvp]),
+    "sigb_matrix_get_format": (C.c_int, [_vp, C.POINTER(C.c_int), _pi32, _pi32, _pi64, _pi32]),
+    "sigb_matrix_get_arrays": (C.c_int, [_vp, _vp, _vp, _vp]),
     "sigb_matvec": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "sigb_matvec_add": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "sigb_matvec_dev": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int]),

@@ -154,6 +154,34 @@ class Matrix:
             return self.g.n * self.g.max_d
         return self.nnz
 
+    # -- copy / format conversion on the device ------------------------------
+    def copy_matrix(self, frmt: str, trans: bool = False) -> "Matrix":
+        """B of format `frmt` ("csr" | "csc" | "ellpack") after `call B%copy_matrix(A, trans)`
+        (cs_matrices.f90:294-322, ellpack_matrices.f90:169-198), built on the device."""
+        code = {"csr": _capi.FMT_CSR, "csc": _capi.FMT_CSC, "ellpack": _capi.FMT_ELLPACK}[frmt]
+        h = C.c_void_p()
+        check(lib().sigb_matrix_copy(self._h, code, int(trans), C.byref(h)))
+        B = Matrix(None, h)
+        B.format = frmt
+        return B
+
+    def arrays(self):
+        """The stored arrays, read back from the device exactly as the Fortran holds them:
+        ("csr"|"csc", ptr, node, val) or ("ellpack", degrees, node[n, max_d], val[n, max_d])."""
+        fmt, n, m, ne, md = C.c_int(), C.c_int32(), C.c_int32(), C.c_int64(), C.c_int32()
+        check(lib().sigb_matrix_get_format(self._h, C.byref(fmt), C.byref(n), C.byref(m), C.byref(ne), C.byref(md)))
+        if fmt.value == _capi.FMT_ELLPACK:
+            deg = np.empty(n.value, np.int32)
+            node = np.empty((n.value, md.value), np.int32)
+            val = np.empty((n.value, md.value))
+            check(lib().sigb_matrix_get_arrays(self._h, ptr(deg), ptr(node), ptr(val)))
+            return "ellpack", deg, node, val
+        p = np.empty(n.value + 1, np.int32)
+        node = np.empty(ne.value, np.int32)
+        val = np.empty(ne.value)
+        check(lib().sigb_matrix_get_arrays(self._h, ptr(p), ptr(node), ptr(val)))
+        return ("csr" if fmt.value == _capi.FMT_CSR else "csc"), p, node, val
+
     # -- operator algebra: interface operator(+) / operator(*) ----------------
     def __add__(self, other):
         return operator_sum(self, other)

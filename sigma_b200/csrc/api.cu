@@ -50,7 +50,7 @@ static int dev_alloc(T **p, size_t count)
 }
 
 // upload the tile table of a CSR view
-static int upload_tiles(CsrView &v, const std::vector<TileDesc> &tiles)
+int upload_tiles(CsrView &v, const std::vector<TileDesc> &tiles)
 {
     v.ntiles = (int32_t)tiles.size();
     SIGB_CHECK(dev_alloc(&v.tiles, tiles.size()));

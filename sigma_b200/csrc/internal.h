@@ -235,6 +235,8 @@ int ell_relayout_val(const double *val_cm_dev, int32_t n, int32_t n_pad,
 // transposed ell values: perm indexes the (line-major) stored layout
 int gather_values_ell(const double *val_sm, const int32_t *perm, int64_t ne,
                       int32_t n_pad, int32_t max_d, double *val_t);
+// exclusive scan of n int32 counts into n + 1 one-based offsets (ptr1[0] = 1)
+int scan_to_ptr1(const int32_t *cnt, int64_t n, int32_t *ptr1);
 int fill_i32(int32_t *p, int64_t n, int32_t v);
 int fill_f64(double *p, int64_t n, double v);
 
@@ -242,6 +244,8 @@ int fill_f64(double *p, int64_t n, double v);
 // matrix-level dispatch (api.cu)
 // ---------------------------------------------------------------------------
 int ensure_transposed(sigb_matrix_t A);
+// upload the tile table of a CSR view (api.cu)
+int upload_tiles(CsrView &v, const std::vector<TileDesc> &tiles);
 // y = op(A) x with device vectors; the single entry every solver goes through
 int matvec_dev(sigb_matrix_t A, int trans, const double *x, double *y,
                SpmvMode mode_csr_like, bool add, const DotSpec &dot);

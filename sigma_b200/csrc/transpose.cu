@@ -262,6 +262,9 @@ inline int grid_for(int64_t n)
     return (int)g;
 }
 
+}  // namespace
+
+// n counts -> n + 1 one-based offsets (also used by convert.cu)
 int scan_to_ptr1(const int32_t *cnt, int64_t n, int32_t *ptr1)
 {
     // n counts -> n + 1 one-based offsets
@@ -278,6 +281,8 @@ int scan_to_ptr1(const int32_t *cnt, int64_t n, int32_t *ptr1)
     SIGB_CUDA(cudaFree(block_sum));
     return SIGB_OK;
 }
+
+namespace {
 
 int finish_transpose(int32_t ntargets, int64_t ne, int32_t *ptr_t, int32_t *perm)
 {

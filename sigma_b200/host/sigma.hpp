@@ -14,6 +14,7 @@
 //   type(csr_matrix|csc_matrix|ellpack_matrix)      csr_matrix, csc_matrix, ellpack_matrix
 //   A%set_graph, zero, set_value, add_value,        same names
 //   get_value, scalar_multiply
+//   A%copy_matrix(B, trans)                         same name (built on the device)
 //   A%matvec / matvec_t / matvec_add / matvec_t_add same names (linear_operator)
 //   A%set_solver / set_preconditioner / solve       same names
 //   cg(tol), bicgstab(tol), jacobi()                same names -> linear_solver*
@@ -258,17 +259,46 @@ struct cs_matrix : device_matrix {
 
     void sync_mirror() override
     {
-        std::shared_ptr<graph_mirror> &gm = g->mirror[COL ? 1 : 0];
-        if (!gm) {
-            gm = std::make_shared<graph_mirror>();
-            sigb_check(sigb_cs_graph_create(g->n, g->m, g->ptr.data(), g->node.data(), COL ? SIGB_COL : SIGB_ROW,
-                                            &gm->h));
-        }
         if (!mirror) {
+            std::shared_ptr<graph_mirror> &gm = g->mirror[COL ? 1 : 0];
+            if (!gm) {
+                gm = std::make_shared<graph_mirror>();
+                sigb_check(sigb_cs_graph_create(g->n, g->m, g->ptr.data(), g->node.data(),
+                                                COL ? SIGB_COL : SIGB_ROW, &gm->h));
+            }
             sigb_check(sigb_matrix_create(gm->h, &mirror));
             dirty = true;
         }
         upload();
+    }
+
+    // call A%copy_matrix(B, trans)   (cs_matrix_copy_matrix :294-322): the graph is
+    // built and the values are placed ON THE DEVICE (sigb_matrix_copy), then read
+    // back into this object's own arrays; the device copy becomes the mirror.
+    void copy_matrix(linear_operator &B, bool trans = false)
+    {
+        const int nr = trans ? B.ncol : B.nrow, nc = trans ? B.nrow : B.ncol;
+        if (nrow != nr || ncol != nc) {
+            std::printf(" Attempted to copy a matrix of inconsistent dimensions\n Terminating.\n");
+            std::exit(1);
+        }
+        sigb_matrix_t h = nullptr;
+        sigb_check(sigb_matrix_copy(B.device_handle(), COL ? SIGB_FMT_CSC : SIGB_FMT_CSR, trans ? 1 : 0, &h));
+        int32_t n = 0, m = 0, md = 0;
+        int64_t ne = 0;
+        sigb_check(sigb_matrix_get_format(h, nullptr, &n, &m, &ne, &md));
+        g = std::make_shared<cs_graph>();
+        g->n = n;
+        g->m = m;
+        g->ne = (int)ne;
+        g->max_d = md;
+        g->ptr.assign((size_t)n + 1, 1);
+        g->node.assign((size_t)ne, 0);
+        val.assign((size_t)ne, 0.0);
+        sigb_check(sigb_matrix_get_arrays(h, g->ptr.data(), g->node.data(), val.data()));
+        if (mirror) sigb_matrix_destroy(mirror);
+        mirror = h;
+        dirty = false;
     }
 };
 using csr_matrix = cs_matrix<false>;
@@ -318,15 +348,43 @@ struct ellpack_matrix : device_matrix {
 
     void sync_mirror() override
     {
-        if (!g->mirror) {
-            g->mirror = std::make_shared<graph_mirror>();
-            sigb_check(sigb_ell_graph_create(g->n, g->m, g->max_d, g->node.data(), g->degrees.data(), &g->mirror->h));
-        }
         if (!mirror) {
+            if (!g->mirror) {
+                g->mirror = std::make_shared<graph_mirror>();
+                sigb_check(sigb_ell_graph_create(g->n, g->m, g->max_d, g->node.data(), g->degrees.data(),
+                                                 &g->mirror->h));
+            }
             sigb_check(sigb_matrix_create(g->mirror->h, &mirror));
             dirty = true;
         }
         upload();
+    }
+
+    // call A%copy_matrix(B, trans)   (ellpack_matrix_copy_matrix :169-198), on the device
+    void copy_matrix(linear_operator &B, bool trans = false)
+    {
+        const int nr = trans ? B.ncol : B.nrow, nc = trans ? B.nrow : B.ncol;
+        if (nrow != nr || ncol != nc) {
+            std::printf(" Attempted to copy a matrix of inconsistent dimensions\n Terminating.\n");
+            std::exit(1);
+        }
+        sigb_matrix_t h = nullptr;
+        sigb_check(sigb_matrix_copy(B.device_handle(), SIGB_FMT_ELLPACK, trans ? 1 : 0, &h));
+        int32_t n = 0, m = 0, md = 0;
+        int64_t ne = 0;
+        sigb_check(sigb_matrix_get_format(h, nullptr, &n, &m, &ne, &md));
+        g = std::make_shared<ellpack_graph>();
+        g->n = n;
+        g->m = m;
+        g->ne = (int)ne;
+        g->max_d = md;
+        g->node.assign((size_t)n * md, 0);
+        g->degrees.assign((size_t)n, 0);
+        val.assign((size_t)n * md, 0.0);
+        sigb_check(sigb_matrix_get_arrays(h, g->degrees.data(), g->node.data(), val.data()));
+        if (mirror) sigb_matrix_destroy(mirror);
+        mirror = h;
+        dirty = false;
     }
 };
 
