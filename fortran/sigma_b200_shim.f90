@@ -265,6 +265,16 @@ interface                                                                  !
         integer(c_int) :: stat
     end function
 
+    function sigb_matrix_add_values(A, count, i1, j1, z) &
+            & bind(c, name='sigb_matrix_add_values') result(stat)
+        import :: c_int, c_int32_t, c_int64_t, c_double, c_ptr
+        type(c_ptr), value :: A
+        integer(c_int64_t), value :: count
+        integer(c_int32_t), intent(in) :: i1(*), j1(*)
+        real(c_double), intent(in) :: z(*)
+        integer(c_int) :: stat
+    end function
+
     function sigb_matrix_retain(A) bind(c, name='sigb_matrix_retain') result(stat)
         import :: c_int, c_ptr
         type(c_ptr), value :: A
@@ -490,3 +500,15 @@ end module sigma_b200_shim
 !         endif
 !     ellpack_matrix_copy_matrix (ellpack_matrices.f90:169-198) likewise with
 !     frmt = 3 and A%g%degrees(n), A%g%node(max_d, n), A%val(max_d, n).
+!
+! --- src/matrix/formats/cs_matrices.f90, csr_matrix_add_multiple_values (:934-967)
+!     (csc and ellpack likewise): when every (is(k), js(l)) is in the pattern,
+!         n = size(is) * size(js)
+!         ii = [(is(k), l = 1, size(js)), k = 1, size(is))]     ! B(k, l) walked k outer, l inner
+!         jj = [(js(l), l = 1, size(js)), k = 1, size(is))]
+!         zz = [((B(k, l), l = 1, size(js)), k = 1, size(is))]
+!         call A%sync_mirror()
+!         call sigb_check( sigb_matrix_add_values(A%mirror, n, ii, jj, zz) )
+!         call sigb_check( sigb_matrix_get_arrays(A%mirror, dummy_ptr, dummy_node, A%val) )
+!     An assembly loop (examples/fem.f90:43-47) gathers its add_value calls into
+!     one such batch per mesh instead of one call per entry.

@@ -169,6 +169,22 @@ SIGB_API int sigb_matrix_get_format(sigb_matrix_t A, int *format,
 SIGB_API int sigb_matrix_get_arrays(sigb_matrix_t A, int32_t *ptr_or_degrees,
                                     int32_t *node, double *val);
 
+/* Assembly on the device: apply `call A%add_value(i1[c], j1[c], z[c])` for
+ * c = 0 .. count-1 IN ORDER (csr_matrix_add_value
+ * src/matrix/formats/cs_matrices.f90:868-891, csc_matrix_add_value :924-947,
+ * ellpack_matrix_add_value src/matrix/formats/ellpack_matrices.f90:471-493;
+ * add_multiple_values is the same statement over B(k, l), cs_matrices.f90:
+ * 934-967; the loop of examples/fem.f90:43-47 is such a stream).  Every stored
+ * entry receives its contributions in ascending call index, so the values
+ * are bit-identical to the serial loop.  All (i, j) must already be in the
+ * sparsity pattern: otherwise SIGB_ERR_ARG and nothing is added (the
+ * reference's reallocation path, cs_matrices.f90:888-890, is not mirrored).
+ * The device values are then ahead of the host copy: read them back with
+ * sigb_matrix_get_arrays. */
+SIGB_API int sigb_matrix_add_values(sigb_matrix_t A, int64_t count,
+                                    const int32_t *i1, const int32_t *j1,
+                                    const double *z);
+
 /* ---- matvec ------------------------------------------------------------ */
 
 /* linear_operator%matvec / matvec_t

@@ -24,7 +24,7 @@ __all__ = [
     "cg_solve", "bicgstab_solve", "lanczos", "generalized_lanczos", "eigensolve", "tridiag_eig",
     "partition_rows", "halo_build", "cs_set_value", "ell_set_value",
     "SUM", "PRODUCT", "ADJOINT", "COMPOSITE", "operator_sum", "operator_product", "adjoint",
-    "composite", "get_value", "matrix_entries", "copy_matrix",
+    "composite", "get_value", "matrix_entries", "copy_matrix", "add_values",
 ]
 
 
@@ -70,6 +70,7 @@ def lib():
         "orc_ell_set_value": (i32, [i32, _i32p, _i32p, _f64p, i32, i32, f64, i32]),
         "orc_ell_get_value": (f64, [i32, _i32p, _i32p, _f64p, i32, i32]),
         "orc_copy_matrix_values": (i64, [i32, i32, vp, _i32p, vp, _f64p, i64, _i32p, _i32p, _f64p, i32]),
+        "orc_add_values": (i64, [i32, i32, vp, _i32p, vp, _f64p, i64, _i32p, _i32p, _f64p]),
         "orc_matvec_add": (None, [mp, i32, _f64p, _f64p]),
         "orc_matvec": (None, [mp, i32, _f64p, _f64p]),
         "orc_get_value": (f64, [mp, i32, i32]),
@@ -276,6 +277,16 @@ def copy_matrix(B: Matrix, fmt, trans=False) -> Matrix:
                                         _f64(sv), int(trans))
     assert miss == 0
     return Matrix(fmt, nrow, ncol, node, val, ptr=ptr)
+
+
+def add_values(A: Matrix, ci, cj, cz):
+    """orc_add_values: apply `call A%add_value(ci[c], cj[c], cz[c])` for c = 0, 1, ... in
+    order, in place on A.val; returns the number of calls that missed the pattern."""
+    if A.format == ELL:
+        return int(lib().orc_add_values(ELL, A.max_d, None, A.node.reshape(-1), A.degrees.ctypes.data,
+                                        A.val.reshape(-1), len(ci), _i32(ci), _i32(cj), _f64(cz)))
+    return int(lib().orc_add_values(A.format, 0, A.ptr.ctypes.data, A.node, None, A.val, len(ci), _i32(ci),
+                                    _i32(cj), _f64(cz)))
 
 
 def matvec(A: Matrix, x, trans=False):

@@ -298,6 +298,33 @@ ORC_API int64_t orc_copy_matrix_values(int32_t target_format, int32_t max_d,
     return missing;
 }
 
+/*
+ * A stream of `call A%add_value(i, j, z)` statements applied in order --
+ * what an assembly loop does (examples/fem.f90:43-47) and what
+ * add_multiple_values does over B(k, l) (csr_matrix_add_multiple_values
+ * cs_matrices.f90:934-967).  Existing-entry branch of csr_matrix_add_value
+ * (cs_matrices.f90:868-891), csc_matrix_add_value (:924-947, scans column j)
+ * and ellpack_matrix_add_value (ellpack_matrices.f90:471-493): val = val + z.
+ * Returns the number of calls whose (i, j) is not in the pattern (the reference
+ * would take the reallocation path there; nothing is done for them here).
+ */
+ORC_API int64_t orc_add_values(int32_t format, int32_t max_d,
+                               const int32_t *ptr, const int32_t *node,
+                               const int32_t *degrees, double *val,
+                               int64_t count, const int32_t *ci,
+                               const int32_t *cj, const double *cz)
+{
+    int64_t c, missing = 0;
+    for (c = 0; c < count; c++) {
+        int32_t found;
+        if (format == 1)      found = orc_cs_set_value(ptr, node, val, ci[c], cj[c], cz[c], 1);
+        else if (format == 2) found = orc_cs_set_value(ptr, node, val, cj[c], ci[c], cz[c], 1);
+        else                  found = orc_ell_set_value(max_d, node, degrees, val, ci[c], cj[c], cz[c], 1);
+        if (!found) missing++;
+    }
+    return missing;
+}
+
 /* ------------------------------------------------------------------------ */
 /* matvec kernels                                                            */
 /* ------------------------------------------------------------------------ */

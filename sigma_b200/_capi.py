@@ -60,6 +60,7 @@ PROTOTYPES = {
     "sigb_matrix_copy": (C.c_int, [_vp, C.c_int, C.c_int, _pvp]),
     "sigb_matrix_get_format": (C.c_int, [_vp, C.POINTER(C.c_int), _pi32, _pi32, _pi64, _pi32]),
     "sigb_matrix_get_arrays": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "sigb_matrix_add_values": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
     "sigb_matvec": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "sigb_matvec_add": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "sigb_matvec_dev": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int]),

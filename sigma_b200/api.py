@@ -165,6 +165,15 @@ class Matrix:
         B.format = frmt
         return B
 
+    def add_values(self, i1, j1, z):
+        """`call A%add_value(i1[c], j1[c], z[c])` for c = 0, 1, ... in order, on the device
+        (cs_matrices.f90:868-891,924-947, ellpack_matrices.f90:471-493)."""
+        i1, j1, z = as_i32(i1), as_i32(j1), as_f64(z)
+        if not (i1.size == j1.size == z.size):
+            raise SigmaError(_capi.ERR_ARG, "add_values: i, j, z differ in length")
+        check(lib().sigb_matrix_add_values(self._h, i1.size, ptr(i1), ptr(j1), ptr(z)))
+        return self
+
     def arrays(self):
         """The stored arrays, read back from the device exactly as the Fortran holds them:
         ("csr"|"csc", ptr, node, val) or ("ellpack", degrees, node[n, max_d], val[n, max_d])."""

@@ -281,14 +281,12 @@ def composite_er_blocks(nn1=768, nn2=512, seed=11):
 # P1 finite-element Laplacian on a perturbed structured triangulation
 # (BASELINE config 4; element matrices per examples/fem.f90:28-49)
 # --------------------------------------------------------------------------
-def fem_p1_csr(N, seed=2024, jitter=0.25):
-    """Stiffness matrix of -Laplace on an N x N vertex grid, each cell split
-    into two triangles along a seeded random diagonal, interior vertices
-    jittered by <= jitter*h; Dirichlet rows/columns replaced by identity.
-
-    Graph build order: loop elements n, add_edge(ele(i,n), ele(j,n)) for
-    j = 1..3, i = 1..3 (the same nesting as the assembly loop fem.f90:43-47);
-    values accumulated in that element order.  Returns (ptr, node, val).
+def fem_p1_add_value_stream(N, seed=2024, jitter=0.25):
+    """The A%add_value(ele(i,n), ele(j,n), AE(i,j)) calls of laplacian2d
+    (examples/fem.f90:28-49) on an N x N vertex grid, each cell split into two
+    triangles along a seeded random diagonal, interior vertices jittered by
+    <= jitter*h.  Returns (I, J, V, interior) -- 0-based int64 vertex ids and the
+    element-matrix entries, in call order: element n, j outer, i inner (:43-47).
     """
     rng = np.random.Generator(np.random.PCG64(seed))
     h = 1.0 / (N - 1)
@@ -317,6 +315,18 @@ def fem_p1_csr(N, seed=2024, jitter=0.25):
     J = ele[:, :, None].repeat(3, 2)        # [n, j, i] -> ele(j)
     Vv = AE.transpose(0, 2, 1)              # [n, j, i] -> AE(i, j)
     I, J, Vv = I.reshape(-1), J.reshape(-1), Vv.reshape(-1)
+    return I, J, Vv, interior
+
+
+def fem_p1_csr(N, seed=2024, jitter=0.25):
+    """Stiffness matrix of -Laplace on an N x N vertex grid (see
+    fem_p1_add_value_stream); Dirichlet rows/columns replaced by identity.
+
+    Graph build order: loop elements n, add_edge(ele(i,n), ele(j,n)) for
+    j = 1..3, i = 1..3 (the same nesting as the assembly loop fem.f90:43-47);
+    values accumulated in that element order.  Returns (ptr, node, val).
+    """
+    I, J, Vv, interior = fem_p1_add_value_stream(N, seed, jitter)
     nv = N * N
     bnd = ~interior.reshape(-1)
     # first-occurrence order per row == ll_graph insertion order

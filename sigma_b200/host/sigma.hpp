@@ -209,6 +209,20 @@ struct device_matrix : linear_operator {
     sigb_matrix_t device_handle() override { sync_mirror(); return mirror; }
     virtual void set_value(int i, int j, dp z) = 0;
     virtual void add_value(int i, int j, dp z) = 0;
+    // A batch of `call A%add_value(is(c), js(c), zs(c))` applied IN ORDER on the device
+    // (an assembly loop, examples/fem.f90:43-47; add_multiple_values cs_matrices.f90:934-967);
+    // bit-identical to issuing the calls one by one.  The host copy of the values is
+    // refreshed from the device afterwards.
+    void add_values(const std::vector<int32_t> &is, const std::vector<int32_t> &js, const std::vector<dp> &zs)
+    {
+        if (is.size() != js.size() || is.size() != zs.size()) {
+            std::printf(" add_values: index and value arrays differ in length\n Terminating.\n");
+            std::exit(1);
+        }
+        sync_mirror();
+        sigb_check(sigb_matrix_add_values(mirror, (int64_t)is.size(), is.data(), js.data(), zs.data()));
+        sigb_check(sigb_matrix_get_arrays(mirror, nullptr, nullptr, val.data()));
+    }
     void zero() { for (dp &v : val) v = 0.0; dirty = true; }
     void scalar_multiply(dp alpha) { for (dp &v : val) v *= alpha; dirty = true; }
     void upload()

@@ -40,6 +40,35 @@ static int check(const char *name, M &A, const std::vector<dp> &B, int nn, rng64
     return 0;
 }
 
+// a batch of add_value calls on the device against the same calls issued one by one on the
+// host (csr_matrix_add_value cs_matrices.f90:868-891 and friends): bit-identical values
+template <class M>
+static int check_assembly(const char *name, const ll_graph &g, int nn, rng64 rnd)
+{
+    M A, B;
+    A.init(nn, nn); A.copy_graph(g);
+    B.init(nn, nn); B.copy_graph(g);
+    std::vector<int32_t> is, js;
+    std::vector<dp> zs;
+    for (int pass = 0; pass < 5; pass++)
+        for (int i = 1; i <= nn; i++)
+            for (int32_t j : g.get_neighbors(i)) {
+                is.push_back(i);
+                js.push_back(j);
+                zs.push_back((2 * rnd.next() - 1) * std::pow(10.0, (int)(rnd.next() * 12) - 6));
+            }
+    for (size_t c = 0; c < is.size(); c++) B.add_value(is[c], js[c], zs[c]);
+    A.add_values(is, js, zs);
+    for (size_t k = 0; k < A.val.size(); k++)
+        if (A.val[k] != B.val[k]) { std::printf(" %s add_values differs from the add_value loop at %zu\n", name, k); return 1; }
+    std::vector<dp> x(nn, 1.0), y(nn), z(nn);
+    A.matvec(x.data(), y.data());
+    B.matvec(x.data(), z.data());
+    for (int i = 0; i < nn; i++)
+        if (y[i] != z[i]) { std::printf(" %s matvec after add_values failed\n", name); return 1; }
+    return 0;
+}
+
 int main()
 {
     const int nn = 64;
@@ -68,6 +97,8 @@ int main()
         }
     if (A1.get_value(1, 1) != B[0] || A2.get_value(1, 1) != B[0] || A3.get_value(1, 1) != B[0]) { std::printf(" get_value failed\n"); return 1; }
     int rc = check("csr", A1, B, nn, rnd) | check("csc", A2, B, nn, rnd) | check("ellpack", A3, B, nn, rnd);
+    rc |= check_assembly<csr_matrix>("csr", g, nn, rnd) | check_assembly<csc_matrix>("csc", g, nn, rnd) |
+          check_assembly<ellpack_matrix>("ellpack", g, nn, rnd);
     // set_solver / set_preconditioner / A%solve facade (linear_operator_interface.f90:213-280)
     csr_matrix S;
     S.init(nn, nn);
