@@ -52,9 +52,15 @@ static int dev_alloc(T **p, size_t count)
 // upload the tile table of a CSR view
 int upload_tiles(CsrView &v, const std::vector<TileDesc> &tiles)
 {
+    // one allocation: the full table, then the sub-table of tiles that hold entries
+    std::vector<TileDesc> both(tiles);
+    for (const TileDesc &t : tiles)
+        if (t.ke > t.ks) both.push_back(t);
     v.ntiles = (int32_t)tiles.size();
-    SIGB_CHECK(dev_alloc(&v.tiles, tiles.size()));
-    SIGB_CUDA(cudaMemcpyAsync(v.tiles, tiles.data(), sizeof(TileDesc) * tiles.size(),
+    v.n_nonempty = (int32_t)(both.size() - tiles.size());
+    SIGB_CHECK(dev_alloc(&v.tiles, both.size()));
+    v.tiles_nonempty = v.tiles + v.ntiles;
+    SIGB_CUDA(cudaMemcpyAsync(v.tiles, both.data(), sizeof(TileDesc) * both.size(),
                               cudaMemcpyHostToDevice, ctx().stream));
     SIGB_CUDA(cudaStreamSynchronize(ctx().stream));
     return SIGB_OK;

@@ -98,6 +98,10 @@ struct CsrView {
     // halo column, boundary tiles do.
     TileDesc *tiles_interior = nullptr, *tiles_boundary = nullptr;
     int32_t n_interior = 0, n_boundary = 0;
+    // tiles that hold at least one stored entry (a view behind `tiles`): all an
+    // accumulating matvec has to visit when rows without entries leave y as it is
+    TileDesc *tiles_nonempty = nullptr;
+    int32_t n_nonempty = 0;
 };
 
 #ifndef SIGB_TILE_NNZ
@@ -178,6 +182,10 @@ struct DotSpec {
     const double *halo = nullptr;         // row-sharded: values of columns nloc+1.. (halo landing buffer)
     int32_t nloc = 0;                     // row-sharded: number of owned columns
     const struct HaloSync *sync = nullptr;  // peer-memory transport: flags to wait on / acknowledge
+    // y += A x only: the caller guarantees no y(i) is -0.0 (true of every y an
+    // expression has already written), so rows without entries -- y(i) + 0.0 in
+    // csr_matvec_add -- may be left untouched and tiles without entries skipped
+    bool y_no_negative_zero = false;
 };
 
 // Peer-memory halo exchange, fused into the SpMV kernel (comm.cu builds it).
@@ -204,7 +212,7 @@ struct HaloSync {
     int64_t dst_stride[kMaxRanks] = {};
 };
 
-// which: 0 = all tiles, 1 = interior subset, 2 = boundary subset
+// which: 0 = all tiles, 1 = interior subset, 2 = boundary subset, 3 = tiles with entries
 int launch_csr_spmv(const CsrView &A, const double *val, const double *x,
                     double *y, SpmvMode mode, const DotSpec &dot, int which = 0,
                     cudaStream_t stream = nullptr, int ticket = 0);

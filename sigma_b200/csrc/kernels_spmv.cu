@@ -279,6 +279,7 @@ static void fill_args(const CsrView &A, const double *val, const double *x, doub
     a.ntiles = A.ntiles;
     if (which == 1) { a.tiles = A.tiles_interior; a.ntiles = A.n_interior; }
     if (which == 2) { a.tiles = A.tiles_boundary; a.ntiles = A.n_boundary; }
+    if (which == 3) { a.tiles = A.tiles_nonempty; a.ntiles = A.n_nonempty; }
     a.x1 = x - 1;
     a.y = y;
     a.u = dot.u;
@@ -308,9 +309,16 @@ int launch_csr_spmv(const CsrView &A, const double *val, const double *x, double
                     SpmvMode mode, const DotSpec &dot, int which, cudaStream_t stream,
                     int ticket)
 {
+    const bool halo = dot.halo != nullptr || dot.sync != nullptr;
+    // Accumulating forms without fused dots only have to visit tiles that hold
+    // entries: csc_matvec_add (MODE_ACC_INIT) never touches a y(i) without
+    // contributions, and csr_matvec_add's y(i) = y(i) + 0.0 is the identity unless
+    // y(i) is -0.0, which the caller rules out with y_no_negative_zero.
+    if (which == 0 && !halo && dot.ndot == 0 && A.tiles_nonempty != nullptr &&
+        (mode == MODE_ACC_INIT || (mode == MODE_ADD_AFTER && dot.y_no_negative_zero)))
+        which = 3;
     CsrKernelArgs a = CsrKernelArgs();
     fill_args(A, val, x, y, dot, which, ticket, a);
-    const bool halo = dot.halo != nullptr || dot.sync != nullptr;
     cudaStream_t st = stream ? stream : ctx().stream;
     if (a.ntiles == 0 && dot.ndot == 0) return SIGB_OK;
 

@@ -127,7 +127,10 @@ diag_ell_kernel(const int32_t *__restrict__ node_sm, const double *__restrict__ 
     }
 }
 
-int apply(sigb_matrix_t A, int trans, const double *x, double *y, bool add_to_y, const int *skip);
+// y_clean: no y(i) is -0.0.  True of any y an expression has already written
+// (a row sum that starts from +0.0 is never -0.0, and y + z is -0.0 only when
+// both are), which lets the later contributions skip tiles without entries.
+int apply(sigb_matrix_t A, int trans, const double *x, double *y, bool add_to_y, const int *skip, bool y_clean);
 
 int apply_product(sigb_matrix_t A, int trans, const double *x, double *y, bool add_to_y, const int *skip)
 {
@@ -139,7 +142,7 @@ int apply_product(sigb_matrix_t A, int trans, const double *x, double *y, bool a
         sigb_matrix_t P = op->kids[(size_t)(trans ? step : nf - 1 - step)];
         const bool last = (step == nf - 1);
         double *dst = (last && !add_to_y) ? y : ((step & 1) ? op->z2 : op->z1);
-        SIGB_CHECK(apply(P, trans, src, dst, false, skip));
+        SIGB_CHECK(apply(P, trans, src, dst, false, skip, false));
         src = dst;
     }
     if (add_to_y) {
@@ -149,21 +152,22 @@ int apply_product(sigb_matrix_t A, int trans, const double *x, double *y, bool a
     return SIGB_OK;
 }
 
-int apply(sigb_matrix_t A, int trans, const double *x, double *y, bool add_to_y, const int *skip)
+int apply(sigb_matrix_t A, int trans, const double *x, double *y, bool add_to_y, const int *skip, bool y_clean)
 {
     OpInfo *op = A->op;
     if (!op) {
         DotSpec d;
         d.skip_flag = skip;
+        d.y_no_negative_zero = add_to_y && y_clean;
         return matvec_dev(A, trans, x, y, MODE_SET, add_to_y, d);
     }
     switch (op->kind) {
     case OP_SUM:
         for (size_t k = 0; k < op->kids.size(); k++)
-            SIGB_CHECK(apply(op->kids[k], trans, x, y, add_to_y || k > 0, skip));
+            SIGB_CHECK(apply(op->kids[k], trans, x, y, add_to_y || k > 0, skip, y_clean || k > 0));
         return SIGB_OK;
     case OP_ADJOINT:
-        return apply(op->kids[0], !trans, x, y, add_to_y, skip);
+        return apply(op->kids[0], !trans, x, y, add_to_y, skip, y_clean);
     case OP_PRODUCT:
         return apply_product(A, trans, x, y, add_to_y, skip);
     default: {
@@ -172,12 +176,12 @@ int apply(sigb_matrix_t A, int trans, const double *x, double *y, bool add_to_y,
             for (int it = 0; it < nr; it++)          // :1086
                 for (int jt = 0; jt < nc; jt++)      // :1090
                     SIGB_CHECK(apply(op->kids[(size_t)it * nc + jt], 0, x + (op->col_ptr[(size_t)jt] - 1),
-                                     y + (op->row_ptr[(size_t)it] - 1), add_to_y || jt > 0, skip));
+                                     y + (op->row_ptr[(size_t)it] - 1), add_to_y || jt > 0, skip, y_clean || jt > 0));
         } else {
             for (int jt = 0; jt < nc; jt++)          // :1115
                 for (int it = 0; it < nr; it++)      // :1119
                     SIGB_CHECK(apply(op->kids[(size_t)it * nc + jt], 1, x + (op->row_ptr[(size_t)it] - 1),
-                                     y + (op->col_ptr[(size_t)jt] - 1), add_to_y || it > 0, skip));
+                                     y + (op->col_ptr[(size_t)jt] - 1), add_to_y || it > 0, skip, y_clean || it > 0));
         }
         return SIGB_OK;
     }
@@ -261,7 +265,7 @@ int diag_range(sigb_matrix_t A, int64_t roff, int64_t coff, int64_t lo, int64_t 
 // SpMV epilogue does for a leaf: optional row scaling and up to two dots.
 int op_matvec(sigb_matrix_t A, int trans, const double *x, double *y, bool add_to_y, const DotSpec &dot)
 {
-    SIGB_CHECK(apply(A, trans, x, y, add_to_y, dot.skip_flag));
+    SIGB_CHECK(apply(A, trans, x, y, add_to_y, dot.skip_flag, false));
     const int64_t n = trans ? A->ncol : A->nrow;
     if (dot.ndot == 0 && !dot.row_scale) return SIGB_OK;
     SIGB_REQUIRE(!add_to_y || !dot.row_scale, SIGB_ERR_ARG, "row scaling needs the overwrite form");

@@ -20,7 +20,8 @@
 //
 // Steps: histogram of targets -> exclusive scan (1-based ptr) -> unordered
 // placement with atomics -> per-row sort of the placed source indices (rows
-// are short; the sort makes the result deterministic) -> gather of line ids.
+// are short; the sort makes the result deterministic; the few rows longer than
+// kLongRow are listed and rank-sorted by one CTA each) -> gather of line ids.
 #include "device_utils.cuh"
 
 namespace sigb {
@@ -146,11 +147,17 @@ place_ell_kernel(const int32_t *__restrict__ node_sm, int32_t n, int32_t n_pad, 
 constexpr int kLongRow = 96;
 
 __global__ void __launch_bounds__(kThreads)
-sort_rows_kernel(const int32_t *__restrict__ ptr_t1, int32_t nrows, int32_t *__restrict__ perm)
+sort_rows_kernel(const int32_t *__restrict__ ptr_t1, int32_t nrows, int32_t *__restrict__ perm,
+                 int32_t *__restrict__ long_rows, int32_t *__restrict__ n_long)
 {
     for (int32_t r = blockIdx.x * kThreads + threadIdx.x; r < nrows; r += gridDim.x * kThreads) {
         const int32_t b = ptr_t1[r] - 1, e = ptr_t1[r + 1] - 1;
-        if (e - b > kLongRow) continue;
+        if (e - b > kLongRow) {
+            // left to sort_long_rows_kernel, which only visits the rows listed here
+            // (their order in the list does not matter: each is sorted on its own)
+            long_rows[atomicAdd(n_long, 1)] = r;
+            continue;
+        }
         for (int32_t a = b + 1; a < e; a++) {
             const int32_t key = perm[a];
             int32_t c = a - 1;
@@ -165,12 +172,12 @@ sort_rows_kernel(const int32_t *__restrict__ ptr_t1, int32_t nrows, int32_t *__r
 
 // One CTA per long row: rank sort (keys are distinct) through a scratch copy.
 __global__ void __launch_bounds__(kThreads)
-sort_long_rows_kernel(const int32_t *__restrict__ ptr_t1, int32_t nrows,
+sort_long_rows_kernel(const int32_t *__restrict__ ptr_t1, const int32_t *__restrict__ long_rows, int32_t n_long,
                       int32_t *__restrict__ perm, int32_t *__restrict__ scratch)
 {
-    for (int32_t r = blockIdx.x; r < nrows; r += gridDim.x) {
+    for (int32_t l = blockIdx.x; l < n_long; l += gridDim.x) {
+        const int32_t r = long_rows[l];
         const int32_t b = ptr_t1[r] - 1, e = ptr_t1[r + 1] - 1;
-        if (e - b <= kLongRow) continue;
         for (int32_t a = b + threadIdx.x; a < e; a += kThreads) scratch[a] = perm[a];
         __syncthreads();
         for (int32_t a = b + threadIdx.x; a < e; a += kThreads) {
@@ -287,14 +294,33 @@ namespace {
 int finish_transpose(int32_t ntargets, int64_t ne, int32_t *ptr_t, int32_t *perm)
 {
     cudaStream_t st = ctx().stream;
-    sort_rows_kernel<<<grid_for(ntargets), kThreads, 0, st>>>(ptr_t, ntargets, perm);
+    // rows longer than kLongRow are listed by the first kernel; at most ne / kLongRow of them
+    const int64_t max_long = ne / kLongRow + 1;
+    int32_t *long_rows = nullptr, *n_long = nullptr;
+    SIGB_CUDA(cudaMalloc(&long_rows, sizeof(int32_t) * (size_t)max_long));
+    SIGB_CUDA(cudaMalloc(&n_long, sizeof(int32_t)));
+    SIGB_CUDA(cudaMemsetAsync(n_long, 0, sizeof(int32_t), st));
+    sort_rows_kernel<<<grid_for(ntargets), kThreads, 0, st>>>(ptr_t, ntargets, perm, long_rows, n_long);
+    count_launch();
+    int32_t h_long = 0;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_long, n_long, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     int32_t *scratch = nullptr;
-    SIGB_CUDA(cudaMalloc(&scratch, sizeof(int32_t) * (size_t)(ne > 0 ? ne : 1)));
-    sort_long_rows_kernel<<<ctx().num_sms * 4, kThreads, 0, st>>>(ptr_t, ntargets, perm, scratch);
-    count_launch(2);
-    SIGB_CUDA(cudaGetLastError());
-    SIGB_CUDA(cudaStreamSynchronize(st));
-    SIGB_CUDA(cudaFree(scratch));
+    if (e == cudaSuccess && h_long > 0) {
+        e = cudaMalloc(&scratch, sizeof(int32_t) * (size_t)(ne > 0 ? ne : 1));
+        if (e == cudaSuccess) {
+            const int grid = h_long < ctx().num_sms * 4 ? h_long : ctx().num_sms * 4;
+            sort_long_rows_kernel<<<grid, kThreads, 0, st>>>(ptr_t, long_rows, h_long, perm, scratch);
+            count_launch();
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    cudaFree(scratch);
+    cudaFree(long_rows);
+    cudaFree(n_long);
+    if (e != cudaSuccess) return cuda_fail(e, "finish_transpose", __FILE__, __LINE__);
     return SIGB_OK;
 }
 

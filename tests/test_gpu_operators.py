@@ -181,6 +181,51 @@ def test_composite_rectangular_blocks_and_nesting(sb, orc):
     all_four(AA, OO, orc, x2, xt2, rng.standard_normal(2 * nr), rng.standard_normal(2 * nc))
 
 
+def test_composite_with_nearly_empty_blocks_and_signed_zeros(sb, orc):
+    """2-D Poisson 256^2 cut into 2 x 2 blocks: the off-diagonal blocks hold 256 entries in
+    32 768 rows, so almost all of their row tiles are empty and are skipped by the
+    accumulating contributions.  Still bit for bit the reference's block loops -- including
+    the sign of zero: csr_matvec_add does y(i) = y(i) + 0.0 for a row without entries, which
+    turns a -0.0 the CALLER passed into +0.0 (only the first contribution can meet one)."""
+    N = 256
+    n, h = N * N, N * N // 2
+    ptr, node, val = G.poisson2d_csr(N)
+    rows = np.repeat(np.arange(n), np.diff(ptr))
+    cols = node.astype(np.int64) - 1
+    blocks, oblocks = [], []
+    for r0, r1 in ((0, h), (h, n)):
+        brow, orow = [], []
+        for c0, c1 in ((0, h), (h, n)):
+            m = (rows >= r0) & (rows < r1) & (cols >= c0) & (cols < c1)
+            bptr = np.concatenate([[1], 1 + np.cumsum(np.bincount(rows[m] - r0, minlength=r1 - r0))]).astype(np.int32)
+            b, o = both(sb, orc, "csr", r1 - r0, c1 - c0, bptr, (cols[m] - c0 + 1).astype(np.int32), val[m])
+            brow.append(b)
+            orow.append(o)
+        blocks.append(brow)
+        oblocks.append(orow)
+    A = sb.sparse_matrix([h, n - h], [h, n - h], blocks)
+    O = orc.composite([h, n - h], [h, n - h], oblocks)
+    rng = np.random.default_rng(8)
+    x, y0 = rng.standard_normal(n), rng.standard_normal(n)
+    all_four(A, O, orc, x, x, y0, y0)
+    # close to the monolithic operator (rows cut by the block boundary add in another order)
+    mono = sb.csr_matrix(n, n, ptr, node, val)
+    assert np.abs(A.matvec(x) - mono.matvec(x)).max() <= 1e-13
+    # signed zeros: x = 0 makes every row sum +0.0; y0 = -0.0 everywhere
+    zero, negz = np.zeros(n), np.full(n, -0.0)
+    for trans in (False, True):
+        got = A.matvec_add(zero, negz, trans=trans)
+        want = orc.matvec_add(O, zero, negz, trans=trans)
+        assert np.array_equal(got, want) and np.array_equal(np.signbit(got), np.signbit(want))
+    # ... and a lone off-diagonal block (rows without entries) as its own operator
+    B12, O12 = blocks[0][1], oblocks[0][1]
+    for trans in (False, True):
+        nin, nout = (h, n - h) if trans else (n - h, h)
+        got = B12.matvec_add(np.zeros(nin), np.full(nout, -0.0), trans=trans)
+        want = orc.matvec_add(O12, np.zeros(nin), np.full(nout, -0.0), trans=trans)
+        assert np.array_equal(np.signbit(got), np.signbit(want))
+
+
 def test_expression_outlives_its_operands(sb, orc):
     """The expression holds references on its operands (add_reference,
     linear_operator_sums.f90:66-67): destroying the caller's handles first is safe."""
