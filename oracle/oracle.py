@@ -24,7 +24,7 @@ __all__ = [
     "cg_solve", "bicgstab_solve", "lanczos", "generalized_lanczos", "eigensolve", "tridiag_eig",
     "partition_rows", "halo_build", "cs_set_value", "ell_set_value",
     "SUM", "PRODUCT", "ADJOINT", "COMPOSITE", "operator_sum", "operator_product", "adjoint",
-    "composite", "get_value", "matrix_entries", "copy_matrix", "add_values",
+    "composite", "get_value", "matrix_entries", "copy_matrix", "add_values", "Ldu", "ldu_setup", "ldu_solve", "cg_solve_ldu",
 ]
 
 
@@ -71,6 +71,10 @@ def lib():
         "orc_ell_get_value": (f64, [i32, _i32p, _i32p, _f64p, i32, i32]),
         "orc_copy_matrix_values": (i64, [i32, i32, vp, _i32p, vp, _f64p, i64, _i32p, _i32p, _f64p, i32]),
         "orc_add_values": (i64, [i32, i32, vp, _i32p, vp, _f64p, i64, _i32p, _i32p, _f64p]),
+        "orc_ldu_factor": (None, [i32, i64, _i32p, _i32p, _f64p, _i32p, _i32p, _f64p, _i32p, _i32p, _f64p, _f64p]),
+        "orc_ldu_solve": (None, [i32, _i32p, _i32p, _f64p, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p]),
+        "orc_cg_solve_ldu": (i64, [mp, _f64p, _f64p, _i32p, _i32p, _f64p, _i32p, _i32p, _f64p, _f64p, f64, i64,
+                                   _f64p, C.POINTER(f64), C.POINTER(i32)]),
         "orc_matvec_add": (None, [mp, i32, _f64p, _f64p]),
         "orc_matvec": (None, [mp, i32, _f64p, _f64p]),
         "orc_get_value": (f64, [mp, i32, i32]),
@@ -287,6 +291,58 @@ def add_values(A: Matrix, ci, cj, cz):
                                         A.val.reshape(-1), len(ci), _i32(ci), _i32(cj), _f64(cz)))
     return int(lib().orc_add_values(A.format, 0, A.ptr.ctypes.data, A.node, None, A.val, len(ci), _i32(ci),
                                     _i32(cj), _f64(cz)))
+
+
+class Ldu:
+    """sparse_ldu_solver after setup (ldu_solvers.f90:35-58): strict-triangular csr factors
+    L, U (unit diagonals implied) and the diagonal D."""
+
+    def __init__(self, n, Lptr, Lnode, Lval, Uptr, Unode, Uval, D):
+        self.n = n
+        self.Lptr, self.Lnode, self.Lval = Lptr, Lnode, Lval
+        self.Uptr, self.Unode, self.Uval = Uptr, Unode, Uval
+        self.D = D
+
+    @property
+    def args(self):
+        return (self.Lptr, self.Lnode, self.Lval, self.Uptr, self.Unode, self.Uval, self.D)
+
+
+def ldu_setup(A: Matrix) -> Ldu:
+    """pc => ldu(); call pc%setup(A) (sparse_ldu_setup ldu_solvers.f90:95-130):
+    incomplete_ldu_sparsity_pattern (:396-441: ll_graph add_edge in A's iteration order,
+    then L%init / U%init copy the ll_graphs to cs graphs) and the numeric factorisation
+    (:275-387)."""
+    n = A.nrow
+    ai, aj, av = matrix_entries(A)
+    lo, up = ai > aj, aj > ai
+
+    def pattern(mask):
+        si, sj, _ = ll_graph_edges(n, ai[mask], aj[mask])
+        ptr, node, _ = cs_graph_build(n, si, sj)
+        return ptr, node
+
+    Lptr, Lnode = pattern(lo)
+    Uptr, Unode = pattern(up)
+    Lval, Uval, D = np.zeros(Lnode.size), np.zeros(Unode.size), np.zeros(n)
+    lib().orc_ldu_factor(n, ai.size, _i32(ai), _i32(aj), _f64(av), Lptr, Lnode, Lval, Uptr, Unode, Uval, D)
+    return Ldu(n, Lptr, Lnode, Lval, Uptr, Unode, Uval, D)
+
+
+def ldu_solve(F: Ldu, b):
+    """call pc%solve(A, x, b) (ldu_solve ldu_solvers.f90:160-176)."""
+    x = np.empty(F.n)
+    lib().orc_ldu_solve(F.n, *F.args, x, _f64(b))
+    return x
+
+
+def cg_solve_ldu(A, x0, b, F: Ldu, tol=1e-16, max_iter=-1):
+    """orc_cg_solve_ldu: call solver%solve(A, x, b, pc) with pc = ldu() -> (x, iterations, res2, capped)."""
+    x = _f64(x0).copy()
+    work = np.zeros(4 * A.nrow)
+    res2, capped = C.c_double(0.0), C.c_int32(0)
+    it = lib().orc_cg_solve_ldu(A.c, x, _f64(b), *F.args, tol, max_iter, work, C.byref(res2), C.byref(capped))
+    return x, int(it), res2.value, bool(capped.value)
 
 
 def matvec(A: Matrix, x, trans=False):

@@ -699,6 +699,136 @@ ORC_API int64_t orc_cg_solve_jacobi(const orc_matrix *A, double *x,
 }
 
 /* ------------------------------------------------------------------------ */
+/* ILDU(0): incomplete A ~= (I + L) D (I + U)                                */
+/* ------------------------------------------------------------------------ */
+
+/*
+ * sparse_static_pattern_ldu_factorization, src/solver/ldu_solvers.f90:275-387.
+ * L and U are csr matrices holding the STRICT lower / upper parts (unit
+ * diagonals are implied); their patterns come from
+ * incomplete_ldu_sparsity_pattern (:396-441): ll_graph add_edge(i, j) calls in
+ * A's iteration order, i.e. row i of L / U lists row i's lower / upper
+ * neighbours in the order A's iterator produced them -- unsorted, and the
+ * elimination below walks them in that stored order (:330-331), exactly as
+ * restated here.
+ *
+ * in : (ai, aj, av)[ne] = A's entry stream in iteration order
+ * out: Lval, D, Uval (patterns Lptr/Lnode, Uptr/Unode given, 1-based)
+ */
+static double ldu_get(const int32_t *ptr, const int32_t *node, const double *val, int32_t i, int32_t j)
+{
+    return orc_cs_get_value(ptr, node, val, i, j);
+}
+
+ORC_API void orc_ldu_factor(int32_t n, int64_t ne, const int32_t *ai,
+                            const int32_t *aj, const double *av,
+                            const int32_t *Lptr, const int32_t *Lnode, double *Lval,
+                            const int32_t *Uptr, const int32_t *Unode, double *Uval,
+                            double *D)
+{
+    int64_t e;
+    int32_t i, ind1, ind2;
+    for (e = 0; e < Lptr[n] - 1; e++) Lval[e] = 0.0;                 /* call L%zero()  :302 */
+    for (e = 0; e < Uptr[n] - 1; e++) Uval[e] = 0.0;                 /* call U%zero()  :303 */
+    for (i = 0; i < n; i++) D[i] = 0.0;                              /* :304 */
+    for (e = 0; e < ne; e++) {                                       /* copy A into L, D, U  :307-324 */
+        if (ai[e] > aj[e])      orc_cs_set_value(Lptr, Lnode, Lval, ai[e], aj[e], av[e], 0);
+        else if (aj[e] > ai[e]) orc_cs_set_value(Uptr, Unode, Uval, ai[e], aj[e], av[e], 0);
+        else                    D[ai[e] - 1] = av[e];
+    }
+    for (i = 1; i <= n; i++) {                                       /* :331 */
+        const int32_t lb = Lptr[i - 1] - 1, dl = Lptr[i] - 1 - lb;
+        const int32_t ub = Uptr[i - 1] - 1, du = Uptr[i] - 1 - ub;
+        for (ind1 = 0; ind1 < dl; ind1++) {                          /* :339 */
+            const int32_t k = Lnode[lb + ind1];
+            double Lik = ldu_get(Lptr, Lnode, Lval, i, k);           /* :342 */
+            const double Uki = ldu_get(Uptr, Unode, Uval, k, i);     /* :343 */
+            orc_cs_set_value(Lptr, Lnode, Lval, i, k, Lik / D[k - 1], 0);   /* :345 */
+            Lik = Lik / D[k - 1];                                    /* :346 */
+            for (ind2 = 0; ind2 < dl; ind2++) {                      /* :350 */
+                const int32_t j = Lnode[lb + ind2];
+                if (j > k) {
+                    const double Ukj = ldu_get(Uptr, Unode, Uval, k, j);        /* :355 */
+                    orc_cs_set_value(Lptr, Lnode, Lval, i, j, -(Lik * D[k - 1] * Ukj), 1);   /* :356 */
+                }
+            }
+            D[i - 1] = D[i - 1] - Lik * D[k - 1] * Uki;              /* :361 */
+            for (ind2 = 0; ind2 < du; ind2++) {                      /* :364 */
+                const int32_t j = Unode[ub + ind2];
+                const double Ukj = ldu_get(Uptr, Unode, Uval, k, j);            /* :366 */
+                orc_cs_set_value(Uptr, Unode, Uval, i, j, -(Lik * D[k - 1] * Ukj), 1);       /* :367 */
+            }
+        }
+        for (ind2 = 0; ind2 < du; ind2++) {                          /* :373 */
+            const int32_t k = Unode[ub + ind2];
+            const double Uik = ldu_get(Uptr, Unode, Uval, i, k);
+            orc_cs_set_value(Uptr, Unode, Uval, i, k, Uik / D[i - 1], 0);       /* :376 */
+        }
+    }
+}
+
+/* ldu_solve, src/solver/ldu_solvers.f90:160-176: x = b ; (I + L) x = x ;
+ * x = x / D ; (I + U) x = x, with lower_triangular_solve (:208-235) and
+ * upper_triangular_solve (:240-263): rows in order, each row's entries in
+ * stored order, z = z - val * x(j). */
+ORC_API void orc_ldu_solve(int32_t n, const int32_t *Lptr, const int32_t *Lnode, const double *Lval,
+                           const int32_t *Uptr, const int32_t *Unode, const double *Uval,
+                           const double *D, double *x, const double *b)
+{
+    int32_t i, k;
+    for (i = 0; i < n; i++) x[i] = b[i];
+    for (i = 1; i <= n; i++) {
+        double z = x[i - 1];
+        for (k = Lptr[i - 1]; k <= Lptr[i] - 1; k++) z = z - Lval[k - 1] * x[Lnode[k - 1] - 1];
+        x[i - 1] = z;
+    }
+    for (i = 0; i < n; i++) x[i] = x[i] / D[i];
+    for (i = n; i >= 1; i--) {
+        double z = x[i - 1];
+        for (k = Uptr[i - 1]; k <= Uptr[i] - 1; k++) z = z - Uval[k - 1] * x[Unode[k - 1] - 1];
+        x[i - 1] = z;
+    }
+}
+
+/* cg_solve_pc, src/solver/cg_solvers.f90:155-194 with pc = sparse_ldu_solver. */
+ORC_API int64_t orc_cg_solve_ldu(const orc_matrix *A, double *x, const double *b,
+                                 const int32_t *Lptr, const int32_t *Lnode, const double *Lval,
+                                 const int32_t *Uptr, const int32_t *Unode, const double *Uval,
+                                 const double *D, double tolerance, int64_t max_iter,
+                                 double *work, double *res2_out, int32_t *capped)
+{
+    const int32_t n = A->nrow;
+    double *p = work, *q = work + n, *r = work + 2 * (int64_t)n, *z = work + 3 * (int64_t)n;
+    double alpha, beta, res2, dpr;
+    int64_t it = 0;
+    int32_t i;
+
+    if (capped) *capped = 0;
+    for (i = 0; i < n; i++) z[i] = x[i];                 /* :167 */
+    orc_matvec(A, 0, z, q);                              /* :168 */
+    for (i = 0; i < n; i++) r[i] = b[i] - q[i];          /* :169 */
+    orc_ldu_solve(n, Lptr, Lnode, Lval, Uptr, Unode, Uval, D, z, r);   /* :170 */
+    for (i = 0; i < n; i++) p[i] = z[i];                 /* :171 */
+    res2 = dot(r, z, n);                                 /* :172 */
+    while (sqrt(res2) > tolerance) {                     /* :174 */
+        if (max_iter >= 0 && it >= max_iter) { if (capped) *capped = 1; break; }
+        orc_matvec(A, 0, p, q);
+        dpr = dot(p, q, n);
+        alpha = res2 / dpr;
+        for (i = 0; i < n; i++) x[i] = x[i] + alpha * p[i];
+        for (i = 0; i < n; i++) r[i] = r[i] - alpha * q[i];
+        orc_ldu_solve(n, Lptr, Lnode, Lval, Uptr, Unode, Uval, D, z, r);   /* :181 */
+        dpr = dot(r, z, n);
+        beta = dpr / res2;
+        for (i = 0; i < n; i++) p[i] = z[i] + beta * p[i];
+        res2 = dpr;
+        it++;
+    }
+    if (res2_out) *res2_out = res2;
+    return it;
+}
+
+/* ------------------------------------------------------------------------ */
 /* BiCGSTAB                                                                  */
 /* ------------------------------------------------------------------------ */
 
