@@ -258,6 +258,49 @@ SIGB_API int sigb_bicgstab_create(double tolerance, sigb_solver_t *s);
 /* jacobi() (src/solver/jacobi_solvers.f90:26-32). */
 SIGB_API int sigb_jacobi_create(sigb_solver_t *s);
 
+/* ldu(incomplete, level) (src/solver/ldu_solvers.f90:73-86): always the
+ * incomplete factorisation of level 0, like the reference (:145,151).
+ * A ~= (I + L) D (I + U) on the strict triangles of A's own pattern.
+ *  - sigb_solver_setup(s, A): sparse_ldu_setup (:95-130) -- the patterns of
+ *    L and U (incomplete_ldu_sparsity_pattern :396-441) and the level schedules
+ *    once per pattern, the numeric factorisation
+ *    (sparse_static_pattern_ldu_factorization :275-387) on every call.  A must
+ *    be a stored csr / csc / ellpack matrix on one GPU.
+ *  - sigb_solver_solve(s, A, x, b, NULL): ldu_solve (:160-176), x = b, forward
+ *    solve with I + L, x = x / D, backward solve with I + U.
+ *  - as the pc of a cg solver: cg_solve_pc (cg_solvers.f90:155-194) calls it
+ *    once per iteration.
+ * Rows that do not depend on each other run concurrently (level scheduling);
+ * each row does the reference's arithmetic in the reference's order, so
+ * factors and solves are bit-identical to the serial loops. */
+SIGB_API int sigb_ldu_create(sigb_solver_t *s);
+/* Sizes of the factors after setup: n rows, nL / nU stored entries of L / U,
+ * and how many row levels the forward / backward sweeps take. */
+SIGB_API int sigb_ldu_get_sizes(sigb_solver_t s, int32_t *n, int64_t *nL,
+                                int64_t *nU, int32_t *n_forward_levels,
+                                int32_t *n_backward_levels);
+/* Read the factors back (parity checks): csr patterns 1-based (n + 1 / nL /
+ * nU entries), values, D(n).  Any pointer may be NULL. */
+SIGB_API int sigb_ldu_get_factors(sigb_solver_t s, int32_t *Lptr1,
+                                  int32_t *Lnode1, double *Lval,
+                                  int32_t *Uptr1, int32_t *Unode1,
+                                  double *Uval, double *D);
+/* Host-only index work behind the setup (no GPU needed; bit-exact contract with
+ * the oracle's restatement of incomplete_ldu_sparsity_pattern): from the rows
+ * of A in iteration order (ptr1 n+1, node1 ne, 1-based) build the patterns,
+ * the destination of every entry of A in the combined value array
+ * [ Lval | Uval | D ] (0-based) and the level schedules: rows (1-based)
+ * grouped by level, level l = rows[lev[l] .. lev[l+1]).  Output arrays are
+ * sized by the caller: ptr arrays and level pointers n + 1, node arrays and
+ * dest ne, row lists n. */
+SIGB_API int sigb_ldu_symbolic(int32_t n, const int32_t *ptr1,
+                               const int32_t *node1, int32_t *Lptr1,
+                               int32_t *Lnode1, int32_t *Uptr1, int32_t *Unode1,
+                               int64_t *dest, int32_t *forward_rows,
+                               int32_t *forward_lev, int32_t *n_forward_levels,
+                               int32_t *backward_rows, int32_t *backward_lev,
+                               int32_t *n_backward_levels);
+
 /* solver%setup(A): cg_setup cg_solvers.f90:52-90, bicgstab_setup
  * bicgstab_solvers.f90:52-100 (allocate + zero work vectors, iterations = 0),
  * jacobi_setup jacobi_solvers.f90:37-63 (idiag(i) = 1 / A(i,i)). */
@@ -273,9 +316,10 @@ SIGB_API int sigb_solver_set_max_iterations(sigb_solver_t s, int64_t cap);
 /* solver%solve(A, x, b [, pc]): linear_solve / linear_solve_pc
  * (cg_solve cg_solvers.f90:116-150, cg_solve_pc :155-194, bicgstab_solve
  * bicgstab_solvers.f90:124-177, bicgstab_solve_pc :182-237, jacobi_solve
- * jacobi_solvers.f90:68-81).  x is the initial guess on entry and the
- * solution on return.  pc may be NULL; the only device preconditioner is
- * jacobi (anything else is SIGB_ERR_UNSUPPORTED).  The whole iteration runs
+ * jacobi_solvers.f90:68-81, ldu_solve ldu_solvers.f90:160-176).  x is the
+ * initial guess on entry and the solution on return.  pc may be NULL; the
+ * device preconditioners are jacobi (cg, bicgstab) and ldu (cg, one GPU);
+ * anything else is SIGB_ERR_UNSUPPORTED.  The whole iteration runs
  * on the device; the loop stops at the same test as the reference,
  * evaluated every iteration. */
 SIGB_API int sigb_solver_solve(sigb_solver_t s, sigb_matrix_t A, double *x,

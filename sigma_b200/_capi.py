@@ -73,6 +73,10 @@ PROTOTYPES = {
     "sigb_cg_create": (C.c_int, [_f64, _pvp]),
     "sigb_bicgstab_create": (C.c_int, [_f64, _pvp]),
     "sigb_jacobi_create": (C.c_int, [_pvp]),
+    "sigb_ldu_create": (C.c_int, [_pvp]),
+    "sigb_ldu_get_sizes": (C.c_int, [_vp, _pi32, _pi64, _pi64, _pi32, _pi32]),
+    "sigb_ldu_get_factors": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sigb_ldu_symbolic": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _pi32, _vp, _vp, _pi32]),
     "sigb_solver_setup": (C.c_int, [_vp, _vp]),
     "sigb_solver_set_params": (C.c_int, [_vp, _f64]),
     "sigb_solver_set_max_iterations": (C.c_int, [_vp, _i64]),

@@ -31,7 +31,7 @@ import numpy as np
 from . import _capi
 from ._capi import ROW, COL, SigmaError, as_f64, as_i32, check, lib, ptr
 
-__all__ = ["init", "Graph", "Matrix", "Solver", "cg", "bicgstab", "jacobi", "lanczos", "eigensolve",
+__all__ = ["init", "Graph", "Matrix", "Solver", "cg", "bicgstab", "jacobi", "ldu", "ldu_symbolic", "lanczos", "eigensolve",
            "generalized_lanczos", "generalized_eigensolve",
            "csr_matrix", "csc_matrix", "ellpack_matrix", "SigmaError", "launch_count", "set_stream",
            "synchronize", "Expression", "operator_sum", "operator_product", "adjoint", "sparse_matrix"]
@@ -283,6 +283,8 @@ class Solver:
             check(lib().sigb_bicgstab_create(tol, C.byref(h)))
         elif kind == "jacobi":
             check(lib().sigb_jacobi_create(C.byref(h)))
+        elif kind == "ldu":
+            check(lib().sigb_ldu_create(C.byref(h)))
         else:
             raise ValueError(kind)
         self.kind, self._h = kind, h
@@ -321,6 +323,17 @@ class Solver:
         check(lib().sigb_solver_get_vector(self._h, name.encode(), ptr(out)))
         return out
 
+    def factors(self):
+        """ldu only: (Lptr, Lnode, Lval, Uptr, Unode, Uval, D, forward levels, backward levels)."""
+        n, nL, nU, nf, nb = C.c_int32(), C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
+        check(lib().sigb_ldu_get_sizes(self._h, C.byref(n), C.byref(nL), C.byref(nU), C.byref(nf), C.byref(nb)))
+        Lptr, Uptr = np.empty(n.value + 1, np.int32), np.empty(n.value + 1, np.int32)
+        Lnode, Unode = np.empty(nL.value, np.int32), np.empty(nU.value, np.int32)
+        Lval, Uval, D = np.empty(nL.value), np.empty(nU.value), np.empty(n.value)
+        check(lib().sigb_ldu_get_factors(self._h, ptr(Lptr), ptr(Lnode), ptr(Lval), ptr(Uptr), ptr(Unode),
+                                         ptr(Uval), ptr(D)))
+        return Lptr, Lnode, Lval, Uptr, Unode, Uval, D, nf.value, nb.value
+
     def destroy(self):
         if self._h:
             check(lib().sigb_solver_destroy(self._h))
@@ -343,6 +356,31 @@ def bicgstab(tolerance=None):
 
 def jacobi():
     return Solver("jacobi")
+
+
+def ldu(incomplete=True, level=0):
+    """pc => ldu(incomplete, level) (ldu_solvers.f90:73-86); like the reference, always the
+    incomplete factorisation of level 0 whatever is asked for (:145,151)."""
+    return Solver("ldu")
+
+
+def ldu_symbolic(n, ptr1, node1):
+    """Host-only index work of the ldu setup (no GPU): patterns of L and U, destinations of A's
+    entries in [Lval | Uval | D], forward / backward level schedules."""
+    ptr1, node1 = as_i32(ptr1), as_i32(node1)
+    ne = node1.size
+    Lptr, Uptr = np.empty(n + 1, np.int32), np.empty(n + 1, np.int32)
+    Lnode, Unode = np.empty(max(ne, 1), np.int32), np.empty(max(ne, 1), np.int32)
+    dest = np.empty(max(ne, 1), np.int64)
+    frows, brows = np.empty(max(n, 1), np.int32), np.empty(max(n, 1), np.int32)
+    flev, blev = np.empty(n + 1, np.int32), np.empty(n + 1, np.int32)
+    nf, nb = C.c_int32(), C.c_int32()
+    check(lib().sigb_ldu_symbolic(n, ptr(ptr1), ptr(node1), ptr(Lptr), ptr(Lnode), ptr(Uptr), ptr(Unode), ptr(dest),
+                                  ptr(frows), ptr(flev), C.byref(nf), ptr(brows), ptr(blev), C.byref(nb)))
+    nL, nU = int(Lptr[n]) - 1, int(Uptr[n]) - 1
+    return dict(Lptr=Lptr, Lnode=Lnode[:nL].copy(), Uptr=Uptr, Unode=Unode[:nU].copy(), dest=dest[:ne].copy(),
+                forward_rows=frows[:n].copy(), forward_lev=flev[: nf.value + 1].copy(),
+                backward_rows=brows[:n].copy(), backward_lev=blev[: nb.value + 1].copy())
 
 
 def lanczos(A: Matrix, n: int, q1=None, seed: int = 0):

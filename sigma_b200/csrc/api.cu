@@ -581,6 +581,7 @@ static int make_solver(int kind, double tol, sigb_solver_t *out)
 int sigb_cg_create(double tolerance, sigb_solver_t *s) { return make_solver(S_CG, tolerance, s); }
 int sigb_bicgstab_create(double tolerance, sigb_solver_t *s) { return make_solver(S_BICGSTAB, tolerance, s); }
 int sigb_jacobi_create(sigb_solver_t *s) { return make_solver(S_JACOBI, -1.0, s); }
+int sigb_ldu_create(sigb_solver_t *s) { return make_solver(S_LDU, -1.0, s); }
 
 int sigb_solver_set_params(sigb_solver_t s, double tolerance)
 {
@@ -603,11 +604,11 @@ int sigb_solver_setup(sigb_solver_t s, sigb_matrix_t A)
     const int64_t nglob_rows = A->dist ? dist_global_n(A) : A->nrow;
     const int64_t nglob_cols = A->dist ? dist_global_n(A) : A->ncol;
     if (nglob_rows != nglob_cols) {
-        const char *what = s->kind == S_CG ? "CG" : (s->kind == S_BICGSTAB ? "BiCG-Stab" : "Jacobi");
-        set_error("Cannot make a %s solver for a non-square matrix", what);
+        const char *what = s->kind == S_CG ? "a CG" : (s->kind == S_BICGSTAB ? "a BiCG-Stab" : (s->kind == S_LDU ? "an LDU" : "a Jacobi"));
+        set_error("Cannot make %s solver for a non-square matrix", what);
         return SIGB_ERR_NONSQUARE;
     }
-    const int nwork = s->kind == S_CG ? 4 : (s->kind == S_BICGSTAB ? 8 : 1);
+    const int nwork = s->kind == S_CG ? 4 : (s->kind == S_BICGSTAB ? 8 : (s->kind == S_LDU ? 0 : 1));
     // work vectors start on 256-byte boundaries (128-bit accesses in the vector phases)
     const int64_t nvec = (((int64_t)A->nrow + dist_halo_len(A)) + 31) & ~31LL;
     if (s->initialized && (s->nvec != nvec || s->nwork != nwork)) {
@@ -629,6 +630,15 @@ int sigb_solver_setup(sigb_solver_t s, sigb_matrix_t A)
         s->initialized = true;
     }
     if (s->kind == S_JACOBI) return jacobi_setup_dev(s, A);
+    if (s->kind == S_LDU) {
+        const int rc = ldu_setup_dev(s, A);
+        if (rc != SIGB_OK) {
+            cudaFree(s->work);
+            s->work = nullptr;
+            s->initialized = false;
+        }
+        return rc;
+    }
     SIGB_CUDA(cudaMemsetAsync(s->work, 0, sizeof(double) * (size_t)nvec * nwork, ctx().stream));
     return SIGB_OK;
 }
@@ -641,14 +651,15 @@ int sigb_solver_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x_dev, const
     SIGB_REQUIRE(s->nn == A->nrow, SIGB_ERR_ARG, "sigb_solver_solve: solver was set up for nn = %d, operator has %d rows",
                  s->nn, A->nrow);
     if (pc) {
-        SIGB_REQUIRE(pc->kind == S_JACOBI, SIGB_ERR_UNSUPPORTED,
-                     "sigb_solver_solve: the only device preconditioner is jacobi");
+        SIGB_REQUIRE(pc->kind == S_JACOBI || (pc->kind == S_LDU && s->kind == S_CG && !A->dist), SIGB_ERR_UNSUPPORTED,
+                     "sigb_solver_solve: the device preconditioners are jacobi (cg, bicgstab) and ldu (cg, one GPU)");
         SIGB_REQUIRE(pc->initialized && pc->nn == s->nn, SIGB_ERR_STATE,
                      "sigb_solver_solve: pc%%setup(A) has not been called");
     }
     switch (s->kind) {
     case S_CG: return cg_solve_dev(s, A, x_dev, b_dev, pc);
     case S_BICGSTAB: return bicgstab_solve_dev(s, A, x_dev, b_dev, pc);
+    case S_LDU: return ldu_apply_dev(s, x_dev, b_dev, nullptr);   // ldu_solve ldu_solvers.f90:160-176
     default:
         // jacobi has no linear_solve_pc override: the default ignores pc
         // (linear_operator_interface.f90:238-254)
@@ -707,8 +718,23 @@ int sigb_solver_destroy(sigb_solver_t s)
     cudaFree(s->xb);
     cudaFree(s->bar);
     cudaFree(s->pers_partials);
+    ldu_destroy_dev(s);
     delete s;
     return SIGB_OK;
+}
+
+int sigb_ldu_get_sizes(sigb_solver_t s, int32_t *n, int64_t *nL, int64_t *nU, int32_t *n_forward_levels,
+                       int32_t *n_backward_levels)
+{
+    SIGB_REQUIRE(s && s->kind == S_LDU, SIGB_ERR_ARG, "sigb_ldu_get_sizes: not an ldu solver");
+    return ldu_sizes(s, n, nL, nU, n_forward_levels, n_backward_levels);
+}
+
+int sigb_ldu_get_factors(sigb_solver_t s, int32_t *Lptr1, int32_t *Lnode1, double *Lval, int32_t *Uptr1,
+                         int32_t *Unode1, double *Uval, double *D)
+{
+    SIGB_REQUIRE(s && s->kind == S_LDU, SIGB_ERR_ARG, "sigb_ldu_get_factors: not an ldu solver");
+    return ldu_read(s, Lptr1, Lnode1, Lval, Uptr1, Unode1, Uval, D);
 }
 
 // ===========================================================================

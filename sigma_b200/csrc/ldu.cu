@@ -1,0 +1,315 @@
+// ldu.cu -- ILDU(0) preconditioner on the device.
+//
+// Replaces the bodies of
+//   sparse_ldu_setup                          src/solver/ldu_solvers.f90:95-130
+//   incomplete_ldu_sparsity_pattern           :396-441   (host index work, ldu_host.cpp)
+//   sparse_static_pattern_ldu_factorization   :275-387
+//   ldu_solve, lower_/upper_triangular_solve  :160-176, :208-263
+//
+// A ~= (I + L) D (I + U) with L, U csr matrices on the strict triangles of A's
+// pattern.  Both the elimination and the triangular solves are sequential in
+// the reference; their only dependencies are "row i needs rows k < i that are
+// lower neighbours of i" (resp. upper neighbours for the backward solve), so
+// rows are grouped into levels on the host once per pattern and each level is
+// one launch in which every row runs the reference's own arithmetic, entry by
+// entry in stored order, with rounded products (no FMA).  Factors, diagonal
+// and every solve are therefore bit-identical to the serial loops.
+//
+// This is latency-bound by construction: a level of the 2-D five-point stencil
+// in natural ordering is one anti-diagonal of the grid (2N - 1 levels of at
+// most N rows).  The value of the row is the drop-in coverage of the only
+// other preconditioner the reference ships, not bandwidth.
+#include <vector>
+
+#include "device_utils.cuh"
+#include "dist.h"
+#include "solvers.h"
+
+namespace sigb {
+
+struct LduInfo {
+    int32_t n = 0;
+    int64_t nL = 0, nU = 0, ne = 0;
+    // patterns (1-based, device) and the combined value array [ Lval | Uval | D ]
+    int32_t *Lptr = nullptr, *Lnode = nullptr, *Uptr = nullptr, *Unode = nullptr;
+    double *fac = nullptr;
+    int64_t *dest = nullptr;          // source entry -> offset in fac
+    int32_t *frows = nullptr, *brows = nullptr;
+    std::vector<int32_t> flev, blev;  // level pointers (host): launches are driven from here
+    sigb_matrix_t rows = nullptr;     // csc / ellpack sources: their row form (device copy), else null
+    double *Lval() const { return fac; }
+    double *Uval() const { return fac + nL; }
+    double *D() const { return fac + nL + nU; }
+};
+
+namespace {
+
+inline int grid_for(int64_t n)
+{
+    int64_t g = (n + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)ctx().num_sms * 8;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// "Copy A into L, D, U" (:307-324)
+__global__ void __launch_bounds__(kThreads)
+ldu_scatter_kernel(const double *__restrict__ aval, const int64_t *__restrict__ dest, int64_t ne,
+                   double *__restrict__ fac)
+{
+    for (int64_t e = blockIdx.x * (int64_t)kThreads + threadIdx.x; e < ne; e += (int64_t)gridDim.x * kThreads)
+        fac[dest[e]] = aval[e];
+}
+
+// M%get_value(i, j) on a csr pattern: last hit wins, 0 when absent (cs_matrices.f90:709-724)
+__device__ __forceinline__ double get_value(const int32_t *ptr1, const int32_t *node1, const double *val, int32_t i,
+                                            int32_t j)
+{
+    double z = 0.0;
+    for (int32_t k = ptr1[i - 1] - 1; k < ptr1[i] - 1; k++)
+        if (node1[k] == j) z = val[k];
+    return z;
+}
+
+// rows of one level of the elimination (:331-381), one thread per row
+__global__ void __launch_bounds__(kThreads)
+ldu_factor_level_kernel(const int32_t *__restrict__ rows, int32_t count, const int32_t *__restrict__ Lptr,
+                        const int32_t *__restrict__ Lnode, double *Lval, const int32_t *__restrict__ Uptr,
+                        const int32_t *__restrict__ Unode, double *Uval, double *D)
+{
+    for (int32_t t = blockIdx.x * kThreads + threadIdx.x; t < count; t += gridDim.x * kThreads) {
+        const int32_t i = rows[t];
+        const int32_t lb = Lptr[i - 1] - 1, dl = Lptr[i] - 1 - lb;
+        const int32_t ub = Uptr[i - 1] - 1, du = Uptr[i] - 1 - ub;
+        for (int32_t ind1 = 0; ind1 < dl; ind1++) {
+            const int32_t k = Lnode[lb + ind1];
+            double Lik = Lval[lb + ind1];                              // L%get_value(i, k)   :342
+            const double Uki = get_value(Uptr, Unode, Uval, k, i);     // :343
+            const double Dk = D[k - 1];
+            Lik = Lik / Dk;                                            // :345-346
+            Lval[lb + ind1] = Lik;
+            const double LikDk = mul(Lik, Dk);
+            for (int32_t ind2 = 0; ind2 < dl; ind2++) {                // :350-358
+                const int32_t j = Lnode[lb + ind2];
+                if (j > k) {
+                    const double Ukj = get_value(Uptr, Unode, Uval, k, j);
+                    Lval[lb + ind2] = add(Lval[lb + ind2], -mul(LikDk, Ukj));
+                }
+            }
+            D[i - 1] = sub(D[i - 1], mul(LikDk, Uki));                 // :361
+            for (int32_t ind2 = 0; ind2 < du; ind2++) {                // :364-368
+                const int32_t j = Unode[ub + ind2];
+                const double Ukj = get_value(Uptr, Unode, Uval, k, j);
+                Uval[ub + ind2] = add(Uval[ub + ind2], -mul(LikDk, Ukj));
+            }
+        }
+        const double Di = D[i - 1];
+        for (int32_t ind2 = 0; ind2 < du; ind2++) Uval[ub + ind2] = Uval[ub + ind2] / Di;   // :373-377
+    }
+}
+
+// rows of one level of lower_/upper_triangular_solve (:226-235, :254-263):
+// z = x(i) ; z = z - M%val(k) * x(node(k)) in stored order ; x(i) = z
+__global__ void __launch_bounds__(kThreads)
+tri_level_kernel(const int32_t *__restrict__ rows, int32_t count, const int32_t *__restrict__ ptr1,
+                 const int32_t *__restrict__ node1, const double *__restrict__ val, double *x, const int *skip)
+{
+    if (skip != nullptr && *skip != 0) return;
+    for (int32_t t = blockIdx.x * kThreads + threadIdx.x; t < count; t += gridDim.x * kThreads) {
+        const int32_t i = rows[t];
+        double z = x[i - 1];
+        for (int32_t k = ptr1[i - 1] - 1; k < ptr1[i] - 1; k++) z = sub(z, mul(val[k], x[node1[k] - 1]));
+        x[i - 1] = z;
+    }
+}
+
+// x = b, then the rows of forward level 0 need nothing else; x = x / D between the sweeps
+__global__ void __launch_bounds__(kThreads)
+copy_kernel(const double *__restrict__ b, double *__restrict__ x, int64_t n, const int *skip)
+{
+    if (skip != nullptr && *skip != 0) return;
+    for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+        x[i] = b[i];
+}
+__global__ void __launch_bounds__(kThreads)
+divide_kernel(double *__restrict__ x, const double *__restrict__ D, int64_t n, const int *skip)
+{
+    if (skip != nullptr && *skip != 0) return;
+    for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+        x[i] = x[i] / D[i];
+}
+
+void free_ldu(LduInfo *F)
+{
+    if (!F) return;
+    cudaFree(F->Lptr); cudaFree(F->Lnode); cudaFree(F->Uptr); cudaFree(F->Unode);
+    cudaFree(F->fac); cudaFree(F->dest); cudaFree(F->frows); cudaFree(F->brows);
+    if (F->rows) sigb_matrix_destroy(F->rows);
+    delete F;
+}
+
+template <typename T>
+int upload(T **dst, const T *src, size_t count)
+{
+    SIGB_CUDA(cudaMalloc((void **)dst, sizeof(T) * (count > 0 ? count : 1)));
+    if (count > 0)
+        SIGB_CUDA(cudaMemcpyAsync(*dst, src, sizeof(T) * count, cudaMemcpyHostToDevice, ctx().stream));
+    return SIGB_OK;
+}
+
+}  // namespace
+
+void ldu_destroy_dev(sigb_solver_t s)
+{
+    free_ldu(s->ldu);
+    s->ldu = nullptr;
+}
+
+// pc%setup(A): the pattern and the schedules once (solver%initialized, :113-121),
+// the numeric factorisation every time (:124-126)
+int ldu_setup_dev(sigb_solver_t s, sigb_matrix_t A)
+{
+    SIGB_REQUIRE(!A->op && !A->dist, SIGB_ERR_UNSUPPORTED,
+                 "ldu setup needs a stored sparse matrix (sparse_ldu_setup selects on sparse_matrix_interface, "
+                 "ldu_solvers.f90:111-112)");
+    cudaStream_t st = ctx().stream;
+    const int32_t n = A->nrow;
+    LduInfo *F = s->ldu;
+    if (F && (F->n != n || F->ne != A->g->ne)) {   // another operator: start over
+        free_ldu(F);
+        F = s->ldu = nullptr;
+    }
+    // the rows of A in iteration order: a csr_matrix as stored, otherwise its csr copy
+    sigb_matrix_t R = A;
+    if (A->g->kind != G_CSR) {
+        if (F && F->rows) { sigb_matrix_destroy(F->rows); F->rows = nullptr; }
+        sigb_matrix_t rows = nullptr;
+        SIGB_CHECK(sigb_matrix_copy(A, SIGB_FMT_CSR, 0, &rows));
+        R = rows;
+    }
+    int rc = SIGB_OK;
+    if (!F) {
+        F = new LduInfo();
+        F->n = n;
+        F->ne = R->g->ne;
+        const int64_t ne = F->ne;
+        std::vector<int32_t> ptr((size_t)n + 1), node((size_t)ne);
+        std::vector<int32_t> Lptr((size_t)n + 1), Uptr((size_t)n + 1), Lnode((size_t)ne), Unode((size_t)ne);
+        std::vector<int64_t> dest((size_t)ne);
+        std::vector<int32_t> frows((size_t)n), brows((size_t)n), flev((size_t)n + 1), blev((size_t)n + 1);
+        int32_t nf = 0, nb = 0;
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(ptr.data(), R->g->stored.ptr, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && ne > 0)
+            e = cudaMemcpy(node.data(), R->g->stored.node, sizeof(int32_t) * (size_t)ne, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "ldu setup read-back", __FILE__, __LINE__);
+        if (rc == SIGB_OK)
+            rc = sigb_ldu_symbolic(n, ptr.data(), node.data(), Lptr.data(), Lnode.data(), Uptr.data(), Unode.data(),
+                                   dest.data(), frows.data(), flev.data(), &nf, brows.data(), blev.data(), &nb);
+        if (rc == SIGB_OK) {
+            F->nL = (int64_t)Lptr[(size_t)n] - 1;
+            F->nU = (int64_t)Uptr[(size_t)n] - 1;
+            F->flev.assign(flev.begin(), flev.begin() + nf + 1);
+            F->blev.assign(blev.begin(), blev.begin() + nb + 1);
+            rc = upload(&F->Lptr, Lptr.data(), (size_t)n + 1);
+            if (rc == SIGB_OK) rc = upload(&F->Uptr, Uptr.data(), (size_t)n + 1);
+            if (rc == SIGB_OK) rc = upload(&F->Lnode, Lnode.data(), (size_t)F->nL);
+            if (rc == SIGB_OK) rc = upload(&F->Unode, Unode.data(), (size_t)F->nU);
+            if (rc == SIGB_OK) rc = upload(&F->dest, dest.data(), (size_t)ne);
+            if (rc == SIGB_OK) rc = upload(&F->frows, frows.data(), (size_t)n);
+            if (rc == SIGB_OK) rc = upload(&F->brows, brows.data(), (size_t)n);
+            if (rc == SIGB_OK) {
+                cudaError_t e2 = cudaMalloc((void **)&F->fac, sizeof(double) * (size_t)(F->nL + F->nU + n + 1));
+                if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(st);   // the host vectors go out of scope below
+                if (e2 != cudaSuccess) rc = cuda_fail(e2, "ldu setup", __FILE__, __LINE__);
+            }
+        }
+        if (rc != SIGB_OK) {
+            free_ldu(F);
+            if (R != A) sigb_matrix_destroy(R);
+            return rc;
+        }
+        s->ldu = F;
+    }
+    if (R != A) F->rows = R;
+
+    // L%zero(), U%zero(), D = 0, then copy A in (:302-324)
+    SIGB_CUDA(cudaMemsetAsync(F->fac, 0, sizeof(double) * (size_t)(F->nL + F->nU + n + 1), st));
+    if (F->ne > 0) {
+        ldu_scatter_kernel<<<grid_for(F->ne), kThreads, 0, st>>>(R->val, F->dest, F->ne, F->fac);
+        count_launch();
+    }
+    // the elimination, level by level
+    const int nlev = (int)F->flev.size() - 1;
+    for (int l = 0; l < nlev; l++) {
+        const int32_t b = F->flev[(size_t)l], cnt = F->flev[(size_t)l + 1] - b;
+        ldu_factor_level_kernel<<<grid_for(cnt), kThreads, 0, st>>>(F->frows + b, cnt, F->Lptr, F->Lnode, F->Lval(),
+                                                                   F->Uptr, F->Unode, F->Uval(), F->D());
+        count_launch();
+    }
+    SIGB_CUDA(cudaGetLastError());
+    return SIGB_OK;
+}
+
+// call pc%solve(A, x, b): x = b ; (I + L) x = x ; x = x / D ; (I + U) x = x   (:167-171)
+int ldu_apply_dev(sigb_solver_t s, double *x, const double *b, const int *skip_flag)
+{
+    LduInfo *F = s->ldu;
+    SIGB_REQUIRE(F, SIGB_ERR_STATE, "ldu solve: pc%%setup(A) has not been called");
+    cudaStream_t st = ctx().stream;
+    const int32_t n = F->n;
+    if (x != b) {
+        copy_kernel<<<grid_for(n), kThreads, 0, st>>>(b, x, n, skip_flag);
+        count_launch();
+    }
+    // level 0 of either sweep has no neighbours to subtract: nothing to do for it
+    for (size_t l = 1; l + 1 < F->flev.size(); l++) {
+        const int32_t b0 = F->flev[l], cnt = F->flev[l + 1] - b0;
+        tri_level_kernel<<<grid_for(cnt), kThreads, 0, st>>>(F->frows + b0, cnt, F->Lptr, F->Lnode, F->Lval(), x,
+                                                            skip_flag);
+        count_launch();
+    }
+    divide_kernel<<<grid_for(n), kThreads, 0, st>>>(x, F->D(), n, skip_flag);
+    count_launch();
+    for (size_t l = 1; l + 1 < F->blev.size(); l++) {
+        const int32_t b0 = F->blev[l], cnt = F->blev[l + 1] - b0;
+        tri_level_kernel<<<grid_for(cnt), kThreads, 0, st>>>(F->brows + b0, cnt, F->Uptr, F->Unode, F->Uval(), x,
+                                                            skip_flag);
+        count_launch();
+    }
+    SIGB_CUDA(cudaGetLastError());
+    return SIGB_OK;
+}
+
+int ldu_sizes(sigb_solver_t s, int32_t *n, int64_t *nL, int64_t *nU, int32_t *nflev, int32_t *nblev)
+{
+    LduInfo *F = s->ldu;
+    SIGB_REQUIRE(F, SIGB_ERR_STATE, "ldu: pc%%setup(A) has not been called");
+    if (n) *n = F->n;
+    if (nL) *nL = F->nL;
+    if (nU) *nU = F->nU;
+    if (nflev) *nflev = (int32_t)F->flev.size() - 1;
+    if (nblev) *nblev = (int32_t)F->blev.size() - 1;
+    return SIGB_OK;
+}
+
+int ldu_read(sigb_solver_t s, int32_t *Lptr, int32_t *Lnode, double *Lval, int32_t *Uptr, int32_t *Unode,
+             double *Uval, double *D)
+{
+    LduInfo *F = s->ldu;
+    SIGB_REQUIRE(F, SIGB_ERR_STATE, "ldu: pc%%setup(A) has not been called");
+    SIGB_CUDA(cudaStreamSynchronize(ctx().stream));
+    const size_t n = (size_t)F->n, nL = (size_t)F->nL, nU = (size_t)F->nU;
+    if (Lptr) SIGB_CUDA(cudaMemcpy(Lptr, F->Lptr, sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost));
+    if (Uptr) SIGB_CUDA(cudaMemcpy(Uptr, F->Uptr, sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost));
+    if (Lnode && nL) SIGB_CUDA(cudaMemcpy(Lnode, F->Lnode, sizeof(int32_t) * nL, cudaMemcpyDeviceToHost));
+    if (Unode && nU) SIGB_CUDA(cudaMemcpy(Unode, F->Unode, sizeof(int32_t) * nU, cudaMemcpyDeviceToHost));
+    if (Lval && nL) SIGB_CUDA(cudaMemcpy(Lval, F->Lval(), sizeof(double) * nL, cudaMemcpyDeviceToHost));
+    if (Uval && nU) SIGB_CUDA(cudaMemcpy(Uval, F->Uval(), sizeof(double) * nU, cudaMemcpyDeviceToHost));
+    if (D && n) SIGB_CUDA(cudaMemcpy(D, F->D(), sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return SIGB_OK;
+}
+
+}  // namespace sigb

@@ -133,6 +133,37 @@ struct CgDirectionOp {
     __device__ double *out(int) { return nullptr; }
 };
 
+// ---- CG with a preconditioner that is applied by its own kernels (ldu) -----
+// p = z ; res2 = r.z   (cg_solvers.f90:171-172)
+struct PcInitOp {
+    static constexpr int ND = 1;
+    static constexpr int NIN = 2;
+    const double *__restrict__ r, *__restrict__ z;
+    double *__restrict__ p;
+    KState *st;
+    __device__ bool begin() { return true; }
+    __device__ void load(int64_t i, double *in) { in[0] = r[i]; in[1] = z[i]; }
+    __device__ void compute(int64_t i, const double *in, double *acc)
+    {
+        p[i] = in[1];
+        acc[0] = add(acc[0], mul(in[0], in[1]));
+    }
+    __device__ double *out(int) { return &st->rr[0]; }
+};
+
+// dpr = r.z   (cg_solvers.f90:183), skipped past the stopping latch
+struct PcDotOp {
+    static constexpr int ND = 1;
+    static constexpr int NIN = 2;
+    const double *__restrict__ r, *__restrict__ z;
+    KState *st;
+    int par;
+    __device__ bool begin() { return st->done[par] == 0; }
+    __device__ void load(int64_t i, double *in) { in[0] = r[i]; in[1] = z[i]; }
+    __device__ void compute(int64_t, const double *in, double *acc) { acc[0] = add(acc[0], mul(in[0], in[1])); }
+    __device__ double *out(int) { return &st->rr[par ^ 1]; }
+};
+
 // ===========================================================================
 // BiCGSTAB kernels
 // ===========================================================================
@@ -709,8 +740,53 @@ int cg_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x, const double *b, s
     return rc;
 }
 
+// cg_solve_pc (cg_solvers.f90:155-194) with a preconditioner applied by its own kernels
+// between the residual update and the direction update: call pc%solve(A, z, r) (:170, :181).
+// Same device-resident control as the fused path: every kernel of an iteration launched
+// past the stopping latch is a no-op.
+static int cg_solve_ldu_pc(sigb_solver_t s, sigb_matrix_t A, double *x, const double *b, sigb_solver_t pc)
+{
+    const int64_t n = s->nn, nv = s->nvec;
+    double *p = s->work, *q = p + nv, *r = q + nv, *z = r + nv;
+    KState *st = s->state;
+    SIGB_CHECK(push_state(s));
+    DotSpec none;
+    SIGB_CHECK(solver_matvec(A, x, q, none, false));            // z = x ; q = A z        :167-168
+    CgInitOp init{b, q, nullptr, r, p, z, st};                  // r = b - q              :169
+    SIGB_CHECK(launch_ew(init, n));
+    SIGB_CHECK(ldu_apply_dev(pc, z, r, nullptr));               // call pc%solve(A, z, r) :170
+    PcInitOp pinit{r, z, p, st};                                // p = z ; res2 = r.z     :171-172
+    SIGB_CHECK(launch_ew(pinit, n));
+    latch0_kernel<<<1, 1, 0, ctx().stream>>>(st);
+    count_launch();
+    const int nb = batch_size(n);
+    int par = 0;
+    for (;;) {
+        for (int it = 0; it < nb; it++) {
+            DotSpec d;
+            d.ndot = 1;
+            d.u = p;
+            d.out[0] = &st->pq;
+            d.skip_flag = &st->done[par];
+            SIGB_CHECK(solver_matvec(A, p, q, d, false));               // q = A p ; dpr = p.q   :175-176
+            CgUpdateOp up{q, nullptr, r, z, st, par, 0.0};              // r = r - alpha q       :179
+            SIGB_CHECK(launch_ew(up, n));                               // (its r.r lands in rr[par^1] and is
+            SIGB_CHECK(ldu_apply_dev(pc, z, r, &st->done[par]));        //  replaced by r.z below)   :181
+            PcDotOp dz{r, z, st, par};                                  // dpr = r.z             :183
+            SIGB_CHECK(launch_ew(dz, n));
+            CgDirectionOp dir{z, p, x, st, par, 0.0, 0.0};              // x, beta, p = z + beta p  :178,184-189
+            SIGB_CHECK(launch_ew(dir, n));
+            par ^= 1;
+        }
+        SIGB_CHECK(sync_state(s));
+        if (s->state_host->done[par]) break;
+    }
+    return finish_solve(s);
+}
+
 static int cg_solve_body(sigb_solver_t s, sigb_matrix_t A, double *x, const double *b, sigb_solver_t pc)
 {
+    if (pc && pc->kind == S_LDU) return cg_solve_ldu_pc(s, A, x, b, pc);
     const int64_t n = s->nn, nv = s->nvec;
     double *p = s->work, *q = p + nv, *r = q + nv, *z = r + nv;
     const double *idiag = pc ? pc->work : nullptr;

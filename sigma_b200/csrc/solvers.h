@@ -6,7 +6,8 @@
 
 namespace sigb {
 struct KState;
-enum SolverKind { S_CG = 0, S_BICGSTAB = 1, S_JACOBI = 2 };
+struct LduInfo;   // ldu.cu
+enum SolverKind { S_CG = 0, S_BICGSTAB = 1, S_JACOBI = 2, S_LDU = 3 };
 }  // namespace sigb
 
 struct sigb_solver_s {
@@ -30,10 +31,19 @@ struct sigb_solver_s {
     // persistent CG kernel (cg_persistent.cu)
     unsigned long long *bar = nullptr;   // grid barrier counter
     double *pers_partials = nullptr;     // 2 x kMaxGrid CTA partial sums
+    sigb::LduInfo *ldu = nullptr;        // sparse_ldu_solver: factors and level schedules (ldu.cu)
 };
 
 namespace sigb {
 
+// ILDU(0) (ldu.cu): setup = pattern + schedules once, numeric factorisation every call;
+// apply = x <- (I+U)^-1 D^-1 (I+L)^-1 b, a no-op when *skip_flag != 0
+int ldu_setup_dev(sigb_solver_t s, sigb_matrix_t A);
+int ldu_apply_dev(sigb_solver_t s, double *x, const double *b, const int *skip_flag);
+void ldu_destroy_dev(sigb_solver_t s);
+int ldu_sizes(sigb_solver_t s, int32_t *n, int64_t *nL, int64_t *nU, int32_t *nflev, int32_t *nblev);
+int ldu_read(sigb_solver_t s, int32_t *Lptr, int32_t *Lnode, double *Lval, int32_t *Uptr, int32_t *Unode,
+             double *Uval, double *D);
 int jacobi_setup_dev(sigb_solver_t s, sigb_matrix_t A);
 int jacobi_apply_dev(sigb_solver_t s, double *x, const double *b);
 int cg_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x, const double *b, sigb_solver_t pc);

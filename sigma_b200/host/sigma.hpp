@@ -17,7 +17,7 @@
 //   A%copy_matrix(B, trans)                         same name (built on the device)
 //   A%matvec / matvec_t / matvec_add / matvec_t_add same names (linear_operator)
 //   A%set_solver / set_preconditioner / solve       same names
-//   cg(tol), bicgstab(tol), jacobi()                same names -> linear_solver*
+//   cg(tol), bicgstab(tol), jacobi(), ldu()         same names -> linear_solver*
 //   solver%setup / solve(A,x,b[,pc]) / destroy      same names
 //   lanczos(A,T,Q), eigensolve(A,lambda,V)          same names
 //   L = A + B, L = A * B, L = adjoint(A)            same (operator_sum/_product/_adjoint)
@@ -618,6 +618,11 @@ struct bicgstab_solver : linear_solver {
     void set_params(dp tol = -1.0) { tolerance = tol < 0 ? 1e-16 : tol; sigb_check(sigb_solver_set_params(dev, tol)); }
 };
 struct jacobi_solver : linear_solver {};
+// src/solver/ldu_solvers.f90:35-58: always incomplete, level 0 (:145,151)
+struct sparse_ldu_solver : linear_solver {
+    bool incomplete = true;
+    int level = 0;
+};
 
 // factory functions of the reference (cg_solvers.f90:36-47, bicgstab_solvers.f90:36-47,
 // jacobi_solvers.f90:26-32); tolerance < 0 selects the default 1e-16
@@ -639,6 +644,16 @@ inline linear_solver *jacobi()
 {
     auto *s = new jacobi_solver();
     sigb_check(sigb_jacobi_create(&s->dev));
+    return s;
+}
+
+// ldu(incomplete, level)   (ldu_solvers.f90:73-86)
+inline linear_solver *ldu(bool incomplete = true, int level = 0)
+{
+    (void)incomplete;
+    (void)level;
+    auto *s = new sparse_ldu_solver();
+    sigb_check(sigb_ldu_create(&s->dev));
     return s;
 }
 

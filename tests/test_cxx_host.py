@@ -10,7 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CXX = os.path.join(ROOT, "tests", "cxx")
 PROGS = ["solver_test_diffusion_1d", "solver_test_advection_diffusion_1d", "solver_test_jacobi",
          "eigensolver_test_lanczos", "eigensolver_test_generalized_lanczos", "matrix_test_basics",
-         "linear_operator_test_algebra", "matrix_test_composite", "matrix_test_copy"]
+         "linear_operator_test_algebra", "matrix_test_composite", "matrix_test_copy",
+         "solver_test_incomplete_cholesky"]
 
 
 def build():
