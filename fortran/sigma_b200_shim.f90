@@ -133,6 +133,30 @@ interface                                                                  !
         integer(c_int) :: stat
     end function
 
+    function sigb_ldu_create(s) bind(c, name='sigb_ldu_create') result(stat)
+        import :: c_int, c_ptr
+        type(c_ptr), intent(out) :: s
+        integer(c_int) :: stat
+    end function
+
+    function sigb_ldu_get_sizes(s, n, nL, nU, nflev, nblev) &
+            & bind(c, name='sigb_ldu_get_sizes') result(stat)
+        import :: c_int, c_int32_t, c_int64_t, c_ptr
+        type(c_ptr), value :: s
+        integer(c_int32_t), intent(out) :: n, nflev, nblev
+        integer(c_int64_t), intent(out) :: nL, nU
+        integer(c_int) :: stat
+    end function
+
+    function sigb_ldu_get_factors(s, Lptr, Lnode, Lval, Uptr, Unode, Uval, D) &
+            & bind(c, name='sigb_ldu_get_factors') result(stat)
+        import :: c_int, c_int32_t, c_double, c_ptr
+        type(c_ptr), value :: s
+        integer(c_int32_t), intent(out) :: Lptr(*), Lnode(*), Uptr(*), Unode(*)
+        real(c_double), intent(out) :: Lval(*), Uval(*), D(*)
+        integer(c_int) :: stat
+    end function
+
     function sigb_solver_setup(s, A) bind(c, name='sigb_solver_setup') result(stat)
         import :: c_int, c_ptr
         type(c_ptr), value :: s, A
@@ -512,3 +536,26 @@ end module sigma_b200_shim
 !         call sigb_check( sigb_matrix_get_arrays(A%mirror, dummy_ptr, dummy_node, A%val) )
 !     An assembly loop (examples/fem.f90:43-47) gathers its add_value calls into
 !     one such batch per mesh instead of one call per entry.
+!
+! --- src/solver/ldu_solvers.f90, type sparse_ldu_solver (:35-58) gains
+!         type(c_ptr), private :: dev = c_null_ptr
+!
+!     subroutine sparse_ldu_setup(solver, A)                ! :95-130
+!         ... unchanged non-square check (print + exit(1)) ...
+!         h = A%device_handle()
+!         if (c_associated(h)) then
+!             if (.not. c_associated(solver%dev)) call sigb_check( sigb_ldu_create(solver%dev) )
+!             call sigb_check( sigb_solver_setup(solver%dev, h) )   ! pattern once, numbers every call
+!             solver%initialized = .true.
+!         else
+!             ... the reference body, unchanged ...
+!         endif
+!     end subroutine
+!
+!     subroutine ldu_solve(solver, A, x, b)                 ! :160-176
+!         call sigb_check( sigb_solver_solve(solver%dev, A%device_handle(), x, b, c_null_ptr) )
+!     end subroutine
+!
+!     and in cg_solve_pc (cg_solvers.f90:155-194) the select type(pc) shown above gains
+!         type is (sparse_ldu_solver)
+!             call sigb_check( sigb_solver_solve(solver%dev, h, x, b, pc%dev) )
