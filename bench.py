@@ -368,6 +368,284 @@ def run_ours(args):
     return out
 
 
+
+# ---------------------------------------------------------------------------
+# rows widened per SURVEY.md 8f (python bench.py --rows widened | ldu): one JSON line per
+# row, each GPU number with the serial port timed beside it on a bounded sample (the
+# cpu_baseline leg -- the only other place this file executes oracle/).
+#   widened: operator expressions, device matrix copies, ordered add_value stream
+#            2-D Poisson --wgrid^2 (default 2048: 250 MB of matrix arrays, larger than L2)
+#            and the P1 FEM stream of examples/fem.f90 on --fem^2 vertices
+#   ldu    : ILDU(0) setup / application / PCG on 2-D Poisson --lgrid^2
+# Kernel times: CUDA events on the library's stream after warm-up; the copy / assembly
+# entry points synchronise internally and are timed with the host clock around the C-ABI
+# call (host pointers in, as a Fortran caller would issue them).
+# ---------------------------------------------------------------------------
+def split_blocks(n, ptr, node, val, h):
+    """The n x n CSR matrix as 2 x 2 CSR blocks split at row / column h (0-based count)."""
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(ptr))
+    cols = node.astype(np.int64) - 1
+    out = []
+    for (r0, r1) in ((0, h), (h, n)):
+        row_blocks = []
+        for (c0, c1) in ((0, h), (h, n)):
+            m = (rows >= r0) & (rows < r1) & (cols >= c0) & (cols < c1)
+            cnt = np.bincount(rows[m] - r0, minlength=r1 - r0)
+            bptr = np.concatenate([[1], 1 + np.cumsum(cnt)]).astype(np.int32)
+            row_blocks.append((r1 - r0, c1 - c0, bptr, (cols[m] - c0 + 1).astype(np.int32), val[m]))
+        out.append(row_blocks)
+    return out
+
+
+def run_widened(args):
+    import torch
+
+    import sigma_b200 as sb
+    from sigma_b200 import generators as G
+
+    peak, _ = peaks()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    sb.init(0)
+    stream = torch.cuda.Stream(device=dev)
+    sb.set_stream(stream.cuda_stream)
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e-3   # seconds per call
+
+    def emit(**kw):
+        print(json.dumps(kw), flush=True)
+
+    # ------------------------------------------------------------------ operators
+    N = args.wgrid
+    n = N * N
+    ptr, node, val = G.poisson2d_csr(N)
+    nnz = int(node.size)
+    b_host, _ = G.poisson2d_rhs(N)
+    A = sb.csr_matrix(n, n, ptr, node, val)
+    with torch.cuda.stream(stream):
+        x = torch.from_numpy(b_host).to(dev)
+        y = torch.empty(n, dtype=torch.float64, device=dev)
+        y2 = torch.empty(n, dtype=torch.float64, device=dev)
+    stream.synchronize()
+
+    bytes_mono = 12 * nnz + 20 * n + 4
+    t_mono = timed(lambda: A.matvec_dev(x, y), args.reps)
+    emit(row="csr matvec (baseline for the expressions)", grid=N, n=n, nnz=nnz, us=t_mono * 1e6,
+         algorithmic_bytes=bytes_mono, gbs=bytes_mono / t_mono / 1e9, frac_of_measured_hbm=bytes_mono / t_mono / 1e9 / peak)
+
+    blocks = split_blocks(n, ptr, node, val, n // 2)
+    mats = [[sb.csr_matrix(r, c, p, nd, v) for (r, c, p, nd, v) in row] for row in blocks]
+    S = sb.sparse_matrix([n // 2, n - n // 2], [n // 2, n - n // 2], mats)
+    S.matvec_dev(x, y2)
+    A.matvec_dev(x, y)
+    stream.synchronize()
+    same = bool(torch.equal(y, y2))   # block sums split each row's additions: equal only when no row is split
+    maxdiff = float((y - y2).abs().max().item())
+    # bytes: every block streams its entries and its ptr slice; x is read once per block column pair,
+    # y is written by the first block of a block row and read + written by the second
+    bytes_comp = 12 * nnz + 4 * 2 * n + 8 * n + 24 * n
+    t_comp = timed(lambda: S.matvec_dev(x, y2), args.reps)
+    emit(row="composite 2x2 sparse_matrix matvec (4 leaf launches)", us=t_comp * 1e6, algorithmic_bytes=bytes_comp,
+         gbs=bytes_comp / t_comp / 1e9, frac_of_measured_hbm=bytes_comp / t_comp / 1e9 / peak,
+         vs_monolithic=t_comp / t_mono, bit_equal_to_monolithic=same, max_abs_diff=maxdiff)
+
+    # operator_sum: strictly-lower + (diagonal and upper) parts of the same matrix
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(ptr))
+    low = (node.astype(np.int64) - 1) < rows
+
+    def part(mask):
+        cnt = np.bincount(rows[mask], minlength=n)
+        return np.concatenate([[1], 1 + np.cumsum(cnt)]).astype(np.int32), node[mask], val[mask]
+
+    L = sb.csr_matrix(n, n, *part(low))
+    U = sb.csr_matrix(n, n, *part(~low))
+    LU = L + U
+    bytes_sum = 12 * nnz + 4 * 2 * n + 2 * 8 * n + 24 * n
+    t_sum = timed(lambda: LU.matvec_dev(x, y2), args.reps)
+    emit(row="operator_sum L + U matvec (2 leaf launches)", us=t_sum * 1e6, algorithmic_bytes=bytes_sum,
+         gbs=bytes_sum / t_sum / 1e9, frac_of_measured_hbm=bytes_sum / t_sum / 1e9 / peak, vs_monolithic=t_sum / t_mono)
+
+    # adjoint(A) * A applied as an expression (2 SpMVs through the device scratch vector)
+    AtA = sb.adjoint(A) * A
+    t_ata = timed(lambda: AtA.matvec_dev(x, y2), max(10, args.reps // 2))
+    emit(row="operator_product adjoint(A) * A matvec (csr SpMV + transposed SpMV)", us=t_ata * 1e6,
+         algorithmic_bytes=2 * bytes_mono, gbs=2 * bytes_mono / t_ata / 1e9,
+         frac_of_measured_hbm=2 * bytes_mono / t_ata / 1e9 / peak, vs_monolithic=t_ata / t_mono)
+
+    # CG driven by the composite vs by the plain matrix (kernel-per-phase path for both)
+    K = args.cg_steps
+    tol = 1e-10 * float(np.linalg.norm(b_host))
+    os.environ["SIGB_CG_PERSISTENT"] = "0"
+    rates = {}
+    for name, op in (("csr_matrix", A), ("composite 2x2", S)):
+        solver = sb.cg(tol)
+        solver.set_max_iterations(K)
+        solver.setup(op)
+        with torch.cuda.stream(stream):
+            xs = torch.zeros(n, dtype=torch.float64, device=dev)
+        solver.solve_dev(op, xs, x)          # warm-up
+        solver.setup(op)
+        with torch.cuda.stream(stream):
+            xs.zero_()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        solver.solve_dev(op, xs, x)
+        e1.record(stream)
+        e1.synchronize()
+        it = solver.info()[0]
+        rates[name] = it / (e0.elapsed_time(e1) * 1e-3)
+        solver.destroy()
+    emit(row="CG iterations/s driven by an expression", grid=N, csr_matrix=rates["csr_matrix"],
+         composite=rates["composite 2x2"], ratio=rates["composite 2x2"] / rates["csr_matrix"], steps=K)
+
+    # ------------------------------------------------------------------ copies
+    def wall(fn):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, r
+
+    A.copy_matrix("csr").destroy()            # warm-up (first-use allocations, kernel loads)
+    for target, trans in (("csr", False), ("csc", False), ("ellpack", False), ("csr", True)):
+        t, B = wall(lambda: A.copy_matrix(target, trans))
+        by = 24 * nnz + 8 * n
+        emit(row=f"copy_matrix csr -> {target}{' (transposed)' if trans else ''}", ms=t * 1e3, algorithmic_bytes=by,
+             gbs=by / t / 1e9, frac_of_measured_hbm=by / t / 1e9 / peak, entries_per_s=nnz / t)
+        B.destroy()
+
+    # host reference point: the oracle's restatement of the first-free-slot builder on a bounded sample
+    import oracle as orc
+
+    Ns = 512
+    sp, sn, sv = G.poisson2d_csr(Ns)
+    O = orc.Matrix(orc.CSR, Ns * Ns, Ns * Ns, sn, sv, ptr=sp)
+    t0 = time.perf_counter()
+    orc.copy_matrix(O, orc.CSC)
+    t_cpu = time.perf_counter() - t0
+    emit(row="cpu port: copy_matrix csr -> csc (cs_graph_build + copy_matrix_values)", sample=f"Poisson {Ns}^2",
+         entries_per_s=sn.size / t_cpu, cores=1, kind="port")
+
+    # ------------------------------------------------------------------ assembly
+    Nf = args.fem
+    I, J, V, _ = G.fem_p1_add_value_stream(Nf)
+    fptr, fnode, _ = G.fem_p1_csr(Nf)
+    ci, cj = (I + 1).astype(np.int32), (J + 1).astype(np.int32)
+    nv = Nf * Nf
+    F = sb.csr_matrix(nv, nv, fptr, fnode, np.zeros(fnode.size))
+    F.add_values(ci[:1000], cj[:1000], V[:1000])      # warm-up
+    t, _ = wall(lambda: F.add_values(ci, cj, V))
+    emit(row="add_value stream (P1 FEM assembly, csr)", vertices=nv, calls=int(ci.size), ms=t * 1e3,
+         calls_per_s=ci.size / t, h2d_bytes=16 * int(ci.size),
+         note="host pointers in: H2D of (i, j, z) inside the timed region; locate + stable bucket sort + ordered reduce")
+    ns = min(2_000_000, ci.size)
+    Of = orc.Matrix(orc.CSR, nv, nv, fnode, np.zeros(fnode.size), ptr=fptr)
+    t0 = time.perf_counter()
+    orc.add_values(Of, ci[:ns], cj[:ns], V[:ns])
+    t_cpu = time.perf_counter() - t0
+    emit(row="cpu port: add_value loop", sample=f"first {ns} calls", calls_per_s=ns / t_cpu, cores=1, kind="port")
+
+
+
+def run_ldu(args):
+    import torch
+
+    import sigma_b200 as sb
+    from sigma_b200 import generators as G
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    sb.init(0)
+    stream = torch.cuda.Stream(device=dev)
+    sb.set_stream(stream.cuda_stream)
+    N = args.lgrid
+    n = N * N
+    ptr, node, val = G.poisson2d_csr(N)
+    b_host, _ = G.poisson2d_rhs(N)
+    A = sb.csr_matrix(n, n, ptr, node, val)
+    with torch.cuda.stream(stream):
+        b = torch.from_numpy(b_host).to(dev)
+        x = torch.zeros(n, dtype=torch.float64, device=dev)
+    stream.synchronize()
+
+    def emit(**kw):
+        print(json.dumps(kw), flush=True)
+
+    def ev_time(fn, reps=1):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / reps
+
+    pc = sb.ldu()
+    t0 = time.perf_counter()
+    pc.setup(A)
+    sb.synchronize()
+    t_first = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    pc.setup(A)
+    sb.synchronize()
+    t_again = time.perf_counter() - t0
+    nf, nb = pc.factors()[-2:]
+    emit(row="ldu setup", grid=N, n=n, levels_forward=nf, levels_backward=nb, first_ms=t_first * 1e3,
+         refactor_ms=t_again * 1e3, note="first = read-back + host symbolic + upload + numeric; refactor = numeric only")
+    launches0 = sb.launch_count()
+    pc.solve_dev(A, x, b)
+    per_apply = sb.launch_count() - launches0
+    t_apply = ev_time(lambda: pc.solve_dev(A, x, b), 5)
+    emit(row="ldu apply (forward sweep, / D, backward sweep)", ms=t_apply * 1e3, launches=int(per_apply),
+         us_per_launch=t_apply * 1e6 / per_apply, algorithmic_bytes=12 * (node.size - n) + 40 * n,
+         note="latency-bound: one launch per level")
+    K = min(args.steps, 30)
+    tol = 1e-10 * float(np.linalg.norm(b_host))
+    rates = {}
+    for name, pcs in (("cg", None), ("cg + jacobi", sb.jacobi()), ("cg + ldu", pc)):
+        if pcs is not None and pcs is not pc:
+            pcs.setup(A)
+        s = sb.cg(tol)
+        s.set_max_iterations(K)
+        s.setup(A)
+        with torch.cuda.stream(stream):
+            x.zero_()
+        t = ev_time(lambda: s.solve_dev(A, x, b, pcs))
+        rates[name] = {"it_per_s": s.info()[0] / t, "res_after": float(np.sqrt(s.info()[1]))}
+        s.destroy()
+    emit(row=f"{K} CG iterations", **{k: v for k, v in rates.items()},
+         note="res_after: stopping quantity after K iterations (r.r for cg, r.z for the preconditioned forms)")
+    # CPU port on a bounded sample
+    import oracle as orc
+
+    Ns = min(N, 512)
+    sp, sn, sv = G.poisson2d_csr(Ns)
+    O = orc.Matrix(orc.CSR, Ns * Ns, Ns * Ns, sn, sv, ptr=sp)
+    t0 = time.perf_counter()
+    F = orc.ldu_setup(O)
+    t_setup = time.perf_counter() - t0
+    rb = np.ones(Ns * Ns)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        orc.ldu_solve(F, rb)
+    t_cpu = (time.perf_counter() - t0) / 5
+    emit(row="cpu port: ldu setup / apply", sample=f"Poisson {Ns}^2", setup_ms=t_setup * 1e3, apply_ms=t_cpu * 1e3,
+         rows_per_s_apply=Ns * Ns / t_cpu, cores=1, kind="port")
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -378,8 +656,19 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=30)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--quick", action="store_true", help="kernel A/B runs: print a short line, skip e2e and the CPU leg")
+    ap.add_argument("--rows", default="headline", choices=["headline", "widened", "ldu"],
+                    help="headline: the contract line (default); widened / ldu: the SURVEY 8f rows, one JSON line each")
+    ap.add_argument("--wgrid", type=int, default=2048)
+    ap.add_argument("--fem", type=int, default=1025)
+    ap.add_argument("--lgrid", type=int, default=1024)
+    ap.add_argument("--reps", type=int, default=50)
+    ap.add_argument("--cg-steps", type=int, default=100)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.rows == "widened":
+        run_widened(args)
+    elif args.rows == "ldu":
+        run_ldu(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
