@@ -264,6 +264,226 @@ cg_persistent_kernel(const CgPersistArgs a)
     }
 }
 
+// ---------------------------------------------------------------------------
+// EXPERIMENTAL, opt-in (SIGB_CG_SINGLE_REDUCE=1; not the default path, not yet
+// run on a GPU): the Chronopoulos-Gear arrangement of the same CG iteration
+// with ONE reduction per iteration instead of two.
+//
+//   given r, w = A r, gamma = r.r, delta = r.w      (one all-reduce of 2 values)
+//   beta = gamma / gamma_old ; alpha = gamma / (delta - beta gamma / alpha_old)
+//   p = r + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s
+//
+// In exact arithmetic p, x, r are those of cg_solve (s = A p by linearity);
+// the stopping quantity is the same r.r tested at the same iteration.  It is
+// NOT the reference's statement order, so results agree with the reference to
+// rounding only (CPU emulation on the 2-D Poisson problems: identical
+// iteration counts, solutions within 1e-14 relative) -- which is why it stays
+// opt-in.  What it buys on a sharded operator: two grid barriers and one
+// cross-GPU all-reduce per iteration instead of three and two, for 8 n more
+// bytes of vector traffic (72 n instead of 64 n).
+// Work vectors: p, s (the q slot), r, w (the z slot); unpreconditioned only.
+// ---------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void grid_allreduce_n(double (&v)[NV], const CgPersistArgs &a, Sync &s, int &pbuf,
+                                                 unsigned long long &red_seq, double (*sm)[kThreads / 32],
+                                                 double *s_bcast)
+{
+    static_assert(NV <= kRedVals, "the all-reduce inbox holds kRedVals values per slot");
+    block_tree<NV>(v, sm);
+    double *part = a.partials + (size_t)pbuf * NV * gridDim.x;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int d = 0; d < NV; d++) part[(size_t)d * gridDim.x + blockIdx.x] = v[d];
+    }
+    grid_barrier(s);
+    double t[NV];
+#pragma unroll
+    for (int d = 0; d < NV; d++) t[d] = 0.0;
+    for (unsigned j = threadIdx.x; j < gridDim.x; j += kThreads) {
+#pragma unroll
+        for (int d = 0; d < NV; d++) t[d] = add(t[d], __ldcg(part + (size_t)d * gridDim.x + j));
+    }
+    block_tree<NV>(t, sm);
+    pbuf ^= 1;
+    if (a.nranks > 1) {
+        red_seq++;
+        const int slot = (int)(red_seq & (kRedSlots - 1));
+        const unsigned flag = (unsigned)red_seq;
+        if (blockIdx.x == gridDim.x - 1 && threadIdx.x < 32) {
+#pragma unroll
+            for (int d = 0; d < NV; d++) {
+                const double local = __shfl_sync(0xffffffffu, t[d], 0);
+                if ((int)threadIdx.x < a.nranks) {
+                    RedEntry *e = a.peer_red[threadIdx.x]->red[slot][a.me];
+                    const unsigned long long bits = (unsigned long long)__double_as_longlong(local);
+                    st_word(&e[d].lo, (unsigned)bits, flag);
+                    st_word(&e[d].hi, (unsigned)(bits >> 32), flag);
+                }
+            }
+        }
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int d = 0; d < NV; d++) {
+                double g = 0.0;
+                for (int q = 0; q < a.nranks; q++) {
+                    const RedEntry *e = &a.red->red[slot][q][d];
+                    uint2 lo, hi;
+                    unsigned spins = 0;
+                    do { lo = ld_word(&e->lo); } while (lo.y != flag && ++spins < kSpinLimit);
+                    do { hi = ld_word(&e->hi); } while (hi.y != flag && ++spins < kSpinLimit);
+                    g = add(g, __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | lo.x)));
+                }
+                s_bcast[d] = g;
+            }
+        }
+    } else if (threadIdx.x == 0) {
+#pragma unroll
+        for (int d = 0; d < NV; d++) s_bcast[d] = t[d];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int d = 0; d < NV; d++) v[d] = s_bcast[d];
+    __syncthreads();
+}
+
+template <bool HALO>
+__global__ void __launch_bounds__(kThreads, 4)
+cg_single_reduce_kernel(const CgPersistArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ double sm_red[2][kThreads / 32];
+    __shared__ double s_bcast[2];
+
+    KState *st = a.st;
+    if (st->done[0]) return;
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    // a.x = x, a.p = p, a.q = s, a.r = r, a.z = w ; a.A: x1 = r - 1, y = w, u = r
+    double gamma = st->rr[0];
+    const double tol = st->tol;
+    const long long cap = st->cap, it0 = st->iters;
+    long long it = 0;
+    bool have = st->itc[0] != 0;        // resumed launch: w and delta of the last pass are still valid
+    double delta = st->st, alpha_old = st->alpha[0], gamma_old = st->rho[0];
+    bool first_of_solve = (it0 == 0 && !have);   // gamma comes from the host-side initial r.r
+    double gpart = 0.0;                 // this thread's share of r.r, accumulated where r is updated
+    Sync s{a.bar, 0ull, nullptr};
+    int pbuf = 0;
+    unsigned long long red_seq = a.nranks > 1 ? a.red->red_seq : 0ull;
+    unsigned long long hseq = 0;
+    if (HALO && a.A.sync.win != nullptr)
+        hseq = *reinterpret_cast<volatile unsigned long long *>(&a.A.sync.win->halo_seq);
+    TilePipe pipe;
+    bool stop = false, capped = false;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+
+    for (;;) {
+        if (!have) {
+            // ---- A: w = A r, partial r.w ; all-reduce (r.r, r.w) ---------------
+            double acc[1] = {0.0};
+            hseq++;
+            spmv_phase<MODE_SET, 1, HALO, false>(a.A, smem, mbar, pipe, acc, hseq, true);
+            double v[2] = {gpart, acc[0]};
+            grid_allreduce_n<2>(v, a, s, pbuf, red_seq, sm_red, s_bcast);
+            if (HALO && a.A.sync.win != nullptr && blockIdx.x == gridDim.x - 1 && tid < kMaxRanks &&
+                (a.A.sync.src_mask & (1u << tid)))
+                *reinterpret_cast<volatile unsigned long long *>(&a.A.sync.peer[tid]->ack[a.A.sync.me]) = hseq;
+            delta = v[1];
+            if (!first_of_solve) gamma = v[0];
+        }
+        have = false;
+        first_of_solve = false;
+        stop = !(sqrt(gamma) > tol);                                    // cg_solvers.f90:133
+        if (!stop && cap >= 0 && it0 + it >= cap) { stop = true; capped = true; }
+        if (stop || it >= a.max_iters) break;
+
+        double alpha, beta;
+        if (it0 + it == 0) {
+            beta = 0.0;
+            alpha = gamma / delta;
+        } else {
+            beta = gamma / gamma_old;
+            alpha = gamma / sub(delta, mul(beta, gamma) / alpha_old);
+        }
+
+        // ---- V: p = r + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; partial r.r
+        gpart = 0.0;
+        for (int64_t base = blockIdx.x * (int64_t)kThreads + tid; base < a.n; base += stride * 2) {
+            double ri[2], wi[2], pi[2], si[2], xi[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int64_t i = base + u * stride;
+                if (i < a.n) { ri[u] = a.r[i]; wi[u] = a.z[i]; pi[u] = a.p[i]; si[u] = a.q[i]; xi[u] = a.x[i]; }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int64_t i = base + u * stride;
+                if (i < a.n) {
+                    const double pn = add(ri[u], mul(beta, pi[u]));
+                    const double sn = add(wi[u], mul(beta, si[u]));
+                    const double rn = sub(ri[u], mul(alpha, sn));
+                    a.p[i] = pn;
+                    a.q[i] = sn;
+                    a.x[i] = add(xi[u], mul(alpha, pn));
+                    a.r[i] = rn;
+                    gpart = add(gpart, mul(rn, rn));
+                }
+            }
+        }
+        gamma_old = gamma;
+        alpha_old = alpha;
+        it++;
+        grid_barrier(s);   // r is complete before the next pass gathers (and pushes) it
+    }
+
+    if (pipe.primed && blockIdx.x < (unsigned)a.A.ntiles) {
+        const int4 d0 = load_desc(a.A.tiles + blockIdx.x);
+        if (tile_staged(d0)) mbar_wait(&mbar[pipe.sidx & 1u], (pipe.sidx >> 1) & 1u);
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        st->iters = it0 + it;
+        st->rr[0] = gamma;
+        st->rr[1] = gamma;
+        st->final_res2 = gamma;
+        st->done[0] = stop ? 1 : 0;
+        st->done[1] = stop ? 1 : 0;
+        if (capped) st->capped = 1;
+        st->st = delta;                 // state of a paused solve: the pass that was reduced but not applied
+        st->alpha[0] = alpha_old;
+        st->rho[0] = gamma_old;
+        st->itc[0] = stop ? 0 : 1;
+        if (a.nranks > 1) a.red->red_seq = red_seq;
+        if (HALO && a.A.sync.win != nullptr)
+            *reinterpret_cast<volatile unsigned long long *>(&a.A.sync.win->halo_seq) = hseq;
+    }
+}
+
+template <bool HALO>
+int launch_single_reduce(const CgPersistArgs &a, cudaStream_t st)
+{
+    const size_t smem = 2 * (size_t)kStageBytes;
+    int grid = 0;
+    SIGB_CHECK((occupancy_grid<cg_single_reduce_kernel<HALO>>(smem, &grid)));
+    CgPersistArgs b = a;
+    if (HALO && b.A.sync.win != nullptr) {
+        int pc = (b.A.sync.total_send + 2 * kThreads - 1) / (2 * kThreads);
+        b.A.sync.push_ctas = b.A.sync.total_send > 0 ? std::max(1, std::min(pc, grid)) : 0;
+    }
+    void *params[] = {(void *)&b};
+    SIGB_CUDA(cudaLaunchCooperativeKernel((const void *)cg_single_reduce_kernel<HALO>, dim3(grid), dim3(kThreads),
+                                          params, smem, st));
+    count_launch();
+    return SIGB_OK;
+}
+
 template <bool HALO, bool PC>
 int launch_persistent(const CgPersistArgs &a, cudaStream_t st)
 {
@@ -314,6 +534,34 @@ int cg_persistent_run(sigb_solver_t s, const CsrView &V, const double *val, cons
     const bool halo_on = halo.sync != nullptr;
     if (halo_on) return idiag ? launch_persistent<true, true>(a, st) : launch_persistent<true, false>(a, st);
     return idiag ? launch_persistent<false, true>(a, st) : launch_persistent<false, false>(a, st);
+}
+
+// EXPERIMENTAL single-reduction arrangement (see cg_single_reduce_kernel): x, p, r as in
+// cg_persistent_run, s_vec = the q slot, w = the z slot.  The kernel leaves the loop with
+// the last reduced pass stored in the KState, so a paused launch resumes without redoing it.
+int cg_single_reduce_run(sigb_solver_t s, const CsrView &V, const double *val, const DotSpec &halo, double *x,
+                         double *p, double *s_vec, double *r, double *w, int64_t n, const PersistComm &pcomm,
+                         long long max_iters)
+{
+    CgPersistArgs a;
+    DotSpec d = halo;
+    d.ndot = 1;
+    d.u = r;
+    SIGB_CHECK(fill_csr_args(V, val, r, w, d, &a.A));
+    a.x = x; a.p = p; a.q = s_vec; a.r = r; a.z = w;
+    a.idiag = nullptr;
+    a.n = n;
+    a.st = s->state;
+    a.bar = s->bar;
+    a.partials = s->pers_partials;
+    a.max_iters = max_iters;
+    a.red = (RedWin *)pcomm.red;
+    for (int k = 0; k < kMaxRanks; k++) a.peer_red[k] = (RedWin *)pcomm.peer_red[k];
+    a.me = pcomm.me;
+    a.nranks = pcomm.nranks;
+    cudaStream_t st = ctx().stream;
+    SIGB_CUDA(cudaMemsetAsync(s->bar, 0, 2 * sizeof(unsigned long long), st));
+    return halo.sync != nullptr ? launch_single_reduce<true>(a, st) : launch_single_reduce<false>(a, st);
 }
 
 }  // namespace sigb

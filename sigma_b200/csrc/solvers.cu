@@ -827,10 +827,19 @@ static int cg_solve_body(sigb_solver_t s, sigb_matrix_t A, double *x, const doub
         if (V != nullptr) {
             if (!s->bar) {
                 SIGB_CUDA(cudaMalloc((void **)&s->bar, 2 * sizeof(unsigned long long)));
-                SIGB_CUDA(cudaMalloc((void **)&s->pers_partials, sizeof(double) * 2 * kMaxGrid));
+                SIGB_CUDA(cudaMalloc((void **)&s->pers_partials, sizeof(double) * 4 * kMaxGrid));
+            }
+            // EXPERIMENTAL opt-in: one reduction per iteration (cg_persistent.cu); unpreconditioned only
+            static int single = -1;
+            if (single < 0) {
+                const char *e = getenv("SIGB_CG_SINGLE_REDUCE");
+                single = (e && atoi(e) == 1) ? 1 : 0;
             }
             for (;;) {
-                SIGB_CHECK(cg_persistent_run(s, *V, val, halo, x, p, q, r, z, idiag, n, 0, pcomm, 4096));
+                if (single && !idiag)
+                    SIGB_CHECK(cg_single_reduce_run(s, *V, val, halo, x, p, q, r, z, n, pcomm, 4096));
+                else
+                    SIGB_CHECK(cg_persistent_run(s, *V, val, halo, x, p, q, r, z, idiag, n, 0, pcomm, 4096));
                 SIGB_CHECK(sync_state(s));
                 if (s->state_host->done[0]) break;
             }

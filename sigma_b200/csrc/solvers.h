@@ -30,7 +30,7 @@ struct sigb_solver_s {
     sigb_matrix_t A = nullptr; // operator given to setup
     // persistent CG kernel (cg_persistent.cu)
     unsigned long long *bar = nullptr;   // grid barrier counter
-    double *pers_partials = nullptr;     // 2 x kMaxGrid CTA partial sums
+    double *pers_partials = nullptr;     // 2 buffers x 2 values x kMaxGrid CTA partial sums
     sigb::LduInfo *ldu = nullptr;        // sparse_ldu_solver: factors and level schedules (ldu.cu)
 };
 
@@ -69,6 +69,10 @@ struct CsrKernelArgs;
 int cg_persistent_run(sigb_solver_t s, const CsrView &V, const double *val, const DotSpec &halo, double *x,
                       double *p, double *q, double *r, double *z, const double *idiag, int64_t n, int grid_hint,
                       const PersistComm &pcomm, long long max_iters);
+// EXPERIMENTAL (SIGB_CG_SINGLE_REDUCE=1): Chronopoulos-Gear arrangement, one reduction per iteration
+int cg_single_reduce_run(sigb_solver_t s, const CsrView &V, const double *val, const DotSpec &halo, double *x,
+                         double *p, double *s_vec, double *r, double *w, int64_t n, const PersistComm &pcomm,
+                         long long max_iters);
 // Row-sharded operators: fills the all-reduce endpoints and the halo spec the
 // persistent kernel needs; *eligible = false when the operator uses a transport
 // the kernel cannot drive (NCCL).
