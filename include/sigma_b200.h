@@ -390,6 +390,13 @@ SIGB_API int sigb_halo_build(int32_t lo, int32_t hi, const int32_t *ptr_blk1,
                              const int32_t *node_glob1, int32_t *halo,
                              int32_t *nhalo, int32_t *local_node);
 
+/* Diagnostic, host-only: the row tiling the streaming CSR kernel uses for a
+ * pattern (<= 2045 entries and <= 512 rows per tile; a longer row alone).
+ * tiles holds {first row, end row, first entry, end entry} per tile, 0-based,
+ * capacity n tiles. */
+SIGB_API int sigb_debug_row_tiles(int32_t n, const int32_t *ptr1, int32_t *tiles,
+                                  int32_t *ntiles);
+
 /* Communicator.  unique_id is SIGB_UNIQUE_ID_BYTES bytes produced by
  * sigb_comm_unique_id on rank 0 and broadcast by the host (torch.distributed,
  * MPI, a file ...). */

@@ -32,6 +32,24 @@ int sigb_partition_rows(int32_t n, const int32_t *ptr1, int32_t nparts, int32_t 
     return SIGB_OK;
 }
 
+// Row tiling of the streaming CSR kernel (kernels_spmv.cu build_tiles_host), exposed so
+// that the index work can be checked without a GPU.  tiles: 4 int32 per tile
+// {first row, end row, first entry, end entry}, 0-based, capacity n tiles.
+int sigb_debug_row_tiles(int32_t n, const int32_t *ptr1, int32_t *tiles, int32_t *ntiles)
+{
+    SIGB_REQUIRE(n >= 0 && ptr1 && tiles && ntiles, SIGB_ERR_ARG, "sigb_debug_row_tiles: bad argument");
+    std::vector<TileDesc> t;
+    build_tiles_host(ptr1, n, t);
+    for (size_t k = 0; k < t.size(); k++) {
+        tiles[4 * k + 0] = t[k].rs;
+        tiles[4 * k + 1] = t[k].re;
+        tiles[4 * k + 2] = t[k].ks;
+        tiles[4 * k + 3] = t[k].ke;
+    }
+    *ntiles = (int32_t)t.size();
+    return SIGB_OK;
+}
+
 int sigb_halo_build(int32_t lo, int32_t hi, const int32_t *ptr_blk1, const int32_t *node_glob1,
                     int32_t *halo, int32_t *nhalo, int32_t *local_node)
 {

@@ -1,0 +1,62 @@
+"""Host-side row tiling of the streaming CSR kernel (csrc/kernels_spmv.cu build_tiles_host),
+checked without a GPU against the plain row-by-row greedy walk it replaces: consecutive rows
+while the tile holds <= 2045 stored entries and <= 512 rows; a longer row is a tile of its own."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from sigma_b200._capi import check, lib, ptr
+
+CAP, ROWS = 2045, 512
+
+
+def greedy(ptr1):
+    n = ptr1.size - 1
+    tiles, s = [], 0
+    while s < n:
+        e = s + 1
+        base = int(ptr1[s])
+        while e < n and int(ptr1[e + 1]) - base <= CAP and e - s < ROWS:
+            e += 1
+        tiles.append((s, e, int(ptr1[s]) - 1, int(ptr1[e]) - 1))
+        s = e
+    return np.array(tiles, np.int32).reshape(-1, 4)
+
+
+def library_tiles(ptr1):
+    ptr1 = np.ascontiguousarray(ptr1, np.int32)
+    n = ptr1.size - 1
+    out = np.empty((max(n, 1), 4), np.int32)
+    nt = C.c_int32()
+    check(lib().sigb_debug_row_tiles(n, ptr(ptr1), ptr(out), C.byref(nt)))
+    return out[: nt.value].copy()
+
+
+def cases():
+    rng = np.random.default_rng(0)
+    yield "empty", np.array([1], np.int32)
+    yield "one_row", np.array([1, 4], np.int32)
+    yield "uniform5", 1 + 5 * np.arange(0, 100_001, dtype=np.int64)
+    yield "all_empty_rows", np.ones(3000, np.int64)
+    yield "row_of_exactly_cap", np.concatenate([[1], 1 + np.cumsum([CAP, 1, CAP - 1, 1, 1])])
+    yield "long_rows", np.concatenate([[1], 1 + np.cumsum(rng.choice([0, 3, 700, 2045, 2046, 9000], 400))])
+    deg = rng.integers(0, 40, 50_000)
+    deg[rng.integers(0, deg.size, 30)] = rng.integers(2000, 5000, 30)
+    yield "random_with_spikes", np.concatenate([[1], 1 + np.cumsum(deg)])
+    yield "dense_band", 1 + 1000 * np.arange(0, 2001, dtype=np.int64)
+
+
+@pytest.mark.parametrize("case", list(cases()), ids=lambda c: c[0])
+def test_tiles_equal_the_greedy_walk(case):
+    _, p = case
+    p = np.asarray(p, np.int32)
+    got, want = library_tiles(p), greedy(p)
+    assert np.array_equal(got, want)
+    n = p.size - 1
+    if n:
+        # a partition of the rows, each tile within the limits unless it is a single long row
+        assert got[0, 0] == 0 and got[-1, 1] == n and np.array_equal(got[1:, 0], got[:-1, 1])
+        nrows, nent = got[:, 1] - got[:, 0], got[:, 3] - got[:, 2]
+        assert np.all(nrows >= 1) and np.all(nrows <= ROWS)
+        assert np.all((nent <= CAP) | (nrows == 1))
