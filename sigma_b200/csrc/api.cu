@@ -99,12 +99,17 @@ static int ensure_graph_transposed(sigb_graph_t g)
     t.ptr = ptr_t;
     t.node = node_t;
     g->perm_t = perm;
-    g->host_ptr_t.resize((size_t)ntargets + 1);
-    SIGB_CUDA(cudaMemcpy(g->host_ptr_t.data(), ptr_t, sizeof(int32_t) * ((size_t)ntargets + 1),
-                         cudaMemcpyDeviceToHost));
-    std::vector<TileDesc> tiles;
-    build_tiles_host(g->host_ptr_t.data(), ntargets, tiles);
-    SIGB_CHECK(upload_tiles(t, tiles));
+    if (device_tiles_enabled()) {
+        // EXPERIMENTAL (SIGB_DEVICE_TILES=1): no read-back of ptr, no host loop
+        SIGB_CHECK(build_tiles_device(ptr_t, ntargets, t, nullptr, nullptr));
+    } else {
+        g->host_ptr_t.resize((size_t)ntargets + 1);
+        SIGB_CUDA(cudaMemcpy(g->host_ptr_t.data(), ptr_t, sizeof(int32_t) * ((size_t)ntargets + 1),
+                             cudaMemcpyDeviceToHost));
+        std::vector<TileDesc> tiles;
+        build_tiles_host(g->host_ptr_t.data(), ntargets, tiles);
+        SIGB_CHECK(upload_tiles(t, tiles));
+    }
     g->has_transposed = true;
     return SIGB_OK;
 }

@@ -6,7 +6,11 @@ subprocess; the whole file is skipped unless SIGB_TEST_EXPERIMENTAL=1.
   SIGB_CG_SINGLE_REDUCE=1   persistent CG in the Chronopoulos-Gear arrangement: one
                             reduction per iteration (csrc/cg_persistent.cu).  Not the
                             reference's statement order: agreement to rounding only, held to
-                            the north_star bars (+-2 % iterations, 1e-10 relative)."""
+                            the north_star bars (+-2 % iterations, 1e-10 relative).
+  SIGB_DEVICE_TILES=1       the row tiling of the streaming CSR kernel built on the device
+                            (csrc/tiles_device.cu) for device transposes and matrix copies:
+                            index work, must equal the host tiling entry for entry, and the
+                            copy / transpose parity tests must stay green with it on."""
 import os
 import subprocess
 import sys
@@ -74,3 +78,36 @@ SINGLE_REDUCE = """
 def test_single_reduction_persistent_cg():
     out = run_snippet(SINGLE_REDUCE, SIGB_CG_SINGLE_REDUCE="1", SIGB_CG_PERSISTENT="1")
     assert "single-reduce ok" in out
+
+
+DEVICE_TILES = """
+    import ctypes as C
+    import numpy as np
+    import sigma_b200 as sb
+    from sigma_b200._capi import check, lib, ptr
+    import tests.test_row_tiles as T
+    sb.init(0)
+    for name, p in T.cases():
+        p = np.ascontiguousarray(p, np.int32)
+        n = p.size - 1
+        out = np.empty((max(n, 1), 4), np.int32)
+        nt = C.c_int32()
+        check(lib().sigb_debug_row_tiles_dev(n, ptr(p), ptr(out), C.byref(nt)))
+        want = T.library_tiles(p)
+        assert nt.value == want.shape[0] and np.array_equal(out[: nt.value], want), name
+    print("device tiles ok")
+"""
+
+
+def test_device_built_tiles_equal_the_host_tiling():
+    out = run_snippet(DEVICE_TILES)
+    assert "device tiles ok" in out
+
+
+def test_copy_and_transpose_parity_with_device_tiles():
+    e = dict(os.environ)
+    e["SIGB_DEVICE_TILES"] = "1"
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_convert.py",
+                        "tests/test_gpu_spmv.py", "tests/test_gpu_operators.py"], cwd=ROOT, env=e,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -60,3 +60,50 @@ def test_tiles_equal_the_greedy_walk(case):
         nrows, nent = got[:, 1] - got[:, 0], got[:, 3] - got[:, 2]
         assert np.all(nrows >= 1) and np.all(nrows <= ROWS)
         assert np.all((nent <= CAP) | (nrows == 1))
+
+
+def device_algorithm_replica(ptr1):
+    """numpy replica, step for step, of the EXPERIMENTAL device tiling (csrc/tiles_device.cu):
+    next(s) by bisection for all rows at once, the orbit of row 0 under next marked by pointer
+    doubling, marked rows compacted by an exclusive scan.  Runs on the CPU so the index logic is
+    checked without a GPU; the gated GPU test compares the kernels themselves."""
+    p = np.asarray(ptr1, np.int64)
+    n = p.size - 1
+    if n == 0:
+        return np.zeros((0, 4), np.int32), 0
+    s = np.arange(n)
+    limit = p[:-1] + CAP
+    hi = np.minimum(s + ROWS, n)
+    # largest e in [s + 1, hi] with p[e] <= limit, s + 1 when the first row alone is too long
+    e = np.searchsorted(p, limit, side="right") - 1          # largest index with p[idx] <= limit
+    nxt = np.concatenate([np.clip(e, s + 1, hi), [n]])
+    mark = np.zeros(n + 1, bool)
+    mark[0] = True
+    jump = nxt.copy()
+    rounds = 1
+    while (1 << rounds) <= n:
+        rounds += 1
+    used = 0
+    for _ in range(rounds):
+        src = np.flatnonzero(mark[:n])
+        dst = jump[src]
+        mark[dst[dst < n]] = True
+        done = jump[0] == n
+        jump = jump[jump]
+        used += 1
+        if done:
+            break
+    starts = np.flatnonzero(mark[:n])
+    tiles = np.stack([starts, nxt[starts], p[starts] - 1, p[nxt[starts]] - 1], axis=1).astype(np.int32)
+    return tiles, used
+
+
+@pytest.mark.parametrize("case", list(cases()), ids=lambda c: c[0])
+def test_device_algorithm_replica_equals_the_greedy_walk(case):
+    _, p = case
+    p = np.asarray(p, np.int32)
+    got, rounds = device_algorithm_replica(p)
+    want = greedy(p)
+    assert np.array_equal(got, want)
+    if want.shape[0] > 1:
+        assert rounds <= int(np.ceil(np.log2(want.shape[0]))) + 1   # log-depth, not one round per tile
