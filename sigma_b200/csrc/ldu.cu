@@ -19,6 +19,8 @@
 // in natural ordering is one anti-diagonal of the grid (2N - 1 levels of at
 // most N rows).  The value of the row is the drop-in coverage of the only
 // other preconditioner the reference ships, not bandwidth.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "device_utils.cuh"
@@ -37,6 +39,11 @@ struct LduInfo {
     int32_t *frows = nullptr, *brows = nullptr;
     std::vector<int32_t> flev, blev;  // level pointers (host): launches are driven from here
     sigb_matrix_t rows = nullptr;     // csc / ellpack sources: their row form (device copy), else null
+    // EXPERIMENTAL sync-free sweeps (SIGB_LDU_SYNCFREE=1): solution entries in flight as
+    // payload+flag words, per-row "factored" flags, and the sequence number of the last sweep
+    RedEntry *xs = nullptr;
+    unsigned *ready = nullptr;
+    unsigned sf_seq = 0;
     double *Lval() const { return fac; }
     double *Uval() const { return fac + nL; }
     double *D() const { return fac + nL + nU; }
@@ -140,9 +147,263 @@ divide_kernel(double *__restrict__ x, const double *__restrict__ D, int64_t n, c
         x[i] = x[i] / D[i];
 }
 
+// ---------------------------------------------------------------------------
+// EXPERIMENTAL, opt-in (SIGB_LDU_SYNCFREE=1; compiled in, not the default path,
+// not yet run on a GPU): the same sweeps WITHOUT one launch per level.
+//
+// One cooperative launch per sweep.  Threads take the rows in level order
+// (frows / brows: every row a row depends on sits at an earlier position) and
+// wait for exactly the entries they read instead of for a whole level:
+//   * triangular solves: a finished x(i) is published as two 8-byte words, each
+//     32 payload bits + the 32-bit sequence number of this sweep (the words of
+//     the all-reduce, device_utils.cuh).  A word is delivered as a unit, so a
+//     reader needs no fence and no second round trip: one L2 hop per
+//     dependency, against one launch (4 us) or one grid barrier (1-2 us) per level;
+//   * factorisation: a row reads whole rows of U and D(k) of its lower
+//     neighbours, so finished rows are announced by a flag behind a fence and
+//     read through L2.
+// Lanes never spin on their own: a warp runs one loop in which every unfinished
+// lane polls once and advances as far as it can, until all 32 are finished --
+// a dependency on a lower lane of the same warp resolves on the next trip.
+// Progress: all CTAs are resident (cooperative launch) and each warp takes its
+// positions in ascending order, so the lowest unfinished position of the sweep
+// always belongs to a running warp and has all its inputs.  Spins are bounded:
+// a wrong answer the tests catch, never a hung GPU.
+// Every row still does the reference's arithmetic in stored order with rounded
+// products, so the factors and the solves stay bit-identical to the serial loops.
+// ---------------------------------------------------------------------------
+constexpr unsigned kSweepSpinLimit = 1u << 24;
+
+__device__ __forceinline__ bool ll_try(const RedEntry *e, unsigned seq, double *out)
+{
+    const uint2 lo = ld_word(&e->lo), hi = ld_word(&e->hi);
+    if (lo.y != seq || hi.y != seq) return false;
+    *out = __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | lo.x));
+    return true;
+}
+__device__ __forceinline__ void ll_publish(RedEntry *e, unsigned seq, double v)
+{
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    st_word(&e->lo, (unsigned)bits, seq);
+    st_word(&e->hi, (unsigned)(bits >> 32), seq);
+}
+
+// (I + M) x = src, or with D: (I + M) x = src / D   (the x = x / D statement of ldu_solve
+// :169 folded into the start of the backward sweep: same division, same operands)
+template <bool DIVIDE>
+__global__ void __launch_bounds__(kThreads)
+tri_syncfree_kernel(const int32_t *__restrict__ rows, int32_t n, const int32_t *__restrict__ ptr1,
+                    const int32_t *__restrict__ node1, const double *__restrict__ val, const double *src,
+                    const double *__restrict__ D, double *x, RedEntry *xs, unsigned seq, unsigned sleep_ns,
+                    const int *skip)
+{
+    if (skip != nullptr && *skip != 0) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t base = blockIdx.x * (int64_t)kThreads + (threadIdx.x - lane); base < n; base += stride) {
+        const int64_t p = base + lane;
+        int32_t i = 0, k = 0, e = 0;
+        double z = 0.0;
+        bool done = true;
+        if (p < n) {
+            i = rows[p];
+            k = ptr1[i - 1] - 1;
+            e = ptr1[i] - 1;
+            z = DIVIDE ? src[i - 1] / D[i - 1] : src[i - 1];
+            done = false;
+        }
+        unsigned spins = 0;
+        for (;;) {
+            if (!done) {
+                while (k < e) {                                   // z = z - M%val(k) * x(node(k)), stored order
+                    double xj;
+                    if (!ll_try(xs + (node1[k] - 1), seq, &xj)) break;
+                    z = sub(z, mul(val[k], xj));
+                    k++;
+                }
+                if (k == e) {
+                    x[i - 1] = z;
+                    ll_publish(xs + (i - 1), seq, z);
+                    done = true;
+                }
+            }
+            if (__all_sync(0xffffffffu, done)) break;
+            if (++spins > kSweepSpinLimit) break;
+            if (sleep_ns) __nanosleep(sleep_ns);
+        }
+    }
+}
+
+// U%get_value(k, j) on a row another thread of this launch has written: read at L2
+__device__ __forceinline__ double get_value_cg(const int32_t *ptr1, const int32_t *node1, const double *val, int32_t i,
+                                               int32_t j)
+{
+    double z = 0.0;
+    for (int32_t k = ptr1[i - 1] - 1; k < ptr1[i] - 1; k++)
+        if (node1[k] == j) z = __ldcg(val + k);
+    return z;
+}
+
+// the elimination (:331-381) in one launch: the body of ldu_factor_level_kernel behind a wait
+// for the "factored" flags of the row's lower neighbours
+__global__ void __launch_bounds__(kThreads)
+ldu_factor_syncfree_kernel(const int32_t *__restrict__ rows, int32_t n, const int32_t *__restrict__ Lptr,
+                           const int32_t *__restrict__ Lnode, double *Lval, const int32_t *__restrict__ Uptr,
+                           const int32_t *__restrict__ Unode, double *Uval, double *D, unsigned *ready, unsigned seq,
+                           unsigned sleep_ns)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t base = blockIdx.x * (int64_t)kThreads + (threadIdx.x - lane); base < n; base += stride) {
+        const int64_t p = base + lane;
+        int32_t i = 0, lb = 0, dl = 0, w = 0;
+        bool done = true;
+        if (p < n) {
+            i = rows[p];
+            lb = Lptr[i - 1] - 1;
+            dl = Lptr[i] - 1 - lb;
+            done = false;
+        }
+        unsigned spins = 0;
+        for (;;) {
+            if (!done) {
+                while (w < dl && *reinterpret_cast<volatile unsigned *>(ready + (Lnode[lb + w] - 1)) == seq) w++;
+                if (w == dl) {
+                    __threadfence();   // the neighbours' rows were written before their flags
+                    const int32_t ub = Uptr[i - 1] - 1, du = Uptr[i] - 1 - ub;
+                    for (int32_t ind1 = 0; ind1 < dl; ind1++) {
+                        const int32_t k = Lnode[lb + ind1];
+                        double Lik = Lval[lb + ind1];
+                        const double Uki = get_value_cg(Uptr, Unode, Uval, k, i);
+                        const double Dk = __ldcg(D + (k - 1));
+                        Lik = Lik / Dk;
+                        Lval[lb + ind1] = Lik;
+                        const double LikDk = mul(Lik, Dk);
+                        for (int32_t ind2 = 0; ind2 < dl; ind2++) {
+                            const int32_t j = Lnode[lb + ind2];
+                            if (j > k) {
+                                const double Ukj = get_value_cg(Uptr, Unode, Uval, k, j);
+                                Lval[lb + ind2] = add(Lval[lb + ind2], -mul(LikDk, Ukj));
+                            }
+                        }
+                        D[i - 1] = sub(D[i - 1], mul(LikDk, Uki));
+                        for (int32_t ind2 = 0; ind2 < du; ind2++) {
+                            const int32_t j = Unode[ub + ind2];
+                            const double Ukj = get_value_cg(Uptr, Unode, Uval, k, j);
+                            Uval[ub + ind2] = add(Uval[ub + ind2], -mul(LikDk, Ukj));
+                        }
+                    }
+                    const double Di = D[i - 1];
+                    for (int32_t ind2 = 0; ind2 < du; ind2++) Uval[ub + ind2] = Uval[ub + ind2] / Di;
+                    __threadfence();   // row i of U and D(i) before the flag
+                    *reinterpret_cast<volatile unsigned *>(ready + (i - 1)) = seq;
+                    done = true;
+                }
+            }
+            if (__all_sync(0xffffffffu, done)) break;
+            if (++spins > kSweepSpinLimit) break;
+            if (sleep_ns) __nanosleep(sleep_ns);
+        }
+    }
+}
+
+struct SyncFreeCfg {
+    bool on = false;
+    int ctas_per_sm = 2;
+    unsigned sleep_ns = 0;
+};
+const SyncFreeCfg &syncfree_cfg()
+{
+    static SyncFreeCfg c;
+    static bool read = false;
+    if (!read) {
+        const char *e = getenv("SIGB_LDU_SYNCFREE");
+        c.on = e && atoi(e) == 1;
+        if ((e = getenv("SIGB_LDU_SF_CTAS_PER_SM")) && atoi(e) > 0) c.ctas_per_sm = atoi(e);
+        if ((e = getenv("SIGB_LDU_SF_SLEEP_NS")) && atoi(e) >= 0) c.sleep_ns = (unsigned)atoi(e);
+        read = true;
+    }
+    return c;
+}
+
+// grid of a sweep kernel: the requested CTAs per SM, never more than can be resident
+template <typename K>
+int syncfree_grid(K kernel, int64_t n, int *grid)
+{
+    int per_sm = 0;
+    SIGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > syncfree_cfg().ctas_per_sm) per_sm = syncfree_cfg().ctas_per_sm;
+    int64_t g = (int64_t)per_sm * ctx().num_sms;
+    const int64_t need = (n + kThreads - 1) / kThreads;
+    if (g > need) g = need;
+    if (g < 1) g = 1;
+    *grid = (int)g;
+    return SIGB_OK;
+}
+
+// scratch of the sync-free sweeps; hands out the next sequence number (0 = never written)
+int syncfree_prepare(LduInfo *F, unsigned *seq)
+{
+    cudaStream_t st = ctx().stream;
+    const size_t n = (size_t)(F->n > 0 ? F->n : 1);
+    if (!F->xs) {
+        SIGB_CUDA(cudaMalloc((void **)&F->xs, sizeof(RedEntry) * n));
+        SIGB_CUDA(cudaMalloc((void **)&F->ready, sizeof(unsigned) * n));
+        F->sf_seq = 0;
+    }
+    if (F->sf_seq == 0 || F->sf_seq == 0xffffffffu) {   // first use, or the counter is about to wrap
+        SIGB_CUDA(cudaMemsetAsync(F->xs, 0, sizeof(RedEntry) * n, st));
+        SIGB_CUDA(cudaMemsetAsync(F->ready, 0, sizeof(unsigned) * n, st));
+        F->sf_seq = 0;
+    }
+    *seq = ++F->sf_seq;
+    return SIGB_OK;
+}
+
+template <bool DIVIDE>
+int launch_tri_syncfree(LduInfo *F, const int32_t *rows, const int32_t *ptr1, const int32_t *node1, const double *val,
+                        const double *src, double *x, const int *skip)
+{
+    unsigned seq = 0;
+    SIGB_CHECK(syncfree_prepare(F, &seq));
+    int grid = 0;
+    SIGB_CHECK(syncfree_grid(tri_syncfree_kernel<DIVIDE>, F->n, &grid));
+    int32_t n = F->n;
+    const double *D = F->D();
+    RedEntry *xs = F->xs;
+    unsigned sleep_ns = syncfree_cfg().sleep_ns;
+    void *params[] = {(void *)&rows, (void *)&n, (void *)&ptr1, (void *)&node1, (void *)&val, (void *)&src,
+                      (void *)&D, (void *)&x, (void *)&xs, (void *)&seq, (void *)&sleep_ns, (void *)&skip};
+    SIGB_CUDA(cudaLaunchCooperativeKernel((const void *)tri_syncfree_kernel<DIVIDE>, dim3(grid), dim3(kThreads), params,
+                                          0, ctx().stream));
+    count_launch();
+    return SIGB_OK;
+}
+
+int launch_factor_syncfree(LduInfo *F)
+{
+    unsigned seq = 0;
+    SIGB_CHECK(syncfree_prepare(F, &seq));
+    int grid = 0;
+    SIGB_CHECK(syncfree_grid(ldu_factor_syncfree_kernel, F->n, &grid));
+    const int32_t *rows = F->frows, *Lptr = F->Lptr, *Lnode = F->Lnode, *Uptr = F->Uptr, *Unode = F->Unode;
+    int32_t n = F->n;
+    double *Lval = F->Lval(), *Uval = F->Uval(), *D = F->D();
+    unsigned *ready = F->ready;
+    unsigned sleep_ns = syncfree_cfg().sleep_ns;
+    void *params[] = {(void *)&rows, (void *)&n, (void *)&Lptr, (void *)&Lnode, (void *)&Lval, (void *)&Uptr,
+                      (void *)&Unode, (void *)&Uval, (void *)&D, (void *)&ready, (void *)&seq, (void *)&sleep_ns};
+    SIGB_CUDA(cudaLaunchCooperativeKernel((const void *)ldu_factor_syncfree_kernel, dim3(grid), dim3(kThreads), params,
+                                          0, ctx().stream));
+    count_launch();
+    return SIGB_OK;
+}
+
 void free_ldu(LduInfo *F)
 {
     if (!F) return;
+    cudaFree(F->xs); cudaFree(F->ready);
     cudaFree(F->Lptr); cudaFree(F->Lnode); cudaFree(F->Uptr); cudaFree(F->Unode);
     cudaFree(F->fac); cudaFree(F->dest); cudaFree(F->frows); cudaFree(F->brows);
     if (F->rows) sigb_matrix_destroy(F->rows);
@@ -241,6 +502,11 @@ int ldu_setup_dev(sigb_solver_t s, sigb_matrix_t A)
         ldu_scatter_kernel<<<grid_for(F->ne), kThreads, 0, st>>>(R->val, F->dest, F->ne, F->fac);
         count_launch();
     }
+    if (syncfree_cfg().on && n > 0) {   // EXPERIMENTAL: the elimination in one launch
+        SIGB_CHECK(launch_factor_syncfree(F));
+        SIGB_CUDA(cudaGetLastError());
+        return SIGB_OK;
+    }
     // the elimination, level by level
     const int nlev = (int)F->flev.size() - 1;
     for (int l = 0; l < nlev; l++) {
@@ -260,6 +526,13 @@ int ldu_apply_dev(sigb_solver_t s, double *x, const double *b, const int *skip_f
     SIGB_REQUIRE(F, SIGB_ERR_STATE, "ldu solve: pc%%setup(A) has not been called");
     cudaStream_t st = ctx().stream;
     const int32_t n = F->n;
+    if (syncfree_cfg().on && n > 0) {
+        // EXPERIMENTAL: two launches; x = b and x = x / D are folded into the sweeps' first reads
+        SIGB_CHECK(launch_tri_syncfree<false>(F, F->frows, F->Lptr, F->Lnode, F->Lval(), b, x, skip_flag));
+        SIGB_CHECK(launch_tri_syncfree<true>(F, F->brows, F->Uptr, F->Unode, F->Uval(), x, x, skip_flag));
+        SIGB_CUDA(cudaGetLastError());
+        return SIGB_OK;
+    }
     if (x != b) {
         copy_kernel<<<grid_for(n), kThreads, 0, st>>>(b, x, n, skip_flag);
         count_launch();

@@ -10,7 +10,11 @@ subprocess; the whole file is skipped unless SIGB_TEST_EXPERIMENTAL=1.
   SIGB_DEVICE_TILES=1       the row tiling of the streaming CSR kernel built on the device
                             (csrc/tiles_device.cu) for device transposes and matrix copies:
                             index work, must equal the host tiling entry for entry, and the
-                            copy / transpose parity tests must stay green with it on."""
+                            copy / transpose parity tests must stay green with it on.
+  SIGB_LDU_SYNCFREE=1       ILDU(0) factorisation and triangular sweeps as one cooperative launch
+                            each, rows waiting for the entries they read instead of one launch
+                            per level (csrc/ldu.cu).  Same arithmetic per row: the ILDU parity
+                            tests (bit-exact factors and solves) must stay green with it on."""
 import os
 import subprocess
 import sys
@@ -110,4 +114,15 @@ def test_copy_and_transpose_parity_with_device_tiles():
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_convert.py",
                         "tests/test_gpu_spmv.py", "tests/test_gpu_operators.py"], cwd=ROOT, env=e,
                        capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("knobs", [{}, {"SIGB_LDU_SF_CTAS_PER_SM": "1"}, {"SIGB_LDU_SF_SLEEP_NS": "100"}],
+                         ids=["default", "1cta_per_sm", "sleep100ns"])
+def test_ldu_parity_with_syncfree_sweeps(knobs):
+    e = dict(os.environ)
+    e["SIGB_LDU_SYNCFREE"] = "1"
+    e.update(knobs)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_ldu.py"], cwd=ROOT,
+                       env=e, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -134,3 +134,75 @@ def test_symbolic_rejects_bad_columns():
     with pytest.raises(sb.SigmaError) as e:
         sb.ldu_symbolic(2, [1, 2, 3], [1, 5])
     assert e.value.status == 1
+
+
+def syncfree_sweep_model(rows, ptr, node, val, start, n, grid_threads, rng, warp=4):
+    """Model of tri_syncfree_kernel's control flow (csrc/ldu.cu, EXPERIMENTAL): positions in
+    level order dealt to `grid_threads` resident threads grid-stride, a warp = `warp`
+    consecutive lanes running ONE loop in which every unfinished lane polls once and advances
+    as far as it can; warps are scheduled in random order, one loop trip at a time.  Returns
+    the solution and the number of trips of the busiest warp; raises if no warp can progress."""
+    x = np.full(n, np.nan)
+    published = np.zeros(n, bool)
+    nwarps = grid_threads // warp
+    state = []
+    for w in range(nwarps):
+        state.append({"base": w * warp, "lanes": None, "trips": 0})
+
+    def load(st):
+        lanes = []
+        for lane in range(warp):
+            p_ = st["base"] + lane
+            if p_ < n:
+                i = rows[p_]
+                lanes.append({"i": i, "k": ptr[i - 1] - 1, "e": ptr[i] - 1, "z": start[i - 1], "done": False})
+            else:
+                lanes.append({"done": True})
+        st["lanes"] = lanes
+
+    live = [w for w in range(nwarps) if state[w]["base"] < n]
+    for w in live:
+        load(state[w])
+    idle_rounds = 0
+    while live:
+        progressed = False
+        for w in rng.permutation(live):
+            st = state[w]
+            st["trips"] += 1
+            for ln in st["lanes"]:
+                if ln["done"]:
+                    continue
+                while ln["k"] < ln["e"] and published[node[ln["k"]] - 1]:
+                    ln["z"] = ln["z"] - val[ln["k"]] * x[node[ln["k"]] - 1]
+                    ln["k"] += 1
+                    progressed = True
+                if ln["k"] == ln["e"]:
+                    x[ln["i"] - 1] = ln["z"]
+                    published[ln["i"] - 1] = True
+                    ln["done"] = True
+                    progressed = True
+            if all(ln["done"] for ln in st["lanes"]):
+                st["base"] += grid_threads
+                if st["base"] < n:
+                    load(st)
+                else:
+                    live = [v for v in live if v != w]
+        idle_rounds = 0 if progressed else idle_rounds + 1
+        assert idle_rounds < 2, "no warp can make progress: the sweep would hang"
+    return x, max(st["trips"] for st in state)
+
+
+@pytest.mark.parametrize("case", list(cases()), ids=lambda c: c[0])
+@pytest.mark.parametrize("grid_threads", [4, 16, 64])
+def test_syncfree_sweep_model_terminates_and_matches(orc, case, grid_threads):
+    """The opt-in sync-free sweeps: under random warp scheduling, with levels cutting through
+    warps and fewer resident threads than rows, every sweep terminates and gives the serial
+    result bit for bit."""
+    _, n, ptr, node, val = case
+    S = sb.ldu_symbolic(n, ptr, node)
+    F = orc.ldu_setup(orc.Matrix(orc.CSR, n, n, node, val, ptr=ptr))
+    rng = np.random.default_rng(grid_threads)
+    b = rng.standard_normal(n)
+    y, _ = syncfree_sweep_model(S["forward_rows"], F.Lptr, F.Lnode, F.Lval, b, n, grid_threads, rng)
+    x, _ = syncfree_sweep_model(S["backward_rows"], F.Uptr, F.Unode, F.Uval, y / F.D, n, grid_threads, rng)
+    assert np.array_equal(x, orc.ldu_solve(F, b))
