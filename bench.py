@@ -166,6 +166,35 @@ def run_reference(args):
 # ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
+PHASES = ("spmv", "barrier1", "xgpu1", "r_update", "barrier2", "xgpu2", "p_update", "barrier3")
+
+
+def phase_report(rank, ms_per_iter):
+    """Diagnostic library builds only (csrc/Makefile VARIANT=_timers, SIGB_LIB_VARIANT=_timers):
+    where an iteration of the persistent CG kernel spends its time, per rank, on stderr.  Numbers
+    from such a build are for the breakdown only -- never a bench value."""
+    import ctypes as C
+
+    from sigma_b200._capi import check, lib
+
+    buf = (C.c_ulonglong * 27)()
+    ok = C.c_int(0)
+    check(lib().sigb_debug_cg_phase_cycles(buf, C.byref(ok)))
+    if not ok.value or ms_per_iter is None:
+        return
+    rows = {}
+    for c, name in enumerate(("first_cta", "middle_cta", "last_cta")):
+        it = buf[c * 9 + 8]
+        if it:
+            cyc = [buf[c * 9 + k] / it for k in range(8)]
+            tot = sum(cyc)
+            # scale cycles to the measured iteration time (the SM clock is not assumed)
+            rows[name] = {ph: round(v / tot * ms_per_iter * 1e3, 2) for ph, v in zip(PHASES, cyc)}
+            rows[name]["iterations"] = int(it)
+    print(json.dumps({"phase_us_per_iteration": rows, "rank": rank, "ms_per_iter": ms_per_iter}), file=sys.stderr,
+          flush=True)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -259,8 +288,10 @@ def run_ours(args):
     with torch.cuda.stream(stream):
         x_dev.zero_()
     launches0 = sb.launch_count()
+    phase_report(rank, None)            # diagnostic builds: drop what the warm-up accumulated
     with ClockSampler(local) as clk:
         ms_cg = timed(lambda: solver.solve_dev(A, x_dev, b_dev))
+        phase_report(rank, ms_cg / K)   # no-op unless SIGB_LIB_VARIANT=_timers
         # dominant kernel, live: CSR SpMV + fused dot (q = A p, p.q)
         reps = max(20, min(K, 200))
 

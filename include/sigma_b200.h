@@ -402,6 +402,15 @@ SIGB_API int sigb_debug_row_tiles(int32_t n, const int32_t *ptr1, int32_t *tiles
 SIGB_API int sigb_debug_row_tiles_dev(int32_t n, const int32_t *ptr1, int32_t *tiles,
                                       int32_t *ntiles);
 
+/* Diagnostic: SM cycles per phase of the persistent CG kernel, accumulated since
+ * the last call (then reset), for its first / middle / last CTA:
+ * out[cta * 9 + k], k = 0 SpMV, 1 barrier of reduction 1, 2 cross-GPU part of
+ * reduction 1, 3 residual update, 4 barrier of reduction 2, 5 cross-GPU part of
+ * reduction 2, 6 direction update, 7 closing barrier, 8 iterations counted.
+ * *supported = 0 and zeros unless the library was built with
+ * -DSIGB_PHASE_TIMERS (csrc/Makefile: make VARIANT=_timers DEFS=-DSIGB_PHASE_TIMERS). */
+SIGB_API int sigb_debug_cg_phase_cycles(unsigned long long *out27, int *supported);
+
 /* Communicator.  unique_id is SIGB_UNIQUE_ID_BYTES bytes produced by
  * sigb_comm_unique_id on rank 0 and broadcast by the host (torch.distributed,
  * MPI, a file ...). */

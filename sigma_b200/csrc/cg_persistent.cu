@@ -32,6 +32,9 @@
 
 namespace sigb {
 
+constexpr int kPhaseSlots = 8;   // phases timed by SIGB_PHASE_TIMERS builds (see PhaseClock)
+constexpr int kPhaseCtas = 3;    // first, middle, last CTA
+
 struct CgPersistArgs {
     CsrKernelArgs A;            // matrix, tile table, x1 = p - 1, y = q, u = p, halo sync
     double *x, *p, *q, *r, *z;
@@ -44,6 +47,7 @@ struct CgPersistArgs {
     RedWin *red;                // all-reduce inbox (nranks > 1)
     RedWin *peer_red[kMaxRanks];
     int me, nranks;
+    unsigned long long *phase_dbg;  // SIGB_PHASE_TIMERS builds: kPhaseCtas x kPhaseSlots cycle counters
 };
 
 namespace {
@@ -52,6 +56,36 @@ struct Sync {
     unsigned long long *bar;
     unsigned long long epoch;   // barriers passed (uniform across the grid)
     int *abort_flag;
+};
+
+// Diagnostic build only (make VARIANT=_timers DEFS=-DSIGB_PHASE_TIMERS, loaded with
+// SIGB_LIB_VARIANT=_timers): where an iteration of the persistent kernel spends its time.
+// Three CTAs (first, middle, last) accumulate SM cycles per phase in registers and add them
+// to phase_dbg on exit; the product build compiles all of it away.
+//   0 spmv   1 barrier of reduction 1   2 cross-GPU part of reduction 1   3 phase B
+//   4 barrier of reduction 2   5 cross-GPU part of reduction 2   6 phase C   7 closing barrier
+struct PhaseClock {
+#ifdef SIGB_PHASE_TIMERS
+    long long last = 0;
+    unsigned long long acc[kPhaseSlots] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool on = false;
+    __device__ __forceinline__ void start(bool enable) { on = enable; if (on) last = clock64(); }
+    __device__ __forceinline__ void stamp(int k)
+    {
+        if (on) { const long long t = clock64(); acc[k] += (unsigned long long)(t - last); last = t; }
+    }
+    __device__ __forceinline__ void flush(unsigned long long *dst, int which, long long iters)
+    {
+        if (on && dst) {
+            for (int k = 0; k < kPhaseSlots; k++) atomicAdd(dst + which * (kPhaseSlots + 1) + k, acc[k]);
+            atomicAdd(dst + which * (kPhaseSlots + 1) + kPhaseSlots, (unsigned long long)iters);
+        }
+    }
+#else
+    __device__ __forceinline__ void start(bool) {}
+    __device__ __forceinline__ void stamp(int) {}
+    __device__ __forceinline__ void flush(unsigned long long *, int, long long) {}
+#endif
 };
 
 __device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v)
@@ -94,13 +128,14 @@ __device__ __forceinline__ void grid_barrier(Sync &s)
 // CTA), then over the ranks (rank order).  Contains one grid barrier.
 __device__ __forceinline__ double grid_allreduce(double v, const CgPersistArgs &a, Sync &s, int &pbuf,
                                                  unsigned long long &red_seq, double (*sm)[kThreads / 32],
-                                                 double *s_bcast)
+                                                 double *s_bcast, PhaseClock &clk, int slot0)
 {
     double acc[1] = {v};
     block_tree<1>(acc, sm);
     double *part = a.partials + (size_t)pbuf * gridDim.x;
     if (threadIdx.x == 0) part[blockIdx.x] = acc[0];
     grid_barrier(s);
+    clk.stamp(slot0);
     double t[1] = {0.0};
     for (unsigned j = threadIdx.x; j < gridDim.x; j += kThreads) t[0] = add(t[0], __ldcg(part + j));
     block_tree<1>(t, sm);
@@ -138,6 +173,7 @@ __device__ __forceinline__ double grid_allreduce(double v, const CgPersistArgs &
     __syncthreads();
     const double out = *s_bcast;
     __syncthreads();
+    clk.stamp(slot0 + 1);
     return out;
 }
 
@@ -175,13 +211,17 @@ cg_persistent_kernel(const CgPersistArgs a)
     bool stop = false, capped = false;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     const double *rz = PC ? a.z : a.r;
+    PhaseClock clk;
+    const int clk_which = blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x / 2 ? 1 : (blockIdx.x == gridDim.x - 1 ? 2 : -1));
+    clk.start(tid == 0 && clk_which >= 0);
 
     for (;;) {
         // ---- A: q = A p, p.q ------------------------------------------------
         double acc[1] = {0.0};
         hseq++;
         spmv_phase<MODE_SET, 1, HALO, false>(a.A, smem, mbar, pipe, acc, hseq, true);
-        const double pq = grid_allreduce(acc[0], a, s, pbuf, red_seq, sm_red, &s_bcast);
+        clk.stamp(0);
+        const double pq = grid_allreduce(acc[0], a, s, pbuf, red_seq, sm_red, &s_bcast, clk, 1);
         if (HALO && a.A.sync.win != nullptr && blockIdx.x == gridDim.x - 1 && tid < kMaxRanks &&
             (a.A.sync.src_mask & (1u << tid))) {
             // every CTA is past the barrier, i.e. has consumed this landing buffer
@@ -216,7 +256,8 @@ cg_persistent_kernel(const CgPersistArgs a)
                 }
             }
         }
-        const double dpr = grid_allreduce(dsum, a, s, pbuf, red_seq, sm_red, &s_bcast);
+        clk.stamp(3);
+        const double dpr = grid_allreduce(dsum, a, s, pbuf, red_seq, sm_red, &s_bcast, clk, 4);
         const double beta = dpr / rr;                                   // :141
         it++;
         stop = !(sqrt(dpr) > tol);                                      // :133
@@ -241,9 +282,12 @@ cg_persistent_kernel(const CgPersistArgs a)
             }
         }
         rr = dpr;                                                       // :143
+        clk.stamp(6);
         grid_barrier(s);
+        clk.stamp(7);
         if (stop || pause) break;
     }
+    clk.flush(a.phase_dbg, clk_which, it);
 
     // the tile primed for a pass that will not run must land before we exit
     if (pipe.primed && blockIdx.x < (unsigned)a.A.ntiles) {
@@ -286,7 +330,7 @@ cg_persistent_kernel(const CgPersistArgs a)
 template <int NV>
 __device__ __forceinline__ void grid_allreduce_n(double (&v)[NV], const CgPersistArgs &a, Sync &s, int &pbuf,
                                                  unsigned long long &red_seq, double (*sm)[kThreads / 32],
-                                                 double *s_bcast)
+                                                 double *s_bcast, PhaseClock &clk, int slot0)
 {
     static_assert(NV <= kRedVals, "the all-reduce inbox holds kRedVals values per slot");
     block_tree<NV>(v, sm);
@@ -296,6 +340,7 @@ __device__ __forceinline__ void grid_allreduce_n(double (&v)[NV], const CgPersis
         for (int d = 0; d < NV; d++) part[(size_t)d * gridDim.x + blockIdx.x] = v[d];
     }
     grid_barrier(s);
+    clk.stamp(slot0);
     double t[NV];
 #pragma unroll
     for (int d = 0; d < NV; d++) t[d] = 0.0;
@@ -344,6 +389,7 @@ __device__ __forceinline__ void grid_allreduce_n(double (&v)[NV], const CgPersis
 #pragma unroll
     for (int d = 0; d < NV; d++) v[d] = s_bcast[d];
     __syncthreads();
+    clk.stamp(slot0 + 1);
 }
 
 template <bool HALO>
@@ -384,6 +430,9 @@ cg_single_reduce_kernel(const CgPersistArgs a)
     TilePipe pipe;
     bool stop = false, capped = false;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
+    PhaseClock clk;   // slots used here: 0 spmv, 1 barrier, 2 cross-GPU part, 6 vector phase, 7 closing barrier
+    const int clk_which = blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x / 2 ? 1 : (blockIdx.x == gridDim.x - 1 ? 2 : -1));
+    clk.start(tid == 0 && clk_which >= 0);
 
     for (;;) {
         if (!have) {
@@ -391,8 +440,9 @@ cg_single_reduce_kernel(const CgPersistArgs a)
             double acc[1] = {0.0};
             hseq++;
             spmv_phase<MODE_SET, 1, HALO, false>(a.A, smem, mbar, pipe, acc, hseq, true);
+            clk.stamp(0);
             double v[2] = {gpart, acc[0]};
-            grid_allreduce_n<2>(v, a, s, pbuf, red_seq, sm_red, s_bcast);
+            grid_allreduce_n<2>(v, a, s, pbuf, red_seq, sm_red, s_bcast, clk, 1);
             if (HALO && a.A.sync.win != nullptr && blockIdx.x == gridDim.x - 1 && tid < kMaxRanks &&
                 (a.A.sync.src_mask & (1u << tid)))
                 *reinterpret_cast<volatile unsigned long long *>(&a.A.sync.peer[tid]->ack[a.A.sync.me]) = hseq;
@@ -441,8 +491,11 @@ cg_single_reduce_kernel(const CgPersistArgs a)
         gamma_old = gamma;
         alpha_old = alpha;
         it++;
+        clk.stamp(6);
         grid_barrier(s);   // r is complete before the next pass gathers (and pushes) it
+        clk.stamp(7);
     }
+    clk.flush(a.phase_dbg, clk_which, it);
 
     if (pipe.primed && blockIdx.x < (unsigned)a.A.ntiles) {
         const int4 d0 = load_desc(a.A.tiles + blockIdx.x);
@@ -504,6 +557,23 @@ int launch_persistent(const CgPersistArgs &a, cudaStream_t st)
 
 }  // namespace
 
+// SIGB_PHASE_TIMERS builds: one device buffer per process, (kPhaseSlots + 1) counters for each
+// of the kPhaseCtas observed CTAs (the last one counts iterations); null in the product build.
+static unsigned long long *phase_dbg_buffer()
+{
+#ifdef SIGB_PHASE_TIMERS
+    static unsigned long long *buf = nullptr;
+    if (!buf) {
+        if (cudaMalloc((void **)&buf, sizeof(unsigned long long) * kPhaseCtas * (kPhaseSlots + 1)) != cudaSuccess)
+            return nullptr;
+        cudaMemset(buf, 0, sizeof(unsigned long long) * kPhaseCtas * (kPhaseSlots + 1));
+    }
+    return buf;
+#else
+    return nullptr;
+#endif
+}
+
 // Fill the SpMV argument block the way launch_csr_spmv does (kernels_spmv.cu).
 int fill_csr_args(const CsrView &V, const double *val, const double *x, double *y, const DotSpec &dot,
                   CsrKernelArgs *out);
@@ -529,6 +599,7 @@ int cg_persistent_run(sigb_solver_t s, const CsrView &V, const double *val, cons
     for (int k = 0; k < kMaxRanks; k++) a.peer_red[k] = (RedWin *)pcomm.peer_red[k];
     a.me = pcomm.me;
     a.nranks = pcomm.nranks;
+    a.phase_dbg = phase_dbg_buffer();
     cudaStream_t st = ctx().stream;
     SIGB_CUDA(cudaMemsetAsync(s->bar, 0, 2 * sizeof(unsigned long long), st));
     const bool halo_on = halo.sync != nullptr;
@@ -559,9 +630,36 @@ int cg_single_reduce_run(sigb_solver_t s, const CsrView &V, const double *val, c
     for (int k = 0; k < kMaxRanks; k++) a.peer_red[k] = (RedWin *)pcomm.peer_red[k];
     a.me = pcomm.me;
     a.nranks = pcomm.nranks;
+    a.phase_dbg = phase_dbg_buffer();
     cudaStream_t st = ctx().stream;
     SIGB_CUDA(cudaMemsetAsync(s->bar, 0, 2 * sizeof(unsigned long long), st));
     return halo.sync != nullptr ? launch_single_reduce<true>(a, st) : launch_single_reduce<false>(a, st);
 }
 
 }  // namespace sigb
+
+extern "C" {
+
+// Diagnostic: cycles per phase of the persistent CG kernel accumulated since the last call
+// (then reset), for the first / middle / last CTA: out[cta * 9 + k], k = 0..7 the phases
+// listed at PhaseClock, k = 8 the iterations counted.  *supported = 0 (and zeros) unless the
+// library was built with -DSIGB_PHASE_TIMERS.
+int sigb_debug_cg_phase_cycles(unsigned long long *out, int *supported)
+{
+    using namespace sigb;
+    SIGB_REQUIRE(out && supported, SIGB_ERR_ARG, "sigb_debug_cg_phase_cycles: bad argument");
+    for (int k = 0; k < kPhaseCtas * (kPhaseSlots + 1); k++) out[k] = 0ull;
+    *supported = 0;
+#ifdef SIGB_PHASE_TIMERS
+    unsigned long long *buf = phase_dbg_buffer();
+    SIGB_REQUIRE(buf, SIGB_ERR_CUDA, "sigb_debug_cg_phase_cycles: no buffer");
+    SIGB_CUDA(cudaStreamSynchronize(ctx().stream));
+    SIGB_CUDA(cudaMemcpy(out, buf, sizeof(unsigned long long) * kPhaseCtas * (kPhaseSlots + 1), cudaMemcpyDeviceToHost));
+    SIGB_CUDA(cudaMemset(buf, 0, sizeof(unsigned long long) * kPhaseCtas * (kPhaseSlots + 1)));
+    *supported = 1;
+#endif
+    return SIGB_OK;
+}
+
+}  // extern "C"
+
