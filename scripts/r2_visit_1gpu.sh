@@ -1,0 +1,44 @@
+#!/bin/bash
+# Round 2, first 1-GPU visit: regression, then every opt-in path written after the round-1
+# GPU budget ran out (none of them has run on a GPU yet), each next to its default.
+#   gpurun --timeout 1500 -- 'bash scripts/r2_visit_1gpu.sh r2a'
+# Reads: gpurun_out/<tag>/summary.txt first.
+TAG=${1:-r2a}; OUT=gpurun_out/$TAG; mkdir -p $OUT
+S=$OUT/summary.txt
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > $OUT/gpu.txt 2>&1
+echo "== 1. regression: pytest -m gpu" | tee $S
+timeout 900 python -m pytest tests -x -q -m gpu > $OUT/pytest_gpu.log 2>&1; echo "rc=$?" | tee -a $S
+tail -5 $OUT/pytest_gpu.log | tee -a $S
+echo "== 2. experimental paths (SIGB_TEST_EXPERIMENTAL=1), one test at a time so a hang costs one timeout" | tee -a $S
+for t in test_device_built_tiles_equal_the_host_tiling test_copy_and_transpose_parity_with_device_tiles \
+         test_ldu_parity_with_syncfree_sweeps test_single_reduction_persistent_cg; do
+  SIGB_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -x -q -k $t > $OUT/exp_$t.log 2>&1
+  echo "$t rc=$?" | tee -a $S; tail -3 $OUT/exp_$t.log | tee -a $S
+done
+echo "== 3. bench (default path)" | tee -a $S
+timeout 600 python bench.py --steps 200 --warmup 5 > $OUT/bench.json 2> $OUT/bench.err; echo "rc=$?" | tee -a $S
+cat $OUT/bench.json | tee -a $S
+echo "== 4. ILDU: per-level launches vs sync-free sweeps" | tee -a $S
+timeout 300 python bench.py --rows ldu > $OUT/ldu_default.jsonl 2> $OUT/ldu_default.err; echo "rc=$?" | tee -a $S
+for k in 1 2 4; do
+  SIGB_LDU_SYNCFREE=1 SIGB_LDU_SF_CTAS_PER_SM=$k timeout 300 python bench.py --rows ldu > $OUT/ldu_syncfree_c$k.jsonl 2> $OUT/ldu_syncfree_c$k.err
+  echo "syncfree ctas/sm=$k rc=$?" | tee -a $S
+done
+SIGB_LDU_SYNCFREE=1 SIGB_LDU_SF_SLEEP_NS=100 timeout 300 python bench.py --rows ldu > $OUT/ldu_syncfree_sleep.jsonl 2> $OUT/ldu_syncfree_sleep.err
+grep -h "ldu apply\|ldu setup\|CG iterations" $OUT/ldu_*.jsonl | cut -c1-300 | tee -a $S
+echo "== 5. copies / assembly: host tiling vs device tiling" | tee -a $S
+timeout 400 python bench.py --rows widened > $OUT/widened_default.jsonl 2> $OUT/widened_default.err; echo "rc=$?" | tee -a $S
+SIGB_DEVICE_TILES=1 timeout 400 python bench.py --rows widened > $OUT/widened_devtiles.jsonl 2> $OUT/widened_devtiles.err; echo "rc=$?" | tee -a $S
+grep -h "copy_matrix" $OUT/widened_*.jsonl | cut -c1-260 | tee -a $S
+echo "== 6. persistent CG at the 8-GPU shard size on one GPU: default / single reduction / phase breakdown" | tee -a $S
+for v in "" 1; do
+  SIGB_CG_PERSISTENT=1 SIGB_CG_SINGLE_REDUCE=$v timeout 300 python bench.py --grid 1448 --steps 400 --warmup 5 --quick 2>> $OUT/pers.err | sed "s/^{/{\"single_reduce\": \"$v\", /" | tee -a $OUT/pers.jsonl | tee -a $S
+done
+for v in "" 1; do
+  SIGB_LIB_VARIANT=_timers SIGB_CG_PERSISTENT=1 SIGB_CG_SINGLE_REDUCE=$v timeout 300 python bench.py --grid 1448 --steps 400 --warmup 5 --quick > /dev/null 2> $OUT/phases_single$v.err
+  grep phase_us $OUT/phases_single$v.err | tee -a $S
+done
+echo "== 7. BASELINE configs 4 and 5 at full size on one GPU" | tee -a $S
+timeout 900 python scripts/bench_configs_dist.py > $OUT/configs_full_1gpu.jsonl 2> $OUT/configs_full_1gpu.err; echo "rc=$?" | tee -a $S
+cut -c1-700 $OUT/configs_full_1gpu.jsonl | tee -a $S
+ls -la $OUT >> $S

@@ -1,0 +1,25 @@
+#!/bin/bash
+# Round 2, 8-GPU visit (charged 8x: keep it short).  Default scaling line, the single-reduction
+# persistent CG, the per-phase breakdown of both, then configs 4 / 5 at full size.
+#   gpurun --gpus 8 --timeout 1200 -- 'bash scripts/r2_visit_8gpu.sh r2n8'
+TAG=${1:-r2n8}; OUT=gpurun_out/$TAG; mkdir -p $OUT
+S=$OUT/summary.txt
+run8() { timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 "$@"; }
+echo "== N=8 default" | tee $S
+run8 bench.py --gpus 8 --steps 200 --warmup 5 > $OUT/bench_n8.json 2> $OUT/bench_n8.err; echo "rc=$?" | tee -a $S
+cat $OUT/bench_n8.json | tee -a $S
+echo "== N=8 single reduction (opt-in; parity bars of tests/test_gpu_experimental.py must be green first)" | tee -a $S
+SIGB_CG_SINGLE_REDUCE=1 run8 bench.py --gpus 8 --steps 200 --warmup 5 > $OUT/bench_n8_single.json 2> $OUT/bench_n8_single.err; echo "rc=$?" | tee -a $S
+cat $OUT/bench_n8_single.json | tee -a $S
+echo "== phase breakdown (diagnostic build; its timings are not bench values)" | tee -a $S
+for v in "" 1; do
+  SIGB_LIB_VARIANT=_timers SIGB_CG_SINGLE_REDUCE=$v run8 bench.py --gpus 8 --steps 200 --warmup 5 --quick > $OUT/phases_single$v.json 2> $OUT/phases_single$v.err
+  grep phase_us $OUT/phases_single$v.err | tee -a $S
+done
+echo "== sharded parity at world 8 (both transports)" | tee -a $S
+timeout 600 python -m pytest tests/test_gpu_dist.py -x -q -k "8" > $OUT/pytest_dist8.log 2>&1; echo "rc=$?" | tee -a $S
+tail -3 $OUT/pytest_dist8.log | tee -a $S
+echo "== configs 4 / 5, full size, 8 GPUs" | tee -a $S
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 \
+  scripts/bench_configs_dist.py > $OUT/configs_full_8gpu.jsonl 2> $OUT/configs_full_8gpu.err; echo "rc=$?" | tee -a $S
+cut -c1-700 $OUT/configs_full_8gpu.jsonl | tee -a $S
