@@ -24,7 +24,7 @@ __all__ = [
     "cg_solve", "bicgstab_solve", "lanczos", "generalized_lanczos", "eigensolve", "tridiag_eig",
     "partition_rows", "halo_build", "cs_set_value", "ell_set_value",
     "SUM", "PRODUCT", "ADJOINT", "COMPOSITE", "operator_sum", "operator_product", "adjoint",
-    "composite", "get_value", "matrix_entries", "copy_matrix", "add_values", "Ldu", "ldu_setup", "ldu_solve", "cg_solve_ldu",
+    "composite", "get_value", "matrix_entries", "copy_matrix", "add_values", "Ldu", "ldu_setup", "ldu_solve", "cg_solve_ldu", "bicgstab_solve_ldu",
 ]
 
 
@@ -75,6 +75,8 @@ def lib():
         "orc_ldu_solve": (None, [i32, _i32p, _i32p, _f64p, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p]),
         "orc_cg_solve_ldu": (i64, [mp, _f64p, _f64p, _i32p, _i32p, _f64p, _i32p, _i32p, _f64p, _f64p, f64, i64,
                                    _f64p, C.POINTER(f64), C.POINTER(i32)]),
+        "orc_bicgstab_solve_ldu": (i64, [mp, _f64p, _f64p, _i32p, _i32p, _f64p, _i32p, _i32p, _f64p, _f64p, f64, i64,
+                                         _f64p, C.POINTER(f64), C.POINTER(i32)]),
         "orc_matvec_add": (None, [mp, i32, _f64p, _f64p]),
         "orc_matvec": (None, [mp, i32, _f64p, _f64p]),
         "orc_get_value": (f64, [mp, i32, i32]),
@@ -342,6 +344,15 @@ def cg_solve_ldu(A, x0, b, F: Ldu, tol=1e-16, max_iter=-1):
     work = np.zeros(4 * A.nrow)
     res2, capped = C.c_double(0.0), C.c_int32(0)
     it = lib().orc_cg_solve_ldu(A.c, x, _f64(b), *F.args, tol, max_iter, work, C.byref(res2), C.byref(capped))
+    return x, int(it), res2.value, bool(capped.value)
+
+
+def bicgstab_solve_ldu(A, x0, b, F: Ldu, tol=1e-16, max_iter=-1):
+    """orc_bicgstab_solve_ldu: bicgstab_solve_pc with pc = ldu() -> (x, iterations, res2, capped)."""
+    x = _f64(x0).copy()
+    work = np.zeros(8 * A.nrow)
+    res2, capped = C.c_double(0.0), C.c_int32(0)
+    it = lib().orc_bicgstab_solve_ldu(A.c, x, _f64(b), *F.args, tol, max_iter, work, C.byref(res2), C.byref(capped))
     return x, int(it), res2.value, bool(capped.value)
 
 

@@ -937,6 +937,63 @@ ORC_API int64_t orc_bicgstab_solve_jacobi(const orc_matrix *A, double *x,
     return it;
 }
 
+/*
+ * bicgstab_solve_pc, src/solver/bicgstab_solvers.f90:182-237 with pc = ldu()
+ * (call pc%solve(A, ., z) = ldu_solve, src/solver/ldu_solvers.f90:160-176).
+ * The reference's tests never pair the two, but linear_solve_pc takes any
+ * class(linear_solver) as pc (linear_operator_interface.f90:238-254), so a
+ * caller may.  Same statements as the jacobi form above, another pc%solve.
+ */
+ORC_API int64_t orc_bicgstab_solve_ldu(const orc_matrix *A, double *x, const double *b,
+                                       const int32_t *Lptr, const int32_t *Lnode, const double *Lval,
+                                       const int32_t *Uptr, const int32_t *Unode, const double *Uval,
+                                       const double *D, double tolerance, int64_t max_iter,
+                                       double *work, double *res2_out, int32_t *capped)
+{
+    const int64_t n = A->nrow;
+    double *p = work, *q = work + n, *r = work + 2 * n, *r0 = work + 3 * n,
+           *v = work + 4 * n, *s = work + 5 * n, *t = work + 6 * n,
+           *z = work + 7 * n;
+    double rho, rho_old, alpha, omega, beta, res2;
+    int64_t it = 0;
+    int32_t i, nn = (int32_t)n;
+
+    if (capped) *capped = 0;
+    orc_matvec(A, 0, x, q);                              /* :199 */
+    for (i = 0; i < n; i++) z[i] = b[i] - q[i];          /* :200 */
+    orc_ldu_solve(nn, Lptr, Lnode, Lval, Uptr, Unode, Uval, D, r0, z);   /* :201 */
+    for (i = 0; i < n; i++) r[i] = r0[i];                /* :202 */
+    rho = 1.0; rho_old = 1.0; alpha = 1.0; omega = 1.0;  /* :204-207 */
+    for (i = 0; i < n; i++) v[i] = 0.0;                  /* :209 */
+    for (i = 0; i < n; i++) p[i] = 0.0;                  /* :210 */
+    res2 = dot(r, r, nn);                                /* :212 */
+
+    while (sqrt(res2) > tolerance) {                     /* :214 */
+        if (max_iter >= 0 && it >= max_iter) { if (capped) *capped = 1; break; }
+        rho = dot(r0, r, nn);                            /* :215 */
+        beta = rho / rho_old * alpha / omega;            /* :216 */
+        for (i = 0; i < n; i++)                          /* :217 */
+            p[i] = r[i] + beta * (p[i] - omega * v[i]);
+        orc_matvec(A, 0, p, z);                          /* :218 */
+        orc_ldu_solve(nn, Lptr, Lnode, Lval, Uptr, Unode, Uval, D, v, z);   /* :219 */
+
+        alpha = rho / dot(r0, v, nn);                    /* :221 */
+        for (i = 0; i < n; i++) s[i] = r[i] - alpha * v[i];   /* :222 */
+        orc_matvec(A, 0, s, z);                          /* :223 */
+        orc_ldu_solve(nn, Lptr, Lnode, Lval, Uptr, Unode, Uval, D, t, z);   /* :224 */
+        omega = dot(s, t, nn) / dot(t, t, nn);           /* :225 */
+        for (i = 0; i < n; i++)                          /* :226 */
+            x[i] = x[i] + alpha * p[i] + omega * s[i];
+        for (i = 0; i < n; i++) r[i] = s[i] - omega * t[i];   /* :227 */
+
+        rho_old = rho;                                   /* :229 */
+        res2 = dot(r, r, nn);                            /* :230 */
+        it++;
+    }
+    if (res2_out) *res2_out = res2;
+    return it;
+}
+
 /* ------------------------------------------------------------------------ */
 /* Lanczos / eigensolve                                                      */
 /* ------------------------------------------------------------------------ */

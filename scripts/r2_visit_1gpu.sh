@@ -11,7 +11,7 @@ timeout 900 python -m pytest tests -x -q -m gpu > $OUT/pytest_gpu.log 2>&1; echo
 tail -5 $OUT/pytest_gpu.log | tee -a $S
 echo "== 2. experimental paths (SIGB_TEST_EXPERIMENTAL=1), one test at a time so a hang costs one timeout" | tee -a $S
 for t in test_device_built_tiles_equal_the_host_tiling test_copy_and_transpose_parity_with_device_tiles \
-         test_ldu_parity_with_syncfree_sweeps test_single_reduction_persistent_cg; do
+         test_ldu_parity_with_syncfree_sweeps test_single_reduction_persistent_cg test_bicgstab_with_ldu_preconditioner; do
   SIGB_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -x -q -k $t > $OUT/exp_$t.log 2>&1
   echo "$t rc=$?" | tee -a $S; tail -3 $OUT/exp_$t.log | tee -a $S
 done

@@ -656,7 +656,14 @@ int sigb_solver_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x_dev, const
     SIGB_REQUIRE(s->nn == A->nrow, SIGB_ERR_ARG, "sigb_solver_solve: solver was set up for nn = %d, operator has %d rows",
                  s->nn, A->nrow);
     if (pc) {
-        SIGB_REQUIRE(pc->kind == S_JACOBI || (pc->kind == S_LDU && s->kind == S_CG && !A->dist), SIGB_ERR_UNSUPPORTED,
+        // EXPERIMENTAL opt-in: bicgstab with the ldu preconditioner (solvers.cu), not yet run on a GPU
+        static int bicg_ldu = -1;
+        if (bicg_ldu < 0) {
+            const char *e = getenv("SIGB_BICGSTAB_LDU");
+            bicg_ldu = (e && atoi(e) == 1) ? 1 : 0;
+        }
+        const bool ldu_ok = pc->kind == S_LDU && !A->dist && (s->kind == S_CG || (s->kind == S_BICGSTAB && bicg_ldu));
+        SIGB_REQUIRE(pc->kind == S_JACOBI || ldu_ok, SIGB_ERR_UNSUPPORTED,
                      "sigb_solver_solve: the device preconditioners are jacobi (cg, bicgstab) and ldu (cg, one GPU)");
         SIGB_REQUIRE(pc->initialized && pc->nn == s->nn, SIGB_ERR_STATE,
                      "sigb_solver_solve: pc%%setup(A) has not been called");

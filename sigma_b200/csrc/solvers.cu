@@ -871,9 +871,128 @@ static int cg_solve_body(sigb_solver_t s, sigb_matrix_t A, double *x, const doub
     return finish_solve(s);
 }
 
+// ---------------------------------------------------------------------------
+// EXPERIMENTAL, opt-in (SIGB_BICGSTAB_LDU=1; not yet run on a GPU): bicgstab_solve_pc
+// (bicgstab_solvers.f90:182-237) with pc = ldu().  The preconditioner is applied by its own
+// kernels (ldu.cu), so the three products of an iteration are plain SpMVs into z followed by
+// call pc%solve(A, ., z), and the dot products that the Jacobi form fuses into the SpMV run
+// as separate passes.  Same device-resident control: everything launched past the stopping
+// latch is a no-op.
+// ---------------------------------------------------------------------------
+// z = b - q   (:200)
+struct BicgResidualOp {
+    static constexpr int ND = 0;
+    static constexpr int NIN = 2;
+    const double *__restrict__ b, *__restrict__ q;
+    double *__restrict__ z;
+    __device__ bool begin() { return true; }
+    __device__ void load(int64_t i, double *in) { in[0] = b[i]; in[1] = q[i]; }
+    __device__ void compute(int64_t i, const double *in, double *) { z[i] = sub(in[0], in[1]); }
+    __device__ double *out(int) { return nullptr; }
+};
+
+// r = r0 ; v = 0 ; p = 0 ; res2 = r.r ; rho = r0.r   (:202-212), r0 = pc%solve(A, ., z) done
+struct BicgInitR0Op {
+    static constexpr int ND = 2;
+    static constexpr int NIN = 1;
+    const double *__restrict__ r0;
+    double *__restrict__ r, *__restrict__ v, *__restrict__ p;
+    KState *st;
+    __device__ bool begin() { return true; }
+    __device__ void load(int64_t i, double *in) { in[0] = r0[i]; }
+    __device__ void compute(int64_t i, const double *in, double *acc)
+    {
+        r[i] = in[0];
+        v[i] = 0.0;
+        p[i] = 0.0;
+        acc[0] = add(acc[0], mul(in[0], in[0]));
+        acc[1] = add(acc[1], mul(in[0], in[0]));
+    }
+    __device__ double *out(int d) { return d == 0 ? &st->rr[0] : &st->rho[0]; }
+};
+
+// r0.v -> pq   (:221), skipped past the stopping latch
+struct BicgDotOp {
+    static constexpr int ND = 1;
+    static constexpr int NIN = 2;
+    const double *__restrict__ a, *__restrict__ b;
+    KState *st;
+    int par;
+    __device__ bool begin() { return st->done[par] == 0; }
+    __device__ void load(int64_t i, double *in) { in[0] = a[i]; in[1] = b[i]; }
+    __device__ void compute(int64_t, const double *in, double *acc) { acc[0] = add(acc[0], mul(in[0], in[1])); }
+    __device__ double *out(int) { return &st->pq; }
+};
+
+// s.t -> st, t.t -> tt   (:225)
+struct BicgDot2Op {
+    static constexpr int ND = 2;
+    static constexpr int NIN = 2;
+    const double *__restrict__ s, *__restrict__ t;
+    KState *st;
+    int par;
+    __device__ bool begin() { return st->done[par] == 0; }
+    __device__ void load(int64_t i, double *in) { in[0] = s[i]; in[1] = t[i]; }
+    __device__ void compute(int64_t, const double *in, double *acc)
+    {
+        acc[0] = add(acc[0], mul(in[0], in[1]));
+        acc[1] = add(acc[1], mul(in[1], in[1]));
+    }
+    __device__ double *out(int d) { return d == 0 ? &st->st : &st->tt; }
+};
+
+static int bicgstab_solve_ldu_pc(sigb_solver_t s, sigb_matrix_t A, double *x, const double *b, sigb_solver_t pc)
+{
+    const int64_t n = s->nn, nv = s->nvec;
+    double *p = s->work, *q = p + nv, *r = q + nv, *r0 = r + nv, *v = r0 + nv, *sv = v + nv,
+           *t = sv + nv, *z = t + nv;
+    KState *st = s->state;
+    SIGB_CHECK(push_state(s));
+    DotSpec none;
+    SIGB_CHECK(solver_matvec(A, x, q, none, false));            // call A%matvec(x, q)      :199
+    BicgResidualOp res{b, q, z};                                // z = b - q                :200
+    SIGB_CHECK(launch_ew(res, n));
+    SIGB_CHECK(ldu_apply_dev(pc, r0, z, nullptr));              // call pc%solve(A, r0, z)  :201
+    BicgInitR0Op init{r0, r, v, p, st};                         // :202-212
+    SIGB_CHECK(launch_ew(init, n));
+    bicg_latch0_kernel<<<1, 1, 0, ctx().stream>>>(st);
+    count_launch();
+    {
+        BicgDirectionOp dir{r, v, p, st, 0, 1, 0.0, 0.0};
+        SIGB_CHECK(launch_ew(dir, n));
+    }
+    const int nb = batch_size(n);
+    int par = 0;
+    for (;;) {
+        for (int it = 0; it < nb; it++) {
+            DotSpec latched;
+            latched.skip_flag = &st->done[par];
+            SIGB_CHECK(solver_matvec(A, p, z, latched, false));             // call A%matvec(p, z)     :218
+            SIGB_CHECK(ldu_apply_dev(pc, v, z, &st->done[par]));            // call pc%solve(A, v, z)  :219
+            BicgDotOp d1{r0, v, st, par};                                   // r0.v                    :221
+            SIGB_CHECK(launch_ew(d1, n));
+            BicgSOp sop{r, v, sv, st, par, 0.0};                            // alpha ; s = r - alpha v :221-222
+            SIGB_CHECK(launch_ew(sop, n));
+            SIGB_CHECK(solver_matvec(A, sv, z, latched, false));            // call A%matvec(s, z)     :223
+            SIGB_CHECK(ldu_apply_dev(pc, t, z, &st->done[par]));            // call pc%solve(A, t, z)  :224
+            BicgDot2Op d2{sv, t, st, par};                                  // s.t, t.t                :225
+            SIGB_CHECK(launch_ew(d2, n));
+            BicgUpdateOp up{p, sv, t, r0, x, r, st, par, 0, 0.0, 0.0};      // omega, x, r, res2, rho  :225-230,215
+            SIGB_CHECK(launch_ew(up, n));
+            BicgDirectionOp dir{r, v, p, st, par ^ 1, 0, 0.0, 0.0};         // loop test, beta, p      :214-217
+            SIGB_CHECK(launch_ew(dir, n));
+            par ^= 1;
+        }
+        SIGB_CHECK(sync_state(s));
+        if (s->state_host->done[par]) break;
+    }
+    return finish_solve(s);
+}
+
 int bicgstab_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x, const double *b,
                        sigb_solver_t pc)
 {
+    if (pc && pc->kind == S_LDU) return bicgstab_solve_ldu_pc(s, A, x, b, pc);
     const int64_t n = s->nn, nv = s->nvec;
     double *p = s->work, *q = p + nv, *r = q + nv, *r0 = r + nv, *v = r0 + nv, *sv = v + nv,
            *t = sv + nv, *z = t + nv;

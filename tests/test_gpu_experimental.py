@@ -14,7 +14,9 @@ subprocess; the whole file is skipped unless SIGB_TEST_EXPERIMENTAL=1.
   SIGB_LDU_SYNCFREE=1       ILDU(0) factorisation and triangular sweeps as one cooperative launch
                             each, rows waiting for the entries they read instead of one launch
                             per level (csrc/ldu.cu).  Same arithmetic per row: the ILDU parity
-                            tests (bit-exact factors and solves) must stay green with it on."""
+                            tests (bit-exact factors and solves) must stay green with it on.
+  SIGB_BICGSTAB_LDU=1       bicgstab_solve_pc with pc = ldu() on the device (csrc/solvers.cu); the
+                            default build refuses the pair (tests/test_gpu_ldu.py checks that)."""
 import os
 import subprocess
 import sys
@@ -126,3 +128,39 @@ def test_ldu_parity_with_syncfree_sweeps(knobs):
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_ldu.py"], cwd=ROOT,
                        env=e, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+BICGSTAB_LDU = """
+    import numpy as np
+    import oracle as orc
+    import sigma_b200 as sb
+    from sigma_b200 import generators as G
+    orc.build(); sb.init(0)
+    def within(it, ref, frac): return abs(it - ref) <= max(1, int(np.ceil(frac * ref)))
+    for nn, seed in ((300, 4), (2000, 5)):
+        ptr, node, val = G.erdos_renyi_csr(nn, seed=seed, weights="random", skew=True, shift=1.0)
+        A = sb.csr_matrix(nn, nn, ptr, node, val)
+        O = orc.Matrix(orc.CSR, nn, nn, node, val, ptr=ptr)
+        F = orc.ldu_setup(O)
+        v = np.random.default_rng(seed).random(nn)
+        f = orc.matvec(O, v)
+        tol = 1e-13
+        s, pc = sb.bicgstab(tol), sb.ldu()
+        s.set_max_iterations(50 * nn); s.setup(A); pc.setup(A)
+        x = s.solve(A, np.zeros(nn), f, pc)
+        it, res2, capped = s.info()
+        xo, ito, _, cappedo = orc.bicgstab_solve_ldu(O, np.zeros(nn), f, F, tol, 50 * nn)
+        assert not capped and not cappedo and within(it, ito, 0.05), (it, ito)
+        assert np.abs(x - xo).max() <= 1e-10 * np.abs(xo).max()
+        assert np.abs(x - v).max() <= 1e-10
+        # a capped solve stops where it is told to
+        s2 = sb.bicgstab(tol); s2.set_max_iterations(3); s2.setup(A)
+        s2.solve(A, np.zeros(nn), f, pc)
+        assert s2.info()[0] == 3 and s2.info()[2]
+    print("bicgstab+ldu ok")
+"""
+
+
+def test_bicgstab_with_ldu_preconditioner():
+    out = run_snippet(BICGSTAB_LDU, SIGB_BICGSTAB_LDU="1")
+    assert "bicgstab+ldu ok" in out
