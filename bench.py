@@ -195,6 +195,26 @@ def phase_report(rank, ms_per_iter):
           flush=True)
 
 
+def spmv_tile_report(rank, us_per_launch):
+    """Diagnostic library builds only: what thread 0 of a CTA of the streaming CSR kernel spends
+    its pass on -- waiting for the staged tile (TMA), the products (x gathers), the row sums --
+    as fractions of the pass, averaged over CTAs and launches; stderr, never a bench value."""
+    import ctypes as C
+
+    from sigma_b200._capi import check, lib
+
+    buf = (C.c_ulonglong * 6)()
+    ok = C.c_int(0)
+    check(lib().sigb_debug_spmv_tile_cycles(buf, C.byref(ok)))
+    if not ok.value or us_per_launch is None or not buf[3]:
+        return
+    tot = float(buf[3])
+    print(json.dumps({"spmv_cta_pass": {"wait_tma": buf[0] / tot, "products": buf[1] / tot, "row_sums": buf[2] / tot,
+                                        "other": 1.0 - (buf[0] + buf[1] + buf[2]) / tot,
+                                        "cycles_per_tile": tot / max(buf[4], 1), "tiles_per_cta_pass": buf[4] / max(buf[5], 1)},
+                      "rank": rank, "us_per_launch": us_per_launch}), file=sys.stderr, flush=True)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -303,7 +323,9 @@ def run_ours(args):
             for _ in range(reps):
                 A.matvec_dot_dev(b_dev, y_dev, fetch=False)
 
+        spmv_tile_report(rank, None)                  # diagnostic builds: reset
         ms_spmv = timed(spmv_loop) / reps
+        spmv_tile_report(rank, ms_spmv * 1e3)         # no-op unless SIGB_LIB_VARIANT=_timers
         ms_spmv_dot = timed(spmv_dot_loop) / reps
     launches = sb.launch_count() - launches0
     it_done, res2, capped = solver.info()

@@ -411,6 +411,12 @@ SIGB_API int sigb_debug_row_tiles_dev(int32_t n, const int32_t *ptr1, int32_t *t
  * -DSIGB_PHASE_TIMERS (csrc/Makefile: make VARIANT=_timers DEFS=-DSIGB_PHASE_TIMERS). */
 SIGB_API int sigb_debug_cg_phase_cycles(unsigned long long *out27, int *supported);
 
+/* Diagnostic, same builds: SM cycles of thread 0 of every CTA of the streaming
+ * CSR kernel summed over the grid and the launches since the last call (then
+ * reset): out[0] waiting for the staged tile, [1] products (gathers), [2] row
+ * sums, [3] whole pass, [4] staged tiles processed, [5] CTA passes. */
+SIGB_API int sigb_debug_spmv_tile_cycles(unsigned long long *out6, int *supported);
+
 /* Communicator.  unique_id is SIGB_UNIQUE_ID_BYTES bytes produced by
  * sigb_comm_unique_id on rank 0 and broadcast by the host (torch.distributed,
  * MPI, a file ...). */

@@ -38,6 +38,9 @@ for v in "" 1; do
   SIGB_LIB_VARIANT=_timers SIGB_CG_PERSISTENT=1 SIGB_CG_SINGLE_REDUCE=$v timeout 300 python bench.py --grid 1448 --steps 400 --warmup 5 --quick > /dev/null 2> $OUT/phases_single$v.err
   grep phase_us $OUT/phases_single$v.err | tee -a $S
 done
+echo "== 6b. where a CTA of the SpMV kernel spends its pass (diagnostic build), full size" | tee -a $S
+SIGB_LIB_VARIANT=_timers timeout 300 python bench.py --steps 50 --warmup 3 --quick > /dev/null 2> $OUT/spmv_tiles.err
+grep spmv_cta_pass $OUT/spmv_tiles.err | tee -a $S
 echo "== 7. BASELINE configs 4 and 5 at full size on one GPU" | tee -a $S
 timeout 900 python scripts/bench_configs_dist.py > $OUT/configs_full_1gpu.jsonl 2> $OUT/configs_full_1gpu.err; echo "rc=$?" | tee -a $S
 cut -c1-700 $OUT/configs_full_1gpu.jsonl | tee -a $S

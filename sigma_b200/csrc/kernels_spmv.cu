@@ -279,9 +279,25 @@ int build_tiles_host(const int32_t *ptr1, int32_t nrows, std::vector<TileDesc> &
 
 // Argument block of one SpMV over all tiles of A (which = 0), or over its
 // interior / boundary sub-tables (which = 1 / 2, NCCL transport).
+#ifdef SIGB_PHASE_TIMERS
+// diagnostic build: one buffer per process for the per-tile cycle counters (spmv_device.cuh)
+static unsigned long long *tile_dbg_buffer()
+{
+    static unsigned long long *buf = nullptr;
+    if (!buf) {
+        if (cudaMalloc((void **)&buf, sizeof(unsigned long long) * 6) != cudaSuccess) return nullptr;
+        cudaMemset(buf, 0, sizeof(unsigned long long) * 6);
+    }
+    return buf;
+}
+#endif
+
 static void fill_args(const CsrView &A, const double *val, const double *x, double *y, const DotSpec &dot,
                       int which, int ticket, CsrKernelArgs &a)
 {
+#ifdef SIGB_PHASE_TIMERS
+    a.tile_dbg = tile_dbg_buffer();
+#endif
     a.ptr = A.ptr;
     a.node = A.node;
     a.val = val;
@@ -375,3 +391,28 @@ int launch_ell_spmv(int32_t n, int32_t n_pad, int32_t max_d, const int32_t *node
 }
 
 }  // namespace sigb
+
+extern "C" {
+
+// Diagnostic: SM cycles of thread 0 of every CTA of the streaming CSR kernel, summed over
+// the grid and over the launches since the last call (then reset): out[0] waiting for the
+// staged tile, [1] products (gathers), [2] row sums, [3] whole pass, [4] staged tiles,
+// [5] CTA passes.  *supported = 0 (and zeros) unless built with -DSIGB_PHASE_TIMERS.
+int sigb_debug_spmv_tile_cycles(unsigned long long *out, int *supported)
+{
+    using namespace sigb;
+    SIGB_REQUIRE(out && supported, SIGB_ERR_ARG, "sigb_debug_spmv_tile_cycles: bad argument");
+    for (int k = 0; k < 6; k++) out[k] = 0ull;
+    *supported = 0;
+#ifdef SIGB_PHASE_TIMERS
+    unsigned long long *buf = tile_dbg_buffer();
+    SIGB_REQUIRE(buf, SIGB_ERR_CUDA, "sigb_debug_spmv_tile_cycles: no buffer");
+    SIGB_CUDA(cudaStreamSynchronize(ctx().stream));
+    SIGB_CUDA(cudaMemcpy(out, buf, sizeof(unsigned long long) * 6, cudaMemcpyDeviceToHost));
+    SIGB_CUDA(cudaMemset(buf, 0, sizeof(unsigned long long) * 6));
+    *supported = 1;
+#endif
+    return SIGB_OK;
+}
+
+}  // extern "C"

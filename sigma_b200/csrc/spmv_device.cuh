@@ -28,7 +28,21 @@ struct CsrKernelArgs {
     const double *add0, *add1;  // optional addends folded into the dot totals
     HaloSync sync;            // peer-memory transport (sync.win == nullptr: none)
     int32_t first_halo_tile;  // tiles from this index on read halo columns
+#ifdef SIGB_PHASE_TIMERS
+    // diagnostic build: SM cycles of thread 0 of every CTA, summed over the grid:
+    // [0] waiting for the staged tile, [1] products (gathers), [2] row sums, [3] the whole pass,
+    // [4] staged tiles processed, [5] CTA passes
+    unsigned long long *tile_dbg;
+#endif
 };
+
+#ifdef SIGB_PHASE_TIMERS
+#define SIGB_TCLK(var) const long long var = clock64()
+#define SIGB_TACC(acc, t1, t0) acc += (unsigned long long)((t1) - (t0))
+#else
+#define SIGB_TCLK(var)
+#define SIGB_TACC(acc, t1, t0)
+#endif
 
 __device__ __forceinline__ int4 load_desc(const TileDesc *t)
 {
@@ -238,6 +252,10 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
         bulk_g2s(base + kStageVal + kStageNode, a.ptr + ra, rcnt * 4u, &mbar[stage], stream_policy);
     };
 
+#ifdef SIGB_PHASE_TIMERS
+    unsigned long long c_wait = 0, c_prod = 0, c_rows = 0, c_tiles = 0;
+#endif
+    SIGB_TCLK(tk_begin);
     int t = blockIdx.x;
     int4 d_cur = make_int4(0, 0, 0, 0), d_next = make_int4(0, 0, 0, 0);
     if (t < a.ntiles) d_cur = load_desc(a.tiles + t);
@@ -279,7 +297,9 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
             const int32_t *sptr = reinterpret_cast<const int32_t *>(base + kStageVal + kStageNode);
             const int rs = d_cur.x, re = d_cur.y, ks = d_cur.z, ke = d_cur.w;
             const int ka = ks & ~3, ra = rs & ~3;
+            SIGB_TCLK(tk0);
             mbar_wait(&mbar[stage], (sidx >> 1) & 1u);
+            SIGB_TCLK(tk1);
             // ---- phase 1: products, in place --------------------------------
             // (entries before ks belong to the previous tile and hold valid
             // columns, so every gather below is in range)
@@ -314,6 +334,7 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
                 if (k < cnt) sval[k] = mul(v[i], xv[i]);
             }
             __syncthreads();
+            SIGB_TCLK(tk2);
             // ---- phase 2: per-row sums in stored order ----------------------
             // operands of the fused dot go through the same read-only path as
             // the gathers, so rows with a (near-)diagonal entry hit L1
@@ -337,6 +358,13 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
             // generic-proxy accesses before it
             fence_proxy_async();
             __syncthreads();
+            SIGB_TCLK(tk3);
+            SIGB_TACC(c_wait, tk1, tk0);
+            SIGB_TACC(c_prod, tk2, tk1);
+            SIGB_TACC(c_rows, tk3, tk2);
+#ifdef SIGB_PHASE_TIMERS
+            c_tiles++;
+#endif
         } else {
             long_row<MODE, NDOT, HALO, XNC>(a, d_cur, h1, acc);
         }
@@ -346,6 +374,16 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
         if (HALO && push_pending) publish_push();
     }
     if (HALO && push_pending) publish_push();   // a CTA without tiles
+#ifdef SIGB_PHASE_TIMERS
+    if (tid == 0 && a.tile_dbg != nullptr) {
+        atomicAdd(a.tile_dbg + 0, c_wait);
+        atomicAdd(a.tile_dbg + 1, c_prod);
+        atomicAdd(a.tile_dbg + 2, c_rows);
+        atomicAdd(a.tile_dbg + 3, (unsigned long long)(clock64() - tk_begin));
+        atomicAdd(a.tile_dbg + 4, c_tiles);
+        atomicAdd(a.tile_dbg + 5, 1ull);
+    }
+#endif
     pipe.sidx = sidx;
     // persistent callers: the matrix does not change between SpMVs, so the first
     // tile of the NEXT pass can already be in flight while other phases run
