@@ -11,13 +11,20 @@ timeout 900 python -m pytest tests -x -q -m gpu > $OUT/pytest_gpu.log 2>&1; echo
 tail -5 $OUT/pytest_gpu.log | tee -a $S
 echo "== 2. experimental paths (SIGB_TEST_EXPERIMENTAL=1), one test at a time so a hang costs one timeout" | tee -a $S
 for t in test_device_built_tiles_equal_the_host_tiling test_copy_and_transpose_parity_with_device_tiles \
-         test_ldu_parity_with_syncfree_sweeps test_single_reduction_persistent_cg test_bicgstab_with_ldu_preconditioner; do
+         test_parity_with_rowdirect_spmv test_persistent_cg_with_rowdirect_spmv test_ldu_parity_with_syncfree_sweeps \
+         test_single_reduction_persistent_cg test_bicgstab_with_ldu_preconditioner; do
   SIGB_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -x -q -k $t > $OUT/exp_$t.log 2>&1
   echo "$t rc=$?" | tee -a $S; tail -3 $OUT/exp_$t.log | tee -a $S
 done
 echo "== 3. bench (default path)" | tee -a $S
 timeout 600 python bench.py --steps 200 --warmup 5 > $OUT/bench.json 2> $OUT/bench.err; echo "rc=$?" | tee -a $S
 cat $OUT/bench.json | tee -a $S
+echo "== 3b. SpMV A/B: two-pass (default) vs row-direct, full size and the 8-GPU shard size" | tee -a $S
+for g in 4096 1448; do for rd in 0 1; do
+  SIGB_SPMV_ROWDIRECT=$rd timeout 300 python bench.py --grid $g --steps 200 --warmup 5 --quick 2>> $OUT/rowdirect.err | sed "s/^{/{\"grid\": $g, \"rowdirect\": $rd, /" | tee -a $OUT/rowdirect.jsonl | tee -a $S
+done; done
+SIGB_LIB_VARIANT=_timers SIGB_SPMV_ROWDIRECT=1 timeout 300 python bench.py --steps 50 --warmup 3 --quick > /dev/null 2> $OUT/spmv_tiles_rowdirect.err
+grep spmv_cta_pass $OUT/spmv_tiles_rowdirect.err | tee -a $S
 echo "== 4. ILDU: per-level launches vs sync-free sweeps" | tee -a $S
 timeout 300 python bench.py --rows ldu > $OUT/ldu_default.jsonl 2> $OUT/ldu_default.err; echo "rc=$?" | tee -a $S
 for k in 1 2 4; do

@@ -177,7 +177,7 @@ __device__ __forceinline__ double grid_allreduce(double v, const CgPersistArgs &
     return out;
 }
 
-template <bool HALO, bool PC>
+template <bool HALO, bool PC, bool RD>
 __global__ void __launch_bounds__(kThreads, 4)
 cg_persistent_kernel(const CgPersistArgs a)
 {
@@ -219,7 +219,7 @@ cg_persistent_kernel(const CgPersistArgs a)
         // ---- A: q = A p, p.q ------------------------------------------------
         double acc[1] = {0.0};
         hseq++;
-        spmv_phase<MODE_SET, 1, HALO, false>(a.A, smem, mbar, pipe, acc, hseq, true);
+        spmv_phase<MODE_SET, 1, HALO, false, RD>(a.A, smem, mbar, pipe, acc, hseq, true);
         clk.stamp(0);
         const double pq = grid_allreduce(acc[0], a, s, pbuf, red_seq, sm_red, &s_bcast, clk, 1);
         if (HALO && a.A.sync.win != nullptr && blockIdx.x == gridDim.x - 1 && tid < kMaxRanks &&
@@ -537,19 +537,19 @@ int launch_single_reduce(const CgPersistArgs &a, cudaStream_t st)
     return SIGB_OK;
 }
 
-template <bool HALO, bool PC>
+template <bool HALO, bool PC, bool RD>
 int launch_persistent(const CgPersistArgs &a, cudaStream_t st)
 {
     const size_t smem = 2 * (size_t)kStageBytes;
     int grid = 0;
-    SIGB_CHECK((occupancy_grid<cg_persistent_kernel<HALO, PC>>(smem, &grid)));
+    SIGB_CHECK((occupancy_grid<cg_persistent_kernel<HALO, PC, RD>>(smem, &grid)));
     CgPersistArgs b = a;
     if (HALO && b.A.sync.win != nullptr) {
         int pc = (b.A.sync.total_send + 2 * kThreads - 1) / (2 * kThreads);
         b.A.sync.push_ctas = b.A.sync.total_send > 0 ? std::max(1, std::min(pc, grid)) : 0;
     }
     void *params[] = {(void *)&b};
-    SIGB_CUDA(cudaLaunchCooperativeKernel((const void *)cg_persistent_kernel<HALO, PC>, dim3(grid), dim3(kThreads),
+    SIGB_CUDA(cudaLaunchCooperativeKernel((const void *)cg_persistent_kernel<HALO, PC, RD>, dim3(grid), dim3(kThreads),
                                           params, smem, st));
     count_launch();
     return SIGB_OK;
@@ -603,8 +603,12 @@ int cg_persistent_run(sigb_solver_t s, const CsrView &V, const double *val, cons
     cudaStream_t st = ctx().stream;
     SIGB_CUDA(cudaMemsetAsync(s->bar, 0, 2 * sizeof(unsigned long long), st));
     const bool halo_on = halo.sync != nullptr;
-    if (halo_on) return idiag ? launch_persistent<true, true>(a, st) : launch_persistent<true, false>(a, st);
-    return idiag ? launch_persistent<false, true>(a, st) : launch_persistent<false, false>(a, st);
+    if (spmv_rowdirect(V)) {   // EXPERIMENTAL (SIGB_SPMV_ROWDIRECT), see spmv_device.cuh
+        if (halo_on) return idiag ? launch_persistent<true, true, true>(a, st) : launch_persistent<true, false, true>(a, st);
+        return idiag ? launch_persistent<false, true, true>(a, st) : launch_persistent<false, false, true>(a, st);
+    }
+    if (halo_on) return idiag ? launch_persistent<true, true, false>(a, st) : launch_persistent<true, false, false>(a, st);
+    return idiag ? launch_persistent<false, true, false>(a, st) : launch_persistent<false, false, false>(a, st);
 }
 
 // EXPERIMENTAL single-reduction arrangement (see cg_single_reduce_kernel): x, p, r as in

@@ -221,6 +221,8 @@ int launch_ell_spmv(int32_t n, int32_t n_pad, int32_t max_d,
                     const double *x, double *y, SpmvMode mode,
                     const DotSpec &dot);
 int build_tiles_host(const int32_t *ptr1, int32_t nrows, std::vector<TileDesc> &tiles);
+// EXPERIMENTAL (SIGB_SPMV_ROWDIRECT): whether the row-direct form of the streaming kernel is used for A
+bool spmv_rowdirect(const CsrView &A);
 // tiles_device.cu -- EXPERIMENTAL (SIGB_DEVICE_TILES=1): the same tiling built on the device
 // from a device-resident ptr (no read-back); also returns the extreme line lengths
 bool device_tiles_enabled();

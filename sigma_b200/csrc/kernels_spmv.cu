@@ -56,7 +56,7 @@ namespace {
 // ---------------------------------------------------------------------------
 // stand-alone SpMV kernel
 // ---------------------------------------------------------------------------
-template <int MODE, int NDOT, bool HALO>
+template <int MODE, int NDOT, bool HALO, bool RD>
 __global__ void __launch_bounds__(kThreads)
 csr_tma_kernel(const CsrKernelArgs a)
 {
@@ -83,7 +83,7 @@ csr_tma_kernel(const CsrKernelArgs a)
         hseq = *reinterpret_cast<volatile unsigned long long *>(&a.sync.win->halo_seq) + 1;
 
     TilePipe pipe;
-    spmv_phase<MODE, NDOT, HALO, true>(a, smem, mbar, pipe, acc, hseq, false);
+    spmv_phase<MODE, NDOT, HALO, true, RD>(a, smem, mbar, pipe, acc, hseq, false);
     finish_dots<NDOT>(a, acc);
 
     // peer-memory transport: the last CTA tells every source rank that this
@@ -195,25 +195,31 @@ ell_kernel(const EllKernelArgs a)
     }
 }
 
-template <int MODE, int NDOT, bool HALO>
-int launch_csr_t(const CsrKernelArgs &a, cudaStream_t st)
+template <int MODE, int NDOT, bool HALO, bool RD>
+int launch_csr_rd(const CsrKernelArgs &a, cudaStream_t st)
 {
     int grid = 0;
     const size_t smem = 2 * (size_t)kStageBytes;
-    SIGB_CHECK((occupancy_grid<csr_tma_kernel<MODE, NDOT, HALO>>(smem, &grid)));
+    SIGB_CHECK((occupancy_grid<csr_tma_kernel<MODE, NDOT, HALO, RD>>(smem, &grid)));
     if (a.ntiles < grid) grid = a.ntiles;
     if (grid < 1) grid = 1;
     if (HALO && a.sync.win != nullptr) {
         CsrKernelArgs b = a;
         int pc = (a.sync.total_send + 2 * kThreads - 1) / (2 * kThreads);   // ~2 entries per thread
         b.sync.push_ctas = a.sync.total_send > 0 ? std::max(1, std::min(pc, grid)) : 0;
-        csr_tma_kernel<MODE, NDOT, HALO><<<grid, kThreads, smem, st>>>(b);
+        csr_tma_kernel<MODE, NDOT, HALO, RD><<<grid, kThreads, smem, st>>>(b);
     } else {
-        csr_tma_kernel<MODE, NDOT, HALO><<<grid, kThreads, smem, st>>>(a);
+        csr_tma_kernel<MODE, NDOT, HALO, RD><<<grid, kThreads, smem, st>>>(a);
     }
     count_launch();
     SIGB_CUDA(cudaGetLastError());
     return SIGB_OK;
+}
+
+template <int MODE, int NDOT, bool HALO>
+int launch_csr_t(const CsrKernelArgs &a, cudaStream_t st, bool rowdirect)
+{
+    return rowdirect ? launch_csr_rd<MODE, NDOT, HALO, true>(a, st) : launch_csr_rd<MODE, NDOT, HALO, false>(a, st);
 }
 
 template <int MODE, int NDOT, int W>
@@ -247,6 +253,22 @@ int launch_ell_w(const EllKernelArgs &a, cudaStream_t st)
 }
 
 }  // namespace
+
+// EXPERIMENTAL row-direct form of the streaming kernel (spmv_device.cuh).  SIGB_SPMV_ROWDIRECT:
+// unset / 0 = never (the measured round-1 kernel), 1 = every matrix (parity runs), 2 = matrices
+// with at most 8 stored entries per row on average.
+bool spmv_rowdirect(const CsrView &A)
+{
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("SIGB_SPMV_ROWDIRECT");
+        mode = e ? atoi(e) : 0;
+        if (mode < 0 || mode > 2) mode = 0;
+    }
+    if (mode == 1) return true;
+    if (mode == 2) return A.nrows > 0 && A.nnz <= 8 * (int64_t)A.nrows;
+    return false;
+}
 
 // Greedy row tiling: consecutive rows while the tile holds <= kTileCap entries
 // and <= kTileRows rows; a longer row gets a tile of its own.  ptr is monotone,
@@ -348,11 +370,12 @@ int launch_csr_spmv(const CsrView &A, const double *val, const double *x, double
     cudaStream_t st = stream ? stream : ctx().stream;
     if (a.ntiles == 0 && dot.ndot == 0) return SIGB_OK;
 
+    const bool rd = spmv_rowdirect(A);
 #define SIGB_DISPATCH(M)                                                            \
     switch (dot.ndot) {                                                             \
-    case 0: return halo ? launch_csr_t<M, 0, true>(a, st) : launch_csr_t<M, 0, false>(a, st);  \
-    case 1: return halo ? launch_csr_t<M, 1, true>(a, st) : launch_csr_t<M, 1, false>(a, st);  \
-    default: return halo ? launch_csr_t<M, 2, true>(a, st) : launch_csr_t<M, 2, false>(a, st); \
+    case 0: return halo ? launch_csr_t<M, 0, true>(a, st, rd) : launch_csr_t<M, 0, false>(a, st, rd);  \
+    case 1: return halo ? launch_csr_t<M, 1, true>(a, st, rd) : launch_csr_t<M, 1, false>(a, st, rd);  \
+    default: return halo ? launch_csr_t<M, 2, true>(a, st, rd) : launch_csr_t<M, 2, false>(a, st, rd); \
     }
     switch (mode) {
     case MODE_SET: SIGB_DISPATCH(MODE_SET)

@@ -182,7 +182,19 @@ struct TilePipe {
 // row-sharded operators on the peer-memory transport -- the halo push in the
 // prologue and the lazy wait before the first boundary tile.  hseq is the
 // sequence number of this SpMV (HALO only).  Dot partials accumulate in acc.
-template <int MODE, int NDOT, bool HALO, bool XNC>
+//
+// RD ("row direct", EXPERIMENTAL, opt-in through SIGB_SPMV_ROWDIRECT, not yet run on a GPU):
+// skip the pass that parks the rounded products in shared memory; the thread that owns a row
+// forms each product itself, in stored order, from the staged val / node slices.  Same
+// rounded products added in the same order, so the result is bit-identical.  Why: with ~5
+// entries per row the two-pass form costs ~28 bytes of shared-memory traffic per entry plus a
+// gather whose 32 lanes touch 6-7 sectors, and L1TEX (which serves both) is the most utilised
+// unit of this kernel (67-69 %, profiles/r1_ncu_csr_tma.txt); row-direct needs 12 bytes per
+// entry, one barrier less per tile, and on banded matrices the j-th entries of consecutive
+// rows are consecutive columns, so the gathers coalesce like the ELLPACK kernel's.  It loses
+// when rows are long or ragged (a warp runs as long as its longest row), hence a per-matrix
+// choice on the host.
+template <int MODE, int NDOT, bool HALO, bool XNC, bool RD = false>
 __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char *smem, uint64_t *mbar,
                                            TilePipe &pipe, double *acc, unsigned long long hseq,
                                            bool prime_next)
@@ -300,6 +312,58 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
             SIGB_TCLK(tk0);
             mbar_wait(&mbar[stage], (sidx >> 1) & 1u);
             SIGB_TCLK(tk1);
+            if (RD) {
+                // ---- row direct: one thread per row, products formed inline -----
+                SIGB_TCLK(tk2);
+                double ur[kTileRows / kThreads];
+#pragma unroll
+                for (int i = 0; i < kTileRows / kThreads; i++) {
+                    const int r = rs + tid + i * kThreads;
+                    ur[i] = (NDOT >= 1 && r < re) ? ld_x<XNC>(a.u + r) : 0.0;
+                }
+                const bool boundary = HALO && t >= a.first_halo_tile;   // CTA-uniform
+#pragma unroll
+                for (int i = 0; i < kTileRows / kThreads; i++) {
+                    const int r = rs + tid + i * kThreads;
+                    if (r < re) {
+                        const int b = sptr[r - ra] - 1 - ka, e = sptr[r + 1 - ra] - 1 - ka;
+                        double z = (MODE == MODE_ACC_INIT) ? a.y[r] : 0.0;
+                        for (int k = b; k < e; k += 4) {
+                            int c[4];
+                            double v[4], xv[4];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const bool ok = k + j < e;
+                                c[j] = ok ? snode[k + j] : 1;
+                                v[j] = ok ? sval[k + j] : 0.0;
+                            }
+                            if (boundary) {
+#pragma unroll
+                                for (int j = 0; j < 4; j++) {
+                                    const double *src = (c[j] > a.nloc) ? h1 + c[j] : a.x1 + c[j];
+                                    xv[j] = __ldcg(src);
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; j++) xv[j] = ld_x<XNC>(a.x1 + c[j]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                if (k + j < e) z = add(z, mul(v[j], xv[j]));
+                        }
+                        emit_row<MODE, NDOT>(a, r, z, ur[i], acc);
+                    }
+                }
+                fence_proxy_async();
+                __syncthreads();
+                SIGB_TCLK(tk3);
+                SIGB_TACC(c_wait, tk1, tk0);
+                SIGB_TACC(c_prod, tk2, tk1);
+                SIGB_TACC(c_rows, tk3, tk2);
+#ifdef SIGB_PHASE_TIMERS
+                c_tiles++;
+#endif
+            } else {
             // ---- phase 1: products, in place --------------------------------
             // (entries before ks belong to the previous tile and hold valid
             // columns, so every gather below is in range)
@@ -365,6 +429,7 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
 #ifdef SIGB_PHASE_TIMERS
             c_tiles++;
 #endif
+            }   // !RD
         } else {
             long_row<MODE, NDOT, HALO, XNC>(a, d_cur, h1, acc);
         }

@@ -15,6 +15,9 @@ subprocess; the whole file is skipped unless SIGB_TEST_EXPERIMENTAL=1.
                             each, rows waiting for the entries they read instead of one launch
                             per level (csrc/ldu.cu).  Same arithmetic per row: the ILDU parity
                             tests (bit-exact factors and solves) must stay green with it on.
+  SIGB_SPMV_ROWDIRECT=1     row-direct form of the streaming CSR kernel for every matrix (csrc/
+                            spmv_device.cuh): same products in the same order, so every SpMV /
+                            solver / operator / sharded parity test must stay green with it on.
   SIGB_BICGSTAB_LDU=1       bicgstab_solve_pc with pc = ldu() on the device (csrc/solvers.cu); the
                             default build refuses the pair (tests/test_gpu_ldu.py checks that)."""
 import os
@@ -164,3 +167,22 @@ BICGSTAB_LDU = """
 def test_bicgstab_with_ldu_preconditioner():
     out = run_snippet(BICGSTAB_LDU, SIGB_BICGSTAB_LDU="1")
     assert "bicgstab+ldu ok" in out
+
+
+@pytest.mark.parametrize("files", [["tests/test_gpu_spmv.py"], ["tests/test_gpu_solvers.py"],
+                                   ["tests/test_gpu_operators.py", "tests/test_gpu_convert.py"],
+                                   ["tests/test_gpu_dist.py"]],
+                         ids=["spmv", "solvers", "operators_copies", "sharded"])
+def test_parity_with_rowdirect_spmv(files):
+    e = dict(os.environ)
+    e["SIGB_SPMV_ROWDIRECT"] = "1"
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu"] + files, cwd=ROOT, env=e,
+                       capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_persistent_cg_with_rowdirect_spmv():
+    # the persistent kernel's own instantiation (small problems take it by default)
+    out = run_snippet(SINGLE_REDUCE.replace("single-reduce ok", "rowdirect persistent ok"),
+                      SIGB_SPMV_ROWDIRECT="1", SIGB_CG_PERSISTENT="1")
+    assert "rowdirect persistent ok" in out
