@@ -74,6 +74,21 @@ static void free_view(CsrView &v)
     v = CsrView();
 }
 
+// Early returns out of the create functions (a CUDA failure half way) must not leak what
+// has been built so far: the guards release it unless dismissed on success.
+struct GraphGuard {
+    sigb_graph_t g;
+    ~GraphGuard() { if (g) sigb_graph_release(g); }
+};
+struct MatrixGuard {
+    sigb_matrix_t A;
+    ~MatrixGuard() { if (A) sigb_matrix_destroy(A); }
+};
+struct DevBufGuard {
+    void *p;
+    ~DevBufGuard() { cudaFree(p); }
+};
+
 // Build the stable transpose of a cs / ell graph on the device (once).
 static int ensure_graph_transposed(sigb_graph_t g)
 {
@@ -311,6 +326,7 @@ int sigb_cs_graph_create(int32_t n, int32_t m, const int32_t *ptr1, const int32_
                      node1[k], m);
 
     sigb_graph_t g = new sigb_graph_s();
+    GraphGuard guard{g};
     g->kind = (order == SIGB_ROW) ? G_CSR : G_CSC;
     g->n = n;
     g->m = m;
@@ -332,6 +348,7 @@ int sigb_cs_graph_create(int32_t n, int32_t m, const int32_t *ptr1, const int32_
     build_tiles_host(ptr1, n, tiles);
     SIGB_CHECK(upload_tiles(v, tiles));
     if (g->kind == G_CSC) SIGB_CHECK(ensure_graph_transposed(g));
+    guard.g = nullptr;
     *out = g;
     return SIGB_OK;
 }
@@ -356,6 +373,7 @@ int sigb_ell_graph_create(int32_t n, int32_t m, int32_t max_d, const int32_t *no
         }
     }
     sigb_graph_t g = new sigb_graph_s();
+    GraphGuard guard{g};
     g->kind = G_ELL;
     g->n = n;
     g->m = m;
@@ -365,13 +383,14 @@ int sigb_ell_graph_create(int32_t n, int32_t m, int32_t max_d, const int32_t *no
     cudaStream_t st = ctx().stream;
     int32_t *tmp = nullptr;
     SIGB_CHECK(dev_alloc(&tmp, (size_t)n * max_d));
+    DevBufGuard tmp_guard{tmp};
     SIGB_CUDA(cudaMemcpyAsync(tmp, node_cm, sizeof(int32_t) * (size_t)n * max_d, cudaMemcpyHostToDevice, st));
     SIGB_CHECK(dev_alloc(&g->ell_node, (size_t)g->n_pad * max_d));
     SIGB_CHECK(ell_relayout_node(tmp, n, g->n_pad, max_d, g->ell_node));
     SIGB_CHECK(dev_alloc(&g->ell_degrees, (size_t)n));
     SIGB_CUDA(cudaMemcpyAsync(g->ell_degrees, degrees, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
     SIGB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(tmp);
+    guard.g = nullptr;
     *out = g;
     return SIGB_OK;
 }
@@ -417,6 +436,7 @@ int sigb_matrix_create(sigb_graph_t g, sigb_matrix_t *out)
     SIGB_CHECK(require_init());
     SIGB_REQUIRE(g && out, SIGB_ERR_ARG, "sigb_matrix_create: bad argument");
     sigb_matrix_t A = new sigb_matrix_s();
+    MatrixGuard guard{A};
     A->g = g;
     g->refcount++;
     if (g->kind == G_CSC) { A->nrow = g->m; A->ncol = g->n; }
@@ -424,6 +444,7 @@ int sigb_matrix_create(sigb_graph_t g, sigb_matrix_t *out)
     const size_t len = (g->kind == G_ELL) ? (size_t)g->n_pad * g->max_d : (size_t)g->ne + 8;
     SIGB_CHECK(dev_alloc(&A->val, len));
     SIGB_CUDA(cudaMemsetAsync(A->val, 0, sizeof(double) * len, ctx().stream));  // A%val = 0
+    guard.A = nullptr;
     *out = A;
     return SIGB_OK;
 }
@@ -440,10 +461,10 @@ int sigb_matrix_set_values(sigb_matrix_t A, const double *val, int64_t count)
                      (long long)count, (long long)want);
         double *tmp = nullptr;
         SIGB_CHECK(dev_alloc(&tmp, (size_t)want));
+        DevBufGuard tmp_guard{tmp};
         SIGB_CUDA(cudaMemcpyAsync(tmp, val, sizeof(double) * (size_t)want, cudaMemcpyHostToDevice, st));
         SIGB_CHECK(ell_relayout_val(tmp, g->n, g->n_pad, g->max_d, A->val));
         SIGB_CUDA(cudaStreamSynchronize(st));
-        cudaFree(tmp);
     } else {
         SIGB_REQUIRE(count == g->ne, SIGB_ERR_ARG, "sigb_matrix_set_values: got %lld values, graph has %lld edges",
                      (long long)count, (long long)g->ne);
