@@ -11,6 +11,7 @@ timeout 900 python -m pytest tests -x -q -m gpu > $OUT/pytest_gpu.log 2>&1; echo
 tail -5 $OUT/pytest_gpu.log | tee -a $S
 echo "== 2. experimental paths (SIGB_TEST_EXPERIMENTAL=1), one test at a time so a hang costs one timeout" | tee -a $S
 for t in test_device_built_tiles_equal_the_host_tiling test_copy_and_transpose_parity_with_device_tiles \
+         test_copy_assembly_parity_with_async_scratch \
          test_parity_with_rowdirect_spmv test_persistent_cg_with_rowdirect_spmv test_ldu_parity_with_syncfree_sweeps \
          test_single_reduction_persistent_cg test_bicgstab_with_ldu_preconditioner; do
   SIGB_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -x -q -k $t > $OUT/exp_$t.log 2>&1
@@ -36,7 +37,8 @@ grep -h "ldu apply\|ldu setup\|CG iterations" $OUT/ldu_*.jsonl | cut -c1-300 | t
 echo "== 5. copies / assembly: host tiling vs device tiling" | tee -a $S
 timeout 400 python bench.py --rows widened > $OUT/widened_default.jsonl 2> $OUT/widened_default.err; echo "rc=$?" | tee -a $S
 SIGB_DEVICE_TILES=1 timeout 400 python bench.py --rows widened > $OUT/widened_devtiles.jsonl 2> $OUT/widened_devtiles.err; echo "rc=$?" | tee -a $S
-grep -h "copy_matrix" $OUT/widened_*.jsonl | cut -c1-260 | tee -a $S
+SIGB_DEVICE_TILES=1 SIGB_ASYNC_ALLOC=1 timeout 400 python bench.py --rows widened > $OUT/widened_devtiles_async.jsonl 2> $OUT/widened_devtiles_async.err; echo "rc=$?" | tee -a $S
+grep -h "copy_matrix\|add_value" $OUT/widened_*.jsonl | cut -c1-260 | tee -a $S
 echo "== 6. persistent CG at the 8-GPU shard size on one GPU: default / single reduction / phase breakdown" | tee -a $S
 for v in "" 1; do
   SIGB_CG_PERSISTENT=1 SIGB_CG_SINGLE_REDUCE=$v timeout 300 python bench.py --grid 1448 --steps 400 --warmup 5 --quick 2>> $OUT/pers.err | sed "s/^{/{\"single_reduce\": \"$v\", /" | tee -a $OUT/pers.jsonl | tee -a $S

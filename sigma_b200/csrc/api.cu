@@ -42,6 +42,39 @@ int require_init()
     return SIGB_OK;
 }
 
+static bool async_alloc_enabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SIGB_ASYNC_ALLOC");
+        v = (e && atoi(e) == 1) ? 1 : 0;
+        if (v) {
+            // keep freed blocks in the pool instead of returning them at every synchronisation
+            cudaMemPool_t pool = nullptr;
+            unsigned long long keep = ~0ull;
+            if (cudaDeviceGetDefaultMemPool(&pool, ctx().device) != cudaSuccess ||
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess) {
+                cudaGetLastError();
+                v = 0;
+            }
+        }
+    }
+    return v != 0;
+}
+
+cudaError_t tmp_alloc_bytes(void **p, size_t bytes)
+{
+    if (async_alloc_enabled()) return cudaMallocAsync(p, bytes, ctx().stream);
+    return cudaMalloc(p, bytes);
+}
+
+cudaError_t tmp_free(void *p)
+{
+    if (p == nullptr) return cudaSuccess;
+    if (async_alloc_enabled()) return cudaFreeAsync(p, ctx().stream);
+    return cudaFree(p);
+}
+
 template <typename T>
 static int dev_alloc(T **p, size_t count)
 {

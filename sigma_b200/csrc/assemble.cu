@@ -133,16 +133,16 @@ int sigb_matrix_add_values(sigb_matrix_t A, int64_t count, const int32_t *i1, co
     Miss *miss = nullptr;
     int rc = SIGB_OK;
     auto cleanup = [&]() {
-        cudaFree(ci); cudaFree(cj); cudaFree(slot1); cudaFree(one_line); cudaFree(bucket_ptr);
-        cudaFree(unused_node); cudaFree(perm); cudaFree(cz); cudaFree(miss);
+        tmp_free(ci); tmp_free(cj); tmp_free(slot1); tmp_free(one_line); tmp_free(cz); tmp_free(miss);
+        cudaFree(bucket_ptr); cudaFree(unused_node); cudaFree(perm);   // outputs of device_transpose_cs
     };
 #define AS_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cleanup(); return cuda_fail(e_, #expr, __FILE__, __LINE__); } } while (0)
 #define AS_TRY(expr) do { rc = (expr); if (rc != SIGB_OK) { cleanup(); return rc; } } while (0)
-    AS_CUDA(cudaMalloc((void **)&ci, sizeof(int32_t) * (size_t)count));
-    AS_CUDA(cudaMalloc((void **)&cj, sizeof(int32_t) * (size_t)count));
-    AS_CUDA(cudaMalloc((void **)&cz, sizeof(double) * (size_t)count));
-    AS_CUDA(cudaMalloc((void **)&slot1, sizeof(int32_t) * ((size_t)count + kPad)));
-    AS_CUDA(cudaMalloc((void **)&miss, sizeof(Miss)));
+    AS_CUDA(tmp_alloc(&ci, (size_t)count));
+    AS_CUDA(tmp_alloc(&cj, (size_t)count));
+    AS_CUDA(tmp_alloc(&cz, (size_t)count));
+    AS_CUDA(tmp_alloc(&slot1, (size_t)count + kPad));
+    AS_CUDA(tmp_alloc(&miss, 1));
     AS_CUDA(cudaMemcpyAsync(ci, i1, sizeof(int32_t) * (size_t)count, cudaMemcpyHostToDevice, st));
     AS_CUDA(cudaMemcpyAsync(cj, j1, sizeof(int32_t) * (size_t)count, cudaMemcpyHostToDevice, st));
     AS_CUDA(cudaMemcpyAsync(cz, z, sizeof(double) * (size_t)count, cudaMemcpyHostToDevice, st));
@@ -177,7 +177,7 @@ int sigb_matrix_add_values(sigb_matrix_t A, int64_t count, const int32_t *i1, co
 
     // 2. group the calls by stored position: the stable transpose of a one-line
     //    "graph" whose ids are the positions
-    AS_CUDA(cudaMalloc((void **)&one_line, sizeof(int32_t) * (2 + kPad)));
+    AS_CUDA(tmp_alloc(&one_line, (size_t)(2 + kPad)));
     {
         int32_t h_line[2] = {1, (int32_t)(count + 1)};
         AS_CUDA(cudaMemcpyAsync(one_line, h_line, sizeof(h_line), cudaMemcpyHostToDevice, st));

@@ -255,6 +255,21 @@ int fill_i32(int32_t *p, int64_t n, int32_t v);
 int fill_f64(double *p, int64_t n, double v);
 
 // ---------------------------------------------------------------------------
+// short-lived device scratch (api.cu).  Default: cudaMalloc / cudaFree.  EXPERIMENTAL
+// (SIGB_ASYNC_ALLOC=1, not yet run on a GPU): stream-ordered cudaMallocAsync / cudaFreeAsync
+// on the library's stream from the device's default pool, kept cached (no release
+// threshold), so a copy / transpose / assembly call does not pay a device-wide
+// synchronisation per temporary.
+// ---------------------------------------------------------------------------
+cudaError_t tmp_alloc_bytes(void **p, size_t bytes);
+cudaError_t tmp_free(void *p);
+template <typename T>
+inline cudaError_t tmp_alloc(T **p, size_t count)
+{
+    return tmp_alloc_bytes((void **)p, sizeof(T) * (count > 0 ? count : 1));
+}
+
+// ---------------------------------------------------------------------------
 // matrix-level dispatch (api.cu)
 // ---------------------------------------------------------------------------
 int ensure_transposed(sigb_matrix_t A);

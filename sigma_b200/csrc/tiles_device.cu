@@ -134,20 +134,20 @@ int build_tiles_device(const int32_t *ptr1_dev, int32_t nrows, CsrView &v, int32
     int *finished = nullptr;
     TileDesc *tiles = nullptr;
     auto cleanup = [&]() {
-        cudaFree(next); cudaFree(jump_a); cudaFree(jump_b); cudaFree(mark); cudaFree(nonempty);
-        cudaFree(pos); cudaFree(pos_ne); cudaFree(minmax); cudaFree(finished);
+        tmp_free(next); tmp_free(jump_a); tmp_free(jump_b); tmp_free(mark); tmp_free(nonempty);
+        tmp_free(pos); tmp_free(pos_ne); tmp_free(minmax); tmp_free(finished);
     };
 #define TD_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cleanup(); cudaFree(tiles); return cuda_fail(e_, #expr, __FILE__, __LINE__); } } while (0)
 #define TD_TRY(expr) do { int rc_ = (expr); if (rc_ != SIGB_OK) { cleanup(); cudaFree(tiles); return rc_; } } while (0)
-    TD_CUDA(cudaMalloc((void **)&next, sizeof(int32_t) * len));
-    TD_CUDA(cudaMalloc((void **)&jump_a, sizeof(int32_t) * len));
-    TD_CUDA(cudaMalloc((void **)&jump_b, sizeof(int32_t) * len));
-    TD_CUDA(cudaMalloc((void **)&mark, sizeof(int32_t) * len));
-    TD_CUDA(cudaMalloc((void **)&nonempty, sizeof(int32_t) * len));
-    TD_CUDA(cudaMalloc((void **)&pos, sizeof(int32_t) * len));
-    TD_CUDA(cudaMalloc((void **)&pos_ne, sizeof(int32_t) * len));
-    TD_CUDA(cudaMalloc((void **)&minmax, sizeof(int32_t) * 2));
-    TD_CUDA(cudaMalloc((void **)&finished, sizeof(int)));
+    TD_CUDA(tmp_alloc(&next, len));
+    TD_CUDA(tmp_alloc(&jump_a, len));
+    TD_CUDA(tmp_alloc(&jump_b, len));
+    TD_CUDA(tmp_alloc(&mark, len));
+    TD_CUDA(tmp_alloc(&nonempty, len));
+    TD_CUDA(tmp_alloc(&pos, len));
+    TD_CUDA(tmp_alloc(&pos_ne, len));
+    TD_CUDA(tmp_alloc(&minmax, 2));
+    TD_CUDA(tmp_alloc(&finished, 1));
     const int32_t h_init[2] = {0, INT32_MAX};
     TD_CUDA(cudaMemcpyAsync(minmax, h_init, sizeof(h_init), cudaMemcpyHostToDevice, st));
     TD_CUDA(cudaMemsetAsync(finished, 0, sizeof(int), st));

@@ -277,7 +277,7 @@ int scan_to_ptr1(const int32_t *cnt, int64_t n, int32_t *ptr1)
     // n counts -> n + 1 one-based offsets
     const int nblocks = (int)((n + 1 + kScanItems - 1) / kScanItems);
     int64_t *block_sum = nullptr;
-    SIGB_CUDA(cudaMalloc(&block_sum, sizeof(int64_t) * (size_t)nblocks));
+    SIGB_CUDA(tmp_alloc(&block_sum, (size_t)nblocks));
     cudaStream_t st = ctx().stream;
     scan_block_sums<<<nblocks, kThreads, 0, st>>>(cnt, n, block_sum);
     scan_block_offsets<<<1, 32, 0, st>>>(block_sum, nblocks);
@@ -285,7 +285,7 @@ int scan_to_ptr1(const int32_t *cnt, int64_t n, int32_t *ptr1)
     count_launch(3);
     SIGB_CUDA(cudaGetLastError());
     SIGB_CUDA(cudaStreamSynchronize(st));
-    SIGB_CUDA(cudaFree(block_sum));
+    SIGB_CUDA(tmp_free(block_sum));
     return SIGB_OK;
 }
 
@@ -297,8 +297,8 @@ int finish_transpose(int32_t ntargets, int64_t ne, int32_t *ptr_t, int32_t *perm
     // rows longer than kLongRow are listed by the first kernel; at most ne / kLongRow of them
     const int64_t max_long = ne / kLongRow + 1;
     int32_t *long_rows = nullptr, *n_long = nullptr;
-    SIGB_CUDA(cudaMalloc(&long_rows, sizeof(int32_t) * (size_t)max_long));
-    SIGB_CUDA(cudaMalloc(&n_long, sizeof(int32_t)));
+    SIGB_CUDA(tmp_alloc(&long_rows, (size_t)max_long));
+    SIGB_CUDA(tmp_alloc(&n_long, 1));
     SIGB_CUDA(cudaMemsetAsync(n_long, 0, sizeof(int32_t), st));
     sort_rows_kernel<<<grid_for(ntargets), kThreads, 0, st>>>(ptr_t, ntargets, perm, long_rows, n_long);
     count_launch();
@@ -308,7 +308,7 @@ int finish_transpose(int32_t ntargets, int64_t ne, int32_t *ptr_t, int32_t *perm
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     int32_t *scratch = nullptr;
     if (e == cudaSuccess && h_long > 0) {
-        e = cudaMalloc(&scratch, sizeof(int32_t) * (size_t)(ne > 0 ? ne : 1));
+        e = tmp_alloc(&scratch, (size_t)(ne > 0 ? ne : 1));
         if (e == cudaSuccess) {
             const int grid = h_long < ctx().num_sms * 4 ? h_long : ctx().num_sms * 4;
             sort_long_rows_kernel<<<grid, kThreads, 0, st>>>(ptr_t, long_rows, h_long, perm, scratch);
@@ -317,9 +317,9 @@ int finish_transpose(int32_t ntargets, int64_t ne, int32_t *ptr_t, int32_t *perm
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     }
-    cudaFree(scratch);
-    cudaFree(long_rows);
-    cudaFree(n_long);
+    tmp_free(scratch);
+    tmp_free(long_rows);
+    tmp_free(n_long);
     if (e != cudaSuccess) return cuda_fail(e, "finish_transpose", __FILE__, __LINE__);
     return SIGB_OK;
 }
@@ -350,7 +350,7 @@ int device_transpose_cs(const int32_t *ptr1, const int32_t *node1, int32_t nline
 {
     cudaStream_t st = ctx().stream;
     int32_t *cnt = nullptr, *ptr_t = nullptr, *node_t = nullptr, *perm = nullptr;
-    SIGB_CUDA(cudaMalloc(&cnt, sizeof(int32_t) * ((size_t)ntargets + 1)));
+    SIGB_CUDA(tmp_alloc(&cnt, (size_t)ntargets + 1));
     SIGB_CUDA(cudaMalloc(&ptr_t, sizeof(int32_t) * ((size_t)ntargets + 1 + kPad)));
     SIGB_CHECK(fill_i32(ptr_t + ntargets + 1, kPad, 1));
     SIGB_CUDA(cudaMalloc(&node_t, sizeof(int32_t) * ((size_t)ne + 8)));
@@ -373,7 +373,7 @@ int device_transpose_cs(const int32_t *ptr1, const int32_t *node1, int32_t nline
     }
     SIGB_CUDA(cudaGetLastError());
     SIGB_CUDA(cudaStreamSynchronize(st));
-    SIGB_CUDA(cudaFree(cnt));
+    SIGB_CUDA(tmp_free(cnt));
     *ptr_t_out = ptr_t;
     *node_t_out = node_t;
     *perm_out = perm;
@@ -387,7 +387,7 @@ int device_transpose_ell(const int32_t *node_sm, int32_t n, int32_t n_pad, int32
     cudaStream_t st = ctx().stream;
     const int64_t ne = (int64_t)n * max_d;
     int32_t *cnt = nullptr, *ptr_t = nullptr, *node_t = nullptr, *perm = nullptr;
-    SIGB_CUDA(cudaMalloc(&cnt, sizeof(int32_t) * ((size_t)ntargets + 1)));
+    SIGB_CUDA(tmp_alloc(&cnt, (size_t)ntargets + 1));
     SIGB_CUDA(cudaMalloc(&ptr_t, sizeof(int32_t) * ((size_t)ntargets + 1 + kPad)));
     SIGB_CHECK(fill_i32(ptr_t + ntargets + 1, kPad, 1));
     SIGB_CUDA(cudaMalloc(&node_t, sizeof(int32_t) * ((size_t)ne + 8)));
@@ -410,7 +410,7 @@ int device_transpose_ell(const int32_t *node_sm, int32_t n, int32_t n_pad, int32
     }
     SIGB_CUDA(cudaGetLastError());
     SIGB_CUDA(cudaStreamSynchronize(st));
-    SIGB_CUDA(cudaFree(cnt));
+    SIGB_CUDA(tmp_free(cnt));
     *ptr_t_out = ptr_t;
     *node_t_out = node_t;
     *perm_out = perm;

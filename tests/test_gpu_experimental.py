@@ -15,6 +15,8 @@ subprocess; the whole file is skipped unless SIGB_TEST_EXPERIMENTAL=1.
                             each, rows waiting for the entries they read instead of one launch
                             per level (csrc/ldu.cu).  Same arithmetic per row: the ILDU parity
                             tests (bit-exact factors and solves) must stay green with it on.
+  SIGB_ASYNC_ALLOC=1        temporaries of transposes / copies / assembly from the stream-ordered pool
+                            (cudaMallocAsync / cudaFreeAsync) instead of cudaMalloc / cudaFree.
   SIGB_SPMV_ROWDIRECT=1     row-direct form of the streaming CSR kernel for every matrix (csrc/
                             spmv_device.cuh): same products in the same order, so every SpMV /
                             solver / operator / sharded parity test must stay green with it on.
@@ -186,3 +188,13 @@ def test_persistent_cg_with_rowdirect_spmv():
     out = run_snippet(SINGLE_REDUCE.replace("single-reduce ok", "rowdirect persistent ok"),
                       SIGB_SPMV_ROWDIRECT="1", SIGB_CG_PERSISTENT="1")
     assert "rowdirect persistent ok" in out
+
+
+def test_copy_assembly_parity_with_async_scratch():
+    e = dict(os.environ)
+    e["SIGB_ASYNC_ALLOC"] = "1"
+    e["SIGB_DEVICE_TILES"] = "1"
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_convert.py",
+                        "tests/test_gpu_assemble.py", "tests/test_gpu_spmv.py", "tests/test_gpu_ldu.py"], cwd=ROOT, env=e,
+                       capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
