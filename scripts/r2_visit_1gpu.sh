@@ -24,6 +24,11 @@ echo "== 3b. SpMV A/B: two-pass (default) vs row-direct, full size and the 8-GPU
 for g in 4096 1448; do for rd in 0 1; do
   SIGB_SPMV_ROWDIRECT=$rd timeout 300 python bench.py --grid $g --steps 200 --warmup 5 --quick 2>> $OUT/rowdirect.err | sed "s/^{/{\"grid\": $g, \"rowdirect\": $rd, /" | tee -a $OUT/rowdirect.jsonl | tee -a $S
 done; done
+# 256-row tiles: with row-direct every thread owns exactly one row of a 5-point tile (built here as
+# make VARIANT=_t1536r256 DEFS="-DSIGB_TILE_NNZ=1536 -DSIGB_TILE_ROWS=256")
+for rd in 0 1; do
+  SIGB_LIB_VARIANT=_t1536r256 SIGB_SPMV_ROWDIRECT=$rd timeout 300 python bench.py --steps 200 --warmup 5 --quick 2>> $OUT/rowdirect.err | sed "s/^{/{\"grid\": 4096, \"rowdirect\": $rd, /" | tee -a $OUT/rowdirect.jsonl | tee -a $S
+done
 SIGB_LIB_VARIANT=_timers SIGB_SPMV_ROWDIRECT=1 timeout 300 python bench.py --steps 50 --warmup 3 --quick > /dev/null 2> $OUT/spmv_tiles_rowdirect.err
 grep spmv_cta_pass $OUT/spmv_tiles_rowdirect.err | tee -a $S
 echo "== 4. ILDU: per-level launches vs sync-free sweeps" | tee -a $S
