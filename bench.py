@@ -140,6 +140,13 @@ def cpu_cg_rate(N, iters, warm=1):
     return it / t, it, t
 
 
+def workload(N):
+    """The same workload string on both arms (the driver pairs the lines by metric and config)."""
+    n = N * N
+    return (f"2D Poisson 5-point CSR {N}x{N} (n={n}, nnz={5 * n - 4 * N}), fp64 CG, x0=0, "
+            f"b=A*rand(seed 12345), tol=1e-10*|b|")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -153,7 +160,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": it, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 / rate, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"2D Poisson 5-point CSR {N}x{N} (n={n}), fp64 CG, x0=0, b=A*rand(seed 12345)"},
+        "config": {"workload": workload(N)},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
                          "sample": f"{it} full-size CG iterations of the serial C restatement of cg_solve "
                                    f"(gcc -O2 -ffp-contract=off), init pass subtracted; reference is serial Fortran, "
@@ -391,8 +398,7 @@ def run_ours(args):
             "metric": METRIC, "value": cg_rate, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_cg / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"2D Poisson 5-point CSR {N}x{N} (n={n}, nnz={nnz_glob}), fp64 CG, x0=0, "
-                                   f"b=A*rand(seed 12345), tol=1e-10*|b|",
+            "config": {"workload": workload(N),
                        "sharding": f"contiguous row blocks over {world} GPU(s), halo + dot all-reduce transport: {transport}",
                        "l2": "inputs larger than L2 (matrix 1.0 GB + 5 vectors of 134 MB per solve)",
                        "step": "one CG iteration (3 kernels)"},
