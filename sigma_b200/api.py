@@ -384,12 +384,14 @@ def ldu_symbolic(n, ptr1, node1):
 
 
 def lanczos(A: Matrix, n: int, q1=None, seed: int = 0):
-    """call lanczos(A, T, Q) -> T[3, n] (T(1,:), T(2,:), T(3,:)), Q[nrow, n]."""
+    """call lanczos(A, T, Q) -> T[3, n] (T(1,:), T(2,:), T(3,:)), Q[nrow, n].
+    Q (and V of the eigensolves below) comes back as the Fortran array it is: column-major,
+    i.e. a transposed VIEW of the buffer the library filled -- no host-side copy."""
     T = np.empty(3 * n)
     Q = np.empty(A.nrow * n)
     q1a = as_f64(q1) if q1 is not None else None
     check(lib().sigb_lanczos(A._h, n, ptr(q1a), seed, ptr(T), ptr(Q)))
-    return T.reshape(n, 3).T.copy(), Q.reshape(n, A.nrow).T.copy()
+    return T.reshape(n, 3).T.copy(), Q.reshape(n, A.nrow).T
 
 
 def eigensolve(A: Matrix, n: int, q1=None, seed: int = 0):
@@ -398,7 +400,7 @@ def eigensolve(A: Matrix, n: int, q1=None, seed: int = 0):
     V = np.empty(A.nrow * n)
     q1a = as_f64(q1) if q1 is not None else None
     check(lib().sigb_eigensolve(A._h, n, ptr(q1a), seed, ptr(lam), ptr(V)))
-    return lam, V.reshape(n, A.nrow).T.copy()
+    return lam, V.reshape(n, A.nrow).T
 
 
 def generalized_lanczos(A: Matrix, B: Matrix, b_solver: Solver, n: int, q1=None, seed: int = 0, b_pc: "Solver | None" = None):
@@ -408,7 +410,7 @@ def generalized_lanczos(A: Matrix, B: Matrix, b_solver: Solver, n: int, q1=None,
     q1a = as_f64(q1) if q1 is not None else None
     check(lib().sigb_generalized_lanczos(A._h, B._h, b_solver._h, b_pc._h if b_pc else None, n, ptr(q1a), seed,
                                          ptr(T), ptr(Q)))
-    return T.reshape(n, 3).T.copy(), Q.reshape(n, A.nrow).T.copy()
+    return T.reshape(n, 3).T.copy(), Q.reshape(n, A.nrow).T
 
 
 def generalized_eigensolve(A: Matrix, B: Matrix, b_solver: Solver, n: int, q1=None, seed: int = 0,
@@ -419,4 +421,4 @@ def generalized_eigensolve(A: Matrix, B: Matrix, b_solver: Solver, n: int, q1=No
     q1a = as_f64(q1) if q1 is not None else None
     check(lib().sigb_generalized_eigensolve(A._h, B._h, b_solver._h, b_pc._h if b_pc else None, n, ptr(q1a), seed,
                                             ptr(lam), ptr(V)))
-    return lam, V.reshape(n, A.nrow).T.copy()
+    return lam, V.reshape(n, A.nrow).T
