@@ -172,7 +172,7 @@ divide_kernel(double *__restrict__ x, const double *__restrict__ D, int64_t n, c
 // Every row still does the reference's arithmetic in stored order with rounded
 // products, so the factors and the solves stay bit-identical to the serial loops.
 // ---------------------------------------------------------------------------
-constexpr unsigned kSweepSpinLimit = 1u << 24;
+constexpr unsigned kSweepSpinLimit = 1u << 22;   // >= 1 s of polling: far beyond a whole sweep
 
 __device__ __forceinline__ bool ll_try(const RedEntry *e, unsigned seq, double *out)
 {
