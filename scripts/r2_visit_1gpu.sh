@@ -33,11 +33,13 @@ SIGB_LIB_VARIANT=_timers SIGB_SPMV_ROWDIRECT=1 timeout 300 python bench.py --ste
 grep spmv_cta_pass $OUT/spmv_tiles_rowdirect.err | tee -a $S
 echo "== 4. ILDU: per-level launches vs sync-free sweeps" | tee -a $S
 timeout 300 python bench.py --rows ldu > $OUT/ldu_default.jsonl 2> $OUT/ldu_default.err; echo "rc=$?" | tee -a $S
-for k in 1 2 4; do
-  SIGB_LDU_SYNCFREE=1 SIGB_LDU_SF_CTAS_PER_SM=$k timeout 300 python bench.py --rows ldu > $OUT/ldu_syncfree_c$k.jsonl 2> $OUT/ldu_syncfree_c$k.err
-  echo "syncfree ctas/sm=$k rc=$?" | tee -a $S
+for cfg in "PER_SM=1 SLEEP=0" "PER_SM=2 SLEEP=0" "PER_SM=1 SLEEP=32" "CTAS=64 SLEEP=0" "CTAS=64 SLEEP=32" "CTAS=32 SLEEP=0" "CTAS=16 SLEEP=0"; do
+  eval $cfg; tag=$(echo $cfg | tr ' =' '__')
+  SIGB_LDU_SYNCFREE=1 SIGB_LDU_SF_CTAS_PER_SM=${PER_SM:-1} SIGB_LDU_SF_CTAS=${CTAS:-0} SIGB_LDU_SF_SLEEP_NS=$SLEEP \
+    timeout 300 python bench.py --rows ldu > $OUT/ldu_syncfree_$tag.jsonl 2> $OUT/ldu_syncfree_$tag.err
+  echo "syncfree $cfg rc=$?" | tee -a $S
+  unset PER_SM CTAS SLEEP
 done
-SIGB_LDU_SYNCFREE=1 SIGB_LDU_SF_SLEEP_NS=100 timeout 300 python bench.py --rows ldu > $OUT/ldu_syncfree_sleep.jsonl 2> $OUT/ldu_syncfree_sleep.err
 grep -h "ldu apply\|ldu setup\|CG iterations" $OUT/ldu_*.jsonl | cut -c1-300 | tee -a $S
 echo "== 5. copies / assembly: host tiling vs device tiling" | tee -a $S
 timeout 400 python bench.py --rows widened > $OUT/widened_default.jsonl 2> $OUT/widened_default.err; echo "rc=$?" | tee -a $S

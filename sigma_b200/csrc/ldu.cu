@@ -21,6 +21,7 @@
 // other preconditioner the reference ships, not bandwidth.
 #include <stdlib.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "device_utils.cuh"
@@ -229,7 +230,7 @@ tri_syncfree_kernel(const int32_t *__restrict__ rows, int32_t n, const int32_t *
             }
             if (__all_sync(0xffffffffu, done)) break;
             if (++spins > kSweepSpinLimit) break;
-            if (sleep_ns) __nanosleep(sleep_ns);
+            if (sleep_ns) __nanosleep(sleep_ns << (spins < 3u ? spins : 3u));   // back off: base, 2x, 4x, 8x
         }
     }
 }
@@ -302,15 +303,17 @@ ldu_factor_syncfree_kernel(const int32_t *__restrict__ rows, int32_t n, const in
             }
             if (__all_sync(0xffffffffu, done)) break;
             if (++spins > kSweepSpinLimit) break;
-            if (sleep_ns) __nanosleep(sleep_ns);
+            if (sleep_ns) __nanosleep(sleep_ns << (spins < 3u ? spins : 3u));   // back off: base, 2x, 4x, 8x
         }
     }
 }
 
 struct SyncFreeCfg {
     bool on = false;
-    int ctas_per_sm = 2;
-    unsigned sleep_ns = 0;
+    int ctas_per_sm = 1;     // SIGB_LDU_SF_CTAS_PER_SM
+    int ctas = 0;            // SIGB_LDU_SF_CTAS: absolute grid size (wins when > 0); fewer resident threads
+                             // = fewer pollers competing with the wavefront for L2
+    unsigned sleep_ns = 0;   // SIGB_LDU_SF_SLEEP_NS: base of the polling back-off (0 = poll flat out)
 };
 const SyncFreeCfg &syncfree_cfg()
 {
@@ -320,6 +323,7 @@ const SyncFreeCfg &syncfree_cfg()
         const char *e = getenv("SIGB_LDU_SYNCFREE");
         c.on = e && atoi(e) == 1;
         if ((e = getenv("SIGB_LDU_SF_CTAS_PER_SM")) && atoi(e) > 0) c.ctas_per_sm = atoi(e);
+        if ((e = getenv("SIGB_LDU_SF_CTAS")) && atoi(e) > 0) c.ctas = atoi(e);
         if ((e = getenv("SIGB_LDU_SF_SLEEP_NS")) && atoi(e) >= 0) c.sleep_ns = (unsigned)atoi(e);
         read = true;
     }
@@ -333,8 +337,10 @@ int syncfree_grid(K kernel, int64_t n, int *grid)
     int per_sm = 0;
     SIGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
     if (per_sm < 1) per_sm = 1;
+    const int64_t resident = (int64_t)per_sm * ctx().num_sms;   // what a cooperative launch can hold
     if (per_sm > syncfree_cfg().ctas_per_sm) per_sm = syncfree_cfg().ctas_per_sm;
     int64_t g = (int64_t)per_sm * ctx().num_sms;
+    if (syncfree_cfg().ctas > 0) g = std::min<int64_t>(syncfree_cfg().ctas, resident);
     const int64_t need = (n + kThreads - 1) / kThreads;
     if (g > need) g = need;
     if (g < 1) g = 1;

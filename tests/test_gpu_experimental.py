@@ -124,8 +124,8 @@ def test_copy_and_transpose_parity_with_device_tiles():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize("knobs", [{}, {"SIGB_LDU_SF_CTAS_PER_SM": "1"}, {"SIGB_LDU_SF_SLEEP_NS": "100"}],
-                         ids=["default", "1cta_per_sm", "sleep100ns"])
+@pytest.mark.parametrize("knobs", [{}, {"SIGB_LDU_SF_CTAS_PER_SM": "2"}, {"SIGB_LDU_SF_CTAS": "8", "SIGB_LDU_SF_SLEEP_NS": "32"}],
+                         ids=["default", "2ctas_per_sm", "8ctas_backoff"])
 def test_ldu_parity_with_syncfree_sweeps(knobs):
     e = dict(os.environ)
     e["SIGB_LDU_SYNCFREE"] = "1"
