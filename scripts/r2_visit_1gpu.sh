@@ -50,6 +50,9 @@ echo "== 6. persistent CG at the 8-GPU shard size on one GPU: default / single r
 for v in "" 1; do
   SIGB_CG_PERSISTENT=1 SIGB_CG_SINGLE_REDUCE=$v timeout 300 python bench.py --grid 1448 --steps 400 --warmup 5 --quick 2>> $OUT/pers.err | sed "s/^{/{\"single_reduce\": \"$v\", /" | tee -a $OUT/pers.jsonl | tee -a $S
 done
+for c in 2 3; do
+  SIGB_CG_PERSISTENT=1 SIGB_CG_PERSIST_CTAS_PER_SM=$c timeout 300 python bench.py --grid 1448 --steps 400 --warmup 5 --quick 2>> $OUT/pers.err | sed "s/^{/{\"ctas_per_sm\": $c, /" | tee -a $OUT/pers.jsonl | tee -a $S
+done
 for v in "" 1; do
   SIGB_LIB_VARIANT=_timers SIGB_CG_PERSISTENT=1 SIGB_CG_SINGLE_REDUCE=$v timeout 300 python bench.py --grid 1448 --steps 400 --warmup 5 --quick > /dev/null 2> $OUT/phases_single$v.err
   grep phase_us $OUT/phases_single$v.err | tee -a $S

@@ -25,6 +25,7 @@
 // Per iteration this moves 12 nnz + 84 n bytes (the reference's statement order
 // costs 92 n: it reads p for the x update and again for the p update).
 #include <math.h>
+#include <stdlib.h>
 
 #include "krylov.cuh"
 #include "solvers.h"
@@ -519,12 +520,27 @@ cg_single_reduce_kernel(const CgPersistArgs a)
     }
 }
 
+// Experiment knob (SIGB_CG_PERSIST_CTAS_PER_SM = 1..4, default: all that fit): fewer resident
+// CTAs make the grid barriers and the partial-sum passes cheaper and the SpMV phase slower.
+static int cap_persistent_grid(int grid)
+{
+    static int per_sm = -1;
+    if (per_sm < 0) {
+        const char *e = getenv("SIGB_CG_PERSIST_CTAS_PER_SM");
+        per_sm = e ? atoi(e) : 0;
+        if (per_sm < 0) per_sm = 0;
+    }
+    if (per_sm > 0 && per_sm * ctx().num_sms < grid) grid = per_sm * ctx().num_sms;
+    return grid;
+}
+
 template <bool HALO>
 int launch_single_reduce(const CgPersistArgs &a, cudaStream_t st)
 {
     const size_t smem = 2 * (size_t)kStageBytes;
     int grid = 0;
     SIGB_CHECK((occupancy_grid<cg_single_reduce_kernel<HALO>>(smem, &grid)));
+    grid = cap_persistent_grid(grid);
     CgPersistArgs b = a;
     if (HALO && b.A.sync.win != nullptr) {
         int pc = (b.A.sync.total_send + 2 * kThreads - 1) / (2 * kThreads);
@@ -543,6 +559,7 @@ int launch_persistent(const CgPersistArgs &a, cudaStream_t st)
     const size_t smem = 2 * (size_t)kStageBytes;
     int grid = 0;
     SIGB_CHECK((occupancy_grid<cg_persistent_kernel<HALO, PC, RD>>(smem, &grid)));
+    grid = cap_persistent_grid(grid);
     CgPersistArgs b = a;
     if (HALO && b.A.sync.win != nullptr) {
         int pc = (b.A.sync.total_send + 2 * kThreads - 1) / (2 * kThreads);
