@@ -13,7 +13,7 @@ echo "== 2. experimental paths (SIGB_TEST_EXPERIMENTAL=1), one test at a time so
 for t in test_device_built_tiles_equal_the_host_tiling test_copy_and_transpose_parity_with_device_tiles \
          test_copy_assembly_parity_with_async_scratch \
          test_parity_with_rowdirect_spmv test_persistent_cg_with_rowdirect_spmv test_ldu_parity_with_syncfree_sweeps \
-         test_single_reduction_persistent_cg test_bicgstab_with_ldu_preconditioner test_matrix_test_strategy_on_the_device; do
+         test_single_reduction_persistent_cg test_bicgstab_with_ldu_preconditioner test_matrix_test_strategy_on_the_device test_matrix_test_set_multiple_entries_on_the_device; do
   SIGB_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -x -q -k $t > $OUT/exp_$t.log 2>&1
   echo "$t rc=$?" | tee -a $S; tail -3 $OUT/exp_$t.log | tee -a $S
 done

@@ -34,7 +34,8 @@ from ._capi import ROW, COL, SigmaError, as_f64, as_i32, check, lib, ptr
 __all__ = ["init", "Graph", "Matrix", "Solver", "cg", "bicgstab", "jacobi", "ldu", "ldu_symbolic", "lanczos", "eigensolve",
            "generalized_lanczos", "generalized_eigensolve",
            "csr_matrix", "csc_matrix", "ellpack_matrix", "SigmaError", "launch_count", "set_stream",
-           "synchronize", "Expression", "operator_sum", "operator_product", "adjoint", "sparse_matrix"]
+           "synchronize", "Expression", "operator_sum", "operator_product", "adjoint", "sparse_matrix",
+           "multiple_values_stream"]
 
 
 def init(device: int = -1):
@@ -174,6 +175,14 @@ class Matrix:
         check(lib().sigb_matrix_add_values(self._h, i1.size, ptr(i1), ptr(j1), ptr(z)))
         return self
 
+    def add_multiple_values(self, is1, js1, B):
+        """`call A%add_multiple_values(is, js, B)` (cs_matrices.f90:934-967, ellpack likewise): the
+        add_value stream (is(k), js(l), B(k, l)) with k outer, l inner.  is1 / js1 / B may carry a
+        leading batch axis -- (nb, ni), (nb, nj), (nb, ni, nj) -- for an assembly loop that issues
+        one small block per element: the blocks are applied in batch order by ONE device call."""
+        I, J, Z = multiple_values_stream(is1, js1, B)
+        return self.add_values(I, J, Z)
+
     def arrays(self):
         """The stored arrays, read back from the device exactly as the Fortran holds them:
         ("csr"|"csc", ptr, node, val) or ("ellpack", degrees, node[n, max_d], val[n, max_d])."""
@@ -254,6 +263,22 @@ def sparse_matrix(rows, cols, blocks) -> Expression:
     h = C.c_void_p()
     check(lib().sigb_composite_create(rows.size, cols.size, ptr(rows), ptr(cols), arr, C.byref(h)))
     return Expression(h, "composite", flat)
+
+
+def multiple_values_stream(is1, js1, B):
+    """The add_value calls `A%add_multiple_values(is, js, B)` makes, in its own loop order (k over
+    is outer, l over js inner, cs_matrices.f90:944-965); with a leading batch axis, block after
+    block.  Returns (i, j, z) ready for add_values / the oracle."""
+    is1, js1, B = np.asarray(is1, np.int32), np.asarray(js1, np.int32), np.asarray(B, np.float64)
+    if is1.ndim == 1:
+        is1, js1, B = is1[None], js1[None], B[None]
+    nb, ni = is1.shape
+    nj = js1.shape[1]
+    if js1.shape[0] != nb or B.shape != (nb, ni, nj):
+        raise SigmaError(_capi.ERR_ARG, "add_multiple_values: B must be size(is) x size(js)")
+    I = np.repeat(is1[:, :, None], nj, axis=2).reshape(-1)
+    J = np.repeat(js1[:, None, :], ni, axis=1).reshape(-1)
+    return I, J, B.reshape(-1)
 
 
 def csr_matrix(n, m, ptr1, node1, val):

@@ -240,3 +240,43 @@ def test_matrix_test_strategy_on_the_device():
     tests/test_gpu_operators.py once it has run."""
     out = run_snippet(STRATEGY)
     assert "strategy ok" in out
+
+
+MULTIPLE = """
+    import numpy as np
+    import oracle as orc
+    import sigma_b200 as sb
+    import tests.test_oracle_strategy as S
+    orc.build(); sb.init(0)
+    nn = 128
+    for fmt in ("csr", "csc", "ellpack"):
+        O, nbrs, connected = S.strategy_case(orc, nn, 23, fmt)
+        O.val[...] = 0.0
+        if fmt == "ellpack":
+            A = sb.ellpack_matrix(nn, nn, O.node, O.degrees, np.zeros(O.node.shape))
+        elif fmt == "csr":
+            A = sb.csr_matrix(nn, nn, O.ptr, O.node, np.zeros(O.node.size))
+        else:
+            A = sb.csc_matrix(nn, nn, O.ptr, O.node, np.zeros(O.node.size))
+        pairs = np.array([(i, j) for i in range(1, nn + 1) for j in nbrs[i - 1] if j > i], np.int32)
+        B = np.broadcast_to(np.array([[1.0, -1.0], [-1.0, 1.0]]), (pairs.shape[0], 2, 2))
+        A.add_multiple_values(pairs, pairs, B)               # all element blocks, one device call
+        assert orc.add_values(O, *sb.multiple_values_stream(pairs, pairs, B)) == 0
+        assert np.array_equal(A.arrays()[-1].reshape(-1), np.asarray(O.val).reshape(-1)), fmt
+        # the checks of the test on the device result, through the matrix's own matvec: row sums
+        # of a graph Laplacian vanish, and A e_i reads column i
+        assert np.array_equal(A.matvec(np.ones(nn)), np.zeros(nn)), fmt
+        for i in (1, 17, nn):
+            e = np.zeros(nn); e[i - 1] = 1.0
+            col = A.matvec(e)
+            want = np.where(connected[:, i - 1], -1.0, 0.0); want[i - 1] = len(nbrs[i - 1]) - 1
+            assert np.array_equal(col, want), (fmt, i)
+    print("multiple entries ok")
+"""
+
+
+def test_matrix_test_set_multiple_entries_on_the_device():
+    """test/matrix_test_set_multiple_entries.f90 through the C-ABI (CPU twin:
+    tests/test_oracle_strategy.py); default paths only, gated until it has run once."""
+    out = run_snippet(MULTIPLE)
+    assert "multiple entries ok" in out

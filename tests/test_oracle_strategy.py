@@ -57,3 +57,42 @@ def test_matrix_test_strategy(orc, fmt):
         y[i] = z
     w_ = orc.matvec(A, x)
     assert np.sqrt(((y - w_) ** 2).sum() / (x @ x)) <= 1e-14
+
+
+def multiple_entries_stream(nbrs, nn):
+    """The add_multiple_values calls of test/matrix_test_set_multiple_entries.f90:103-114: for
+    every vertex i and every neighbour j > i (in g%get_neighbors order), is = [i, j] and
+    B = [[1, -1], [-1, 1]]."""
+    import sigma_b200 as sb
+
+    pairs = [(i, j) for i in range(1, nn + 1) for j in nbrs[i - 1] if j > i]
+    is_ = np.array(pairs, np.int32).reshape(-1, 2)
+    B = np.broadcast_to(np.array([[1.0, -1.0], [-1.0, 1.0]]), (is_.shape[0], 2, 2))
+    return sb.multiple_values_stream(is_, is_, B)
+
+
+def test_multiple_values_stream_order():
+    import sigma_b200 as sb
+
+    I, J, Z = sb.multiple_values_stream([3, 7], [1, 2, 5], [[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]])
+    assert I.tolist() == [3, 3, 3, 7, 7, 7] and J.tolist() == [1, 2, 5, 1, 2, 5]      # k outer, l inner
+    assert Z.tolist() == [1.0, 2.0, 3.0, 4.0, 5.0, 6.0]
+    I, J, Z = sb.multiple_values_stream([[1, 2], [2, 3]], [[1, 2], [2, 3]], np.arange(8.0).reshape(2, 2, 2))
+    assert I.tolist() == [1, 1, 2, 2, 2, 2, 3, 3] and J.tolist() == [1, 2, 1, 2, 2, 3, 2, 3]
+    assert Z.tolist() == list(np.arange(8.0))
+
+
+@pytest.mark.parametrize("fmt", ["csr", "csc", "ellpack"])
+def test_matrix_test_set_multiple_entries(orc, fmt):
+    """test/matrix_test_set_multiple_entries.f90: the graph Laplacian assembled from 2 x 2 element
+    blocks with add_multiple_values must have degree - 1 on the diagonal, -1 on every edge and
+    nothing else (:120-152, exact comparisons)."""
+    nn = 128
+    A, nbrs, connected = strategy_case(orc, nn, 23, fmt)
+    A.val[...] = 0.0                                        # call A%zero()
+    I, J, Z = multiple_entries_stream(nbrs, nn)
+    assert orc.add_values(A, I, J, Z) == 0
+    for i in range(1, nn + 1):
+        for j in range(1, nn + 1):
+            want = len(nbrs[i - 1]) - 1 if i == j else (-1.0 if connected[i - 1, j - 1] else 0.0)
+            assert orc.get_value(A, i, j) == want
