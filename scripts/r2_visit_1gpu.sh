@@ -17,6 +17,8 @@ for t in test_device_built_tiles_equal_the_host_tiling test_copy_and_transpose_p
   SIGB_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -x -q -k $t > $OUT/exp_$t.log 2>&1
   echo "$t rc=$?" | tee -a $S; tail -3 $OUT/exp_$t.log | tee -a $S
 done
+SIGB_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_cxx_host.py -x -q -k not_yet_run > $OUT/exp_cxx.log 2>&1; echo "cxx not-yet-run programs rc=$?" | tee -a $S
+tail -3 $OUT/exp_cxx.log | tee -a $S
 echo "== 3. bench (default path)" | tee -a $S
 timeout 600 python bench.py --steps 200 --warmup 5 > $OUT/bench.json 2> $OUT/bench.err; echo "rc=$?" | tee -a $S
 cat $OUT/bench.json | tee -a $S

@@ -223,6 +223,23 @@ struct device_matrix : linear_operator {
         sigb_check(sigb_matrix_add_values(mirror, (int64_t)is.size(), is.data(), js.data(), zs.data()));
         sigb_check(sigb_matrix_get_arrays(mirror, nullptr, nullptr, val.data()));
     }
+    // call A%add_multiple_values(is, js, B)   (cs_matrices.f90:934-967, ellpack likewise): the
+    // add_value stream (is(k), js(l), B(k, l)), k outer, l inner; B is given row by row
+    // (B[k * size(js) + l]).  One device call per block; an assembly loop gathers the blocks
+    // of a whole mesh into one add_values batch instead.
+    void add_multiple_values(const std::vector<int32_t> &is, const std::vector<int32_t> &js, const std::vector<dp> &B)
+    {
+        if (B.size() != is.size() * js.size()) {
+            std::printf(" add_multiple_values: B must be size(is) x size(js)\n Terminating.\n");
+            std::exit(1);
+        }
+        std::vector<int32_t> ii, jj;
+        ii.reserve(B.size());
+        jj.reserve(B.size());
+        for (int32_t i : is)
+            for (int32_t j : js) { ii.push_back(i); jj.push_back(j); }
+        add_values(ii, jj, B);
+    }
     void zero() { for (dp &v : val) v = 0.0; dirty = true; }
     void scalar_multiply(dp alpha) { for (dp &v : val) v *= alpha; dirty = true; }
     void upload()
