@@ -134,6 +134,21 @@ struct cs_graph {
             if (node[(size_t)k - 1] == j) return k - 1;
         return -1;
     }
+    // g%add_edge(i, j)   (cs_add_edge :400-442): the new neighbour goes to the END of line i,
+    // everything behind it moves up by one.  Returns the 0-based position it took (-1 if the
+    // edge was there already).  Host-side index work; the device mirrors are dropped.
+    int add_edge(int i, int j)
+    {
+        if (find_edge(i, j) >= 0) return -1;
+        const int indx = ptr[(size_t)i];                       // 1-based ptr(i + 1)
+        node.insert(node.begin() + (indx - 1), (int32_t)j);
+        for (int k = i; k <= n; k++) ptr[(size_t)k] += 1;      // ptr(i+1 .. n+1)
+        ne++;
+        max_d = std::max(max_d, ptr[(size_t)i] - ptr[(size_t)i - 1]);
+        mirror[0].reset();
+        mirror[1].reset();
+        return indx - 1;
+    }
 };
 
 // src/graph/formats/ellpack_graphs.f90: node(max_d, n), padding = last neighbour
@@ -159,6 +174,38 @@ struct ellpack_graph {
             }
         }
         mirror.reset();
+    }
+    bool connected(int i, int j) const
+    {
+        for (int k = 0; k < degrees[(size_t)i - 1]; k++)
+            if (node[(size_t)(i - 1) * max_d + k] == j) return true;
+        return false;
+    }
+    // g%add_edge(i, j)   (ellpack_add_edge :379-413, add_edge_with_reallocation :600-639): fill the
+    // rest of row i with j while there is room, otherwise widen every row by one slot (padding =
+    // copy of the last neighbour).  Returns true when max_d grew.
+    bool add_edge(int i, int j)
+    {
+        if (connected(i, j)) return false;
+        const int k = degrees[(size_t)i - 1];
+        bool widened = false;
+        if (k < max_d) {
+            for (int l = k; l < max_d; l++) node[(size_t)(i - 1) * max_d + l] = j;
+        } else {
+            std::vector<int32_t> wide((size_t)n * (max_d + 1), 0);
+            for (int r = 0; r < n; r++) {
+                for (int l = 0; l < max_d; l++) wide[(size_t)r * (max_d + 1) + l] = node[(size_t)r * max_d + l];
+                if (max_d > 0) wide[(size_t)r * (max_d + 1) + max_d] = node[(size_t)r * max_d + max_d - 1];
+            }
+            wide[(size_t)(i - 1) * (max_d + 1) + max_d] = j;
+            node.swap(wide);
+            max_d += 1;
+            widened = true;
+        }
+        degrees[(size_t)i - 1] = k + 1;
+        ne++;
+        mirror.reset();
+        return widened;
     }
 };
 
@@ -209,6 +256,7 @@ struct device_matrix : linear_operator {
     sigb_matrix_t device_handle() override { sync_mirror(); return mirror; }
     virtual void set_value(int i, int j, dp z) = 0;
     virtual void add_value(int i, int j, dp z) = 0;
+    virtual bool in_pattern(int i, int j) const = 0;
     // A batch of `call A%add_value(is(c), js(c), zs(c))` applied IN ORDER on the device
     // (an assembly loop, examples/fem.f90:43-47; add_multiple_values cs_matrices.f90:934-967);
     // bit-identical to issuing the calls one by one.  The host copy of the values is
@@ -236,9 +284,12 @@ struct device_matrix : linear_operator {
         std::vector<int32_t> ii, jj;
         ii.reserve(B.size());
         jj.reserve(B.size());
+        bool all_in = true;
         for (int32_t i : is)
-            for (int32_t j : js) { ii.push_back(i); jj.push_back(j); }
-        add_values(ii, jj, B);
+            for (int32_t j : js) { ii.push_back(i); jj.push_back(j); all_in = all_in && in_pattern(i, j); }
+        if (all_in) { add_values(ii, jj, B); return; }
+        // an entry outside the pattern makes the graph grow: the reference loop on the host
+        for (size_t c = 0; c < B.size(); c++) add_value(ii[c], jj[c], B[c]);
     }
     void zero() { for (dp &v : val) v = 0.0; dirty = true; }
     void scalar_multiply(dp alpha) { for (dp &v : val) v *= alpha; dirty = true; }
@@ -279,13 +330,27 @@ struct cs_matrix : device_matrix {
         set_graph(gg);
     }
     int slot(int i, int j) const { return COL ? g->find_edge(j, i) : g->find_edge(i, j); }
-    void missing(int i, int j) const
+    // set_matrix_value_with_reallocation (default_sparse_matrix_kernels.f90:176-229) for an entry
+    // outside the pattern: the graph gains the edge (a csc_matrix adds (j, i), cs_matrices.f90:992),
+    // every stored value moves to its new index and the new slot receives z.  Host-side, like the
+    // reference; the device mirrors of the graph and of the matrix are dropped and rebuilt by the
+    // next matvec / solve.  A graph shared with other matrices is cloned first (the reference
+    // mutates the shared object and leaves the other matrices' value arrays behind).
+    void grow(int i, int j, dp z)
     {
-        std::printf(" entry (%d,%d) is not in the sparsity pattern; the reallocation path of set_value is not part of this mirror\n Terminating.\n", i, j);
-        std::exit(1);
+        if (i < 1 || i > nrow || j < 1 || j > ncol) {
+            std::printf(" entry (%d,%d) is outside the %d x %d matrix\n Terminating.\n", i, j, nrow, ncol);
+            std::exit(1);
+        }
+        if (g.use_count() > 1) g = std::make_shared<cs_graph>(*g);
+        const int pos = COL ? g->add_edge(j, i) : g->add_edge(i, j);
+        val.insert(val.begin() + pos, z);
+        if (mirror) { sigb_matrix_destroy(mirror); mirror = nullptr; }
+        dirty = true;
     }
-    void set_value(int i, int j, dp z) override { const int k = slot(i, j); if (k < 0) missing(i, j); val[(size_t)k] = z; dirty = true; }
-    void add_value(int i, int j, dp z) override { const int k = slot(i, j); if (k < 0) missing(i, j); val[(size_t)k] += z; dirty = true; }
+    void set_value(int i, int j, dp z) override { const int k = slot(i, j); if (k < 0) { grow(i, j, z); return; } val[(size_t)k] = z; dirty = true; }
+    void add_value(int i, int j, dp z) override { const int k = slot(i, j); if (k < 0) { grow(i, j, z); return; } val[(size_t)k] += z; dirty = true; }
+    bool in_pattern(int i, int j) const override { return slot(i, j) >= 0; }
     dp get_value(int i, int j) override { const int k = slot(i, j); return k < 0 ? 0.0 : val[(size_t)k]; }
 
     void sync_mirror() override
@@ -361,20 +426,41 @@ struct ellpack_matrix : device_matrix {
             if (g->node[(size_t)(i - 1) * g->max_d + k] == j) found = (i - 1) * g->max_d + k;
         return found;
     }
+    // set_unallocated_matrix_value (ellpack_matrices.f90:801-825): widen val by one zero slot per
+    // row when row i is full, add the edge, val(d + 1, i) = z.  Host-side; mirrors dropped.
+    void grow(int i, int j, dp z)
+    {
+        if (i < 1 || i > nrow || j < 1 || j > ncol) {
+            std::printf(" entry (%d,%d) is outside the %d x %d matrix\n Terminating.\n", i, j, nrow, ncol);
+            std::exit(1);
+        }
+        if (g.use_count() > 1) g = std::make_shared<ellpack_graph>(*g);
+        const int d = g->degrees[(size_t)i - 1], old_w = g->max_d;
+        if (g->add_edge(i, j)) {
+            std::vector<dp> wide((size_t)g->n * g->max_d, 0.0);
+            for (int r = 0; r < g->n; r++)
+                for (int l = 0; l < old_w; l++) wide[(size_t)r * g->max_d + l] = val[(size_t)r * old_w + l];
+            val.swap(wide);
+        }
+        val[(size_t)(i - 1) * g->max_d + d] = z;
+        if (mirror) { sigb_matrix_destroy(mirror); mirror = nullptr; }
+        dirty = true;
+    }
     void set_value(int i, int j, dp z) override
     {
         const int k = slot(i, j);
-        if (k < 0) { std::printf(" entry (%d,%d) is not in the sparsity pattern\n Terminating.\n", i, j); std::exit(1); }
+        if (k < 0) { grow(i, j, z); return; }
         val[(size_t)k] = z;
         dirty = true;
     }
     void add_value(int i, int j, dp z) override
     {
         const int k = slot(i, j);
-        if (k < 0) { std::printf(" entry (%d,%d) is not in the sparsity pattern\n Terminating.\n", i, j); std::exit(1); }
+        if (k < 0) { grow(i, j, z); return; }
         val[(size_t)k] += z;
         dirty = true;
     }
+    bool in_pattern(int i, int j) const override { return slot(i, j) >= 0; }
     dp get_value(int i, int j) override { const int k = slot(i, j); return k < 0 ? 0.0 : val[(size_t)k]; }
 
     void sync_mirror() override

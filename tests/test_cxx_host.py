@@ -16,7 +16,7 @@ PROGS = ["solver_test_diffusion_1d", "solver_test_advection_diffusion_1d", "solv
 
 # written after the last GPU visit of round 1: compiled on every run, executed only with
 # SIGB_TEST_EXPERIMENTAL=1 until they have passed on a GPU once (then move them into PROGS)
-PROGS_NOT_YET_RUN = ["matrix_test_strategy", "matrix_test_set_multiple_entries"]
+PROGS_NOT_YET_RUN = ["matrix_test_strategy", "matrix_test_set_multiple_entries", "matrix_test_set_entry_with_realloc"]
 
 
 def build():
@@ -44,3 +44,14 @@ def test_reference_test_program_not_yet_run(prog):
     build()
     r = subprocess.run([os.path.join(CXX, "_build", prog), "-v"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_set_entry_with_realloc_host_side():
+    """test/matrix_test_set_entry_with_realloc.f90: growing the graph under set_value / add_value /
+    add_multiple_values is host-side work in the reference and in the mirror, so the restated
+    program runs here without a GPU (--host-only skips its final device matvec)."""
+    build()
+    r = subprocess.run([os.path.join(CXX, "_build", "matrix_test_set_entry_with_realloc"), "-v", "--host-only"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("setting unallocated entries works") == 3
