@@ -16,6 +16,12 @@ for v in "" 1; do
   SIGB_LIB_VARIANT=_timers SIGB_CG_SINGLE_REDUCE=$v run8 bench.py --gpus 8 --steps 200 --warmup 5 --quick > $OUT/phases_single$v.json 2> $OUT/phases_single$v.err
   grep phase_us $OUT/phases_single$v.err | tee -a $S
 done
+echo "== N=2 and N=4 (kernel-per-phase path): separate all-reduce launches vs fused into their producers" | tee -a $S
+SIGB_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_experimental.py -x -q -k fused_allreduce > $OUT/exp_fused.log 2>&1; echo "parity rc=$?" | tee -a $S
+for n in 2 4; do for f in 0 1; do
+  SIGB_FUSED_ALLREDUCE=$f timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 \
+    bench.py --gpus $n --steps 200 --warmup 5 --quick 2>> $OUT/fused.err | sed "s/^{/{\"fused_allreduce\": $f, /" | tee -a $OUT/fused.jsonl | tee -a $S
+done; done
 echo "== sharded parity at world 8 (both transports)" | tee -a $S
 timeout 600 python -m pytest tests/test_gpu_dist.py -x -q -k "8" > $OUT/pytest_dist8.log 2>&1; echo "rc=$?" | tee -a $S
 tail -3 $OUT/pytest_dist8.log | tee -a $S

@@ -243,6 +243,26 @@ static int allreduce_ptrs(sigb_comm_t C, double *const *vals, int count, const i
     return SIGB_OK;
 }
 
+// EXPERIMENTAL (SIGB_FUSED_ALLREDUCE=1, peer-memory transport only): endpoints for kernels that
+// finish their own reduction across the GPUs; false = use dist_allreduce after the kernel.
+bool dist_red_fuse(sigb_matrix_t A, RedFuse *rf)
+{
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("SIGB_FUSED_ALLREDUCE");
+        on = (e && atoi(e) == 1) ? 1 : 0;
+    }
+    *rf = RedFuse();
+    DistInfo *D = A->dist;
+    if (!on || !D || D->comm->nranks == 1 || !D->comm->p2p) return false;
+    sigb_comm_t C = D->comm;
+    rf->win = C->red;
+    for (int q = 0; q < kMaxRanks; q++) rf->peer[q] = C->peer_red[q];
+    rf->me = C->rank;
+    rf->nranks = C->nranks;
+    return true;
+}
+
 int dist_allreduce(sigb_matrix_t A, double *vals, int count, const int *skip_flag)
 {
     DistInfo *D = A->dist;

@@ -158,7 +158,7 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[ND], double *partials,
 template <int ND>
 __device__ __forceinline__ void grid_reduce(double (&acc)[ND], double *partials,
                                             unsigned *ticket, double *const (&out)[ND],
-                                            const double *const (&addend)[ND])
+                                            const double *const (&addend)[ND], const RedFuse *red = nullptr)
 {
     __shared__ double sm[ND][kThreads / 32];
     __shared__ bool is_last;
@@ -184,9 +184,49 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[ND], double *partials,
         block_tree<ND>(v, sm);
         if (threadIdx.x == 0) {
 #pragma unroll
-            for (int d = 0; d < ND; d++)
-                *out[d] = addend[d] ? add(__ldcg(addend[d]), v[d]) : v[d];
+            for (int d = 0; d < ND; d++) {
+                v[d] = addend[d] ? add(__ldcg(addend[d]), v[d]) : v[d];
+                *out[d] = v[d];
+            }
             *ticket = 0u;
+        }
+        // EXPERIMENTAL (SIGB_FUSED_ALLREDUCE=1): the cross-GPU part, by warp 0 of this last CTA --
+        // what red_kernel (comm.cu) does in a launch of its own: lane q stores this rank's sums
+        // into rank q's inbox as payload+flag words, lane d adds the nranks contributions to
+        // value d in rank order (bit-identical totals on every rank) and overwrites *out[d].
+        if (red != nullptr && red->nranks > 1 && threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            const unsigned long long seq = red->win->red_seq + 1;
+            const int slot = (int)(seq & (kRedSlots - 1));
+            const unsigned int flag = (unsigned int)seq;
+#pragma unroll
+            for (int d = 0; d < ND; d++) {
+                const double local = __shfl_sync(0xffffffffu, v[d], 0);
+                if (lane < red->nranks) {
+                    RedEntry *e = red->peer[lane]->red[slot][red->me];
+                    const unsigned long long bits = (unsigned long long)__double_as_longlong(local);
+                    st_word(&e[d].lo, (unsigned int)bits, flag);
+                    st_word(&e[d].hi, (unsigned int)(bits >> 32), flag);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int d = 0; d < ND; d++) {
+                if (lane == d) {
+                    double g = 0.0;
+                    for (int q = 0; q < red->nranks; q++) {
+                        const RedEntry *e = &red->win->red[slot][q][d];
+                        uint2 lo, hi;
+                        unsigned spins = 0;
+                        do { lo = ld_word(&e->lo); } while (lo.y != flag && ++spins < kSpinLimit);
+                        do { hi = ld_word(&e->hi); } while (hi.y != flag && ++spins < kSpinLimit);
+                        g = add(g, __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | lo.x)));
+                    }
+                    *out[d] = g;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) red->win->red_seq = seq;
         }
     }
 }
@@ -200,6 +240,17 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[ND], double *partials,
     for (int d = 0; d < ND; d++) addend[d] = nullptr;
     const double *const(&ref)[ND] = addend;
     grid_reduce<ND>(acc, partials, ticket, out, ref);
+}
+
+template <int ND>
+__device__ __forceinline__ void grid_reduce(double (&acc)[ND], double *partials,
+                                            unsigned *ticket, double *const (&out)[ND], const RedFuse *red)
+{
+    const double *addend[ND];
+#pragma unroll
+    for (int d = 0; d < ND; d++) addend[d] = nullptr;
+    const double *const(&ref)[ND] = addend;
+    grid_reduce<ND>(acc, partials, ticket, out, ref, red);
 }
 
 // Persistent grid = resident CTAs per SM x SMs, queried once per kernel.  The

@@ -186,6 +186,9 @@ struct DotSpec {
     // expression has already written), so rows without entries -- y(i) + 0.0 in
     // csr_matvec_add -- may be left untouched and tiles without entries skipped
     bool y_no_negative_zero = false;
+    // EXPERIMENTAL (SIGB_FUSED_ALLREDUCE=1): complete the cross-GPU part of the dot products
+    // inside this kernel (its last CTA) instead of a separate all-reduce launch
+    const struct RedFuse *red = nullptr;
 };
 
 // Peer-memory halo exchange, fused into the SpMV kernel (comm.cu builds it).
@@ -195,6 +198,14 @@ struct DotSpec {
 // reaches its first boundary tile; the last CTA acknowledges consumption.
 constexpr int kMaxRanks = 8;
 struct HaloWin;  // device-resident, IPC-shared (device_utils.cuh)
+struct RedWin;   // all-reduce inbox, IPC-shared (device_utils.cuh)
+// All-reduce endpoints handed to a kernel that finishes its own reduction across the GPUs
+// (device_utils.cuh grid_reduce): nranks <= 1 means "local sums only".
+struct RedFuse {
+    RedWin *win = nullptr;                // this rank's inbox
+    RedWin *peer[kMaxRanks] = {};         // every rank's inbox, peer-mapped (peer[me] == win)
+    int me = 0, nranks = 1;
+};
 struct HaloSync {
     HaloWin *win = nullptr;               // this rank's window
     HaloWin *peer[kMaxRanks] = {};        // the peers' windows (peer-mapped)

@@ -342,6 +342,7 @@ static void fill_args(const CsrView &A, const double *val, const double *x, doub
     a.nloc = dot.nloc;
     a.h1 = dot.halo ? dot.halo - (dot.nloc + 1) : nullptr;
     if (dot.sync) a.sync = *dot.sync;
+    if (dot.red) a.red = *dot.red;
     a.first_halo_tile = (which == 0 && dot.sync) ? A.n_interior : 0;
 }
 

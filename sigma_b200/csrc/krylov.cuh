@@ -109,6 +109,57 @@ int launch_ew(const Op &op, int64_t n, cudaStream_t st = nullptr)
     return SIGB_OK;
 }
 
+// EXPERIMENTAL (SIGB_FUSED_ALLREDUCE=1): the same kernel with the Op's dot products all-reduced
+// across the GPUs by its last CTA (device_utils.cuh grid_reduce) instead of a separate launch.
+// A twin rather than a parameter of ew_kernel, so that the product kernels keep their code.
+template <class Op>
+__global__ void __launch_bounds__(kThreads)
+ew_fused_kernel(Op op, int64_t n, double *partials, unsigned *ticket, const RedFuse red)
+{
+    if (!op.begin()) return;
+    constexpr int ND = Op::ND;
+    static_assert(ND == 1 || ND == 2, "fused all-reduce needs an Op that produces dot products");
+    constexpr int NIN = Op::NIN > 0 ? Op::NIN : 1;
+    double acc[ND];
+#pragma unroll
+    for (int d = 0; d < ND; d++) acc[d] = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t base = blockIdx.x * (int64_t)kThreads + threadIdx.x; base < n;
+         base += stride * kUnroll) {
+        double in[kUnroll][NIN];
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const int64_t i = base + u * stride;
+            if (i < n) op.load(i, in[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const int64_t i = base + u * stride;
+            if (i < n) op.compute(i, in[u], acc);
+        }
+    }
+    if constexpr (ND == 1) {
+        double *const out[1] = {op.out(0)};
+        grid_reduce<1>(acc, partials, ticket, out, &red);
+    } else {
+        double *const out[2] = {op.out(0), op.out(1)};
+        grid_reduce<2>(acc, partials, ticket, out, &red);
+    }
+}
+
+template <class Op>
+int launch_ew_fused(const Op &op, int64_t n, const RedFuse &red)
+{
+    int grid = 0;
+    SIGB_CHECK((occupancy_grid<ew_fused_kernel<Op>>(0, &grid)));
+    const int need = ew_grid(n);
+    if (need < grid) grid = need;
+    ew_fused_kernel<Op><<<grid, kThreads, 0, ctx().stream>>>(op, n, ctx().partials, ctx().tickets, red);
+    count_launch();
+    SIGB_CUDA(cudaGetLastError());
+    return SIGB_OK;
+}
+
 __device__ __forceinline__ bool first_thread() { return blockIdx.x == 0 && threadIdx.x == 0; }
 
 }  // namespace sigb

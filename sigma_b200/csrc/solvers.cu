@@ -849,6 +849,8 @@ static int cg_solve_body(sigb_solver_t s, sigb_matrix_t A, double *x, const doub
 
     const int nb = batch_size(n);
     int par = 0;
+    RedFuse rf;
+    const bool fused = dist_red_fuse(A, &rf);   // EXPERIMENTAL: the two all-reduces inside their producers
     for (;;) {
         for (int it = 0; it < nb; it++) {
             DotSpec d;
@@ -856,11 +858,13 @@ static int cg_solve_body(sigb_solver_t s, sigb_matrix_t A, double *x, const doub
             d.u = p;
             d.out[0] = &st->pq;
             d.skip_flag = &st->done[par];
+            if (fused) d.red = &rf;
             SIGB_CHECK(solver_matvec(A, p, q, d, /*x_has_halo=*/true));   // q = A p ; dpr = p.q
-            SIGB_CHECK(dist_allreduce(A, &st->pq, 1, &st->done[par]));
+            if (!fused) SIGB_CHECK(dist_allreduce(A, &st->pq, 1, &st->done[par]));
             CgUpdateOp up{q, idiag, r, z, st, par, 0.0};
-            SIGB_CHECK(launch_ew(up, n));
-            SIGB_CHECK(dist_allreduce(A, &st->rr[par ^ 1], 1, &st->done[par]));
+            if (fused) SIGB_CHECK(launch_ew_fused(up, n, rf));
+            else SIGB_CHECK(launch_ew(up, n));
+            if (!fused) SIGB_CHECK(dist_allreduce(A, &st->rr[par ^ 1], 1, &st->done[par]));
             CgDirectionOp dir{idiag ? z : r, p, x, st, par, 0.0, 0.0};
             SIGB_CHECK(launch_ew(dir, n));
             par ^= 1;

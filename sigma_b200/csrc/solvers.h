@@ -86,6 +86,7 @@ int solver_matvec(sigb_matrix_t A, const double *x, double *y, const DotSpec &do
 // Sum `count` contiguous device doubles over all ranks (no-op on one GPU).
 // skip_flag: device int; when non-zero at execution time the reduction is a
 // no-op (iterations launched past the stopping test), on every rank alike.
+bool dist_red_fuse(sigb_matrix_t A, RedFuse *rf);   // EXPERIMENTAL, see comm.cu
 int dist_allreduce(sigb_matrix_t A, double *vals, int count, const int *skip_flag = nullptr);
 int dist_allreduce2(sigb_matrix_t A, double *a, double *b, const int *skip_flag = nullptr);
 // extra elements a work vector needs behind its owned part (0 on one GPU)

@@ -28,6 +28,7 @@ struct CsrKernelArgs {
     const double *add0, *add1;  // optional addends folded into the dot totals
     HaloSync sync;            // peer-memory transport (sync.win == nullptr: none)
     int32_t first_halo_tile;  // tiles from this index on read halo columns
+    RedFuse red;              // EXPERIMENTAL: finish the dots across the GPUs in this kernel (nranks <= 1: no)
 #ifdef SIGB_PHASE_TIMERS
     // diagnostic build: SM cycles of thread 0 of every CTA, summed over the grid:
     // [0] waiting for the staged tile, [1] products (gathers), [2] row sums, [3] the whole pass,
@@ -163,12 +164,12 @@ __device__ __forceinline__ void finish_dots(const CsrKernelArgs &a, double *acc)
         double *const out[1] = {a.out0};
         const double *const addend[1] = {a.add0};
         double v[1] = {acc[0]};
-        grid_reduce<1>(v, a.partials, a.ticket, out, addend);
+        grid_reduce<1>(v, a.partials, a.ticket, out, addend, &a.red);
     } else if (NDOT == 2) {
         double *const out[2] = {a.out0, a.out1};
         const double *const addend[2] = {a.add0, a.add1};
         double v[2] = {acc[0], acc[NDOT > 1 ? 1 : 0]};
-        grid_reduce<2>(v, a.partials, a.ticket, out, addend);
+        grid_reduce<2>(v, a.partials, a.ticket, out, addend, &a.red);
     }
 }
 

@@ -15,6 +15,10 @@ subprocess; the whole file is skipped unless SIGB_TEST_EXPERIMENTAL=1.
                             each, rows waiting for the entries they read instead of one launch
                             per level (csrc/ldu.cu).  Same arithmetic per row: the ILDU parity
                             tests (bit-exact factors and solves) must stay green with it on.
+  SIGB_FUSED_ALLREDUCE=1    row-sharded CG, kernel-per-phase path: the two all-reduces of an iteration are
+                            finished by the last CTA of the kernels that produce the local sums
+                            (csrc/device_utils.cuh grid_reduce) instead of separate one-warp launches.
+                            Same values added in the same rank order: results must be identical.
   SIGB_ASYNC_ALLOC=1        temporaries of transposes / copies / assembly from the stream-ordered pool
                             (cudaMallocAsync / cudaFreeAsync) instead of cudaMalloc / cudaFree.
   SIGB_SPMV_ROWDIRECT=1     row-direct form of the streaming CSR kernel for every matrix (csrc/
@@ -280,3 +284,16 @@ def test_matrix_test_set_multiple_entries_on_the_device():
     tests/test_oracle_strategy.py); default paths only, gated until it has run once."""
     out = run_snippet(MULTIPLE)
     assert "multiple entries ok" in out
+
+
+def test_sharded_parity_with_fused_allreduce():
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    e = dict(os.environ)
+    e["SIGB_FUSED_ALLREDUCE"] = "1"
+    e["SIGB_CG_PERSISTENT"] = "0"          # the kernel-per-phase path is where the fusion applies
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_dist.py", "-k", "p2p"],
+                       cwd=ROOT, env=e, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
