@@ -1018,6 +1018,8 @@ int bicgstab_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x, const double
 
     const int nb = batch_size(n);
     int par = 0;
+    RedFuse rf;
+    const bool fused = dist_red_fuse(A, &rf);   // EXPERIMENTAL: the three all-reduces inside their producers
     for (;;) {
         for (int it = 0; it < nb; it++) {
             DotSpec d1;                      // v = [M] A p ; r0.v
@@ -1026,8 +1028,9 @@ int bicgstab_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x, const double
             d1.out[0] = &st->pq;
             d1.skip_flag = &st->done[par];
             d1.row_scale = idiag;
+            if (fused) d1.red = &rf;
             SIGB_CHECK(solver_matvec(A, p, v, d1, true));
-            SIGB_CHECK(dist_allreduce(A, &st->pq, 1, &st->done[par]));
+            if (!fused) SIGB_CHECK(dist_allreduce(A, &st->pq, 1, &st->done[par]));
             BicgSOp sop{r, v, sv, st, par, 0.0};
             SIGB_CHECK(launch_ew(sop, n));
             DotSpec d2;                      // t = [M] A s ; s.t, t.t
@@ -1037,11 +1040,13 @@ int bicgstab_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x, const double
             d2.out[1] = &st->tt;
             d2.skip_flag = &st->done[par];
             d2.row_scale = idiag;
+            if (fused) d2.red = &rf;
             SIGB_CHECK(solver_matvec(A, sv, t, d2, true));
-            SIGB_CHECK(dist_allreduce(A, &st->st, 2, &st->done[par]));
+            if (!fused) SIGB_CHECK(dist_allreduce(A, &st->st, 2, &st->done[par]));
             BicgUpdateOp up{p, sv, t, r0, x, r, st, par, pc ? 0 : 1, 0.0, 0.0};
-            SIGB_CHECK(launch_ew(up, n));
-            SIGB_CHECK(dist_allreduce2(A, &st->rr[par ^ 1], &st->rho[par ^ 1], &st->done[par]));
+            if (fused) SIGB_CHECK(launch_ew_fused(up, n, rf));
+            else SIGB_CHECK(launch_ew(up, n));
+            if (!fused) SIGB_CHECK(dist_allreduce2(A, &st->rr[par ^ 1], &st->rho[par ^ 1], &st->done[par]));
             BicgDirectionOp dir{r, v, p, st, par ^ 1, 0, 0.0, 0.0};
             SIGB_CHECK(launch_ew(dir, n));
             par ^= 1;
