@@ -11,6 +11,13 @@ cat $OUT/bench_n8.json | tee -a $S
 echo "== N=8 single reduction (opt-in; parity bars of tests/test_gpu_experimental.py must be green first)" | tee -a $S
 SIGB_CG_SINGLE_REDUCE=1 run8 bench.py --gpus 8 --steps 200 --warmup 5 > $OUT/bench_n8_single.json 2> $OUT/bench_n8_single.err; echo "rc=$?" | tee -a $S
 cat $OUT/bench_n8_single.json | tee -a $S
+echo "== N=8 with the halo push moved to the last CTAs (SIGB_PUSH_LAST=1), default and single reduction" | tee -a $S
+for v in "" 1; do
+  SIGB_PUSH_LAST=1 SIGB_CG_SINGLE_REDUCE=$v run8 bench.py --gpus 8 --steps 200 --warmup 5 --quick 2>> $OUT/pushlast.err | sed "s/^{/{\"push_last\": 1, \"single_reduce\": \"$v\", /" | tee -a $OUT/pushlast.jsonl | tee -a $S
+done
+echo "== N=8 row-direct SpMV inside the persistent kernel, alone and with everything else" | tee -a $S
+SIGB_SPMV_ROWDIRECT=1 run8 bench.py --gpus 8 --steps 200 --warmup 5 --quick 2>> $OUT/rd8.err | sed "s/^{/{\"rowdirect\": 1, /" | tee -a $OUT/rd8.jsonl | tee -a $S
+SIGB_SPMV_ROWDIRECT=1 SIGB_PUSH_LAST=1 SIGB_CG_SINGLE_REDUCE=1 run8 bench.py --gpus 8 --steps 200 --warmup 5 --quick 2>> $OUT/rd8.err | sed "s/^{/{\"rowdirect\": 1, \"push_last\": 1, \"single_reduce\": 1, /" | tee -a $OUT/rd8.jsonl | tee -a $S
 echo "== phase breakdown (diagnostic build; its timings are not bench values)" | tee -a $S
 for v in "" 1; do
   SIGB_LIB_VARIANT=_timers SIGB_CG_SINGLE_REDUCE=$v run8 bench.py --gpus 8 --steps 200 --warmup 5 --quick > $OUT/phases_single$v.json 2> $OUT/phases_single$v.err

@@ -545,6 +545,7 @@ int launch_single_reduce(const CgPersistArgs &a, cudaStream_t st)
     if (HALO && b.A.sync.win != nullptr) {
         int pc = (b.A.sync.total_send + 2 * kThreads - 1) / (2 * kThreads);
         b.A.sync.push_ctas = b.A.sync.total_send > 0 ? std::max(1, std::min(pc, grid)) : 0;
+        b.A.sync.push_first = halo_push_first(grid, b.A.sync.push_ctas);
     }
     void *params[] = {(void *)&b};
     SIGB_CUDA(cudaLaunchCooperativeKernel((const void *)cg_single_reduce_kernel<HALO>, dim3(grid), dim3(kThreads),
@@ -564,6 +565,7 @@ int launch_persistent(const CgPersistArgs &a, cudaStream_t st)
     if (HALO && b.A.sync.win != nullptr) {
         int pc = (b.A.sync.total_send + 2 * kThreads - 1) / (2 * kThreads);
         b.A.sync.push_ctas = b.A.sync.total_send > 0 ? std::max(1, std::min(pc, grid)) : 0;
+        b.A.sync.push_first = halo_push_first(grid, b.A.sync.push_ctas);
     }
     void *params[] = {(void *)&b};
     SIGB_CUDA(cudaLaunchCooperativeKernel((const void *)cg_persistent_kernel<HALO, PC, RD>, dim3(grid), dim3(kThreads),

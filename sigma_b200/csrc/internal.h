@@ -218,6 +218,7 @@ struct HaloSync {
     const int32_t *send_rows = nullptr;   // 1-based owned rows, grouped by destination
     int32_t total_send = 0;
     int32_t push_ctas = 0;
+    int32_t push_first = 0;               // first pushing CTA (experiment knob SIGB_PUSH_LAST: grid - push_ctas)
     int32_t send_off[kMaxRanks + 1] = {};
     double *dst[kMaxRanks] = {};          // peer landing buffer 0, offset to our slice
     int64_t dst_stride[kMaxRanks] = {};
@@ -232,6 +233,11 @@ int launch_ell_spmv(int32_t n, int32_t n_pad, int32_t max_d,
                     const double *x, double *y, SpmvMode mode,
                     const DotSpec &dot);
 int build_tiles_host(const int32_t *ptr1, int32_t nrows, std::vector<TileDesc> &tiles);
+// Experiment knob SIGB_PUSH_LAST=1: the halo push is done by the LAST CTAs of the grid -- with
+// round-robin tiles they own one tile less than the first ones whenever the tile count is not a
+// multiple of the grid, which pays for the system-scope fence behind their push -- instead of the
+// first ones (the very last CTA is left out: it publishes the persistent kernel's reductions).  Returns the first pushing CTA for a grid / number of pushing CTAs.
+int32_t halo_push_first(int grid, int push_ctas);
 // EXPERIMENTAL (SIGB_SPMV_ROWDIRECT): whether the row-direct form of the streaming kernel is used for A
 bool spmv_rowdirect(const CsrView &A);
 // tiles_device.cu -- EXPERIMENTAL (SIGB_DEVICE_TILES=1): the same tiling built on the device

@@ -207,6 +207,7 @@ int launch_csr_rd(const CsrKernelArgs &a, cudaStream_t st)
         CsrKernelArgs b = a;
         int pc = (a.sync.total_send + 2 * kThreads - 1) / (2 * kThreads);   // ~2 entries per thread
         b.sync.push_ctas = a.sync.total_send > 0 ? std::max(1, std::min(pc, grid)) : 0;
+        b.sync.push_first = halo_push_first(grid, b.sync.push_ctas);
         csr_tma_kernel<MODE, NDOT, HALO, RD><<<grid, kThreads, smem, st>>>(b);
     } else {
         csr_tma_kernel<MODE, NDOT, HALO, RD><<<grid, kThreads, smem, st>>>(a);
@@ -253,6 +254,17 @@ int launch_ell_w(const EllKernelArgs &a, cudaStream_t st)
 }
 
 }  // namespace
+
+int32_t halo_push_first(int grid, int push_ctas)
+{
+    static int last = -1;
+    if (last < 0) {
+        const char *e = getenv("SIGB_PUSH_LAST");
+        last = (e && atoi(e) == 1) ? 1 : 0;
+    }
+    // ... except the very last CTA, which publishes the reductions of the persistent CG kernel
+    return last ? std::max(0, grid - 1 - push_ctas) : 0;
+}
 
 // EXPERIMENTAL row-direct form of the streaming kernel (spmv_device.cuh).  SIGB_SPMV_ROWDIRECT:
 // unset / 0 = never (the measured round-1 kernel), 1 = every matrix (parity runs), 2 = matrices

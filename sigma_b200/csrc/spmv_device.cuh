@@ -209,7 +209,8 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
     bool halo_ready = !(HALO && a.sync.win != nullptr);
     bool push_pending = false;
     if (HALO && a.sync.win != nullptr) {
-        if ((int)blockIdx.x < a.sync.push_ctas) {
+        const int push_rank = (int)blockIdx.x - a.sync.push_first;   // position among the pushing CTAs
+        if (push_rank >= 0 && push_rank < a.sync.push_ctas) {
             const int buf = (int)(hseq & 1);
             // landing buffer `buf` was last filled for SpMV hseq-2: wait until
             // every consumer has acknowledged reading it
@@ -220,7 +221,7 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
                         while (ld_acquire_sys(&a.sync.win->ack[q]) < hseq - 2 && ++spins < kSpinLimit) {}
                     }
             __syncthreads();
-            for (int k = blockIdx.x * kThreads + tid; k < a.sync.total_send; k += a.sync.push_ctas * kThreads) {
+            for (int k = push_rank * kThreads + tid; k < a.sync.total_send; k += a.sync.push_ctas * kThreads) {
                 int q = 0;
                 while (k >= a.sync.send_off[q + 1]) q++;
                 a.sync.dst[q][buf * a.sync.dst_stride[q] + (k - a.sync.send_off[q])] =

@@ -293,7 +293,20 @@ def test_sharded_parity_with_fused_allreduce():
         pytest.skip("needs 2 GPUs")
     e = dict(os.environ)
     e["SIGB_FUSED_ALLREDUCE"] = "1"
+    e["SIGB_PUSH_LAST"] = "1"              # experiment knob: halo push by the last CTAs of the grid
     e["SIGB_CG_PERSISTENT"] = "0"          # the kernel-per-phase path is where the fusion applies
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_dist.py", "-k", "p2p"],
+                       cwd=ROOT, env=e, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_sharded_parity_with_push_by_the_last_ctas():
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    e = dict(os.environ)
+    e["SIGB_PUSH_LAST"] = "1"
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_dist.py", "-k", "p2p"],
                        cwd=ROOT, env=e, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
