@@ -100,7 +100,8 @@ DEVICE_TILES = """
     import numpy as np
     import sigma_b200 as sb
     from sigma_b200._capi import check, lib, ptr
-    import tests.test_row_tiles as T
+    import sys; sys.path.insert(0, "tests")      # (a foreign top-level package named tests may be installed)
+    import test_row_tiles as T
     sb.init(0)
     for name, p in T.cases():
         p = np.ascontiguousarray(p, np.int32)
@@ -208,7 +209,8 @@ STRATEGY = """
     import numpy as np
     import oracle as orc
     import sigma_b200 as sb
-    import tests.test_oracle_strategy as S
+    import sys; sys.path.insert(0, "tests")
+    import test_oracle_strategy as S
     orc.build(); sb.init(0)
     nn = 256
     for fmt in ("csr", "csc", "ellpack"):
@@ -250,7 +252,8 @@ MULTIPLE = """
     import numpy as np
     import oracle as orc
     import sigma_b200 as sb
-    import tests.test_oracle_strategy as S
+    import sys; sys.path.insert(0, "tests")
+    import test_oracle_strategy as S
     orc.build(); sb.init(0)
     nn = 128
     for fmt in ("csr", "csc", "ellpack"):
