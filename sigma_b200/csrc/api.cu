@@ -46,8 +46,7 @@ static bool async_alloc_enabled()
 {
     static int v = -1;
     if (v < 0) {
-        const char *e = getenv("SIGB_ASYNC_ALLOC");
-        v = (e && atoi(e) == 1) ? 1 : 0;
+        v = env_int("SIGB_ASYNC_ALLOC", 0) == 1 ? 1 : 0;
         if (v) {
             // keep freed blocks in the pool instead of returning them at every synchronisation
             cudaMemPool_t pool = nullptr;
@@ -711,11 +710,7 @@ int sigb_solver_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x_dev, const
                  s->nn, A->nrow);
     if (pc) {
         // EXPERIMENTAL opt-in: bicgstab with the ldu preconditioner (solvers.cu), not yet run on a GPU
-        static int bicg_ldu = -1;
-        if (bicg_ldu < 0) {
-            const char *e = getenv("SIGB_BICGSTAB_LDU");
-            bicg_ldu = (e && atoi(e) == 1) ? 1 : 0;
-        }
+        static const bool bicg_ldu = env_int("SIGB_BICGSTAB_LDU", 0) == 1;
         const bool ldu_ok = pc->kind == S_LDU && !A->dist && (s->kind == S_CG || (s->kind == S_BICGSTAB && bicg_ldu));
         SIGB_REQUIRE(pc->kind == S_JACOBI || ldu_ok, SIGB_ERR_UNSUPPORTED,
                      "sigb_solver_solve: the device preconditioners are jacobi (cg, bicgstab) and ldu (cg, one GPU)");

@@ -524,12 +524,7 @@ cg_single_reduce_kernel(const CgPersistArgs a)
 // CTAs make the grid barriers and the partial-sum passes cheaper and the SpMV phase slower.
 static int cap_persistent_grid(int grid)
 {
-    static int per_sm = -1;
-    if (per_sm < 0) {
-        const char *e = getenv("SIGB_CG_PERSIST_CTAS_PER_SM");
-        per_sm = e ? atoi(e) : 0;
-        if (per_sm < 0) per_sm = 0;
-    }
+    static const int per_sm = env_int("SIGB_CG_PERSIST_CTAS_PER_SM", 0);
     if (per_sm > 0 && per_sm * ctx().num_sms < grid) grid = per_sm * ctx().num_sms;
     return grid;
 }

@@ -247,11 +247,7 @@ static int allreduce_ptrs(sigb_comm_t C, double *const *vals, int count, const i
 // finish their own reduction across the GPUs; false = use dist_allreduce after the kernel.
 bool dist_red_fuse(sigb_matrix_t A, RedFuse *rf)
 {
-    static int on = -1;
-    if (on < 0) {
-        const char *e = getenv("SIGB_FUSED_ALLREDUCE");
-        on = (e && atoi(e) == 1) ? 1 : 0;
-    }
+    static const bool on = env_int("SIGB_FUSED_ALLREDUCE", 0) == 1;
     *rf = RedFuse();
     DistInfo *D = A->dist;
     if (!on || !D || D->comm->nranks == 1 || !D->comm->p2p) return false;

@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -65,6 +66,14 @@ constexpr int kMaxDots = 4;
 constexpr int kNumTickets = 8;
 
 inline void count_launch(int n = 1) { ctx().launches += n; }
+
+// Integer environment switch (opt-in paths and experiment knobs); callers keep the result in a
+// function-local static, so each switch is read once per process.
+inline int env_int(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
 
 // ---------------------------------------------------------------------------
 // device-side sparse structures

@@ -257,11 +257,7 @@ int launch_ell_w(const EllKernelArgs &a, cudaStream_t st)
 
 int32_t halo_push_first(int grid, int push_ctas)
 {
-    static int last = -1;
-    if (last < 0) {
-        const char *e = getenv("SIGB_PUSH_LAST");
-        last = (e && atoi(e) == 1) ? 1 : 0;
-    }
+    static const bool last = env_int("SIGB_PUSH_LAST", 0) == 1;
     // ... except the very last CTA, which publishes the reductions of the persistent CG kernel
     return last ? std::max(0, grid - 1 - push_ctas) : 0;
 }
@@ -271,12 +267,7 @@ int32_t halo_push_first(int grid, int push_ctas)
 // with at most 8 stored entries per row on average.
 bool spmv_rowdirect(const CsrView &A)
 {
-    static int mode = -1;
-    if (mode < 0) {
-        const char *e = getenv("SIGB_SPMV_ROWDIRECT");
-        mode = e ? atoi(e) : 0;
-        if (mode < 0 || mode > 2) mode = 0;
-    }
+    static const int mode = env_int("SIGB_SPMV_ROWDIRECT", 0);
     if (mode == 1) return true;
     if (mode == 2) return A.nrows > 0 && A.nnz <= 8 * (int64_t)A.nrows;
     return false;

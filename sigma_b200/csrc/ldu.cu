@@ -320,11 +320,10 @@ const SyncFreeCfg &syncfree_cfg()
     static SyncFreeCfg c;
     static bool read = false;
     if (!read) {
-        const char *e = getenv("SIGB_LDU_SYNCFREE");
-        c.on = e && atoi(e) == 1;
-        if ((e = getenv("SIGB_LDU_SF_CTAS_PER_SM")) && atoi(e) > 0) c.ctas_per_sm = atoi(e);
-        if ((e = getenv("SIGB_LDU_SF_CTAS")) && atoi(e) > 0) c.ctas = atoi(e);
-        if ((e = getenv("SIGB_LDU_SF_SLEEP_NS")) && atoi(e) >= 0) c.sleep_ns = (unsigned)atoi(e);
+        c.on = env_int("SIGB_LDU_SYNCFREE", 0) == 1;
+        c.ctas_per_sm = std::max(1, env_int("SIGB_LDU_SF_CTAS_PER_SM", c.ctas_per_sm));
+        c.ctas = std::max(0, env_int("SIGB_LDU_SF_CTAS", 0));
+        c.sleep_ns = (unsigned)std::max(0, env_int("SIGB_LDU_SF_SLEEP_NS", 0));
         read = true;
     }
     return c;

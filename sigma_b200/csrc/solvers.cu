@@ -830,11 +830,7 @@ static int cg_solve_body(sigb_solver_t s, sigb_matrix_t A, double *x, const doub
                 SIGB_CUDA(cudaMalloc((void **)&s->pers_partials, sizeof(double) * 4 * kMaxGrid));
             }
             // EXPERIMENTAL opt-in: one reduction per iteration (cg_persistent.cu); unpreconditioned only
-            static int single = -1;
-            if (single < 0) {
-                const char *e = getenv("SIGB_CG_SINGLE_REDUCE");
-                single = (e && atoi(e) == 1) ? 1 : 0;
-            }
+            static const bool single = env_int("SIGB_CG_SINGLE_REDUCE", 0) == 1;
             for (;;) {
                 if (single && !idiag)
                     SIGB_CHECK(cg_single_reduce_run(s, *V, val, halo, x, p, q, r, z, n, pcomm, 4096));

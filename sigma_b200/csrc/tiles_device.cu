@@ -115,12 +115,8 @@ tile_emit_kernel(const int32_t *__restrict__ mark, const int32_t *__restrict__ n
 
 bool device_tiles_enabled()
 {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("SIGB_DEVICE_TILES");
-        v = (e && atoi(e) == 1) ? 1 : 0;
-    }
-    return v != 0;
+    static const bool on = env_int("SIGB_DEVICE_TILES", 0) == 1;
+    return on;
 }
 
 // Tile table (+ its sub-table of tiles with entries) of a pattern whose ptr lives on the
