@@ -201,10 +201,9 @@ int dist_persist_info(sigb_matrix_t A, PersistComm *pc, DotSpec *halo, bool *eli
     return SIGB_OK;
 }
 
-int dist_destroy(sigb_matrix_t A)
+static void free_dist(DistInfo *D)
 {
-    DistInfo *D = A->dist;
-    if (!D) return SIGB_OK;
+    if (!D) return;
     cudaDeviceSynchronize();
     if (D->win) {
         for (int q = 0; q < D->comm->nranks; q++)
@@ -216,6 +215,11 @@ int dist_destroy(sigb_matrix_t A)
     cudaFree(D->halo);
     cudaFree(D->dot_tmp);
     delete D;
+}
+
+int dist_destroy(sigb_matrix_t A)
+{
+    free_dist(A->dist);
     A->dist = nullptr;
     return SIGB_OK;
 }
@@ -432,6 +436,12 @@ int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global, const int32_t *part
     SIGB_REQUIRE(ne == 0 || node_glob1, SIGB_ERR_ARG, "sigb_dist_csr_create: null node array");
 
     DistInfo *D = new DistInfo();
+    // an early return (bad argument, CUDA failure) releases what has been built so far
+    struct Guard {
+        DistInfo *D;
+        sigb_graph_t g;
+        ~Guard() { free_dist(D); if (g) sigb_graph_release(g); }
+    } guard{D, nullptr};
     D->comm = comm;
     D->n_global = n_global;
     D->lo = lo;
@@ -442,7 +452,7 @@ int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global, const int32_t *part
     std::vector<int32_t> halo((size_t)std::max<int64_t>(ne, 1)), local((size_t)std::max<int64_t>(ne, 1));
     int32_t nhalo = 0;
     int rc = sigb_halo_build(lo, hi, ptr_blk1, node_glob1, halo.data(), &nhalo, local.data());
-    if (rc != SIGB_OK) { delete D; return rc; }
+    if (rc != SIGB_OK) return rc;
     halo.resize((size_t)nhalo);
     D->nhalo = nhalo;
     D->halo_host = halo;
@@ -474,7 +484,8 @@ int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global, const int32_t *part
     for (int32_t i = 0; i <= nloc; i++) ptr[i] = ptr_blk1[i] - ptr_blk1[0] + 1;
     sigb_graph_t g = nullptr;
     rc = sigb_cs_graph_create(nloc, nloc + nhalo, ptr.data(), local.data(), SIGB_ROW, &g);
-    if (rc != SIGB_OK) { delete D; return rc; }
+    if (rc != SIGB_OK) return rc;
+    guard.g = g;
 
     // interior / boundary tile lists
     std::vector<TileDesc> tiles, ti, tb;
@@ -548,8 +559,10 @@ int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global, const int32_t *part
 
     sigb_matrix_t A = nullptr;
     rc = sigb_matrix_create(g, &A);
+    if (rc != SIGB_OK) return rc;
+    guard.g = nullptr;
     sigb_graph_release(g);   // the matrix holds its own reference
-    if (rc != SIGB_OK) { delete D; return rc; }
+    guard.D = nullptr;
     A->dist = D;
     A->nrow = nloc;
     A->ncol = nloc;   // owned columns; the halo is internal
