@@ -175,9 +175,22 @@ divide_kernel(double *__restrict__ x, const double *__restrict__ D, int64_t n, c
 // ---------------------------------------------------------------------------
 constexpr unsigned kSweepSpinLimit = 1u << 22;   // >= 1 s of polling: far beyond a whole sweep
 
+// payload+flag words as in device_utils.cuh, but at GPU scope: these sweeps never leave the device,
+// so the accesses need not be ordered against the peers (system scope) like the all-reduce's
+__device__ __forceinline__ void st_word_gpu(unsigned int *p, unsigned int payload, unsigned int flag)
+{
+    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(flag) : "memory");
+}
+__device__ __forceinline__ uint2 ld_word_gpu(const unsigned int *p)
+{
+    uint2 r;
+    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+    return r;
+}
+
 __device__ __forceinline__ bool ll_try(const RedEntry *e, unsigned seq, double *out)
 {
-    const uint2 lo = ld_word(&e->lo), hi = ld_word(&e->hi);
+    const uint2 lo = ld_word_gpu(&e->lo), hi = ld_word_gpu(&e->hi);
     if (lo.y != seq || hi.y != seq) return false;
     *out = __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | lo.x));
     return true;
@@ -185,8 +198,8 @@ __device__ __forceinline__ bool ll_try(const RedEntry *e, unsigned seq, double *
 __device__ __forceinline__ void ll_publish(RedEntry *e, unsigned seq, double v)
 {
     const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
-    st_word(&e->lo, (unsigned)bits, seq);
-    st_word(&e->hi, (unsigned)(bits >> 32), seq);
+    st_word_gpu(&e->lo, (unsigned)bits, seq);
+    st_word_gpu(&e->hi, (unsigned)(bits >> 32), seq);
 }
 
 // (I + M) x = src, or with D: (I + M) x = src / D   (the x = x / D statement of ldu_solve
