@@ -31,6 +31,9 @@ done; done
 for rd in 0 1; do
   SIGB_LIB_VARIANT=_t1536r256 SIGB_SPMV_ROWDIRECT=$rd timeout 300 python bench.py --steps 200 --warmup 5 --quick 2>> $OUT/rowdirect.err | sed "s/^{/{\"grid\": 4096, \"rowdirect\": $rd, /" | tee -a $OUT/rowdirect.jsonl | tee -a $S
 done
+# the two-pass kernel compiled with a minimum of 4 resident CTAs named (ptxas: 32 -> up to 64 registers),
+# built here as make VARIANT=_mb4 DEFS=-DSIGB_SPMV_MINBLOCKS=4
+SIGB_LIB_VARIANT=_mb4 timeout 300 python bench.py --steps 200 --warmup 5 --quick 2>> $OUT/rowdirect.err | sed "s/^{/{\"grid\": 4096, \"rowdirect\": 0, /" | tee -a $OUT/rowdirect.jsonl | tee -a $S
 SIGB_LIB_VARIANT=_timers SIGB_SPMV_ROWDIRECT=1 timeout 300 python bench.py --steps 50 --warmup 3 --quick > /dev/null 2> $OUT/spmv_tiles_rowdirect.err
 grep spmv_cta_pass $OUT/spmv_tiles_rowdirect.err | tee -a $S
 echo "== 4. ILDU: per-level launches vs sync-free sweeps" | tee -a $S

@@ -57,8 +57,7 @@ namespace {
 // stand-alone SpMV kernel
 // ---------------------------------------------------------------------------
 template <int MODE, int NDOT, bool HALO, bool RD>
-__global__ void __launch_bounds__(kThreads)
-csr_tma_kernel(const CsrKernelArgs a)
+__device__ __forceinline__ void csr_tma_body(const CsrKernelArgs &a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t mbar[2];
@@ -103,6 +102,31 @@ csr_tma_kernel(const CsrKernelArgs a)
             }
         }
     }
+}
+
+// The measured round-1 kernel.  Its launch bounds name no minimum of resident CTAs: ptxas then
+// settles on 32 registers.  (Experiment: -DSIGB_SPMV_MINBLOCKS=4 tells it that four CTAs per SM is
+// all shared memory allows, which frees 64 registers per thread for deeper load batching.)
+#ifdef SIGB_SPMV_MINBLOCKS
+#define SIGB_SPMV_BOUNDS __launch_bounds__(kThreads, SIGB_SPMV_MINBLOCKS)
+#else
+#define SIGB_SPMV_BOUNDS __launch_bounds__(kThreads)
+#endif
+template <int MODE, int NDOT, bool HALO>
+__global__ void SIGB_SPMV_BOUNDS
+csr_tma_kernel(const CsrKernelArgs a)
+{
+    csr_tma_body<MODE, NDOT, HALO, false>(a);
+}
+
+// EXPERIMENTAL row-direct form (spmv_device.cuh).  Four resident CTAs per SM are named so that
+// ptxas may use 64 registers: at 32 it serialises the row's gathers behind the running sum, with
+// 64 it issues the four gathers of a trip back to back (checked in the SASS).
+template <int MODE, int NDOT, bool HALO>
+__global__ void __launch_bounds__(kThreads, 4)
+csr_tma_rd_kernel(const CsrKernelArgs a)
+{
+    csr_tma_body<MODE, NDOT, HALO, true>(a);
 }
 
 // ---------------------------------------------------------------------------
@@ -200,7 +224,8 @@ int launch_csr_rd(const CsrKernelArgs &a, cudaStream_t st)
 {
     int grid = 0;
     const size_t smem = 2 * (size_t)kStageBytes;
-    SIGB_CHECK((occupancy_grid<csr_tma_kernel<MODE, NDOT, HALO, RD>>(smem, &grid)));
+    constexpr auto kernel = RD ? csr_tma_rd_kernel<MODE, NDOT, HALO> : csr_tma_kernel<MODE, NDOT, HALO>;
+    SIGB_CHECK((occupancy_grid<kernel>(smem, &grid)));
     if (a.ntiles < grid) grid = a.ntiles;
     if (grid < 1) grid = 1;
     if (HALO && a.sync.win != nullptr) {
@@ -208,9 +233,9 @@ int launch_csr_rd(const CsrKernelArgs &a, cudaStream_t st)
         int pc = (a.sync.total_send + 2 * kThreads - 1) / (2 * kThreads);   // ~2 entries per thread
         b.sync.push_ctas = a.sync.total_send > 0 ? std::max(1, std::min(pc, grid)) : 0;
         b.sync.push_first = halo_push_first(grid, b.sync.push_ctas);
-        csr_tma_kernel<MODE, NDOT, HALO, RD><<<grid, kThreads, smem, st>>>(b);
+        kernel<<<grid, kThreads, smem, st>>>(b);
     } else {
-        csr_tma_kernel<MODE, NDOT, HALO, RD><<<grid, kThreads, smem, st>>>(a);
+        kernel<<<grid, kThreads, smem, st>>>(a);
     }
     count_launch();
     SIGB_CUDA(cudaGetLastError());

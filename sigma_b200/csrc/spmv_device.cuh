@@ -331,13 +331,17 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
                         const int b = sptr[r - ra] - 1 - ka, e = sptr[r + 1 - ra] - 1 - ka;
                         double z = (MODE == MODE_ACC_INIT) ? a.y[r] : 0.0;
                         for (int k = b; k < e; k += 4) {
+                            // Four entries per trip.  Indices past the row's end are clamped to its
+                            // last entry (a valid read) and their products are not added, so there is
+                            // no branch inside the trip: the four gathers are issued back to back
+                            // (with per-entry branches the compiler serialised them behind the adds).
                             int c[4];
-                            double v[4], xv[4];
+                            double v[4], xv[4], pr[4];
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
-                                const bool ok = k + j < e;
-                                c[j] = ok ? snode[k + j] : 1;
-                                v[j] = ok ? sval[k + j] : 0.0;
+                                const int kk = min(k + j, e - 1);
+                                c[j] = snode[kk];
+                                v[j] = sval[kk];
                             }
                             if (boundary) {
 #pragma unroll
@@ -350,8 +354,12 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
                                 for (int j = 0; j < 4; j++) xv[j] = ld_x<XNC>(a.x1 + c[j]);
                             }
 #pragma unroll
-                            for (int j = 0; j < 4; j++)
-                                if (k + j < e) z = add(z, mul(v[j], xv[j]));
+                            for (int j = 0; j < 4; j++) pr[j] = mul(v[j], xv[j]);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const double zn = add(z, pr[j]);
+                                z = (k + j < e) ? zn : z;
+                            }
                         }
                         emit_row<MODE, NDOT>(a, r, z, ur[i], acc);
                     }
