@@ -55,6 +55,12 @@ echo "== 6. persistent CG at the 8-GPU shard size on one GPU: default / single r
 for v in "" 1; do
   SIGB_CG_PERSISTENT=1 SIGB_CG_SINGLE_REDUCE=$v timeout 300 python bench.py --grid 1448 --steps 400 --warmup 5 --quick 2>> $OUT/pers.err | sed "s/^{/{\"single_reduce\": \"$v\", /" | tee -a $OUT/pers.jsonl | tee -a $S
 done
+# persistent kernels compiled for 3 resident CTAs per SM (80 registers, almost no spills), built here
+# as make VARIANT=_pb3 DEFS=-DSIGB_PERSIST_MINBLOCKS=3
+for rd in 0 1; do
+  SIGB_LIB_VARIANT=_pb3 SIGB_CG_PERSISTENT=1 SIGB_SPMV_ROWDIRECT=$rd timeout 300 python bench.py --grid 1448 --steps 400 --warmup 5 --quick 2>> $OUT/pers.err | sed "s/^{/{\"pb3\": 1, \"rowdirect\": $rd, /" | tee -a $OUT/pers.jsonl | tee -a $S
+done
+SIGB_CG_PERSISTENT=1 SIGB_SPMV_ROWDIRECT=1 timeout 300 python bench.py --grid 1448 --steps 400 --warmup 5 --quick 2>> $OUT/pers.err | sed "s/^{/{\"rowdirect\": 1, /" | tee -a $OUT/pers.jsonl | tee -a $S
 for c in 2 3; do
   SIGB_CG_PERSISTENT=1 SIGB_CG_PERSIST_CTAS_PER_SM=$c timeout 300 python bench.py --grid 1448 --steps 400 --warmup 5 --quick 2>> $OUT/pers.err | sed "s/^{/{\"ctas_per_sm\": $c, /" | tee -a $OUT/pers.jsonl | tee -a $S
 done

@@ -18,6 +18,8 @@ done
 echo "== N=8 row-direct SpMV inside the persistent kernel, alone and with everything else" | tee -a $S
 SIGB_SPMV_ROWDIRECT=1 run8 bench.py --gpus 8 --steps 200 --warmup 5 --quick 2>> $OUT/rd8.err | sed "s/^{/{\"rowdirect\": 1, /" | tee -a $OUT/rd8.jsonl | tee -a $S
 SIGB_SPMV_ROWDIRECT=1 SIGB_PUSH_LAST=1 SIGB_CG_SINGLE_REDUCE=1 run8 bench.py --gpus 8 --steps 200 --warmup 5 --quick 2>> $OUT/rd8.err | sed "s/^{/{\"rowdirect\": 1, \"push_last\": 1, \"single_reduce\": 1, /" | tee -a $OUT/rd8.jsonl | tee -a $S
+echo "== N=8 with the persistent kernels compiled for 3 CTAs per SM (variant _pb3)" | tee -a $S
+SIGB_LIB_VARIANT=_pb3 run8 bench.py --gpus 8 --steps 200 --warmup 5 --quick 2>> $OUT/pb3.err | sed "s/^{/{\"pb3\": 1, /" | tee -a $OUT/pb3.jsonl | tee -a $S
 echo "== phase breakdown (diagnostic build; its timings are not bench values)" | tee -a $S
 for v in "" 1; do
   SIGB_LIB_VARIANT=_timers SIGB_CG_SINGLE_REDUCE=$v run8 bench.py --gpus 8 --steps 200 --warmup 5 --quick > $OUT/phases_single$v.json 2> $OUT/phases_single$v.err

@@ -33,6 +33,13 @@
 
 namespace sigb {
 
+// Resident CTAs per SM the persistent kernels are compiled for.  4 is what shared memory allows and
+// caps them at 64 registers, which they exceed (ptxas spills 36-124 bytes); the experiment build
+// `make VARIANT=_pb3 DEFS=-DSIGB_PERSIST_MINBLOCKS=3` trades a quarter of the CTAs for 80 registers.
+#ifndef SIGB_PERSIST_MINBLOCKS
+#define SIGB_PERSIST_MINBLOCKS 4
+#endif
+
 constexpr int kPhaseSlots = 8;   // phases timed by SIGB_PHASE_TIMERS builds (see PhaseClock)
 constexpr int kPhaseCtas = 3;    // first, middle, last CTA
 
@@ -179,7 +186,7 @@ __device__ __forceinline__ double grid_allreduce(double v, const CgPersistArgs &
 }
 
 template <bool HALO, bool PC, bool RD>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, SIGB_PERSIST_MINBLOCKS)
 cg_persistent_kernel(const CgPersistArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -394,7 +401,7 @@ __device__ __forceinline__ void grid_allreduce_n(double (&v)[NV], const CgPersis
 }
 
 template <bool HALO>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, SIGB_PERSIST_MINBLOCKS)
 cg_single_reduce_kernel(const CgPersistArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];

@@ -260,7 +260,7 @@ __device__ __forceinline__ double get_value_cg(const int32_t *ptr1, const int32_
 
 // the elimination (:331-381) in one launch: the body of ldu_factor_level_kernel behind a wait
 // for the "factored" flags of the row's lower neighbours
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)   // (room for registers: at the default bounds ptxas spilled)
 ldu_factor_syncfree_kernel(const int32_t *__restrict__ rows, int32_t n, const int32_t *__restrict__ Lptr,
                            const int32_t *__restrict__ Lnode, double *Lval, const int32_t *__restrict__ Uptr,
                            const int32_t *__restrict__ Unode, double *Uval, double *D, unsigned *ready, unsigned seq,
