@@ -3,6 +3,7 @@
 # GPU budget ran out (none of them has run on a GPU yet), each next to its default.
 #   gpurun --timeout 1500 -- 'bash scripts/r2_visit_1gpu.sh r2a'
 # Reads: gpurun_out/<tag>/summary.txt first.
+make -s -C sigma_b200/csrc all variants > /dev/null 2>&1 || echo "variant build failed (prebuilt .so files are used if present)"
 TAG=${1:-r2a}; OUT=gpurun_out/$TAG; mkdir -p $OUT
 S=$OUT/summary.txt
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > $OUT/gpu.txt 2>&1

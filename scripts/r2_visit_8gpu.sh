@@ -2,6 +2,7 @@
 # Round 2, 8-GPU visit (charged 8x: keep it short).  Default scaling line, the single-reduction
 # persistent CG, the per-phase breakdown of both, then configs 4 / 5 at full size.
 #   gpurun --gpus 8 --timeout 1200 -- 'bash scripts/r2_visit_8gpu.sh r2n8'
+make -s -C sigma_b200/csrc all variants > /dev/null 2>&1 || echo "variant build failed (prebuilt .so files are used if present)"
 TAG=${1:-r2n8}; OUT=gpurun_out/$TAG; mkdir -p $OUT
 S=$OUT/summary.txt
 run8() { timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 "$@"; }
