@@ -16,8 +16,15 @@ echo "== N=8 with the halo push moved to the last CTAs (SIGB_PUSH_LAST=1), defau
 for v in "" 1; do
   SIGB_PUSH_LAST=1 SIGB_CG_SINGLE_REDUCE=$v run8 bench.py --gpus 8 --steps 200 --warmup 5 --quick 2>> $OUT/pushlast.err | sed "s/^{/{\"push_last\": 1, \"single_reduce\": \"$v\", /" | tee -a $OUT/pushlast.jsonl | tee -a $S
 done
+echo "== N=8 fence-free halo (SIGB_HALO_LL=1): parity at world 2..8, then bench alone and with push-last off/on" | tee -a $S
+SIGB_TEST_EXPERIMENTAL=1 timeout 1500 python -m pytest tests/test_gpu_experimental.py -x -q -k "fence_free_halo and default" > $OUT/exp_halo_ll.log 2>&1; echo "parity rc=$?" | tee -a $S
+tail -3 $OUT/exp_halo_ll.log | tee -a $S
+for v in "" 1; do
+  SIGB_HALO_LL=1 SIGB_CG_SINGLE_REDUCE=$v run8 bench.py --gpus 8 --steps 200 --warmup 5 --quick 2>> $OUT/halo_ll.err | sed "s/^{/{\"halo_ll\": 1, \"single_reduce\": \"$v\", /" | tee -a $OUT/halo_ll.jsonl | tee -a $S
+done
 echo "== N=8 row-direct SpMV inside the persistent kernel, alone and with everything else" | tee -a $S
 SIGB_SPMV_ROWDIRECT=1 run8 bench.py --gpus 8 --steps 200 --warmup 5 --quick 2>> $OUT/rd8.err | sed "s/^{/{\"rowdirect\": 1, /" | tee -a $OUT/rd8.jsonl | tee -a $S
+SIGB_SPMV_ROWDIRECT=1 SIGB_HALO_LL=1 run8 bench.py --gpus 8 --steps 200 --warmup 5 --quick 2>> $OUT/rd8.err | sed "s/^{/{\"rowdirect\": 1, \"halo_ll\": 1, /" | tee -a $OUT/rd8.jsonl | tee -a $S
 SIGB_SPMV_ROWDIRECT=1 SIGB_PUSH_LAST=1 SIGB_CG_SINGLE_REDUCE=1 run8 bench.py --gpus 8 --steps 200 --warmup 5 --quick 2>> $OUT/rd8.err | sed "s/^{/{\"rowdirect\": 1, \"push_last\": 1, \"single_reduce\": 1, /" | tee -a $OUT/rd8.jsonl | tee -a $S
 echo "== N=8 with the persistent kernels compiled for 3 CTAs per SM (variant _pb3)" | tee -a $S
 SIGB_LIB_VARIANT=_pb3 run8 bench.py --gpus 8 --steps 200 --warmup 5 --quick 2>> $OUT/pb3.err | sed "s/^{/{\"pb3\": 1, /" | tee -a $OUT/pb3.jsonl | tee -a $S

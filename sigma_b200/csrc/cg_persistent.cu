@@ -185,7 +185,7 @@ __device__ __forceinline__ double grid_allreduce(double v, const CgPersistArgs &
     return out;
 }
 
-template <bool HALO, bool PC, bool RD>
+template <bool HALO, bool PC, bool RD, bool LL = false>
 __global__ void __launch_bounds__(kThreads, SIGB_PERSIST_MINBLOCKS)
 cg_persistent_kernel(const CgPersistArgs a)
 {
@@ -227,7 +227,7 @@ cg_persistent_kernel(const CgPersistArgs a)
         // ---- A: q = A p, p.q ------------------------------------------------
         double acc[1] = {0.0};
         hseq++;
-        spmv_phase<MODE_SET, 1, HALO, false, RD>(a.A, smem, mbar, pipe, acc, hseq, true);
+        spmv_phase<MODE_SET, 1, HALO, false, RD, LL>(a.A, smem, mbar, pipe, acc, hseq, true);
         clk.stamp(0);
         const double pq = grid_allreduce(acc[0], a, s, pbuf, red_seq, sm_red, &s_bcast, clk, 1);
         if (HALO && a.A.sync.win != nullptr && blockIdx.x == gridDim.x - 1 && tid < kMaxRanks &&
@@ -556,12 +556,12 @@ int launch_single_reduce(const CgPersistArgs &a, cudaStream_t st)
     return SIGB_OK;
 }
 
-template <bool HALO, bool PC, bool RD>
+template <bool HALO, bool PC, bool RD, bool LL = false>
 int launch_persistent(const CgPersistArgs &a, cudaStream_t st)
 {
     const size_t smem = 2 * (size_t)kStageBytes;
     int grid = 0;
-    SIGB_CHECK((occupancy_grid<cg_persistent_kernel<HALO, PC, RD>>(smem, &grid)));
+    SIGB_CHECK((occupancy_grid<cg_persistent_kernel<HALO, PC, RD, LL>>(smem, &grid)));
     grid = cap_persistent_grid(grid);
     CgPersistArgs b = a;
     if (HALO && b.A.sync.win != nullptr) {
@@ -570,7 +570,7 @@ int launch_persistent(const CgPersistArgs &a, cudaStream_t st)
         b.A.sync.push_first = halo_push_first(grid, b.A.sync.push_ctas);
     }
     void *params[] = {(void *)&b};
-    SIGB_CUDA(cudaLaunchCooperativeKernel((const void *)cg_persistent_kernel<HALO, PC, RD>, dim3(grid), dim3(kThreads),
+    SIGB_CUDA(cudaLaunchCooperativeKernel((const void *)cg_persistent_kernel<HALO, PC, RD, LL>, dim3(grid), dim3(kThreads),
                                           params, smem, st));
     count_launch();
     return SIGB_OK;
@@ -624,6 +624,11 @@ int cg_persistent_run(sigb_solver_t s, const CsrView &V, const double *val, cons
     cudaStream_t st = ctx().stream;
     SIGB_CUDA(cudaMemsetAsync(s->bar, 0, 2 * sizeof(unsigned long long), st));
     const bool halo_on = halo.sync != nullptr;
+    if (halo_on && halo.halo_ll) {   // EXPERIMENTAL fence-free halo (SIGB_HALO_LL), see spmv_device.cuh
+        if (spmv_rowdirect(V))
+            return idiag ? launch_persistent<true, true, true, true>(a, st) : launch_persistent<true, false, true, true>(a, st);
+        return idiag ? launch_persistent<true, true, false, true>(a, st) : launch_persistent<true, false, false, true>(a, st);
+    }
     if (spmv_rowdirect(V)) {   // EXPERIMENTAL (SIGB_SPMV_ROWDIRECT), see spmv_device.cuh
         if (halo_on) return idiag ? launch_persistent<true, true, true>(a, st) : launch_persistent<true, false, true>(a, st);
         return idiag ? launch_persistent<false, true, true>(a, st) : launch_persistent<false, false, true>(a, st);

@@ -76,7 +76,8 @@ struct DistInfo {
     double *dot_tmp = nullptr;      // device, 2 doubles: interior partial sums
     // peer-memory transport
     HaloWin *win = nullptr;         // our window (flags + two landing buffers)
-    int64_t stride = 0;             // doubles between the two landing buffers
+    int64_t stride = 0;             // entries between the two landing buffers
+    bool ll = false;                // EXPERIMENTAL (SIGB_HALO_LL=1): entries are 16-byte payload+flag records
     HaloSync sync;                  // what boundary launches need
 };
 
@@ -198,6 +199,7 @@ int dist_persist_info(sigb_matrix_t A, PersistComm *pc, DotSpec *halo, bool *eli
     pc->me = C->rank;
     pc->nranks = C->nranks;
     if (D->total_send > 0 || D->nhalo > 0) halo->sync = &D->sync;
+    halo->halo_ll = D->ll;
     return SIGB_OK;
 }
 
@@ -296,6 +298,7 @@ int dist_matvec(sigb_matrix_t A, const double *x, double *y, bool add, const Dot
         // ONE kernel does push + interior + (wait) + boundary + acknowledge
         DotSpec db = dot;
         db.sync = &D->sync;
+        db.halo_ll = D->ll;
         return launch_csr_spmv(V, A->val, x, y, mode, db, 0, main, 0);
     } else if (exchange) {
         if (D->total_send > 0) {
@@ -517,7 +520,10 @@ int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global, const int32_t *part
         // window = flags + two landing buffers; tell every rank where our slice
         // of ITS landing buffer starts (its recv offset for us) and its stride
         D->stride = ((int64_t)nhalo + 15) & ~15LL;
-        const size_t bytes = sizeof(HaloWin) + sizeof(double) * 2 * (size_t)std::max<int64_t>(D->stride, 16);
+        static const bool halo_ll = env_int("SIGB_HALO_LL", 0) == 1;   // every rank must agree (same environment)
+        D->ll = halo_ll;
+        const size_t entry = D->ll ? sizeof(RedEntry) : sizeof(double);
+        const size_t bytes = sizeof(HaloWin) + entry * 2 * (size_t)std::max<int64_t>(D->stride, 16);
         SIGB_CUDA(cudaMalloc((void **)&D->win, bytes));
         SIGB_CUDA(cudaMemsetAsync(D->win, 0, bytes, st));
         SIGB_CUDA(cudaStreamSynchronize(st));
@@ -546,7 +552,10 @@ int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global, const int32_t *part
                              "sigb_dist_csr_create: rank %d expects %d entries from rank %d, send list has %d", q,
                              all[q].recv_cnt[me], me, D->send_cnt[q]);
                 D->sync.dst_mask |= 1u << q;
-                D->sync.dst[q] = reinterpret_cast<double *>((HaloWin *)peers[q] + 1) + all[q].recv_off[me];
+                // our slice of rank q's landing buffer 0 (LL: in records, the kernel re-casts the pointer)
+                D->sync.dst[q] = D->ll ? reinterpret_cast<double *>(reinterpret_cast<RedEntry *>((HaloWin *)peers[q] + 1) +
+                                                                     all[q].recv_off[me])
+                                       : reinterpret_cast<double *>((HaloWin *)peers[q] + 1) + all[q].recv_off[me];
                 D->sync.dst_stride[q] = all[q].stride;
             }
         }

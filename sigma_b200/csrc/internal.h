@@ -198,6 +198,9 @@ struct DotSpec {
     // EXPERIMENTAL (SIGB_FUSED_ALLREDUCE=1): complete the cross-GPU part of the dot products
     // inside this kernel (its last CTA) instead of a separate all-reduce launch
     const struct RedFuse *red = nullptr;
+    // EXPERIMENTAL (SIGB_HALO_LL=1): the landing buffers of `sync` hold payload+flag records
+    // (spmv_device.cuh); host-side choice of the kernel instantiation, not a kernel argument
+    bool halo_ll = false;
 };
 
 // Peer-memory halo exchange, fused into the SpMV kernel (comm.cu builds it).

@@ -56,7 +56,7 @@ namespace {
 // ---------------------------------------------------------------------------
 // stand-alone SpMV kernel
 // ---------------------------------------------------------------------------
-template <int MODE, int NDOT, bool HALO, bool RD>
+template <int MODE, int NDOT, bool HALO, bool RD, bool LL = false>
 __device__ __forceinline__ void csr_tma_body(const CsrKernelArgs &a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -82,7 +82,7 @@ __device__ __forceinline__ void csr_tma_body(const CsrKernelArgs &a)
         hseq = *reinterpret_cast<volatile unsigned long long *>(&a.sync.win->halo_seq) + 1;
 
     TilePipe pipe;
-    spmv_phase<MODE, NDOT, HALO, true, RD>(a, smem, mbar, pipe, acc, hseq, false);
+    spmv_phase<MODE, NDOT, HALO, true, RD, LL>(a, smem, mbar, pipe, acc, hseq, false);
     finish_dots<NDOT>(a, acc);
 
     // peer-memory transport: the last CTA tells every source rank that this
@@ -127,6 +127,15 @@ __global__ void __launch_bounds__(kThreads, 4)
 csr_tma_rd_kernel(const CsrKernelArgs a)
 {
     csr_tma_body<MODE, NDOT, HALO, true>(a);
+}
+
+// EXPERIMENTAL fence-free halo (SIGB_HALO_LL=1, spmv_device.cuh): the row-sharded kernels over
+// landing buffers of payload+flag records, two-pass and row-direct
+template <int MODE, int NDOT, bool RD>
+__global__ void __launch_bounds__(kThreads, 4)
+csr_tma_ll_kernel(const CsrKernelArgs a)
+{
+    csr_tma_body<MODE, NDOT, true, RD, true>(a);
 }
 
 // ---------------------------------------------------------------------------
@@ -219,12 +228,13 @@ ell_kernel(const EllKernelArgs a)
     }
 }
 
-template <int MODE, int NDOT, bool HALO, bool RD>
+template <int MODE, int NDOT, bool HALO, bool RD, bool LL = false>
 int launch_csr_rd(const CsrKernelArgs &a, cudaStream_t st)
 {
     int grid = 0;
     const size_t smem = 2 * (size_t)kStageBytes;
-    constexpr auto kernel = RD ? csr_tma_rd_kernel<MODE, NDOT, HALO> : csr_tma_kernel<MODE, NDOT, HALO>;
+    constexpr auto kernel = LL ? csr_tma_ll_kernel<MODE, NDOT, RD>
+                               : (RD ? csr_tma_rd_kernel<MODE, NDOT, HALO> : csr_tma_kernel<MODE, NDOT, HALO>);
     SIGB_CHECK((occupancy_grid<kernel>(smem, &grid)));
     if (a.ntiles < grid) grid = a.ntiles;
     if (grid < 1) grid = 1;
@@ -243,8 +253,11 @@ int launch_csr_rd(const CsrKernelArgs &a, cudaStream_t st)
 }
 
 template <int MODE, int NDOT, bool HALO>
-int launch_csr_t(const CsrKernelArgs &a, cudaStream_t st, bool rowdirect)
+int launch_csr_t(const CsrKernelArgs &a, cudaStream_t st, bool rowdirect, bool halo_ll)
 {
+    if (HALO && halo_ll)
+        return rowdirect ? launch_csr_rd<MODE, NDOT, true, true, true>(a, st)
+                         : launch_csr_rd<MODE, NDOT, true, false, true>(a, st);
     return rowdirect ? launch_csr_rd<MODE, NDOT, HALO, true>(a, st) : launch_csr_rd<MODE, NDOT, HALO, false>(a, st);
 }
 
@@ -400,11 +413,12 @@ int launch_csr_spmv(const CsrView &A, const double *val, const double *x, double
     if (a.ntiles == 0 && dot.ndot == 0) return SIGB_OK;
 
     const bool rd = spmv_rowdirect(A);
+    const bool ll = dot.sync != nullptr && dot.halo_ll;
 #define SIGB_DISPATCH(M)                                                            \
     switch (dot.ndot) {                                                             \
-    case 0: return halo ? launch_csr_t<M, 0, true>(a, st, rd) : launch_csr_t<M, 0, false>(a, st, rd);  \
-    case 1: return halo ? launch_csr_t<M, 1, true>(a, st, rd) : launch_csr_t<M, 1, false>(a, st, rd);  \
-    default: return halo ? launch_csr_t<M, 2, true>(a, st, rd) : launch_csr_t<M, 2, false>(a, st, rd); \
+    case 0: return halo ? launch_csr_t<M, 0, true>(a, st, rd, ll) : launch_csr_t<M, 0, false>(a, st, rd, ll);  \
+    case 1: return halo ? launch_csr_t<M, 1, true>(a, st, rd, ll) : launch_csr_t<M, 1, false>(a, st, rd, ll);  \
+    default: return halo ? launch_csr_t<M, 2, true>(a, st, rd, ll) : launch_csr_t<M, 2, false>(a, st, rd, ll); \
     }
     switch (mode) {
     case MODE_SET: SIGB_DISPATCH(MODE_SET)

@@ -127,6 +127,28 @@ __device__ __forceinline__ void emit_row(const CsrKernelArgs &a, int r, double z
     if (NDOT >= 2) acc[NDOT > 1 ? 1 : 0] = add(acc[NDOT > 1 ? 1 : 0], mul(z, z));
 }
 
+// ---- EXPERIMENTAL fence-free halo (LL, opt-in through SIGB_HALO_LL=1, not yet run on a GPU) ------
+// The landing buffers hold one 16-byte record per halo entry -- two words of 32 payload bits + the
+// 32-bit sequence number of the SpMV, like the all-reduce inbox -- instead of bare doubles behind a
+// per-source flag.  A word is delivered as a unit, so a record is either old or complete: the
+// producer needs no system-scope fence and publishes nothing (that fence sits on the pushing CTAs'
+// critical path today and makes them the last to reach the barrier), and a consumer simply polls
+// the record it is about to gather.  Buffer reuse is still guarded by the acknowledgements.
+__device__ __forceinline__ void halo_ll_store(RedEntry *e, unsigned seq, double v)
+{
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    st_word(&e->lo, (unsigned)bits, seq);
+    st_word(&e->hi, (unsigned)(bits >> 32), seq);
+}
+__device__ __forceinline__ double halo_ll_load(const RedEntry *e, unsigned seq)
+{
+    uint2 lo, hi;
+    unsigned spins = 0;
+    do { lo = ld_word(&e->lo); } while (lo.y != seq && ++spins < kSpinLimit);
+    do { hi = ld_word(&e->hi); } while (hi.y != seq && ++spins < kSpinLimit);
+    return __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | lo.x));
+}
+
 // one row longer than a tile: CTA-wide fixed-tree reduction, direct loads
 // XNC: x (and the dot operand u) may be read through the non-coherent read-only
 // path.  True for stand-alone launches, where the vectors are constant for the
@@ -138,14 +160,17 @@ __device__ __forceinline__ double ld_x(const double *p)
     return XNC ? __ldg(p) : *p;
 }
 
-template <int MODE, int NDOT, bool HALO, bool XNC>
-__device__ __forceinline__ void long_row(const CsrKernelArgs &a, const int4 &d, const double *h1, double *acc)
+template <int MODE, int NDOT, bool HALO, bool XNC, bool LL = false>
+__device__ __forceinline__ void long_row(const CsrKernelArgs &a, const int4 &d, const double *h1, double *acc,
+                                         const RedEntry *hll = nullptr, unsigned seq = 0)
 {
     __shared__ double smr[1][kThreads / 32];
     double s[1] = {0.0};
     for (int k = d.z + threadIdx.x; k < d.w; k += kThreads) {
         const int c = a.node[k];
-        const double xv = (HALO && c > a.nloc) ? __ldcg(h1 + c) : ld_x<XNC>(a.x1 + c);
+        double xv;
+        if (LL && HALO && c > a.nloc) xv = halo_ll_load(hll + c, seq);
+        else xv = (HALO && c > a.nloc) ? __ldcg(h1 + c) : ld_x<XNC>(a.x1 + c);
         s[0] = add(s[0], mul(a.val[k], xv));
     }
     block_tree<1>(s, smr);
@@ -195,7 +220,7 @@ struct TilePipe {
 // rows are consecutive columns, so the gathers coalesce like the ELLPACK kernel's.  It loses
 // when rows are long or ragged (a warp runs as long as its longest row), hence a per-matrix
 // choice on the host.
-template <int MODE, int NDOT, bool HALO, bool XNC, bool RD = false>
+template <int MODE, int NDOT, bool HALO, bool XNC, bool RD = false, bool LL = false>
 __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char *smem, uint64_t *mbar,
                                            TilePipe &pipe, double *acc, unsigned long long hseq,
                                            bool prime_next)
@@ -206,6 +231,7 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
     // finish, so every CTA reads the same value here.
     const int tid = threadIdx.x;
     const double *h1 = a.h1;
+    const RedEntry *hll = nullptr;    // LL: records of the landing buffer, indexable by column ids > nloc
     bool halo_ready = !(HALO && a.sync.win != nullptr);
     bool push_pending = false;
     if (HALO && a.sync.win != nullptr) {
@@ -224,10 +250,15 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
             for (int k = push_rank * kThreads + tid; k < a.sync.total_send; k += a.sync.push_ctas * kThreads) {
                 int q = 0;
                 while (k >= a.sync.send_off[q + 1]) q++;
-                a.sync.dst[q][buf * a.sync.dst_stride[q] + (k - a.sync.send_off[q])] =
-                    ld_x<XNC>(a.x1 + a.sync.send_rows[k]);
+                if (LL)
+                    halo_ll_store(reinterpret_cast<RedEntry *>(a.sync.dst[q]) + buf * a.sync.dst_stride[q] +
+                                      (k - a.sync.send_off[q]),
+                                  (unsigned)hseq, ld_x<XNC>(a.x1 + a.sync.send_rows[k]));
+                else
+                    a.sync.dst[q][buf * a.sync.dst_stride[q] + (k - a.sync.send_off[q])] =
+                        ld_x<XNC>(a.x1 + a.sync.send_rows[k]);
             }
-            push_pending = true;   // published after the first tile, see below
+            push_pending = !LL;    // published after the first tile, see below (LL: nothing to publish)
         }
     }
     // The stores above need a system-scope fence before the sequence number may
@@ -290,16 +321,22 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
         if (HALO && !halo_ready && t >= a.first_halo_tile) {   // CTA-uniform
             // never wait on peers while our own push is unpublished (two ranks
             // whose pushing CTAs start on a boundary tile would wait forever)
-            if (push_pending) publish_push();
-            if (tid == 0) {
-                for (int q = 0; q < kMaxRanks; q++)
-                    if (a.sync.src_mask & (1u << q)) {
-                        unsigned spins = 0;
-                        while (ld_acquire_sys(&a.sync.win->hflag[hseq & 1][q]) < hseq && ++spins < kSpinLimit) {}
-                    }
+            if (LL) {
+                // nothing to wait for here: every gathered record is polled where it is read
+                hll = reinterpret_cast<const RedEntry *>(a.sync.halo_base) + (hseq & 1) * a.sync.halo_stride -
+                      (a.nloc + 1);
+            } else {
+                if (push_pending) publish_push();
+                if (tid == 0) {
+                    for (int q = 0; q < kMaxRanks; q++)
+                        if (a.sync.src_mask & (1u << q)) {
+                            unsigned spins = 0;
+                            while (ld_acquire_sys(&a.sync.win->hflag[hseq & 1][q]) < hseq && ++spins < kSpinLimit) {}
+                        }
+                }
+                __syncthreads();
+                h1 = a.sync.halo_base + (hseq & 1) * a.sync.halo_stride - (a.nloc + 1);
             }
-            __syncthreads();
-            h1 = a.sync.halo_base + (hseq & 1) * a.sync.halo_stride - (a.nloc + 1);
             halo_ready = true;
         }
 
@@ -343,7 +380,12 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
                                 c[j] = snode[kk];
                                 v[j] = sval[kk];
                             }
-                            if (boundary) {
+                            if (boundary && LL) {
+#pragma unroll
+                                for (int j = 0; j < 4; j++)
+                                    xv[j] = (c[j] > a.nloc) ? halo_ll_load(hll + c[j], (unsigned)hseq)
+                                                            : __ldcg(a.x1 + c[j]);
+                            } else if (boundary) {
 #pragma unroll
                                 for (int j = 0; j < 4; j++) {
                                     const double *src = (c[j] > a.nloc) ? h1 + c[j] : a.x1 + c[j];
@@ -392,7 +434,16 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
             // boundary tiles the address is selected (no divergent branch between
             // the gathers, which would serialise them) and everything is read at
             // L2 -- halo entries are written by peers, so L1 must not serve them.
-            if (HALO && t >= a.first_halo_tile) {
+            if (LL && HALO && t >= a.first_halo_tile) {
+                // (entries of the previous tile that share this tile's first 16-byte group are
+                //  multiplied too and never used: they must not be waited for)
+#pragma unroll
+                for (int i = 0; i < kTileNnz / kThreads; i++) {
+                    const int k = tid + i * kThreads;
+                    xv[i] = (c[i] > a.nloc && k >= ks - ka && k < cnt) ? halo_ll_load(hll + c[i], (unsigned)hseq)
+                                                                       : __ldcg(a.x1 + min(c[i], a.nloc));
+                }
+            } else if (HALO && t >= a.first_halo_tile) {
 #pragma unroll
                 for (int i = 0; i < kTileNnz / kThreads; i++) {
                     const double *src = (c[i] > a.nloc) ? h1 + c[i] : a.x1 + c[i];
@@ -441,7 +492,7 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
 #endif
             }   // !RD
         } else {
-            long_row<MODE, NDOT, HALO, XNC>(a, d_cur, h1, acc);
+            long_row<MODE, NDOT, HALO, XNC, LL>(a, d_cur, h1, acc, hll, (unsigned)hseq);
         }
         sidx = sidx_after;
         d_cur = d_next;

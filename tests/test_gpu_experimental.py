@@ -19,6 +19,9 @@ subprocess; the whole file is skipped unless SIGB_TEST_EXPERIMENTAL=1.
                             finished by the last CTA of the kernels that produce the local sums
                             (csrc/device_utils.cuh grid_reduce) instead of separate one-warp launches.
                             Same values added in the same rank order: results must be identical.
+  SIGB_HALO_LL=1            fence-free halo exchange: landing buffers of payload+flag records, no publish
+                            fence on the pushing CTAs, consumers poll the records they gather
+                            (csrc/spmv_device.cuh).  Same values: sharded parity must be unchanged.
   SIGB_ASYNC_ALLOC=1        temporaries of transposes / copies / assembly from the stream-ordered pool
                             (cudaMallocAsync / cudaFreeAsync) instead of cudaMalloc / cudaFree.
   SIGB_SPMV_ROWDIRECT=1     row-direct form of the streaming CSR kernel for every matrix (csrc/
@@ -310,6 +313,21 @@ def test_sharded_parity_with_push_by_the_last_ctas():
         pytest.skip("needs 2 GPUs")
     e = dict(os.environ)
     e["SIGB_PUSH_LAST"] = "1"
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_dist.py", "-k", "p2p"],
+                       cwd=ROOT, env=e, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("extra", [{}, {"SIGB_SPMV_ROWDIRECT": "1"}, {"SIGB_CG_PERSISTENT": "0"}],
+                         ids=["default", "rowdirect", "kernel_per_phase"])
+def test_sharded_parity_with_fence_free_halo(extra):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    e = dict(os.environ)
+    e["SIGB_HALO_LL"] = "1"
+    e.update(extra)
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_dist.py", "-k", "p2p"],
                        cwd=ROOT, env=e, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
