@@ -103,3 +103,46 @@ def test_halo_irregular_graph(orc):
         _capi.check(L.sigb_halo_build(lo, hi, _capi.ptr(bptr), _capi.ptr(bnode), _capi.ptr(halo), C.byref(nh),
                                       _capi.ptr(local)))
         assert np.array_equal(halo[: nh.value], ohalo) and np.array_equal(local, olocal)
+
+
+def declared_arity():
+    """{symbol: number of parameters} parsed from the header."""
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"SIGB_API\s+[\w\s\*]+?\b(sigb_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+    return out
+
+
+def test_python_prototypes_have_the_header_arity():
+    """A ctypes prototype with the wrong number of arguments corrupts the call silently: every
+    binding must take exactly as many arguments as the header declares."""
+    from sigma_b200 import _capi
+
+    arity = declared_arity()
+    assert sorted(arity) == declared_symbols()
+    wrong = {name: (len(proto[1]), arity[name]) for name, proto in _capi.PROTOTYPES.items() if len(proto[1]) != arity[name]}
+    assert not wrong, wrong
+
+
+def test_environment_switches_are_documented():
+    """Every SIGB_* switch the library reads is named in README.md, and README.md names no switch
+    that nothing reads."""
+    csrc = os.path.join(ROOT, "sigma_b200", "csrc")
+    read = set()
+    for f in os.listdir(csrc):
+        if f.endswith((".cu", ".cpp", ".cuh", ".h")):
+            read |= set(re.findall(r'(?:getenv|env_int)\("(SIGB_\w+)"', open(os.path.join(csrc, f)).read()))
+    read |= set(re.findall(r'environ\.get\("(SIGB_\w+)"', open(os.path.join(ROOT, "sigma_b200", "_capi.py")).read()))
+    readme = open(os.path.join(ROOT, "README.md")).read()
+    named = set(re.findall(r"`(SIGB_[A-Z0-9_]+)", readme))
+    # families written as SIGB_LDU_SF_* and the test-only / build-only names
+    named_prefixes = {m[:-1] for m in re.findall(r"`(SIGB_[A-Z0-9_]+\*)", readme.replace("_\\*", "_*"))}
+    undocumented = {s for s in read if s not in named and not any(s.startswith(p) for p in named_prefixes)}
+    assert not undocumented, undocumented
+    build_or_test_only = {"SIGB_TEST_EXPERIMENTAL", "SIGB_PHASE_TIMERS", "SIGB_SPMV_MINBLOCKS", "SIGB_PERSIST_MINBLOCKS",
+                          "SIGB_TILE_NNZ", "SIGB_TILE_ROWS"}
+    stale = {s for s in named if s not in read and s not in build_or_test_only and not s.endswith("_")}
+    assert not stale, stale

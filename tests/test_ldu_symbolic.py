@@ -206,3 +206,45 @@ def test_syncfree_sweep_model_terminates_and_matches(orc, case, grid_threads):
     y, _ = syncfree_sweep_model(S["forward_rows"], F.Lptr, F.Lnode, F.Lval, b, n, grid_threads, rng)
     x, _ = syncfree_sweep_model(S["backward_rows"], F.Uptr, F.Unode, F.Uval, y / F.D, n, grid_threads, rng)
     assert np.array_equal(x, orc.ldu_solve(F, b))
+
+
+def test_symbolic_on_random_patterns_hypothesis(orc):
+    """Random square patterns -- empty rows, missing diagonals, unsorted rows, dense rows -- through
+    the host symbolic analysis: patterns equal the oracle's, every row appears once per schedule,
+    and a row's level is one more than the highest level among the rows it reads."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 40), st.floats(0.0, 0.6), st.integers(0, 2**31 - 1))
+    def check(n, density, seed):
+        rng = np.random.default_rng(seed)
+        mask = rng.random((n, n)) < density
+        if rng.random() < 0.5:
+            mask |= np.eye(n, dtype=bool)
+        rows = []
+        for i in range(n):
+            cols = np.flatnonzero(mask[i]) + 1
+            rows.append(rng.permutation(cols))                    # stored order is arbitrary
+        ptr = np.concatenate([[1], 1 + np.cumsum([r.size for r in rows])]).astype(np.int32)
+        node = (np.concatenate(rows) if ptr[-1] > 1 else np.zeros(0)).astype(np.int32)
+        S = sb.ldu_symbolic(n, ptr, node)
+        for i in range(n):
+            row = node[ptr[i] - 1: ptr[i + 1] - 1]
+            assert np.array_equal(S["Lnode"][S["Lptr"][i] - 1: S["Lptr"][i + 1] - 1], row[row < i + 1])
+            assert np.array_equal(S["Unode"][S["Uptr"][i] - 1: S["Uptr"][i + 1] - 1], row[row > i + 1])
+        # dest is a bijection onto [0, nL + nU) plus the diagonal slots of the rows that store one
+        nL, nU = S["Lnode"].size, S["Unode"].size
+        dest = S["dest"]
+        assert dest.size == node.size and np.unique(dest).size == dest.size
+        assert np.all((dest >= 0) & (dest < nL + nU + n))
+        for rows_, lev, p_, nd in ((S["forward_rows"], S["forward_lev"], S["Lptr"], S["Lnode"]),
+                                   (S["backward_rows"], S["backward_lev"], S["Uptr"], S["Unode"])):
+            assert np.array_equal(np.sort(rows_), np.arange(1, n + 1))
+            level_of = np.empty(n + 1, np.int64)
+            for l in range(lev.size - 1):
+                level_of[rows_[lev[l]:lev[l + 1]]] = l
+            for i in range(1, n + 1):
+                nb = nd[p_[i - 1] - 1: p_[i] - 1]
+                assert level_of[i] == (level_of[nb].max() + 1 if nb.size else 0)
+
+    check()
