@@ -146,3 +146,40 @@ def test_environment_switches_are_documented():
                           "SIGB_TILE_NNZ", "SIGB_TILE_ROWS"}
     stale = {s for s in named if s not in read and s not in build_or_test_only and not s.endswith("_")}
     assert not stale, stale
+
+
+def test_partition_and_halo_on_random_patterns_hypothesis(orc):
+    """Random rectangular-free patterns (empty rows, full rows, any number of parts up to the row
+    count): partition offsets, halo lists and local renumbering equal the oracle's, entry for entry."""
+    from hypothesis import given, settings, strategies as st
+
+    from sigma_b200 import _capi
+
+    L = _capi.lib()
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 60), st.floats(0.0, 0.5), st.integers(1, 8), st.integers(0, 2**31 - 1))
+    def check(n, density, P, seed):
+        rng = np.random.default_rng(seed)
+        mask = rng.random((n, n)) < density
+        rows = [rng.permutation(np.flatnonzero(mask[i]) + 1) for i in range(n)]
+        ptr = np.concatenate([[1], 1 + np.cumsum([r.size for r in rows])]).astype(np.int32)
+        node = (np.concatenate(rows) if ptr[-1] > 1 else np.zeros(0)).astype(np.int32)
+        part = np.empty(P + 1, np.int32)
+        _capi.check(L.sigb_partition_rows(n, _capi.ptr(ptr), P, _capi.ptr(part)))
+        assert np.array_equal(part, orc.partition_rows(ptr, P))
+        assert part[0] == 0 and part[-1] == n and np.all(np.diff(part) >= 0)
+        for r in range(P):
+            lo, hi = int(part[r]), int(part[r + 1])
+            bptr = np.ascontiguousarray(ptr[lo:hi + 1])
+            bnode = np.ascontiguousarray(node[ptr[lo] - 1: ptr[hi] - 1])
+            halo = np.empty(max(bnode.size, 1), np.int32)
+            local = np.empty(max(bnode.size, 1), np.int32)
+            nh = C.c_int32()
+            _capi.check(L.sigb_halo_build(lo, hi, _capi.ptr(bptr), _capi.ptr(bnode) if bnode.size else _capi.ptr(halo),
+                                          _capi.ptr(halo), C.byref(nh), _capi.ptr(local)))
+            ohalo, olocal = orc.halo_build(lo, hi, ptr, node)
+            assert np.array_equal(halo[: nh.value], ohalo)
+            assert np.array_equal(local[: bnode.size], olocal)
+
+    check()

@@ -47,3 +47,30 @@ def test_blocks_tile_the_matrix():
     nodes = np.concatenate([G.fem_p1_csr_rows(N, a, b)[1] for a, b in zip(cuts[:-1], cuts[1:])])
     vals = np.concatenate([G.fem_p1_csr_rows(N, a, b)[2] for a, b in zip(cuts[:-1], cuts[1:])])
     assert np.array_equal(nodes, node) and np.array_equal(vals, val)
+
+
+def test_row_blocks_hypothesis():
+    """Any block [lo, hi) of either generator equals the slice of the whole matrix."""
+    from hypothesis import given, settings, strategies as st
+
+    fem = {N: G.fem_p1_csr(N) for N in (4, 9, 16)}
+    er = G.erdos_renyi_csr(400, seed=21, weights="random", skew=True)
+    cache = {}
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.sampled_from([4, 9, 16]), st.integers(0, 10**6), st.integers(0, 10**6))
+    def check(N, a, b):
+        n = N * N
+        lo, hi = sorted((a % (n + 1), b % (n + 1)))
+        if lo == hi:
+            return
+        for x, y in zip(G.fem_p1_csr_rows(N, lo, hi), block_of(*fem[N], lo, hi)):
+            assert np.array_equal(x, y)
+        lo, hi = sorted((a % 401, b % 401))
+        if lo == hi:
+            return
+        *got, _ = G.erdos_renyi_csr_rows(400, lo, hi, seed=21, weights="random", skew=True, cache=cache)
+        for x, y in zip(got, block_of(*er, lo, hi)):
+            assert np.array_equal(x, y)
+
+    check()

@@ -107,3 +107,22 @@ def test_device_algorithm_replica_equals_the_greedy_walk(case):
     assert np.array_equal(got, want)
     if want.shape[0] > 1:
         assert rounds <= int(np.ceil(np.log2(want.shape[0]))) + 1   # log-depth, not one round per tile
+
+
+def test_tilings_on_random_row_lengths_hypothesis():
+    """Random row-length sequences (mixtures of empty, short, cap-sized and oversized rows): the
+    library's bisection tiling and the replica of the device algorithm both equal the greedy walk."""
+    from hypothesis import given, settings, strategies as st
+
+    lengths = st.lists(st.one_of(st.integers(0, 12), st.sampled_from([0, 0, 1, 2044, 2045, 2046, 4000]),
+                                 st.integers(0, 700)), min_size=0, max_size=1500)
+
+    @settings(max_examples=80, deadline=None)
+    @given(lengths)
+    def check(deg):
+        p = np.concatenate([[1], 1 + np.cumsum(np.asarray(deg, np.int64))]).astype(np.int32)
+        want = greedy(p)
+        assert np.array_equal(library_tiles(p), want)
+        assert np.array_equal(device_algorithm_replica(p)[0], want)
+
+    check()
