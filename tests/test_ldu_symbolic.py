@@ -248,3 +248,31 @@ def test_symbolic_on_random_patterns_hypothesis(orc):
                 assert level_of[i] == (level_of[nb].max() + 1 if nb.size else 0)
 
     check()
+
+
+def test_syncfree_sweep_model_on_random_patterns_hypothesis(orc):
+    """The sync-free sweep model on random patterns, warp widths and resident-thread counts: it
+    always terminates (no schedule can starve the lowest unfinished position) and reproduces the
+    serial solve bit for bit."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(2, 60), st.floats(0.02, 0.5), st.sampled_from([1, 2, 4, 8]), st.integers(1, 6),
+           st.integers(0, 2**31 - 1))
+    def check(n, density, warp, warps, seed):
+        rng = np.random.default_rng(seed)
+        mask = (rng.random((n, n)) < density) | np.eye(n, dtype=bool)
+        rows = [rng.permutation(np.flatnonzero(mask[i]) + 1) for i in range(n)]
+        ptr = np.concatenate([[1], 1 + np.cumsum([r.size for r in rows])]).astype(np.int32)
+        node = np.concatenate(rows).astype(np.int32)
+        val = rng.uniform(-1, 1, node.size)
+        val[node == np.repeat(np.arange(1, n + 1), np.diff(ptr))] += n      # diagonally dominant: no pivot trouble
+        S = sb.ldu_symbolic(n, ptr, node)
+        F = orc.ldu_setup(orc.Matrix(orc.CSR, n, n, node, val, ptr=ptr))
+        b = rng.standard_normal(n)
+        g = warp * warps
+        y, _ = syncfree_sweep_model(S["forward_rows"], F.Lptr, F.Lnode, F.Lval, b, n, g, rng, warp=warp)
+        x, _ = syncfree_sweep_model(S["backward_rows"], F.Uptr, F.Unode, F.Uval, y / F.D, n, g, rng, warp=warp)
+        assert np.array_equal(x, orc.ldu_solve(F, b))
+
+    check()
