@@ -149,6 +149,33 @@ struct cs_graph {
         mirror[1].reset();
         return indx - 1;
     }
+    // g%left_permute(p, edge_p)   (cs_graph_left_permute :499-549): line i becomes line p(i), each
+    // line keeps its stored order.  from[i-1] / to[i-1] / len[i-1] (0-based offsets) say where the
+    // entries of old line i went -- the reference's compressed edge permutation.
+    void left_permute(const std::vector<int> &p, std::vector<int> &from, std::vector<int> &to, std::vector<int> &len)
+    {
+        std::vector<int32_t> nptr((size_t)n + 1, 0), nnode((size_t)ne);
+        from.assign((size_t)n, 0); to.assign((size_t)n, 0); len.assign((size_t)n, 0);
+        for (int i = 1; i <= n; i++) nptr[(size_t)p[(size_t)i - 1]] = ptr[(size_t)i] - ptr[(size_t)i - 1];
+        nptr[0] = 1;
+        for (int i = 1; i <= n; i++) nptr[(size_t)i] += nptr[(size_t)i - 1];
+        for (int i = 1; i <= n; i++) {
+            const int d = ptr[(size_t)i] - ptr[(size_t)i - 1], src = ptr[(size_t)i - 1] - 1, dst = nptr[(size_t)p[(size_t)i - 1] - 1] - 1;
+            for (int k = 0; k < d; k++) nnode[(size_t)dst + k] = node[(size_t)src + k];
+            from[(size_t)i - 1] = src; to[(size_t)i - 1] = dst; len[(size_t)i - 1] = d;
+        }
+        ptr.swap(nptr);
+        node.swap(nnode);
+        mirror[0].reset();
+        mirror[1].reset();
+    }
+    // g%right_permute(p)   (cs_graph_right_permute :554-570): the ids are relabelled in place
+    void right_permute(const std::vector<int> &p)
+    {
+        for (int32_t &c : node) c = p[(size_t)c - 1];
+        mirror[0].reset();
+        mirror[1].reset();
+    }
 };
 
 // src/graph/formats/ellpack_graphs.f90: node(max_d, n), padding = last neighbour
@@ -206,6 +233,23 @@ struct ellpack_graph {
         ne++;
         mirror.reset();
         return widened;
+    }
+    // ellpack_graph_left_permute :486-518 / ellpack_graph_right_permute :523-541
+    void left_permute(const std::vector<int> &p)
+    {
+        std::vector<int32_t> nnode(node.size()), ndeg(degrees.size());
+        for (int i = 1; i <= n; i++) {
+            for (int l = 0; l < max_d; l++) nnode[(size_t)(p[(size_t)i - 1] - 1) * max_d + l] = node[(size_t)(i - 1) * max_d + l];
+            ndeg[(size_t)p[(size_t)i - 1] - 1] = degrees[(size_t)i - 1];
+        }
+        node.swap(nnode);
+        degrees.swap(ndeg);
+        mirror.reset();
+    }
+    void right_permute(const std::vector<int> &p)
+    {
+        for (int32_t &c : node) if (c != 0) c = p[(size_t)c - 1];
+        mirror.reset();
     }
 };
 
@@ -352,6 +396,28 @@ struct cs_matrix : device_matrix {
     void add_value(int i, int j, dp z) override { const int k = slot(i, j); if (k < 0) { grow(i, j, z); return; } val[(size_t)k] += z; dirty = true; }
     bool in_pattern(int i, int j) const override { return slot(i, j) >= 0; }
     dp get_value(int i, int j) override { const int k = slot(i, j); return k < 0 ? 0.0 : val[(size_t)k]; }
+    // call A%left_permute(p) / A%right_permute(p)   (cs_matrices.f90:471-490): rows (columns) i move to
+    // p(i).  A csr_matrix moves its lines for a left permutation and relabels its ids for a right one
+    // (graph_leftperm / graph_rightperm, default_sparse_matrix_kernels.f90:234-277); a csc_matrix the
+    // other way round (:186-187).  Host-side, like the reference; the device mirrors are dropped.
+    void move_lines(const std::vector<int> &p)
+    {
+        std::vector<int> from, to, len;
+        g->left_permute(p, from, to, len);
+        std::vector<dp> nval(val.size());
+        for (size_t b = 0; b < from.size(); b++)
+            for (int k = 0; k < len[b]; k++) nval[(size_t)to[b] + k] = val[(size_t)from[b] + k];
+        val.swap(nval);
+    }
+    void permute(const std::vector<int> &p, bool lines)
+    {
+        if (g.use_count() > 1) g = std::make_shared<cs_graph>(*g);
+        if (lines) move_lines(p); else g->right_permute(p);
+        if (mirror) { sigb_matrix_destroy(mirror); mirror = nullptr; }
+        dirty = true;
+    }
+    void left_permute(const std::vector<int> &p) { permute(p, !COL); }
+    void right_permute(const std::vector<int> &p) { permute(p, COL); }
 
     void sync_mirror() override
     {
@@ -462,6 +528,25 @@ struct ellpack_matrix : device_matrix {
     }
     bool in_pattern(int i, int j) const override { return slot(i, j) >= 0; }
     dp get_value(int i, int j) override { const int k = slot(i, j); return k < 0 ? 0.0 : val[(size_t)k]; }
+    // ellpack_matrix_left_permute / _right_permute (ellpack_matrices.f90:601-630), host-side
+    void left_permute(const std::vector<int> &p)
+    {
+        if (g.use_count() > 1) g = std::make_shared<ellpack_graph>(*g);
+        std::vector<dp> nval(val.size());
+        for (int i = 1; i <= g->n; i++)
+            for (int l = 0; l < g->max_d; l++) nval[(size_t)(p[(size_t)i - 1] - 1) * g->max_d + l] = val[(size_t)(i - 1) * g->max_d + l];
+        val.swap(nval);
+        g->left_permute(p);
+        if (mirror) { sigb_matrix_destroy(mirror); mirror = nullptr; }
+        dirty = true;
+    }
+    void right_permute(const std::vector<int> &p)
+    {
+        if (g.use_count() > 1) g = std::make_shared<ellpack_graph>(*g);
+        g->right_permute(p);
+        if (mirror) { sigb_matrix_destroy(mirror); mirror = nullptr; }
+        dirty = true;
+    }
 
     void sync_mirror() override
     {

@@ -16,7 +16,8 @@ PROGS = ["solver_test_diffusion_1d", "solver_test_advection_diffusion_1d", "solv
 
 # written after the last GPU visit of round 1: compiled on every run, executed only with
 # SIGB_TEST_EXPERIMENTAL=1 until they have passed on a GPU once (then move them into PROGS)
-PROGS_NOT_YET_RUN = ["matrix_test_strategy", "matrix_test_set_multiple_entries", "matrix_test_set_entry_with_realloc"]
+PROGS_NOT_YET_RUN = ["matrix_test_strategy", "matrix_test_set_multiple_entries", "matrix_test_set_entry_with_realloc",
+                     "matrix_test_permute"]
 
 
 def build():
@@ -55,3 +56,14 @@ def test_set_entry_with_realloc_host_side():
                        capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("setting unallocated entries works") == 3
+
+
+def test_permutations_host_side():
+    """The permutation part of test/matrix_test_basics.f90 (:139-158, :364-392): right_permute and
+    left_permute of csr / csc / ellpack matrices are host-side index work in the reference and in
+    the mirror; the restated program runs here without a GPU (--host-only skips its device matvec)."""
+    build()
+    r = subprocess.run([os.path.join(CXX, "_build", "matrix_test_permute"), "-v", "--host-only"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("right and left permutation work") == 3
