@@ -418,6 +418,25 @@ struct cs_matrix : device_matrix {
     }
     void left_permute(const std::vector<int> &p) { permute(p, !COL); }
     void right_permute(const std::vector<int> &p) { permute(p, COL); }
+    // call A%get_row(nodes, slice, k) / A%get_column(nodes, slice, k)   (cs_matrices.f90:370-392): the
+    // stored line itself when the format keeps that direction (get_slice_contiguous,
+    // default_sparse_matrix_kernels.f90:94-123), a scan over all lines otherwise
+    // (get_slice_discontiguous :128-165).  Host-side reads of the mirror's own arrays.
+    void line_slice(int k, std::vector<int32_t> &nodes, std::vector<dp> &slice) const
+    {
+        nodes.clear(); slice.clear();
+        for (int q = g->ptr[(size_t)k - 1] - 1; q < g->ptr[(size_t)k] - 1; q++) { nodes.push_back(g->node[(size_t)q]); slice.push_back(val[(size_t)q]); }
+    }
+    void cross_slice(int k, std::vector<int32_t> &nodes, std::vector<dp> &slice) const
+    {
+        nodes.clear(); slice.clear();
+        for (int l = 1; l <= g->n; l++) {
+            const int q = g->find_edge(l, k);
+            if (q >= 0) { nodes.push_back(l); slice.push_back(val[(size_t)q]); }
+        }
+    }
+    void get_row(std::vector<int32_t> &nodes, std::vector<dp> &slice, int k) const { if (COL) cross_slice(k, nodes, slice); else line_slice(k, nodes, slice); }
+    void get_column(std::vector<int32_t> &nodes, std::vector<dp> &slice, int k) const { if (COL) line_slice(k, nodes, slice); else cross_slice(k, nodes, slice); }
 
     void sync_mirror() override
     {
@@ -546,6 +565,23 @@ struct ellpack_matrix : device_matrix {
         g->right_permute(p);
         if (mirror) { sigb_matrix_destroy(mirror); mirror = nullptr; }
         dirty = true;
+    }
+    // get_row: the first degrees(k) slots of row k; get_column: a scan over the rows
+    void get_row(std::vector<int32_t> &nodes, std::vector<dp> &slice, int k) const
+    {
+        nodes.clear(); slice.clear();
+        for (int l = 0; l < g->degrees[(size_t)k - 1]; l++) {
+            nodes.push_back(g->node[(size_t)(k - 1) * g->max_d + l]);
+            slice.push_back(val[(size_t)(k - 1) * g->max_d + l]);
+        }
+    }
+    void get_column(std::vector<int32_t> &nodes, std::vector<dp> &slice, int k) const
+    {
+        nodes.clear(); slice.clear();
+        for (int i = 1; i <= g->n; i++) {
+            const int q = slot(i, k);
+            if (q >= 0) { nodes.push_back(i); slice.push_back(val[(size_t)q]); }
+        }
     }
 
     void sync_mirror() override

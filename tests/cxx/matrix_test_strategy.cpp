@@ -13,7 +13,7 @@
 using namespace sigma;
 
 template <class M>
-static int run(const ll_graph &g, int nn, const std::vector<dp> &x, const char *name, bool verbose)
+static int run(const ll_graph &g, int nn, const std::vector<dp> &x, const char *name, bool verbose, bool on_device)
 {
     auto *L = new M();
     L->init(nn, nn);
@@ -36,6 +36,23 @@ static int run(const ll_graph &g, int nn, const std::vector<dp> &x, const char *
             if (z != want) { std::printf(" %s: Setting or getting matrix entry (%d,%d) failed: %g\n", name, i, j, z); return 1; }
         }
     }
+    // rows and columns (:158-219): every stored neighbour carries -1, the vertex itself degree - 1
+    std::vector<int32_t> nodes;
+    std::vector<dp> slice;
+    for (int dir = 0; dir < 2; dir++)
+        for (int i = 1; i <= nn; i++) {
+            if (dir == 0) L->get_row(nodes, slice, i); else L->get_column(nodes, slice, i);
+            if ((int)nodes.size() != g.get_degree(i)) { std::printf(" %s: Getting matrix %s %d failed: %zu entries\n", name, dir ? "column" : "row", i, nodes.size()); return 1; }
+            for (size_t k = 0; k < nodes.size(); k++) {
+                const dp want = nodes[k] == i ? g.get_degree(i) - 1.0 : -1.0;
+                if (slice[k] != want || !g.connected(i, nodes[k])) { std::printf(" %s: Getting matrix %s failed at (%d,%d)\n", name, dir ? "column" : "row", i, nodes[k]); return 1; }
+            }
+        }
+    if (!on_device) {
+        if (verbose) std::printf(" o %s: entries, rows and columns work (host only)\n", name);
+        A.destroy();
+        return 0;
+    }
     std::vector<dp> y(nn), w(nn, 0.0);
     for (int i = 1; i <= nn; i++) {
         dp z = g.get_degree(i) * x[(size_t)i - 1];
@@ -54,7 +71,11 @@ static int run(const ll_graph &g, int nn, const std::vector<dp> &x, const char *
 
 int main(int argc, char **argv)
 {
-    const bool verbose = argc > 1 && (!std::strcmp(argv[1], "-v") || !std::strcmp(argv[1], "-V") || !std::strcmp(argv[1], "--verbose"));
+    bool verbose = false, on_device = true;
+    for (int a = 1; a < argc; a++) {
+        if (!std::strcmp(argv[a], "-v") || !std::strcmp(argv[a], "-V") || !std::strcmp(argv[a], "--verbose")) verbose = true;
+        if (!std::strcmp(argv[a], "--host-only")) on_device = false;
+    }
     rng64 rnd(2718);
     const int nn = 256;
     const dp c = std::log(1.0 * nn) / std::log(2.0) / nn;
@@ -68,8 +89,8 @@ int main(int argc, char **argv)
     if (verbose) std::printf(" o Done generating Erdos-Renyi graph: %d vertices, %d edges\n", nn, g.get_num_edges());
     std::vector<dp> x(nn);
     for (dp &v : x) v = rnd.next();
-    if (run<csr_matrix>(g, nn, x, "csr", verbose)) return 1;
-    if (run<csc_matrix>(g, nn, x, "csc", verbose)) return 1;
-    if (run<ellpack_matrix>(g, nn, x, "ellpack", verbose)) return 1;
+    if (run<csr_matrix>(g, nn, x, "csr", verbose, on_device)) return 1;
+    if (run<csc_matrix>(g, nn, x, "csc", verbose, on_device)) return 1;
+    if (run<ellpack_matrix>(g, nn, x, "ellpack", verbose, on_device)) return 1;
     return 0;
 }

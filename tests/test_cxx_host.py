@@ -67,3 +67,14 @@ def test_permutations_host_side():
                        capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("right and left permutation work") == 3
+
+
+def test_strategy_host_side():
+    """test/matrix_test_strategy.f90 up to its matvec: entries through the 1 x 1 composite, rows and
+    columns through the storage strategy (get_row / get_column), all host-side reads -- run here
+    without a GPU (--host-only); the matvec part runs with the gated programs."""
+    build()
+    r = subprocess.run([os.path.join(CXX, "_build", "matrix_test_strategy"), "-v", "--host-only"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("entries, rows and columns work") == 3
