@@ -147,6 +147,18 @@ def workload(N):
             f"b=A*rand(seed 12345), tol=1e-10*|b|")
 
 
+def config_dict(N, world):
+    """`config` of the JSON line, identical on both arms for a given N and --gpus."""
+    n = N * N
+    mat_mb = (12 * (5 * n - 4 * N) + 4 * n) / world / 1e6
+    vec_mb = 8 * n / world / 1e6
+    return {"workload": workload(N),
+            "sharding": f"contiguous row blocks over {world} GPU(s)",
+            "l2": f"inputs larger than L2: per GPU {mat_mb:.0f} MB of matrix arrays + 5 vectors of {vec_mb:.0f} MB "
+                  f"touched every iteration (L2: 126 MB)",
+            "step": "one CG iteration"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -154,13 +166,14 @@ def run_reference(args):
     N = args.grid
     # bounded sample: one full-size iteration costs ~0.3-0.6 s on one core
     steps = min(args.steps, 60)
-    rate, it, t = cpu_cg_rate(N, steps, warm=min(args.warmup, 2))
+    warm = max(0, min(args.warmup, 10))
+    rate, it, t = cpu_cg_rate(N, steps, warm=warm)
     n = N * N
     out = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": it, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 / rate, "higher_is_better": True,
+        "steps": it, "warmup": warm, "ms_per_step": 1e3 / rate, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload(N)},
+        "config": config_dict(N, args.gpus),
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
                          "sample": f"{it} full-size CG iterations of the serial C restatement of cg_solve "
                                    f"(gcc -O2 -ffp-contract=off), init pass subtracted; reference is serial Fortran, "
@@ -169,6 +182,95 @@ def run_reference(args):
     }
     print(json.dumps(out), flush=True)
 
+
+
+# ---------------------------------------------------------------------------
+# parity gate (last row): runs UNTIMED before every benchmark, at every N, on a
+# parity-sized instance sharded / transported / solved by the same kernels as the full-size run.
+# The oracle is the checker here, never the thing measured.
+# ---------------------------------------------------------------------------
+PARITY_GRID = 256
+
+
+def parity_gate(world, rank, dev, comm, persistent, dist):
+    """Poisson PARITY_GRID^2 over `world` GPUs against the serial oracle:
+      * index work bit-exact: partition, halo list, send lists (the halo lists' mirror image)
+      * sharded SpMV and SpMV-add array_equal with the serial reference loop
+      * CG: iterations within 2 %, ||x - x_orc|| / ||x_orc|| <= 1e-10, same stopping iteration on every rank
+    `persistent` is the loop form the full-size run takes (forced here so the same kernels are checked).
+    Returns the dict printed as "parity"; every rank returns the same verdict."""
+    import torch
+
+    import oracle as orc
+    import sigma_b200 as sb
+    from sigma_b200 import distributed as D
+    from sigma_b200 import generators as G
+
+    Np = PARITY_GRID
+    n = Np * Np
+    ptr, node, val = G.poisson2d_csr(Np)
+    b, _ = G.poisson2d_rhs(Np)
+    O = orc.Matrix(orc.CSR, n, n, node, val, ptr=ptr)
+    res = {"instance": f"2D Poisson {Np}x{Np} CSR over {world} GPU(s)", "cg_form": "persistent" if persistent else "kernel-per-phase"}
+    lo, hi = 0, n
+    if world > 1:
+        part = D.partition_rows(ptr, world)
+        res["partition_bit_exact"] = bool(np.array_equal(part, orc.partition_rows(ptr, world)))
+        lo, hi = int(part[rank]), int(part[rank + 1])
+        sl = slice(ptr[lo] - 1, ptr[hi] - 1)
+        A = D.dist_csr_matrix(comm, n, part, ptr[lo:hi + 1], node[sl], val[sl])
+        ohalo, olocal = orc.halo_build(lo, hi, ptr, node)
+        res["halo_bit_exact"] = bool(np.array_equal(A.plan.halo, ohalo) and np.array_equal(A.plan.local_node, olocal))
+        # send list towards q = the part of q's halo that falls into our rows, as local 1-based rows
+        want = []
+        for q in range(world):
+            if q == rank:
+                continue
+            hq, _ = orc.halo_build(int(part[q]), int(part[q + 1]), ptr, node)
+            want.append(hq[(hq > lo) & (hq <= hi)] - lo)
+        want = np.concatenate(want).astype(np.int32) if want else np.zeros(0, np.int32)
+        res["send_lists_bit_exact"] = bool(np.array_equal(A.plan.send_rows, want))
+    else:
+        A = sb.csr_matrix(n, n, ptr, node, val)
+    rng = np.random.default_rng(77)
+    x, y0 = rng.standard_normal(n), rng.standard_normal(n)
+    ok = True
+    for _ in range(2):                      # twice: both halo landing buffers
+        ok = ok and np.array_equal(A.matvec(x[lo:hi]), orc.matvec(O, x)[lo:hi])
+        x = np.cos(x)
+    ok = ok and np.array_equal(A.matvec_add(x[lo:hi], y0[lo:hi]), orc.matvec_add(O, x, y0)[lo:hi])
+    res["spmv_bit_exact"] = bool(ok)
+
+    tol = 1e-10 * float(np.linalg.norm(b))
+    xo, ito, _, _ = orc.cg_solve(O, np.zeros(n), b, tol)
+    s = sb.cg(tol)
+    s.set_persistent(1 if persistent else 0)
+    s.setup(A)
+    xl = s.solve(A, np.zeros(hi - lo), b[lo:hi])
+    it, _, capped = s.info()
+    err2 = float(np.sum((xl - xo[lo:hi]) ** 2))
+    its = [it]
+    if world > 1:
+        t = torch.tensor([err2], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        err2 = float(t.item())
+        its = [None] * world
+        dist.all_gather_object(its, it)
+    relerr = float(np.sqrt(err2) / np.linalg.norm(xo))
+    res.update({"cg_iterations": int(it), "cg_iterations_oracle": int(ito),
+                "cg_iterations_within_2pct": bool(not capped and abs(it - ito) <= max(1, int(np.ceil(0.02 * ito)))),
+                "cg_same_iteration_on_all_ranks": bool(len(set(its)) == 1),
+                "cg_solution_rel_err": relerr, "cg_solution_within_1e-10": bool(relerr <= 1e-10)})
+    s.destroy()
+    A.destroy()
+    flags = [v for k, v in res.items() if isinstance(v, bool)]
+    good = all(flags)
+    if world > 1:                            # one verdict for the job
+        t = torch.tensor([1.0 if good else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        good = bool(t.item() > 0.5)
+    res["ok"] = good
+    return res
 
 # ---------------------------------------------------------------------------
 # our arm
@@ -276,7 +378,25 @@ def run_ours(args):
         y_dev = torch.empty(nloc, dtype=torch.float64, device=dev)
     stream.synchronize()
 
+    # the loop form the library takes at this shard size (csrc/solvers.cu persistent_enabled), named
+    # explicitly so that the parity gate below checks the same kernels on its small instance
+    forced = os.environ.get("SIGB_CG_PERSISTENT")
+    persistent = (nloc <= 3_000_000) if forced is None else (int(forced) != 0)
+    persistent = persistent and transport != "nccl"
+    parity = None
+    if not args.no_parity:
+        parity = parity_gate(world, rank, dev, ctx.comm if world > 1 else None, persistent, dist)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "n_gpus": world, "parity": parity,
+                                  "error": "parity gate failed: no benchmark number is reported"}), flush=True)
+            if world > 1:
+                dist.barrier()
+                dist.destroy_process_group()
+            raise SystemExit(1)
+
     solver = sb.cg(tol)
+    solver.set_persistent(1 if persistent else 0)
     solver.setup(A)
 
     def barrier():
@@ -384,9 +504,11 @@ def run_ours(args):
     # (SURVEY 8d counts 92 n for the reference's statement order; reading p once for both the x and
     #  the p update saves 8 n with identical arithmetic.)
     bytes_cg_glob = 12 * nnz_glob + 84 * n + 4
+    # dram bytes of one launch from the committed ncu capture: taken at 1 GPU and full size, so it is
+    # only meaningful for that launch shape (null otherwise)
     traffic = None
     tfile = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tfile):
+    if world == 1 and N == 4096 and os.path.exists(tfile):
         try:
             traffic = json.load(open(tfile)).get("csr_stream_kernel_dot_bytes_per_launch")
         except Exception:
@@ -398,16 +520,16 @@ def run_ours(args):
             "metric": METRIC, "value": cg_rate, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_cg / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload(N),
-                       "sharding": f"contiguous row blocks over {world} GPU(s), halo + dot all-reduce transport: {transport}",
-                       "l2": "inputs larger than L2 (matrix 1.0 GB + 5 vectors of 134 MB per solve)",
-                       "step": "one CG iteration (3 kernels)"},
+            "config": config_dict(N, world),
+            "transport": transport,
+            "cg_form": "one persistent cooperative kernel" if persistent else "three kernels per iteration",
             "clocks": clk.summary(),
             "e2e": {"value": e2e_rate, "unit": UNIT, "h2d_bytes_per_step": 16 * nloc / K,
                     "d2h_bytes_per_step": 8 * nloc / K,
                     "note": f"sigb_solver_solve with pinned host x,b: H2D x0+b, {K} iterations, D2H x; "
                             f"final |r| = {res_e2e:.3e}"},
             "gpu_launches": int(launches),
+            "parity": parity,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic,
                          "kernel": "csr_tma_kernel<MODE_SET,NDOT=1,HALO=%d> (q = A p fused with p.q)" % (1 if world > 1 else 0),
@@ -722,6 +844,7 @@ def main():
     ap.add_argument("--grid", type=int, default=4096)
     ap.add_argument("--cpu-iters", type=int, default=30)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed parity gate (kernel A/B runs only)")
     ap.add_argument("--quick", action="store_true", help="kernel A/B runs: print a short line, skip e2e and the CPU leg")
     ap.add_argument("--rows", default="headline", choices=["headline", "widened", "ldu"],
                     help="headline: the contract line (default); widened / ldu: the SURVEY 8f rows, one JSON line each")

@@ -312,6 +312,13 @@ SIGB_API int sigb_solver_set_params(sigb_solver_t s, double tolerance);
  * cg_solvers.f90:133).  cap < 0 (default) = no cap.  A capped solve still
  * returns SIGB_OK; query it with sigb_solver_get_info. */
 SIGB_API int sigb_solver_set_max_iterations(sigb_solver_t s, int64_t cap);
+/* NOT in the reference: which form of the CG loop (cg_solvers.f90:133-146)
+ * runs -- 1: the whole loop as ONE persistent cooperative kernel, 0: three
+ * kernels per iteration, -1 (default): the library chooses by shard size
+ * (persistent at <= 3 M rows per GPU).  Same recurrence, statement order and
+ * rounding either way; bench.py's parity gate uses it to check the small
+ * instance with the kernels the full-size run takes. */
+SIGB_API int sigb_solver_set_persistent(sigb_solver_t s, int mode);
 
 /* solver%solve(A, x, b [, pc]): linear_solve / linear_solve_pc
  * (cg_solve cg_solvers.f90:116-150, cg_solve_pc :155-194, bicgstab_solve

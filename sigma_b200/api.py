@@ -325,6 +325,10 @@ class Solver:
     def set_max_iterations(self, cap: int):
         check(lib().sigb_solver_set_max_iterations(self._h, int(cap)))
 
+    def set_persistent(self, mode: int):
+        """CG loop form: 1 one persistent kernel, 0 three kernels per iteration, -1 the library's choice."""
+        check(lib().sigb_solver_set_persistent(self._h, int(mode)))
+
     def solve(self, A: Matrix, x, b, pc: "Solver | None" = None):
         """call solver%solve(A, x, b [, pc]); x is the initial guess, returns the solution."""
         x, b = as_f64(x).copy(), as_f64(b)

@@ -656,6 +656,13 @@ int sigb_solver_set_max_iterations(sigb_solver_t s, int64_t cap)
     return SIGB_OK;
 }
 
+int sigb_solver_set_persistent(sigb_solver_t s, int mode)
+{
+    SIGB_REQUIRE(s && mode >= -1 && mode <= 1, SIGB_ERR_ARG, "sigb_solver_set_persistent: bad argument");
+    s->persistent = mode;
+    return SIGB_OK;
+}
+
 int sigb_solver_setup(sigb_solver_t s, sigb_matrix_t A)
 {
     SIGB_REQUIRE(s && A, SIGB_ERR_ARG, "sigb_solver_setup: bad argument");

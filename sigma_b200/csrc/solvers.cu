@@ -659,8 +659,9 @@ static int finish_solve(sigb_solver_t s)
 // slower than the dedicated kernels, which wins when an iteration is long.
 // Measured cross-over on B200 (profiles/r1_size_sweep_persistent.jsonl): ~3 M
 // rows per GPU.  SIGB_CG_PERSISTENT=1 / 0 forces one or the other.
-static bool persistent_enabled(int64_t n_local, int nranks)
+static bool persistent_enabled(int64_t n_local, int nranks, int solver_choice)
 {
+    if (solver_choice >= 0) return solver_choice != 0;   // sigb_solver_set_persistent
     static int v = -2;
     if (v == -2) {
         const char *e = getenv("SIGB_CG_PERSISTENT");
@@ -812,7 +813,7 @@ static int cg_solve_body(sigb_solver_t s, sigb_matrix_t A, double *x, const doub
         DotSpec halo;
         bool eligible = true;
         SIGB_CHECK(dist_persist_info(A, &pcomm, &halo, &eligible));
-        eligible = eligible && persistent_enabled(n, pcomm.nranks);
+        eligible = eligible && persistent_enabled(n, pcomm.nranks, s->persistent);
         if (eligible && !A->op) {   // operator expressions run kernel-per-phase
             sigb_graph_t g = A->g;
             if (g->kind == G_CSR) {

@@ -16,6 +16,7 @@ struct sigb_solver_s {
     bool params_set = false;
     bool initialized = false;  // work vectors allocated (cg_setup :78-81)
     int64_t cap = -1;          // safety cap per solve (not in the reference)
+    int persistent = -1;       // CG loop form: -1 library's choice, 0 kernel per phase, 1 one persistent kernel
     int32_t nn = 0;            // solver%nn: owned rows
     int64_t nvec = 0;          // allocated length of each work vector (nn + halo room)
     int64_t iterations = 0;    // solver%iterations (accumulates until the next setup)
