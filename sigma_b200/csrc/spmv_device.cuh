@@ -309,6 +309,130 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
     if (!pipe.primed && tid == 0 && t < a.ntiles && tile_staged(d_cur)) issue((int)(sidx & 1u), d_cur);
     pipe.primed = false;
 
+#ifdef SIGB_SPMV_PIPE
+    // ---- software-pipelined two-pass form (build variant _pipe) -------------------------------
+    // The x gathers of tile t are issued BEFORE the row sums of tile t-1 are formed, so that the
+    // latency of the gathers (one in five is the first touch of an x line and comes from HBM, not
+    // from L1/L2) overlaps the row sums, the y stores and the barrier of the previous tile instead
+    // of stalling the product pass; the gathered values wait in registers.  Same rounded products,
+    // added in the same stored order: results are bit-identical to the unpipelined form.
+    //   iteration t:  wait stage(t) | gather x for t | row sums of t-1 | barrier (stage(t-1) free)
+    //                 | TMA for t+1 into stage(t-1) | products of t into stage(t) | barrier
+    if (!RD) {
+        bool pending = false;              // a tile whose products are parked and whose rows are not summed yet
+        int4 d_pend = make_int4(0, 0, 0, 0);
+        int stage_pend = 0;
+        auto row_sums = [&](const int4 &d, int stage) {
+            unsigned char *base = smem + stage * kStageBytes;
+            const double *sval = reinterpret_cast<const double *>(base);
+            const int32_t *sptr = reinterpret_cast<const int32_t *>(base + kStageVal + kStageNode);
+            const int rs = d.x, re = d.y, ka = d.z & ~3, ra = d.x & ~3;
+            double ur[kTileRows / kThreads];
+#pragma unroll
+            for (int i = 0; i < kTileRows / kThreads; i++) {
+                const int r = rs + tid + i * kThreads;
+                ur[i] = (NDOT >= 1 && r < re) ? ld_x<XNC>(a.u + r) : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < kTileRows / kThreads; i++) {
+                const int r = rs + tid + i * kThreads;
+                if (r < re) {
+                    const int b = sptr[r - ra] - 1 - ka, e = sptr[r + 1 - ra] - 1 - ka;
+                    double z = (MODE == MODE_ACC_INIT) ? a.y[r] : 0.0;
+                    for (int k = b; k < e; k++) z = add(z, sval[k]);
+                    emit_row<MODE, NDOT>(a, r, z, ur[i], acc);
+                }
+            }
+            fence_proxy_async();           // the stage is overwritten by the async proxy next
+        };
+        for (; t < a.ntiles; t += gridDim.x) {
+            const int tn = t + gridDim.x, tnn = tn + gridDim.x;
+            const bool have_next = tn < a.ntiles;
+            int4 d_next2 = make_int4(0, 0, 0, 0);
+            if (tnn < a.ntiles) d_next2 = load_desc(a.tiles + tnn);
+            const bool staged = tile_staged(d_cur);
+            if (HALO && !halo_ready && t >= a.first_halo_tile) {   // CTA-uniform, as in the unpipelined form
+                if (LL) {
+                    hll = reinterpret_cast<const RedEntry *>(a.sync.halo_base) + (hseq & 1) * a.sync.halo_stride -
+                          (a.nloc + 1);
+                } else {
+                    if (push_pending) publish_push();
+                    if (tid == 0) {
+                        for (int q = 0; q < kMaxRanks; q++)
+                            if (a.sync.src_mask & (1u << q)) {
+                                unsigned spins = 0;
+                                while (ld_acquire_sys(&a.sync.win->hflag[hseq & 1][q]) < hseq && ++spins < kSpinLimit) {}
+                            }
+                    }
+                    __syncthreads();
+                    h1 = a.sync.halo_base + (hseq & 1) * a.sync.halo_stride - (a.nloc + 1);
+                }
+                halo_ready = true;
+            }
+            if (staged) {
+                const int stage = (int)(sidx & 1u);
+                unsigned char *base = smem + stage * kStageBytes;
+                double *sval = reinterpret_cast<double *>(base);
+                const int32_t *snode = reinterpret_cast<const int32_t *>(base + kStageVal);
+                const int ks = d_cur.z, ke = d_cur.w, ka = ks & ~3;
+                const int cnt = ke - ka;
+                mbar_wait(&mbar[stage], (sidx >> 1) & 1u);
+                int c[kTileNnz / kThreads];
+                double xv[kTileNnz / kThreads];
+#pragma unroll
+                for (int i = 0; i < kTileNnz / kThreads; i++) {
+                    const int k = tid + i * kThreads;
+                    c[i] = (k < cnt) ? snode[k] : 1;
+                }
+                if (LL && HALO && t >= a.first_halo_tile) {
+#pragma unroll
+                    for (int i = 0; i < kTileNnz / kThreads; i++) {
+                        const int k = tid + i * kThreads;
+                        xv[i] = (c[i] > a.nloc && k >= ks - ka && k < cnt) ? halo_ll_load(hll + c[i], (unsigned)hseq)
+                                                                           : __ldcg(a.x1 + min(c[i], a.nloc));
+                    }
+                } else if (HALO && t >= a.first_halo_tile) {
+#pragma unroll
+                    for (int i = 0; i < kTileNnz / kThreads; i++) {
+                        const double *src = (c[i] > a.nloc) ? h1 + c[i] : a.x1 + c[i];
+                        xv[i] = __ldcg(src);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < kTileNnz / kThreads; i++) xv[i] = ld_x<XNC>(a.x1 + c[i]);
+                }
+                if (pending) row_sums(d_pend, stage_pend);     // ... while the gathers are in flight
+                __syncthreads();                               // the other stage has been consumed by everybody
+                if (tid == 0 && have_next && tile_staged(d_next)) issue((int)((sidx + 1u) & 1u), d_next);
+#pragma unroll
+                for (int i = 0; i < kTileNnz / kThreads; i++) {
+                    const int k = tid + i * kThreads;
+                    if (k < cnt) sval[k] = mul(sval[k], xv[i]);
+                }
+                __syncthreads();
+                pending = true;
+                d_pend = d_cur;
+                stage_pend = stage;
+                sidx++;
+            } else {
+                if (pending) {
+                    row_sums(d_pend, stage_pend);
+                    __syncthreads();
+                    pending = false;
+                }
+                if (tid == 0 && have_next && tile_staged(d_next)) issue((int)(sidx & 1u), d_next);   // both stages are free
+                long_row<MODE, NDOT, HALO, XNC, LL>(a, d_cur, h1, acc, hll, (unsigned)hseq);
+            }
+            d_cur = d_next;
+            d_next = d_next2;
+            if (HALO && push_pending) publish_push();
+        }
+        if (pending) {
+            row_sums(d_pend, stage_pend);
+            __syncthreads();
+        }
+    }
+#endif
     for (; t < a.ntiles; t += gridDim.x) {
         const int tn = t + gridDim.x, tnn = tn + gridDim.x;
         const bool have_next = tn < a.ntiles;
