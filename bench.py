@@ -275,7 +275,7 @@ def parity_gate(world, rank, dev, comm, persistent, dist):
 # ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
-PHASES = ("spmv", "barrier1", "xgpu1", "r_update", "barrier2", "xgpu2", "p_update", "barrier3")
+PHASES = ("spmv", "barrier1", "sum_xgpu1", "r_update", "barrier2", "sum_xgpu2", "p_update", "barrier3")
 
 
 def phase_report(rank, ms_per_iter):
@@ -318,7 +318,8 @@ def spmv_tile_report(rank, us_per_launch):
     if not ok.value or us_per_launch is None or not buf[3]:
         return
     tot = float(buf[3])
-    print(json.dumps({"spmv_cta_pass": {"wait_tma": buf[0] / tot, "products": buf[1] / tot, "row_sums": buf[2] / tot,
+    print(json.dumps({"spmv_cta_pass": {"wait_tma": buf[0] / tot, "gathers_issued_and_row_sums_of_previous_tile": buf[1] / tot,
+                                        "products_incl_gather_wait": buf[2] / tot,
                                         "other": 1.0 - (buf[0] + buf[1] + buf[2]) / tot,
                                         "cycles_per_tile": tot / max(buf[4], 1), "tiles_per_cta_pass": buf[4] / max(buf[5], 1)},
                       "rank": rank, "us_per_launch": us_per_launch}), file=sys.stderr, flush=True)
@@ -381,7 +382,7 @@ def run_ours(args):
     # the loop form the library takes at this shard size (csrc/solvers.cu persistent_enabled), named
     # explicitly so that the parity gate below checks the same kernels on its small instance
     forced = os.environ.get("SIGB_CG_PERSISTENT")
-    persistent = (nloc <= 3_000_000) if forced is None else (int(forced) != 0)
+    persistent = (nloc <= (4_500_000 if world > 1 else 4_000_000)) if forced is None else (int(forced) != 0)
     persistent = persistent and transport != "nccl"
     parity = None
     if not args.no_parity:

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "device_utils.cuh"
 #include "dist.h"
 #include "internal.h"
 #include "solvers.h"
@@ -42,20 +43,36 @@ int require_init()
     return SIGB_OK;
 }
 
+int check_fault(const char *where)
+{
+    const Ctx &c = ctx();
+    if (c.fault == nullptr) return SIGB_OK;
+    const unsigned code = *reinterpret_cast<volatile unsigned int *>(&c.fault->code);
+    if (code == 0u) return SIGB_OK;
+    static const char *what[] = {"", "a grid barrier", "an all-reduce inbox", "a halo acknowledgement", "a halo flag",
+                                 "a sync-free sweep"};
+    set_error("%s: a device-side wait on %s timed out (a peer GPU is late or gone, or a kernel was descheduled); "
+              "results since then are invalid and the row-sharded operators of this process are unusable",
+              where, code < sizeof(what) / sizeof(what[0]) ? what[code] : "a flag");
+    return SIGB_ERR_COMM;
+}
+
+// Short-lived device scratch of the copy / transpose / assembly entry points comes from the
+// device's default memory pool, stream-ordered on the library's stream, with the release
+// threshold lifted so that freed blocks stay cached: cudaMalloc / cudaFree synchronise the whole
+// device per call, which was most of a transposing copy (round 2: 12.7 ms -> 4.9 ms for 21 M
+// entries, profiles/r2_visit_a_1gpu_summary.txt).  Falls back to cudaMalloc when the driver has no pool.
 static bool async_alloc_enabled()
 {
     static int v = -1;
     if (v < 0) {
-        v = env_int("SIGB_ASYNC_ALLOC", 0) == 1 ? 1 : 0;
-        if (v) {
-            // keep freed blocks in the pool instead of returning them at every synchronisation
-            cudaMemPool_t pool = nullptr;
-            unsigned long long keep = ~0ull;
-            if (cudaDeviceGetDefaultMemPool(&pool, ctx().device) != cudaSuccess ||
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess) {
-                cudaGetLastError();
-                v = 0;
-            }
+        v = 1;
+        cudaMemPool_t pool = nullptr;
+        unsigned long long keep = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx().device) != cudaSuccess ||
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess) {
+            cudaGetLastError();
+            v = 0;
         }
     }
     return v != 0;
@@ -146,17 +163,9 @@ static int ensure_graph_transposed(sigb_graph_t g)
     t.ptr = ptr_t;
     t.node = node_t;
     g->perm_t = perm;
-    if (device_tiles_enabled()) {
-        // EXPERIMENTAL (SIGB_DEVICE_TILES=1): no read-back of ptr, no host loop
-        SIGB_CHECK(build_tiles_device(ptr_t, ntargets, t, nullptr, nullptr));
-    } else {
-        g->host_ptr_t.resize((size_t)ntargets + 1);
-        SIGB_CUDA(cudaMemcpy(g->host_ptr_t.data(), ptr_t, sizeof(int32_t) * ((size_t)ntargets + 1),
-                             cudaMemcpyDeviceToHost));
-        std::vector<TileDesc> tiles;
-        build_tiles_host(g->host_ptr_t.data(), ntargets, tiles);
-        SIGB_CHECK(upload_tiles(t, tiles));
-    }
+    // the tile table is built on the device from the device-resident ptr (tiles_device.cu): no
+    // read-back, no host loop
+    SIGB_CHECK(build_tiles_device(ptr_t, ntargets, t, nullptr, nullptr));
     g->has_transposed = true;
     return SIGB_OK;
 }
@@ -266,6 +275,12 @@ int sigb_init(int device)
     SIGB_CUDA(cudaMemset(c.tickets, 0, sizeof(unsigned) * kNumTickets));
     c.pinned_bytes = 1 << 16;
     SIGB_CUDA(cudaMallocHost(&c.pinned, c.pinned_bytes));
+    // device-side wait timeouts (device_utils.cuh spin_wait): one block in mapped pinned memory
+    SIGB_CUDA(cudaHostAlloc((void **)&c.fault, sizeof(FaultBlock), cudaHostAllocMapped));
+    c.fault->code = 0u;
+    c.fault->pad_ = 0u;
+    c.fault->limit_ns = (unsigned long long)std::max(1, env_int("SIGB_WAIT_TIMEOUT_MS", 30000)) * 1000000ull;
+    SIGB_CUDA(cudaHostGetDevicePointer((void **)&c.fault_dev, c.fault, 0));
     c.launches = 0;
     c.inited = true;
     return SIGB_OK;
@@ -279,6 +294,7 @@ int sigb_finalize(void)
     cudaFree(c.partials);
     cudaFree(c.tickets);
     cudaFreeHost(c.pinned);
+    cudaFreeHost(c.fault);
     cudaStreamDestroy(c.own_stream);
     cudaStreamDestroy(c.aux_stream);
     c = Ctx();
@@ -296,7 +312,7 @@ int sigb_synchronize(void)
 {
     SIGB_CHECK(require_init());
     SIGB_CUDA(cudaStreamSynchronize(ctx().stream));
-    return SIGB_OK;
+    return check_fault("sigb_synchronize");
 }
 
 int64_t sigb_launch_count(void) { return ctx().launches; }
@@ -716,11 +732,11 @@ int sigb_solver_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x_dev, const
     SIGB_REQUIRE(s->nn == A->nrow, SIGB_ERR_ARG, "sigb_solver_solve: solver was set up for nn = %d, operator has %d rows",
                  s->nn, A->nrow);
     if (pc) {
-        // EXPERIMENTAL opt-in: bicgstab with the ldu preconditioner (solvers.cu), not yet run on a GPU
-        static const bool bicg_ldu = env_int("SIGB_BICGSTAB_LDU", 0) == 1;
-        const bool ldu_ok = pc->kind == S_LDU && !A->dist && (s->kind == S_CG || (s->kind == S_BICGSTAB && bicg_ldu));
+        // linear_solve_pc takes any linear_solver as pc (linear_operator_interface.f90:238-254): jacobi and
+        // ldu behind cg and bicgstab (ldu on one GPU only: its sweeps are not row-sharded)
+        const bool ldu_ok = pc->kind == S_LDU && !A->dist && (s->kind == S_CG || s->kind == S_BICGSTAB);
         SIGB_REQUIRE(pc->kind == S_JACOBI || ldu_ok, SIGB_ERR_UNSUPPORTED,
-                     "sigb_solver_solve: the device preconditioners are jacobi (cg, bicgstab) and ldu (cg, one GPU)");
+                     "sigb_solver_solve: the device preconditioners are jacobi and ldu (ldu on one GPU only)");
         SIGB_REQUIRE(pc->initialized && pc->nn == s->nn, SIGB_ERR_STATE,
                      "sigb_solver_solve: pc%%setup(A) has not been called");
     }

@@ -77,7 +77,6 @@ struct DistInfo {
     // peer-memory transport
     HaloWin *win = nullptr;         // our window (flags + two landing buffers)
     int64_t stride = 0;             // entries between the two landing buffers
-    bool ll = false;                // EXPERIMENTAL (SIGB_HALO_LL=1): entries are 16-byte payload+flag records
     HaloSync sync;                  // what boundary launches need
 };
 
@@ -127,6 +126,7 @@ struct RedArgs {
     RedWin *peer[kMaxRanks];
     int me, nranks;
     const int *skip_flag;
+    FaultBlock *fault;
 };
 
 // One warp.  Lane q < nranks stores this rank's partial sums into rank q's
@@ -144,23 +144,13 @@ __global__ void red_kernel(const RedArgs a)
     const unsigned int flag = (unsigned int)s;
     if (lane < a.nranks) {
         RedEntry *e = a.peer[lane]->red[slot][a.me];
-        for (int c = 0; c < a.count; c++) {
-            const unsigned long long bits = (unsigned long long)__double_as_longlong(*a.vals[c]);
-            st_word(&e[c].lo, (unsigned int)bits, flag);
-            st_word(&e[c].hi, (unsigned int)(bits >> 32), flag);
-        }
+        for (int c = 0; c < a.count; c++) red_entry_store(&e[c], *a.vals[c], flag);
     }
     __syncwarp();
     if (lane < a.count) {
         double v = 0.0;
-        for (int q = 0; q < a.nranks; q++) {   // rank order
-            const RedEntry *e = &a.win->red[slot][q][lane];
-            uint2 lo, hi;
-            unsigned spins = 0;
-            do { lo = ld_word(&e->lo); } while (lo.y != flag && ++spins < kSpinLimit);
-            do { hi = ld_word(&e->hi); } while (hi.y != flag && ++spins < kSpinLimit);
-            v = add(v, __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | lo.x)));
-        }
+        for (int q = 0; q < a.nranks; q++)   // rank order
+            v = add(v, red_entry_wait(&a.win->red[slot][q][lane], flag, a.fault));
         *a.vals[lane] = v;
     }
     __syncwarp();
@@ -199,7 +189,6 @@ int dist_persist_info(sigb_matrix_t A, PersistComm *pc, DotSpec *halo, bool *eli
     pc->me = C->rank;
     pc->nranks = C->nranks;
     if (D->total_send > 0 || D->nhalo > 0) halo->sync = &D->sync;
-    halo->halo_ll = D->ll;
     return SIGB_OK;
 }
 
@@ -237,6 +226,7 @@ static int allreduce_ptrs(sigb_comm_t C, double *const *vals, int count, const i
         a.me = C->rank;
         a.nranks = C->nranks;
         a.skip_flag = skip_flag;
+        a.fault = ctx().fault_dev;
         red_kernel<<<1, 32, 0, ctx().stream>>>(a);
         count_launch();
         SIGB_CUDA(cudaGetLastError());
@@ -249,19 +239,22 @@ static int allreduce_ptrs(sigb_comm_t C, double *const *vals, int count, const i
     return SIGB_OK;
 }
 
-// EXPERIMENTAL (SIGB_FUSED_ALLREDUCE=1, peer-memory transport only): endpoints for kernels that
-// finish their own reduction across the GPUs; false = use dist_allreduce after the kernel.
+// Peer-memory transport: endpoints for kernels that finish their own reduction across the GPUs
+// (the last CTA of the producing kernel stores the local sum into the peers' inboxes and adds the
+// ranks' contributions in rank order -- device_utils.cuh grid_reduce); false = NCCL transport or a
+// single rank, use dist_allreduce after the kernel.  Round-2 A/B at 2 GPUs, full size: 226.4 us per
+// CG iteration against 233.2 us with the separate one-warp launches (profiles/r2_visit_b_2gpu_summary.txt).
 bool dist_red_fuse(sigb_matrix_t A, RedFuse *rf)
 {
-    static const bool on = env_int("SIGB_FUSED_ALLREDUCE", 0) == 1;
     *rf = RedFuse();
     DistInfo *D = A->dist;
-    if (!on || !D || D->comm->nranks == 1 || !D->comm->p2p) return false;
+    if (!D || D->comm->nranks == 1 || !D->comm->p2p) return false;
     sigb_comm_t C = D->comm;
     rf->win = C->red;
     for (int q = 0; q < kMaxRanks; q++) rf->peer[q] = C->peer_red[q];
     rf->me = C->rank;
     rf->nranks = C->nranks;
+    rf->fault = ctx().fault_dev;
     return true;
 }
 
@@ -298,7 +291,6 @@ int dist_matvec(sigb_matrix_t A, const double *x, double *y, bool add, const Dot
         // ONE kernel does push + interior + (wait) + boundary + acknowledge
         DotSpec db = dot;
         db.sync = &D->sync;
-        db.halo_ll = D->ll;
         return launch_csr_spmv(V, A->val, x, y, mode, db, 0, main, 0);
     } else if (exchange) {
         if (D->total_send > 0) {
@@ -434,9 +426,17 @@ int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global, const int32_t *part
     SIGB_REQUIRE(comm && part && ptr_blk1 && out && send_counts, SIGB_ERR_ARG, "sigb_dist_csr_create: bad argument");
     const int P = comm->nranks, me = comm->rank;
     SIGB_REQUIRE(part[0] == 0 && part[P] == n_global, SIGB_ERR_ARG, "sigb_dist_csr_create: part must span 0..n_global");
+    for (int q = 0; q < P; q++)
+        SIGB_REQUIRE(part[q] <= part[q + 1], SIGB_ERR_ARG, "sigb_dist_csr_create: part must be monotone (part[%d] = %d > part[%d] = %d)",
+                     q, part[q], q + 1, part[q + 1]);
     const int32_t lo = part[me], hi = part[me + 1], nloc = hi - lo;
+    for (int32_t i = 0; i < nloc; i++)
+        SIGB_REQUIRE(ptr_blk1[i] <= ptr_blk1[i + 1], SIGB_ERR_ARG, "sigb_dist_csr_create: ptr must be monotone (row %d)", i + 1);
     const int64_t ne = (int64_t)ptr_blk1[nloc] - ptr_blk1[0];
     SIGB_REQUIRE(ne == 0 || node_glob1, SIGB_ERR_ARG, "sigb_dist_csr_create: null node array");
+    for (int64_t k = 0; k < ne; k++)
+        SIGB_REQUIRE(node_glob1[k] >= 1 && node_glob1[k] <= n_global, SIGB_ERR_ARG,
+                     "sigb_dist_csr_create: column id %d of entry %lld outside 1..%d", node_glob1[k], (long long)k + 1, n_global);
 
     DistInfo *D = new DistInfo();
     // an early return (bad argument, CUDA failure) releases what has been built so far
@@ -520,10 +520,7 @@ int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global, const int32_t *part
         // window = flags + two landing buffers; tell every rank where our slice
         // of ITS landing buffer starts (its recv offset for us) and its stride
         D->stride = ((int64_t)nhalo + 15) & ~15LL;
-        static const bool halo_ll = env_int("SIGB_HALO_LL", 0) == 1;   // every rank must agree (same environment)
-        D->ll = halo_ll;
-        const size_t entry = D->ll ? sizeof(RedEntry) : sizeof(double);
-        const size_t bytes = sizeof(HaloWin) + entry * 2 * (size_t)std::max<int64_t>(D->stride, 16);
+        const size_t bytes = sizeof(HaloWin) + sizeof(double) * 2 * (size_t)std::max<int64_t>(D->stride, 16);
         SIGB_CUDA(cudaMalloc((void **)&D->win, bytes));
         SIGB_CUDA(cudaMemsetAsync(D->win, 0, bytes, st));
         SIGB_CUDA(cudaStreamSynchronize(st));
@@ -539,6 +536,8 @@ int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global, const int32_t *part
         D->sync.halo_stride = D->stride;
         D->sync.send_rows = D->send_rows;
         D->sync.total_send = total_send;
+        // communication CTAs of the fused SpMV (spmv_device.cuh): ~8 entries per thread, at most 8 CTAs
+        D->sync.push_ctas = total_send > 0 ? std::min(8, (total_send + 8 * kThreads - 1) / (8 * kThreads)) : 0;
         for (int q = 0; q < kMaxRanks; q++) {
             D->sync.peer[q] = q < P ? (HaloWin *)peers[q] : nullptr;
             D->sync.dst[q] = nullptr;
@@ -552,10 +551,8 @@ int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global, const int32_t *part
                              "sigb_dist_csr_create: rank %d expects %d entries from rank %d, send list has %d", q,
                              all[q].recv_cnt[me], me, D->send_cnt[q]);
                 D->sync.dst_mask |= 1u << q;
-                // our slice of rank q's landing buffer 0 (LL: in records, the kernel re-casts the pointer)
-                D->sync.dst[q] = D->ll ? reinterpret_cast<double *>(reinterpret_cast<RedEntry *>((HaloWin *)peers[q] + 1) +
-                                                                     all[q].recv_off[me])
-                                       : reinterpret_cast<double *>((HaloWin *)peers[q] + 1) + all[q].recv_off[me];
+                // our slice of rank q's landing buffer 0
+                D->sync.dst[q] = reinterpret_cast<double *>((HaloWin *)peers[q] + 1) + all[q].recv_off[me];
                 D->sync.dst_stride[q] = all[q].stride;
             }
         }

@@ -207,29 +207,14 @@ int sigb_matrix_copy(sigb_matrix_t A, int format, int trans, sigb_matrix_t *B_ou
     }
     if (rc != SIGB_OK) { S.release(); T.release(); return rc; }
 
-    // the target's ptr on the host: tiling, max_d, empty-line check
-    // (EXPERIMENTAL, SIGB_DEVICE_TILES=1: all three come from the device instead, tiles_device.cu)
-    const bool dev_tiles = device_tiles_enabled();
-    std::vector<int32_t> hptr;
+    // tiling, max_d and the empty-line check come from the device-resident ptr (tiles_device.cu):
+    // no read-back, no host loop
     int32_t max_d = 0, min_d = INT32_MAX;
     CsrView dev_view;
-    if (dev_tiles) {
-        rc = build_tiles_device(T.ptr, T.nlines, dev_view, &max_d, &min_d);
-        if (rc != SIGB_OK) { S.release(); T.release(); return rc; }
-        if (T.nlines == 0) min_d = INT32_MAX;
-        S.release();
-    } else {
-        hptr.resize((size_t)T.nlines + 1);
-        cudaError_t e = cudaMemcpyAsync(hptr.data(), T.ptr, sizeof(int32_t) * hptr.size(), cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) { S.release(); T.release(); return cuda_fail(e, "matrix copy", __FILE__, __LINE__); }
-        S.release();
-        for (int32_t i = 0; i < T.nlines; i++) {
-            const int32_t d = hptr[(size_t)i + 1] - hptr[(size_t)i];
-            max_d = std::max(max_d, d);
-            min_d = std::min(min_d, d);
-        }
-    }
+    rc = build_tiles_device(T.ptr, T.nlines, dev_view, &max_d, &min_d);
+    if (rc != SIGB_OK) { S.release(); T.release(); return rc; }
+    if (T.nlines == 0) min_d = INT32_MAX;
+    S.release();
 
     sigb_graph_t g = new sigb_graph_s();
     sigb_matrix_t B = new sigb_matrix_s();
@@ -279,21 +264,10 @@ int sigb_matrix_copy(sigb_matrix_t A, int format, int trans, sigb_matrix_t *B_ou
         v.ptr = T.ptr;      // ownership moves to the graph / matrix
         v.node = T.node;
         B->val = T.val;
-        if (dev_tiles) {
-            v.tiles = dev_view.tiles;
-            v.ntiles = dev_view.ntiles;
-            v.tiles_nonempty = dev_view.tiles_nonempty;
-            v.n_nonempty = dev_view.n_nonempty;
-            rc = SIGB_OK;
-        } else {
-            std::vector<TileDesc> tiles;
-            build_tiles_host(hptr.data(), g->n, tiles);
-            rc = upload_tiles(v, tiles);
-        }
-        if (rc != SIGB_OK) {
-            sigb_matrix_destroy(B);
-            return rc;
-        }
+        v.tiles = dev_view.tiles;
+        v.ntiles = dev_view.ntiles;
+        v.tiles_nonempty = dev_view.tiles_nonempty;
+        v.n_nonempty = dev_view.n_nonempty;
     }
     *B_out = B;
     return SIGB_OK;

@@ -90,10 +90,77 @@ __device__ __forceinline__ uint2 ld_word(const unsigned int *p)
     return r;
 }
 
-// Bounded spinning: a peer that never answers must not hang the GPU (a hung
-// box is worse than a wrong answer that the host then reports).  ~1e8 polls of
-// an L2-resident word is several seconds.
-constexpr unsigned kSpinLimit = 1u << 27;
+// ---------------------------------------------------------------------------
+// Bounded waits.  Every device-side wait (grid barrier, all-reduce inbox, halo
+// flags and acknowledgements, sync-free sweeps) goes through spin_wait: it polls
+// flat out, and every 4096 polls looks at the clock and at the process-wide fault
+// word.  A wait that outlives FaultBlock::limit_ns (default 30 s, environment
+// SIGB_WAIT_TIMEOUT_MS) records its code in the fault word and gives up; once the
+// word is set every later wait gives up after its first 4096 polls, the persistent
+// kernels leave their loops, and the host turns the word into SIGB_ERR_COMM at
+// its next synchronisation (api.cu check_fault) -- a late or dead peer produces an
+// error, never a silently wrong result and never a hung GPU.  The block lives in
+// mapped pinned host memory: the host reads it without a copy, the device only
+// touches it on the slow path.
+// ---------------------------------------------------------------------------
+struct FaultBlock {
+    unsigned int code;               // 0 = healthy; else the first FaultCode that timed out (sticky)
+    unsigned int pad_;
+    unsigned long long limit_ns;     // how long a single wait may last
+};
+enum FaultCode : unsigned {
+    FAULT_GRID_BARRIER = 1, FAULT_ALLREDUCE = 2, FAULT_HALO_ACK = 3, FAULT_HALO_FLAG = 4, FAULT_LDU_SWEEP = 5
+};
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Slow path of spin_wait, out of line so that the polling loops stay small.
+// Returns false when the wait must be abandoned.
+static __device__ __noinline__ bool spin_check(FaultBlock *fb, unsigned long long *t0, unsigned code)
+{
+    if (fb == nullptr) return true;
+    if (*reinterpret_cast<volatile unsigned int *>(&fb->code) != 0u) return false;
+    const unsigned long long now = global_timer_ns();
+    if (*t0 == 0ull) { *t0 = now; return true; }
+    if (now - *t0 > *reinterpret_cast<volatile unsigned long long *>(&fb->limit_ns)) {
+        atomicCAS(&fb->code, 0u, code);
+        __threadfence_system();
+        return false;
+    }
+    return true;
+}
+
+// Polls ready() until it holds; false = gave up (fault recorded).
+template <class Ready>
+__device__ __forceinline__ bool spin_wait(Ready ready, FaultBlock *fb, unsigned code)
+{
+    unsigned spins = 0;
+    unsigned long long t0 = 0ull;
+    while (!ready()) {
+        if ((++spins & 0xfffu) == 0u && !spin_check(fb, &t0, code)) return false;
+    }
+    return true;
+}
+
+// One fp64 through an inbox entry: two payload+flag words (see RedEntry).
+__device__ __forceinline__ void red_entry_store(RedEntry *e, double v, unsigned int flag)
+{
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    st_word(&e->lo, (unsigned int)bits, flag);
+    st_word(&e->hi, (unsigned int)(bits >> 32), flag);
+}
+__device__ __forceinline__ double red_entry_wait(const RedEntry *e, unsigned int flag, FaultBlock *fb)
+{
+    uint2 lo = make_uint2(0u, 0u), hi = make_uint2(0u, 0u);
+    spin_wait([&] { lo = ld_word(&e->lo); return lo.y == flag; }, fb, FAULT_ALLREDUCE);
+    spin_wait([&] { hi = ld_word(&e->hi); return hi.y == flag; }, fb, FAULT_ALLREDUCE);
+    return __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | lo.x));
+}
 
 // Window of a row-sharded operator: everything peers write into this rank.
 struct HaloWin {
@@ -190,7 +257,7 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[ND], double *partials,
             }
             *ticket = 0u;
         }
-        // EXPERIMENTAL (SIGB_FUSED_ALLREDUCE=1): the cross-GPU part, by warp 0 of this last CTA --
+        // Row-sharded operators on the peer-memory transport: the cross-GPU part, by warp 0 of this last CTA --
         // what red_kernel (comm.cu) does in a launch of its own: lane q stores this rank's sums
         // into rank q's inbox as payload+flag words, lane d adds the nranks contributions to
         // value d in rank order (bit-identical totals on every rank) and overwrites *out[d].
@@ -202,26 +269,15 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[ND], double *partials,
 #pragma unroll
             for (int d = 0; d < ND; d++) {
                 const double local = __shfl_sync(0xffffffffu, v[d], 0);
-                if (lane < red->nranks) {
-                    RedEntry *e = red->peer[lane]->red[slot][red->me];
-                    const unsigned long long bits = (unsigned long long)__double_as_longlong(local);
-                    st_word(&e[d].lo, (unsigned int)bits, flag);
-                    st_word(&e[d].hi, (unsigned int)(bits >> 32), flag);
-                }
+                if (lane < red->nranks) red_entry_store(&red->peer[lane]->red[slot][red->me][d], local, flag);
             }
             __syncwarp();
 #pragma unroll
             for (int d = 0; d < ND; d++) {
                 if (lane == d) {
                     double g = 0.0;
-                    for (int q = 0; q < red->nranks; q++) {
-                        const RedEntry *e = &red->win->red[slot][q][d];
-                        uint2 lo, hi;
-                        unsigned spins = 0;
-                        do { lo = ld_word(&e->lo); } while (lo.y != flag && ++spins < kSpinLimit);
-                        do { hi = ld_word(&e->hi); } while (hi.y != flag && ++spins < kSpinLimit);
-                        g = add(g, __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | lo.x)));
-                    }
+                    for (int q = 0; q < red->nranks; q++)
+                        g = add(g, red_entry_wait(&red->win->red[slot][q][d], flag, red->fault));
                     *out[d] = g;
                 }
             }

@@ -56,9 +56,15 @@ struct Ctx {
     unsigned *tickets = nullptr;      // kNumTickets counters, zero between kernels
     void *pinned = nullptr;           // small pinned host staging area
     size_t pinned_bytes = 0;
+    // device-side wait timeouts (device_utils.cuh spin_wait): mapped pinned host memory
+    struct FaultBlock *fault = nullptr;       // host address
+    struct FaultBlock *fault_dev = nullptr;   // the same block as the device sees it
 };
 Ctx &ctx();
 int require_init();
+// SIGB_OK, or SIGB_ERR_COMM once a device-side wait has timed out (sticky: the row-sharded
+// state of this process can no longer be trusted).  Called wherever the host synchronises.
+int check_fault(const char *where);
 
 constexpr int kThreads = 256;          // every kernel in this library uses 256-thread CTAs
 constexpr int kMaxGrid = 148 * 16;     // upper bound on persistent grid sizes
@@ -195,19 +201,17 @@ struct DotSpec {
     // expression has already written), so rows without entries -- y(i) + 0.0 in
     // csr_matvec_add -- may be left untouched and tiles without entries skipped
     bool y_no_negative_zero = false;
-    // EXPERIMENTAL (SIGB_FUSED_ALLREDUCE=1): complete the cross-GPU part of the dot products
-    // inside this kernel (its last CTA) instead of a separate all-reduce launch
+    // row-sharded operators on the peer-memory transport: complete the cross-GPU part of the dot
+    // products inside this kernel (its last CTA) instead of a separate all-reduce launch
     const struct RedFuse *red = nullptr;
-    // EXPERIMENTAL (SIGB_HALO_LL=1): the landing buffers of `sync` hold payload+flag records
-    // (spmv_device.cuh); host-side choice of the kernel instantiation, not a kernel argument
-    bool halo_ll = false;
 };
 
 // Peer-memory halo exchange, fused into the SpMV kernel (comm.cu builds it).
-// Producer side: the first push_ctas CTAs store the owned entries other ranks
-// need straight into those ranks' landing buffers and publish a sequence
-// number.  Consumer side: a CTA waits for the peers' sequence numbers when it
-// reaches its first boundary tile; the last CTA acknowledges consumption.
+// Producer side: the first push_ctas CTAs of the grid (communication CTAs, no
+// tiles of their own) store the owned entries other ranks need straight into
+// those ranks' landing buffers and publish a sequence number.  Consumer side: a
+// CTA waits for the peers' sequence numbers when it reaches its first boundary
+// tile; the last CTA acknowledges consumption.
 constexpr int kMaxRanks = 8;
 struct HaloWin;  // device-resident, IPC-shared (device_utils.cuh)
 struct RedWin;   // all-reduce inbox, IPC-shared (device_utils.cuh)
@@ -217,6 +221,7 @@ struct RedFuse {
     RedWin *win = nullptr;                // this rank's inbox
     RedWin *peer[kMaxRanks] = {};         // every rank's inbox, peer-mapped (peer[me] == win)
     int me = 0, nranks = 1;
+    struct FaultBlock *fault = nullptr;   // wait timeouts (device_utils.cuh)
 };
 struct HaloSync {
     HaloWin *win = nullptr;               // this rank's window
@@ -229,8 +234,7 @@ struct HaloSync {
     // push plan
     const int32_t *send_rows = nullptr;   // 1-based owned rows, grouped by destination
     int32_t total_send = 0;
-    int32_t push_ctas = 0;
-    int32_t push_first = 0;               // first pushing CTA (experiment knob SIGB_PUSH_LAST: grid - push_ctas)
+    int32_t push_ctas = 0;                // communication CTAs (fixed when the operator is created)
     int32_t send_off[kMaxRanks + 1] = {};
     double *dst[kMaxRanks] = {};          // peer landing buffer 0, offset to our slice
     int64_t dst_stride[kMaxRanks] = {};
@@ -245,16 +249,8 @@ int launch_ell_spmv(int32_t n, int32_t n_pad, int32_t max_d,
                     const double *x, double *y, SpmvMode mode,
                     const DotSpec &dot);
 int build_tiles_host(const int32_t *ptr1, int32_t nrows, std::vector<TileDesc> &tiles);
-// Experiment knob SIGB_PUSH_LAST=1: the halo push is done by the LAST CTAs of the grid -- with
-// round-robin tiles they own one tile less than the first ones whenever the tile count is not a
-// multiple of the grid, which pays for the system-scope fence behind their push -- instead of the
-// first ones (the very last CTA is left out: it publishes the persistent kernel's reductions).  Returns the first pushing CTA for a grid / number of pushing CTAs.
-int32_t halo_push_first(int grid, int push_ctas);
-// EXPERIMENTAL (SIGB_SPMV_ROWDIRECT): whether the row-direct form of the streaming kernel is used for A
-bool spmv_rowdirect(const CsrView &A);
-// tiles_device.cu -- EXPERIMENTAL (SIGB_DEVICE_TILES=1): the same tiling built on the device
-// from a device-resident ptr (no read-back); also returns the extreme line lengths
-bool device_tiles_enabled();
+// tiles_device.cu: the same tiling built on the device from a device-resident ptr (no read-back);
+// also returns the extreme line lengths
 int build_tiles_device(const int32_t *ptr1_dev, int32_t nrows, CsrView &v, int32_t *max_d, int32_t *min_d);
 
 // ---------------------------------------------------------------------------
@@ -284,11 +280,9 @@ int fill_i32(int32_t *p, int64_t n, int32_t v);
 int fill_f64(double *p, int64_t n, double v);
 
 // ---------------------------------------------------------------------------
-// short-lived device scratch (api.cu).  Default: cudaMalloc / cudaFree.  EXPERIMENTAL
-// (SIGB_ASYNC_ALLOC=1, not yet run on a GPU): stream-ordered cudaMallocAsync / cudaFreeAsync
-// on the library's stream from the device's default pool, kept cached (no release
-// threshold), so a copy / transpose / assembly call does not pay a device-wide
-// synchronisation per temporary.
+// short-lived device scratch (api.cu): stream-ordered cudaMallocAsync / cudaFreeAsync on the
+// library's stream from the device's default pool, kept cached (no release threshold), so a
+// copy / transpose / assembly call does not pay a device-wide synchronisation per temporary.
 // ---------------------------------------------------------------------------
 cudaError_t tmp_alloc_bytes(void **p, size_t bytes);
 cudaError_t tmp_free(void *p);

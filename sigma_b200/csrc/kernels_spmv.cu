@@ -12,15 +12,15 @@
 //
 // CSR kernel ("stream" layout).  Rows are grouped on the host into tiles of at
 // most kTileCap stored entries and kTileRows rows.  A persistent CTA walks its
-// tiles round-robin; per tile
-//   stage  : the tile's slices of val / node / ptr are brought into shared
-//            memory by the TMA engine (cp.async.bulk, 1-D, completion on an
-//            mbarrier), double-buffered: the copy of tile t+1 is in flight
-//            while tile t is processed, and no register or thread is tied up
-//            by the HBM stream;
-//   phase 1: every entry is multiplied with its gathered x (L1/L2 hits) and
-//            the ROUNDED product replaces the value in shared memory;
-//   phase 2: one thread per row adds that row's products in STORED order.
+// tiles round-robin; per tile (spmv_device.cuh has the pipeline)
+//   stage   : the tile's slices of val / node / ptr are brought into shared
+//             memory by the TMA engine (cp.async.bulk, 1-D, completion on an
+//             mbarrier), double-buffered, so no register or thread is tied up
+//             by the HBM stream;
+//   gather  : every entry's x is gathered -- issued one tile ahead of the row
+//             sums, so the HBM latency of first-touch x lines is overlapped;
+//   product : the ROUNDED product replaces the value in shared memory;
+//   row sums: one thread per row adds that row's products in STORED order.
 // Because the product is rounded before it is added and the adds run in stored
 // order, every y(i) is bit-identical to the reference's serial loop
 // (z = z + val(k) * x(node(k)), no FMA) -- not merely within 1e-12.
@@ -37,12 +37,12 @@
 // register variant was removed.)
 //
 // Row-sharded operators (comm.cu, HALO = true) use the same kernel as a fused
-// compute + exchange step over NVLink peer memory: in its prologue the first few
-// CTAs store the owned x entries other ranks need straight into those ranks'
-// landing buffers and publish a sequence number; tiles are ordered interior
-// first, so the transfer overlaps the bulk of the work, and a CTA only waits on
-// its peers' sequence numbers when it reaches its first boundary tile, whose
-// gathers take columns beyond the owned range from the landing buffer.
+// compute + exchange step over NVLink peer memory: a few communication CTAs store
+// the owned x entries other ranks need straight into those ranks' landing buffers
+// and publish a sequence number while the others stream the matrix; tiles are
+// ordered interior first, so the transfer overlaps the bulk of the work, and a CTA
+// only waits on its peers' sequence numbers when it reaches its first boundary
+// tile, whose gathers take columns beyond the owned range from the landing buffer.
 #include <stdlib.h>
 
 #include <algorithm>
@@ -56,8 +56,9 @@ namespace {
 // ---------------------------------------------------------------------------
 // stand-alone SpMV kernel
 // ---------------------------------------------------------------------------
-template <int MODE, int NDOT, bool HALO, bool RD, bool LL = false>
-__device__ __forceinline__ void csr_tma_body(const CsrKernelArgs &a)
+template <int MODE, int NDOT, bool HALO>
+__global__ void __launch_bounds__(kThreads)
+csr_tma_kernel(const CsrKernelArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t mbar[2];
@@ -82,7 +83,8 @@ __device__ __forceinline__ void csr_tma_body(const CsrKernelArgs &a)
         hseq = *reinterpret_cast<volatile unsigned long long *>(&a.sync.win->halo_seq) + 1;
 
     TilePipe pipe;
-    spmv_phase<MODE, NDOT, HALO, true, RD, LL>(a, smem, mbar, pipe, acc, hseq, false);
+    const SpmvVecs v{a.x1, a.y, a.u};
+    spmv_phase<MODE, NDOT, HALO, true>(a, v, smem, mbar, pipe, acc, hseq, false);
     finish_dots<NDOT>(a, acc);
 
     // peer-memory transport: the last CTA tells every source rank that this
@@ -102,40 +104,6 @@ __device__ __forceinline__ void csr_tma_body(const CsrKernelArgs &a)
             }
         }
     }
-}
-
-// The measured round-1 kernel.  Its launch bounds name no minimum of resident CTAs: ptxas then
-// settles on 32 registers.  (Experiment: -DSIGB_SPMV_MINBLOCKS=4 tells it that four CTAs per SM is
-// all shared memory allows, which frees 64 registers per thread for deeper load batching.)
-#ifdef SIGB_SPMV_MINBLOCKS
-#define SIGB_SPMV_BOUNDS __launch_bounds__(kThreads, SIGB_SPMV_MINBLOCKS)
-#else
-#define SIGB_SPMV_BOUNDS __launch_bounds__(kThreads)
-#endif
-template <int MODE, int NDOT, bool HALO>
-__global__ void SIGB_SPMV_BOUNDS
-csr_tma_kernel(const CsrKernelArgs a)
-{
-    csr_tma_body<MODE, NDOT, HALO, false>(a);
-}
-
-// EXPERIMENTAL row-direct form (spmv_device.cuh).  Four resident CTAs per SM are named so that
-// ptxas may use 64 registers: at 32 it serialises the row's gathers behind the running sum, with
-// 64 it issues the four gathers of a trip back to back (checked in the SASS).
-template <int MODE, int NDOT, bool HALO>
-__global__ void __launch_bounds__(kThreads, 4)
-csr_tma_rd_kernel(const CsrKernelArgs a)
-{
-    csr_tma_body<MODE, NDOT, HALO, true>(a);
-}
-
-// EXPERIMENTAL fence-free halo (SIGB_HALO_LL=1, spmv_device.cuh): the row-sharded kernels over
-// landing buffers of payload+flag records, two-pass and row-direct
-template <int MODE, int NDOT, bool RD>
-__global__ void __launch_bounds__(kThreads, 4)
-csr_tma_ll_kernel(const CsrKernelArgs a)
-{
-    csr_tma_body<MODE, NDOT, true, RD, true>(a);
 }
 
 // ---------------------------------------------------------------------------
@@ -228,37 +196,20 @@ ell_kernel(const EllKernelArgs a)
     }
 }
 
-template <int MODE, int NDOT, bool HALO, bool RD, bool LL = false>
-int launch_csr_rd(const CsrKernelArgs &a, cudaStream_t st)
+template <int MODE, int NDOT, bool HALO>
+int launch_csr_t(const CsrKernelArgs &a, cudaStream_t st)
 {
     int grid = 0;
     const size_t smem = 2 * (size_t)kStageBytes;
-    constexpr auto kernel = LL ? csr_tma_ll_kernel<MODE, NDOT, RD>
-                               : (RD ? csr_tma_rd_kernel<MODE, NDOT, HALO> : csr_tma_kernel<MODE, NDOT, HALO>);
-    SIGB_CHECK((occupancy_grid<kernel>(smem, &grid)));
-    if (a.ntiles < grid) grid = a.ntiles;
-    if (grid < 1) grid = 1;
-    if (HALO && a.sync.win != nullptr) {
-        CsrKernelArgs b = a;
-        int pc = (a.sync.total_send + 2 * kThreads - 1) / (2 * kThreads);   // ~2 entries per thread
-        b.sync.push_ctas = a.sync.total_send > 0 ? std::max(1, std::min(pc, grid)) : 0;
-        b.sync.push_first = halo_push_first(grid, b.sync.push_ctas);
-        kernel<<<grid, kThreads, smem, st>>>(b);
-    } else {
-        kernel<<<grid, kThreads, smem, st>>>(a);
-    }
+    SIGB_CHECK((occupancy_grid<csr_tma_kernel<MODE, NDOT, HALO>>(smem, &grid)));
+    // one CTA per tile is enough; the communication CTAs of a row-sharded operator come on top
+    const int comm = (HALO && a.sync.win != nullptr) ? a.sync.push_ctas : 0;
+    if (a.ntiles + comm < grid) grid = a.ntiles + comm;
+    if (grid < comm + 1) grid = comm + 1;
+    csr_tma_kernel<MODE, NDOT, HALO><<<grid, kThreads, smem, st>>>(a);
     count_launch();
     SIGB_CUDA(cudaGetLastError());
     return SIGB_OK;
-}
-
-template <int MODE, int NDOT, bool HALO>
-int launch_csr_t(const CsrKernelArgs &a, cudaStream_t st, bool rowdirect, bool halo_ll)
-{
-    if (HALO && halo_ll)
-        return rowdirect ? launch_csr_rd<MODE, NDOT, true, true, true>(a, st)
-                         : launch_csr_rd<MODE, NDOT, true, false, true>(a, st);
-    return rowdirect ? launch_csr_rd<MODE, NDOT, HALO, true>(a, st) : launch_csr_rd<MODE, NDOT, HALO, false>(a, st);
 }
 
 template <int MODE, int NDOT, int W>
@@ -292,24 +243,6 @@ int launch_ell_w(const EllKernelArgs &a, cudaStream_t st)
 }
 
 }  // namespace
-
-int32_t halo_push_first(int grid, int push_ctas)
-{
-    static const bool last = env_int("SIGB_PUSH_LAST", 0) == 1;
-    // ... except the very last CTA, which publishes the reductions of the persistent CG kernel
-    return last ? std::max(0, grid - 1 - push_ctas) : 0;
-}
-
-// EXPERIMENTAL row-direct form of the streaming kernel (spmv_device.cuh).  SIGB_SPMV_ROWDIRECT:
-// unset / 0 = never (the measured round-1 kernel), 1 = every matrix (parity runs), 2 = matrices
-// with at most 8 stored entries per row on average.
-bool spmv_rowdirect(const CsrView &A)
-{
-    static const int mode = env_int("SIGB_SPMV_ROWDIRECT", 0);
-    if (mode == 1) return true;
-    if (mode == 2) return A.nrows > 0 && A.nnz <= 8 * (int64_t)A.nrows;
-    return false;
-}
 
 // Greedy row tiling: consecutive rows while the tile holds <= kTileCap entries
 // and <= kTileRows rows; a longer row gets a tile of its own.  ptr is monotone,
@@ -385,6 +318,7 @@ static void fill_args(const CsrView &A, const double *val, const double *x, doub
     if (dot.sync) a.sync = *dot.sync;
     if (dot.red) a.red = *dot.red;
     a.first_halo_tile = (which == 0 && dot.sync) ? A.n_interior : 0;
+    a.fault = ctx().fault_dev;
 }
 
 int fill_csr_args(const CsrView &V, const double *val, const double *x, double *y, const DotSpec &dot,
@@ -412,13 +346,11 @@ int launch_csr_spmv(const CsrView &A, const double *val, const double *x, double
     cudaStream_t st = stream ? stream : ctx().stream;
     if (a.ntiles == 0 && dot.ndot == 0) return SIGB_OK;
 
-    const bool rd = spmv_rowdirect(A);
-    const bool ll = dot.sync != nullptr && dot.halo_ll;
 #define SIGB_DISPATCH(M)                                                            \
     switch (dot.ndot) {                                                             \
-    case 0: return halo ? launch_csr_t<M, 0, true>(a, st, rd, ll) : launch_csr_t<M, 0, false>(a, st, rd, ll);  \
-    case 1: return halo ? launch_csr_t<M, 1, true>(a, st, rd, ll) : launch_csr_t<M, 1, false>(a, st, rd, ll);  \
-    default: return halo ? launch_csr_t<M, 2, true>(a, st, rd, ll) : launch_csr_t<M, 2, false>(a, st, rd, ll); \
+    case 0: return halo ? launch_csr_t<M, 0, true>(a, st) : launch_csr_t<M, 0, false>(a, st);  \
+    case 1: return halo ? launch_csr_t<M, 1, true>(a, st) : launch_csr_t<M, 1, false>(a, st);  \
+    default: return halo ? launch_csr_t<M, 2, true>(a, st) : launch_csr_t<M, 2, false>(a, st); \
     }
     switch (mode) {
     case MODE_SET: SIGB_DISPATCH(MODE_SET)

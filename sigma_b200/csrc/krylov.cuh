@@ -33,7 +33,7 @@ struct KState {
     long long itc[2];  // BiCGSTAB: parity-indexed copy of iters (race-free reads)
     int done[2];       // latch of the loop test, parity-indexed
     int capped;
-    int pad_;
+    int started;       // persistent CG kernel: the initial residual has been formed (a later launch resumes)
     double lz[8];      // Lanczos scalars: [0] alpha, [1] beta, [2] c / norm2
 };
 
@@ -109,7 +109,7 @@ int launch_ew(const Op &op, int64_t n, cudaStream_t st = nullptr)
     return SIGB_OK;
 }
 
-// EXPERIMENTAL (SIGB_FUSED_ALLREDUCE=1): the same kernel with the Op's dot products all-reduced
+// Row-sharded operators, peer-memory transport: the same kernel with the Op's dot products all-reduced
 // across the GPUs by its last CTA (device_utils.cuh grid_reduce) instead of a separate launch.
 // A twin rather than a parameter of ew_kernel, so that the product kernels keep their code.
 template <class Op>

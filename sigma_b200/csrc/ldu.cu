@@ -15,10 +15,11 @@
 // entry in stored order, with rounded products (no FMA).  Factors, diagonal
 // and every solve are therefore bit-identical to the serial loops.
 //
-// This is latency-bound by construction: a level of the 2-D five-point stencil
-// in natural ordering is one anti-diagonal of the grid (2N - 1 levels of at
-// most N rows).  The value of the row is the drop-in coverage of the only
-// other preconditioner the reference ships, not bandwidth.
+// The sweeps are latency-bound by construction: a level of the 2-D five-point stencil in natural
+// ordering is one anti-diagonal of the grid (2N - 1 levels of at most N rows).  One launch per
+// level (round 1) costs ~4 us per level -- 16.8 ms per application at 1024^2, slower than one host
+// core.  Deep schedules therefore run as CHUNKED SWEEPS (below): one launch per sweep, every
+// thread walks a contiguous chunk of rows in order and waits only for the entries it reads.
 #include <stdlib.h>
 
 #include <algorithm>
@@ -40,11 +41,11 @@ struct LduInfo {
     int32_t *frows = nullptr, *brows = nullptr;
     std::vector<int32_t> flev, blev;  // level pointers (host): launches are driven from here
     sigb_matrix_t rows = nullptr;     // csc / ellpack sources: their row form (device copy), else null
-    // EXPERIMENTAL sync-free sweeps (SIGB_LDU_SYNCFREE=1): solution entries in flight as
-    // payload+flag words, per-row "factored" flags, and the sequence number of the last sweep
+    // chunked sweeps: solution entries in flight as payload+flag words, the sequence number of the
+    // last sweep, and the chunking (0 rows per chunk = one launch per level instead)
     RedEntry *xs = nullptr;
-    unsigned *ready = nullptr;
     unsigned sf_seq = 0;
+    int32_t chunk_rows = 0, nchunks = 0;
     double *Lval() const { return fac; }
     double *Uval() const { return fac + nL; }
     double *D() const { return fac + nL + nU; }
@@ -149,34 +150,26 @@ divide_kernel(double *__restrict__ x, const double *__restrict__ D, int64_t n, c
 }
 
 // ---------------------------------------------------------------------------
-// EXPERIMENTAL, opt-in (SIGB_LDU_SYNCFREE=1; compiled in, not the default path,
-// not yet run on a GPU): the same sweeps WITHOUT one launch per level.
+// Chunked sweeps: (I + L) x = b and (I + U) x = x / D in ONE launch each.
 //
-// One cooperative launch per sweep.  Threads take the rows in level order
-// (frows / brows: every row a row depends on sits at an earlier position) and
-// wait for exactly the entries they read instead of for a whole level:
-//   * triangular solves: a finished x(i) is published as two 8-byte words, each
-//     32 payload bits + the 32-bit sequence number of this sweep (the words of
-//     the all-reduce, device_utils.cuh).  A word is delivered as a unit, so a
-//     reader needs no fence and no second round trip: one L2 hop per
-//     dependency, against one launch (4 us) or one grid barrier (1-2 us) per level;
-//   * factorisation: a row reads whole rows of U and D(k) of its lower
-//     neighbours, so finished rows are announced by a flag behind a fence and
-//     read through L2.
-// Lanes never spin on their own: a warp runs one loop in which every unfinished
-// lane polls once and advances as far as it can, until all 32 are finished --
-// a dependency on a lower lane of the same warp resolves on the next trip.
-// Progress: all CTAs are resident (cooperative launch) and each warp takes its
-// positions in ascending order, so the lowest unfinished position of the sweep
-// always belongs to a running warp and has all its inputs.  Spins are bounded:
-// a wrong answer the tests catch, never a hung GPU.
-// Every row still does the reference's arithmetic in stored order with rounded
-// products, so the factors and the solves stay bit-identical to the serial loops.
+// Thread t owns the contiguous rows [t B, (t + 1) B) and solves them one after the other, in
+// order (the backward sweep mirrors this from the last row down).  A finished x(i) is published as
+// two 8-byte words, each 32 payload bits + the 32-bit sequence number of this sweep (the words of
+// the all-reduce, device_utils.cuh): a word is delivered as a unit, so a reader needs no fence and
+// no second round trip.  A row waits for exactly the entries it reads, in stored order; the entry
+// it has just produced itself comes from a register.
+// B = the bandwidth of the factor (max |i - j| over its entries): row i of thread t then depends on
+// rows of thread t - 1 at the same position or earlier, so the threads run as a systolic wavefront
+// one step apart and the sweep takes ~(B + n / B) dependent steps of one L2 round trip each instead
+// of one launch (or one grid barrier) per level -- for the N x N five-point stencil B = N: 2 N steps.
+// Lanes never spin on their own: a warp runs one loop in which every unfinished lane polls once
+// and advances as far as it can; a dependency on a lower lane resolves on a later trip.  Progress:
+// all threads are resident (the grid is sized for that) and every row depends on lower rows only,
+// i.e. on its own thread's past or on lower threads.  Every row still does the reference's
+// arithmetic in stored order with rounded products, so the solves stay bit-identical to the serial
+// loops (ldu_solvers.f90:226-235, :254-263).  Waits are bounded through spin_check.
 // ---------------------------------------------------------------------------
-constexpr unsigned kSweepSpinLimit = 1u << 22;   // >= 1 s of polling: far beyond a whole sweep
-
-// payload+flag words as in device_utils.cuh, but at GPU scope: these sweeps never leave the device,
-// so the accesses need not be ordered against the peers (system scope) like the all-reduce's
+// payload+flag words as in device_utils.cuh, but at GPU scope: these sweeps never leave the device
 __device__ __forceinline__ void st_word_gpu(unsigned int *p, unsigned int payload, unsigned int flag)
 {
     asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(flag) : "memory");
@@ -187,7 +180,6 @@ __device__ __forceinline__ uint2 ld_word_gpu(const unsigned int *p)
     asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
     return r;
 }
-
 __device__ __forceinline__ bool ll_try(const RedEntry *e, unsigned seq, double *out)
 {
     const uint2 lo = ld_word_gpu(&e->lo), hi = ld_word_gpu(&e->hi);
@@ -202,226 +194,128 @@ __device__ __forceinline__ void ll_publish(RedEntry *e, unsigned seq, double v)
     st_word_gpu(&e->hi, (unsigned)(bits >> 32), seq);
 }
 
-// (I + M) x = src, or with D: (I + M) x = src / D   (the x = x / D statement of ldu_solve
-// :169 folded into the start of the backward sweep: same division, same operands)
-template <bool DIVIDE>
-__global__ void __launch_bounds__(kThreads)
-tri_syncfree_kernel(const int32_t *__restrict__ rows, int32_t n, const int32_t *__restrict__ ptr1,
-                    const int32_t *__restrict__ node1, const double *__restrict__ val, const double *src,
-                    const double *__restrict__ D, double *x, RedEntry *xs, unsigned seq, unsigned sleep_ns,
-                    const int *skip)
+constexpr int kSweepThreads = 32;    // one warp per CTA: the wavefront spreads over as many SMs as possible
+
+// BACKWARD = false: (I + M) x = src, rows ascending.  BACKWARD = true: (I + M) x = src / D, rows
+// descending (the x = x / D statement of ldu_solve :169 folded into the start of the sweep: same
+// division, same operands).
+template <bool BACKWARD>
+__global__ void __launch_bounds__(kSweepThreads)
+tri_chunked_kernel(int32_t n, int32_t chunk_rows, int32_t nchunks, const int32_t *__restrict__ ptr1,
+                   const int32_t *__restrict__ node1, const double *__restrict__ val, const double *src,
+                   const double *__restrict__ D, double *x, RedEntry *xs, unsigned seq, FaultBlock *fault,
+                   const int *skip)
 {
     if (skip != nullptr && *skip != 0) return;
-    const int lane = threadIdx.x & 31;
-    const int64_t stride = (int64_t)gridDim.x * kThreads;
-    for (int64_t base = blockIdx.x * (int64_t)kThreads + (threadIdx.x - lane); base < n; base += stride) {
-        const int64_t p = base + lane;
-        int32_t i = 0, k = 0, e = 0;
-        double z = 0.0;
-        bool done = true;
-        if (p < n) {
-            i = rows[p];
-            k = ptr1[i - 1] - 1;
-            e = ptr1[i] - 1;
-            z = DIVIDE ? src[i - 1] / D[i - 1] : src[i - 1];
-            done = false;
-        }
-        unsigned spins = 0;
-        for (;;) {
-            if (!done) {
-                while (k < e) {                                   // z = z - M%val(k) * x(node(k)), stored order
-                    double xj;
-                    if (!ll_try(xs + (node1[k] - 1), seq, &xj)) break;
-                    z = sub(z, mul(val[k], xj));
-                    k++;
-                }
-                if (k == e) {
-                    x[i - 1] = z;
-                    ll_publish(xs + (i - 1), seq, z);
-                    done = true;
-                }
+    const int32_t t = blockIdx.x * kSweepThreads + threadIdx.x;
+    // rows of this chunk, 1-based, in sweep order: i, i + step, ..., last
+    int32_t i = 0, last = 0;
+    const int32_t step = BACKWARD ? -1 : 1;
+    bool done = true;
+    if (t < nchunks) {
+        const int64_t lo = (int64_t)t * chunk_rows, hi = min((int64_t)n, lo + chunk_rows);   // 0-based [lo, hi) from the sweep's start
+        if (!BACKWARD) { i = (int32_t)lo + 1; last = (int32_t)hi; }
+        else { i = n - (int32_t)lo; last = n - (int32_t)hi + 1; }
+        done = false;
+    }
+    int32_t k = 0, e = 0, prev_row = 0;
+    double z = 0.0, prev_z = 0.0;
+    bool have_row = false;
+    unsigned trips = 0;
+    unsigned long long t0 = 0ull;
+    for (;;) {
+        if (!done) {
+            if (!have_row) {
+                k = ptr1[i - 1] - 1;
+                e = ptr1[i] - 1;
+                z = BACKWARD ? src[i - 1] / D[i - 1] : src[i - 1];
+                have_row = true;
             }
-            if (__all_sync(0xffffffffu, done)) break;
-            if (++spins > kSweepSpinLimit) break;
-            if (sleep_ns) __nanosleep(sleep_ns << (spins < 3u ? spins : 3u));   // back off: base, 2x, 4x, 8x
-        }
-    }
-}
-
-// U%get_value(k, j) on a row another thread of this launch has written: read at L2
-__device__ __forceinline__ double get_value_cg(const int32_t *ptr1, const int32_t *node1, const double *val, int32_t i,
-                                               int32_t j)
-{
-    double z = 0.0;
-    for (int32_t k = ptr1[i - 1] - 1; k < ptr1[i] - 1; k++)
-        if (node1[k] == j) z = __ldcg(val + k);
-    return z;
-}
-
-// the elimination (:331-381) in one launch: the body of ldu_factor_level_kernel behind a wait
-// for the "factored" flags of the row's lower neighbours
-__global__ void __launch_bounds__(kThreads, 2)   // (room for registers: at the default bounds ptxas spilled)
-ldu_factor_syncfree_kernel(const int32_t *__restrict__ rows, int32_t n, const int32_t *__restrict__ Lptr,
-                           const int32_t *__restrict__ Lnode, double *Lval, const int32_t *__restrict__ Uptr,
-                           const int32_t *__restrict__ Unode, double *Uval, double *D, unsigned *ready, unsigned seq,
-                           unsigned sleep_ns)
-{
-    const int lane = threadIdx.x & 31;
-    const int64_t stride = (int64_t)gridDim.x * kThreads;
-    for (int64_t base = blockIdx.x * (int64_t)kThreads + (threadIdx.x - lane); base < n; base += stride) {
-        const int64_t p = base + lane;
-        int32_t i = 0, lb = 0, dl = 0, w = 0;
-        bool done = true;
-        if (p < n) {
-            i = rows[p];
-            lb = Lptr[i - 1] - 1;
-            dl = Lptr[i] - 1 - lb;
-            done = false;
-        }
-        unsigned spins = 0;
-        for (;;) {
-            if (!done) {
-                while (w < dl && *reinterpret_cast<volatile unsigned *>(ready + (Lnode[lb + w] - 1)) == seq) w++;
-                if (w == dl) {
-                    __threadfence();   // the neighbours' rows were written before their flags
-                    const int32_t ub = Uptr[i - 1] - 1, du = Uptr[i] - 1 - ub;
-                    for (int32_t ind1 = 0; ind1 < dl; ind1++) {
-                        const int32_t k = Lnode[lb + ind1];
-                        double Lik = Lval[lb + ind1];
-                        const double Uki = get_value_cg(Uptr, Unode, Uval, k, i);
-                        const double Dk = __ldcg(D + (k - 1));
-                        Lik = Lik / Dk;
-                        Lval[lb + ind1] = Lik;
-                        const double LikDk = mul(Lik, Dk);
-                        for (int32_t ind2 = 0; ind2 < dl; ind2++) {
-                            const int32_t j = Lnode[lb + ind2];
-                            if (j > k) {
-                                const double Ukj = get_value_cg(Uptr, Unode, Uval, k, j);
-                                Lval[lb + ind2] = add(Lval[lb + ind2], -mul(LikDk, Ukj));
-                            }
-                        }
-                        D[i - 1] = sub(D[i - 1], mul(LikDk, Uki));
-                        for (int32_t ind2 = 0; ind2 < du; ind2++) {
-                            const int32_t j = Unode[ub + ind2];
-                            const double Ukj = get_value_cg(Uptr, Unode, Uval, k, j);
-                            Uval[ub + ind2] = add(Uval[ub + ind2], -mul(LikDk, Ukj));
-                        }
-                    }
-                    const double Di = D[i - 1];
-                    for (int32_t ind2 = 0; ind2 < du; ind2++) Uval[ub + ind2] = Uval[ub + ind2] / Di;
-                    __threadfence();   // row i of U and D(i) before the flag
-                    *reinterpret_cast<volatile unsigned *>(ready + (i - 1)) = seq;
-                    done = true;
-                }
+            while (k < e) {                                   // z = z - M%val(k) * x(node(k)), stored order
+                const int32_t j = node1[k];
+                double xj;
+                if (j == prev_row) xj = prev_z;
+                else if (!ll_try(xs + (j - 1), seq, &xj)) break;
+                z = sub(z, mul(val[k], xj));
+                k++;
             }
-            if (__all_sync(0xffffffffu, done)) break;
-            if (++spins > kSweepSpinLimit) break;
-            if (sleep_ns) __nanosleep(sleep_ns << (spins < 3u ? spins : 3u));   // back off: base, 2x, 4x, 8x
+            if (k == e) {
+                x[i - 1] = z;
+                ll_publish(xs + (i - 1), seq, z);
+                prev_row = i;
+                prev_z = z;
+                have_row = false;
+                if (i == last) done = true;
+                else i += step;
+            }
         }
+        if (__all_sync(0xffffffffu, done)) break;
+        if ((++trips & 0xfffu) == 0u && !spin_check(fault, &t0, FAULT_LDU_SWEEP)) break;
     }
 }
 
-struct SyncFreeCfg {
-    bool on = false;
-    int ctas_per_sm = 1;     // SIGB_LDU_SF_CTAS_PER_SM
-    int ctas = 0;            // SIGB_LDU_SF_CTAS: absolute grid size (wins when > 0); fewer resident threads
-                             // = fewer pollers competing with the wavefront for L2
-    unsigned sleep_ns = 0;   // SIGB_LDU_SF_SLEEP_NS: base of the polling back-off (0 = poll flat out)
-};
-const SyncFreeCfg &syncfree_cfg()
-{
-    static SyncFreeCfg c;
-    static bool read = false;
-    if (!read) {
-        c.on = env_int("SIGB_LDU_SYNCFREE", 0) == 1;
-        c.ctas_per_sm = std::max(1, env_int("SIGB_LDU_SF_CTAS_PER_SM", c.ctas_per_sm));
-        c.ctas = std::max(0, env_int("SIGB_LDU_SF_CTAS", 0));
-        c.sleep_ns = (unsigned)std::max(0, env_int("SIGB_LDU_SF_SLEEP_NS", 0));
-        read = true;
-    }
-    return c;
-}
-
-// grid of a sweep kernel: the requested CTAs per SM, never more than can be resident
-template <typename K>
-int syncfree_grid(K kernel, int64_t n, int *grid)
-{
-    int per_sm = 0;
-    SIGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
-    if (per_sm < 1) per_sm = 1;
-    const int64_t resident = (int64_t)per_sm * ctx().num_sms;   // what a cooperative launch can hold
-    if (per_sm > syncfree_cfg().ctas_per_sm) per_sm = syncfree_cfg().ctas_per_sm;
-    int64_t g = (int64_t)per_sm * ctx().num_sms;
-    if (syncfree_cfg().ctas > 0) g = std::min<int64_t>(syncfree_cfg().ctas, resident);
-    const int64_t need = (n + kThreads - 1) / kThreads;
-    if (g > need) g = need;
-    if (g < 1) g = 1;
-    *grid = (int)g;
-    return SIGB_OK;
-}
-
-// scratch of the sync-free sweeps; hands out the next sequence number (0 = never written)
-int syncfree_prepare(LduInfo *F, unsigned *seq)
+// scratch of the chunked sweeps; hands out the next sequence number (0 = never written)
+int sweep_prepare(LduInfo *F, unsigned *seq)
 {
     cudaStream_t st = ctx().stream;
     const size_t n = (size_t)(F->n > 0 ? F->n : 1);
     if (!F->xs) {
         SIGB_CUDA(cudaMalloc((void **)&F->xs, sizeof(RedEntry) * n));
-        SIGB_CUDA(cudaMalloc((void **)&F->ready, sizeof(unsigned) * n));
         F->sf_seq = 0;
     }
     if (F->sf_seq == 0 || F->sf_seq == 0xffffffffu) {   // first use, or the counter is about to wrap
         SIGB_CUDA(cudaMemsetAsync(F->xs, 0, sizeof(RedEntry) * n, st));
-        SIGB_CUDA(cudaMemsetAsync(F->ready, 0, sizeof(unsigned) * n, st));
         F->sf_seq = 0;
     }
     *seq = ++F->sf_seq;
     return SIGB_OK;
 }
 
-template <bool DIVIDE>
-int launch_tri_syncfree(LduInfo *F, const int32_t *rows, const int32_t *ptr1, const int32_t *node1, const double *val,
-                        const double *src, double *x, const int *skip)
+template <bool BACKWARD>
+int launch_tri_chunked(LduInfo *F, const int32_t *ptr1, const int32_t *node1, const double *val, const double *src,
+                       double *x, const int *skip)
 {
     unsigned seq = 0;
-    SIGB_CHECK(syncfree_prepare(F, &seq));
-    int grid = 0;
-    SIGB_CHECK(syncfree_grid(tri_syncfree_kernel<DIVIDE>, F->n, &grid));
-    int32_t n = F->n;
-    const double *D = F->D();
-    RedEntry *xs = F->xs;
-    unsigned sleep_ns = syncfree_cfg().sleep_ns;
-    void *params[] = {(void *)&rows, (void *)&n, (void *)&ptr1, (void *)&node1, (void *)&val, (void *)&src,
-                      (void *)&D, (void *)&x, (void *)&xs, (void *)&seq, (void *)&sleep_ns, (void *)&skip};
-    SIGB_CUDA(cudaLaunchCooperativeKernel((const void *)tri_syncfree_kernel<DIVIDE>, dim3(grid), dim3(kThreads), params,
-                                          0, ctx().stream));
+    SIGB_CHECK(sweep_prepare(F, &seq));
+    const int grid = (F->nchunks + kSweepThreads - 1) / kSweepThreads;
+    tri_chunked_kernel<BACKWARD><<<grid, kSweepThreads, 0, ctx().stream>>>(F->n, F->chunk_rows, F->nchunks, ptr1, node1,
+                                                                           val, src, F->D(), x, F->xs, seq,
+                                                                           ctx().fault_dev, skip);
     count_launch();
+    SIGB_CUDA(cudaGetLastError());
     return SIGB_OK;
 }
 
-int launch_factor_syncfree(LduInfo *F)
+// Chunking of the sweeps from the patterns of L and U (host index work, once per pattern): chunk
+// length = bandwidth of the factors, at least n / kMaxChunks.  Chunked sweeps are used when the level
+// schedule is deep (one launch per level costs ~4 us per level) and the chunking leaves at least a
+// warp of chunks; otherwise -- few, wide levels, e.g. a random graph -- the level launches stay.
+constexpr int kMaxChunks = 4096;   // threads of one sweep; all must be resident (32 per CTA -> 128 CTAs)
+void choose_chunking(LduInfo *F, const std::vector<int32_t> &Lptr, const std::vector<int32_t> &Lnode,
+                     const std::vector<int32_t> &Uptr, const std::vector<int32_t> &Unode)
 {
-    unsigned seq = 0;
-    SIGB_CHECK(syncfree_prepare(F, &seq));
-    int grid = 0;
-    SIGB_CHECK(syncfree_grid(ldu_factor_syncfree_kernel, F->n, &grid));
-    const int32_t *rows = F->frows, *Lptr = F->Lptr, *Lnode = F->Lnode, *Uptr = F->Uptr, *Unode = F->Unode;
-    int32_t n = F->n;
-    double *Lval = F->Lval(), *Uval = F->Uval(), *D = F->D();
-    unsigned *ready = F->ready;
-    unsigned sleep_ns = syncfree_cfg().sleep_ns;
-    void *params[] = {(void *)&rows, (void *)&n, (void *)&Lptr, (void *)&Lnode, (void *)&Lval, (void *)&Uptr,
-                      (void *)&Unode, (void *)&Uval, (void *)&D, (void *)&ready, (void *)&seq, (void *)&sleep_ns};
-    SIGB_CUDA(cudaLaunchCooperativeKernel((const void *)ldu_factor_syncfree_kernel, dim3(grid), dim3(kThreads), params,
-                                          0, ctx().stream));
-    count_launch();
-    return SIGB_OK;
+    const int32_t n = F->n;
+    int64_t bw = 1;
+    for (int32_t i = 1; i <= n; i++) {
+        for (int32_t k = Lptr[(size_t)i - 1] - 1; k < Lptr[(size_t)i] - 1; k++) bw = std::max<int64_t>(bw, i - Lnode[(size_t)k]);
+        for (int32_t k = Uptr[(size_t)i - 1] - 1; k < Uptr[(size_t)i] - 1; k++) bw = std::max<int64_t>(bw, Unode[(size_t)k] - i);
+    }
+    int64_t rows = std::max<int64_t>(bw, ((int64_t)n + kMaxChunks - 1) / kMaxChunks);
+    const int64_t chunks = n > 0 ? ((int64_t)n + rows - 1) / rows : 0;
+    const int64_t levels = std::max(F->flev.size(), F->blev.size());
+    if (levels > 64 && chunks >= 32) {
+        F->chunk_rows = (int32_t)rows;
+        F->nchunks = (int32_t)chunks;
+    } else {
+        F->chunk_rows = 0;
+        F->nchunks = 0;
+    }
 }
 
 void free_ldu(LduInfo *F)
 {
     if (!F) return;
-    cudaFree(F->xs); cudaFree(F->ready);
+    cudaFree(F->xs);
     cudaFree(F->Lptr); cudaFree(F->Lnode); cudaFree(F->Uptr); cudaFree(F->Unode);
     cudaFree(F->fac); cudaFree(F->dest); cudaFree(F->frows); cudaFree(F->brows);
     if (F->rows) sigb_matrix_destroy(F->rows);
@@ -492,6 +386,7 @@ int ldu_setup_dev(sigb_solver_t s, sigb_matrix_t A)
             F->nU = (int64_t)Uptr[(size_t)n] - 1;
             F->flev.assign(flev.begin(), flev.begin() + nf + 1);
             F->blev.assign(blev.begin(), blev.begin() + nb + 1);
+            choose_chunking(F, Lptr, Lnode, Uptr, Unode);
             rc = upload(&F->Lptr, Lptr.data(), (size_t)n + 1);
             if (rc == SIGB_OK) rc = upload(&F->Uptr, Uptr.data(), (size_t)n + 1);
             if (rc == SIGB_OK) rc = upload(&F->Lnode, Lnode.data(), (size_t)F->nL);
@@ -520,11 +415,6 @@ int ldu_setup_dev(sigb_solver_t s, sigb_matrix_t A)
         ldu_scatter_kernel<<<grid_for(F->ne), kThreads, 0, st>>>(R->val, F->dest, F->ne, F->fac);
         count_launch();
     }
-    if (syncfree_cfg().on && n > 0) {   // EXPERIMENTAL: the elimination in one launch
-        SIGB_CHECK(launch_factor_syncfree(F));
-        SIGB_CUDA(cudaGetLastError());
-        return SIGB_OK;
-    }
     // the elimination, level by level
     const int nlev = (int)F->flev.size() - 1;
     for (int l = 0; l < nlev; l++) {
@@ -544,11 +434,10 @@ int ldu_apply_dev(sigb_solver_t s, double *x, const double *b, const int *skip_f
     SIGB_REQUIRE(F, SIGB_ERR_STATE, "ldu solve: pc%%setup(A) has not been called");
     cudaStream_t st = ctx().stream;
     const int32_t n = F->n;
-    if (syncfree_cfg().on && n > 0) {
-        // EXPERIMENTAL: two launches; x = b and x = x / D are folded into the sweeps' first reads
-        SIGB_CHECK(launch_tri_syncfree<false>(F, F->frows, F->Lptr, F->Lnode, F->Lval(), b, x, skip_flag));
-        SIGB_CHECK(launch_tri_syncfree<true>(F, F->brows, F->Uptr, F->Unode, F->Uval(), x, x, skip_flag));
-        SIGB_CUDA(cudaGetLastError());
+    if (F->nchunks > 0 && n > 0) {
+        // deep schedule: two launches; x = b and x = x / D are folded into the sweeps' first reads
+        SIGB_CHECK(launch_tri_chunked<false>(F, F->Lptr, F->Lnode, F->Lval(), b, x, skip_flag));
+        SIGB_CHECK(launch_tri_chunked<true>(F, F->Uptr, F->Unode, F->Uval(), x, x, skip_flag));
         return SIGB_OK;
     }
     if (x != b) {

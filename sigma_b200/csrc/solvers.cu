@@ -606,7 +606,7 @@ static int sync_state(sigb_solver_t s)
     SIGB_CUDA(cudaMemcpyAsync(s->state_host, s->state, sizeof(KState), cudaMemcpyDeviceToHost,
                               ctx().stream));
     SIGB_CUDA(cudaStreamSynchronize(ctx().stream));
-    return SIGB_OK;
+    return check_fault("solve");   // a device-side wait that timed out invalidates what was computed
 }
 
 static int push_state(sigb_solver_t s)
@@ -644,9 +644,9 @@ int jacobi_apply_dev(sigb_solver_t s, double *x, const double *b)
     return launch_ew(op, s->nn);
 }
 
-static int finish_solve(sigb_solver_t s)
+static int finish_solve(sigb_solver_t s, bool state_is_current = false)
 {
-    SIGB_CHECK(sync_state(s));
+    if (!state_is_current) SIGB_CHECK(sync_state(s));
     s->iterations += s->state_host->iters;
     s->res2 = s->state_host->final_res2;
     s->capped = s->state_host->capped;
@@ -668,8 +668,10 @@ static bool persistent_enabled(int64_t n_local, int nranks, int solver_choice)
         v = e ? (atoi(e) != 0 ? 1 : 0) : -1;
     }
     if (v >= 0) return v != 0;
-    (void)nranks;   // same cross-over measured at 1, 4 and 8 ranks (profiles/README.md)
-    return n_local <= 3000000;
+    // cross-over on B200 with the 3-CTA kernel: ~4.2 M rows on one GPU (107.9 vs 108.8 us per iteration,
+    // profiles/r2_visit_d_1gpu_summary.txt); on a sharded operator the persistent form also saves the
+    // launches between the phases, so 4 GPUs x 4.2 M rows take it too
+    return n_local <= (nranks > 1 ? 4500000 : 4000000);
 }
 
 // L2 persistence for the solver's work vectors (north_star: "x-vector reuse
@@ -794,18 +796,10 @@ static int cg_solve_body(sigb_solver_t s, sigb_matrix_t A, double *x, const doub
     KState *st = s->state;
     SIGB_CHECK(push_state(s));
 
-    DotSpec none;
-    // q = A x ; r = b - q ; [z = M r] ; p = r|z ; res2 = r.r | r.z
-    SIGB_CHECK(solver_matvec(A, x, q, none, /*x_has_halo=*/false));
-    CgInitOp init{b, q, idiag, r, p, z, st};
-    SIGB_CHECK(launch_ew(init, n));
-    SIGB_CHECK(dist_allreduce(A, &st->rr[0], 1));
-    latch0_kernel<<<1, 1, 0, ctx().stream>>>(st);
-    count_launch();
-
-    // ---- the whole loop as one persistent cooperative kernel ---------------
-    // (CSR-shaped operators; SIGB_CG_PERSISTENT=0 selects the kernel-per-phase
-    // path below, which is also what ELLPACK and the NCCL transport use)
+    // ---- the whole solve as one persistent cooperative kernel ---------------
+    // (CSR-shaped operators; sigb_solver_set_persistent / SIGB_CG_PERSISTENT=0 select the
+    // kernel-per-phase path below, which is also what ELLPACK, operator expressions and the
+    // NCCL transport use).  The kernel forms the initial residual itself: one launch per solve.
     {
         const CsrView *V = nullptr;
         const double *val = nullptr;
@@ -830,24 +824,28 @@ static int cg_solve_body(sigb_solver_t s, sigb_matrix_t A, double *x, const doub
                 SIGB_CUDA(cudaMalloc((void **)&s->bar, 2 * sizeof(unsigned long long)));
                 SIGB_CUDA(cudaMalloc((void **)&s->pers_partials, sizeof(double) * 4 * kMaxGrid));
             }
-            // EXPERIMENTAL opt-in: one reduction per iteration (cg_persistent.cu); unpreconditioned only
-            static const bool single = env_int("SIGB_CG_SINGLE_REDUCE", 0) == 1;
             for (;;) {
-                if (single && !idiag)
-                    SIGB_CHECK(cg_single_reduce_run(s, *V, val, halo, x, p, q, r, z, n, pcomm, 4096));
-                else
-                    SIGB_CHECK(cg_persistent_run(s, *V, val, halo, x, p, q, r, z, idiag, n, 0, pcomm, 4096));
+                SIGB_CHECK(cg_persistent_run(s, *V, val, halo, x, b, p, q, r, z, idiag, n, pcomm, 4096));
                 SIGB_CHECK(sync_state(s));
                 if (s->state_host->done[0]) break;
             }
-            return finish_solve(s);
+            return finish_solve(s, /*state_is_current=*/true);
         }
     }
+
+    DotSpec none;
+    // q = A x ; r = b - q ; [z = M r] ; p = r|z ; res2 = r.r | r.z
+    SIGB_CHECK(solver_matvec(A, x, q, none, /*x_has_halo=*/false));
+    CgInitOp init{b, q, idiag, r, p, z, st};
+    SIGB_CHECK(launch_ew(init, n));
+    SIGB_CHECK(dist_allreduce(A, &st->rr[0], 1));
+    latch0_kernel<<<1, 1, 0, ctx().stream>>>(st);
+    count_launch();
 
     const int nb = batch_size(n);
     int par = 0;
     RedFuse rf;
-    const bool fused = dist_red_fuse(A, &rf);   // EXPERIMENTAL: the two all-reduces inside their producers
+    const bool fused = dist_red_fuse(A, &rf);   // peer-memory transport: the two all-reduces inside their producers
     for (;;) {
         for (int it = 0; it < nb; it++) {
             DotSpec d;

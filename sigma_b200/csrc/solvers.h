@@ -68,12 +68,8 @@ struct PersistComm {          // all-reduce endpoints of a row-sharded operator
 };
 struct CsrKernelArgs;
 int cg_persistent_run(sigb_solver_t s, const CsrView &V, const double *val, const DotSpec &halo, double *x,
-                      double *p, double *q, double *r, double *z, const double *idiag, int64_t n, int grid_hint,
+                      const double *b, double *p, double *q, double *r, double *z, const double *idiag, int64_t n,
                       const PersistComm &pcomm, long long max_iters);
-// EXPERIMENTAL (SIGB_CG_SINGLE_REDUCE=1): Chronopoulos-Gear arrangement, one reduction per iteration
-int cg_single_reduce_run(sigb_solver_t s, const CsrView &V, const double *val, const DotSpec &halo, double *x,
-                         double *p, double *s_vec, double *r, double *w, int64_t n, const PersistComm &pcomm,
-                         long long max_iters);
 // Row-sharded operators: fills the all-reduce endpoints and the halo spec the
 // persistent kernel needs; *eligible = false when the operator uses a transport
 // the kernel cannot drive (NCCL).
@@ -87,7 +83,7 @@ int solver_matvec(sigb_matrix_t A, const double *x, double *y, const DotSpec &do
 // Sum `count` contiguous device doubles over all ranks (no-op on one GPU).
 // skip_flag: device int; when non-zero at execution time the reduction is a
 // no-op (iterations launched past the stopping test), on every rank alike.
-bool dist_red_fuse(sigb_matrix_t A, RedFuse *rf);   // EXPERIMENTAL, see comm.cu
+bool dist_red_fuse(sigb_matrix_t A, RedFuse *rf);   // peer-memory transport: reductions finished inside their producers (comm.cu)
 int dist_allreduce(sigb_matrix_t A, double *vals, int count, const int *skip_flag = nullptr);
 int dist_allreduce2(sigb_matrix_t A, double *a, double *b, const int *skip_flag = nullptr);
 // extra elements a work vector needs behind its owned part (0 on one GPU)

@@ -28,10 +28,12 @@ struct CsrKernelArgs {
     const double *add0, *add1;  // optional addends folded into the dot totals
     HaloSync sync;            // peer-memory transport (sync.win == nullptr: none)
     int32_t first_halo_tile;  // tiles from this index on read halo columns
-    RedFuse red;              // EXPERIMENTAL: finish the dots across the GPUs in this kernel (nranks <= 1: no)
+    RedFuse red;              // finish the dots across the GPUs in this kernel (nranks <= 1: no)
+    FaultBlock *fault;        // wait timeouts (device_utils.cuh)
 #ifdef SIGB_PHASE_TIMERS
     // diagnostic build: SM cycles of thread 0 of every CTA, summed over the grid:
-    // [0] waiting for the staged tile, [1] products (gathers), [2] row sums, [3] the whole pass,
+    // [0] waiting for the staged tile, [1] gathers issued + row sums of the previous tile,
+    // [2] products (this is where the gathers are waited for), [3] the whole pass,
     // [4] staged tiles processed, [5] CTA passes
     unsigned long long *tile_dbg;
 #endif
@@ -111,45 +113,37 @@ constexpr int kStageVal = kTileNnz * 8;
 constexpr int kStageNode = kTileNnz * 4;
 constexpr int kStagePtr = (kTileRows + 8) * 4;
 constexpr int kStageBytes = (kStageVal + kStageNode + kStagePtr + 127) & ~127;
+constexpr int kRowSlots = kTileRows / kThreads;    // rows of a tile a thread may own
+constexpr int kEntrySlots = kTileNnz / kThreads;   // entries of a tile a thread gathers
 
 __device__ __forceinline__ bool tile_staged(const int4 &d)
 {
     return (d.w - d.z) <= kTileCap;  // else: one long row, streamed directly
 }
 
-template <int MODE, int NDOT>
-__device__ __forceinline__ void emit_row(const CsrKernelArgs &a, int r, double z, double ur, double *acc)
+// the vectors of one SpMV pass (the persistent kernel runs the same matrix over different ones)
+struct SpmvVecs {
+    const double *x1;   // x - 1
+    double *y;
+    const double *u;    // dot operand (NDOT >= 1)
+};
+
+// how the row sum z meets y(r) (SpmvMode), then the optional row scaling; returns what was stored
+template <int MODE>
+__device__ __forceinline__ double store_row(const CsrKernelArgs &a, const SpmvVecs &v, int r, double z)
 {
-    if (MODE == MODE_ADD_AFTER) z = add(a.y[r], z);
+    if (MODE == MODE_ADD_AFTER) z = add(v.y[r], z);
     if (MODE == MODE_SET && a.scale) z = mul(a.scale[r], z);
-    a.y[r] = z;
+    v.y[r] = z;
+    return z;
+}
+template <int NDOT>
+__device__ __forceinline__ void dot_row(double ur, double z, double *acc)
+{
     if (NDOT >= 1) acc[0] = add(acc[0], mul(ur, z));
     if (NDOT >= 2) acc[NDOT > 1 ? 1 : 0] = add(acc[NDOT > 1 ? 1 : 0], mul(z, z));
 }
 
-// ---- EXPERIMENTAL fence-free halo (LL, opt-in through SIGB_HALO_LL=1, not yet run on a GPU) ------
-// The landing buffers hold one 16-byte record per halo entry -- two words of 32 payload bits + the
-// 32-bit sequence number of the SpMV, like the all-reduce inbox -- instead of bare doubles behind a
-// per-source flag.  A word is delivered as a unit, so a record is either old or complete: the
-// producer needs no system-scope fence and publishes nothing (that fence sits on the pushing CTAs'
-// critical path today and makes them the last to reach the barrier), and a consumer simply polls
-// the record it is about to gather.  Buffer reuse is still guarded by the acknowledgements.
-__device__ __forceinline__ void halo_ll_store(RedEntry *e, unsigned seq, double v)
-{
-    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
-    st_word(&e->lo, (unsigned)bits, seq);
-    st_word(&e->hi, (unsigned)(bits >> 32), seq);
-}
-__device__ __forceinline__ double halo_ll_load(const RedEntry *e, unsigned seq)
-{
-    uint2 lo, hi;
-    unsigned spins = 0;
-    do { lo = ld_word(&e->lo); } while (lo.y != seq && ++spins < kSpinLimit);
-    do { hi = ld_word(&e->hi); } while (hi.y != seq && ++spins < kSpinLimit);
-    return __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | lo.x));
-}
-
-// one row longer than a tile: CTA-wide fixed-tree reduction, direct loads
 // XNC: x (and the dot operand u) may be read through the non-coherent read-only
 // path.  True for stand-alone launches, where the vectors are constant for the
 // kernel's lifetime; false inside the persistent CG kernel, which rewrites them
@@ -160,24 +154,25 @@ __device__ __forceinline__ double ld_x(const double *p)
     return XNC ? __ldg(p) : *p;
 }
 
-template <int MODE, int NDOT, bool HALO, bool XNC, bool LL = false>
-__device__ __forceinline__ void long_row(const CsrKernelArgs &a, const int4 &d, const double *h1, double *acc,
-                                         const RedEntry *hll = nullptr, unsigned seq = 0)
+// one row longer than a tile: CTA-wide fixed-tree reduction, direct loads (the only case where
+// the order of the additions differs from the reference's)
+template <int MODE, int NDOT, bool HALO, bool XNC>
+__device__ __forceinline__ void long_row(const CsrKernelArgs &a, const SpmvVecs &v, const int4 &d, const double *h1,
+                                         double *acc)
 {
     __shared__ double smr[1][kThreads / 32];
     double s[1] = {0.0};
     for (int k = d.z + threadIdx.x; k < d.w; k += kThreads) {
         const int c = a.node[k];
-        double xv;
-        if (LL && HALO && c > a.nloc) xv = halo_ll_load(hll + c, seq);
-        else xv = (HALO && c > a.nloc) ? __ldcg(h1 + c) : ld_x<XNC>(a.x1 + c);
+        const double xv = (HALO && c > a.nloc) ? __ldcg(h1 + c) : ld_x<XNC>(v.x1 + c);
         s[0] = add(s[0], mul(a.val[k], xv));
     }
     block_tree<1>(s, smr);
     if (threadIdx.x == 0) {
         double z = s[0];
-        if (MODE == MODE_ACC_INIT) z = add(a.y[d.x], z);
-        emit_row<MODE, NDOT>(a, d.x, z, NDOT >= 1 ? ld_x<XNC>(a.u + d.x) : 0.0, acc);
+        if (MODE == MODE_ACC_INIT) z = add(v.y[d.x], z);
+        z = store_row<MODE>(a, v, d.x, z);
+        dot_row<NDOT>(NDOT >= 1 ? ld_x<XNC>(v.u + d.x) : 0.0, z, acc);
     }
     __syncthreads();
 }
@@ -198,91 +193,129 @@ __device__ __forceinline__ void finish_dots(const CsrKernelArgs &a, double *acc)
     }
 }
 
+// z + p(b) + p(b+1) + ... + p(e-1), strictly left to right (the reference's z = z + val(k) * x(node(k))
+// with the rounded products already formed).  The products are fetched from shared memory eight at a
+// time BEFORE the dependent chain of additions starts: a plain loop exposes the shared-memory latency
+// on every step (load, add, load, add ...), which made the row sums of matrices with ~20 entries per
+// row the longest part of a tile (ncu on the Erdos-Renyi operator: warps mostly stalled at the CTA
+// barrier behind the few threads that own rows, profiles/r2_ncu_er_2m_round1_kernel.txt).
+__device__ __forceinline__ double ordered_sum(const double *sval, int b, int e, double z)
+{
+    int k = b;
+    for (; k + 8 <= e; k += 8) {
+        double p[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) p[j] = sval[k + j];
+#pragma unroll
+        for (int j = 0; j < 8; j++) z = add(z, p[j]);
+    }
+    if (k < e) {
+        double p[7];
+#pragma unroll
+        for (int j = 0; j < 7; j++) p[j] = (k + j < e) ? sval[k + j] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 7; j++)
+            if (k + j < e) z = add(z, p[j]);
+    }
+    return z;
+}
+
 // Per-CTA state of the double-buffered TMA pipeline, carried across calls.
 struct TilePipe {
     unsigned sidx = 0;     // staged tiles consumed so far: stage = sidx & 1, mbarrier parity = (sidx >> 1) & 1
     bool primed = false;   // the first tile of the next pass has already been issued
 };
 
-// One SpMV pass of this CTA over its tiles (round-robin), including -- for
-// row-sharded operators on the peer-memory transport -- the halo push in the
-// prologue and the lazy wait before the first boundary tile.  hseq is the
-// sequence number of this SpMV (HALO only).  Dot partials accumulate in acc.
-//
-// RD ("row direct", EXPERIMENTAL, opt-in through SIGB_SPMV_ROWDIRECT, not yet run on a GPU):
-// skip the pass that parks the rounded products in shared memory; the thread that owns a row
-// forms each product itself, in stored order, from the staged val / node slices.  Same
-// rounded products added in the same order, so the result is bit-identical.  Why: with ~5
-// entries per row the two-pass form costs ~28 bytes of shared-memory traffic per entry plus a
-// gather whose 32 lanes touch 6-7 sectors, and L1TEX (which serves both) is the most utilised
-// unit of this kernel (67-69 %, profiles/r1_ncu_csr_tma.txt); row-direct needs 12 bytes per
-// entry, one barrier less per tile, and on banded matrices the j-th entries of consecutive
-// rows are consecutive columns, so the gathers coalesce like the ELLPACK kernel's.  It loses
-// when rows are long or ragged (a warp runs as long as its longest row), hence a per-matrix
-// choice on the host.
-template <int MODE, int NDOT, bool HALO, bool XNC, bool RD = false, bool LL = false>
-__device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char *smem, uint64_t *mbar,
-                                           TilePipe &pipe, double *acc, unsigned long long hseq,
-                                           bool prime_next)
+// Row-sharded operators on the peer-memory transport: the first sync.push_ctas CTAs of the grid are
+// COMMUNICATION CTAs.  They take no tiles: they store the owned entries other ranks need straight
+// into those ranks' landing buffers (NVLink stores), fence at system scope and publish the sequence
+// number of this SpMV -- off the critical path of the CTAs that stream the matrix.  (Round 1 let the
+// first compute CTAs push before their own tiles, which made them the last to reach the end of the
+// pass: 35.1 us against 30.3 us for the others, profiles/r2_visit_b_2gpu_summary.txt.)
+__device__ __forceinline__ bool is_comm_cta(const CsrKernelArgs &a)
 {
-    // ---- peer-memory halo exchange, producer side ------------------------
-    // tiles [first_halo_tile, ntiles) read halo columns.  This SpMV has
-    // sequence number hseq; halo_seq is only advanced by the last CTA to
-    // finish, so every CTA reads the same value here.
+    return a.sync.win != nullptr && (int)blockIdx.x < a.sync.push_ctas;
+}
+// position of this CTA among the compute CTAs, and how many there are
+__device__ __forceinline__ int compute_rank(const CsrKernelArgs &a)
+{
+    return a.sync.win != nullptr ? (int)blockIdx.x - a.sync.push_ctas : (int)blockIdx.x;
+}
+__device__ __forceinline__ int compute_ctas(const CsrKernelArgs &a)
+{
+    return a.sync.win != nullptr ? (int)gridDim.x - a.sync.push_ctas : (int)gridDim.x;
+}
+
+template <bool XNC>
+__device__ __forceinline__ void halo_push(const CsrKernelArgs &a, const double *x1, unsigned long long hseq)
+{
     const int tid = threadIdx.x;
-    const double *h1 = a.h1;
-    const RedEntry *hll = nullptr;    // LL: records of the landing buffer, indexable by column ids > nloc
-    bool halo_ready = !(HALO && a.sync.win != nullptr);
-    bool push_pending = false;
-    if (HALO && a.sync.win != nullptr) {
-        const int push_rank = (int)blockIdx.x - a.sync.push_first;   // position among the pushing CTAs
-        if (push_rank >= 0 && push_rank < a.sync.push_ctas) {
-            const int buf = (int)(hseq & 1);
-            // landing buffer `buf` was last filled for SpMV hseq-2: wait until
-            // every consumer has acknowledged reading it
-            if (tid == 0 && hseq > 2)
-                for (int q = 0; q < kMaxRanks; q++)
-                    if (a.sync.dst_mask & (1u << q)) {
-                        unsigned spins = 0;
-                        while (ld_acquire_sys(&a.sync.win->ack[q]) < hseq - 2 && ++spins < kSpinLimit) {}
-                    }
-            __syncthreads();
-            for (int k = push_rank * kThreads + tid; k < a.sync.total_send; k += a.sync.push_ctas * kThreads) {
-                int q = 0;
-                while (k >= a.sync.send_off[q + 1]) q++;
-                if (LL)
-                    halo_ll_store(reinterpret_cast<RedEntry *>(a.sync.dst[q]) + buf * a.sync.dst_stride[q] +
-                                      (k - a.sync.send_off[q]),
-                                  (unsigned)hseq, ld_x<XNC>(a.x1 + a.sync.send_rows[k]));
-                else
-                    a.sync.dst[q][buf * a.sync.dst_stride[q] + (k - a.sync.send_off[q])] =
-                        ld_x<XNC>(a.x1 + a.sync.send_rows[k]);
-            }
-            push_pending = !LL;    // published after the first tile, see below (LL: nothing to publish)
+    const int buf = (int)(hseq & 1);
+    // landing buffer `buf` was last filled for SpMV hseq-2: wait until every consumer has
+    // acknowledged reading it
+    if (tid < kMaxRanks && hseq > 2 && (a.sync.dst_mask & (1u << tid))) {
+        const unsigned long long *ack = &a.sync.win->ack[tid];
+        spin_wait([&] { return ld_acquire_sys(ack) >= hseq - 2; }, a.fault, FAULT_HALO_ACK);
+    }
+    __syncthreads();
+    for (int k = (int)blockIdx.x * kThreads + tid; k < a.sync.total_send; k += a.sync.push_ctas * kThreads) {
+        int q = 0;
+        while (k >= a.sync.send_off[q + 1]) q++;
+        a.sync.dst[q][buf * a.sync.dst_stride[q] + (k - a.sync.send_off[q])] = ld_x<XNC>(x1 + a.sync.send_rows[k]);
+    }
+    __syncthreads();   // the CTA's stores happen-before thread 0's fence (cumulative)
+    if (tid == 0) {
+        __threadfence_system();
+        const unsigned t0 = atomicAdd(&a.sync.win->push_ticket, 1u);
+        if (t0 == (unsigned)a.sync.push_ctas - 1) {
+            a.sync.win->push_ticket = 0u;
+            __threadfence_system();
+            for (int q = 0; q < kMaxRanks; q++)
+                if (a.sync.dst_mask & (1u << q))
+                    *reinterpret_cast<volatile unsigned long long *>(&a.sync.peer[q]->hflag[buf][a.sync.me]) = hseq;
         }
     }
-    // The stores above need a system-scope fence before the sequence number may
-    // be published.  Issued right away that fence costs the pushing CTAs a few
-    // microseconds of NVLink round trip before they touch their first tile (and
-    // the whole grid waits for them at the end); issued after the first tile the
-    // stores have long landed and the fence is cheap.  Consumers only look at
-    // the flags when they reach their boundary tiles, at the END of their pass.
-    auto publish_push = [&]() {
-        __syncthreads();   // the CTA's stores happen-before thread 0's fence (cumulative)
-        if (tid == 0) {
-            const int buf = (int)(hseq & 1);
-            __threadfence_system();
-            const unsigned t0 = atomicAdd(&a.sync.win->push_ticket, 1u);
-            if (t0 == (unsigned)a.sync.push_ctas - 1) {
-                a.sync.win->push_ticket = 0u;
-                __threadfence_system();
-                for (int q = 0; q < kMaxRanks; q++)
-                    if (a.sync.dst_mask & (1u << q))
-                        *reinterpret_cast<volatile unsigned long long *>(&a.sync.peer[q]->hflag[buf][a.sync.me]) = hseq;
-            }
-        }
-        push_pending = false;
-    };
+}
+
+// One SpMV pass of this CTA over its tiles (round-robin over the compute CTAs), including -- for
+// row-sharded operators on the peer-memory transport -- the halo push by the communication CTAs and
+// the lazy wait before the first boundary tile.  hseq is the sequence number of this SpMV (HALO
+// only).  Dot partials accumulate in acc.
+//
+// Two-pass form, software-pipelined across tiles.  Per tile the TMA engine stages the val / node /
+// ptr slices in shared memory (double-buffered, evict-first in L2);
+//   gather  : every entry's x is gathered (kEntrySlots independent requests per thread);
+//   product : the ROUNDED product replaces the value in shared memory;
+//   row sums: one thread per row adds that row's products in STORED order
+// and the gathers of tile t are issued BEFORE the row sums of tile t-1, so that their latency (one
+// gather in five of the 5-point matrix is the first touch of an x line and comes from HBM, not from
+// L1/L2) overlaps the row sums, the y stores and the barrier of the previous tile instead of stalling
+// the product pass (round-2 diagnostic build of the unpipelined form: 46 % of a CTA's pass sat in
+// the product pass, 2.6 % waiting for TMA):
+//   iteration t:  wait stage(t) | gather x for t, load u for the rows of t-1 | row sums of t-1
+//                 | barrier (stage(t-1) free) | TMA for t+1 into stage(t-1)
+//                 | products of t into stage(t) | dot contributions of t-1 | barrier
+// The fused dot is kept out of the row sums: u for the rows of tile t-1 is loaded next to the gathers of
+// tile t and meets the finished row values only after the product pass of tile t, i.e. behind a point
+// where every load of the iteration has landed
+// -- inside the row sums it made them wait for the gathers in flight (288 us instead of 225 us).
+// Same rounded products, added in the same order: bit-identical to the serial reference loop.
+// Measured on the 4096^2 Poisson matrix: 226.6 -> 213.8 us (0.97 of the measured copy bandwidth),
+// with the dot 229.3 -> 225.4 us (profiles/r2_visit_c_1gpu_summary.txt, r2_visit_d_1gpu_summary.txt).
+template <int MODE, int NDOT, bool HALO, bool XNC>
+__device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, const SpmvVecs &v, unsigned char *smem,
+                                           uint64_t *mbar, TilePipe &pipe, double *acc, unsigned long long hseq,
+                                           bool prime_next)
+{
+    const int tid = threadIdx.x;
+    if (HALO && is_comm_cta(a)) {
+        halo_push<XNC>(a, v.x1, hseq);
+        return;
+    }
+    const int crank = HALO ? compute_rank(a) : (int)blockIdx.x;
+    const int cstride = HALO ? compute_ctas(a) : (int)gridDim.x;
+    const double *h1 = a.h1;
+    bool halo_ready = !(HALO && a.sync.win != nullptr);
 
     // thread 0 is the producer: it programs the TMA engine for one tile
     const uint64_t stream_policy = policy_evict_first();
@@ -298,169 +331,83 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
     };
 
 #ifdef SIGB_PHASE_TIMERS
-    unsigned long long c_wait = 0, c_prod = 0, c_rows = 0, c_tiles = 0;
+    unsigned long long c_wait = 0, c_gather = 0, c_prod = 0, c_tiles = 0;
 #endif
     SIGB_TCLK(tk_begin);
-    int t = blockIdx.x;
+    int t = crank;
     int4 d_cur = make_int4(0, 0, 0, 0), d_next = make_int4(0, 0, 0, 0);
     if (t < a.ntiles) d_cur = load_desc(a.tiles + t);
-    if (t + (int)gridDim.x < a.ntiles) d_next = load_desc(a.tiles + t + gridDim.x);
+    if (t + cstride < a.ntiles) d_next = load_desc(a.tiles + t + cstride);
     unsigned sidx = pipe.sidx;  // staged tiles consumed so far (identical in all threads)
     if (!pipe.primed && tid == 0 && t < a.ntiles && tile_staged(d_cur)) issue((int)(sidx & 1u), d_cur);
     pipe.primed = false;
 
-#ifdef SIGB_SPMV_PIPE
-    // ---- software-pipelined two-pass form (build variant _pipe) -------------------------------
-    // The x gathers of tile t are issued BEFORE the row sums of tile t-1 are formed, so that the
-    // latency of the gathers (one in five is the first touch of an x line and comes from HBM, not
-    // from L1/L2) overlaps the row sums, the y stores and the barrier of the previous tile instead
-    // of stalling the product pass; the gathered values wait in registers.  Same rounded products,
-    // added in the same stored order: results are bit-identical to the unpipelined form.
-    //   iteration t:  wait stage(t) | gather x for t | row sums of t-1 | barrier (stage(t-1) free)
-    //                 | TMA for t+1 into stage(t-1) | products of t into stage(t) | barrier
-    if (!RD) {
-        bool pending = false;              // a tile whose products are parked and whose rows are not summed yet
-        int4 d_pend = make_int4(0, 0, 0, 0);
-        int stage_pend = 0;
-        auto row_sums = [&](const int4 &d, int stage) {
-            unsigned char *base = smem + stage * kStageBytes;
-            const double *sval = reinterpret_cast<const double *>(base);
-            const int32_t *sptr = reinterpret_cast<const int32_t *>(base + kStageVal + kStageNode);
-            const int rs = d.x, re = d.y, ka = d.z & ~3, ra = d.x & ~3;
-            double ur[kTileRows / kThreads];
+    // the tile whose products are parked in shared memory and whose rows have not been summed yet
+    bool pending = false;
+    int4 d_pend = make_int4(0, 0, 0, 0);
+    int stage_pend = 0;
+    // the tile whose rows have been summed and whose dot contributions have not been added yet
+    bool dot_pending = false;
+    int4 d_dot = make_int4(0, 0, 0, 0);
+    double ur_dot[kRowSlots], z_dot[kRowSlots];
 #pragma unroll
-            for (int i = 0; i < kTileRows / kThreads; i++) {
-                const int r = rs + tid + i * kThreads;
-                ur[i] = (NDOT >= 1 && r < re) ? ld_x<XNC>(a.u + r) : 0.0;
-            }
+    for (int i = 0; i < kRowSlots; i++) { ur_dot[i] = 0.0; z_dot[i] = 0.0; }
+
+    auto flush_dot = [&]() {
+        if (NDOT >= 1 && dot_pending) {
 #pragma unroll
-            for (int i = 0; i < kTileRows / kThreads; i++) {
-                const int r = rs + tid + i * kThreads;
-                if (r < re) {
-                    const int b = sptr[r - ra] - 1 - ka, e = sptr[r + 1 - ra] - 1 - ka;
-                    double z = (MODE == MODE_ACC_INIT) ? a.y[r] : 0.0;
-                    for (int k = b; k < e; k++) z = add(z, sval[k]);
-                    emit_row<MODE, NDOT>(a, r, z, ur[i], acc);
-                }
-            }
-            fence_proxy_async();           // the stage is overwritten by the async proxy next
-        };
-        for (; t < a.ntiles; t += gridDim.x) {
-            const int tn = t + gridDim.x, tnn = tn + gridDim.x;
-            const bool have_next = tn < a.ntiles;
-            int4 d_next2 = make_int4(0, 0, 0, 0);
-            if (tnn < a.ntiles) d_next2 = load_desc(a.tiles + tnn);
-            const bool staged = tile_staged(d_cur);
-            if (HALO && !halo_ready && t >= a.first_halo_tile) {   // CTA-uniform, as in the unpipelined form
-                if (LL) {
-                    hll = reinterpret_cast<const RedEntry *>(a.sync.halo_base) + (hseq & 1) * a.sync.halo_stride -
-                          (a.nloc + 1);
-                } else {
-                    if (push_pending) publish_push();
-                    if (tid == 0) {
-                        for (int q = 0; q < kMaxRanks; q++)
-                            if (a.sync.src_mask & (1u << q)) {
-                                unsigned spins = 0;
-                                while (ld_acquire_sys(&a.sync.win->hflag[hseq & 1][q]) < hseq && ++spins < kSpinLimit) {}
-                            }
-                    }
-                    __syncthreads();
-                    h1 = a.sync.halo_base + (hseq & 1) * a.sync.halo_stride - (a.nloc + 1);
-                }
-                halo_ready = true;
-            }
-            if (staged) {
-                const int stage = (int)(sidx & 1u);
-                unsigned char *base = smem + stage * kStageBytes;
-                double *sval = reinterpret_cast<double *>(base);
-                const int32_t *snode = reinterpret_cast<const int32_t *>(base + kStageVal);
-                const int ks = d_cur.z, ke = d_cur.w, ka = ks & ~3;
-                const int cnt = ke - ka;
-                mbar_wait(&mbar[stage], (sidx >> 1) & 1u);
-                int c[kTileNnz / kThreads];
-                double xv[kTileNnz / kThreads];
-#pragma unroll
-                for (int i = 0; i < kTileNnz / kThreads; i++) {
-                    const int k = tid + i * kThreads;
-                    c[i] = (k < cnt) ? snode[k] : 1;
-                }
-                if (LL && HALO && t >= a.first_halo_tile) {
-#pragma unroll
-                    for (int i = 0; i < kTileNnz / kThreads; i++) {
-                        const int k = tid + i * kThreads;
-                        xv[i] = (c[i] > a.nloc && k >= ks - ka && k < cnt) ? halo_ll_load(hll + c[i], (unsigned)hseq)
-                                                                           : __ldcg(a.x1 + min(c[i], a.nloc));
-                    }
-                } else if (HALO && t >= a.first_halo_tile) {
-#pragma unroll
-                    for (int i = 0; i < kTileNnz / kThreads; i++) {
-                        const double *src = (c[i] > a.nloc) ? h1 + c[i] : a.x1 + c[i];
-                        xv[i] = __ldcg(src);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < kTileNnz / kThreads; i++) xv[i] = ld_x<XNC>(a.x1 + c[i]);
-                }
-                if (pending) row_sums(d_pend, stage_pend);     // ... while the gathers are in flight
-                __syncthreads();                               // the other stage has been consumed by everybody
-                if (tid == 0 && have_next && tile_staged(d_next)) issue((int)((sidx + 1u) & 1u), d_next);
-#pragma unroll
-                for (int i = 0; i < kTileNnz / kThreads; i++) {
-                    const int k = tid + i * kThreads;
-                    if (k < cnt) sval[k] = mul(sval[k], xv[i]);
-                }
-                __syncthreads();
-                pending = true;
-                d_pend = d_cur;
-                stage_pend = stage;
-                sidx++;
-            } else {
-                if (pending) {
-                    row_sums(d_pend, stage_pend);
-                    __syncthreads();
-                    pending = false;
-                }
-                if (tid == 0 && have_next && tile_staged(d_next)) issue((int)(sidx & 1u), d_next);   // both stages are free
-                long_row<MODE, NDOT, HALO, XNC, LL>(a, d_cur, h1, acc, hll, (unsigned)hseq);
-            }
-            d_cur = d_next;
-            d_next = d_next2;
-            if (HALO && push_pending) publish_push();
+            for (int i = 0; i < kRowSlots; i++)
+                if (d_dot.x + tid + i * kThreads < d_dot.y) dot_row<NDOT>(ur_dot[i], z_dot[i], acc);
         }
-        if (pending) {
-            row_sums(d_pend, stage_pend);
-            __syncthreads();
+        dot_pending = false;
+    };
+    auto load_u_pending = [&]() {
+        if (NDOT >= 1) {
+#pragma unroll
+            for (int i = 0; i < kRowSlots; i++) {
+                const int r = d_pend.x + tid + i * kThreads;
+                ur_dot[i] = (r < d_pend.y) ? ld_x<XNC>(v.u + r) : 0.0;
+            }
         }
-    }
-#endif
-    for (; t < a.ntiles; t += gridDim.x) {
-        const int tn = t + gridDim.x, tnn = tn + gridDim.x;
+    };
+    // rows of the pending tile, summed in stored order
+    auto row_sums = [&]() {
+        unsigned char *base = smem + stage_pend * kStageBytes;
+        const double *sval = reinterpret_cast<const double *>(base);
+        const int32_t *sptr = reinterpret_cast<const int32_t *>(base + kStageVal + kStageNode);
+        const int rs = d_pend.x, re = d_pend.y, ka = d_pend.z & ~3, ra = d_pend.x & ~3;
+#pragma unroll
+        for (int i = 0; i < kRowSlots; i++) {
+            const int r = rs + tid + i * kThreads;
+            if (r < re) {
+                const int b = sptr[r - ra] - 1 - ka, e = sptr[r + 1 - ra] - 1 - ka;
+                const double z = ordered_sum(sval, b, e, (MODE == MODE_ACC_INIT) ? v.y[r] : 0.0);
+                z_dot[i] = store_row<MODE>(a, v, r, z);
+            }
+        }
+        d_dot = d_pend;
+        dot_pending = NDOT >= 1;
+        pending = false;
+        fence_proxy_async();           // the stage is overwritten by the async proxy next
+    };
+
+    for (; t < a.ntiles; t += cstride) {
+        const int tn = t + cstride, tnn = tn + cstride;
         const bool have_next = tn < a.ntiles;
         int4 d_next2 = make_int4(0, 0, 0, 0);
         if (tnn < a.ntiles) d_next2 = load_desc(a.tiles + tnn);  // two tiles ahead, off the critical path
         const bool staged = tile_staged(d_cur);
-        const unsigned sidx_after = sidx + (staged ? 1u : 0u);
-        if (tid == 0 && have_next && tile_staged(d_next)) issue((int)(sidx_after & 1u), d_next);
 
-        if (HALO && !halo_ready && t >= a.first_halo_tile) {   // CTA-uniform
-            // never wait on peers while our own push is unpublished (two ranks
-            // whose pushing CTAs start on a boundary tile would wait forever)
-            if (LL) {
-                // nothing to wait for here: every gathered record is polled where it is read
-                hll = reinterpret_cast<const RedEntry *>(a.sync.halo_base) + (hseq & 1) * a.sync.halo_stride -
-                      (a.nloc + 1);
-            } else {
-                if (push_pending) publish_push();
-                if (tid == 0) {
-                    for (int q = 0; q < kMaxRanks; q++)
-                        if (a.sync.src_mask & (1u << q)) {
-                            unsigned spins = 0;
-                            while (ld_acquire_sys(&a.sync.win->hflag[hseq & 1][q]) < hseq && ++spins < kSpinLimit) {}
-                        }
-                }
-                __syncthreads();
-                h1 = a.sync.halo_base + (hseq & 1) * a.sync.halo_stride - (a.nloc + 1);
+        // tiles [first_halo_tile, ntiles) read halo columns: wait for the peers' pushes of this
+        // SpMV when the first one comes up (CTA-uniform; at the END of a CTA's pass, the tiles
+        // being ordered interior first)
+        if (HALO && !halo_ready && t >= a.first_halo_tile) {
+            if (tid < kMaxRanks && (a.sync.src_mask & (1u << tid))) {
+                const unsigned long long *flag = &a.sync.win->hflag[hseq & 1][tid];
+                spin_wait([&] { return ld_acquire_sys(flag) >= hseq; }, a.fault, FAULT_HALO_FLAG);
             }
+            __syncthreads();
+            h1 = a.sync.halo_base + (hseq & 1) * a.sync.halo_stride - (a.nloc + 1);
             halo_ready = true;
         }
 
@@ -469,166 +416,85 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
             unsigned char *base = smem + stage * kStageBytes;
             double *sval = reinterpret_cast<double *>(base);
             const int32_t *snode = reinterpret_cast<const int32_t *>(base + kStageVal);
-            const int32_t *sptr = reinterpret_cast<const int32_t *>(base + kStageVal + kStageNode);
-            const int rs = d_cur.x, re = d_cur.y, ks = d_cur.z, ke = d_cur.w;
-            const int ka = ks & ~3, ra = rs & ~3;
+            const int ks = d_cur.z, ke = d_cur.w, ka = ks & ~3;
+            const int cnt = ke - ka;
             SIGB_TCLK(tk0);
             mbar_wait(&mbar[stage], (sidx >> 1) & 1u);
             SIGB_TCLK(tk1);
-            if (RD) {
-                // ---- row direct: one thread per row, products formed inline -----
-                SIGB_TCLK(tk2);
-                double ur[kTileRows / kThreads];
+            // ---- gathers of this tile (entries before ks belong to the previous tile and hold
+            // valid columns, so every gather is in range)
+            int c[kEntrySlots];
+            double xv[kEntrySlots];
 #pragma unroll
-                for (int i = 0; i < kTileRows / kThreads; i++) {
-                    const int r = rs + tid + i * kThreads;
-                    ur[i] = (NDOT >= 1 && r < re) ? ld_x<XNC>(a.u + r) : 0.0;
-                }
-                const bool boundary = HALO && t >= a.first_halo_tile;   // CTA-uniform
-#pragma unroll
-                for (int i = 0; i < kTileRows / kThreads; i++) {
-                    const int r = rs + tid + i * kThreads;
-                    if (r < re) {
-                        const int b = sptr[r - ra] - 1 - ka, e = sptr[r + 1 - ra] - 1 - ka;
-                        double z = (MODE == MODE_ACC_INIT) ? a.y[r] : 0.0;
-                        for (int k = b; k < e; k += 4) {
-                            // Four entries per trip.  Indices past the row's end are clamped to its
-                            // last entry (a valid read) and their products are not added, so there is
-                            // no branch inside the trip: the four gathers are issued back to back
-                            // (with per-entry branches the compiler serialised them behind the adds).
-                            int c[4];
-                            double v[4], xv[4], pr[4];
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                const int kk = min(k + j, e - 1);
-                                c[j] = snode[kk];
-                                v[j] = sval[kk];
-                            }
-                            if (boundary && LL) {
-#pragma unroll
-                                for (int j = 0; j < 4; j++)
-                                    xv[j] = (c[j] > a.nloc) ? halo_ll_load(hll + c[j], (unsigned)hseq)
-                                                            : __ldcg(a.x1 + c[j]);
-                            } else if (boundary) {
-#pragma unroll
-                                for (int j = 0; j < 4; j++) {
-                                    const double *src = (c[j] > a.nloc) ? h1 + c[j] : a.x1 + c[j];
-                                    xv[j] = __ldcg(src);
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 4; j++) xv[j] = ld_x<XNC>(a.x1 + c[j]);
-                            }
-#pragma unroll
-                            for (int j = 0; j < 4; j++) pr[j] = mul(v[j], xv[j]);
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                const double zn = add(z, pr[j]);
-                                z = (k + j < e) ? zn : z;
-                            }
-                        }
-                        emit_row<MODE, NDOT>(a, r, z, ur[i], acc);
-                    }
-                }
-                fence_proxy_async();
-                __syncthreads();
-                SIGB_TCLK(tk3);
-                SIGB_TACC(c_wait, tk1, tk0);
-                SIGB_TACC(c_prod, tk2, tk1);
-                SIGB_TACC(c_rows, tk3, tk2);
-#ifdef SIGB_PHASE_TIMERS
-                c_tiles++;
-#endif
-            } else {
-            // ---- phase 1: products, in place --------------------------------
-            // (entries before ks belong to the previous tile and hold valid
-            // columns, so every gather below is in range)
-            const int cnt = ke - ka;
-            int c[kTileNnz / kThreads];
-            double v[kTileNnz / kThreads];
-#pragma unroll
-            for (int i = 0; i < kTileNnz / kThreads; i++) {
+            for (int i = 0; i < kEntrySlots; i++) {
                 const int k = tid + i * kThreads;
                 c[i] = (k < cnt) ? snode[k] : 1;
-                v[i] = (k < cnt) ? sval[k] : 0.0;
             }
-            double xv[kTileNnz / kThreads];
-            // Only boundary tiles can hold halo columns, and whether a tile is one
-            // is uniform over the CTA: interior tiles take the plain gather; in
-            // boundary tiles the address is selected (no divergent branch between
-            // the gathers, which would serialise them) and everything is read at
-            // L2 -- halo entries are written by peers, so L1 must not serve them.
-            if (LL && HALO && t >= a.first_halo_tile) {
-                // (entries of the previous tile that share this tile's first 16-byte group are
-                //  multiplied too and never used: they must not be waited for)
+            // Only boundary tiles can hold halo columns, and whether a tile is one is uniform
+            // over the CTA: interior tiles take the plain gather; in boundary tiles the address
+            // is selected (no divergent branch between the gathers, which would serialise them)
+            // and everything is read at L2 -- halo entries are written by peers, so L1 must not
+            // serve them.
+            if (HALO && t >= a.first_halo_tile) {
 #pragma unroll
-                for (int i = 0; i < kTileNnz / kThreads; i++) {
-                    const int k = tid + i * kThreads;
-                    xv[i] = (c[i] > a.nloc && k >= ks - ka && k < cnt) ? halo_ll_load(hll + c[i], (unsigned)hseq)
-                                                                       : __ldcg(a.x1 + min(c[i], a.nloc));
-                }
-            } else if (HALO && t >= a.first_halo_tile) {
-#pragma unroll
-                for (int i = 0; i < kTileNnz / kThreads; i++) {
-                    const double *src = (c[i] > a.nloc) ? h1 + c[i] : a.x1 + c[i];
+                for (int i = 0; i < kEntrySlots; i++) {
+                    const double *src = (c[i] > a.nloc) ? h1 + c[i] : v.x1 + c[i];
                     xv[i] = __ldcg(src);
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < kTileNnz / kThreads; i++) xv[i] = ld_x<XNC>(a.x1 + c[i]);
+                for (int i = 0; i < kEntrySlots; i++) xv[i] = ld_x<XNC>(v.x1 + c[i]);
             }
-#pragma unroll
-            for (int i = 0; i < kTileNnz / kThreads; i++) {
-                const int k = tid + i * kThreads;
-                if (k < cnt) sval[k] = mul(v[i], xv[i]);
-            }
-            __syncthreads();
+            // u for the rows of the PENDING tile, next to the gathers: consumed after the product pass
+            if (pending) load_u_pending();
+            // ---- row sums of the previous tile while the gathers are in flight
+            if (pending) row_sums();
+            __syncthreads();                               // the other stage has been consumed by everybody
+            if (tid == 0 && have_next && tile_staged(d_next)) issue((int)((sidx + 1u) & 1u), d_next);
             SIGB_TCLK(tk2);
-            // ---- phase 2: per-row sums in stored order ----------------------
-            // operands of the fused dot go through the same read-only path as
-            // the gathers, so rows with a (near-)diagonal entry hit L1
-            double ur[kTileRows / kThreads];
+            // ---- products, in place
 #pragma unroll
-            for (int i = 0; i < kTileRows / kThreads; i++) {
-                const int r = rs + tid + i * kThreads;
-                ur[i] = (NDOT >= 1 && r < re) ? ld_x<XNC>(a.u + r) : 0.0;
+            for (int i = 0; i < kEntrySlots; i++) {
+                const int k = tid + i * kThreads;
+                if (k < cnt) sval[k] = mul(sval[k], xv[i]);
             }
-#pragma unroll
-            for (int i = 0; i < kTileRows / kThreads; i++) {
-                const int r = rs + tid + i * kThreads;
-                if (r < re) {
-                    const int b = sptr[r - ra] - 1 - ka, e = sptr[r + 1 - ra] - 1 - ka;
-                    double z = (MODE == MODE_ACC_INIT) ? a.y[r] : 0.0;
-                    for (int k = b; k < e; k++) z = add(z, sval[k]);
-                    emit_row<MODE, NDOT>(a, r, z, ur[i], acc);
-                }
-            }
-            // the stage is overwritten by the async proxy next: order our
-            // generic-proxy accesses before it
-            fence_proxy_async();
+            flush_dot();                                   // every load of this iteration has landed
             __syncthreads();
             SIGB_TCLK(tk3);
             SIGB_TACC(c_wait, tk1, tk0);
-            SIGB_TACC(c_prod, tk2, tk1);
-            SIGB_TACC(c_rows, tk3, tk2);
+            SIGB_TACC(c_gather, tk2, tk1);
+            SIGB_TACC(c_prod, tk3, tk2);
 #ifdef SIGB_PHASE_TIMERS
             c_tiles++;
 #endif
-            }   // !RD
+            pending = true;
+            d_pend = d_cur;
+            stage_pend = stage;
+            sidx++;
         } else {
-            long_row<MODE, NDOT, HALO, XNC, LL>(a, d_cur, h1, acc, hll, (unsigned)hseq);
+            if (pending) {
+                load_u_pending();
+                row_sums();
+                __syncthreads();
+            }
+            flush_dot();
+            if (tid == 0 && have_next && tile_staged(d_next)) issue((int)(sidx & 1u), d_next);   // both stages are free
+            long_row<MODE, NDOT, HALO, XNC>(a, v, d_cur, h1, acc);
         }
-        sidx = sidx_after;
         d_cur = d_next;
         d_next = d_next2;
-        if (HALO && push_pending) publish_push();
     }
-    if (HALO && push_pending) publish_push();   // a CTA without tiles
+    if (pending) {
+        load_u_pending();
+        row_sums();
+        __syncthreads();
+    }
+    flush_dot();
 #ifdef SIGB_PHASE_TIMERS
     if (tid == 0 && a.tile_dbg != nullptr) {
         atomicAdd(a.tile_dbg + 0, c_wait);
-        atomicAdd(a.tile_dbg + 1, c_prod);
-        atomicAdd(a.tile_dbg + 2, c_rows);
+        atomicAdd(a.tile_dbg + 1, c_gather);
+        atomicAdd(a.tile_dbg + 2, c_prod);
         atomicAdd(a.tile_dbg + 3, (unsigned long long)(clock64() - tk_begin));
         atomicAdd(a.tile_dbg + 4, c_tiles);
         atomicAdd(a.tile_dbg + 5, 1ull);
@@ -638,11 +504,23 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, unsigned char
     // persistent callers: the matrix does not change between SpMVs, so the first
     // tile of the NEXT pass can already be in flight while other phases run
     if (prime_next) {
-        if (blockIdx.x < (unsigned)a.ntiles) {
-            const int4 d0 = load_desc(a.tiles + blockIdx.x);
+        if (crank < a.ntiles) {
+            const int4 d0 = load_desc(a.tiles + crank);
             if (tid == 0 && tile_staged(d0)) issue((int)(sidx & 1u), d0);
         }
         pipe.primed = true;
+    }
+}
+
+// The tile a persistent caller primed for a pass that will not run must land before the CTA exits.
+__device__ __forceinline__ void drain_primed(const CsrKernelArgs &a, uint64_t *mbar, const TilePipe &pipe, bool halo)
+{
+    if (!pipe.primed) return;
+    if (halo && is_comm_cta(a)) return;
+    const int crank = halo ? compute_rank(a) : (int)blockIdx.x;
+    if (crank < a.ntiles) {
+        const int4 d0 = load_desc(a.tiles + crank);
+        if (tile_staged(d0)) mbar_wait(&mbar[pipe.sidx & 1u], (pipe.sidx >> 1) & 1u);
     }
 }
 

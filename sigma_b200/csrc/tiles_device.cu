@@ -1,8 +1,8 @@
-// tiles_device.cu -- EXPERIMENTAL, opt-in (SIGB_DEVICE_TILES=1; compiled in, not the
-// default path, not yet run on a GPU): the row tiling of the streaming CSR kernel built on
-// the device, so that device-side transposes and matrix copies need no read-back of `ptr`
-// and no host loop (profiles/README.md: that read-back + loop is most of what a device
-// copy costs today).
+// tiles_device.cu -- the row tiling of the streaming CSR kernel built on the device, so
+// that device-side transposes and matrix copies need no read-back of `ptr` and no host
+// loop (that read-back + loop was most of what a device copy cost in round 1; with the
+// stream-ordered scratch of api.cu a transposing copy of 21 M entries went from 12.7 ms
+// to 4.9 ms, profiles/r2_visit_a_1gpu_summary.txt).
 //
 // The tiling is the greedy one of build_tiles_host (kernels_spmv.cu): from row s a tile
 // runs to next(s) = the largest e <= s + kTileRows with ptr(e) - ptr(s) <= kTileCap (at
@@ -15,9 +15,8 @@
 //      jump(0) reached the end return immediately);
 //   3. the marked rows are compacted with the scan of transpose.cu into the tile table,
 //      followed by the sub-table of tiles that hold entries.
-// The result equals build_tiles_host bit for bit (numpy replica of these steps checked
-// against the greedy walk in the round-1 session; gated GPU test:
-// tests/test_gpu_experimental.py).
+// The result equals build_tiles_host bit for bit (tests/test_row_tiles.py: numpy replica of
+// these steps against the greedy walk; tests/test_gpu_convert.py: device against host).
 #include <algorithm>
 
 #include "internal.h"
@@ -113,12 +112,6 @@ tile_emit_kernel(const int32_t *__restrict__ mark, const int32_t *__restrict__ n
 
 }  // namespace
 
-bool device_tiles_enabled()
-{
-    static const bool on = env_int("SIGB_DEVICE_TILES", 0) == 1;
-    return on;
-}
-
 // Tile table (+ its sub-table of tiles with entries) of a pattern whose ptr lives on the
 // device.  max_d / min_d: extreme line lengths (either may be null).
 int build_tiles_device(const int32_t *ptr1_dev, int32_t nrows, CsrView &v, int32_t *max_d, int32_t *min_d)
@@ -202,8 +195,7 @@ using namespace sigb;
 extern "C" {
 
 // Diagnostic: the device-built tiling of a pattern given by its host ptr (uploaded here),
-// in the layout of sigb_debug_row_tiles.  Runs the experimental path whatever
-// SIGB_DEVICE_TILES says.
+// in the layout of sigb_debug_row_tiles.
 int sigb_debug_row_tiles_dev(int32_t n, const int32_t *ptr1, int32_t *tiles, int32_t *ntiles)
 {
     SIGB_CHECK(require_init());

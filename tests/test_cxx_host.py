@@ -14,10 +14,9 @@ PROGS = ["solver_test_diffusion_1d", "solver_test_advection_diffusion_1d", "solv
          "solver_test_incomplete_cholesky"]
 
 
-# written after the last GPU visit of round 1: compiled on every run, executed only with
-# SIGB_TEST_EXPERIMENTAL=1 until they have passed on a GPU once (then move them into PROGS)
-PROGS_NOT_YET_RUN = ["matrix_test_strategy", "matrix_test_set_multiple_entries", "matrix_test_set_entry_with_realloc",
-                     "matrix_test_permute"]
+# (first run on a GPU in round 2, visit r2a)
+PROGS += ["matrix_test_strategy", "matrix_test_set_multiple_entries", "matrix_test_set_entry_with_realloc",
+          "matrix_test_permute"]
 
 
 def build():
@@ -26,22 +25,13 @@ def build():
 
 def test_cxx_programs_compile_and_link():
     build()
-    for p in PROGS + PROGS_NOT_YET_RUN:
+    for p in PROGS:
         assert os.path.exists(os.path.join(CXX, "_build", p))
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("prog", PROGS)
 def test_reference_test_program(prog):
-    build()
-    r = subprocess.run([os.path.join(CXX, "_build", prog), "-v"], capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, r.stdout + r.stderr
-
-
-@pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("SIGB_TEST_EXPERIMENTAL") != "1", reason="not yet run on a GPU: set SIGB_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("prog", PROGS_NOT_YET_RUN)
-def test_reference_test_program_not_yet_run(prog):
     build()
     r = subprocess.run([os.path.join(CXX, "_build", prog), "-v"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr

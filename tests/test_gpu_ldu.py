@@ -54,6 +54,38 @@ def test_factors_and_solve_bit_exact(sb, orc, case, fmt):
     assert np.array_equal(pc.solve(A, np.zeros(n), b), orc.ldu_solve(F2, b))
 
 
+def deep_cases():
+    """Schedules deep enough (> 64 levels, >= 32 chunks) for the chunked sweeps of csrc/ldu.cu."""
+    from test_ldu_symbolic import shuffled
+
+    p, n_, v = G.poisson2d_csr(64)
+    yield "poisson64", 64 * 64, p, n_, v
+    yield "poisson48_shuffled", 48 * 48, G.poisson2d_csr(48)[0], *shuffled(*G.poisson2d_csr(48), 7)
+    p, n_, v = G.fem_p1_csr(70)
+    yield "fem70_shuffled", 70 * 70, p, *shuffled(p, n_, v, 3)
+    yield "tridiag5000", 5000, *G.tridiag_csr(5000, 2.5, -1.0, -0.5)
+
+
+@pytest.mark.parametrize("case", list(deep_cases()), ids=lambda c: c[0])
+def test_chunked_sweeps_bit_exact(sb, orc, case):
+    """Deep level schedules run the triangular solves as chunked sweeps (one launch per sweep, every
+    thread a contiguous chunk of rows, waiting for exactly the entries it reads): same arithmetic per
+    row in stored order, so pc%solve must equal the serial loops bit for bit -- repeatedly (the
+    sequence numbers of the published entries advance) and for csr and csc sources."""
+    _, n, ptr, node, val = case
+    for fmt in ("csr", "csc"):
+        A, O = in_format(sb, orc, fmt, n, ptr, node, val)
+        F = orc.ldu_setup(O)
+        pc = sb.ldu()
+        pc.setup(A)
+        nf, nb = same_factors(pc, F)
+        assert nf > 64 and nb > 64
+        rng = np.random.default_rng(1)
+        for _ in range(3):
+            b = rng.standard_normal(n)
+            assert np.array_equal(pc.solve(A, np.zeros(n), b), orc.ldu_solve(F, b))
+
+
 def test_incomplete_cholesky_like_the_reference(sb, orc):
     """test/solver_test_incomplete_cholesky.f90: nn = 128 random weighted graph Laplacian + I;
     the factorisation as a stationary solver (10 nn sweeps, 1e-14, :182-202) and as the
@@ -127,14 +159,35 @@ def test_ldu_errors(sb):
     assert e.value.status == 7
     pc = sb.ldu()
     pc.setup(sq)
-    s = sb.bicgstab(1e-12)
-    s.setup(sq)
-    with pytest.raises(sb.SigmaError) as e:      # only cg drives the ldu preconditioner on the device
-        s.solve(sq, np.zeros(2), np.ones(2), pc)
-    assert e.value.status == 7
     # 2 x 2 by hand: D = [4, 3 - 1/4], L21 = 1/4, U12 = 1/4
     Lptr, Lnode, Lval, Uptr, Unode, Uval, D, nf, nb = pc.factors()
     assert np.array_equal(D, [4.0, 2.75]) and np.array_equal(Lval, [0.25]) and np.array_equal(Uval, [0.25])
     assert (nf, nb) == (2, 2)
     x = pc.solve(sq, np.zeros(2), np.array([5.0, 4.0]))
     assert np.allclose(x, [1.0, 1.0], rtol=0, atol=1e-15)
+
+
+def test_bicgstab_with_ldu_preconditioner(sb, orc):
+    """bicgstab_solve_pc with pc = ldu() (bicgstab_solvers.f90:182-237; linear_solve_pc takes any
+    linear_solver): iterations within 5 % of the oracle's restatement (the count of BiCGSTAB on a
+    random nonsymmetric operator moves with summation order alone), solution 1e-10."""
+    for nn, seed in ((300, 4), (2000, 5)):
+        ptr, node, val = G.erdos_renyi_csr(nn, seed=seed, weights="random", skew=True, shift=1.0)
+        A = sb.csr_matrix(nn, nn, ptr, node, val)
+        O = orc.Matrix(orc.CSR, nn, nn, node, val, ptr=ptr)
+        F = orc.ldu_setup(O)
+        v = np.random.default_rng(seed).random(nn)
+        f = orc.matvec(O, v)
+        tol = 1e-13
+        s, pc = sb.bicgstab(tol), sb.ldu()
+        s.set_max_iterations(50 * nn); s.setup(A); pc.setup(A)
+        x = s.solve(A, np.zeros(nn), f, pc)
+        it, res2, capped = s.info()
+        xo, ito, _, cappedo = orc.bicgstab_solve_ldu(O, np.zeros(nn), f, F, tol, 50 * nn)
+        assert not capped and not cappedo and within(it, ito, 0.05), (it, ito)
+        assert np.abs(x - xo).max() <= 1e-10 * np.abs(xo).max()
+        assert np.abs(x - v).max() <= 1e-10
+        # a capped solve stops where it is told to
+        s2 = sb.bicgstab(tol); s2.set_max_iterations(3); s2.setup(A)
+        s2.solve(A, np.zeros(nn), f, pc)
+        assert s2.info()[0] == 3 and s2.info()[2]
