@@ -454,6 +454,36 @@ SIGB_API int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global,
                                   const int32_t *node_glob1,
                                   const int32_t *send_counts,
                                   const int32_t *send_rows1, sigb_matrix_t *A);
+/* ---- single-process multi-GPU mode ---------------------------------------
+ * One caller thread, all GPUs of the box, through the same entry points as a
+ * single GPU.  Replaces nothing in the reference (which is serial); the seam is
+ * the block-row loop of composite_matvec_add
+ * (src/matrix/sparse_matrix_composites.f90:1076-1100) behind the unchanged
+ * solver interface (src/linear_operator/linear_operator_interface.f90:108-123):
+ * a serial `use sigma` caller keeps calling A%matvec(x, y) and
+ * solver%solve(A, x, b) on whole vectors.
+ *
+ *  sigb_mgpu_init(ndev)   ndev <= 0: every visible GPU.  One worker thread per GPU
+ *                         inside the library, peer access between all pairs, the
+ *                         peer-memory transport of the row-sharded operators (no
+ *                         NCCL, no IPC handles).  SIGB_ERR_COMM when two of the
+ *                         GPUs cannot address each other: there is no fallback.
+ *  sigb_mgpu_csr_create   whole n x n CSR pattern in (1-based ptr / node as the
+ *                         Fortran holds them): partition into row blocks balanced
+ *                         by stored entries, halo lists and send lists are derived
+ *                         here (bit-identical to sigb_partition_rows /
+ *                         sigb_halo_build) and one row block goes to every GPU.
+ * The handle is then used with WHOLE host arrays in sigb_matrix_set_values,
+ * sigb_matvec, sigb_matvec_add, sigb_matrix_get_dims, sigb_solver_setup (cg,
+ * bicgstab, jacobi), sigb_solver_solve (pc: jacobi), sigb_solver_get_info,
+ * sigb_solver_get_vector and the destroy calls; the *_dev entry points, matvec_t,
+ * copies, expressions, ldu and the eigensolvers return SIGB_ERR_UNSUPPORTED for it. */
+SIGB_API int sigb_mgpu_init(int ndev);
+SIGB_API int sigb_mgpu_finalize(void);
+SIGB_API int sigb_mgpu_device_count(int *ndev);
+SIGB_API int sigb_mgpu_csr_create(int32_t n, const int32_t *ptr1, const int32_t *node1,
+                                  sigb_matrix_t *A);
+
 /* Halo / send lists of a distributed matrix (index parity checks). */
 SIGB_API int sigb_dist_get_halo(sigb_matrix_t A, int32_t *nhalo, int32_t *halo);
 

@@ -102,6 +102,10 @@ PROTOTYPES = {
     "sigb_comm_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "sigb_dist_csr_create": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _pvp]),
     "sigb_dist_get_halo": (C.c_int, [_vp, _pi32, _vp]),
+    "sigb_mgpu_init": (C.c_int, [C.c_int]),
+    "sigb_mgpu_finalize": (C.c_int, []),
+    "sigb_mgpu_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "sigb_mgpu_csr_create": (C.c_int, [_i32, _vp, _vp, _pvp]),
 }
 
 _lib = None

@@ -35,7 +35,7 @@ __all__ = ["init", "Graph", "Matrix", "Solver", "cg", "bicgstab", "jacobi", "ldu
            "generalized_lanczos", "generalized_eigensolve",
            "csr_matrix", "csc_matrix", "ellpack_matrix", "SigmaError", "launch_count", "set_stream",
            "synchronize", "Expression", "operator_sum", "operator_product", "adjoint", "sparse_matrix",
-           "multiple_values_stream"]
+           "multiple_values_stream", "mgpu_init", "mgpu_finalize", "mgpu_csr_matrix"]
 
 
 def init(device: int = -1):
@@ -284,6 +284,30 @@ def multiple_values_stream(is1, js1, B):
 def csr_matrix(n, m, ptr1, node1, val):
     """type(csr_matrix): A%init(n, m); A%set_graph(g); values as stored."""
     return Matrix(Graph.cs(n, m, ptr1, node1, ROW)).set_values(val)
+
+
+def mgpu_init(ndev: int = 0) -> int:
+    """Single-process multi-GPU mode (sigb_mgpu_init): one worker thread per GPU inside the library.
+    Returns the number of GPUs in use."""
+    check(lib().sigb_mgpu_init(int(ndev)))
+    n = C.c_int()
+    check(lib().sigb_mgpu_device_count(C.byref(n)))
+    return n.value
+
+
+def mgpu_finalize():
+    check(lib().sigb_mgpu_finalize())
+
+
+def mgpu_csr_matrix(n, ptr1, node1, val):
+    """type(csr_matrix) spread over the GPUs of mgpu_init: the whole pattern in, row blocks / halo /
+    send lists derived in the library; matvec and the solvers take whole host vectors."""
+    ptr1, node1 = as_i32(ptr1), as_i32(node1)
+    if ptr1.size != n + 1:
+        raise SigmaError(_capi.ERR_ARG, "ptr must have n+1 entries")
+    h = C.c_void_p()
+    check(lib().sigb_mgpu_csr_create(n, ptr(ptr1), ptr(node1), C.byref(h)))
+    return Matrix(None, handle=h).set_values(val)
 
 
 def csc_matrix(nrow, ncol, ptr1, node1, val):

@@ -33,7 +33,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 
 Ctx &ctx()
 {
-    static Ctx c;
+    static thread_local Ctx c;
     return c;
 }
 
@@ -64,7 +64,7 @@ int check_fault(const char *where)
 // entries, profiles/r2_visit_a_1gpu_summary.txt).  Falls back to cudaMalloc when the driver has no pool.
 static bool async_alloc_enabled()
 {
-    static int v = -1;
+    static thread_local int v = -1;   // per device: every host thread of this library drives one GPU
     if (v < 0) {
         v = 1;
         cudaMemPool_t pool = nullptr;
@@ -295,6 +295,8 @@ int sigb_finalize(void)
     cudaFree(c.tickets);
     cudaFreeHost(c.pinned);
     cudaFreeHost(c.fault);
+    cudaFree(c.stage[0]);
+    cudaFree(c.stage[1]);
     cudaStreamDestroy(c.own_stream);
     cudaStreamDestroy(c.aux_stream);
     c = Ctx();
@@ -315,7 +317,7 @@ int sigb_synchronize(void)
     return check_fault("sigb_synchronize");
 }
 
-int64_t sigb_launch_count(void) { return ctx().launches; }
+int64_t sigb_launch_count(void) { return ctx().launches + mgpu_launch_count(); }
 
 int sigb_dev_alloc(int64_t bytes, void **ptr_dev)
 {
@@ -500,6 +502,7 @@ int sigb_matrix_create(sigb_graph_t g, sigb_matrix_t *out)
 int sigb_matrix_set_values(sigb_matrix_t A, const double *val, int64_t count)
 {
     SIGB_REQUIRE(A && val, SIGB_ERR_ARG, "sigb_matrix_set_values: bad argument");
+    if (A->mg) return mgpu_set_values(A, val, count);
     SIGB_REQUIRE(!A->op, SIGB_ERR_UNSUPPORTED, "sigb_matrix_set_values: an operator expression has no values of its own");
     sigb_graph_t g = A->g;
     cudaStream_t st = ctx().stream;
@@ -531,6 +534,7 @@ int sigb_matrix_destroy(sigb_matrix_t A)
     // remove_reference; the mirror goes away with its last owner (an expression
     // that still points at this operator keeps it alive)
     if (--A->refcount > 0) return SIGB_OK;
+    if (A->mg) mgpu_matrix_free(A);
     cudaFree(A->val);
     cudaFree(A->val_t);
     if (A->dist) dist_destroy(A);
@@ -549,7 +553,9 @@ int sigb_matrix_get_dims(sigb_matrix_t A, int32_t *nrow, int32_t *ncol, int64_t 
         // composite_mat_get_nnz sums its blocks (sparse_matrix_composites.f90:445-460);
         // the lazy expressions hold no entries of their own
         int64_t total = 0;
-        if (A->op) {
+        if (A->mg) {
+            total = mgpu_nnz(A);
+        } else if (A->op) {
             if (A->op->kind == OP_COMPOSITE)
                 for (sigb_matrix_t k : A->op->kids) {
                     int64_t sub = 0;
@@ -566,6 +572,7 @@ int sigb_matrix_get_dims(sigb_matrix_t A, int32_t *nrow, int32_t *ncol, int64_t 
 
 int sigb_matrix_get_transpose_values(sigb_matrix_t A, double *val_t)
 {
+    if (A && A->mg) { ::sigb::set_error("sigb_matrix_get_transpose_values: not available for a single-process multi-GPU operator"); return SIGB_ERR_UNSUPPORTED; }
     SIGB_REQUIRE(A && val_t, SIGB_ERR_ARG, "sigb_matrix_get_transpose_values: bad argument");
     SIGB_REQUIRE(!A->op, SIGB_ERR_UNSUPPORTED, "sigb_matrix_get_transpose_values: not a stored matrix");
     SIGB_CHECK(ensure_transposed(A));
@@ -579,26 +586,42 @@ int sigb_matrix_get_transpose_values(sigb_matrix_t A, double *val_t)
 // matvec
 // ===========================================================================
 
+// grow-only device staging for the host-pointer entry points: A%matvec through the Fortran shim /
+// sigma.hpp comes here on every call, so no cudaMalloc / cudaFree pair (each synchronises the
+// device) and nothing to leak on an early return
+static int ensure_stage(int which, size_t count, double **p)
+{
+    Ctx &c = ctx();
+    if (c.stage_len[which] < count) {
+        SIGB_CUDA(cudaStreamSynchronize(c.stream));
+        cudaFree(c.stage[which]);
+        c.stage[which] = nullptr;
+        c.stage_len[which] = 0;
+        const size_t len = count + count / 4 + 32;
+        SIGB_CUDA(cudaMalloc((void **)&c.stage[which], sizeof(double) * len));
+        c.stage_len[which] = len;
+    }
+    *p = c.stage[which];
+    return SIGB_OK;
+}
+
 static int host_matvec(sigb_matrix_t A, int trans, const double *x, double *y, bool add)
 {
     SIGB_REQUIRE(A && x && y, SIGB_ERR_ARG, "sigb_matvec: bad argument");
+    if (A->mg) return mgpu_matvec(A, trans, x, y, add);
+    SIGB_CHECK(check_fault("sigb_matvec"));
     const int64_t nx = trans ? A->nrow : A->ncol, ny = trans ? A->ncol : A->nrow;
     cudaStream_t st = ctx().stream;
     double *xd = nullptr, *yd = nullptr;
-    SIGB_CHECK(dev_alloc(&xd, (size_t)nx));
-    SIGB_CHECK(dev_alloc(&yd, (size_t)ny));
+    SIGB_CHECK(ensure_stage(0, (size_t)nx, &xd));
+    SIGB_CHECK(ensure_stage(1, (size_t)ny, &yd));
     SIGB_CUDA(cudaMemcpyAsync(xd, x, sizeof(double) * (size_t)nx, cudaMemcpyHostToDevice, st));
     if (add) SIGB_CUDA(cudaMemcpyAsync(yd, y, sizeof(double) * (size_t)ny, cudaMemcpyHostToDevice, st));
     DotSpec none;
-    int rc = matvec_dev(A, trans, xd, yd, MODE_SET, add, none);
-    if (rc == SIGB_OK) {
-        cudaError_t e = cudaMemcpyAsync(y, yd, sizeof(double) * (size_t)ny, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) rc = cuda_fail(e, "matvec copy-back", __FILE__, __LINE__);
-    }
-    cudaFree(xd);
-    cudaFree(yd);
-    return rc;
+    SIGB_CHECK(matvec_dev(A, trans, xd, yd, MODE_SET, add, none));
+    SIGB_CUDA(cudaMemcpyAsync(y, yd, sizeof(double) * (size_t)ny, cudaMemcpyDeviceToHost, st));
+    SIGB_CUDA(cudaStreamSynchronize(st));
+    return check_fault("sigb_matvec");
 }
 
 int sigb_matvec(sigb_matrix_t A, int trans, const double *x, double *y)
@@ -614,6 +637,7 @@ int sigb_matvec_add(sigb_matrix_t A, int trans, const double *x, double *y)
 int sigb_matvec_dev(sigb_matrix_t A, int trans, const double *x_dev, double *y_dev, int add)
 {
     SIGB_REQUIRE(A && x_dev && y_dev, SIGB_ERR_ARG, "sigb_matvec_dev: bad argument");
+    SIGB_REQUIRE(!A->mg, SIGB_ERR_UNSUPPORTED, "sigb_matvec_dev: a multi-GPU operator takes host vectors (its rows live on several devices)");
     DotSpec none;
     return matvec_dev(A, trans, x_dev, y_dev, MODE_SET, add != 0, none);
 }
@@ -621,17 +645,22 @@ int sigb_matvec_dev(sigb_matrix_t A, int trans, const double *x_dev, double *y_d
 int sigb_matvec_dot_dev(sigb_matrix_t A, const double *x_dev, double *y_dev, double *dot)
 {
     SIGB_REQUIRE(A && x_dev && y_dev, SIGB_ERR_ARG, "sigb_matvec_dot_dev: bad argument");
+    SIGB_REQUIRE(!A->mg, SIGB_ERR_UNSUPPORTED, "sigb_matvec_dot_dev: a multi-GPU operator takes host vectors");
     SIGB_REQUIRE(A->nrow == A->ncol, SIGB_ERR_NONSQUARE, "sigb_matvec_dot_dev: operator is not square");
     double *slot = ctx().partials + (size_t)kMaxGrid * kMaxDots * (kNumTickets - 1);
     DotSpec d;
     d.ndot = 1;
     d.u = x_dev;
     d.out[0] = slot;
+    RedFuse rf;
+    const bool fused = dist_red_fuse(A, &rf);   // peer-memory transport: the kernel's last CTA finishes the sum across the GPUs
+    if (fused) d.red = &rf;
     SIGB_CHECK(solver_matvec(A, x_dev, y_dev, d, false));
-    SIGB_CHECK(dist_allreduce(A, slot, 1));
+    if (!fused) SIGB_CHECK(dist_allreduce(A, slot, 1));
     if (dot) {  // dot == NULL: leave everything asynchronous (timing loops)
         SIGB_CUDA(cudaMemcpyAsync(dot, slot, sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
         SIGB_CUDA(cudaStreamSynchronize(ctx().stream));
+        return check_fault("sigb_matvec_dot_dev");
     }
     return SIGB_OK;
 }
@@ -682,6 +711,8 @@ int sigb_solver_set_persistent(sigb_solver_t s, int mode)
 int sigb_solver_setup(sigb_solver_t s, sigb_matrix_t A)
 {
     SIGB_REQUIRE(s && A, SIGB_ERR_ARG, "sigb_solver_setup: bad argument");
+    if (A->mg) return mgpu_solver_setup(s, A);
+    SIGB_REQUIRE(s->sub.empty(), SIGB_ERR_STATE, "sigb_solver_setup: solver was set up on a multi-GPU operator");
     const int64_t nglob_rows = A->dist ? dist_global_n(A) : A->nrow;
     const int64_t nglob_cols = A->dist ? dist_global_n(A) : A->ncol;
     if (nglob_rows != nglob_cols) {
@@ -728,6 +759,7 @@ int sigb_solver_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x_dev, const
                           sigb_solver_t pc)
 {
     SIGB_REQUIRE(s && A && x_dev && b_dev, SIGB_ERR_ARG, "sigb_solver_solve: bad argument");
+    SIGB_REQUIRE(!A->mg, SIGB_ERR_UNSUPPORTED, "sigb_solver_solve_dev: a multi-GPU operator takes host vectors");
     SIGB_REQUIRE(s->initialized, SIGB_ERR_STATE, "sigb_solver_solve: solver%%setup(A) has not been called");
     SIGB_REQUIRE(s->nn == A->nrow, SIGB_ERR_ARG, "sigb_solver_solve: solver was set up for nn = %d, operator has %d rows",
                  s->nn, A->nrow);
@@ -754,6 +786,7 @@ int sigb_solver_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x_dev, const
 int sigb_solver_solve(sigb_solver_t s, sigb_matrix_t A, double *x, const double *b, sigb_solver_t pc)
 {
     SIGB_REQUIRE(s && A && x && b, SIGB_ERR_ARG, "sigb_solver_solve: bad argument");
+    if (A->mg) return mgpu_solver_solve(s, A, x, b, pc);
     SIGB_REQUIRE(s->initialized, SIGB_ERR_STATE, "sigb_solver_solve: solver%%setup(A) has not been called");
     const int64_t n = s->nn;
     SIGB_CHECK(ensure_xb(s, 2 * n));
@@ -779,6 +812,7 @@ int sigb_solver_get_info(sigb_solver_t s, int64_t *iterations, double *res2, int
 int sigb_solver_get_vector(sigb_solver_t s, const char *name, double *out)
 {
     SIGB_REQUIRE(s && name && out && s->initialized, SIGB_ERR_ARG, "sigb_solver_get_vector: bad argument");
+    if (!s->sub.empty()) return mgpu_solver_get_vector(s, name, out);
     static const char *cg_names[] = {"p", "q", "r", "z"};
     static const char *bi_names[] = {"p", "q", "r", "r0", "v", "s", "t", "z"};
     int idx = -1;
@@ -796,6 +830,7 @@ int sigb_solver_get_vector(sigb_solver_t s, const char *name, double *out)
 int sigb_solver_destroy(sigb_solver_t s)
 {
     if (!s) return SIGB_OK;
+    mgpu_solver_free(s);
     cudaFree(s->work);
     cudaFree(s->state);
     cudaFreeHost(s->state_host);
@@ -898,12 +933,14 @@ static int lanczos_common(sigb_matrix_t A, int32_t n, const double *q1, uint64_t
 
 int sigb_lanczos(sigb_matrix_t A, int32_t n, const double *q1, uint64_t seed, double *T, double *Q)
 {
+    if (A && A->mg) { ::sigb::set_error("sigb_lanczos: not available for a single-process multi-GPU operator"); return SIGB_ERR_UNSUPPORTED; }
     SIGB_REQUIRE(T && Q, SIGB_ERR_ARG, "sigb_lanczos: T and Q are required");
     return lanczos_common(A, n, q1, seed, T, Q, nullptr, false);
 }
 
 int sigb_eigensolve(sigb_matrix_t A, int32_t n, const double *q1, uint64_t seed, double *lambda, double *V)
 {
+    if (A && A->mg) { ::sigb::set_error("sigb_eigensolve: not available for a single-process multi-GPU operator"); return SIGB_ERR_UNSUPPORTED; }
     SIGB_REQUIRE(lambda && V, SIGB_ERR_ARG, "sigb_eigensolve: lambda and V are required");
     SIGB_REQUIRE(!(A && A->dist), SIGB_ERR_UNSUPPORTED, "sigb_eigensolve on a row-sharded operator");
     return lanczos_common(A, n, q1, seed, nullptr, V, lambda, true);
@@ -912,6 +949,7 @@ int sigb_eigensolve(sigb_matrix_t A, int32_t n, const double *q1, uint64_t seed,
 int sigb_generalized_lanczos(sigb_matrix_t A, sigb_matrix_t B, sigb_solver_t b_solver, sigb_solver_t b_pc,
                              int32_t n, const double *q1, uint64_t seed, double *T, double *Q)
 {
+    if (A && A->mg) { ::sigb::set_error("sigb_generalized_lanczos: not available for a single-process multi-GPU operator"); return SIGB_ERR_UNSUPPORTED; }
     SIGB_REQUIRE(B && T && Q, SIGB_ERR_ARG, "sigb_generalized_lanczos: B, T and Q are required");
     return lanczos_common(A, n, q1, seed, T, Q, nullptr, false, B, b_solver, b_pc);
 }
@@ -919,6 +957,7 @@ int sigb_generalized_lanczos(sigb_matrix_t A, sigb_matrix_t B, sigb_solver_t b_s
 int sigb_generalized_eigensolve(sigb_matrix_t A, sigb_matrix_t B, sigb_solver_t b_solver, sigb_solver_t b_pc,
                                 int32_t n, const double *q1, uint64_t seed, double *lambda, double *V)
 {
+    if (A && A->mg) { ::sigb::set_error("sigb_generalized_eigensolve: not available for a single-process multi-GPU operator"); return SIGB_ERR_UNSUPPORTED; }
     SIGB_REQUIRE(B && lambda && V, SIGB_ERR_ARG, "sigb_generalized_eigensolve: B, lambda and V are required");
     SIGB_REQUIRE(!(A && A->dist), SIGB_ERR_UNSUPPORTED, "sigb_generalized_eigensolve on a row-sharded operator");
     return lanczos_common(A, n, q1, seed, nullptr, V, lambda, true, B, b_solver, b_pc);

@@ -116,6 +116,7 @@ extern "C" {
 
 int sigb_matrix_add_values(sigb_matrix_t A, int64_t count, const int32_t *i1, const int32_t *j1, const double *z)
 {
+    if (A && A->mg) { ::sigb::set_error("sigb_matrix_add_values: not available for a single-process multi-GPU operator"); return SIGB_ERR_UNSUPPORTED; }
     SIGB_CHECK(require_init());
     SIGB_REQUIRE(A && count >= 0 && (count == 0 || (i1 && j1 && z)), SIGB_ERR_ARG, "sigb_matrix_add_values: bad argument");
     SIGB_REQUIRE(!A->op && !A->dist, SIGB_ERR_UNSUPPORTED,

@@ -37,6 +37,7 @@
 // Round-2 A/B, 2.1 M rows per GPU: 55.6 -> 50.5 us per iteration on one GPU, 67.1 -> 57.1 us on two
 // (profiles/r2_visit_a_1gpu_summary.txt, r2_visit_b_2gpu_summary.txt).
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "krylov.cuh"
@@ -191,8 +192,16 @@ __device__ __forceinline__ double grid_allreduce(double v, const CgPersistArgs &
 // unrolled vector phases for one allocation -- inlined, ptxas spilled 60-170 bytes per thread at the
 // kernel's 80 registers.  The kernel arguments are __grid_constant__, so the callee reads them in
 // place (no local copy of the argument block).
+#ifndef SIGB_SPMV_NOINLINE
+#define SIGB_SPMV_NOINLINE 0
+#endif
+#if SIGB_SPMV_NOINLINE
+#define SIGB_PASS_ATTR __noinline__
+#else
+#define SIGB_PASS_ATTR __forceinline__
+#endif
 template <bool HALO>
-__device__ __noinline__ void spmv_pass(const CgPersistArgs &a, const double *xin, unsigned char *smem, uint64_t *mbar,
+__device__ SIGB_PASS_ATTR void spmv_pass(const CgPersistArgs &a, const double *xin, unsigned char *smem, uint64_t *mbar,
                                        TilePipe &pipe, double *acc, unsigned long long hseq)
 {
     const SpmvVecs v{xin - 1, a.q, xin};
@@ -286,12 +295,12 @@ cg_persistent_kernel(const __grid_constant__ CgPersistArgs a)
         for (int64_t base = blockIdx.x * (int64_t)kThreads + tid; base < a.n; base += stride * 4) {
             double ri[4], qi[4], di[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 4; u++) {                               // (every slot assigned: the arrays stay in registers)
                 const int64_t i = base + u * stride;
-                if (i < a.n) {
-                    ri[u] = a.r[i]; qi[u] = a.q[i];
-                    if (PC) di[u] = a.idiag[i];
-                }
+                const bool in = i < a.n;
+                ri[u] = in ? a.r[i] : 0.0;
+                qi[u] = in ? a.q[i] : 0.0;
+                di[u] = (PC && in) ? a.idiag[i] : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -319,7 +328,10 @@ cg_persistent_kernel(const __grid_constant__ CgPersistArgs a)
 #pragma unroll
             for (int u = 0; u < 3; u++) {
                 const int64_t i = base + u * stride;
-                if (i < a.n) { v0[u] = rz[i]; p0[u] = a.p[i]; x0[u] = a.x[i]; }
+                const bool in = i < a.n;
+                v0[u] = in ? rz[i] : 0.0;
+                p0[u] = in ? a.p[i] : 0.0;
+                x0[u] = in ? a.x[i] : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < 3; u++) {
@@ -361,6 +373,9 @@ int launch_persistent(const CgPersistArgs &a, cudaStream_t st)
     int grid = 0;
     SIGB_CHECK((occupancy_grid<cg_persistent_kernel<HALO, PC>>(smem, &grid)));
     void *params[] = {(void *)&a};
+    static const bool verbose = env_int("SIGB_VERBOSE", 0) == 1;
+    if (verbose) fprintf(stderr, "sigma_b200: cg_persistent_kernel<%d,%d> grid %d x %d threads, %zu B dynamic shared memory\n",
+                         (int)HALO, (int)PC, grid, kThreads, smem);
     SIGB_CUDA(cudaLaunchCooperativeKernel((const void *)cg_persistent_kernel<HALO, PC>, dim3(grid), dim3(kThreads),
                                           params, smem, st));
     count_launch();
@@ -374,7 +389,7 @@ int launch_persistent(const CgPersistArgs &a, cudaStream_t st)
 static unsigned long long *phase_dbg_buffer()
 {
 #ifdef SIGB_PHASE_TIMERS
-    static unsigned long long *buf = nullptr;
+    static thread_local unsigned long long *buf = nullptr;
     if (!buf) {
         if (cudaMalloc((void **)&buf, sizeof(unsigned long long) * kPhaseCtas * (kPhaseSlots + 1)) != cudaSuccess)
             return nullptr;

@@ -30,6 +30,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
 #include <vector>
 
 #include "device_utils.cuh"
@@ -38,9 +40,34 @@
 
 namespace sigb {
 
+// Ranks that live in ONE process (single-process multi-device mode, mgpu.cu: one host thread per
+// GPU): the bootstrap exchanges go through host memory and the windows are shared as plain
+// pointers (peer access is enabled between the devices) -- no NCCL, no IPC handles.
+struct LocalGroup {
+    int nranks = 0;
+    std::mutex m;
+    std::condition_variable cv;
+    int arrived = 0;
+    unsigned generation = 0;
+    std::vector<std::vector<char>> slot;   // one per rank
+    void barrier()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        const unsigned gen = generation;
+        if (++arrived == nranks) {
+            arrived = 0;
+            generation++;
+            cv.notify_all();
+        } else {
+            cv.wait(lk, [&] { return generation != gen; });
+        }
+    }
+};
+
 }  // namespace sigb
 
 struct sigb_comm_s {
+    sigb::LocalGroup *grp = nullptr;   // non-null: the ranks are threads of this process
     ncclComm_t nccl = nullptr;
     int rank = 0, nranks = 1;
     cudaStream_t stream = nullptr;   // NCCL halo exchange stream
@@ -85,6 +112,14 @@ namespace {
 // ---- bootstrap: all-gather of a few bytes per rank over NCCL ---------------
 int allgather_bytes(sigb_comm_t c, const void *mine, size_t bytes, void *all)
 {
+    if (c->grp) {
+        LocalGroup *g = c->grp;
+        g->slot[(size_t)c->rank].assign((const char *)mine, (const char *)mine + bytes);
+        g->barrier();
+        for (int q = 0; q < c->nranks; q++) memcpy((char *)all + (size_t)q * bytes, g->slot[(size_t)q].data(), bytes);
+        g->barrier();   // nobody overwrites its slot before everybody has read it
+        return SIGB_OK;
+    }
     const size_t need = bytes * (size_t)(c->nranks + 1);
     if (c->stage_bytes < need) {
         cudaFree(c->stage);
@@ -104,6 +139,12 @@ int allgather_bytes(sigb_comm_t c, const void *mine, size_t bytes, void *all)
 // address it is mapped at in this process.  Collective.
 int share_window(sigb_comm_t c, void *ptr, void **peers)
 {
+    if (c->grp) {   // one address space, peer access enabled: the pointers themselves
+        std::vector<void *> all((size_t)c->nranks);
+        SIGB_CHECK(allgather_bytes(c, &ptr, sizeof(void *), all.data()));
+        for (int q = 0; q < c->nranks; q++) peers[q] = all[(size_t)q];
+        return SIGB_OK;
+    }
     cudaIpcMemHandle_t mine;
     SIGB_CUDA(cudaIpcGetMemHandle(&mine, ptr));
     std::vector<cudaIpcMemHandle_t> all((size_t)c->nranks);
@@ -135,7 +176,7 @@ struct RedArgs {
 // totals and all ranks take the same stopping decision.  A slot is reused every
 // kRedSlots reductions; an all-reduce is a full barrier, so no rank can be that
 // far ahead.
-__global__ void red_kernel(const RedArgs a)
+__global__ void red_kernel(const __grid_constant__ RedArgs a)
 {
     if (a.skip_flag != nullptr && *a.skip_flag != 0) return;
     const int lane = threadIdx.x;
@@ -197,8 +238,9 @@ static void free_dist(DistInfo *D)
     if (!D) return;
     cudaDeviceSynchronize();
     if (D->win) {
-        for (int q = 0; q < D->comm->nranks; q++)
-            if (q != D->comm->rank && D->sync.peer[q]) cudaIpcCloseMemHandle(D->sync.peer[q]);
+        if (!D->comm->grp)
+            for (int q = 0; q < D->comm->nranks; q++)
+                if (q != D->comm->rank && D->sync.peer[q]) cudaIpcCloseMemHandle(D->sync.peer[q]);
         cudaFree(D->win);
     }
     cudaFree(D->send_rows);
@@ -336,6 +378,53 @@ int dist_matvec(sigb_matrix_t A, const double *x, double *y, bool add, const Dot
     return launch_csr_spmv(V, A->val, x, y, mode, db, 2, main, 0);
 }
 
+// ---- ranks as threads of one process (mgpu.cu) ---------------------------------
+LocalGroup *local_group_create(int nranks)
+{
+    LocalGroup *g = new LocalGroup();
+    g->nranks = nranks;
+    g->slot.resize((size_t)nranks);
+    return g;
+}
+void local_group_destroy(LocalGroup *g) { delete g; }
+void local_group_barrier(LocalGroup *g) { g->barrier(); }
+
+// Collective over the threads of the group; the calling thread's device is its rank's GPU and peer
+// access to the other devices has been enabled.  Peer-memory transport only.
+int comm_create_local(LocalGroup *grp, int rank, int nranks, sigb_comm_t *out)
+{
+    SIGB_CHECK(require_init());
+    SIGB_REQUIRE(grp && out && nranks >= 1 && nranks <= kMaxRanks && rank >= 0 && rank < nranks, SIGB_ERR_ARG,
+                 "comm_create_local: bad argument");
+    sigb_comm_t c = new sigb_comm_s();
+    c->grp = grp;
+    c->rank = rank;
+    c->nranks = nranks;
+    int ok = 1;
+    if (nranks > 1) {
+        if (cudaMalloc((void **)&c->red, sizeof(RedWin)) != cudaSuccess) ok = 0;
+        if (ok && cudaMemset(c->red, 0, sizeof(RedWin)) != cudaSuccess) ok = 0;
+        void *peers[kMaxRanks] = {};
+        share_window(c, c->red, peers);
+        std::vector<int> oks((size_t)nranks);
+        allgather_bytes(c, &ok, sizeof(int), oks.data());
+        for (int q = 0; q < nranks; q++) ok = ok && oks[(size_t)q];
+        if (ok) {
+            for (int q = 0; q < nranks; q++) c->peer_red[q] = (RedWin *)peers[q];
+            c->p2p = true;
+        }
+    }
+    if (!ok) {
+        cudaGetLastError();
+        cudaFree(c->red);
+        delete c;
+        set_error("comm_create_local: could not allocate the all-reduce window");
+        return SIGB_ERR_CUDA;
+    }
+    *out = c;
+    return SIGB_OK;
+}
+
 }  // namespace sigb
 
 using namespace sigb;
@@ -360,6 +449,10 @@ int sigb_comm_create(const void *unique_id, int rank, int nranks, sigb_comm_t *o
                  "sigb_comm_create: bad argument");
     SIGB_REQUIRE(nranks <= kMaxRanks, SIGB_ERR_UNSUPPORTED, "sigb_comm_create: at most %d ranks (one box)", kMaxRanks);
     sigb_comm_t c = new sigb_comm_s();
+    struct CommGuard {            // an early return releases what has been built so far
+        sigb_comm_t c;
+        ~CommGuard() { if (c) sigb_comm_destroy(c); }
+    } guard{c};
     c->rank = rank;
     c->nranks = nranks;
     ncclUniqueId id;
@@ -387,6 +480,7 @@ int sigb_comm_create(const void *unique_id, int rank, int nranks, sigb_comm_t *o
             c->p2p = true;
         }
     }
+    guard.c = nullptr;
     *out = c;
     return SIGB_OK;
 }
@@ -396,15 +490,16 @@ int sigb_comm_destroy(sigb_comm_t c)
     if (!c) return SIGB_OK;
     cudaDeviceSynchronize();
     if (c->red) {
-        for (int q = 0; q < c->nranks; q++)
-            if (q != c->rank && c->peer_red[q]) cudaIpcCloseMemHandle(c->peer_red[q]);
+        if (!c->grp)
+            for (int q = 0; q < c->nranks; q++)
+                if (q != c->rank && c->peer_red[q]) cudaIpcCloseMemHandle(c->peer_red[q]);
         cudaFree(c->red);
     }
     cudaFree(c->stage);
     if (c->nccl) ncclCommDestroy(c->nccl);
-    cudaStreamDestroy(c->stream);
-    cudaEventDestroy(c->ev_pack);
-    cudaEventDestroy(c->ev_halo);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->ev_pack) cudaEventDestroy(c->ev_pack);
+    if (c->ev_halo) cudaEventDestroy(c->ev_halo);
     delete c;
     return SIGB_OK;
 }

@@ -159,6 +159,7 @@ extern "C" {
 
 int sigb_matrix_copy(sigb_matrix_t A, int format, int trans, sigb_matrix_t *B_out)
 {
+    if (A && A->mg) { ::sigb::set_error("sigb_matrix_copy: not available for a single-process multi-GPU operator"); return SIGB_ERR_UNSUPPORTED; }
     SIGB_CHECK(require_init());
     SIGB_REQUIRE(A && B_out, SIGB_ERR_ARG, "sigb_matrix_copy: bad argument");
     SIGB_REQUIRE(format == SIGB_FMT_CSR || format == SIGB_FMT_CSC || format == SIGB_FMT_ELLPACK, SIGB_ERR_ARG,
@@ -276,6 +277,7 @@ int sigb_matrix_copy(sigb_matrix_t A, int format, int trans, sigb_matrix_t *B_ou
 int sigb_matrix_get_format(sigb_matrix_t A, int *format, int32_t *n_lines, int32_t *n_ids, int64_t *ne,
                            int32_t *max_d)
 {
+    if (A && A->mg) { ::sigb::set_error("sigb_matrix_get_format: not available for a single-process multi-GPU operator"); return SIGB_ERR_UNSUPPORTED; }
     SIGB_REQUIRE(A, SIGB_ERR_ARG, "sigb_matrix_get_format: null matrix");
     SIGB_REQUIRE(!A->op && !A->dist, SIGB_ERR_UNSUPPORTED, "sigb_matrix_get_format: not a stored matrix");
     sigb_graph_t g = A->g;
@@ -289,6 +291,7 @@ int sigb_matrix_get_format(sigb_matrix_t A, int *format, int32_t *n_lines, int32
 
 int sigb_matrix_get_arrays(sigb_matrix_t A, int32_t *ptr_or_degrees, int32_t *node, double *val)
 {
+    if (A && A->mg) { ::sigb::set_error("sigb_matrix_get_arrays: not available for a single-process multi-GPU operator"); return SIGB_ERR_UNSUPPORTED; }
     SIGB_REQUIRE(A, SIGB_ERR_ARG, "sigb_matrix_get_arrays: null matrix");
     SIGB_REQUIRE(!A->op && !A->dist, SIGB_ERR_UNSUPPORTED, "sigb_matrix_get_arrays: not a stored matrix");
     sigb_graph_t g = A->g;

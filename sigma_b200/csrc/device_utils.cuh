@@ -315,7 +315,7 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[ND], double *partials,
 template <auto Kernel>
 int occupancy_grid(size_t smem, int *grid_out)
 {
-    static int cached = 0;
+    static thread_local int cached = 0;   // per host thread = per device (cudaFuncSetAttribute is per device)
     if (cached == 0) {
         int per_sm = 0;
         SIGB_CUDA(cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -12,4 +12,12 @@ int dist_destroy(sigb_matrix_t A);
 int64_t dist_global_n(sigb_matrix_t A);
 int64_t dist_row_offset(sigb_matrix_t A);
 
+
+// ranks as threads of one process (single-process multi-device mode, mgpu.cu)
+struct LocalGroup;
+LocalGroup *local_group_create(int nranks);
+void local_group_destroy(LocalGroup *g);
+void local_group_barrier(LocalGroup *g);
+int comm_create_local(LocalGroup *grp, int rank, int nranks, sigb_comm_t *out);
+
 }  // namespace sigb

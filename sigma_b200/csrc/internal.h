@@ -41,7 +41,8 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
     } while (0)
 
 // ---------------------------------------------------------------------------
-// runtime context (one per process: one process drives one GPU)
+// runtime context: one per host THREAD (thread_local).  One process per GPU uses the main thread's;
+// the single-process multi-GPU mode (mgpu.cu) gives every worker thread its own, bound to its GPU
 // ---------------------------------------------------------------------------
 struct Ctx {
     bool inited = false;
@@ -56,6 +57,9 @@ struct Ctx {
     unsigned *tickets = nullptr;      // kNumTickets counters, zero between kernels
     void *pinned = nullptr;           // small pinned host staging area
     size_t pinned_bytes = 0;
+    // grow-only device staging of the host-pointer matvec entry points (x | y)
+    double *stage[2] = {nullptr, nullptr};
+    size_t stage_len[2] = {0, 0};
     // device-side wait timeouts (device_utils.cuh spin_wait): mapped pinned host memory
     struct FaultBlock *fault = nullptr;       // host address
     struct FaultBlock *fault_dev = nullptr;   // the same block as the device sees it
@@ -135,7 +139,8 @@ constexpr int kPad = 8;          // slack entries behind ptr / node / val arrays
 
 enum GraphKind { G_CSR = 0, G_CSC = 1, G_ELL = 2 };
 
-struct DistInfo;  // comm.cu
+struct DistInfo;    // comm.cu
+struct MgpuMatrix;  // mgpu.cu
 
 // An operator expression over other operators (operators.cu): operator_sum,
 // operator_product, operator_adjoint (src/linear_operator/linear_operator_
@@ -179,6 +184,7 @@ struct sigb_matrix_s {
     bool val_t_valid = false;
     int32_t nrow = 0, ncol = 0;
     sigb::DistInfo *dist = nullptr;  // non-null for row-sharded operators
+    sigb::MgpuMatrix *mg = nullptr;  // non-null for the single-process multi-GPU operator (one row block per GPU)
     sigb::OpInfo *op = nullptr;      // non-null for operator expressions (no graph, no values of their own)
 };
 
@@ -301,6 +307,16 @@ int upload_tiles(CsrView &v, const std::vector<TileDesc> &tiles);
 // y = op(A) x with device vectors; the single entry every solver goes through
 int matvec_dev(sigb_matrix_t A, int trans, const double *x, double *y,
                SpmvMode mode_csr_like, bool add, const DotSpec &dot);
+
+// ---------------------------------------------------------------------------
+// mgpu.cu: single-process multi-GPU mode (one worker thread per GPU behind the C-ABI)
+// ---------------------------------------------------------------------------
+bool mgpu_active();
+void mgpu_matrix_free(sigb_matrix_t A);
+int mgpu_set_values(sigb_matrix_t A, const double *val, int64_t count);
+int mgpu_matvec(sigb_matrix_t A, int trans, const double *x, double *y, bool add);
+int64_t mgpu_nnz(sigb_matrix_t A);
+int64_t mgpu_launch_count();
 
 // ---------------------------------------------------------------------------
 // operators.cu: operator expressions

@@ -58,7 +58,7 @@ namespace {
 // ---------------------------------------------------------------------------
 template <int MODE, int NDOT, bool HALO>
 __global__ void __launch_bounds__(kThreads)
-csr_tma_kernel(const CsrKernelArgs a)
+csr_tma_kernel(const __grid_constant__ CsrKernelArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t mbar[2];
@@ -279,7 +279,7 @@ int build_tiles_host(const int32_t *ptr1, int32_t nrows, std::vector<TileDesc> &
 // diagnostic build: one buffer per process for the per-tile cycle counters (spmv_device.cuh)
 static unsigned long long *tile_dbg_buffer()
 {
-    static unsigned long long *buf = nullptr;
+    static thread_local unsigned long long *buf = nullptr;
     if (!buf) {
         if (cudaMalloc((void **)&buf, sizeof(unsigned long long) * 6) != cudaSuccess) return nullptr;
         cudaMemset(buf, 0, sizeof(unsigned long long) * 6);

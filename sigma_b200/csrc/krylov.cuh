@@ -114,7 +114,7 @@ int launch_ew(const Op &op, int64_t n, cudaStream_t st = nullptr)
 // A twin rather than a parameter of ew_kernel, so that the product kernels keep their code.
 template <class Op>
 __global__ void __launch_bounds__(kThreads)
-ew_fused_kernel(Op op, int64_t n, double *partials, unsigned *ticket, const RedFuse red)
+ew_fused_kernel(Op op, int64_t n, double *partials, unsigned *ticket, const __grid_constant__ RedFuse red)
 {
     if (!op.begin()) return;
     constexpr int ND = Op::ND;

@@ -20,6 +20,7 @@
 // level (round 1) costs ~4 us per level -- 16.8 ms per application at 1024^2, slower than one host
 // core.  Deep schedules therefore run as CHUNKED SWEEPS (below): one launch per sweep, every
 // thread walks a contiguous chunk of rows in order and waits only for the entries it reads.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -207,31 +208,69 @@ tri_chunked_kernel(int32_t n, int32_t chunk_rows, int32_t nchunks, const int32_t
                    const int *skip)
 {
     if (skip != nullptr && *skip != 0) return;
-    const int32_t t = blockIdx.x * kSweepThreads + threadIdx.x;
+    const int lane = threadIdx.x;
+    const int32_t t = blockIdx.x * kSweepThreads + lane;      // chunk of this thread; the warp owns chunks [t - lane, t - lane + 32)
     // rows of this chunk, 1-based, in sweep order: i, i + step, ..., last
     int32_t i = 0, last = 0;
     const int32_t step = BACKWARD ? -1 : 1;
     bool done = true;
     if (t < nchunks) {
-        const int64_t lo = (int64_t)t * chunk_rows, hi = min((int64_t)n, lo + chunk_rows);   // 0-based [lo, hi) from the sweep's start
+        const int64_t lo = (int64_t)t * chunk_rows, hi = min((int64_t)n, lo + chunk_rows);   // [lo, hi) counted from the sweep's start
         if (!BACKWARD) { i = (int32_t)lo + 1; last = (int32_t)hi; }
         else { i = n - (int32_t)lo; last = n - (int32_t)hi + 1; }
         done = false;
     }
+    // chunk -> lane of this warp that owns row j (or a value outside 0..31)
+    auto owner_lane = [&](int32_t j) {
+        const int64_t pos = BACKWARD ? (int64_t)n - j : (int64_t)j - 1;      // position from the sweep's start
+        return (int)(pos / chunk_rows) - (int)(t - lane);
+    };
     int32_t k = 0, e = 0, prev_row = 0;
     double z = 0.0, prev_z = 0.0;
     bool have_row = false;
     unsigned trips = 0;
     unsigned long long t0 = 0ull;
+#ifdef SIGB_SWEEP_STATS
+    unsigned n_own = 0, n_shfl = 0, n_try = 0, n_fail = 0, n_rows = 0;
+    const long long c_begin = clock64();
+#define SIGB_STAT(x) x
+#else
+#define SIGB_STAT(x)
+#endif
     for (;;) {
-        if (!done) {
-            if (!have_row) {
-                k = ptr1[i - 1] - 1;
-                e = ptr1[i] - 1;
-                z = BACKWARD ? src[i - 1] / D[i - 1] : src[i - 1];
-                have_row = true;
+        if (!done && !have_row) {
+            k = ptr1[i - 1] - 1;
+            e = ptr1[i] - 1;
+            z = BACKWARD ? src[i - 1] / D[i - 1] : src[i - 1];
+            have_row = true;
+        }
+        // Two convergent rounds: the next entry of every lane is looked for, in this order, in the
+        // lane's own last result (a register), in the last result of the lane of this warp that owns
+        // it (a shuffle: in a banded matrix the neighbouring chunk finished exactly that row one trip
+        // ago -- no round trip through L2), and in the published words.  z = z - M%val(k) * x(node(k)),
+        // entries strictly in stored order.
+#pragma unroll
+        for (int round = 0; round < 2; round++) {
+            const bool want = !done && k < e;
+            const int32_t j = want ? node1[k] : 0;
+            const int ol = want ? owner_lane(j) : lane;
+            const int src_lane = (ol >= 0 && ol < 32) ? ol : lane;
+            const int32_t their_row = __shfl_sync(0xffffffffu, prev_row, src_lane);
+            const double their_z = __shfl_sync(0xffffffffu, prev_z, src_lane);
+            if (want) {
+                double xj = 0.0;
+                bool got = false;
+                if (j == prev_row) { xj = prev_z; got = true; SIGB_STAT(n_own++); }
+                else if (their_row == j) { xj = their_z; got = true; SIGB_STAT(n_shfl++); }
+                else { got = ll_try(xs + (j - 1), seq, &xj); SIGB_STAT(n_try++); SIGB_STAT(if (!got) n_fail++); }
+                if (got) {
+                    z = sub(z, mul(val[k], xj));
+                    k++;
+                }
             }
-            while (k < e) {                                   // z = z - M%val(k) * x(node(k)), stored order
+        }
+        if (!done) {
+            while (k < e) {                                   // further entries: own register or published words
                 const int32_t j = node1[k];
                 double xj;
                 if (j == prev_row) xj = prev_z;
@@ -245,6 +284,7 @@ tri_chunked_kernel(int32_t n, int32_t chunk_rows, int32_t nchunks, const int32_t
                 prev_row = i;
                 prev_z = z;
                 have_row = false;
+                SIGB_STAT(n_rows++);
                 if (i == last) done = true;
                 else i += step;
             }
@@ -252,6 +292,12 @@ tri_chunked_kernel(int32_t n, int32_t chunk_rows, int32_t nchunks, const int32_t
         if (__all_sync(0xffffffffu, done)) break;
         if ((++trips & 0xfffu) == 0u && !spin_check(fault, &t0, FAULT_LDU_SWEEP)) break;
     }
+#ifdef SIGB_SWEEP_STATS
+    if ((blockIdx.x == 0 || blockIdx.x == gridDim.x / 2 || blockIdx.x == gridDim.x - 1) && (lane == 0 || lane == 31))
+        printf("sweep%s cta %d lane %d: trips %u rows %u own %u shfl %u try %u fail %u cycles %lld (%.0f per trip)\n",
+               BACKWARD ? "B" : "F", blockIdx.x, lane, trips, n_rows, n_own, n_shfl, n_try, n_fail,
+               (long long)(clock64() - c_begin), (double)(clock64() - c_begin) / (trips + 1));
+#endif
 }
 
 // scratch of the chunked sweeps; hands out the next sequence number (0 = never written)

@@ -333,6 +333,7 @@ static int check_operand(sigb_matrix_t A, const char *who)
 
 int sigb_operator_sum(sigb_matrix_t A, sigb_matrix_t B, sigb_matrix_t *C)
 {
+    if (A && A->mg) { ::sigb::set_error("sigb_operator_sum: not available for a single-process multi-GPU operator"); return SIGB_ERR_UNSUPPORTED; }
     SIGB_CHECK(require_init());
     SIGB_REQUIRE(C, SIGB_ERR_ARG, "sigb_operator_sum: null output");
     SIGB_CHECK(check_operand(A, "sigb_operator_sum"));
@@ -348,6 +349,7 @@ int sigb_operator_sum(sigb_matrix_t A, sigb_matrix_t B, sigb_matrix_t *C)
 
 int sigb_operator_product(sigb_matrix_t A, sigb_matrix_t B, sigb_matrix_t *C)
 {
+    if (A && A->mg) { ::sigb::set_error("sigb_operator_product: not available for a single-process multi-GPU operator"); return SIGB_ERR_UNSUPPORTED; }
     SIGB_CHECK(require_init());
     SIGB_REQUIRE(C, SIGB_ERR_ARG, "sigb_operator_product: null output");
     SIGB_CHECK(check_operand(A, "sigb_operator_product"));
@@ -372,6 +374,7 @@ int sigb_operator_product(sigb_matrix_t A, sigb_matrix_t B, sigb_matrix_t *C)
 
 int sigb_operator_adjoint(sigb_matrix_t A, sigb_matrix_t *B)
 {
+    if (A && A->mg) { ::sigb::set_error("sigb_operator_adjoint: not available for a single-process multi-GPU operator"); return SIGB_ERR_UNSUPPORTED; }
     SIGB_CHECK(require_init());
     SIGB_REQUIRE(B, SIGB_ERR_ARG, "sigb_operator_adjoint: null output");
     SIGB_CHECK(check_operand(A, "sigb_operator_adjoint"));

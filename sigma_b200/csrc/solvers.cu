@@ -685,8 +685,8 @@ struct L2Window {
     cudaStream_t stream = nullptr;
     int begin(void *base, size_t bytes)
     {
-        static int enabled = -1;
-        static size_t max_persist = 0, max_window = 0;
+        static thread_local int enabled = -1;
+        static thread_local size_t max_persist = 0, max_window = 0;
         if (enabled < 0) {
             // measured on B200 (gpurun visit r1s, 2.1 M and 4.2 M rows): the carve-out
             // starves the matrix stream and the iteration gets 15-50 % SLOWER

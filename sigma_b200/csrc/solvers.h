@@ -33,6 +33,7 @@ struct sigb_solver_s {
     unsigned long long *bar = nullptr;   // grid barrier counter
     double *pers_partials = nullptr;     // 2 buffers x 2 values x kMaxGrid CTA partial sums
     sigb::LduInfo *ldu = nullptr;        // sparse_ldu_solver: factors and level schedules (ldu.cu)
+    std::vector<sigb_solver_s *> sub;    // single-process multi-GPU mode: the same solver on every row block (mgpu.cu)
 };
 
 namespace sigb {
@@ -59,6 +60,12 @@ int tridiag_eig_host(int n, double *d, double *e, double *Z);
 int ritz_vectors_dev(double *V, double *V2, const double *Qm_dev, int64_t nr, int32_t n,
                      double *first_row_dev);
 size_t kstate_bytes();
+
+// ---- single-process multi-GPU mode (mgpu.cu) --------------------------------
+int mgpu_solver_setup(sigb_solver_t s, sigb_matrix_t A);
+int mgpu_solver_solve(sigb_solver_t s, sigb_matrix_t A, double *x, const double *b, sigb_solver_t pc);
+int mgpu_solver_get_vector(sigb_solver_t s, const char *name, double *out);
+void mgpu_solver_free(sigb_solver_t s);
 
 // ---- persistent cooperative CG kernel (cg_persistent.cu) -------------------
 struct PersistComm {          // all-reduce endpoints of a row-sharded operator

@@ -199,8 +199,18 @@ __device__ __forceinline__ void finish_dots(const CsrKernelArgs &a, double *acc)
 // on every step (load, add, load, add ...), which made the row sums of matrices with ~20 entries per
 // row the longest part of a tile (ncu on the Erdos-Renyi operator: warps mostly stalled at the CTA
 // barrier behind the few threads that own rows, profiles/r2_ncu_er_2m_round1_kernel.txt).
+#ifndef SIGB_ROWSUM_BATCH
+#define SIGB_ROWSUM_BATCH 0
+#endif
+#ifndef SIGB_UR_STAGES
+#define SIGB_UR_STAGES 3
+#endif
 __device__ __forceinline__ double ordered_sum(const double *sval, int b, int e, double z)
 {
+#if !SIGB_ROWSUM_BATCH
+    for (int k = b; k < e; k++) z = add(z, sval[k]);
+    return z;
+#endif
     int k = b;
     for (; k + 8 <= e; k += 8) {
         double p[8];
@@ -352,6 +362,11 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, const SpmvVec
     double ur_dot[kRowSlots], z_dot[kRowSlots];
 #pragma unroll
     for (int i = 0; i < kRowSlots; i++) { ur_dot[i] = 0.0; z_dot[i] = 0.0; }
+#if SIGB_UR_STAGES == 3
+    double ur_pend[kRowSlots];
+#pragma unroll
+    for (int i = 0; i < kRowSlots; i++) ur_pend[i] = 0.0;
+#endif
 
     auto flush_dot = [&]() {
         if (NDOT >= 1 && dot_pending) {
@@ -362,6 +377,13 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, const SpmvVec
         dot_pending = false;
     };
     auto load_u_pending = [&]() {
+#if SIGB_UR_STAGES == 3
+        if (NDOT >= 1) {
+#pragma unroll
+            for (int i = 0; i < kRowSlots; i++) ur_dot[i] = ur_pend[i];
+        }
+        return;
+#endif
         if (NDOT >= 1) {
 #pragma unroll
             for (int i = 0; i < kRowSlots; i++) {
@@ -447,6 +469,14 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, const SpmvVec
             }
             // u for the rows of the PENDING tile, next to the gathers: consumed after the product pass
             if (pending) load_u_pending();
+#if SIGB_UR_STAGES == 3
+            double ur_cur[kRowSlots];
+#pragma unroll
+            for (int i = 0; i < kRowSlots; i++) {
+                const int r = d_cur.x + tid + i * kThreads;
+                ur_cur[i] = (NDOT >= 1 && r < d_cur.y) ? ld_x<XNC>(v.u + r) : 0.0;
+            }
+#endif
             // ---- row sums of the previous tile while the gathers are in flight
             if (pending) row_sums();
             __syncthreads();                               // the other stage has been consumed by everybody
@@ -470,6 +500,10 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, const SpmvVec
             pending = true;
             d_pend = d_cur;
             stage_pend = stage;
+#if SIGB_UR_STAGES == 3
+#pragma unroll
+            for (int i = 0; i < kRowSlots; i++) ur_pend[i] = ur_cur[i];
+#endif
             sidx++;
         } else {
             if (pending) {

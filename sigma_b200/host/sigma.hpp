@@ -52,6 +52,19 @@ inline void sigb_check(int stat)
     }
 }
 
+// Single-process multi-GPU mode.  After sigma::use_gpus(ndev) (ndev <= 0: all visible GPUs) every
+// square csr_matrix is mirrored as one row block per GPU (sigb_mgpu_csr_create): A%matvec, A%matvec_add
+// and solver%solve(A, x, b [, pc]) with cg / bicgstab / jacobi run on all of them, with the caller's
+// whole vectors and no change to the calling program.  What a multi-GPU mirror cannot do (matvec_t,
+// copies, expressions, ldu, the eigensolvers) is what the library refuses for it.
+inline int &gpus_in_use() { static int n = 0; return n; }
+inline int use_gpus(int ndev = 0)
+{
+    sigb_check(sigb_mgpu_init(ndev));
+    sigb_check(sigb_mgpu_device_count(&gpus_in_use()));
+    return gpus_in_use();
+}
+
 // ---------------------------------------------------------------------------
 // graphs
 // ---------------------------------------------------------------------------
@@ -440,6 +453,12 @@ struct cs_matrix : device_matrix {
 
     void sync_mirror() override
     {
+        if (!mirror && !COL && gpus_in_use() > 0 && g->n == g->m) {
+            // multi-GPU mode: the pattern goes in whole, the library shards it (row blocks, halo and
+            // send lists derived from the graph)
+            sigb_check(sigb_mgpu_csr_create(g->n, g->ptr.data(), g->node.data(), &mirror));
+            dirty = true;
+        }
         if (!mirror) {
             std::shared_ptr<graph_mirror> &gm = g->mirror[COL ? 1 : 0];
             if (!gm) {

@@ -1,0 +1,117 @@
+// The multi-GPU path through the host mirror alone (no Python, one process, one caller thread):
+// a serial `use sigma` style program builds the 2-D Poisson matrix on a 512 x 512 grid the way the
+// reference's tests build theirs (ll_graph add_edge calls -> cs_graph -> set_value), solves it with
+// cg on ONE GPU, then calls sigma::use_gpus() and solves the same system again: the csr_matrix is
+// now mirrored as one row block per visible GPU (sigb_mgpu_csr_create) and solver%solve(A, x, b)
+// drives all of them.  Bars (north_star): SpMV identical bit for bit, iterations within 2 %,
+// solution within 1e-10 relative.  Also Jacobi-PCG and BiCGSTAB on the sharded operator.
+//   seam: sparse_matrix_composites.f90:1076-1100 behind linear_operator_interface.f90:108-123
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../sigma_b200/host/sigma.hpp"
+#include "test_util.hpp"
+using namespace sigma;
+
+static void build_poisson(int N, csr_matrix &A)
+{
+    const int n = N * N;
+    ll_graph g;
+    g.init(n);
+    for (int ix = 0; ix < N; ix++)
+        for (int iy = 0; iy < N; iy++) {
+            const int k = N * ix + iy + 1;
+            g.add_edge(k, k);
+            if (iy + 1 < N) { g.add_edge(k, k + 1); g.add_edge(k + 1, k); }
+            if (ix + 1 < N) { g.add_edge(k, k + N); g.add_edge(k + N, k); }
+        }
+    auto cg_ = std::make_shared<cs_graph>();
+    cg_->copy(g);
+    A.init(n, n);
+    A.set_graph(cg_);
+    A.zero();
+    for (int k = 1; k <= n; k++)
+        for (int32_t j : g.get_neighbors(k)) A.set_value(k, j, j == k ? 4.0 : -1.0);
+}
+
+static dp rel_diff(const std::vector<dp> &a, const std::vector<dp> &b)
+{
+    dp num = 0.0, den = 0.0;
+    for (size_t i = 0; i < a.size(); i++) { num += (a[i] - b[i]) * (a[i] - b[i]); den += b[i] * b[i]; }
+    return std::sqrt(num / den);
+}
+
+int main(int argc, char **argv)
+{
+    const bool verbose = argc > 1 && !strcmp(argv[1], "-v");
+    int want_gpus = 0;
+    if (argc > 2) want_gpus = atoi(argv[2]);
+    const int N = 512, n = N * N;
+    rng64 rnd(7);
+    std::vector<dp> xs(n), b(n), y1(n), x1(n, 0.0);
+    for (dp &v : xs) v = rnd.next();
+
+    // ---- one GPU ------------------------------------------------------------
+    csr_matrix A1;
+    build_poisson(N, A1);
+    A1.matvec(xs.data(), b.data());
+    dp bnorm = 0.0;
+    for (dp v : b) bnorm += v * v;
+    const dp tol = 1e-10 * std::sqrt(bnorm);
+    linear_solver *s1 = cg(tol);
+    s1->setup(A1);
+    s1->set_max_iterations(20 * N);
+    s1->solve(A1, x1.data(), b.data());
+    const long it1 = (long)s1->iterations;
+    if (s1->capped()) { std::printf(" one-GPU cg hit the safety cap\n"); return 1; }
+    y1 = b;
+
+    // ---- all visible GPUs, same program ---------------------------------------
+    const int ndev = use_gpus(want_gpus);
+    csr_matrix A;
+    build_poisson(N, A);
+    std::vector<dp> y(n), x(n, 0.0);
+    A.matvec(xs.data(), y.data());
+    for (int i = 0; i < n; i++)
+        if (y[i] != y1[i]) { std::printf(" multi-GPU matvec differs from the one-GPU result at row %d\n", i + 1); return 1; }
+    std::vector<dp> ya(y1), yb(y1);
+    A.matvec_add(xs.data(), ya.data());
+    A1.matvec_add(xs.data(), yb.data());
+    for (int i = 0; i < n; i++)
+        if (ya[i] != yb[i]) { std::printf(" multi-GPU matvec_add differs at row %d\n", i + 1); return 1; }
+
+    linear_solver *s = cg(tol);
+    s->setup(A);
+    s->set_max_iterations(20 * N);
+    s->solve(A, x.data(), b.data());
+    const long it = (long)s->iterations;
+    if (s->capped()) { std::printf(" multi-GPU cg hit the safety cap\n"); return 1; }
+    const long slack = std::max(1L, (long)std::ceil(0.02 * it1));
+    if (std::labs(it - it1) > slack) { std::printf(" cg iterations: %ld on %d GPUs, %ld on one\n", it, ndev, it1); return 1; }
+    const dp d = rel_diff(x, x1), e = rel_diff(x, xs);
+    if (d > 1e-10) { std::printf(" multi-GPU cg solution differs from the one-GPU solution by %g\n", d); return 1; }
+    if (verbose) std::printf(" o cg on %d GPU(s): %ld iterations (one GPU: %ld), |x - x_1gpu| / |x_1gpu| = %g, error vs manufactured %g\n",
+                             ndev, it, it1, d, e);
+
+    // Jacobi-preconditioned cg and bicgstab on the sharded operator against the manufactured solution
+    linear_solver *pc = jacobi();
+    pc->setup(A);
+    std::fill(x.begin(), x.end(), 0.0);
+    linear_solver *s2 = cg(tol);
+    s2->setup(A);
+    s2->set_max_iterations(20 * N);
+    s2->solve(A, x.data(), b.data(), pc);
+    if (s2->capped() || rel_diff(x, x1) > 1e-8) { std::printf(" multi-GPU jacobi-pcg failed: %g\n", rel_diff(x, x1)); return 1; }
+    if (verbose) std::printf(" o jacobi-pcg on %d GPU(s): %ld iterations\n", ndev, (long)s2->iterations);
+    std::fill(x.begin(), x.end(), 0.0);
+    linear_solver *s3 = bicgstab(tol);
+    s3->setup(A);
+    s3->set_max_iterations(20 * N);
+    s3->solve(A, x.data(), b.data());
+    if (s3->capped() || rel_diff(x, x1) > 1e-8) { std::printf(" multi-GPU bicgstab failed: %g\n", rel_diff(x, x1)); return 1; }
+    if (verbose) std::printf(" o bicgstab on %d GPU(s): %ld iterations\n", ndev, (long)s3->iterations);
+    return 0;
+}

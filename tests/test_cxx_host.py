@@ -17,6 +17,8 @@ PROGS = ["solver_test_diffusion_1d", "solver_test_advection_diffusion_1d", "solv
 # (first run on a GPU in round 2, visit r2a)
 PROGS += ["matrix_test_strategy", "matrix_test_set_multiple_entries", "matrix_test_set_entry_with_realloc",
           "matrix_test_permute"]
+# the multi-GPU path through the host mirror alone: all visible GPUs, one process, no Python
+PROGS += ["solver_test_multi_gpu"]
 
 
 def build():

@@ -42,3 +42,20 @@ def test_row_sharded_parity(world, transport):
     assert "dist gpu ok" in r.stdout
     if world > 1:
         assert f"transport {'peer-memory' if transport == 'p2p' else 'nccl'}" in r.stdout, r.stdout[-500:]
+
+
+def test_a_missing_peer_is_an_error():
+    """Every device-side wait is bounded (device_utils.cuh spin_wait): a peer that never shows up turns
+    into SIGB_ERR_COMM at the next synchronisation instead of stale halo data in the result."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
+           os.path.join(ROOT, "tests", "dist_fault_worker.py")]
+    env = dict(os.environ, SIGB_WAIT_TIMEOUT_MS="1500")
+    env.pop("SIGB_TRANSPORT", None)
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
+    assert "fault ok" in r.stdout

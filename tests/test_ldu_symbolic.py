@@ -136,76 +136,124 @@ def test_symbolic_rejects_bad_columns():
     assert e.value.status == 1
 
 
-def syncfree_sweep_model(rows, ptr, node, val, start, n, grid_threads, rng, warp=4):
-    """Model of tri_syncfree_kernel's control flow (csrc/ldu.cu, EXPERIMENTAL): positions in
-    level order dealt to `grid_threads` resident threads grid-stride, a warp = `warp`
-    consecutive lanes running ONE loop in which every unfinished lane polls once and advances
-    as far as it can; warps are scheduled in random order, one loop trip at a time.  Returns
-    the solution and the number of trips of the busiest warp; raises if no warp can progress."""
-    x = np.full(n, np.nan)
-    published = np.zeros(n, bool)
-    nwarps = grid_threads // warp
-    state = []
-    for w in range(nwarps):
-        state.append({"base": w * warp, "lanes": None, "trips": 0})
+def chunked_sweep_model(ptr, node, val, start, n, chunk_rows, backward, rng, warp=4, max_delay=3):
+    """Model of tri_chunked_kernel (csrc/ldu.cu): thread t owns the rows [t B, (t + 1) B) counted from
+    the sweep's start and solves them in order; warps run trips in lockstep, the warps in a random
+    order; per trip two convergent rounds resolve the next entry from the lane's own last result, from
+    the last result of the owning lane of the same warp (the shuffle), or from the published words,
+    which become visible only a random number of scheduling steps after they were written."""
+    nchunks = (n + chunk_rows - 1) // chunk_rows
+    nwarps = (nchunks + warp - 1) // warp
+    x = np.zeros(n)
+    visible_at = np.full(n, np.inf)          # global step at which the published words of row i can be read
+    clock = 0
+    lanes = []
+    for t in range(nwarps * warp):
+        if t < nchunks:
+            lo, hi = t * chunk_rows, min(n, (t + 1) * chunk_rows)
+            i, last = (lo + 1, hi) if not backward else (n - lo, n - hi + 1)
+            lanes.append({"i": i, "last": last, "done": False, "have": False, "k": 0, "e": 0, "z": 0.0,
+                          "prev_row": 0, "prev_z": 0.0})
+        else:
+            lanes.append({"done": True, "prev_row": 0, "prev_z": 0.0, "have": False})
+    step = -1 if backward else 1
 
-    def load(st):
-        lanes = []
-        for lane in range(warp):
-            p_ = st["base"] + lane
-            if p_ < n:
-                i = rows[p_]
-                lanes.append({"i": i, "k": ptr[i - 1] - 1, "e": ptr[i] - 1, "z": start[i - 1], "done": False})
-            else:
-                lanes.append({"done": True})
-        st["lanes"] = lanes
+    def owner(j, t_base):
+        pos = (n - j) if backward else (j - 1)
+        return pos // chunk_rows - t_base
 
-    live = [w for w in range(nwarps) if state[w]["base"] < n]
-    for w in live:
-        load(state[w])
-    idle_rounds = 0
+    def consume(ln, xj):
+        ln["z"] = ln["z"] - val[ln["k"]] * xj
+        ln["k"] += 1
+
+    live = list(range(nwarps))
+    idle = 0
+    trips = 0
     while live:
         progressed = False
         for w in rng.permutation(live):
-            st = state[w]
-            st["trips"] += 1
-            for ln in st["lanes"]:
+            clock += 1
+            trips += 1
+            base = w * warp
+            wl = lanes[base:base + warp]
+            for ln in wl:
+                if not ln["done"] and not ln["have"]:
+                    i = ln["i"]
+                    ln["k"], ln["e"], ln["z"], ln["have"] = ptr[i - 1] - 1, ptr[i] - 1, start[i - 1], True
+            for _ in range(2):                                   # the convergent rounds
+                snap = [(l["prev_row"], l["prev_z"]) for l in wl]    # what the shuffles can deliver
+                for ln in wl:
+                    if ln["done"] or ln["k"] >= ln["e"]:
+                        continue
+                    j = node[ln["k"]]
+                    ol = owner(j, base)
+                    if j == ln["prev_row"]:
+                        consume(ln, ln["prev_z"]); progressed = True
+                    elif 0 <= ol < warp and snap[ol][0] == j:
+                        consume(ln, snap[ol][1]); progressed = True
+                    elif visible_at[j - 1] <= clock:
+                        consume(ln, x[j - 1]); progressed = True
+            for ln in wl:
                 if ln["done"]:
                     continue
-                while ln["k"] < ln["e"] and published[node[ln["k"]] - 1]:
-                    ln["z"] = ln["z"] - val[ln["k"]] * x[node[ln["k"]] - 1]
-                    ln["k"] += 1
+                while ln["k"] < ln["e"]:
+                    j = node[ln["k"]]
+                    if j == ln["prev_row"]:
+                        consume(ln, ln["prev_z"])
+                    elif visible_at[j - 1] <= clock:
+                        consume(ln, x[j - 1])
+                    else:
+                        break
                     progressed = True
                 if ln["k"] == ln["e"]:
-                    x[ln["i"] - 1] = ln["z"]
-                    published[ln["i"] - 1] = True
-                    ln["done"] = True
+                    i = ln["i"]
+                    x[i - 1] = ln["z"]
+                    visible_at[i - 1] = clock + int(rng.integers(0, max_delay + 1))
+                    ln["prev_row"], ln["prev_z"], ln["have"] = i, ln["z"], False
                     progressed = True
-            if all(ln["done"] for ln in st["lanes"]):
-                st["base"] += grid_threads
-                if st["base"] < n:
-                    load(st)
-                else:
-                    live = [v for v in live if v != w]
-        idle_rounds = 0 if progressed else idle_rounds + 1
-        assert idle_rounds < 2, "no warp can make progress: the sweep would hang"
-    return x, max(st["trips"] for st in state)
+                    if i == ln["last"]:
+                        ln["done"] = True
+                    else:
+                        ln["i"] = i + step
+            if all(l["done"] for l in wl):
+                live = [v for v in live if v != w]
+        idle = 0 if progressed else idle + 1
+        assert idle <= max_delay + 2, "no warp can make progress: the sweep would hang"
+    return x, trips
 
 
 @pytest.mark.parametrize("case", list(cases()), ids=lambda c: c[0])
-@pytest.mark.parametrize("grid_threads", [4, 16, 64])
-def test_syncfree_sweep_model_terminates_and_matches(orc, case, grid_threads):
-    """The opt-in sync-free sweeps: under random warp scheduling, with levels cutting through
-    warps and fewer resident threads than rows, every sweep terminates and gives the serial
-    result bit for bit."""
+@pytest.mark.parametrize("chunk_rows", [1, 3, 16])
+def test_chunked_sweep_model_terminates_and_matches(orc, case, chunk_rows):
+    """The chunked sweeps: under random warp scheduling, delayed visibility of the published words and
+    any chunk length, every sweep terminates and gives the serial result bit for bit."""
     _, n, ptr, node, val = case
-    S = sb.ldu_symbolic(n, ptr, node)
     F = orc.ldu_setup(orc.Matrix(orc.CSR, n, n, node, val, ptr=ptr))
-    rng = np.random.default_rng(grid_threads)
+    rng = np.random.default_rng(chunk_rows)
     b = rng.standard_normal(n)
-    y, _ = syncfree_sweep_model(S["forward_rows"], F.Lptr, F.Lnode, F.Lval, b, n, grid_threads, rng)
-    x, _ = syncfree_sweep_model(S["backward_rows"], F.Uptr, F.Unode, F.Uval, y / F.D, n, grid_threads, rng)
+    y, _ = chunked_sweep_model(F.Lptr, F.Lnode, F.Lval, b, n, chunk_rows, False, rng)
+    x, _ = chunked_sweep_model(F.Uptr, F.Unode, F.Uval, y / F.D, n, chunk_rows, True, rng)
     assert np.array_equal(x, orc.ldu_solve(F, b))
+
+
+def test_chunked_sweep_is_a_wavefront_on_the_stencil(orc):
+    """Chunk length = bandwidth on the N x N five-point stencil: the chunks run one trip apart, so a
+    sweep takes about N (own rows) + N (fill of the wavefront) lockstep trips per warp when published
+    words are visible at once -- the dependency through the neighbouring chunk comes from the shuffle."""
+    N = 16
+    n = N * N
+    ptr, node, val = G.poisson2d_csr(N)
+    F = orc.ldu_setup(orc.Matrix(orc.CSR, n, n, node, val, ptr=ptr))
+    b = np.random.default_rng(0).standard_normal(n)
+
+    class InOrder:                       # warps scheduled round-robin, no visibility delay
+        def permutation(self, live): return list(live)
+        def integers(self, a, b): return 0
+
+    y, trips = chunked_sweep_model(F.Lptr, F.Lnode, F.Lval, b, n, N, False, InOrder(), warp=N, max_delay=0)
+    x, trips_b = chunked_sweep_model(F.Uptr, F.Unode, F.Uval, y / F.D, n, N, True, InOrder(), warp=N, max_delay=0)
+    assert np.array_equal(x, orc.ldu_solve(F, b))
+    assert trips <= 2 * N + 2 and trips_b <= 2 * N + 2, (trips, trips_b)
 
 
 def test_symbolic_on_random_patterns_hypothesis(orc):
@@ -250,16 +298,16 @@ def test_symbolic_on_random_patterns_hypothesis(orc):
     check()
 
 
-def test_syncfree_sweep_model_on_random_patterns_hypothesis(orc):
-    """The sync-free sweep model on random patterns, warp widths and resident-thread counts: it
-    always terminates (no schedule can starve the lowest unfinished position) and reproduces the
-    serial solve bit for bit."""
+def test_chunked_sweep_model_on_random_patterns_hypothesis(orc):
+    """The chunked sweep model on random patterns, warp widths, chunk lengths and visibility delays:
+    it always terminates (every row depends on lower rows only, i.e. on its own thread's past or on
+    lower threads) and reproduces the serial solve bit for bit."""
     from hypothesis import given, settings, strategies as st
 
     @settings(max_examples=40, deadline=None)
-    @given(st.integers(2, 60), st.floats(0.02, 0.5), st.sampled_from([1, 2, 4, 8]), st.integers(1, 6),
-           st.integers(0, 2**31 - 1))
-    def check(n, density, warp, warps, seed):
+    @given(st.integers(2, 60), st.floats(0.02, 0.5), st.sampled_from([1, 2, 4, 8]), st.integers(1, 9),
+           st.integers(0, 4), st.integers(0, 2**31 - 1))
+    def check(n, density, warp, chunk_rows, delay, seed):
         rng = np.random.default_rng(seed)
         mask = (rng.random((n, n)) < density) | np.eye(n, dtype=bool)
         rows = [rng.permutation(np.flatnonzero(mask[i]) + 1) for i in range(n)]
@@ -267,12 +315,10 @@ def test_syncfree_sweep_model_on_random_patterns_hypothesis(orc):
         node = np.concatenate(rows).astype(np.int32)
         val = rng.uniform(-1, 1, node.size)
         val[node == np.repeat(np.arange(1, n + 1), np.diff(ptr))] += n      # diagonally dominant: no pivot trouble
-        S = sb.ldu_symbolic(n, ptr, node)
         F = orc.ldu_setup(orc.Matrix(orc.CSR, n, n, node, val, ptr=ptr))
         b = rng.standard_normal(n)
-        g = warp * warps
-        y, _ = syncfree_sweep_model(S["forward_rows"], F.Lptr, F.Lnode, F.Lval, b, n, g, rng, warp=warp)
-        x, _ = syncfree_sweep_model(S["backward_rows"], F.Uptr, F.Unode, F.Uval, y / F.D, n, g, rng, warp=warp)
+        y, _ = chunked_sweep_model(F.Lptr, F.Lnode, F.Lval, b, n, chunk_rows, False, rng, warp=warp, max_delay=delay)
+        x, _ = chunked_sweep_model(F.Uptr, F.Unode, F.Uval, y / F.D, n, chunk_rows, True, rng, warp=warp, max_delay=delay)
         assert np.array_equal(x, orc.ldu_solve(F, b))
 
     check()
