@@ -836,6 +836,99 @@ def run_ldu(args):
 
 
 
+def run_lanczos(args):
+    """`lanczos(A, T, Q)` (src/eigensolver.f90:27-90) device-resident: steps/s with the basis left on
+    the device (sigb_lanczos_dev), the share of the re-orthogonalisation sweeps, and the same call
+    through host pointers (copy-back of Q inside).  Per step i: one SpMV + dot, the three-term
+    update, i - 2 re-orthogonalisation sweeps (w -= (q_k . w) q_k, strictly one after the other as in
+    the reference: each coefficient needs the updated w), the norm and the scaling.
+    Algorithmic bytes: SpMV 12 nnz + 20 n; a sweep reads w, q_k and writes w, with the next
+    coefficient's operand q_{k+1} read alongside = 32 n moved, 24 n per earlier vector compulsory."""
+    import torch
+
+    import sigma_b200 as sb
+    from sigma_b200 import generators as G
+
+    peak, _ = peaks()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    sb.init(0)
+    stream = torch.cuda.Stream(device=dev)
+    sb.set_stream(stream.cuda_stream)
+    nq = args.lanczos_steps
+    for kind, n in (("er", args.lanczos_n), ("surrogate", args.lanczos_n_big)):
+        if n <= 0:
+            continue
+        t0 = time.time()
+        if kind == "er":
+            ptr, node, val = G.erdos_renyi_csr(n, seed=7, shift=0.0)
+        else:   # same row-length law, uniformly random columns, made symmetric in pattern only by chance: Lanczos
+                # identities that need symmetry are not checked on it, only throughput
+            rng = np.random.default_rng(7)
+            deg = 1 + rng.poisson(np.log2(n), n).astype(np.int64)
+            ptr = np.concatenate([[1], 1 + np.cumsum(deg)]).astype(np.int32)
+            node = rng.integers(1, n + 1, int(ptr[-1] - 1), dtype=np.int32)
+            val = rng.random(node.size)
+        gen_s = time.time() - t0
+        nnz = int(node.size)
+        A = sb.csr_matrix(n, n, ptr, node, val)
+        del ptr, node, val
+        q1h = 2 * np.random.default_rng(3).random(n) - 1
+        with torch.cuda.stream(stream):
+            q1 = torch.from_numpy(q1h).to(dev)
+            Q = torch.empty(n * nq, dtype=torch.float64, device=dev)
+            x = torch.from_numpy(q1h).to(dev)
+            y = torch.empty(n, dtype=torch.float64, device=dev)
+        stream.synchronize()
+        sb.lanczos_dev(A, min(nq, 4), Q, q1)                      # warm-up (kernel loads, scratch pool)
+        torch.cuda.synchronize()
+        launches0 = sb.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        T = sb.lanczos_dev(A, nq, Q, q1)
+        e1.record(stream)
+        e1.synchronize()
+        t_dev = e0.elapsed_time(e1) * 1e-3
+        launches = sb.launch_count() - launches0
+        # SpMV + dot alone, for the split
+        for _ in range(3):
+            A.matvec_dot_dev(x, y, fetch=False)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(10):
+            A.matvec_dot_dev(x, y, fetch=False)
+        e1.record(stream)
+        e1.synchronize()
+        t_spmv = e0.elapsed_time(e1) * 1e-4
+        sweeps = sum(max(i - 2, 0) for i in range(2, nq))
+        t_sweeps = t_dev - nq * t_spmv                           # everything that is not SpMV: sweeps + 3 passes per step
+        by_sweeps = 32 * n * sweeps + (40 + 16 + 24) * n * nq    # recurrence (w, q_i, q_{i-1}, q_1 in, w out), norm, scale
+        out = {"row": "lanczos, device-resident (sigb_lanczos_dev)", "matrix": kind, "n": n, "nnz": nnz, "steps": nq,
+               "seconds": t_dev, "steps_per_s": nq / t_dev, "launches": int(launches),
+               "spmv_dot_us": t_spmv * 1e6, "spmv_share": nq * t_spmv / t_dev,
+               "reorth_sweeps": sweeps, "vector_passes_seconds": t_sweeps,
+               "roofline": {"bound": "hbm", "kernel": "re-orthogonalisation sweep + recurrence / norm / scale passes (ew_kernel)",
+                            "algorithmic_bytes": by_sweeps, "achieved": by_sweeps / max(t_sweeps, 1e-9) / 1e9, "peak": peak,
+                            "unit": "GB/s", "frac": by_sweeps / max(t_sweeps, 1e-9) / 1e9 / peak},
+               "gen_s": gen_s}
+        if kind == "er":
+            # identities of the symmetric operator: T symmetric tridiagonal by construction; Q orthonormal
+            Qh = Q.view(nq, n)
+            gram = (Qh @ Qh.T).cpu().numpy()
+            out["orthogonality_per_entry"] = float(np.sqrt(((gram - np.eye(nq)) ** 2).sum()) / nq)
+            # the host-pointer call (what the Fortran shim issues): H2D of q1, D2H of Q inside
+            Qhost = np.zeros(n * nq)                                # touched: no first-touch page faults in the timing
+            t1 = time.perf_counter()
+            T2, _ = sb.lanczos(A, nq, q1h)
+            t_host = time.perf_counter() - t1
+            out["host_pointer_call"] = {"seconds": t_host, "steps_per_s": nq / t_host, "d2h_bytes": 8 * n * nq,
+                                        "T_equal_to_device_resident": bool(np.array_equal(T, T2))}
+            del Qhost
+        print(json.dumps(out), flush=True)
+        A.destroy()
+        del Q, q1, x, y
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -847,7 +940,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed parity gate (kernel A/B runs only)")
     ap.add_argument("--quick", action="store_true", help="kernel A/B runs: print a short line, skip e2e and the CPU leg")
-    ap.add_argument("--rows", default="headline", choices=["headline", "widened", "ldu"],
+    ap.add_argument("--lanczos-steps", type=int, default=64)
+    ap.add_argument("--lanczos-n", type=int, default=2_000_000)
+    ap.add_argument("--lanczos-n-big", type=int, default=0, help="second size with the surrogate generator (e.g. 20000000)")
+    ap.add_argument("--rows", default="headline", choices=["headline", "widened", "ldu", "lanczos"],
                     help="headline: the contract line (default); widened / ldu: the SURVEY 8f rows, one JSON line each")
     ap.add_argument("--wgrid", type=int, default=2048)
     ap.add_argument("--fem", type=int, default=1025)
@@ -859,6 +955,8 @@ def main():
         run_widened(args)
     elif args.rows == "ldu":
         run_ldu(args)
+    elif args.rows == "lanczos":
+        run_lanczos(args)
     elif args.impl == "reference":
         run_reference(args)
     else:

@@ -355,6 +355,11 @@ SIGB_API int sigb_solver_destroy(sigb_solver_t s);
  *  T  : T(3, n) column-major;  Q : Q(nrow, n) column-major. */
 SIGB_API int sigb_lanczos(sigb_matrix_t A, int32_t n, const double *q1,
                           uint64_t seed, double *T, double *Q);
+/* lanczos with the basis resident on the device: Q_dev (nrow x n, column-major)
+ * and the optional start vector q1_dev are DEVICE pointers; only T comes back to
+ * the host.  Same loop (eigensolver.f90:27-90). */
+SIGB_API int sigb_lanczos_dev(sigb_matrix_t A, int32_t n, const double *q1_dev,
+                              uint64_t seed, double *T, double *Q_dev);
 /* eigensolve(A, lambda, V) (src/eigensolver.f90:160-184): lanczos, symmetric
  * tridiagonal eigen-solve (stands in for LAPACK dstev, :174), V = V*Q on the
  * device, sign normalisation (:178-180).  lambda ascending. */

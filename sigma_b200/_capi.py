@@ -87,6 +87,7 @@ PROTOTYPES = {
     "sigb_solver_get_vector": (C.c_int, [_vp, C.c_char_p, _vp]),
     "sigb_solver_destroy": (C.c_int, [_vp]),
     "sigb_lanczos": (C.c_int, [_vp, _i32, _vp, C.c_uint64, _vp, _vp]),
+    "sigb_lanczos_dev": (C.c_int, [_vp, _i32, _vp, C.c_uint64, _vp, _vp]),
     "sigb_eigensolve": (C.c_int, [_vp, _i32, _vp, C.c_uint64, _vp, _vp]),
     "sigb_generalized_lanczos": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, C.c_uint64, _vp, _vp]),
     "sigb_generalized_eigensolve": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, C.c_uint64, _vp, _vp]),

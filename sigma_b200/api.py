@@ -31,7 +31,7 @@ import numpy as np
 from . import _capi
 from ._capi import ROW, COL, SigmaError, as_f64, as_i32, check, lib, ptr
 
-__all__ = ["init", "Graph", "Matrix", "Solver", "cg", "bicgstab", "jacobi", "ldu", "ldu_symbolic", "lanczos", "eigensolve",
+__all__ = ["init", "Graph", "Matrix", "Solver", "cg", "bicgstab", "jacobi", "ldu", "ldu_symbolic", "lanczos", "lanczos_dev", "eigensolve",
            "generalized_lanczos", "generalized_eigensolve",
            "csr_matrix", "csc_matrix", "ellpack_matrix", "SigmaError", "launch_count", "set_stream",
            "synchronize", "Expression", "operator_sum", "operator_product", "adjoint", "sparse_matrix",
@@ -445,6 +445,14 @@ def lanczos(A: Matrix, n: int, q1=None, seed: int = 0):
     q1a = as_f64(q1) if q1 is not None else None
     check(lib().sigb_lanczos(A._h, n, ptr(q1a), seed, ptr(T), ptr(Q)))
     return T.reshape(n, 3).T.copy(), Q.reshape(n, A.nrow).T
+
+
+def lanczos_dev(A: Matrix, n: int, Q_dev, q1_dev=None, seed: int = 0):
+    """lanczos with the basis left on the device: Q_dev is a device buffer of nrow * n doubles
+    (column-major Q(nrow, n)), q1_dev an optional device start vector.  Returns T[3, n]."""
+    T = np.empty(3 * n)
+    check(lib().sigb_lanczos_dev(A._h, n, ptr(q1_dev), seed, ptr(T), ptr(Q_dev)))
+    return T.reshape(n, 3).T.copy()
 
 
 def eigensolve(A: Matrix, n: int, q1=None, seed: int = 0):

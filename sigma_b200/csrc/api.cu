@@ -938,6 +938,37 @@ int sigb_lanczos(sigb_matrix_t A, int32_t n, const double *q1, uint64_t seed, do
     return lanczos_common(A, n, q1, seed, T, Q, nullptr, false);
 }
 
+// lanczos with everything resident on the device: Q_dev (nrow x n, column-major like the Fortran
+// array) and the optional start vector are device pointers, only T (3 n doubles) comes back to the
+// host.  What a caller that keeps the Lanczos basis on the device uses -- and what bench.py times
+// (the host-pointer form above spends most of its time copying Q back).
+int sigb_lanczos_dev(sigb_matrix_t A, int32_t n, const double *q1_dev, uint64_t seed, double *T, double *Q_dev)
+{
+    if (A && A->mg) { ::sigb::set_error("sigb_lanczos_dev: not available for a single-process multi-GPU operator"); return SIGB_ERR_UNSUPPORTED; }
+    SIGB_REQUIRE(A && n >= 1 && T && Q_dev, SIGB_ERR_ARG, "sigb_lanczos_dev: bad argument");
+    const int64_t nglob = A->dist ? dist_global_n(A) : A->ncol;
+    SIGB_REQUIRE((A->dist ? dist_global_n(A) : A->nrow) == nglob, SIGB_ERR_NONSQUARE, "lanczos: operator is not square");
+    const int64_t nr = A->nrow;
+    cudaStream_t st = ctx().stream;
+    double *Td = nullptr, *w = nullptr;
+    void *kst = nullptr;
+    auto cleanup = [&]() { tmp_free(Td); tmp_free(w); tmp_free(kst); };
+    cudaError_t e = tmp_alloc(&Td, (size_t)3 * n);
+    if (e == cudaSuccess) e = tmp_alloc(&w, (size_t)nr);
+    if (e == cudaSuccess) e = tmp_alloc_bytes(&kst, kstate_bytes());
+    if (e == cudaSuccess) e = cudaMemsetAsync(kst, 0, kstate_bytes(), st);
+    if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "lanczos scratch", __FILE__, __LINE__); }
+    int rc = lanczos_dev(A, n, q1_dev, seed, A->dist ? dist_row_offset(A) : 0, Td, Q_dev, w, (KState *)kst);
+    if (rc == SIGB_OK) {
+        e = cudaMemcpyAsync(T, Td, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "lanczos T", __FILE__, __LINE__);
+    }
+    cleanup();
+    if (rc == SIGB_OK) rc = check_fault("sigb_lanczos_dev");
+    return rc;
+}
+
 int sigb_eigensolve(sigb_matrix_t A, int32_t n, const double *q1, uint64_t seed, double *lambda, double *V)
 {
     if (A && A->mg) { ::sigb::set_error("sigb_eigensolve: not available for a single-process multi-GPU operator"); return SIGB_ERR_UNSUPPORTED; }

@@ -23,6 +23,9 @@
 // shape.  Index work + one pass over the calls: HBM-bound, ~40 B per call.
 #include <vector>
 
+#include <chrono>
+#include <stdio.h>
+
 #include "internal.h"
 #include "device_utils.cuh"
 
@@ -128,6 +131,14 @@ int sigb_matrix_add_values(sigb_matrix_t A, int64_t count, const int32_t *i1, co
     const int64_t nslots = (g->kind == G_ELL) ? (int64_t)g->n_pad * g->max_d : g->ne;
     SIGB_REQUIRE(nslots <= INT32_MAX - 16, SIGB_ERR_ARG, "sigb_matrix_add_values: matrix too large for int32 positions");
 
+    static const bool verbose = env_int("SIGB_VERBOSE", 0) == 1;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto stage = [&](const char *what) {
+        if (!verbose) return;
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "sigma_b200: add_values %-28s at %8.3f ms\n", what,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
     int32_t *ci = nullptr, *cj = nullptr, *slot1 = nullptr, *one_line = nullptr;
     int32_t *bucket_ptr = nullptr, *unused_node = nullptr, *perm = nullptr;
     double *cz = nullptr;
@@ -151,6 +162,7 @@ int sigb_matrix_add_values(sigb_matrix_t A, int64_t count, const int32_t *i1, co
     h_miss.count = 0;
     h_miss.first = ~0ull;
     AS_CUDA(cudaMemcpyAsync(miss, &h_miss, sizeof(Miss), cudaMemcpyHostToDevice, st));
+    stage("scratch + host-to-device");
 
     // 1. locate
     if (g->kind == G_ELL)
@@ -176,6 +188,7 @@ int sigb_matrix_add_values(sigb_matrix_t A, int64_t count, const int32_t *i1, co
         return SIGB_ERR_ARG;
     }
 
+    stage("locate");
     // 2. group the calls by stored position: the stable transpose of a one-line
     //    "graph" whose ids are the positions
     AS_CUDA(tmp_alloc(&one_line, (size_t)(2 + kPad)));
@@ -186,13 +199,16 @@ int sigb_matrix_add_values(sigb_matrix_t A, int64_t count, const int32_t *i1, co
     }
     AS_TRY(device_transpose_cs(one_line, slot1, 1, (int32_t)nslots, count, &bucket_ptr, &unused_node, &perm));
 
+    stage("stable bucket sort");
     // 3. reduce, in call order
     reduce_buckets_kernel<<<grid_for(nslots), kThreads, 0, st>>>(bucket_ptr, perm, cz, nslots, A->val);
     count_launch();
     AS_CUDA(cudaGetLastError());
     AS_CUDA(cudaStreamSynchronize(st));
     A->val_t_valid = false;
+    stage("ordered reduce");
     cleanup();
+    stage("scratch released");
 #undef AS_CUDA
 #undef AS_TRY
     return SIGB_OK;
