@@ -408,8 +408,12 @@ SIGB_API int sigb_halo_build(int32_t lo, int32_t hi, const int32_t *ptr_blk1,
  * capacity n tiles. */
 SIGB_API int sigb_debug_row_tiles(int32_t n, const int32_t *ptr1, int32_t *tiles,
                                   int32_t *ntiles);
-/* Diagnostic, needs the GPU: the same tiling built by the experimental device
- * path (csrc/tiles_device.cu, SIGB_DEVICE_TILES=1) from an uploaded copy of
+/* The balanced tiling used for row-sharded operators: exactly m * groups tiles of
+ * nearly equal entry counts when the limits allow it (else the greedy tiling). */
+SIGB_API int sigb_debug_row_tiles_balanced(int32_t n, const int32_t *ptr1, int32_t groups,
+                                           int32_t *tiles, int32_t *ntiles);
+/* Diagnostic, needs the GPU: the same tiling built by the device
+ * path (csrc/tiles_device.cu) from an uploaded copy of
  * ptr1; same output layout.  Must equal sigb_debug_row_tiles entry for entry. */
 SIGB_API int sigb_debug_row_tiles_dev(int32_t n, const int32_t *ptr1, int32_t *tiles,
                                       int32_t *ntiles);

@@ -172,10 +172,9 @@ __device__ __forceinline__ double grid_allreduce(double v, const CgPersistArgs &
             const double local = __shfl_sync(0xffffffffu, t[0], 0);
             if ((int)threadIdx.x < a.nranks) red_entry_store(&a.peer_red[threadIdx.x]->red[slot][a.me][0], local, flag);
         }
-        if (threadIdx.x == 0) {
-            double g = 0.0;
-            for (int q = 0; q < a.nranks; q++) g = add(g, red_entry_wait(&a.red->red[slot][q][0], flag, s.fault));
-            *s_bcast = g;
+        if (threadIdx.x < 32) {
+            const double g = warp_rank_sum(a.red, slot, 0, a.nranks, flag, s.fault);
+            if (threadIdx.x == 0) *s_bcast = g;
         }
     } else {
         if (threadIdx.x == 0) *s_bcast = t[0];
@@ -383,6 +382,8 @@ int launch_persistent(const CgPersistArgs &a, cudaStream_t st)
 }
 
 }  // namespace
+
+int persistent_grid_ctas() { return SIGB_PERSIST_MINBLOCKS * ctx().num_sms; }
 
 // SIGB_PHASE_TIMERS builds: one device buffer per process, (kPhaseSlots + 1) counters for each
 // of the kPhaseCtas observed CTAs (the last one counts iterations); null in the product build.

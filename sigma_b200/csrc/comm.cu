@@ -188,11 +188,9 @@ __global__ void red_kernel(const __grid_constant__ RedArgs a)
         for (int c = 0; c < a.count; c++) red_entry_store(&e[c], *a.vals[c], flag);
     }
     __syncwarp();
-    if (lane < a.count) {
-        double v = 0.0;
-        for (int q = 0; q < a.nranks; q++)   // rank order
-            v = add(v, red_entry_wait(&a.win->red[slot][q][lane], flag, a.fault));
-        *a.vals[lane] = v;
+    for (int c = 0; c < a.count; c++) {
+        const double v = warp_rank_sum(a.win, slot, c, a.nranks, flag, a.fault);   // rank order, all lanes alike
+        if (lane == 0) *a.vals[c] = v;
     }
     __syncwarp();
     if (lane == 0) a.win->red_seq = s;
@@ -585,9 +583,11 @@ int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global, const int32_t *part
     if (rc != SIGB_OK) return rc;
     guard.g = g;
 
-    // interior / boundary tile lists
+    // communication CTAs of the fused SpMV (spmv_device.cuh): ~8 entries per thread, at most 8 CTAs
+    const int push_ctas = (P > 1 && comm->p2p && total_send > 0) ? std::min(8, (total_send + 8 * kThreads - 1) / (8 * kThreads)) : 0;
+    // interior / boundary tile lists; the tiling is balanced over the compute CTAs of the persistent CG kernel
     std::vector<TileDesc> tiles, ti, tb;
-    build_tiles_host(ptr.data(), nloc, tiles);
+    build_tiles_balanced(ptr.data(), nloc, persistent_grid_ctas() - push_ctas, tiles);
     for (const TileDesc &t : tiles) {
         bool boundary = false;
         for (int32_t k = t.ks; k < t.ke && !boundary; k++) boundary = local[k] > nloc;
@@ -595,14 +595,15 @@ int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global, const int32_t *part
     }
     // the device tile table is re-ordered: interior tiles first, boundary last
     CsrView &V = g->stored;
-    V.n_interior = (int32_t)ti.size();
-    V.n_boundary = (int32_t)tb.size();
     cudaStream_t st = ctx().stream;
     std::vector<TileDesc> ordered(ti);
     ordered.insert(ordered.end(), tb.begin(), tb.end());
-    if (!ordered.empty())
-        SIGB_CUDA(cudaMemcpyAsync(V.tiles, ordered.data(), sizeof(TileDesc) * ordered.size(), cudaMemcpyHostToDevice, st));
     SIGB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(V.tiles);                           // the greedy table of sigb_cs_graph_create
+    V.tiles = nullptr;
+    SIGB_CHECK(upload_tiles(V, ordered));
+    V.n_interior = (int32_t)ti.size();
+    V.n_boundary = (int32_t)tb.size();
     V.tiles_interior = V.tiles;                  // views into the same table
     V.tiles_boundary = V.tiles + V.n_interior;
     SIGB_CUDA(cudaMalloc((void **)&D->send_rows, sizeof(int32_t) * std::max(total_send, 1)));
@@ -631,8 +632,7 @@ int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global, const int32_t *part
         D->sync.halo_stride = D->stride;
         D->sync.send_rows = D->send_rows;
         D->sync.total_send = total_send;
-        // communication CTAs of the fused SpMV (spmv_device.cuh): ~8 entries per thread, at most 8 CTAs
-        D->sync.push_ctas = total_send > 0 ? std::min(8, (total_send + 8 * kThreads - 1) / (8 * kThreads)) : 0;
+        D->sync.push_ctas = push_ctas;
         for (int q = 0; q < kMaxRanks; q++) {
             D->sync.peer[q] = q < P ? (HaloWin *)peers[q] : nullptr;
             D->sync.dst[q] = nullptr;

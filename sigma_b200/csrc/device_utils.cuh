@@ -162,6 +162,21 @@ __device__ __forceinline__ double red_entry_wait(const RedEntry *e, unsigned int
     return __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | lo.x));
 }
 
+// Warp-collective: lane q < nranks fetches rank q's contribution to value d of this slot (all ranks
+// polled at once: one L2 round trip whatever the number of GPUs, where a single thread walking the
+// ranks paid two dependent round trips per rank), then every lane adds the contributions in RANK ORDER,
+// so all ranks -- and all lanes -- compute bit-identical totals.
+__device__ __forceinline__ double warp_rank_sum(const RedWin *win, int slot, int d, int nranks, unsigned int flag,
+                                                FaultBlock *fb)
+{
+    const int lane = threadIdx.x & 31;
+    double mine = 0.0;
+    if (lane < nranks) mine = red_entry_wait(&win->red[slot][lane][d], flag, fb);
+    double g = 0.0;
+    for (int q = 0; q < nranks; q++) g = add(g, __shfl_sync(0xffffffffu, mine, q));
+    return g;
+}
+
 // Window of a row-sharded operator: everything peers write into this rank.
 struct HaloWin {
     unsigned long long hflag[2][kMaxRanks];  // [buffer][source]: sequence number of the halo it holds
@@ -274,12 +289,8 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[ND], double *partials,
             __syncwarp();
 #pragma unroll
             for (int d = 0; d < ND; d++) {
-                if (lane == d) {
-                    double g = 0.0;
-                    for (int q = 0; q < red->nranks; q++)
-                        g = add(g, red_entry_wait(&red->win->red[slot][q][d], flag, red->fault));
-                    *out[d] = g;
-                }
+                const double g = warp_rank_sum(red->win, slot, d, red->nranks, flag, red->fault);
+                if (lane == 0) *out[d] = g;
             }
             __syncwarp();
             if (lane == 0) red->win->red_seq = seq;

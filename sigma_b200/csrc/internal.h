@@ -255,6 +255,10 @@ int launch_ell_spmv(int32_t n, int32_t n_pad, int32_t max_d,
                     const double *x, double *y, SpmvMode mode,
                     const DotSpec &dot);
 int build_tiles_host(const int32_t *ptr1, int32_t nrows, std::vector<TileDesc> &tiles);
+// exactly m * groups tiles of nearly equal entry counts when the caps allow it, else the greedy tiling
+int build_tiles_balanced(const int32_t *ptr1, int32_t nrows, int groups, std::vector<TileDesc> &tiles);
+// compute CTAs of the persistent CG kernel on this device (cg_persistent.cu), before communication CTAs are taken off
+int persistent_grid_ctas();
 // tiles_device.cu: the same tiling built on the device from a device-resident ptr (no read-back);
 // also returns the extreme line lengths
 int build_tiles_device(const int32_t *ptr1_dev, int32_t nrows, CsrView &v, int32_t *max_d, int32_t *min_d);

@@ -273,6 +273,53 @@ int build_tiles_host(const int32_t *ptr1, int32_t nrows, std::vector<TileDesc> &
     return SIGB_OK;
 }
 
+// Balanced tiling for operators whose tiles are shared round-robin by a KNOWN number of CTAs (`groups`:
+// the compute CTAs of the persistent CG kernel on a row-sharded operator): exactly m * groups tiles of
+// nearly equal entry counts, so that every CTA streams the same number of tiles -- with the greedy
+// tiling a shard of 5130 tiles on 440 CTAs gives some of them 12 tiles and the others 11, and the
+// whole grid waits at the barrier behind the phase for the twelfth (8 % of the SpMV phase).  Tile
+// boundaries sit at the rows where the running entry count passes j * nnz / T.  Falls back to the
+// greedy tiling when the caps cannot be met that way (long or empty rows, tiny matrices).  Tiling
+// never changes a result: rows are summed by one thread each, in stored order, whatever the tile.
+int build_tiles_balanced(const int32_t *ptr1, int32_t nrows, int groups, std::vector<TileDesc> &tiles)
+{
+    const int64_t nnz = nrows > 0 ? (int64_t)ptr1[nrows] - 1 : 0;
+    if (groups <= 0 || nrows <= 0 || nnz <= 0) return build_tiles_host(ptr1, nrows, tiles);
+    int64_t maxrow = 0;
+    for (int32_t i = 0; i < nrows; i++) maxrow = std::max<int64_t>(maxrow, ptr1[i + 1] - ptr1[i]);
+    const int64_t m0 = std::max<int64_t>(1, (nnz + (int64_t)kTileCap * groups - 1) / ((int64_t)kTileCap * groups));
+    for (int64_t m = m0; m <= m0 + 3; m++) {
+        const int64_t T = m * groups;
+        if (T > nrows) break;
+        if ((nnz + T - 1) / T + maxrow > kTileCap) continue;
+        tiles.clear();
+        tiles.reserve((size_t)T);
+        bool ok = true;
+        int32_t s = 0;
+        for (int64_t j = 1; j <= T && ok; j++) {
+            int32_t e;
+            if (j == T) {
+                e = nrows;
+            } else {
+                // first row whose preceding entries reach j * nnz / T (as sigb_partition_rows does)
+                const int64_t target = (nnz * j) / T + 1;     // compare with 1-based ptr
+                e = (int32_t)(std::lower_bound(ptr1 + s, ptr1 + nrows, target,
+                                               [](int32_t p_, int64_t t_) { return (int64_t)p_ < t_; }) - ptr1);
+            }
+            TileDesc d;
+            d.rs = s;
+            d.re = e;
+            d.ks = ptr1[s] - 1;
+            d.ke = ptr1[e] - 1;
+            if (e <= s || e - s > kTileRows || d.ke - d.ks > kTileCap) ok = false;
+            tiles.push_back(d);
+            s = e;
+        }
+        if (ok && s == nrows) return SIGB_OK;
+    }
+    return build_tiles_host(ptr1, nrows, tiles);
+}
+
 // Argument block of one SpMV over all tiles of A (which = 0), or over its
 // interior / boundary sub-tables (which = 1 / 2, NCCL transport).
 #ifdef SIGB_PHASE_TIMERS

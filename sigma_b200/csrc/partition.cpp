@@ -50,6 +50,22 @@ int sigb_debug_row_tiles(int32_t n, const int32_t *ptr1, int32_t *tiles, int32_t
     return SIGB_OK;
 }
 
+// The balanced tiling of row-sharded operators (kernels_spmv.cu build_tiles_balanced), same layout.
+int sigb_debug_row_tiles_balanced(int32_t n, const int32_t *ptr1, int32_t groups, int32_t *tiles, int32_t *ntiles)
+{
+    SIGB_REQUIRE(n >= 0 && ptr1 && tiles && ntiles, SIGB_ERR_ARG, "sigb_debug_row_tiles_balanced: bad argument");
+    std::vector<TileDesc> t;
+    build_tiles_balanced(ptr1, n, groups, t);
+    for (size_t k = 0; k < t.size(); k++) {
+        tiles[4 * k + 0] = t[k].rs;
+        tiles[4 * k + 1] = t[k].re;
+        tiles[4 * k + 2] = t[k].ks;
+        tiles[4 * k + 3] = t[k].ke;
+    }
+    *ntiles = (int32_t)t.size();
+    return SIGB_OK;
+}
+
 int sigb_halo_build(int32_t lo, int32_t hi, const int32_t *ptr_blk1, const int32_t *node_glob1,
                     int32_t *halo, int32_t *nhalo, int32_t *local_node)
 {

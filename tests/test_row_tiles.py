@@ -126,3 +126,50 @@ def test_tilings_on_random_row_lengths_hypothesis():
         assert np.array_equal(device_algorithm_replica(p)[0], want)
 
     check()
+
+
+def balanced_tiles(ptr1, groups):
+    ptr1 = np.ascontiguousarray(ptr1, np.int32)
+    n = ptr1.size - 1
+    out = np.empty((max(n, 1), 4), np.int32)
+    nt = C.c_int32()
+    check(lib().sigb_debug_row_tiles_balanced(n, ptr(ptr1), groups, ptr(out), C.byref(nt)))
+    return out[: nt.value].copy()
+
+
+@pytest.mark.parametrize("groups", [1, 7, 440, 444])
+@pytest.mark.parametrize("case", list(cases()), ids=lambda c: c[0])
+def test_balanced_tiles_are_a_valid_tiling(case, groups):
+    """build_tiles_balanced (row-sharded operators): always a partition of the rows within the limits
+    of the kernel (or single long rows); when it does not fall back to the greedy walk, the tile count
+    is a multiple of `groups` and the tiles differ by at most one row's worth of entries."""
+    _, p = case
+    p = np.asarray(p, np.int32)
+    got = balanced_tiles(p, groups)
+    n = p.size - 1
+    if n == 0:
+        assert got.shape[0] == 0
+        return
+    assert got[0, 0] == 0 and got[-1, 1] == n and np.array_equal(got[1:, 0], got[:-1, 1])
+    assert np.array_equal(got[:, 2], p[got[:, 0]] - 1) and np.array_equal(got[:, 3], p[got[:, 1]] - 1)
+    nrows, nent = got[:, 1] - got[:, 0], got[:, 3] - got[:, 2]
+    assert np.all(nrows >= 1) and np.all(nrows <= ROWS)
+    assert np.all((nent <= CAP) | (nrows == 1))
+    if not np.array_equal(got, greedy(p)):
+        assert got.shape[0] % groups == 0
+        assert nent.max() - nent.min() <= 2 * np.diff(p.astype(np.int64)).max()
+
+
+def test_balanced_tiles_on_a_poisson_shard():
+    """The 8-GPU shard of the headline matrix (2.1 M rows, 5 entries per row) on the 440 compute CTAs of
+    the persistent kernel: 12 tiles for every CTA instead of 11 for some and 12 for the others."""
+    N, rows = 4096, 4096 * 512
+    cnt = np.full(rows, 5, np.int64)
+    cnt[::N] -= 1
+    cnt[N - 1::N] -= 1
+    p = np.concatenate([[1], 1 + np.cumsum(cnt)]).astype(np.int32)
+    g, b = greedy(p), balanced_tiles(p, 440)
+    assert g.shape[0] % 440 != 0 and b.shape[0] % 440 == 0
+    assert b.shape[0] // 440 == -(-g.shape[0] // 440)          # the same number of tiles for the slowest CTA ...
+    nent = b[:, 3] - b[:, 2]
+    assert nent.max() - nent.min() <= 10                       # ... and nobody holds more than anybody else
