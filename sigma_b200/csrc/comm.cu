@@ -583,8 +583,9 @@ int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global, const int32_t *part
     if (rc != SIGB_OK) return rc;
     guard.g = g;
 
-    // communication CTAs of the fused SpMV (spmv_device.cuh): ~8 entries per thread, at most 8 CTAs
-    const int push_ctas = (P > 1 && comm->p2p && total_send > 0) ? std::min(8, (total_send + 8 * kThreads - 1) / (8 * kThreads)) : 0;
+    // communication CTAs of the fused SpMV (spmv_device.cuh): ~8 entries per thread; at most 32 CTAs (7 % of the
+    // persistent grid) -- a graph without locality sends nearly all of x (config 5: 17.5 M entries per rank)
+    const int push_ctas = (P > 1 && comm->p2p && total_send > 0) ? std::min(32, (total_send + 8 * kThreads - 1) / (8 * kThreads)) : 0;
     // interior / boundary tile lists; the tiling is balanced over the compute CTAs of the persistent CG kernel
     std::vector<TileDesc> tiles, ti, tb;
     build_tiles_balanced(ptr.data(), nloc, persistent_grid_ctas() - push_ctas, tiles);
