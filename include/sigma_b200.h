@@ -109,6 +109,24 @@ SIGB_API int sigb_ell_graph_create(int32_t n, int32_t m, int32_t max_d,
 
 /* Reference counting like graph_interface add_reference/remove_reference
  * (src/graph/graph_interfaces.f90:345-363).  create returns refcount 1. */
+/* The graph builders fed by an EDGE STREAM, on the device:
+ *   cs_graph_build       src/graph/formats/cs_graphs.f90:109-197
+ *   ellpack_graph_build  src/graph/formats/ellpack_graphs.f90:105-170
+ * as copy_graph / convert_graph_type drive them (graph_interfaces.f90:276-318).
+ * src_i / src_j: the source graph's edges in ITS iteration order (1-based; an
+ * endpoint 0 in the second role is a null edge and is skipped); trans != 0 swaps
+ * the roles of the endpoints.  Line l of the result holds its DISTINCT neighbours
+ * in the order of their first appearance in the stream -- what the reference's
+ * first-free-slot insertion with its duplicate check and final pruning produces,
+ * bit for bit.  n lines, ids in 1..m.  order as in sigb_cs_graph_create.
+ * The ellpack form pads every row with its last neighbour (:164) and refuses a
+ * row without edges (SIGB_ERR_ISOLATED), like sigb_ell_graph_create. */
+SIGB_API int sigb_cs_graph_build(int32_t n, int32_t m, int64_t count,
+                                 const int32_t *src_i, const int32_t *src_j,
+                                 int trans, int order, sigb_graph_t *g);
+SIGB_API int sigb_ell_graph_build(int32_t n, int32_t m, int64_t count,
+                                  const int32_t *src_i, const int32_t *src_j,
+                                  int trans, sigb_graph_t *g);
 SIGB_API int sigb_graph_retain(sigb_graph_t g);
 SIGB_API int sigb_graph_release(sigb_graph_t g);
 

@@ -49,6 +49,8 @@ PROTOTYPES = {
     "sigb_copy_d2h": (C.c_int, [_vp, _vp, _i64]),
     "sigb_cs_graph_create": (C.c_int, [_i32, _i32, _vp, _vp, C.c_int, _pvp]),
     "sigb_ell_graph_create": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _pvp]),
+    "sigb_cs_graph_build": (C.c_int, [_i32, _i32, _i64, _vp, _vp, C.c_int, C.c_int, _pvp]),
+    "sigb_ell_graph_build": (C.c_int, [_i32, _i32, _i64, _vp, _vp, C.c_int, _pvp]),
     "sigb_graph_retain": (C.c_int, [_vp]),
     "sigb_graph_release": (C.c_int, [_vp]),
     "sigb_cs_graph_get_transpose": (C.c_int, [_vp, _vp, _vp]),

@@ -79,6 +79,22 @@ class Graph:
         g.max_d = node.shape[1]
         return g
 
+    @classmethod
+    def build(cls, frmt, n, m, src_i, src_j, trans=False):
+        """g%build(n, m, get_edges, make_cursor, trans) on the device (cs_graphs.f90:109-197,
+        ellpack_graphs.f90:105-170): the pattern from the source graph's edge stream (src_i, src_j) in
+        its iteration order; frmt "csr" | "csc" | "ellpack"."""
+        src_i, src_j = as_i32(src_i), as_i32(src_j)
+        if src_i.size != src_j.size:
+            raise SigmaError(_capi.ERR_ARG, "edge stream: src_i and src_j differ in length")
+        h = C.c_void_p()
+        if frmt == "ellpack":
+            check(lib().sigb_ell_graph_build(n, m, src_i.size, ptr(src_i), ptr(src_j), int(trans), C.byref(h)))
+        else:
+            check(lib().sigb_cs_graph_build(n, m, src_i.size, ptr(src_i), ptr(src_j), int(trans),
+                                            ROW if frmt == "csr" else COL, C.byref(h)))
+        return cls(h, frmt, n, m)
+
     def transpose_arrays(self, other_dim, ne):
         ptr_t = np.empty(other_dim + 1, np.int32)
         node_t = np.empty(ne, np.int32)

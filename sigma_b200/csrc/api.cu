@@ -139,7 +139,7 @@ struct DevBufGuard {
 };
 
 // Build the stable transpose of a cs / ell graph on the device (once).
-static int ensure_graph_transposed(sigb_graph_t g)
+int ensure_graph_transposed(sigb_graph_t g)
 {
     if (g->has_transposed) return SIGB_OK;
     int32_t *ptr_t = nullptr, *node_t = nullptr, *perm = nullptr;
