@@ -22,6 +22,10 @@ implicit none
 
 integer(c_int), parameter :: SIGB_OK = 0, SIGB_ROW = 0, SIGB_COL = 1
 
+! number of GPUs of the single-process multi-GPU mode (0: one GPU, the default);
+! set by sigma_use_gpus below
+integer(c_int), save :: sigma_gpus_in_use = 0
+
 
 !--------------------------------------------------------------------------!
 interface                                                                  !
@@ -305,6 +309,66 @@ interface                                                                  !
         integer(c_int) :: stat
     end function
 
+    ! single-process multi-GPU mode: the whole pattern in, one row block per GPU behind one handle;
+    ! every other entry point above then takes that handle with the caller's whole arrays
+    function sigb_mgpu_init(ndev) bind(c, name='sigb_mgpu_init') result(stat)
+        import :: c_int
+        integer(c_int), value :: ndev
+        integer(c_int) :: stat
+    end function
+
+    function sigb_mgpu_finalize() bind(c, name='sigb_mgpu_finalize') result(stat)
+        import :: c_int
+        integer(c_int) :: stat
+    end function
+
+    function sigb_mgpu_device_count(ndev) bind(c, name='sigb_mgpu_device_count') result(stat)
+        import :: c_int
+        integer(c_int), intent(out) :: ndev
+        integer(c_int) :: stat
+    end function
+
+    function sigb_mgpu_csr_create(n, ptr1, node1, A) bind(c, name='sigb_mgpu_csr_create') result(stat)
+        import :: c_int, c_int32_t, c_ptr
+        integer(c_int32_t), value :: n
+        integer(c_int32_t), intent(in) :: ptr1(*), node1(*)
+        type(c_ptr), intent(out) :: A
+        integer(c_int) :: stat
+    end function
+
+    ! the graph builders fed by an edge stream (cs_graph_build, ellpack_graph_build), on the device
+    function sigb_cs_graph_build(n, m, count, src_i, src_j, trans, order, g) &
+            & bind(c, name='sigb_cs_graph_build') result(stat)
+        import :: c_int, c_int32_t, c_int64_t, c_ptr
+        integer(c_int32_t), value :: n, m
+        integer(c_int64_t), value :: count
+        integer(c_int32_t), intent(in) :: src_i(*), src_j(*)
+        integer(c_int), value :: trans, order
+        type(c_ptr), intent(out) :: g
+        integer(c_int) :: stat
+    end function
+
+    function sigb_ell_graph_build(n, m, count, src_i, src_j, trans, g) &
+            & bind(c, name='sigb_ell_graph_build') result(stat)
+        import :: c_int, c_int32_t, c_int64_t, c_ptr
+        integer(c_int32_t), value :: n, m
+        integer(c_int64_t), value :: count
+        integer(c_int32_t), intent(in) :: src_i(*), src_j(*)
+        integer(c_int), value :: trans
+        type(c_ptr), intent(out) :: g
+        integer(c_int) :: stat
+    end function
+
+    ! lanczos with Q left on the device (Q_dev, q1_dev are device addresses held as c_ptr)
+    function sigb_lanczos_dev(A, n, q1_dev, seed, T, Q_dev) bind(c, name='sigb_lanczos_dev') result(stat)
+        import :: c_int, c_int32_t, c_int64_t, c_double, c_ptr
+        type(c_ptr), value :: A, q1_dev, Q_dev
+        integer(c_int32_t), value :: n
+        integer(c_int64_t), value :: seed
+        real(c_double), intent(out) :: T(*)
+        integer(c_int) :: stat
+    end function
+
     function c_strlen(s) bind(c, name='strlen') result(n)
         import :: c_ptr, c_size_t
         type(c_ptr), value :: s
@@ -314,6 +378,20 @@ end interface
 
 
 contains
+
+
+!--------------------------------------------------------------------------!
+subroutine sigma_use_gpus(ndev)                                            !
+!--------------------------------------------------------------------------!
+! Switch a serial `use sigma` program to all GPUs of the box (ndev <= 0) or  !
+! to ndev of them: csr matrices mirrored from now on are row-sharded by the  !
+! library (sigb_mgpu_csr_create); nothing else in the program changes.       !
+!--------------------------------------------------------------------------!
+    integer, intent(in) :: ndev
+    call sigb_check( sigb_mgpu_init(int(ndev, c_int)) )
+    call sigb_check( sigb_mgpu_device_count(sigma_gpus_in_use) )
+end subroutine sigma_use_gpus
+
 
 
 !--------------------------------------------------------------------------!
@@ -376,7 +454,16 @@ end module sigma_b200_shim
 !     subroutine sync_mirror(A)                             ! new, private
 !         class(cs_matrix), intent(inout) :: A
 !         integer(c_int) :: order
-!         if (.not. c_associated(A%g%mirror)) then
+!         ! single-process multi-GPU mode (after sigb_mgpu_init): the whole pattern
+!         ! goes in, the library makes one row block per GPU; set_values, matvec,
+!         ! matvec_add and the solvers below then drive all GPUs with whole arrays
+!         if (.not. c_associated(A%mirror) .and. sigma_gpus_in_use > 0 &
+!                 & .and. .not. A%get_col_is_fast .and. A%nrow == A%ncol) then
+!             call sigb_check( sigb_mgpu_csr_create(A%g%n, A%g%ptr, A%g%node, &
+!                                         & A%mirror) )
+!             A%dirty = .true.
+!         endif
+!         if (.not. c_associated(A%mirror) .and. .not. c_associated(A%g%mirror)) then
 !             order = SIGB_ROW
 !             if (A%get_col_is_fast) order = SIGB_COL       ! csc_matrix
 !             call sigb_check( sigb_cs_graph_create(A%g%n, A%g%m, A%g%ptr, &
