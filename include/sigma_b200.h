@@ -337,6 +337,15 @@ SIGB_API int sigb_solver_set_max_iterations(sigb_solver_t s, int64_t cap);
  * rounding either way; bench.py's parity gate uses it to check the small
  * instance with the kernels the full-size run takes. */
 SIGB_API int sigb_solver_set_persistent(sigb_solver_t s, int mode);
+/* NOT in the reference, a PARITY AID: with on != 0 every dot product of the cg /
+ * bicgstab recurrence is summed strictly left to right by one thread -- the
+ * serial `sum(a * b)` of the reference (cg_solvers.f90:135,140;
+ * bicgstab_solvers.f90:155,160,164,168), rounded products, no FMA.  Everything else
+ * in the solvers is element-wise and already reproduces the reference statement for
+ * statement, so a strict-order solve must equal the serial loops BIT FOR BIT:
+ * iterates, scalars and the stopping iteration (tests/test_gpu_solvers.py).  One
+ * GPU, kernel-per-phase path; slow by construction (one thread per dot product). */
+SIGB_API int sigb_solver_set_strict_order(sigb_solver_t s, int on);
 
 /* solver%solve(A, x, b [, pc]): linear_solve / linear_solve_pc
  * (cg_solve cg_solvers.f90:116-150, cg_solve_pc :155-194, bicgstab_solve

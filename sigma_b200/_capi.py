@@ -83,6 +83,7 @@ PROTOTYPES = {
     "sigb_solver_set_params": (C.c_int, [_vp, _f64]),
     "sigb_solver_set_max_iterations": (C.c_int, [_vp, _i64]),
     "sigb_solver_set_persistent": (C.c_int, [_vp, C.c_int]),
+    "sigb_solver_set_strict_order": (C.c_int, [_vp, C.c_int]),
     "sigb_solver_solve": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "sigb_solver_solve_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "sigb_solver_get_info": (C.c_int, [_vp, _pi64, _pf64, C.POINTER(C.c_int)]),

@@ -369,6 +369,11 @@ class Solver:
         """CG loop form: 1 one persistent kernel, 0 three kernels per iteration, -1 the library's choice."""
         check(lib().sigb_solver_set_persistent(self._h, int(mode)))
 
+    def set_strict_order(self, on: bool = True):
+        """Parity aid: dot products summed strictly left to right (one thread), so that the solve equals the
+        serial reference loops bit for bit."""
+        check(lib().sigb_solver_set_strict_order(self._h, int(bool(on))))
+
     def solve(self, A: Matrix, x, b, pc: "Solver | None" = None):
         """call solver%solve(A, x, b [, pc]); x is the initial guess, returns the solution."""
         x, b = as_f64(x).copy(), as_f64(b)

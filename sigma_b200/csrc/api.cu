@@ -708,6 +708,13 @@ int sigb_solver_set_persistent(sigb_solver_t s, int mode)
     return SIGB_OK;
 }
 
+int sigb_solver_set_strict_order(sigb_solver_t s, int on)
+{
+    SIGB_REQUIRE(s, SIGB_ERR_ARG, "sigb_solver_set_strict_order: null solver");
+    s->strict_order = on ? 1 : 0;
+    return SIGB_OK;
+}
+
 int sigb_solver_setup(sigb_solver_t s, sigb_matrix_t A)
 {
     SIGB_REQUIRE(s && A, SIGB_ERR_ARG, "sigb_solver_setup: bad argument");
@@ -772,6 +779,8 @@ int sigb_solver_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x_dev, const
         SIGB_REQUIRE(pc->initialized && pc->nn == s->nn, SIGB_ERR_STATE,
                      "sigb_solver_solve: pc%%setup(A) has not been called");
     }
+    SIGB_REQUIRE(!s->strict_order || (!A->dist && !(pc && pc->kind == S_LDU)), SIGB_ERR_UNSUPPORTED,
+                 "sigb_solver_solve: strict-order dot products are a one-GPU parity aid (cg, bicgstab, jacobi pc)");
     switch (s->kind) {
     case S_CG: return cg_solve_dev(s, A, x_dev, b_dev, pc);
     case S_BICGSTAB: return bicgstab_solve_dev(s, A, x_dev, b_dev, pc);

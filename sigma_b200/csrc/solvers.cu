@@ -597,6 +597,43 @@ __global__ void grab_first_row_kernel(const double *V, int64_t nr, int32_t n, do
     for (int j = threadIdx.x; j < n; j += blockDim.x) first_row[j] = V[(size_t)j * nr];
 }
 
+// ---------------------------------------------------------------------------
+// Strict-order dot products (sigb_solver_set_strict_order): a parity aid, not a fast path.
+// Everything in the solvers except the dot products is element-wise and reproduces the reference
+// statement for statement; the dot products differ from the serial loops only by the ORDER of the
+// additions, which on an ill-conditioned nonsymmetric operator is enough to move the BiCGSTAB
+// iteration count by several per cent.  With this switch every dot product the
+// recurrence uses is recomputed after its producing kernel as sum = sum + a(i) * b(i), i = 1..n, by
+// ONE thread (rounded product, then rounded add -- `sum(a * b)` of the reference, no FMA), so that the
+// whole solve -- iterates, scalars, stopping iteration -- must equal the serial restatement BIT FOR
+// BIT.  One GPU, kernel-per-phase path; used by the parity tests on parity-sized instances.
+// ---------------------------------------------------------------------------
+__global__ void seq_dot_kernel(const double *__restrict__ a, const double *__restrict__ b, int64_t n, double *out,
+                               const int *skip)
+{
+    if (skip != nullptr && *skip != 0) return;
+    double s = 0.0;
+    int64_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        double pa[8], pb[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) { pa[j] = a[i + j]; pb[j] = b[i + j]; }
+#pragma unroll
+        for (int j = 0; j < 8; j++) s = add(s, mul(pa[j], pb[j]));
+    }
+    for (; i < n; i++) s = add(s, mul(a[i], b[i]));
+    *out = s;
+}
+
+static int strict_dot(sigb_solver_t s, const double *a, const double *b, double *out, const int *skip)
+{
+    if (!s->strict_order) return SIGB_OK;
+    seq_dot_kernel<<<1, 1, 0, ctx().stream>>>(a, b, s->nn, out, skip);
+    count_launch();
+    SIGB_CUDA(cudaGetLastError());
+    return SIGB_OK;
+}
+
 // ===========================================================================
 // host drivers
 // ===========================================================================
@@ -807,7 +844,7 @@ static int cg_solve_body(sigb_solver_t s, sigb_matrix_t A, double *x, const doub
         DotSpec halo;
         bool eligible = true;
         SIGB_CHECK(dist_persist_info(A, &pcomm, &halo, &eligible));
-        eligible = eligible && persistent_enabled(n, pcomm.nranks, s->persistent);
+        eligible = eligible && persistent_enabled(n, pcomm.nranks, s->persistent) && !s->strict_order;
         if (eligible && !A->op) {   // operator expressions run kernel-per-phase
             sigb_graph_t g = A->g;
             if (g->kind == G_CSR) {
@@ -839,6 +876,7 @@ static int cg_solve_body(sigb_solver_t s, sigb_matrix_t A, double *x, const doub
     CgInitOp init{b, q, idiag, r, p, z, st};
     SIGB_CHECK(launch_ew(init, n));
     SIGB_CHECK(dist_allreduce(A, &st->rr[0], 1));
+    SIGB_CHECK(strict_dot(s, r, idiag ? z : r, &st->rr[0], nullptr));
     latch0_kernel<<<1, 1, 0, ctx().stream>>>(st);
     count_launch();
 
@@ -856,10 +894,12 @@ static int cg_solve_body(sigb_solver_t s, sigb_matrix_t A, double *x, const doub
             if (fused) d.red = &rf;
             SIGB_CHECK(solver_matvec(A, p, q, d, /*x_has_halo=*/true));   // q = A p ; dpr = p.q
             if (!fused) SIGB_CHECK(dist_allreduce(A, &st->pq, 1, &st->done[par]));
+            SIGB_CHECK(strict_dot(s, p, q, &st->pq, &st->done[par]));
             CgUpdateOp up{q, idiag, r, z, st, par, 0.0};
             if (fused) SIGB_CHECK(launch_ew_fused(up, n, rf));
             else SIGB_CHECK(launch_ew(up, n));
             if (!fused) SIGB_CHECK(dist_allreduce(A, &st->rr[par ^ 1], 1, &st->done[par]));
+            SIGB_CHECK(strict_dot(s, r, idiag ? z : r, &st->rr[par ^ 1], &st->done[par]));
             CgDirectionOp dir{idiag ? z : r, p, x, st, par, 0.0, 0.0};
             SIGB_CHECK(launch_ew(dir, n));
             par ^= 1;
@@ -871,7 +911,7 @@ static int cg_solve_body(sigb_solver_t s, sigb_matrix_t A, double *x, const doub
 }
 
 // ---------------------------------------------------------------------------
-// EXPERIMENTAL, opt-in (SIGB_BICGSTAB_LDU=1; not yet run on a GPU): bicgstab_solve_pc
+// bicgstab_solve_pc
 // (bicgstab_solvers.f90:182-237) with pc = ldu().  The preconditioner is applied by its own
 // kernels (ldu.cu), so the three products of an iteration are plain SpMVs into z followed by
 // call pc%solve(A, ., z), and the dot products that the Jacobi form fuses into the SpMV run
@@ -1004,6 +1044,8 @@ int bicgstab_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x, const double
     BicgInitOp init{b, q, idiag, r, r0, v, p, z, st};
     SIGB_CHECK(launch_ew(init, n));
     SIGB_CHECK(dist_allreduce(A, &st->rr[0], 3));  // rr[0], rr[1], rho[0] are contiguous
+    SIGB_CHECK(strict_dot(s, r, r, &st->rr[0], nullptr));
+    SIGB_CHECK(strict_dot(s, r0, r, &st->rho[0], nullptr));
     bicg_latch0_kernel<<<1, 1, 0, ctx().stream>>>(st);
     count_launch();
     {
@@ -1014,7 +1056,7 @@ int bicgstab_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x, const double
     const int nb = batch_size(n);
     int par = 0;
     RedFuse rf;
-    const bool fused = dist_red_fuse(A, &rf);   // EXPERIMENTAL: the three all-reduces inside their producers
+    const bool fused = dist_red_fuse(A, &rf);   // peer-memory transport: the three all-reduces inside their producers
     for (;;) {
         for (int it = 0; it < nb; it++) {
             DotSpec d1;                      // v = [M] A p ; r0.v
@@ -1026,6 +1068,7 @@ int bicgstab_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x, const double
             if (fused) d1.red = &rf;
             SIGB_CHECK(solver_matvec(A, p, v, d1, true));
             if (!fused) SIGB_CHECK(dist_allreduce(A, &st->pq, 1, &st->done[par]));
+            SIGB_CHECK(strict_dot(s, r0, v, &st->pq, &st->done[par]));
             BicgSOp sop{r, v, sv, st, par, 0.0};
             SIGB_CHECK(launch_ew(sop, n));
             DotSpec d2;                      // t = [M] A s ; s.t, t.t
@@ -1038,10 +1081,14 @@ int bicgstab_solve_dev(sigb_solver_t s, sigb_matrix_t A, double *x, const double
             if (fused) d2.red = &rf;
             SIGB_CHECK(solver_matvec(A, sv, t, d2, true));
             if (!fused) SIGB_CHECK(dist_allreduce(A, &st->st, 2, &st->done[par]));
+            SIGB_CHECK(strict_dot(s, sv, t, &st->st, &st->done[par]));
+            SIGB_CHECK(strict_dot(s, t, t, &st->tt, &st->done[par]));
             BicgUpdateOp up{p, sv, t, r0, x, r, st, par, pc ? 0 : 1, 0.0, 0.0};
             if (fused) SIGB_CHECK(launch_ew_fused(up, n, rf));
             else SIGB_CHECK(launch_ew(up, n));
             if (!fused) SIGB_CHECK(dist_allreduce2(A, &st->rr[par ^ 1], &st->rho[par ^ 1], &st->done[par]));
+            SIGB_CHECK(strict_dot(s, r, r, &st->rr[par ^ 1], &st->done[par]));
+            SIGB_CHECK(strict_dot(s, r0, r, &st->rho[par ^ 1], &st->done[par]));
             BicgDirectionOp dir{r, v, p, st, par ^ 1, 0, 0.0, 0.0};
             SIGB_CHECK(launch_ew(dir, n));
             par ^= 1;

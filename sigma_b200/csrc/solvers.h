@@ -17,6 +17,7 @@ struct sigb_solver_s {
     bool initialized = false;  // work vectors allocated (cg_setup :78-81)
     int64_t cap = -1;          // safety cap per solve (not in the reference)
     int persistent = -1;       // CG loop form: -1 library's choice, 0 kernel per phase, 1 one persistent kernel
+    int strict_order = 0;      // parity aid: dot products summed strictly left to right, like the serial reference
     int32_t nn = 0;            // solver%nn: owned rows
     int64_t nvec = 0;          // allocated length of each work vector (nn + halo room)
     int64_t iterations = 0;    // solver%iterations (accumulates until the next setup)

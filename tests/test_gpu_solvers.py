@@ -322,3 +322,79 @@ def test_generalized_lanczos_like_reference_test(sb, orc):
     # Ritz values of a positive semi-definite pencil: non-negative, smallest one near
     # the zero eigenvalue of the periodic stiffness matrix (48 steps, no re-orthogonalisation)
     assert lam[0] > -1e-8 and lam[0] < 0.05
+
+
+# ---------------------------------------------------------------------------
+# strict-order dot products: the whole solve bit for bit
+# ---------------------------------------------------------------------------
+def _strict(sb, kind, tol, A, cap):
+    s = sb.cg(tol) if kind == "cg" else sb.bicgstab(tol)
+    s.set_strict_order(True)
+    s.set_max_iterations(cap)
+    s.setup(A)
+    return s
+
+
+def test_strict_order_kat_programs_equal_the_serial_loops(sb, orc):
+    """The reference's two deterministic test programs with the dot products summed left to right
+    (sigb_solver_set_strict_order): 64 CG iterations and 1133 BiCGSTAB iterations -- the counts of the
+    serial restatement, exactly -- and the same solution vector, bit for bit."""
+    nn = 127
+    dx = 1.0 / (nn + 1)
+    enode, edeg, eval_ = G.tridiag_ell(nn)
+    f = np.full(nn, 2.0 * dx**2)
+    O = orc.Matrix(orc.ELL, nn, nn, enode, eval_, degrees=edeg)
+    xo, ito, _, _ = orc.cg_solve(O, np.zeros(nn), f, 1e-16, 20 * nn)
+    A = sb.ellpack_matrix(nn, nn, enode, edeg, eval_)
+    s = _strict(sb, "cg", 1e-16, A, 20 * nn)
+    x = s.solve(A, np.zeros(nn), f)
+    assert s.info()[0] == ito == GOLD["diffusion_1d"]["iterations"] and not s.info()[2]
+    assert np.array_equal(x, xo)
+
+    nn, c = 1024, 0.5
+    dx = 1.0 / (nn + 1)
+    enode, edeg, eval_ = G.tridiag_ell(nn, 2.0, -1.0 + c * dx / 2, -1.0 - c * dx / 2)
+    f = np.full(nn, 2.0 * dx**2)
+    O = orc.Matrix(orc.ELL, nn, nn, enode, eval_, degrees=edeg)
+    xo, ito, _, _ = orc.bicgstab_solve(O, np.zeros(nn), f, 1e-12, 20 * nn)
+    A = sb.ellpack_matrix(nn, nn, enode, edeg, eval_)
+    s = _strict(sb, "bicgstab", 1e-12, A, 20 * nn)
+    x = s.solve(A, np.zeros(nn), f)
+    assert s.info()[0] == ito == GOLD["advection_diffusion_1d"]["iterations"] and not s.info()[2]
+    assert np.array_equal(x, xo)
+
+
+@pytest.mark.parametrize("case", ["cg_poisson", "pcg_er", "bicgstab_er", "bicgstab_jacobi_er"])
+def test_strict_order_solves_are_bit_identical(sb, orc, case):
+    """CG, Jacobi-PCG, BiCGSTAB and Jacobi-BiCGSTAB on the parity-sized operators: with strict-order
+    dot products the iteration count EQUALS the oracle's and the solution is the same array -- which
+    shows that every other statement of the recurrences (SpMV rows, element-wise updates, scalar
+    expressions, stopping test) is the reference's, rounding included.  The +-2 % / +-5 % bars of the
+    tests above are therefore entirely the summation order of the default (parallel) dot products."""
+    if case == "cg_poisson":
+        N = 96
+        n = N * N
+        ptr, node, val = G.poisson2d_csr(N)
+        b, _ = G.poisson2d_rhs(N)
+        tol, kind, pc_on = 1e-10 * np.linalg.norm(b), "cg", False
+    else:
+        n = 3000
+        skew = case.startswith("bicgstab")
+        ptr, node, val = G.erdos_renyi_csr(n, seed=12 if skew else 8, weights="random", skew=skew)
+        b = orc.matvec(orc.Matrix(orc.CSR, n, n, node, val, ptr=ptr), np.random.default_rng(9).random(n))
+        tol, kind, pc_on = 1e-13, ("bicgstab" if skew else "cg"), case in ("pcg_er", "bicgstab_jacobi_er")
+    O = orc.Matrix(orc.CSR, n, n, node, val, ptr=ptr)
+    idiag = orc.jacobi_setup(O) if pc_on else None
+    fn = orc.cg_solve if kind == "cg" else orc.bicgstab_solve
+    xo, ito, _, cappedo = fn(O, np.zeros(n), b, tol, 10 * n, idiag=idiag)
+    A = sb.csr_matrix(n, n, ptr, node, val)
+    s = _strict(sb, kind, tol, A, 10 * n)
+    pc = None
+    if pc_on:
+        pc = sb.jacobi()
+        pc.setup(A)
+    x = s.solve(A, np.zeros(n), b, pc)
+    it, res2, capped = s.info()
+    assert not capped and not cappedo
+    assert it == ito, (case, it, ito)
+    assert np.array_equal(x, xo), (case, float(np.abs(x - xo).max()))
