@@ -113,7 +113,18 @@ int main(int argc, char **argv)
     s3->setup(A);
     s3->set_max_iterations(20 * N);
     s3->solve(A, x.data(), b.data());
-    if (s3->capped() || rel_diff(x, xs) > 1e-6) { std::printf(" multi-GPU bicgstab failed: %g\n", rel_diff(x, xs)); return 1; }
+    // bicgstab stops on |r| <= tol like cg, but where inside the bar its irregular residual lands depends on
+    // the summation order of the dot products (8 GPUs: 1.2e-6 from the manufactured solution, one GPU: 6e-7;
+    // the bound is cond(A) * 1e-10 ~ 3e-5 at this size), so the gate is the TRUE residual of the returned x,
+    // formed by the one-GPU operator, next to a bar on the error that the condition number allows
+    std::vector<dp> r3(n);
+    A1.matvec(x.data(), r3.data());
+    dp rn = 0.0;
+    for (int i = 0; i < n; i++) rn += (b[i] - r3[i]) * (b[i] - r3[i]);
+    if (s3->capped() || std::sqrt(rn) > 10.0 * tol || rel_diff(x, xs) > 1e-5) {
+        std::printf(" multi-GPU bicgstab failed: error %g, true residual %g (tolerance %g)\n", rel_diff(x, xs), std::sqrt(rn), tol);
+        return 1;
+    }
     if (verbose) std::printf(" o bicgstab on %d GPU(s): %ld iterations\n", ndev, (long)s3->iterations);
     return 0;
 }
