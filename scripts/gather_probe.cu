@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <cstdlib>
+#include <string>
 #include <vector>
 #include <cuda_runtime.h>
 
@@ -61,12 +62,15 @@ __global__ void __launch_bounds__(256, MINB) gather_kernel(const int32_t *__rest
 }
 
 template <int FLAVOUR, int U, bool HALF, int MINB = 4>
-static void run(const char *name, const int32_t *node, const double *x, long nnz, long n, int ctas_per_sm, double *out)
+static void run(const char *name, const int32_t *node, const double *x, long nnz, long n, int ctas_per_sm, double *out,
+                int smem_kb = -1)
 {
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
-    // residency is capped with dynamic shared memory: 227 KB / ctas_per_sm each
-    const int smem = ctas_per_sm >= 8 ? 0 : (220 * 1024) / ctas_per_sm;
+    // smem_kb < 0: residency is capped with dynamic shared memory, 220 KB / ctas_per_sm each (which also
+    // shrinks the L1: the unified array is 256 KB).  smem_kb >= 0: that much per CTA, residency set by the
+    // grid alone (one wave of sms * ctas_per_sm CTAs) -- the sweep that separates L1 size from warp count.
+    const int smem = smem_kb >= 0 ? smem_kb * 1024 : (ctas_per_sm >= 8 ? 0 : (220 * 1024) / ctas_per_sm);
     CK(cudaFuncSetAttribute(gather_kernel<FLAVOUR, U, HALF, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int grid = sms * ctas_per_sm;
     cudaEvent_t e0, e1;
@@ -82,15 +86,16 @@ static void run(const char *name, const int32_t *node, const double *x, long nnz
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     const double us = ms * 1000.0 / reps;
-    std::printf("{\"probe\": \"gather\", \"load\": \"%s\", \"in_flight_per_thread\": %d, \"half_populated\": %s, \"ctas_per_sm\": %d, "
+    std::printf("{\"probe\": \"gather\", \"load\": \"%s\", \"in_flight_per_thread\": %d, \"half_populated\": %s, \"ctas_per_sm\": %d, \"smem_kb_per_cta\": %.1f, "
                 "\"x_mb\": %.0f, \"gathers\": %ld, \"us\": %.1f, \"g_gathers_per_s\": %.1f, \"cycles_per_gather_per_sm_at_1965mhz\": %.2f}\n",
-                name, U, HALF ? "true" : "false", ctas_per_sm, n * 8.0 / 1e6, nnz, us, nnz / us / 1e3,
+                name, U, HALF ? "true" : "false", ctas_per_sm, smem / 1024.0, n * 8.0 / 1e6, nnz, us, nnz / us / 1e3,
                 us * 1965.0 * sms / nnz);
     std::fflush(stdout);
 }
 
-int main()
+int main(int argc, char **argv)
 {
+    const bool sweep = argc > 1 && std::string(argv[1]) == "sweep";   // L1-size sweep instead of the flavour table
     const long nnz = 1L << 26;  // 67 M gathers
     const long sizes[2] = {2000000L, 20000000L};
     double *out;
@@ -109,6 +114,18 @@ int main()
         CK(cudaMalloc(&x, n * 8));
         CK(cudaMemcpy(node, h.data(), nnz * 4, cudaMemcpyHostToDevice));
         CK(cudaMemset(x, 0, n * 8));
+        if (sweep) {
+            const int kb8[] = {0, 4, 8, 12, 16, 20, 24, 27};
+            for (int kb : kb8) run<1, 8, false, 8>("ldg.nc", node, x, nnz, n, 8, out, kb);
+            const int kb4[] = {0, 8, 16, 24, 32, 40, 48, 54};
+            for (int kb : kb4) run<1, 8, false, 8>("ldg.nc", node, x, nnz, n, 4, out, kb);
+            const int kb6[] = {0, 8, 16, 21, 26, 32, 36};
+            for (int kb : kb6) run<1, 8, false, 8>("ldg.nc", node, x, nnz, n, 6, out, kb);
+            for (int kb : kb8) run<2, 8, false, 8>("ldcg", node, x, nnz, n, 8, out, kb);
+            CK(cudaFree(node));
+            CK(cudaFree(x));
+            continue;
+        }
         run<0, 8, false>("plain", node, x, nnz, n, 4, out);
         run<1, 8, false>("ldg.nc", node, x, nnz, n, 4, out);
         run<2, 8, false>("ldcg", node, x, nnz, n, 4, out);

@@ -84,6 +84,7 @@ for r in rows:
     ok = ok and (z == yh[r])
 by = 12 * nnz + 20 * n + 4
 print(json.dumps({"kind": args.kind, "n": n, "nnz": nnz, "nnz_per_row": nnz / n, "x_mb": 8 * n / 1e6, "dot": args.dot,
-                  "variant": os.environ.get("SIGB_LIB_VARIANT", ""), "rowdirect": os.environ.get("SIGB_SPMV_ROWDIRECT", ""),
+                  "variant": os.environ.get("SIGB_LIB_VARIANT", ""), "env": {k: v for k, v in os.environ.items() if k.startswith("SIGB_")},
+                  "g_gathers_per_s": nnz / t / 1e9,
                   "us": t * 1e6, "algorithmic_bytes": by, "gbs": by / t / 1e9, "frac_of_measured_hbm": by / t / 1e9 / HBM,
                   "rows_bit_exact_sample": bool(ok), "gen_s": gen_s}), flush=True)

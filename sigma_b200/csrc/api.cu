@@ -165,7 +165,7 @@ int ensure_graph_transposed(sigb_graph_t g)
     g->perm_t = perm;
     // the tile table is built on the device from the device-resident ptr (tiles_device.cu): no
     // read-back, no host loop
-    SIGB_CHECK(build_tiles_device(ptr_t, ntargets, t, nullptr, nullptr));
+    SIGB_CHECK(build_tiles_device(ptr_t, ntargets, ne, t, nullptr, nullptr));
     g->has_transposed = true;
     return SIGB_OK;
 }
@@ -395,7 +395,9 @@ int sigb_cs_graph_create(int32_t n, int32_t m, const int32_t *ptr1, const int32_
         SIGB_CUDA(cudaMemcpyAsync(v.node, node1, sizeof(int32_t) * (size_t)ne, cudaMemcpyHostToDevice, st));
     SIGB_CHECK(fill_i32(v.node + ne, kPad, 1));
     std::vector<TileDesc> tiles;
-    build_tiles_host(ptr1, n, tiles);
+    TileShape shape;
+    build_tiles_host(ptr1, n, tiles, &shape);
+    v.tile_nnz = shape.nnz;
     SIGB_CHECK(upload_tiles(v, tiles));
     if (g->kind == G_CSC) SIGB_CHECK(ensure_graph_transposed(g));
     guard.g = nullptr;

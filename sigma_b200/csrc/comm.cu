@@ -588,7 +588,8 @@ int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global, const int32_t *part
     const int push_ctas = (P > 1 && comm->p2p && total_send > 0) ? std::min(32, (total_send + 8 * kThreads - 1) / (8 * kThreads)) : 0;
     // interior / boundary tile lists; the tiling is balanced over the compute CTAs of the persistent CG kernel
     std::vector<TileDesc> tiles, ti, tb;
-    build_tiles_balanced(ptr.data(), nloc, persistent_grid_ctas() - push_ctas, tiles);
+    TileShape shape;
+    build_tiles_balanced(ptr.data(), nloc, persistent_grid_ctas() - push_ctas, tiles, &shape);
     for (const TileDesc &t : tiles) {
         bool boundary = false;
         for (int32_t k = t.ks; k < t.ke && !boundary; k++) boundary = local[k] > nloc;
@@ -603,6 +604,7 @@ int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global, const int32_t *part
     cudaFree(V.tiles);                           // the greedy table of sigb_cs_graph_create
     V.tiles = nullptr;
     SIGB_CHECK(upload_tiles(V, ordered));
+    V.tile_nnz = shape.nnz;
     V.n_interior = (int32_t)ti.size();
     V.n_boundary = (int32_t)tb.size();
     V.tiles_interior = V.tiles;                  // views into the same table

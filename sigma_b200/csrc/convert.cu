@@ -212,7 +212,7 @@ int sigb_matrix_copy(sigb_matrix_t A, int format, int trans, sigb_matrix_t *B_ou
     // no read-back, no host loop
     int32_t max_d = 0, min_d = INT32_MAX;
     CsrView dev_view;
-    rc = build_tiles_device(T.ptr, T.nlines, dev_view, &max_d, &min_d);
+    rc = build_tiles_device(T.ptr, T.nlines, T.ne, dev_view, &max_d, &min_d);
     if (rc != SIGB_OK) { S.release(); T.release(); return rc; }
     if (T.nlines == 0) min_d = INT32_MAX;
     S.release();
@@ -266,6 +266,7 @@ int sigb_matrix_copy(sigb_matrix_t A, int format, int trans, sigb_matrix_t *B_ou
         v.node = T.node;
         B->val = T.val;
         v.tiles = dev_view.tiles;
+        v.tile_nnz = dev_view.tile_nnz;
         v.ntiles = dev_view.ntiles;
         v.tiles_nonempty = dev_view.tiles_nonempty;
         v.n_nonempty = dev_view.n_nonempty;

@@ -195,7 +195,7 @@ int sigb_cs_graph_build(int32_t n, int32_t m, int64_t count, const int32_t *src_
     v.ptr = L.ptr;      // ownership moves to the graph
     v.node = L.node;
     int32_t max_d = 0;
-    int rc = build_tiles_device(v.ptr, n, v, &max_d, nullptr);
+    int rc = build_tiles_device(v.ptr, n, L.ne, v, &max_d, nullptr);
     if (rc == SIGB_OK) {
         g->max_d = n > 0 ? max_d : 0;
         if (g->kind == G_CSC) rc = ensure_graph_transposed(g);
@@ -222,7 +222,7 @@ int sigb_ell_graph_build(int32_t n, int32_t m, int64_t count, const int32_t *src
     } free_lines{&L};
     CsrView probe;     // only the extreme line lengths are needed
     int32_t max_d = 0, min_d = 0;
-    SIGB_CHECK(build_tiles_device(L.ptr, n, probe, &max_d, &min_d));
+    SIGB_CHECK(build_tiles_device(L.ptr, n, L.ne, probe, &max_d, &min_d));
     cudaFree(probe.tiles);
     SIGB_REQUIRE(n == 0 || min_d >= 1, SIGB_ERR_ISOLATED,
                  "sigb_ell_graph_build: a row has no edge; the reference would read x(0) in its matvec (README.md:71-73)");

@@ -121,6 +121,8 @@ struct CsrView {
     // accumulating matvec has to visit when rows without entries leave y as it is
     TileDesc *tiles_nonempty = nullptr;
     int32_t n_nonempty = 0;
+    // entries per tile the table was built for (0 = kTileNnz): selects the kernel's tile shape
+    int32_t tile_nnz = 0;
 };
 
 #ifndef SIGB_TILE_NNZ
@@ -135,6 +137,26 @@ constexpr int kTileNnz = SIGB_TILE_NNZ;   // entries staged per tile
 // entries keeps the widened range within kTileNnz.
 constexpr int kTileCap = kTileNnz - 3;
 constexpr int kTileRows = SIGB_TILE_ROWS;   // rows per tile (their ptr slice is staged too)
+// Second tile shape, for operators whose SpMV is bound by uncoalesced x gathers (long rows with scattered
+// columns): small stages leave most of the SM's unified shared-memory / L1 array to the L1, and the
+// gather rate follows the L1 share (spmv_device.cuh, TileCfg).
+#ifndef SIGB_TILE_NNZ_SMALL
+#define SIGB_TILE_NNZ_SMALL 1024
+#endif
+constexpr int kTileNnzSmall = SIGB_TILE_NNZ_SMALL;
+// caps of a row tiling: at most `cap` stored entries and `rows` rows per tile
+struct TileShape {
+    int32_t nnz;    // staged entries per tile the kernel is compiled for (kTileNnz or kTileNnzSmall)
+    int32_t cap;    // nnz - 3 (the entry range is widened down to a 4-entry boundary)
+    int32_t rows;
+};
+inline TileShape tile_shape_of(int32_t tile_nnz)
+{
+    const int32_t tn = tile_nnz > 0 ? tile_nnz : kTileNnz;
+    return TileShape{tn, tn - 3, tn == kTileNnz ? kTileRows : (tn / 4 < 128 ? 128 : tn / 4)};
+}
+// the shape for a pattern with nnz entries in nrows rows (kernels_spmv.cu; SIGB_TILE_CLASS overrides)
+TileShape tile_shape_for(int64_t nnz, int64_t nrows);
 constexpr int kPad = 8;          // slack entries behind ptr / node / val arrays
 
 enum GraphKind { G_CSR = 0, G_CSC = 1, G_ELL = 2 };
@@ -254,14 +276,15 @@ int launch_ell_spmv(int32_t n, int32_t n_pad, int32_t max_d,
                     const int32_t *node_sm, const double *val_sm,
                     const double *x, double *y, SpmvMode mode,
                     const DotSpec &dot);
-int build_tiles_host(const int32_t *ptr1, int32_t nrows, std::vector<TileDesc> &tiles);
+int build_tiles_host(const int32_t *ptr1, int32_t nrows, std::vector<TileDesc> &tiles, TileShape *shape_out = nullptr);
 // exactly m * groups tiles of nearly equal entry counts when the caps allow it, else the greedy tiling
-int build_tiles_balanced(const int32_t *ptr1, int32_t nrows, int groups, std::vector<TileDesc> &tiles);
+int build_tiles_balanced(const int32_t *ptr1, int32_t nrows, int groups, std::vector<TileDesc> &tiles,
+                         TileShape *shape_out = nullptr);
 // compute CTAs of the persistent CG kernel on this device (cg_persistent.cu), before communication CTAs are taken off
 int persistent_grid_ctas();
 // tiles_device.cu: the same tiling built on the device from a device-resident ptr (no read-back);
 // also returns the extreme line lengths
-int build_tiles_device(const int32_t *ptr1_dev, int32_t nrows, CsrView &v, int32_t *max_d, int32_t *min_d);
+int build_tiles_device(const int32_t *ptr1_dev, int32_t nrows, int64_t nnz, CsrView &v, int32_t *max_d, int32_t *min_d);
 
 // ---------------------------------------------------------------------------
 // transpose.cu

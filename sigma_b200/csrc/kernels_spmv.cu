@@ -49,6 +49,10 @@
 
 #include "spmv_device.cuh"
 
+#ifndef SIGB_SMALL_TILE_CTAS
+#define SIGB_SMALL_TILE_CTAS 4
+#endif
+
 namespace sigb {
 
 namespace {
@@ -56,7 +60,7 @@ namespace {
 // ---------------------------------------------------------------------------
 // stand-alone SpMV kernel
 // ---------------------------------------------------------------------------
-template <int MODE, int NDOT, bool HALO>
+template <int MODE, int NDOT, bool HALO, class CFG>
 __global__ void __launch_bounds__(kThreads)
 csr_tma_kernel(const __grid_constant__ CsrKernelArgs a)
 {
@@ -84,7 +88,7 @@ csr_tma_kernel(const __grid_constant__ CsrKernelArgs a)
 
     TilePipe pipe;
     const SpmvVecs v{a.x1, a.y, a.u};
-    spmv_phase<MODE, NDOT, HALO, true>(a, v, smem, mbar, pipe, acc, hseq, false);
+    spmv_phase<MODE, NDOT, HALO, true, CFG>(a, v, smem, mbar, pipe, acc, hseq, false);
     finish_dots<NDOT>(a, acc);
 
     // peer-memory transport: the last CTA tells every source rank that this
@@ -196,20 +200,50 @@ ell_kernel(const EllKernelArgs a)
     }
 }
 
-template <int MODE, int NDOT, bool HALO>
-int launch_csr_t(const CsrKernelArgs &a, cudaStream_t st)
+// Small-shape launches name the shared-memory carve-out they want (the driver's default sizes it for
+// the largest residency the register count allows, which leaves the L1 too small for the gathers):
+// kSmallCtasPerSm CTAs of two stages each, rounded up by the driver to the next configuration.
+constexpr int kSmallCtasPerSm = SIGB_SMALL_TILE_CTAS;
+
+template <int MODE, int NDOT, bool HALO, class CFG>
+int launch_csr_cfg(const CsrKernelArgs &a, cudaStream_t st)
 {
     int grid = 0;
-    const size_t smem = 2 * (size_t)kStageBytes;
-    SIGB_CHECK((occupancy_grid<csr_tma_kernel<MODE, NDOT, HALO>>(smem, &grid)));
+    const size_t smem = 2 * (size_t)CFG::kStageBytes;
+    constexpr bool small = CFG::kNnz != kTileNnz;
+    if (small) {
+        static thread_local int cached = 0;   // per host thread = per device
+        if (cached == 0) {
+            auto kernel = csr_tma_kernel<MODE, NDOT, HALO, CFG>;
+            const int ctas = env_int("SIGB_SMALL_TILE_CTAS", kSmallCtasPerSm);
+            const int carve_kb = env_int("SIGB_SMALL_TILE_CARVEOUT_KB", (int)((ctas * (smem + 1024) + 1023) / 1024));
+            SIGB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SIGB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                           std::min(100, (carve_kb * 100 + 227) / 228)));
+            int per_sm = 0;
+            SIGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
+            per_sm = std::max(1, std::min(per_sm, ctas));
+            cached = std::min(per_sm * ctx().num_sms, (kMaxGrid / ctx().num_sms) * ctx().num_sms);
+        }
+        grid = cached;
+    } else {
+        SIGB_CHECK((occupancy_grid<csr_tma_kernel<MODE, NDOT, HALO, CFG>>(smem, &grid)));
+    }
     // one CTA per tile is enough; the communication CTAs of a row-sharded operator come on top
     const int comm = (HALO && a.sync.win != nullptr) ? a.sync.push_ctas : 0;
     if (a.ntiles + comm < grid) grid = a.ntiles + comm;
     if (grid < comm + 1) grid = comm + 1;
-    csr_tma_kernel<MODE, NDOT, HALO><<<grid, kThreads, smem, st>>>(a);
+    csr_tma_kernel<MODE, NDOT, HALO, CFG><<<grid, kThreads, smem, st>>>(a);
     count_launch();
     SIGB_CUDA(cudaGetLastError());
     return SIGB_OK;
+}
+
+template <int MODE, int NDOT, bool HALO>
+int launch_csr_t(const CsrKernelArgs &a, cudaStream_t st, int32_t tile_nnz)
+{
+    if (tile_nnz == kTileNnzSmall) return launch_csr_cfg<MODE, NDOT, HALO, TileCfgSmall>(a, st);
+    return launch_csr_cfg<MODE, NDOT, HALO, TileCfgLarge>(a, st);
 }
 
 template <int MODE, int NDOT, int W>
@@ -244,19 +278,35 @@ int launch_ell_w(const EllKernelArgs &a, cudaStream_t st)
 
 }  // namespace
 
-// Greedy row tiling: consecutive rows while the tile holds <= kTileCap entries
-// and <= kTileRows rows; a longer row gets a tile of its own.  ptr is monotone,
-// so the end of a tile is found by bisection inside the kTileRows window (the
+// Which tile shape a pattern gets.  Long rows mean many gathers per row, and a row of a banded /
+// stencil operator is short; the measured cross-over is not sharp (Poisson, 5 per row: large shape
+// 0.97 of HBM; Erdos-Renyi, 22 per row: gather-bound, small shape), so the rule is the mean row
+// length.  SIGB_TILE_CLASS = 0 / 1 forces the large / small shape (A/B runs).
+TileShape tile_shape_for(int64_t nnz, int64_t nrows)
+{
+    static const int forced = env_int("SIGB_TILE_CLASS", -1);
+    static const int min_mean = env_int("SIGB_SMALL_TILE_MIN_ROW", 12);
+    bool small = nrows > 0 && nnz >= (int64_t)min_mean * nrows;
+    if (forced == 0) small = false;
+    if (forced == 1) small = true;
+    return tile_shape_of(small ? kTileNnzSmall : kTileNnz);
+}
+
+// Greedy row tiling: consecutive rows while the tile holds <= cap entries
+// and <= rows rows; a longer row gets a tile of its own.  ptr is monotone,
+// so the end of a tile is found by bisection inside the row window (the
 // row-by-row walk cost 5 ms per 4 M rows on the host, more than the device side
 // of a matrix copy).
-int build_tiles_host(const int32_t *ptr1, int32_t nrows, std::vector<TileDesc> &tiles)
+int build_tiles_host(const int32_t *ptr1, int32_t nrows, std::vector<TileDesc> &tiles, TileShape *shape_out)
 {
+    const TileShape shape = tile_shape_for(nrows > 0 ? (int64_t)ptr1[nrows] - 1 : 0, nrows);
+    if (shape_out) *shape_out = shape;
     tiles.clear();
     tiles.reserve((size_t)nrows / 256 + 16);
     int32_t s = 0;
     while (s < nrows) {
-        const int64_t limit = (int64_t)ptr1[s] + kTileCap;          // ptr1[e] <= limit keeps the tile within the cap
-        const int32_t hi = (int32_t)std::min<int64_t>((int64_t)s + kTileRows, nrows);
+        const int64_t limit = (int64_t)ptr1[s] + shape.cap;          // ptr1[e] <= limit keeps the tile within the cap
+        const int32_t hi = (int32_t)std::min<int64_t>((int64_t)s + shape.rows, nrows);
         // largest e in [s + 1, hi] with ptr1[e] <= limit; s + 1 when even the first row is too long
         const int32_t *first = ptr1 + s + 1, *last = ptr1 + hi + 1;
         int32_t e = (int32_t)(std::upper_bound(first, last, limit,
@@ -279,12 +329,16 @@ int build_tiles_host(const int32_t *ptr1, int32_t nrows, std::vector<TileDesc> &
 // tiling a shard of 5130 tiles on 440 CTAs gives some of them 12 tiles and the others 11, and the
 // whole grid waits at the barrier behind the phase for the twelfth (8 % of the SpMV phase).  Tile
 // boundaries sit at the rows where the running entry count passes j * nnz / T.  Falls back to the
-// greedy tiling when the caps cannot be met that way (long or empty rows, tiny matrices).  Tiling
+// greedy tiling when the caps cannot be met that way (long or empty rows, tiny matrices), and for
+// the small tile shape (gather-bound operators run kernel per phase, on a grid of their own).  Tiling
 // never changes a result: rows are summed by one thread each, in stored order, whatever the tile.
-int build_tiles_balanced(const int32_t *ptr1, int32_t nrows, int groups, std::vector<TileDesc> &tiles)
+int build_tiles_balanced(const int32_t *ptr1, int32_t nrows, int groups, std::vector<TileDesc> &tiles,
+                         TileShape *shape_out)
 {
     const int64_t nnz = nrows > 0 ? (int64_t)ptr1[nrows] - 1 : 0;
-    if (groups <= 0 || nrows <= 0 || nnz <= 0) return build_tiles_host(ptr1, nrows, tiles);
+    const TileShape shape = tile_shape_for(nnz, nrows);
+    if (groups <= 0 || nrows <= 0 || nnz <= 0 || shape.nnz != kTileNnz) return build_tiles_host(ptr1, nrows, tiles, shape_out);
+    if (shape_out) *shape_out = shape;
     int64_t maxrow = 0;
     for (int32_t i = 0; i < nrows; i++) maxrow = std::max<int64_t>(maxrow, ptr1[i + 1] - ptr1[i]);
     const int64_t m0 = std::max<int64_t>(1, (nnz + (int64_t)kTileCap * groups - 1) / ((int64_t)kTileCap * groups));
@@ -317,7 +371,7 @@ int build_tiles_balanced(const int32_t *ptr1, int32_t nrows, int groups, std::ve
         }
         if (ok && s == nrows) return SIGB_OK;
     }
-    return build_tiles_host(ptr1, nrows, tiles);
+    return build_tiles_host(ptr1, nrows, tiles, shape_out);
 }
 
 // Argument block of one SpMV over all tiles of A (which = 0), or over its
@@ -395,9 +449,9 @@ int launch_csr_spmv(const CsrView &A, const double *val, const double *x, double
 
 #define SIGB_DISPATCH(M)                                                            \
     switch (dot.ndot) {                                                             \
-    case 0: return halo ? launch_csr_t<M, 0, true>(a, st) : launch_csr_t<M, 0, false>(a, st);  \
-    case 1: return halo ? launch_csr_t<M, 1, true>(a, st) : launch_csr_t<M, 1, false>(a, st);  \
-    default: return halo ? launch_csr_t<M, 2, true>(a, st) : launch_csr_t<M, 2, false>(a, st); \
+    case 0: return halo ? launch_csr_t<M, 0, true>(a, st, A.tile_nnz) : launch_csr_t<M, 0, false>(a, st, A.tile_nnz);  \
+    case 1: return halo ? launch_csr_t<M, 1, true>(a, st, A.tile_nnz) : launch_csr_t<M, 1, false>(a, st, A.tile_nnz);  \
+    default: return halo ? launch_csr_t<M, 2, true>(a, st, A.tile_nnz) : launch_csr_t<M, 2, false>(a, st, A.tile_nnz); \
     }
     switch (mode) {
     case MODE_SET: SIGB_DISPATCH(MODE_SET)

@@ -856,6 +856,9 @@ static int cg_solve_body(sigb_solver_t s, sigb_matrix_t A, double *x, const doub
                 val = A->val_t;
             }
         }
+        // gather-bound operators (small tile shape): kernel per phase, where the SpMV gets the L1 share
+        // it needs; the persistent kernel is compiled for the large stages
+        if (V != nullptr && V->tile_nnz == kTileNnzSmall && s->persistent < 0) V = nullptr;
         if (V != nullptr) {
             if (!s->bar) {
                 SIGB_CUDA(cudaMalloc((void **)&s->bar, 2 * sizeof(unsigned long long)));

@@ -108,17 +108,38 @@ __device__ __forceinline__ void fence_mbar_init()
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 
-// shared-memory stage: val | node | ptr slices of one tile
-constexpr int kStageVal = kTileNnz * 8;
-constexpr int kStageNode = kTileNnz * 4;
-constexpr int kStagePtr = (kTileRows + 8) * 4;
-constexpr int kStageBytes = (kStageVal + kStageNode + kStagePtr + 127) & ~127;
-constexpr int kRowSlots = kTileRows / kThreads;    // rows of a tile a thread may own
-constexpr int kEntrySlots = kTileNnz / kThreads;   // entries of a tile a thread gathers
+// shared-memory stage: val | node | ptr slices of one tile.  The kernels are compiled for two tile
+// shapes (TileCfg<TN>, TN = staged entries per tile; a quarter as many rows, at least 128):
+//   TN = 2048 (kTileNnz) -- short rows with locality (stencils, FEM): 4 CTAs x 52 KB per SM;
+//   TN = kTileNnzSmall   -- long rows with scattered columns (random graphs): the SM's unified 256 KB
+//     array is shared by shared memory and L1, and the RATE of uncoalesced gathers follows the L1 share
+//     (pure-gather probe, profiles/r2_gather_probe.jsonl: 270 G gathers/s with <= 100 KB carved out for
+//     shared memory, 247 at 132 KB, 197 at 164 KB, 101 at 228 KB -- whatever the number of warps), so a
+//     gather-bound operator wants small stages, not deep ones.
+// A table built for the smaller shape is valid for the larger kernel (the persistent CG kernel keeps
+// the large one); the reverse is not.
+template <int TN>
+struct TileCfg {
+    static constexpr int kNnz = TN;
+    static constexpr int kCap = TN - 3;
+    static constexpr int kRows = (TN / 4 < 128) ? 128 : TN / 4;
+    static constexpr int kStageVal = TN * 8;
+    static constexpr int kStageNode = TN * 4;
+    static constexpr int kStagePtr = (kRows + 8) * 4;
+    static constexpr int kStageBytes = (kStageVal + kStageNode + kStagePtr + 127) & ~127;
+    static constexpr int kRowSlots = (kRows + kThreads - 1) / kThreads;   // rows of a tile a thread may own
+    static constexpr int kEntrySlots = TN / kThreads;                     // entries of a tile a thread gathers
+    static_assert(TN % kThreads == 0 && TN >= kThreads, "tile entries: a multiple of the CTA size");
+};
+using TileCfgLarge = TileCfg<kTileNnz>;
+using TileCfgSmall = TileCfg<kTileNnzSmall>;
+static_assert(TileCfgLarge::kRows == kTileRows, "kTileRows is the row cap of the large shape");
+constexpr int kStageBytes = TileCfgLarge::kStageBytes;   // callers that size the large shape's stages
 
+template <class CFG>
 __device__ __forceinline__ bool tile_staged(const int4 &d)
 {
-    return (d.w - d.z) <= kTileCap;  // else: one long row, streamed directly
+    return (d.w - d.z) <= CFG::kCap;  // else: one long row, streamed directly
 }
 
 // the vectors of one SpMV pass (the persistent kernel runs the same matrix over different ones)
@@ -312,11 +333,13 @@ __device__ __forceinline__ void halo_push(const CsrKernelArgs &a, const double *
 // Same rounded products, added in the same order: bit-identical to the serial reference loop.
 // Measured on the 4096^2 Poisson matrix: 226.6 -> 213.8 us (0.97 of the measured copy bandwidth),
 // with the dot 229.3 -> 225.4 us (profiles/r2_visit_c_1gpu_summary.txt, r2_visit_d_1gpu_summary.txt).
-template <int MODE, int NDOT, bool HALO, bool XNC>
+template <int MODE, int NDOT, bool HALO, bool XNC, class CFG = TileCfgLarge>
 __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, const SpmvVecs &v, unsigned char *smem,
                                            uint64_t *mbar, TilePipe &pipe, double *acc, unsigned long long hseq,
                                            bool prime_next)
 {
+    constexpr int kStageBytes = CFG::kStageBytes, kStageVal = CFG::kStageVal, kStageNode = CFG::kStageNode;
+    constexpr int kRowSlots = CFG::kRowSlots, kEntrySlots = CFG::kEntrySlots;
     const int tid = threadIdx.x;
     if (HALO && is_comm_cta(a)) {
         halo_push<XNC>(a, v.x1, hseq);
@@ -349,7 +372,7 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, const SpmvVec
     if (t < a.ntiles) d_cur = load_desc(a.tiles + t);
     if (t + cstride < a.ntiles) d_next = load_desc(a.tiles + t + cstride);
     unsigned sidx = pipe.sidx;  // staged tiles consumed so far (identical in all threads)
-    if (!pipe.primed && tid == 0 && t < a.ntiles && tile_staged(d_cur)) issue((int)(sidx & 1u), d_cur);
+    if (!pipe.primed && tid == 0 && t < a.ntiles && tile_staged<CFG>(d_cur)) issue((int)(sidx & 1u), d_cur);
     pipe.primed = false;
 
     // the tile whose products are parked in shared memory and whose rows have not been summed yet
@@ -418,7 +441,7 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, const SpmvVec
         const bool have_next = tn < a.ntiles;
         int4 d_next2 = make_int4(0, 0, 0, 0);
         if (tnn < a.ntiles) d_next2 = load_desc(a.tiles + tnn);  // two tiles ahead, off the critical path
-        const bool staged = tile_staged(d_cur);
+        const bool staged = tile_staged<CFG>(d_cur);
 
         // tiles [first_halo_tile, ntiles) read halo columns: wait for the peers' pushes of this
         // SpMV when the first one comes up (CTA-uniform; at the END of a CTA's pass, the tiles
@@ -480,7 +503,7 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, const SpmvVec
             // ---- row sums of the previous tile while the gathers are in flight
             if (pending) row_sums();
             __syncthreads();                               // the other stage has been consumed by everybody
-            if (tid == 0 && have_next && tile_staged(d_next)) issue((int)((sidx + 1u) & 1u), d_next);
+            if (tid == 0 && have_next && tile_staged<CFG>(d_next)) issue((int)((sidx + 1u) & 1u), d_next);
             SIGB_TCLK(tk2);
             // ---- products, in place
 #pragma unroll
@@ -512,7 +535,7 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, const SpmvVec
                 __syncthreads();
             }
             flush_dot();
-            if (tid == 0 && have_next && tile_staged(d_next)) issue((int)(sidx & 1u), d_next);   // both stages are free
+            if (tid == 0 && have_next && tile_staged<CFG>(d_next)) issue((int)(sidx & 1u), d_next);   // both stages are free
             long_row<MODE, NDOT, HALO, XNC>(a, v, d_cur, h1, acc);
         }
         d_cur = d_next;
@@ -540,13 +563,14 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, const SpmvVec
     if (prime_next) {
         if (crank < a.ntiles) {
             const int4 d0 = load_desc(a.tiles + crank);
-            if (tid == 0 && tile_staged(d0)) issue((int)(sidx & 1u), d0);
+            if (tid == 0 && tile_staged<CFG>(d0)) issue((int)(sidx & 1u), d0);
         }
         pipe.primed = true;
     }
 }
 
 // The tile a persistent caller primed for a pass that will not run must land before the CTA exits.
+template <class CFG = TileCfgLarge>
 __device__ __forceinline__ void drain_primed(const CsrKernelArgs &a, uint64_t *mbar, const TilePipe &pipe, bool halo)
 {
     if (!pipe.primed) return;
@@ -554,7 +578,7 @@ __device__ __forceinline__ void drain_primed(const CsrKernelArgs &a, uint64_t *m
     const int crank = halo ? compute_rank(a) : (int)blockIdx.x;
     if (crank < a.ntiles) {
         const int4 d0 = load_desc(a.tiles + crank);
-        if (tile_staged(d0)) mbar_wait(&mbar[pipe.sidx & 1u], (pipe.sidx >> 1) & 1u);
+        if (tile_staged<CFG>(d0)) mbar_wait(&mbar[pipe.sidx & 1u], (pipe.sidx >> 1) & 1u);
     }
 }
 

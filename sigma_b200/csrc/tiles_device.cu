@@ -36,13 +36,14 @@ inline int grid_for(int64_t n)
 
 // next[s] for s < n, next[n] = n; also the extreme line lengths (minmax[0] = max, [1] = min)
 __global__ void __launch_bounds__(kThreads)
-tile_next_kernel(const int32_t *__restrict__ ptr1, int32_t n, int32_t *__restrict__ next, int32_t *minmax)
+tile_next_kernel(const int32_t *__restrict__ ptr1, int32_t n, int32_t cap, int32_t rows, int32_t *__restrict__ next,
+                 int32_t *minmax)
 {
     int32_t dmax = 0, dmin = INT32_MAX;
     for (int32_t s = blockIdx.x * kThreads + threadIdx.x; s <= n; s += gridDim.x * kThreads) {
         if (s == n) { next[n] = n; continue; }
-        const int64_t limit = (int64_t)ptr1[s] + kTileCap;
-        int32_t a = s + 1, b = (int32_t)min((int64_t)n, (int64_t)s + kTileRows);
+        const int64_t limit = (int64_t)ptr1[s] + cap;
+        int32_t a = s + 1, b = (int32_t)min((int64_t)n, (int64_t)s + rows);
         if ((int64_t)ptr1[a] <= limit) {
             while (a < b) {
                 const int32_t mid = (int32_t)(((int64_t)a + b + 1) >> 1);
@@ -113,9 +114,10 @@ tile_emit_kernel(const int32_t *__restrict__ mark, const int32_t *__restrict__ n
 }  // namespace
 
 // Tile table (+ its sub-table of tiles with entries) of a pattern whose ptr lives on the
-// device.  max_d / min_d: extreme line lengths (either may be null).
-int build_tiles_device(const int32_t *ptr1_dev, int32_t nrows, CsrView &v, int32_t *max_d, int32_t *min_d)
+// device; nnz (known to every caller) selects the tile shape as on the host.  max_d / min_d: extreme line lengths (either may be null).
+int build_tiles_device(const int32_t *ptr1_dev, int32_t nrows, int64_t nnz, CsrView &v, int32_t *max_d, int32_t *min_d)
 {
+    const TileShape shape = tile_shape_for(nnz, nrows);
     cudaStream_t st = ctx().stream;
     const size_t len = (size_t)nrows + 1;
     int32_t *next = nullptr, *jump_a = nullptr, *jump_b = nullptr, *mark = nullptr, *nonempty = nullptr;
@@ -144,7 +146,8 @@ int build_tiles_device(const int32_t *ptr1_dev, int32_t nrows, CsrView &v, int32
     int32_t ntiles = 0, n_nonempty = 0, h_minmax[2] = {0, 0};
     if (nrows > 0) {
         TD_TRY(fill_i32(mark, 1, 1));                                   // row 0 starts the first tile
-        tile_next_kernel<<<grid_for((int64_t)nrows + 1), kThreads, 0, st>>>(ptr1_dev, nrows, next, minmax);
+        tile_next_kernel<<<grid_for((int64_t)nrows + 1), kThreads, 0, st>>>(ptr1_dev, nrows, shape.cap, shape.rows, next,
+                                                                                      minmax);
         count_launch();
         TD_CUDA(cudaMemcpyAsync(jump_a, next, sizeof(int32_t) * len, cudaMemcpyDeviceToDevice, st));
         int rounds = 1;
@@ -180,6 +183,7 @@ int build_tiles_device(const int32_t *ptr1_dev, int32_t nrows, CsrView &v, int32
 #undef TD_TRY
     cleanup();
     v.tiles = tiles;
+    v.tile_nnz = shape.nnz;
     v.ntiles = ntiles;
     v.tiles_nonempty = tiles + ntiles;
     v.n_nonempty = n_nonempty;
@@ -205,7 +209,7 @@ int sigb_debug_row_tiles_dev(int32_t n, const int32_t *ptr1, int32_t *tiles, int
     cudaError_t e = cudaMemcpy(pd, ptr1, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(pd); return cuda_fail(e, "upload", __FILE__, __LINE__); }
     CsrView v;
-    const int rc = build_tiles_device(pd, n, v, nullptr, nullptr);
+    const int rc = build_tiles_device(pd, n, n > 0 ? (int64_t)ptr1[n] - 1 : 0, v, nullptr, nullptr);
     if (rc == SIGB_OK && v.ntiles > 0) {
         e = cudaMemcpy(tiles, v.tiles, sizeof(TileDesc) * (size_t)v.ntiles, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { cudaFree(pd); cudaFree(v.tiles); return cuda_fail(e, "read-back", __FILE__, __LINE__); }

@@ -126,6 +126,45 @@ def test_long_rows_within_tolerance(sb, orc):
     assert np.array_equal(y[short], yo[short])
 
 
+def test_small_tile_shape_rows_at_the_cap(sb, orc):
+    """Patterns with >= 12 stored entries per row get the small tile shape (1024 staged entries,
+    <= 1021 per tile, <= 256 rows): rows of exactly 1021 entries are still summed in stored order by one
+    thread (bit-exact), rows of 1022 and more take the CTA tree (1e-12); all forms of the kernel
+    (set / add / transposed / csc)."""
+    n = 20000
+    rng = np.random.default_rng(11)
+    special = {5: 1021, 6: 1, 7: 1020, 8: 1, 9: 1022, 4000: 3000, n - 1: 1021}
+    ptr = [1]
+    node, val = [], []
+    for i in range(n):
+        d = special.get(i, int(rng.integers(8, 40)))
+        cols = rng.choice(n, size=d, replace=False) + 1          # unsorted, scattered
+        node.append(cols)
+        val.append(rng.standard_normal(d))
+        ptr.append(ptr[-1] + d)
+    ptr, node, val = np.array(ptr, np.int32), np.concatenate(node).astype(np.int32), np.concatenate(val)
+    assert node.size >= 12 * n
+    x, y0 = rng.standard_normal(n), rng.standard_normal(n)
+    A = sb.csr_matrix(n, n, ptr, node, val)
+    O = orc.Matrix(orc.CSR, n, n, node, val, ptr=ptr)
+    y, yo = A.matvec(x), orc.matvec(O, x)
+    scale = orc.matvec(orc.Matrix(orc.CSR, n, n, node, np.abs(val), ptr=ptr), np.abs(x))
+    assert np.all(np.abs(y - yo) <= 1e-12 * scale)
+    tree = np.array([9, 4000])
+    exact = np.setdiff1d(np.arange(n), tree)
+    assert np.array_equal(y[exact], yo[exact])
+    ya, yao = A.matvec_add(x, y0), orc.matvec_add(O, x, y0)
+    assert np.array_equal(ya[exact], yao[exact]) and np.all(np.abs(ya - yao) <= 1e-12 * (scale + np.abs(y0)))
+    # transposed forms: the device-built stable transpose has its own row lengths (all short here
+    # except the columns the long rows share with nobody) and its own tiling
+    assert np.allclose(A.matvec_t(x), orc.matvec(O, x, trans=True), rtol=0, atol=1e-12 * np.abs(scale).max())
+    cptr, cnode, cval = G.csr_transpose(n, n, ptr, node, val)
+    Ac = sb.csc_matrix(n, n, cptr, cnode, cval)
+    Oc = orc.Matrix(orc.CSC, n, n, cnode, cval, ptr=cptr)
+    yc, yco = Ac.matvec(x), orc.matvec(Oc, x)
+    assert np.all(np.abs(yc - yco) <= 1e-12 * scale)
+
+
 def test_ellpack_isolated_vertex_rejected(sb):
     node = np.array([[1, 2], [0, 0], [3, 3]], np.int32)
     deg = np.array([2, 0, 1], np.int32)

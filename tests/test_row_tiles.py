@@ -1,6 +1,8 @@
 """Host-side row tiling of the streaming CSR kernel (csrc/kernels_spmv.cu build_tiles_host),
 checked without a GPU against the plain row-by-row greedy walk it replaces: consecutive rows
-while the tile holds <= 2045 stored entries and <= 512 rows; a longer row is a tile of its own."""
+while the tile holds <= 2045 stored entries and <= 512 rows (patterns with at least 12 stored
+entries per row on average: <= 1021 entries and <= 256 rows, the small tile shape of gather-bound
+operators, csrc/kernels_spmv.cu tile_shape_for); a longer row is a tile of its own."""
 import ctypes as C
 
 import numpy as np
@@ -9,10 +11,19 @@ import pytest
 from sigma_b200._capi import check, lib, ptr
 
 CAP, ROWS = 2045, 512
+SMALL_CAP, SMALL_ROWS, SMALL_MIN_ROW = 1021, 256, 12
+
+
+def shape(ptr1):
+    """tile_shape_for: the caps the library picks for this pattern"""
+    n = ptr1.size - 1
+    nnz = int(ptr1[-1]) - 1
+    return (SMALL_CAP, SMALL_ROWS) if n > 0 and nnz >= SMALL_MIN_ROW * n else (CAP, ROWS)
 
 
 def greedy(ptr1):
     n = ptr1.size - 1
+    CAP, ROWS = shape(ptr1)
     tiles, s = [], 0
     while s < n:
         e = s + 1
@@ -39,7 +50,9 @@ def cases():
     yield "one_row", np.array([1, 4], np.int32)
     yield "uniform5", 1 + 5 * np.arange(0, 100_001, dtype=np.int64)
     yield "all_empty_rows", np.ones(3000, np.int64)
-    yield "row_of_exactly_cap", np.concatenate([[1], 1 + np.cumsum([CAP, 1, CAP - 1, 1, 1])])
+    yield "row_of_exactly_cap", np.concatenate([[1], 1 + np.cumsum([CAP, 1, CAP - 1, 1, 1] + [0] * 400)])
+    yield "row_of_exactly_small_cap", np.concatenate([[1], 1 + np.cumsum([SMALL_CAP, 1, SMALL_CAP - 1, 1, 1, 2 * SMALL_CAP])])
+    yield "uniform22", 1 + 22 * np.arange(0, 50_001, dtype=np.int64)
     yield "long_rows", np.concatenate([[1], 1 + np.cumsum(rng.choice([0, 3, 700, 2045, 2046, 9000], 400))])
     deg = rng.integers(0, 40, 50_000)
     deg[rng.integers(0, deg.size, 30)] = rng.integers(2000, 5000, 30)
@@ -58,8 +71,9 @@ def test_tiles_equal_the_greedy_walk(case):
         # a partition of the rows, each tile within the limits unless it is a single long row
         assert got[0, 0] == 0 and got[-1, 1] == n and np.array_equal(got[1:, 0], got[:-1, 1])
         nrows, nent = got[:, 1] - got[:, 0], got[:, 3] - got[:, 2]
-        assert np.all(nrows >= 1) and np.all(nrows <= ROWS)
-        assert np.all((nent <= CAP) | (nrows == 1))
+        cap, rows = shape(p)
+        assert np.all(nrows >= 1) and np.all(nrows <= rows)
+        assert np.all((nent <= cap) | (nrows == 1))
 
 
 def device_algorithm_replica(ptr1):
@@ -72,6 +86,7 @@ def device_algorithm_replica(ptr1):
     if n == 0:
         return np.zeros((0, 4), np.int32), 0
     s = np.arange(n)
+    CAP, ROWS = shape(np.asarray(ptr1))
     limit = p[:-1] + CAP
     hi = np.minimum(s + ROWS, n)
     # largest e in [s + 1, hi] with p[e] <= limit, s + 1 when the first row alone is too long
