@@ -800,7 +800,10 @@ def run_ldu(args):
     t_apply = ev_time(lambda: pc.solve_dev(A, x, b), 5)
     emit(row="ldu apply (forward sweep, / D, backward sweep)", ms=t_apply * 1e3, launches=int(per_apply),
          us_per_launch=t_apply * 1e6 / per_apply, algorithmic_bytes=12 * (node.size - n) + 40 * n,
-         note="latency-bound: one launch per level")
+         form={6: "statically scheduled sweeps (one CTA per sweep + transposes into / out of trip order)",
+               2: "chunked sweeps (one launch per sweep)"}.get(int(per_apply), "one launch per level"),
+         env={k: v for k, v in os.environ.items() if k.startswith("SIGB_")},
+         note="latency-bound by construction: 2N - 1 dependent levels per sweep on the N x N five-point stencil")
     K = min(args.steps, 30)
     tol = 1e-10 * float(np.linalg.norm(b_host))
     rates = {}

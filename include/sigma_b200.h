@@ -445,6 +445,16 @@ SIGB_API int sigb_debug_row_tiles_balanced(int32_t n, const int32_t *ptr1, int32
 SIGB_API int sigb_debug_row_tiles_dev(int32_t n, const int32_t *ptr1, int32_t *tiles,
                                       int32_t *ntiles);
 
+/* Diagnostic (host only, no GPU): the plan of a statically scheduled ILDU sweep (csrc/ldu_sweep.h) for the
+ * strictly triangular factor given by its rows (ptr1 n+1, node1, 1-based); backward = 0 for L (rows ascending),
+ * 1 for U (rows descending); levels = depth of the level schedule of the same sweep.  info[16] = eligible, R
+ * (rows per chunk), sigma (skew), C (chunks), trips, W (ring depth), S_max, w16_max, nstage, stage_bytes,
+ * threads, total (lo, hi), total_s (lo, hi), n.  The arrays may be null (a first call returns the sizes):
+ * trip_table trips x 8 int32 (vlo, w, w16, S, off lo/hi, soff lo/hi), src and valmap total_s, cnt total.
+ * tests/test_ldu_sweep_plan.py replays the device kernel on these arrays against the serial solves. */
+SIGB_API int sigb_debug_ldu_sweep_plan(int32_t n, const int32_t *ptr1, const int32_t *node1, int backward,
+                                       int64_t levels, int32_t *info, int32_t *trip_table, int32_t *src,
+                                       uint8_t *cnt, int64_t *valmap);
 /* Diagnostic: SM cycles per phase of the persistent CG kernel, accumulated since
  * the last call (then reset), for its first / middle / last CTA:
  * out[cta * 9 + k], k = 0 SpMV, 1 barrier of reduction 1, 2 cross-GPU part of

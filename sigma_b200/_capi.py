@@ -97,6 +97,7 @@ PROTOTYPES = {
     "sigb_debug_row_tiles": (C.c_int, [_i32, _vp, _vp, _pi32]),
     "sigb_debug_row_tiles_dev": (C.c_int, [_i32, _vp, _vp, _pi32]),
     "sigb_debug_row_tiles_balanced": (C.c_int, [_i32, _vp, _i32, _vp, _pi32]),
+    "sigb_debug_ldu_sweep_plan": (C.c_int, [_i32, _vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _vp]),
     "sigb_debug_cg_phase_cycles": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "sigb_debug_spmv_tile_cycles": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "sigb_partition_rows": (C.c_int, [_i32, _vp, _i32, _vp]),

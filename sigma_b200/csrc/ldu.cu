@@ -28,9 +28,30 @@
 
 #include "device_utils.cuh"
 #include "dist.h"
+#include "ldu_sweep.h"
 #include "solvers.h"
+#include "spmv_device.cuh"
 
 namespace sigb {
+
+// device side of a SweepPlan (ldu_sweep.h)
+struct SweepDev {
+    bool on = false;
+    int32_t n = 0, backward = 0, R = 0, sigma = 0, C = 0, trips = 0, W = 0, S_max = 0, w16_max = 0;
+    int32_t nstage = 0, stage_bytes = 0, threads = 0;
+    int64_t total = 0, total_s = 0;
+    SweepTrip *trip = nullptr;
+    int32_t *src = nullptr;
+    uint8_t *cnt = nullptr;
+    int64_t *valmap = nullptr;
+    double *val = nullptr;                  // the factor's values in trip order (refreshed by every factorisation)
+    double *rhs = nullptr, *xs = nullptr;   // right-hand side and solution in trip order
+    void release()
+    {
+        cudaFree(trip); cudaFree(src); cudaFree(cnt); cudaFree(valmap); cudaFree(val); cudaFree(rhs); cudaFree(xs);
+        *this = SweepDev();
+    }
+};
 
 struct LduInfo {
     int32_t n = 0;
@@ -47,6 +68,8 @@ struct LduInfo {
     RedEntry *xs = nullptr;
     unsigned sf_seq = 0;
     int32_t chunk_rows = 0, nchunks = 0;
+    // statically scheduled sweeps (both or neither)
+    SweepDev fsw, bsw;
     double *Lval() const { return fac; }
     double *Uval() const { return fac + nL; }
     double *D() const { return fac + nL + nU; }
@@ -313,6 +336,220 @@ tri_chunked_kernel(int32_t n, int32_t chunk_rows, int32_t nchunks, const int32_t
 #endif
 }
 
+
+// ---------------------------------------------------------------------------
+// Statically scheduled sweeps (ldu_sweep.h has the schedule): (I + M) x = rhs as ONE CTA.
+//
+// Thread u of trip t owns chunk vlo(t) + u and computes its row at position t - sigma * chunk: the
+// reference's z = x(i); z = z - M%val(k) * x(node(k)) in stored order, rounded products (bit-identical
+// to the serial loops, ldu_solvers.f90:226-235, :254-263).  x(node(k)) comes from the shared-memory ring
+// (the last W positions of every chunk; slot computed on the host) or, further back, from the
+// trip-ordered solution in global memory.  Per trip the slices [rhs | val | src | cnt] are contiguous in
+// global memory and are staged by the TMA engine nstage - 1 trips ahead; one barrier per trip.  No
+// polling anywhere: the host has shown that every value a trip reads was produced by an earlier trip.
+// The right-hand side and the solution are kept in trip order (coalesced in the sweep); two tiled
+// transposes (sweep_in / sweep_out) convert from and to the natural order.
+// ---------------------------------------------------------------------------
+struct SweepArgs {
+    int32_t n, backward, R, sigma, C, trips, W, S_max, w16_max, nstage, stage_bytes;
+    const SweepTrip *trip;
+    const double *val;
+    const int32_t *src;
+    const uint8_t *cnt;
+    double *rhs;
+    double *xs;
+};
+
+__global__ void __launch_bounds__(kThreads)
+sweep_pack_kernel(const int64_t *__restrict__ valmap, const double *__restrict__ fac, int64_t count,
+                  double *__restrict__ out)
+{
+    for (int64_t k = blockIdx.x * (int64_t)kThreads + threadIdx.x; k < count; k += (int64_t)gridDim.x * kThreads) {
+        const int64_t m = valmap[k];
+        out[k] = m >= 0 ? fac[m] : 0.0;
+    }
+}
+
+// natural order -> trip order.  Tile of 32 trips x 32 chunks through shared memory: for a fixed chunk
+// consecutive trips are consecutive rows (coalesced reads), for a fixed trip consecutive chunks are
+// consecutive trip-ordered entries (coalesced writes).  BACKWARD folds x = x / D (ldu_solve :169) in.
+template <bool BACKWARD, bool OUT>
+__global__ void __launch_bounds__(256)
+sweep_transpose_kernel(const SweepArgs a, const double *__restrict__ src, const double *__restrict__ D,
+                       double *__restrict__ dst, const int *skip)
+{
+    if (skip != nullptr && *skip != 0) return;
+    __shared__ double tile[32][33];
+    const int t0 = blockIdx.x * 32, v0 = blockIdx.y * 32;
+    // position p = t - sigma * v over the tile: nothing to do when no (t, v) has 0 <= p < R
+    const long long pmin = (long long)t0 - (long long)a.sigma * (v0 + 31), pmax = (long long)t0 + 31 - (long long)a.sigma * v0;
+    if (pmax < 0 || pmin >= a.R) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    auto row_of = [&](int t, int v, long long *i0) {
+        if (t >= a.trips || v >= a.C) return false;
+        const long long p = (long long)t - (long long)a.sigma * v;
+        if (p < 0 || p >= a.R) return false;
+        const long long q = (long long)v * a.R + p;
+        if (q >= a.n) return false;
+        *i0 = BACKWARD ? (long long)a.n - 1 - q : q;
+        return true;
+    };
+    if (!OUT) {
+        for (int j = ty; j < 32; j += 8) {
+            long long i0;
+            if (row_of(t0 + tx, v0 + j, &i0)) tile[j][tx] = BACKWARD ? src[i0] / D[i0] : src[i0];
+        }
+        __syncthreads();
+        for (int j = ty; j < 32; j += 8) {
+            long long i0;
+            const int t = t0 + j, v = v0 + tx;
+            if (row_of(t, v, &i0)) dst[a.trip[t].off + (v - a.trip[t].vlo)] = tile[tx][j];
+        }
+    } else {
+        for (int j = ty; j < 32; j += 8) {
+            long long i0;
+            const int t = t0 + j, v = v0 + tx;
+            if (row_of(t, v, &i0)) tile[tx][j] = src[a.trip[t].off + (v - a.trip[t].vlo)];
+        }
+        __syncthreads();
+        for (int j = ty; j < 32; j += 8) {
+            long long i0;
+            if (row_of(t0 + tx, v0 + j, &i0)) dst[i0] = tile[j][tx];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+sweep_static_kernel(const __grid_constant__ SweepArgs a, const int *skip)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t mbar[4];
+    if (skip != nullptr && *skip != 0) return;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    double *ring = reinterpret_cast<double *>(smem + (size_t)a.nstage * a.stage_bytes);
+    const int o_val = 8 * a.w16_max, o_src = o_val + 8 * a.S_max * a.w16_max, o_cnt = o_src + 4 * a.S_max * a.w16_max;
+    if (tid == 0) {
+        for (int k = 0; k < a.nstage; k++) mbar_init(&mbar[k], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const uint64_t policy = policy_evict_first();
+    auto issue = [&](int t) {
+        const int stage = t % a.nstage;
+        unsigned char *base = smem + (size_t)stage * a.stage_bytes;
+        const SweepTrip T = a.trip[t];
+        const uint32_t w16 = (uint32_t)T.w16, S = (uint32_t)T.S;
+        mbar_expect_tx(&mbar[stage], w16 * 9u + S * w16 * 12u);
+        if (w16 == 0) return;
+        bulk_g2s(base, a.rhs + T.off, w16 * 8u, &mbar[stage], policy);
+        bulk_g2s(base + o_cnt, a.cnt + T.off, w16, &mbar[stage], policy);
+        if (S > 0) {
+            bulk_g2s(base + o_val, a.val + T.soff, S * w16 * 8u, &mbar[stage], policy);
+            bulk_g2s(base + o_src, a.src + T.soff, S * w16 * 4u, &mbar[stage], policy);
+        }
+    };
+    if (tid == 0)
+        for (int t = 0; t < a.nstage - 1 && t < a.trips; t++) issue(t);
+    const int wmask = a.W - 1;
+    for (int t = 0; t < a.trips; t++) {
+        // the stage trip t - 1 used was released by the barrier that ended it
+        if (tid == 0 && t + a.nstage - 1 < a.trips) issue(t + a.nstage - 1);
+        const int stage = t % a.nstage;
+        const int4 d = __ldg(reinterpret_cast<const int4 *>(a.trip + t));     // vlo, w, w16, S
+        const long long off = __ldg(&a.trip[t].off);
+        mbar_wait(&mbar[stage], (uint32_t)(t / a.nstage) & 1u);
+        const unsigned char *base = smem + (size_t)stage * a.stage_bytes;
+        const double *s_rhs = reinterpret_cast<const double *>(base);
+        const double *s_val = reinterpret_cast<const double *>(base + o_val);
+        const int32_t *s_src = reinterpret_cast<const int32_t *>(base + o_src);
+        const unsigned char *s_cnt = base + o_cnt;
+        for (int u = tid; u < d.y; u += nthreads) {
+            const int c = s_cnt[u];
+            if (c == kSweepNoRow) continue;
+            double z = s_rhs[u];
+            for (int s = 0; s < c; s++) {
+                const int src = s_src[s * d.z + u];
+                const double xj = src >= 0 ? ring[src] : __ldcg(a.xs + (-(long long)src - 1));
+                z = sub(z, mul(s_val[s * d.z + u], xj));
+            }
+            const int v = d.x + u, p = t - a.sigma * v;
+            a.xs[off + u] = z;
+            ring[(p & wmask) * a.C + v] = z;
+        }
+        fence_proxy_async();     // this stage is refilled by the async proxy after the barrier
+        __syncthreads();
+    }
+}
+
+static SweepArgs sweep_args(const SweepDev &W)
+{
+    SweepArgs a;
+    a.n = W.n; a.backward = W.backward; a.R = W.R; a.sigma = W.sigma; a.C = W.C; a.trips = W.trips; a.W = W.W;
+    a.S_max = W.S_max; a.w16_max = W.w16_max; a.nstage = W.nstage; a.stage_bytes = W.stage_bytes;
+    a.trip = W.trip; a.val = W.val; a.src = W.src; a.cnt = W.cnt; a.rhs = W.rhs; a.xs = W.xs;
+    return a;
+}
+
+// one statically scheduled sweep: src (natural order; BACKWARD: / D) -> trip order, the sweep, -> x
+template <bool BACKWARD>
+int launch_sweep_static(const SweepDev &W, const double *src, const double *D, double *x, const int *skip)
+{
+    cudaStream_t st = ctx().stream;
+    const SweepArgs a = sweep_args(W);
+    const dim3 tg((unsigned)((W.trips + 31) / 32), (unsigned)((W.C + 31) / 32));
+    sweep_transpose_kernel<BACKWARD, false><<<tg, 256, 0, st>>>(a, src, D, W.rhs, skip);
+    const size_t smem = (size_t)W.nstage * W.stage_bytes + (size_t)W.W * W.C * 8;
+    static thread_local bool attr_set = false;   // per host thread = per device
+    if (!attr_set) {
+        SIGB_CUDA(cudaFuncSetAttribute(sweep_static_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+        attr_set = true;
+    }
+    sweep_static_kernel<<<1, W.threads, smem, st>>>(a, skip);
+    sweep_transpose_kernel<BACKWARD, true><<<tg, 256, 0, st>>>(a, W.xs, nullptr, x, skip);
+    count_launch(3);
+    SIGB_CUDA(cudaGetLastError());
+    return SIGB_OK;
+}
+
+static int upload_sweep(const SweepPlan &P, SweepDev &W)
+{
+    W = SweepDev();
+    if (!P.eligible) return SIGB_OK;
+    W.n = P.n; W.backward = P.backward; W.R = P.R; W.sigma = P.sigma; W.C = P.C; W.trips = P.trips; W.W = P.W;
+    W.S_max = P.S_max; W.w16_max = P.w16_max; W.nstage = P.nstage; W.stage_bytes = P.stage_bytes; W.threads = P.threads;
+    W.total = P.total; W.total_s = P.total_s;
+    cudaStream_t st = ctx().stream;
+    const size_t ts = (size_t)std::max<int64_t>(P.total_s, 1), tt = (size_t)std::max<int64_t>(P.total, 1);
+    SIGB_CUDA(cudaMalloc((void **)&W.trip, sizeof(SweepTrip) * P.trip.size()));
+    SIGB_CUDA(cudaMalloc((void **)&W.src, sizeof(int32_t) * ts));
+    SIGB_CUDA(cudaMalloc((void **)&W.cnt, tt));
+    SIGB_CUDA(cudaMalloc((void **)&W.valmap, sizeof(int64_t) * ts));
+    SIGB_CUDA(cudaMalloc((void **)&W.val, sizeof(double) * ts));
+    SIGB_CUDA(cudaMalloc((void **)&W.rhs, sizeof(double) * tt));
+    SIGB_CUDA(cudaMalloc((void **)&W.xs, sizeof(double) * tt));
+    SIGB_CUDA(cudaMemcpyAsync(W.trip, P.trip.data(), sizeof(SweepTrip) * P.trip.size(), cudaMemcpyHostToDevice, st));
+    if (P.total_s > 0) {
+        SIGB_CUDA(cudaMemcpyAsync(W.src, P.src.data(), sizeof(int32_t) * (size_t)P.total_s, cudaMemcpyHostToDevice, st));
+        SIGB_CUDA(cudaMemcpyAsync(W.valmap, P.valmap.data(), sizeof(int64_t) * (size_t)P.total_s, cudaMemcpyHostToDevice, st));
+    }
+    SIGB_CUDA(cudaMemcpyAsync(W.cnt, P.cnt.data(), (size_t)P.total, cudaMemcpyHostToDevice, st));
+    // padding of a trip's right-hand side / solution is staged and never used: defined values all the same
+    SIGB_CUDA(cudaMemsetAsync(W.rhs, 0, sizeof(double) * tt, st));
+    SIGB_CUDA(cudaMemsetAsync(W.xs, 0, sizeof(double) * tt, st));
+    SIGB_CUDA(cudaStreamSynchronize(st));    // the plan's host vectors go out of scope in the caller
+    W.on = true;
+    return SIGB_OK;
+}
+
+static int pack_sweep(const SweepDev &W, const double *fac_part)
+{
+    if (!W.on || W.total_s == 0) return SIGB_OK;
+    sweep_pack_kernel<<<grid_for(W.total_s), kThreads, 0, ctx().stream>>>(W.valmap, fac_part, W.total_s, W.val);
+    count_launch();
+    SIGB_CUDA(cudaGetLastError());
+    return SIGB_OK;
+}
+
 // scratch of the chunked sweeps; hands out the next sequence number (0 = never written)
 int sweep_prepare(LduInfo *F, unsigned *seq)
 {
@@ -374,6 +611,8 @@ void choose_chunking(LduInfo *F, const std::vector<int32_t> &Lptr, const std::ve
 void free_ldu(LduInfo *F)
 {
     if (!F) return;
+    F->fsw.release();
+    F->bsw.release();
     cudaFree(F->xs);
     cudaFree(F->Lptr); cudaFree(F->Lnode); cudaFree(F->Uptr); cudaFree(F->Unode);
     cudaFree(F->fac); cudaFree(F->dest); cudaFree(F->frows); cudaFree(F->brows);
@@ -446,6 +685,16 @@ int ldu_setup_dev(sigb_solver_t s, sigb_matrix_t A)
             F->flev.assign(flev.begin(), flev.begin() + nf + 1);
             F->blev.assign(blev.begin(), blev.begin() + nb + 1);
             choose_chunking(F, Lptr, Lnode, Uptr, Unode);
+            // statically scheduled sweeps where the pattern has a wavefront (both sweeps or neither)
+            if (env_int("SIGB_LDU_STATIC", 1) != 0) {
+                SweepPlan Pf, Pb;
+                build_sweep_plan(n, Lptr.data(), Lnode.data(), 0, (int64_t)nf, Pf);
+                if (Pf.eligible) build_sweep_plan(n, Uptr.data(), Unode.data(), 1, (int64_t)nb, Pb);
+                if (Pf.eligible && Pb.eligible) {
+                    rc = upload_sweep(Pf, F->fsw);
+                    if (rc == SIGB_OK) rc = upload_sweep(Pb, F->bsw);
+                }
+            }
             rc = upload(&F->Lptr, Lptr.data(), (size_t)n + 1);
             if (rc == SIGB_OK) rc = upload(&F->Uptr, Uptr.data(), (size_t)n + 1);
             if (rc == SIGB_OK) rc = upload(&F->Lnode, Lnode.data(), (size_t)F->nL);
@@ -483,6 +732,9 @@ int ldu_setup_dev(sigb_solver_t s, sigb_matrix_t A)
         count_launch();
     }
     SIGB_CUDA(cudaGetLastError());
+    // the factors in trip order for the statically scheduled sweeps
+    SIGB_CHECK(pack_sweep(F->fsw, F->Lval()));
+    SIGB_CHECK(pack_sweep(F->bsw, F->Uval()));
     return SIGB_OK;
 }
 
@@ -493,6 +745,13 @@ int ldu_apply_dev(sigb_solver_t s, double *x, const double *b, const int *skip_f
     SIGB_REQUIRE(F, SIGB_ERR_STATE, "ldu solve: pc%%setup(A) has not been called");
     cudaStream_t st = ctx().stream;
     const int32_t n = F->n;
+    if (F->fsw.on && F->bsw.on && n > 0) {
+        // wavefront pattern: each sweep is one CTA on a schedule fixed at setup; x = b and x = x / D are
+        // folded into the transposes that bring the right-hand sides into trip order
+        SIGB_CHECK(launch_sweep_static<false>(F->fsw, b, nullptr, x, skip_flag));
+        SIGB_CHECK(launch_sweep_static<true>(F->bsw, x, F->D(), x, skip_flag));
+        return SIGB_OK;
+    }
     if (F->nchunks > 0 && n > 0) {
         // deep schedule: two launches; x = b and x = x / D are folded into the sweeps' first reads
         SIGB_CHECK(launch_tri_chunked<false>(F, F->Lptr, F->Lnode, F->Lval(), b, x, skip_flag));

@@ -129,6 +129,7 @@ struct TileCfg {
     static constexpr int kStageBytes = (kStageVal + kStageNode + kStagePtr + 127) & ~127;
     static constexpr int kRowSlots = (kRows + kThreads - 1) / kThreads;   // rows of a tile a thread may own
     static constexpr int kEntrySlots = TN / kThreads;                     // entries of a tile a thread gathers
+    static constexpr bool kBatchRowSums = TN != kTileNnz;                 // ordered_sum: products fetched eight at a time
     static_assert(TN % kThreads == 0 && TN >= kThreads, "tile entries: a multiple of the CTA size");
 };
 using TileCfgLarge = TileCfg<kTileNnz>;
@@ -219,19 +220,20 @@ __device__ __forceinline__ void finish_dots(const CsrKernelArgs &a, double *acc)
 // time BEFORE the dependent chain of additions starts: a plain loop exposes the shared-memory latency
 // on every step (load, add, load, add ...), which made the row sums of matrices with ~20 entries per
 // row the longest part of a tile (ncu on the Erdos-Renyi operator: warps mostly stalled at the CTA
-// barrier behind the few threads that own rows, profiles/r2_ncu_er_2m_round1_kernel.txt).
-#ifndef SIGB_ROWSUM_BATCH
-#define SIGB_ROWSUM_BATCH 0
-#endif
+// barrier behind the few threads that own rows, profiles/r2_ncu_er_2m_large_shape.txt).
+// BATCH: the small tile shape (long rows); the large one keeps the plain loop -- with ~5 entries per row
+// the batches never fill (A/B on the Poisson matrix: 225.3 us plain, 226.8 us batched,
+// profiles/r2_visit_f_1gpu_summary.txt).
 #ifndef SIGB_UR_STAGES
 #define SIGB_UR_STAGES 3
 #endif
+template <bool BATCH>
 __device__ __forceinline__ double ordered_sum(const double *sval, int b, int e, double z)
 {
-#if !SIGB_ROWSUM_BATCH
-    for (int k = b; k < e; k++) z = add(z, sval[k]);
-    return z;
-#endif
+    if (!BATCH) {
+        for (int k = b; k < e; k++) z = add(z, sval[k]);
+        return z;
+    }
     int k = b;
     for (; k + 8 <= e; k += 8) {
         double p[8];
@@ -426,7 +428,7 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, const SpmvVec
             const int r = rs + tid + i * kThreads;
             if (r < re) {
                 const int b = sptr[r - ra] - 1 - ka, e = sptr[r + 1 - ra] - 1 - ka;
-                const double z = ordered_sum(sval, b, e, (MODE == MODE_ACC_INIT) ? v.y[r] : 0.0);
+                const double z = ordered_sum<CFG::kBatchRowSums>(sval, b, e, (MODE == MODE_ACC_INIT) ? v.y[r] : 0.0);
                 z_dot[i] = store_row<MODE>(a, v, r, z);
             }
         }

@@ -66,13 +66,17 @@ def deep_cases():
     yield "tridiag5000", 5000, *G.tridiag_csr(5000, 2.5, -1.0, -0.5)
 
 
+@pytest.mark.parametrize("static", [1, 0], ids=["static_schedule", "chunked_polling"])
 @pytest.mark.parametrize("case", list(deep_cases()), ids=lambda c: c[0])
-def test_chunked_sweeps_bit_exact(sb, orc, case):
-    """Deep level schedules run the triangular solves as chunked sweeps (one launch per sweep, every
-    thread a contiguous chunk of rows, waiting for exactly the entries it reads): same arithmetic per
-    row in stored order, so pc%solve must equal the serial loops bit for bit -- repeatedly (the
-    sequence numbers of the published entries advance) and for csr and csc sources."""
-    _, n, ptr, node, val = case
+def test_deep_sweeps_bit_exact(sb, orc, case, static, monkeypatch):
+    """Deep level schedules run the triangular solves as ONE launch per sweep: on a schedule fixed at setup
+    where the pattern has a wavefront (one CTA, a thread per chunk of rows, lock-step trips, values handed on
+    through a shared-memory ring; csrc/ldu_sweep.h -- 6 launches per pc%solve with the transposes into and
+    out of trip order), else as chunked sweeps that wait for exactly the entries they read (2 launches;
+    forced here with SIGB_LDU_STATIC=0).  Same arithmetic per row in stored order either way, so pc%solve
+    must equal the serial loops bit for bit -- repeatedly, and for csr and csc sources."""
+    name, n, ptr, node, val = case
+    monkeypatch.setenv("SIGB_LDU_STATIC", str(static))
     for fmt in ("csr", "csc"):
         A, O = in_format(sb, orc, fmt, n, ptr, node, val)
         F = orc.ldu_setup(O)
@@ -81,9 +85,19 @@ def test_chunked_sweeps_bit_exact(sb, orc, case):
         nf, nb = same_factors(pc, F)
         assert nf > 64 and nb > 64
         rng = np.random.default_rng(1)
+        x = np.zeros(n)
         for _ in range(3):
             b = rng.standard_normal(n)
-            assert np.array_equal(pc.solve(A, np.zeros(n), b), orc.ldu_solve(F, b))
+            before = sb.launch_count()
+            x = pc.solve(A, x, b)
+            launches = sb.launch_count() - before
+            assert np.array_equal(x, orc.ldu_solve(F, b))
+        assert launches == (6 if static else 2), (name, launches)
+        # a second numeric factorisation on the same pattern (the values in trip order are refreshed)
+        A2, O2 = in_format(sb, orc, fmt, n, ptr, node, val * 1.25 + 0.0)
+        pc.setup(A2)
+        b = rng.standard_normal(n)
+        assert np.array_equal(pc.solve(A2, np.zeros(n), b), orc.ldu_solve(orc.ldu_setup(O2), b))
 
 
 def test_incomplete_cholesky_like_the_reference(sb, orc):

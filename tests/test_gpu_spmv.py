@@ -68,12 +68,13 @@ def test_ellpack_matvec_bit_exact(sb, orc, case):
     assert np.array_equal(A.matvec_add(x, y0), orc.matvec_add(O, x, y0))
     # ellpack_matvec_t_add scatters every slot, padding included; the last
     # neighbour of many rows can therefore own a transposed row longer than a
-    # tile, which is summed by a fixed CTA tree (order differs): bit-exact for
+    # tile (1021 entries in the small tile shape this pattern gets, 2045 in the large one),
+    # which is summed by a fixed CTA tree (order differs): bit-exact for
     # rows within a tile, 1e-12 relative to sum|a_ij x_j| otherwise
     yt, yto = A.matvec_t(x), orc.matvec(O, x, trans=True)
     yta, ytao = A.matvec_t_add(x, y0), orc.matvec_add(O, x, y0, trans=True)
     counts = np.bincount(enode.reshape(-1) - 1, minlength=n)
-    short = counts <= 2000
+    short = counts <= 1000
     assert np.array_equal(yt[short], yto[short]) and np.array_equal(yta[short], ytao[short])
     scale = orc.matvec(orc.Matrix(orc.ELL, n, n, enode, np.abs(eval_), degrees=edeg), np.abs(x), trans=True)
     assert np.all(np.abs(yt - yto) <= 1e-12 * scale) and np.all(np.abs(yta - ytao) <= 1e-12 * (scale + np.abs(y0)))
