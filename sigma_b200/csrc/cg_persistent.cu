@@ -417,6 +417,7 @@ int cg_persistent_run(sigb_solver_t s, const CsrView &V, const double *val, cons
     d.ndot = 1;
     d.u = p;
     SIGB_CHECK(fill_csr_args(V, val, p, q, d, &a.A));
+    a.A.sync.push_all = 0;     // dedicated communication CTAs inside the persistent kernel
     a.x = x; a.p = p; a.q = q; a.r = r; a.z = z;
     a.b = b;
     a.idiag = idiag;

@@ -636,6 +636,11 @@ int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global, const int32_t *part
         D->sync.send_rows = D->send_rows;
         D->sync.total_send = total_send;
         D->sync.push_ctas = push_ctas;
+        // fewer than a quarter of the tiles are free of halo columns: nothing to hide the transfer behind,
+        // every CTA of a stand-alone SpMV pushes its share first (HaloSync::push_all)
+        D->sync.push_all = (push_ctas > 0 && ti.size() * 4 < tiles.size()) ? 1 : 0;
+        const int forced = env_int("SIGB_PUSH_ALL", -1);      // A/B runs: 0 / 1 whatever the pattern
+        if (forced >= 0 && push_ctas > 0) D->sync.push_all = forced ? 1 : 0;
         for (int q = 0; q < kMaxRanks; q++) {
             D->sync.peer[q] = q < P ? (HaloWin *)peers[q] : nullptr;
             D->sync.dst[q] = nullptr;

@@ -263,6 +263,11 @@ struct HaloSync {
     const int32_t *send_rows = nullptr;   // 1-based owned rows, grouped by destination
     int32_t total_send = 0;
     int32_t push_ctas = 0;                // communication CTAs (fixed when the operator is created)
+    // Operators without locality (a random graph: nearly every tile reads halo columns, nearly all of x is
+    // sent): there is no interior work to hide the transfer behind, so in a stand-alone launch EVERY CTA
+    // first pushes its share of the send list and then takes tiles (the launcher sets push_ctas = grid).
+    // The persistent CG kernel keeps dedicated communication CTAs and clears this.
+    int32_t push_all = 0;
     int32_t send_off[kMaxRanks + 1] = {};
     double *dst[kMaxRanks] = {};          // peer landing buffer 0, offset to our slice
     int64_t dst_stride[kMaxRanks] = {};

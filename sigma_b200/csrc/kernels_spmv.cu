@@ -229,11 +229,19 @@ int launch_csr_cfg(const CsrKernelArgs &a, cudaStream_t st)
     } else {
         SIGB_CHECK((occupancy_grid<csr_tma_kernel<MODE, NDOT, HALO, CFG>>(smem, &grid)));
     }
-    // one CTA per tile is enough; the communication CTAs of a row-sharded operator come on top
-    const int comm = (HALO && a.sync.win != nullptr) ? a.sync.push_ctas : 0;
+    // one CTA per tile is enough; the communication CTAs of a row-sharded operator come on top --
+    // unless every CTA pushes (HaloSync::push_all): then the whole grid is named as pushers
+    const bool push_all = HALO && a.sync.win != nullptr && a.sync.push_all != 0;
+    const int comm = (HALO && a.sync.win != nullptr && !push_all) ? a.sync.push_ctas : 0;
     if (a.ntiles + comm < grid) grid = a.ntiles + comm;
     if (grid < comm + 1) grid = comm + 1;
-    csr_tma_kernel<MODE, NDOT, HALO, CFG><<<grid, kThreads, smem, st>>>(a);
+    if (push_all) {
+        CsrKernelArgs b = a;
+        b.sync.push_ctas = grid;
+        csr_tma_kernel<MODE, NDOT, HALO, CFG><<<grid, kThreads, smem, st>>>(b);
+    } else {
+        csr_tma_kernel<MODE, NDOT, HALO, CFG><<<grid, kThreads, smem, st>>>(a);
+    }
     count_launch();
     SIGB_CUDA(cudaGetLastError());
     return SIGB_OK;

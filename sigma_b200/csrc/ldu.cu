@@ -434,10 +434,9 @@ sweep_static_kernel(const __grid_constant__ SweepArgs a, const int *skip)
     }
     __syncthreads();
     const uint64_t policy = policy_evict_first();
-    auto issue = [&](int t) {
+    auto issue = [&](int t, const SweepTrip &T) {
         const int stage = t % a.nstage;
         unsigned char *base = smem + (size_t)stage * a.stage_bytes;
-        const SweepTrip T = a.trip[t];
         const uint32_t w16 = (uint32_t)T.w16, S = (uint32_t)T.S;
         mbar_expect_tx(&mbar[stage], w16 * 9u + S * w16 * 12u);
         if (w16 == 0) return;
@@ -448,36 +447,63 @@ sweep_static_kernel(const __grid_constant__ SweepArgs a, const int *skip)
             bulk_g2s(base + o_src, a.src + T.soff, S * w16 * 4u, &mbar[stage], policy);
         }
     };
-    if (tid == 0)
-        for (int t = 0; t < a.nstage - 1 && t < a.trips; t++) issue(t);
+    // Trip descriptors are read one trip before they are needed (by the producer thread for the trip it
+    // stages next, by everybody for the trip computed next): a global load at the head of a trip would
+    // sit on the critical path of all 2 N trips (first version: 1.05 us per trip; visit r2p).
+    int t_issue = 0;
+    SweepTrip T_issue = a.trip[0];
+    if (tid == 0) {
+        for (; t_issue < a.nstage - 1 && t_issue < a.trips; t_issue++) {
+            issue(t_issue, T_issue);
+            if (t_issue + 1 < a.trips) T_issue = a.trip[t_issue + 1];
+        }
+    }
     const int wmask = a.W - 1;
+    int4 d = __ldg(reinterpret_cast<const int4 *>(a.trip));                   // vlo, w, w16, S of trip 0
+    long long off = __ldg(&a.trip[0].off);
     for (int t = 0; t < a.trips; t++) {
         // the stage trip t - 1 used was released by the barrier that ended it
-        if (tid == 0 && t + a.nstage - 1 < a.trips) issue(t + a.nstage - 1);
+        if (tid == 0 && t_issue < a.trips) {
+            issue(t_issue, T_issue);
+            t_issue++;
+            if (t_issue < a.trips) T_issue = a.trip[t_issue];
+        }
+        int4 d_next = d;
+        long long off_next = off;
+        if (t + 1 < a.trips) {
+            d_next = __ldg(reinterpret_cast<const int4 *>(a.trip + t + 1));
+            off_next = __ldg(&a.trip[t + 1].off);
+        }
         const int stage = t % a.nstage;
-        const int4 d = __ldg(reinterpret_cast<const int4 *>(a.trip + t));     // vlo, w, w16, S
-        const long long off = __ldg(&a.trip[t].off);
         mbar_wait(&mbar[stage], (uint32_t)(t / a.nstage) & 1u);
         const unsigned char *base = smem + (size_t)stage * a.stage_bytes;
         const double *s_rhs = reinterpret_cast<const double *>(base);
         const double *s_val = reinterpret_cast<const double *>(base + o_val);
         const int32_t *s_src = reinterpret_cast<const int32_t *>(base + o_src);
         const unsigned char *s_cnt = base + o_cnt;
+        auto fetch = [&](int src) { return src >= 0 ? ring[src] : __ldcg(a.xs + (-(long long)src - 1)); };
         for (int u = tid; u < d.y; u += nthreads) {
             const int c = s_cnt[u];
             if (c == kSweepNoRow) continue;
             double z = s_rhs[u];
-            for (int s = 0; s < c; s++) {
-                const int src = s_src[s * d.z + u];
-                const double xj = src >= 0 ? ring[src] : __ldcg(a.xs + (-(long long)src - 1));
-                z = sub(z, mul(s_val[s * d.z + u], xj));
+            int s = 0;
+            for (; s + 2 <= c; s += 2) {          // two slots at a time: their loads do not wait for each other
+                const int i0 = s_src[s * d.z + u], i1 = s_src[(s + 1) * d.z + u];
+                const double a0 = s_val[s * d.z + u], a1 = s_val[(s + 1) * d.z + u];
+                const double x0 = fetch(i0), x1 = fetch(i1);
+                z = sub(z, mul(a0, x0));
+                z = sub(z, mul(a1, x1));
             }
+            if (s < c) z = sub(z, mul(s_val[s * d.z + u], fetch(s_src[s * d.z + u])));
             const int v = d.x + u, p = t - a.sigma * v;
             a.xs[off + u] = z;
             ring[(p & wmask) * a.C + v] = z;
         }
-        fence_proxy_async();     // this stage is refilled by the async proxy after the barrier
+        // (the stage is only READ through the generic proxy, so the barrier alone orders it before the
+        //  bulk copy that refills it)
         __syncthreads();
+        d = d_next;
+        off = off_next;
     }
 }
 
@@ -504,7 +530,9 @@ int launch_sweep_static(const SweepDev &W, const double *src, const double *D, d
         SIGB_CUDA(cudaFuncSetAttribute(sweep_static_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
         attr_set = true;
     }
-    sweep_static_kernel<<<1, W.threads, smem, st>>>(a, skip);
+    static const int max_threads = env_int("SIGB_LDU_SWEEP_THREADS", 1024);
+    const int threads = std::max(32, std::min(W.threads, max_threads & ~31));
+    sweep_static_kernel<<<1, threads, smem, st>>>(a, skip);
     sweep_transpose_kernel<BACKWARD, true><<<tg, 256, 0, st>>>(a, W.xs, nullptr, x, skip);
     count_launch(3);
     SIGB_CUDA(cudaGetLastError());

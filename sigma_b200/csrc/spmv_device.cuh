@@ -267,16 +267,16 @@ struct TilePipe {
 // pass: 35.1 us against 30.3 us for the others, profiles/r2_visit_b_2gpu_summary.txt.)
 __device__ __forceinline__ bool is_comm_cta(const CsrKernelArgs &a)
 {
-    return a.sync.win != nullptr && (int)blockIdx.x < a.sync.push_ctas;
+    return a.sync.win != nullptr && !a.sync.push_all && (int)blockIdx.x < a.sync.push_ctas;
 }
 // position of this CTA among the compute CTAs, and how many there are
 __device__ __forceinline__ int compute_rank(const CsrKernelArgs &a)
 {
-    return a.sync.win != nullptr ? (int)blockIdx.x - a.sync.push_ctas : (int)blockIdx.x;
+    return (a.sync.win != nullptr && !a.sync.push_all) ? (int)blockIdx.x - a.sync.push_ctas : (int)blockIdx.x;
 }
 __device__ __forceinline__ int compute_ctas(const CsrKernelArgs &a)
 {
-    return a.sync.win != nullptr ? (int)gridDim.x - a.sync.push_ctas : (int)gridDim.x;
+    return (a.sync.win != nullptr && !a.sync.push_all) ? (int)gridDim.x - a.sync.push_ctas : (int)gridDim.x;
 }
 
 template <bool XNC>
@@ -347,6 +347,8 @@ __device__ __forceinline__ void spmv_phase(const CsrKernelArgs &a, const SpmvVec
         halo_push<XNC>(a, v.x1, hseq);
         return;
     }
+    // no interior work to overlap with: every CTA pushes its share first (push_ctas == gridDim.x here)
+    if (HALO && a.sync.win != nullptr && a.sync.push_all) halo_push<XNC>(a, v.x1, hseq);
     const int crank = HALO ? compute_rank(a) : (int)blockIdx.x;
     const int cstride = HALO ? compute_ctas(a) : (int)gridDim.x;
     const double *h1 = a.h1;
