@@ -449,7 +449,7 @@ SIGB_API int sigb_debug_row_tiles_dev(int32_t n, const int32_t *ptr1, int32_t *t
  * strictly triangular factor given by its rows (ptr1 n+1, node1, 1-based); backward = 0 for L (rows ascending),
  * 1 for U (rows descending); levels = depth of the level schedule of the same sweep.  info[16] = eligible, R
  * (rows per chunk), sigma (skew), C (chunks), trips, W (ring depth), S_max, w16_max, nstage, stage_bytes,
- * threads, total (lo, hi), total_s (lo, hi), n.  The arrays may be null (a first call returns the sizes):
+ * threads, total (lo, hi), total_s (lo, hi), has_far.  The arrays may be null (a first call returns the sizes):
  * trip_table trips x 8 int32 (vlo, w, w16, S, off lo/hi, soff lo/hi), src and valmap total_s, cnt total.
  * tests/test_ldu_sweep_plan.py replays the device kernel on these arrays against the serial solves. */
 SIGB_API int sigb_debug_ldu_sweep_plan(int32_t n, const int32_t *ptr1, const int32_t *node1, int backward,

@@ -38,17 +38,15 @@ namespace sigb {
 struct SweepDev {
     bool on = false;
     int32_t n = 0, backward = 0, R = 0, sigma = 0, C = 0, trips = 0, W = 0, S_max = 0, w16_max = 0;
-    int32_t nstage = 0, stage_bytes = 0, threads = 0;
+    int32_t nstage = 0, stage_bytes = 0, threads = 0, has_far = 0;
     int64_t total = 0, total_s = 0;
     SweepTrip *trip = nullptr;
-    int32_t *src = nullptr;
-    uint8_t *cnt = nullptr;
-    int64_t *valmap = nullptr;
-    double *val = nullptr;                  // the factor's values in trip order (refreshed by every factorisation)
-    double *rhs = nullptr, *xs = nullptr;   // right-hand side and solution in trip order
+    int64_t *valmap = nullptr;              // entry of the factor behind every slot (-1: padding)
+    unsigned char *slab = nullptr;          // what the trips read, trip by trip (sweep_static_kernel)
+    double *xs = nullptr;                   // the solution in trip order
     void release()
     {
-        cudaFree(trip); cudaFree(src); cudaFree(cnt); cudaFree(valmap); cudaFree(val); cudaFree(rhs); cudaFree(xs);
+        cudaFree(trip); cudaFree(valmap); cudaFree(slab); cudaFree(xs);
         *this = SweepDev();
     }
 };
@@ -344,35 +342,54 @@ tri_chunked_kernel(int32_t n, int32_t chunk_rows, int32_t nchunks, const int32_t
 // reference's z = x(i); z = z - M%val(k) * x(node(k)) in stored order, rounded products (bit-identical
 // to the serial loops, ldu_solvers.f90:226-235, :254-263).  x(node(k)) comes from the shared-memory ring
 // (the last W positions of every chunk; slot computed on the host) or, further back, from the
-// trip-ordered solution in global memory.  Per trip the slices [rhs | val | src | cnt] are contiguous in
-// global memory and are staged by the TMA engine nstage - 1 trips ahead; one barrier per trip.  No
-// polling anywhere: the host has shown that every value a trip reads was produced by an earlier trip.
-// The right-hand side and the solution are kept in trip order (coalesced in the sweep); two tiled
-// transposes (sweep_in / sweep_out) convert from and to the natural order.
+// trip-ordered solution in global memory.  Everything a trip reads -- its right-hand sides, values,
+// ring slots and row lengths -- is ONE contiguous slab [rhs | val | src | cnt] in global memory, staged
+// by one bulk copy (TMA) nstage - 1 trips ahead; one barrier per trip; no polling anywhere: the host has
+// shown that every value a trip reads was produced by an earlier trip.
+//
+// The sweep is bound by INSTRUCTION ISSUE, not by memory (diagnostic build _sweepstats, visit r2t: with a
+// generic row loop ~140 instructions per row, 1 140 cycles per trip in the rows, 8 cycles at the barrier,
+// ~120 waiting for the stage), so rows of at most two entries without far reads -- every stencil-like
+// factor -- take a straight-line body, and the producer issues one copy per trip instead of four.
+// The right-hand side and the solution live in trip order (coalesced in the sweep); two tiled transposes
+// convert from and to the natural order.
 // ---------------------------------------------------------------------------
 struct SweepArgs {
     int32_t n, backward, R, sigma, C, trips, W, S_max, w16_max, nstage, stage_bytes;
     const SweepTrip *trip;
-    const double *val;
-    const int32_t *src;
-    const uint8_t *cnt;
-    double *rhs;
-    double *xs;
+    unsigned char *slab;     // per trip [rhs 8 w16 | val 8 S w16 | src 4 S w16 | cnt w16] at byte 9 off + 12 soff
+    double *xs;              // the solution in trip order
 };
 
+__device__ __forceinline__ long long slab_offset(const SweepTrip &T) { return 9ll * T.off + 12ll * T.soff; }
+
+// static parts of the slabs (src, cnt: once per pattern) and the values (every factorisation); one CTA per trip
+template <bool VALUES>
 __global__ void __launch_bounds__(kThreads)
-sweep_pack_kernel(const int64_t *__restrict__ valmap, const double *__restrict__ fac, int64_t count,
-                  double *__restrict__ out)
+sweep_pack_kernel(const SweepTrip *__restrict__ trip, const int64_t *__restrict__ valmap, const int32_t *__restrict__ src,
+                  const uint8_t *__restrict__ cnt, const double *__restrict__ fac, unsigned char *__restrict__ slab)
 {
-    for (int64_t k = blockIdx.x * (int64_t)kThreads + threadIdx.x; k < count; k += (int64_t)gridDim.x * kThreads) {
-        const int64_t m = valmap[k];
-        out[k] = m >= 0 ? fac[m] : 0.0;
+    const SweepTrip T = trip[blockIdx.x];
+    unsigned char *base = slab + slab_offset(T);
+    const int nslots = T.S * T.w16;
+    if (VALUES) {
+        double *val = reinterpret_cast<double *>(base + 8ll * T.w16);
+        for (int k = threadIdx.x; k < nslots; k += kThreads) {
+            const int64_t m = valmap[T.soff + k];
+            val[k] = m >= 0 ? fac[m] : 0.0;
+        }
+    } else {
+        int32_t *d_src = reinterpret_cast<int32_t *>(base + 8ll * T.w16 * (1 + T.S));
+        unsigned char *d_cnt = base + 8ll * T.w16 * (1 + T.S) + 4ll * nslots;
+        for (int k = threadIdx.x; k < nslots; k += kThreads) d_src[k] = src[T.soff + k];
+        for (int k = threadIdx.x; k < T.w16; k += kThreads) d_cnt[k] = cnt[T.off + k];
     }
 }
 
-// natural order -> trip order.  Tile of 32 trips x 32 chunks through shared memory: for a fixed chunk
-// consecutive trips are consecutive rows (coalesced reads), for a fixed trip consecutive chunks are
-// consecutive trip-ordered entries (coalesced writes).  BACKWARD folds x = x / D (ldu_solve :169) in.
+// natural order <-> trip order.  Tile of 32 trips x 32 chunks through shared memory: for a fixed chunk
+// consecutive trips are consecutive rows (coalesced in the natural order), for a fixed trip consecutive
+// chunks are consecutive trip-ordered entries.  IN: natural -> the rhs part of the slabs (BACKWARD folds
+// x = x / D, ldu_solve :169, in); OUT: trip-ordered solution -> natural.
 template <bool BACKWARD, bool OUT>
 __global__ void __launch_bounds__(256)
 sweep_transpose_kernel(const SweepArgs a, const double *__restrict__ src, const double *__restrict__ D,
@@ -403,7 +420,10 @@ sweep_transpose_kernel(const SweepArgs a, const double *__restrict__ src, const 
         for (int j = ty; j < 32; j += 8) {
             long long i0;
             const int t = t0 + j, v = v0 + tx;
-            if (row_of(t, v, &i0)) dst[a.trip[t].off + (v - a.trip[t].vlo)] = tile[tx][j];
+            if (row_of(t, v, &i0)) {
+                const SweepTrip T = a.trip[t];
+                reinterpret_cast<double *>(a.slab + slab_offset(T))[v - T.vlo] = tile[tx][j];
+            }
         }
     } else {
         for (int j = ty; j < 32; j += 8) {
@@ -419,6 +439,9 @@ sweep_transpose_kernel(const SweepArgs a, const double *__restrict__ src, const 
     }
 }
 
+// SHORT: every row has at most two entries and none is read from global memory (straight-line body);
+// otherwise the general loop.
+template <bool SHORT>
 __global__ void __launch_bounds__(1024, 1)
 sweep_static_kernel(const __grid_constant__ SweepArgs a, const int *skip)
 {
@@ -427,84 +450,107 @@ sweep_static_kernel(const __grid_constant__ SweepArgs a, const int *skip)
     if (skip != nullptr && *skip != 0) return;
     const int tid = threadIdx.x, nthreads = blockDim.x;
     double *ring = reinterpret_cast<double *>(smem + (size_t)a.nstage * a.stage_bytes);
-    const int o_val = 8 * a.w16_max, o_src = o_val + 8 * a.S_max * a.w16_max, o_cnt = o_src + 4 * a.S_max * a.w16_max;
     if (tid == 0) {
         for (int k = 0; k < a.nstage; k++) mbar_init(&mbar[k], 1);
         fence_mbar_init();
     }
     __syncthreads();
     const uint64_t policy = policy_evict_first();
-    auto issue = [&](int t, const SweepTrip &T) {
-        const int stage = t % a.nstage;
-        unsigned char *base = smem + (size_t)stage * a.stage_bytes;
-        const uint32_t w16 = (uint32_t)T.w16, S = (uint32_t)T.S;
-        mbar_expect_tx(&mbar[stage], w16 * 9u + S * w16 * 12u);
-        if (w16 == 0) return;
-        bulk_g2s(base, a.rhs + T.off, w16 * 8u, &mbar[stage], policy);
-        bulk_g2s(base + o_cnt, a.cnt + T.off, w16, &mbar[stage], policy);
-        if (S > 0) {
-            bulk_g2s(base + o_val, a.val + T.soff, S * w16 * 8u, &mbar[stage], policy);
-            bulk_g2s(base + o_src, a.src + T.soff, S * w16 * 4u, &mbar[stage], policy);
-        }
-    };
-    // Trip descriptors are read one trip before they are needed (by the producer thread for the trip it
-    // stages next, by everybody for the trip computed next): a global load at the head of a trip would
-    // sit on the critical path of all 2 N trips (first version: 1.05 us per trip; visit r2p).
-    int t_issue = 0;
+    // Warp 0 is the PRODUCER: its lane 0 programs one bulk copy per trip (descriptor read one trip earlier)
+    // and takes no rows.  With the producer's ~100 instructions in a warp that also owned rows, that warp
+    // was the last at every barrier: 800 of 1 585 cycles per trip (diagnostic build, visit r2u).
+    const bool producer = tid < 32;
+    const int ctid = tid - 32, ncompute = nthreads - 32;
+    int t_issue = 0, stage_issue = 0;
     SweepTrip T_issue = a.trip[0];
-    if (tid == 0) {
-        for (; t_issue < a.nstage - 1 && t_issue < a.trips; t_issue++) {
-            issue(t_issue, T_issue);
-            if (t_issue + 1 < a.trips) T_issue = a.trip[t_issue + 1];
-        }
-    }
+    auto issue = [&]() {
+        const uint32_t bytes = (uint32_t)T_issue.w16 * (9u + 12u * (uint32_t)T_issue.S);
+        mbar_expect_tx(&mbar[stage_issue], bytes);
+        if (bytes) bulk_g2s(smem + (size_t)stage_issue * a.stage_bytes, a.slab + slab_offset(T_issue), bytes, &mbar[stage_issue], policy);
+        t_issue++;
+        stage_issue = stage_issue + 1 == a.nstage ? 0 : stage_issue + 1;
+        if (t_issue < a.trips) T_issue = a.trip[t_issue];
+    };
+    if (tid == 0)
+        while (t_issue < a.nstage - 1 && t_issue < a.trips) issue();
     const int wmask = a.W - 1;
-    int4 d = __ldg(reinterpret_cast<const int4 *>(a.trip));                   // vlo, w, w16, S of trip 0
+    // compute threads: (vlo, w, w16, S) and the offset in xs of the trip computed next, read one trip earlier
+    int4 d = __ldg(reinterpret_cast<const int4 *>(a.trip));
     long long off = __ldg(&a.trip[0].off);
+    int stage = 0;
+    uint32_t parity = 0;
+#ifdef SIGB_SWEEP_STATS
+    long long c_issue = 0, c_wait = 0, c_rows = 0, c_bar = 0;
+    const long long c_begin = clock64();
+#define SWEEP_CLK(var) const long long var = clock64()
+#define SWEEP_ACC(acc, t1, t0) acc += (t1) - (t0)
+#else
+#define SWEEP_CLK(var)
+#define SWEEP_ACC(acc, t1, t0)
+#endif
     for (int t = 0; t < a.trips; t++) {
-        // the stage trip t - 1 used was released by the barrier that ended it
-        if (tid == 0 && t_issue < a.trips) {
-            issue(t_issue, T_issue);
-            t_issue++;
-            if (t_issue < a.trips) T_issue = a.trip[t_issue];
-        }
+        SWEEP_CLK(k0);
         int4 d_next = d;
         long long off_next = off;
-        if (t + 1 < a.trips) {
+        if (producer) {
+            // the stage trip t - 1 used was released by the barrier that ended it
+            if (tid == 0 && t_issue < a.trips) issue();
+        } else if (t + 1 < a.trips) {
             d_next = __ldg(reinterpret_cast<const int4 *>(a.trip + t + 1));
             off_next = __ldg(&a.trip[t + 1].off);
         }
-        const int stage = t % a.nstage;
-        mbar_wait(&mbar[stage], (uint32_t)(t / a.nstage) & 1u);
+        SWEEP_CLK(k1);
+        if (!producer) mbar_wait(&mbar[stage], parity);
+        SWEEP_CLK(k2);
+        const int w16 = d.z, S = d.w;
         const unsigned char *base = smem + (size_t)stage * a.stage_bytes;
         const double *s_rhs = reinterpret_cast<const double *>(base);
-        const double *s_val = reinterpret_cast<const double *>(base + o_val);
-        const int32_t *s_src = reinterpret_cast<const int32_t *>(base + o_src);
-        const unsigned char *s_cnt = base + o_cnt;
-        auto fetch = [&](int src) { return src >= 0 ? ring[src] : __ldcg(a.xs + (-(long long)src - 1)); };
-        for (int u = tid; u < d.y; u += nthreads) {
+        const double *s_val = s_rhs + w16;
+        const int32_t *s_src = reinterpret_cast<const int32_t *>(s_val + (size_t)S * w16);
+        const unsigned char *s_cnt = reinterpret_cast<const unsigned char *>(s_src + (size_t)S * w16);
+        for (int u = producer ? d.y : ctid; u < d.y; u += ncompute) {
             const int c = s_cnt[u];
-            if (c == kSweepNoRow) continue;
             double z = s_rhs[u];
-            int s = 0;
-            for (; s + 2 <= c; s += 2) {          // two slots at a time: their loads do not wait for each other
-                const int i0 = s_src[s * d.z + u], i1 = s_src[(s + 1) * d.z + u];
-                const double a0 = s_val[s * d.z + u], a1 = s_val[(s + 1) * d.z + u];
-                const double x0 = fetch(i0), x1 = fetch(i1);
-                z = sub(z, mul(a0, x0));
-                z = sub(z, mul(a1, x1));
+            if (SHORT) {
+                // padded slots carry ring index 0 and are not applied (z - 0 * x would turn -0 into +0)
+                const int i0 = S > 0 ? s_src[u] : 0, i1 = S > 1 ? s_src[w16 + u] : 0;
+                const double a0 = S > 0 ? s_val[u] : 0.0, a1 = S > 1 ? s_val[w16 + u] : 0.0;
+                const double x0 = ring[i0], x1 = ring[i1];
+                if (c == kSweepNoRow) continue;
+                if (c >= 1) z = sub(z, mul(a0, x0));
+                if (c >= 2) z = sub(z, mul(a1, x1));
+            } else {
+                if (c == kSweepNoRow) continue;
+                for (int s = 0; s < c; s++) {
+                    const int src = s_src[s * w16 + u];
+                    const double xj = src >= 0 ? ring[src] : __ldcg(a.xs + (-(long long)src - 1));
+                    z = sub(z, mul(s_val[s * w16 + u], xj));
+                }
             }
-            if (s < c) z = sub(z, mul(s_val[s * d.z + u], fetch(s_src[s * d.z + u])));
             const int v = d.x + u, p = t - a.sigma * v;
             a.xs[off + u] = z;
             ring[(p & wmask) * a.C + v] = z;
         }
+        SWEEP_CLK(k3);
         // (the stage is only READ through the generic proxy, so the barrier alone orders it before the
-        //  bulk copy that refills it)
+        //  bulk copy that refills it; the barrier also makes this trip's x visible to the CTA)
         __syncthreads();
+        SWEEP_CLK(k4);
         d = d_next;
         off = off_next;
+        if (++stage == a.nstage) { stage = 0; parity ^= 1u; }
+        SWEEP_ACC(c_issue, k1, k0);
+        SWEEP_ACC(c_wait, k2, k1);
+        SWEEP_ACC(c_rows, k3, k2);
+        SWEEP_ACC(c_bar, k4, k3);
     }
+#ifdef SIGB_SWEEP_STATS
+    if (tid == 0 || tid == 32 || tid == nthreads - 1)
+        printf("sweep %s thread %d of %d: trips %d, cycles per trip: issue+descriptors %.0f, wait for the stage %.0f, rows %.0f, "
+               "barrier %.0f, all %.0f\n", a.backward ? "B" : "F", tid, nthreads, a.trips, (double)c_issue / a.trips,
+               (double)c_wait / a.trips, (double)c_rows / a.trips, (double)c_bar / a.trips,
+               (double)(clock64() - c_begin) / a.trips);
+#endif
 }
 
 static SweepArgs sweep_args(const SweepDev &W)
@@ -512,7 +558,7 @@ static SweepArgs sweep_args(const SweepDev &W)
     SweepArgs a;
     a.n = W.n; a.backward = W.backward; a.R = W.R; a.sigma = W.sigma; a.C = W.C; a.trips = W.trips; a.W = W.W;
     a.S_max = W.S_max; a.w16_max = W.w16_max; a.nstage = W.nstage; a.stage_bytes = W.stage_bytes;
-    a.trip = W.trip; a.val = W.val; a.src = W.src; a.cnt = W.cnt; a.rhs = W.rhs; a.xs = W.xs;
+    a.trip = W.trip; a.slab = W.slab; a.xs = W.xs;
     return a;
 }
 
@@ -523,16 +569,19 @@ int launch_sweep_static(const SweepDev &W, const double *src, const double *D, d
     cudaStream_t st = ctx().stream;
     const SweepArgs a = sweep_args(W);
     const dim3 tg((unsigned)((W.trips + 31) / 32), (unsigned)((W.C + 31) / 32));
-    sweep_transpose_kernel<BACKWARD, false><<<tg, 256, 0, st>>>(a, src, D, W.rhs, skip);
+    sweep_transpose_kernel<BACKWARD, false><<<tg, 256, 0, st>>>(a, src, D, nullptr, skip);
     const size_t smem = (size_t)W.nstage * W.stage_bytes + (size_t)W.W * W.C * 8;
     static thread_local bool attr_set = false;   // per host thread = per device
     if (!attr_set) {
-        SIGB_CUDA(cudaFuncSetAttribute(sweep_static_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+        SIGB_CUDA(cudaFuncSetAttribute(sweep_static_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+        SIGB_CUDA(cudaFuncSetAttribute(sweep_static_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
         attr_set = true;
     }
-    static const int max_threads = env_int("SIGB_LDU_SWEEP_THREADS", 1024);
-    const int threads = std::max(32, std::min(W.threads, max_threads & ~31));
-    sweep_static_kernel<<<1, threads, smem, st>>>(a, skip);
+    // one producer warp + compute threads, each of which takes ceil(chunks / compute threads) rows per trip
+    static const int max_threads = env_int("SIGB_LDU_SWEEP_THREADS", 512);
+    const int threads = 32 + std::max(32, std::min(std::min(W.threads, 992), max_threads & ~31));
+    if (W.S_max <= 2 && !W.has_far) sweep_static_kernel<true><<<1, threads, smem, st>>>(a, skip);
+    else sweep_static_kernel<false><<<1, threads, smem, st>>>(a, skip);
     sweep_transpose_kernel<BACKWARD, true><<<tg, 256, 0, st>>>(a, W.xs, nullptr, x, skip);
     count_launch(3);
     SIGB_CUDA(cudaGetLastError());
@@ -545,34 +594,41 @@ static int upload_sweep(const SweepPlan &P, SweepDev &W)
     if (!P.eligible) return SIGB_OK;
     W.n = P.n; W.backward = P.backward; W.R = P.R; W.sigma = P.sigma; W.C = P.C; W.trips = P.trips; W.W = P.W;
     W.S_max = P.S_max; W.w16_max = P.w16_max; W.nstage = P.nstage; W.stage_bytes = P.stage_bytes; W.threads = P.threads;
-    W.total = P.total; W.total_s = P.total_s;
+    W.total = P.total; W.total_s = P.total_s; W.has_far = P.has_far;
     cudaStream_t st = ctx().stream;
     const size_t ts = (size_t)std::max<int64_t>(P.total_s, 1), tt = (size_t)std::max<int64_t>(P.total, 1);
+    int32_t *src = nullptr;
+    uint8_t *cnt = nullptr;
     SIGB_CUDA(cudaMalloc((void **)&W.trip, sizeof(SweepTrip) * P.trip.size()));
-    SIGB_CUDA(cudaMalloc((void **)&W.src, sizeof(int32_t) * ts));
-    SIGB_CUDA(cudaMalloc((void **)&W.cnt, tt));
     SIGB_CUDA(cudaMalloc((void **)&W.valmap, sizeof(int64_t) * ts));
-    SIGB_CUDA(cudaMalloc((void **)&W.val, sizeof(double) * ts));
-    SIGB_CUDA(cudaMalloc((void **)&W.rhs, sizeof(double) * tt));
+    SIGB_CUDA(cudaMalloc((void **)&W.slab, 9 * tt + 12 * ts));
     SIGB_CUDA(cudaMalloc((void **)&W.xs, sizeof(double) * tt));
-    SIGB_CUDA(cudaMemcpyAsync(W.trip, P.trip.data(), sizeof(SweepTrip) * P.trip.size(), cudaMemcpyHostToDevice, st));
-    if (P.total_s > 0) {
-        SIGB_CUDA(cudaMemcpyAsync(W.src, P.src.data(), sizeof(int32_t) * (size_t)P.total_s, cudaMemcpyHostToDevice, st));
-        SIGB_CUDA(cudaMemcpyAsync(W.valmap, P.valmap.data(), sizeof(int64_t) * (size_t)P.total_s, cudaMemcpyHostToDevice, st));
+    cudaError_t e = cudaMalloc((void **)&src, sizeof(int32_t) * ts);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&cnt, tt);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(W.trip, P.trip.data(), sizeof(SweepTrip) * P.trip.size(), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && P.total_s > 0) e = cudaMemcpyAsync(src, P.src.data(), sizeof(int32_t) * (size_t)P.total_s, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && P.total_s > 0) e = cudaMemcpyAsync(W.valmap, P.valmap.data(), sizeof(int64_t) * (size_t)P.total_s, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(cnt, P.cnt.data(), (size_t)P.total, cudaMemcpyHostToDevice, st);
+    // the padding of a trip's right-hand side / solution is staged and never used: defined values all the same
+    if (e == cudaSuccess) e = cudaMemsetAsync(W.slab, 0, 9 * tt + 12 * ts, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(W.xs, 0, sizeof(double) * tt, st);
+    if (e == cudaSuccess && P.trips > 0) {
+        sweep_pack_kernel<false><<<P.trips, kThreads, 0, st>>>(W.trip, W.valmap, src, cnt, nullptr, W.slab);
+        count_launch();
+        e = cudaGetLastError();
     }
-    SIGB_CUDA(cudaMemcpyAsync(W.cnt, P.cnt.data(), (size_t)P.total, cudaMemcpyHostToDevice, st));
-    // padding of a trip's right-hand side / solution is staged and never used: defined values all the same
-    SIGB_CUDA(cudaMemsetAsync(W.rhs, 0, sizeof(double) * tt, st));
-    SIGB_CUDA(cudaMemsetAsync(W.xs, 0, sizeof(double) * tt, st));
-    SIGB_CUDA(cudaStreamSynchronize(st));    // the plan's host vectors go out of scope in the caller
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);    // the plan's host vectors go out of scope in the caller
+    cudaFree(src);
+    cudaFree(cnt);
+    if (e != cudaSuccess) return cuda_fail(e, "ldu sweep plan upload", __FILE__, __LINE__);
     W.on = true;
     return SIGB_OK;
 }
 
 static int pack_sweep(const SweepDev &W, const double *fac_part)
 {
-    if (!W.on || W.total_s == 0) return SIGB_OK;
-    sweep_pack_kernel<<<grid_for(W.total_s), kThreads, 0, ctx().stream>>>(W.valmap, fac_part, W.total_s, W.val);
+    if (!W.on || W.total_s == 0 || W.trips == 0) return SIGB_OK;
+    sweep_pack_kernel<true><<<W.trips, kThreads, 0, ctx().stream>>>(W.trip, W.valmap, nullptr, nullptr, fac_part, W.slab);
     count_launch();
     SIGB_CUDA(cudaGetLastError());
     return SIGB_OK;

@@ -226,6 +226,7 @@ void build_sweep_plan(int32_t n, const int32_t *ptr1, const int32_t *node1, int 
         if (nstage >= 2) break;
     }
     if (W < 2 || nstage < 2) return;
+    P.has_far = dmax + 1 > W ? 1 : 0;
     P.W = (int32_t)W;
     P.nstage = (int32_t)nstage;
     P.stage_bytes = (int32_t)stage;
@@ -265,7 +266,7 @@ void build_sweep_plan(int32_t n, const int32_t *ptr1, const int32_t *node1, int 
 extern "C" {
 
 // Diagnostic / test entry (no GPU): the plan of a statically scheduled sweep.  info[16] = eligible, R,
-// sigma, C, trips, W, S_max, w16_max, nstage, stage_bytes, threads, total (lo, hi), total_s (lo, hi), n.
+// sigma, C, trips, W, S_max, w16_max, nstage, stage_bytes, threads, total (lo, hi), total_s (lo, hi), has_far.
 // The arrays may be null (first call: sizes); trip_table is trips x 8 int32 (vlo, w, w16, S, off lo / hi,
 // soff lo / hi), src and valmap total_s, cnt total.
 int sigb_debug_ldu_sweep_plan(int32_t n, const int32_t *ptr1, const int32_t *node1, int backward, int64_t levels,
@@ -277,7 +278,7 @@ int sigb_debug_ldu_sweep_plan(int32_t n, const int32_t *ptr1, const int32_t *nod
     build_sweep_plan(n, ptr1, node1, backward, levels, P);
     const int32_t vals[16] = {P.eligible ? 1 : 0, P.R, P.sigma, P.C, P.trips, P.W, P.S_max, P.w16_max, P.nstage,
                               P.stage_bytes, P.threads, (int32_t)(P.total & 0xffffffff), (int32_t)(P.total >> 32),
-                              (int32_t)(P.total_s & 0xffffffff), (int32_t)(P.total_s >> 32), P.n};
+                              (int32_t)(P.total_s & 0xffffffff), (int32_t)(P.total_s >> 32), P.has_far};
     for (int k = 0; k < 16; k++) info[k] = vals[k];
     if (!P.eligible) return SIGB_OK;
     if (trip_table)

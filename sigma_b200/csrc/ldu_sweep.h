@@ -9,8 +9,8 @@
 // nine-point stencil).  R is chosen among the offsets the pattern uses and its bandwidth for the fewest
 // trips, R + sigma (C - 1).  The whole sweep is ONE CTA: one thread per
 // chunk, one barrier per trip, finished values handed on through a shared-memory ring of the last
-// few positions of every chunk; the per-trip slices of the factor are stored in trip order
-// (contiguous per trip), so the TMA engine streams them into shared memory a few trips ahead.  Nothing
+// few positions of every chunk; everything a trip reads is stored as one contiguous slab per trip,
+// which the TMA engine brings into shared memory a few trips ahead.  Nothing
 // is polled: the schedule is proven valid on the host for the pattern at hand, otherwise the plan
 // is not eligible and ldu.cu keeps its other forms.
 #pragma once
@@ -35,6 +35,7 @@ struct SweepPlan {
     int32_t W = 0;                 // ring depth (positions kept per chunk)
     int32_t S_max = 0, w16_max = 0;
     int32_t nstage = 0, stage_bytes = 0, threads = 0;
+    int32_t has_far = 0;           // some entries are read from the trip-ordered solution in global memory
     int64_t total = 0, total_s = 0;
     std::vector<SweepTrip> trip;
     std::vector<int32_t> src;      // >= 0: ring index (p' mod W) * C + v' ; < 0: -(1 + index into the trip-ordered x)

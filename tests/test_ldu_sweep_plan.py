@@ -36,6 +36,7 @@ def sweep_plan(n, p, nd, backward, levels):
     P = dict(zip(keys, (int(v) for v in info[:11])))
     P["total"] = int(np.uint32(info[11])) | (int(info[12]) << 32)
     P["total_s"] = int(np.uint32(info[13])) | (int(info[14]) << 32)
+    P["has_far"] = int(info[15])
     if not P["eligible"]:
         return P
     trip = np.zeros((P["trips"], 8), np.int32)
@@ -79,6 +80,8 @@ def replay(n, p, nd, val, rhs, backward, P):
                 rhs_s[off + u] = rhs[row_of(q)]
     xs = np.full(total, np.nan)
     xs_row = np.full(total, -1, np.int64)
+    xs_trip = np.full(total, -1, np.int64)
+    far_seen = False
     ring = np.full(W * Cn, np.nan)
     ring_row = np.full(W * Cn, -1, np.int64)
     seen = np.zeros(n, bool)
@@ -110,17 +113,20 @@ def replay(n, p, nd, val, rhs, backward, P):
                     xj = ring[d]
                 else:
                     assert xs_row[-d - 1] == j0, "trip-ordered entry does not hold the entry the serial loop reads"
+                    assert t - xs_trip[-d - 1] >= W, "far entry within reach of the ring"
+                    far_seen = True
                     xj = xs[-d - 1]
                 z = z - val[k] * xj
             out.append((u, v, pp, i0, z))
         for u, v, pp, i0, z in out:              # ... then all write (one barrier per trip)
             xs[off + u] = z
             xs_row[off + u] = i0
+            xs_trip[off + u] = t
             ring[(pp % W) * Cn + v] = z
             ring_row[(pp % W) * Cn + v] = i0
             assert not seen[i0]
             seen[i0] = True
-    assert seen.all()
+    assert seen.all() and far_seen == bool(P["has_far"])
     x = np.empty(n)
     for t in range(P["trips"]):
         vlo, w = int(trip[t, 0]), int(trip[t, 1])
