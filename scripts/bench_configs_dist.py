@@ -218,8 +218,10 @@ def main():
                  spmv_gbs=b_spmv / t_spmv / 1e9, spmv_frac_of_hbm=b_spmv / t_spmv / 1e9 / (hbm * world),
                  halo_per_rank=int(A.plan.halo.size), gen_seconds=gen_s,
                  transport=comm.transport if world > 1 else "none", cpu_baseline_spmv=cpu,
-                 note="random columns: every gathered x entry costs a 32-byte sector, so the algorithmic-byte "
-                      "fraction is bounded near 12/(12+32) even at full DRAM rate")
+                 note="random columns: gather-bound, not stream-bound -- with x (160 MB) beyond the L2 every gathered "
+                      "entry costs a 64-byte DRAM access (ncu: 61.8 B per gather) and a B200 serves 96 G such gathers/s "
+                      "to a kernel that does nothing else (profiles/r2_gather_probe.jsonl): 12 algorithmic bytes per "
+                      "entry against 12 + 64 moved bound the fraction near 0.16 of HBM per GPU")
             s.destroy(); A.destroy()
             del xd, fd, x, y
 

@@ -41,7 +41,7 @@ struct SweepDev {
     int32_t nstage = 0, stage_bytes = 0, threads = 0, has_far = 0;
     int64_t total = 0, total_s = 0;
     SweepTrip *trip = nullptr;
-    int64_t *valmap = nullptr;              // entry of the factor behind every slot (-1: padding)
+    int32_t *valmap = nullptr;              // entry of the factor behind every slot (-1: padding)
     unsigned char *slab = nullptr;          // what the trips read, trip by trip (sweep_static_kernel)
     double *xs = nullptr;                   // the solution in trip order
     void release()
@@ -363,26 +363,61 @@ struct SweepArgs {
 
 __device__ __forceinline__ long long slab_offset(const SweepTrip &T) { return 9ll * T.off + 12ll * T.soff; }
 
-// static parts of the slabs (src, cnt: once per pattern) and the values (every factorisation); one CTA per trip
-template <bool VALUES>
+// The slots of a trip, from the device-resident pattern of the factor (one CTA per trip; the statements of
+// build_sweep_plan's slot loop, ldu_host.cpp -- which tests/test_ldu_sweep_plan.py replays on the CPU):
+// row length and ring slot / far index of every entry into the slab, the entry's position in the factor
+// into valmap.  Once per pattern.
 __global__ void __launch_bounds__(kThreads)
-sweep_pack_kernel(const SweepTrip *__restrict__ trip, const int64_t *__restrict__ valmap, const int32_t *__restrict__ src,
-                  const uint8_t *__restrict__ cnt, const double *__restrict__ fac, unsigned char *__restrict__ slab)
+sweep_slots_kernel(const SweepArgs a, const int32_t *__restrict__ ptr1, const int32_t *__restrict__ node1,
+                   int32_t *__restrict__ valmap)
+{
+    const int t = blockIdx.x;
+    const SweepTrip T = a.trip[t];
+    unsigned char *base = a.slab + slab_offset(T);
+    int32_t *d_src = reinterpret_cast<int32_t *>(base + 8ll * T.w16 * (1 + T.S));
+    unsigned char *d_cnt = base + 8ll * T.w16 * (1 + T.S) + 4ll * T.S * T.w16;
+    for (int u = threadIdx.x; u < T.w16; u += kThreads) {
+        const long long v = T.vlo + u, p = (long long)t - (long long)a.sigma * v, q = v * a.R + p;
+        int c = kSweepNoRow;
+        if (u < T.w && q < a.n) {
+            const int i = a.backward ? (int)(a.n - q) : (int)(q + 1);          // 1-based row at sweep position q
+            const int kb = ptr1[i - 1] - 1;
+            c = ptr1[i] - 1 - kb;
+            for (int s = 0; s < c; s++) {
+                const int j = node1[kb + s];
+                const long long q2 = a.backward ? (long long)a.n - j : (long long)j - 1;
+                const long long v2 = q2 / a.R, p2 = q2 % a.R, t2 = p2 + (long long)a.sigma * v2;
+                const long long d = t - t2;                                    // >= 1: finished in an earlier trip
+                int src;
+                if (d < a.W) {
+                    src = (int)((p2 & (a.W - 1)) * a.C + v2);
+                } else {
+                    const SweepTrip T2 = a.trip[t2];
+                    src = -(int)(1 + T2.off + (v2 - T2.vlo));
+                }
+                d_src[s * T.w16 + u] = src;
+                valmap[T.soff + (long long)s * T.w16 + u] = kb + s;
+            }
+        }
+        for (int s = (c == kSweepNoRow ? 0 : c); s < T.S; s++) {               // padding: ring slot 0, no entry
+            d_src[s * T.w16 + u] = 0;
+            valmap[T.soff + (long long)s * T.w16 + u] = -1;
+        }
+        d_cnt[u] = (unsigned char)c;
+    }
+}
+
+// the factor's values into the slabs (every factorisation); one CTA per trip
+__global__ void __launch_bounds__(kThreads)
+sweep_pack_kernel(const SweepTrip *__restrict__ trip, const int32_t *__restrict__ valmap, const double *__restrict__ fac,
+                  unsigned char *__restrict__ slab)
 {
     const SweepTrip T = trip[blockIdx.x];
-    unsigned char *base = slab + slab_offset(T);
+    double *val = reinterpret_cast<double *>(slab + slab_offset(T) + 8ll * T.w16);
     const int nslots = T.S * T.w16;
-    if (VALUES) {
-        double *val = reinterpret_cast<double *>(base + 8ll * T.w16);
-        for (int k = threadIdx.x; k < nslots; k += kThreads) {
-            const int64_t m = valmap[T.soff + k];
-            val[k] = m >= 0 ? fac[m] : 0.0;
-        }
-    } else {
-        int32_t *d_src = reinterpret_cast<int32_t *>(base + 8ll * T.w16 * (1 + T.S));
-        unsigned char *d_cnt = base + 8ll * T.w16 * (1 + T.S) + 4ll * nslots;
-        for (int k = threadIdx.x; k < nslots; k += kThreads) d_src[k] = src[T.soff + k];
-        for (int k = threadIdx.x; k < T.w16; k += kThreads) d_cnt[k] = cnt[T.off + k];
+    for (int k = threadIdx.x; k < nslots; k += kThreads) {
+        const int32_t m = valmap[T.soff + k];
+        val[k] = m >= 0 ? fac[m] : 0.0;
     }
 }
 
@@ -588,7 +623,8 @@ int launch_sweep_static(const SweepDev &W, const double *src, const double *D, d
     return SIGB_OK;
 }
 
-static int upload_sweep(const SweepPlan &P, SweepDev &W)
+// plan -> device: the trip table is uploaded, the slots are computed here from the device-resident pattern
+static int upload_sweep(const SweepPlan &P, const int32_t *ptr1_dev, const int32_t *node1_dev, SweepDev &W)
 {
     W = SweepDev();
     if (!P.eligible) return SIGB_OK;
@@ -597,30 +633,20 @@ static int upload_sweep(const SweepPlan &P, SweepDev &W)
     W.total = P.total; W.total_s = P.total_s; W.has_far = P.has_far;
     cudaStream_t st = ctx().stream;
     const size_t ts = (size_t)std::max<int64_t>(P.total_s, 1), tt = (size_t)std::max<int64_t>(P.total, 1);
-    int32_t *src = nullptr;
-    uint8_t *cnt = nullptr;
     SIGB_CUDA(cudaMalloc((void **)&W.trip, sizeof(SweepTrip) * P.trip.size()));
-    SIGB_CUDA(cudaMalloc((void **)&W.valmap, sizeof(int64_t) * ts));
+    SIGB_CUDA(cudaMalloc((void **)&W.valmap, sizeof(int32_t) * ts));
     SIGB_CUDA(cudaMalloc((void **)&W.slab, 9 * tt + 12 * ts));
     SIGB_CUDA(cudaMalloc((void **)&W.xs, sizeof(double) * tt));
-    cudaError_t e = cudaMalloc((void **)&src, sizeof(int32_t) * ts);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&cnt, tt);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(W.trip, P.trip.data(), sizeof(SweepTrip) * P.trip.size(), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess && P.total_s > 0) e = cudaMemcpyAsync(src, P.src.data(), sizeof(int32_t) * (size_t)P.total_s, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess && P.total_s > 0) e = cudaMemcpyAsync(W.valmap, P.valmap.data(), sizeof(int64_t) * (size_t)P.total_s, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(cnt, P.cnt.data(), (size_t)P.total, cudaMemcpyHostToDevice, st);
+    SIGB_CUDA(cudaMemcpyAsync(W.trip, P.trip.data(), sizeof(SweepTrip) * P.trip.size(), cudaMemcpyHostToDevice, st));
     // the padding of a trip's right-hand side / solution is staged and never used: defined values all the same
-    if (e == cudaSuccess) e = cudaMemsetAsync(W.slab, 0, 9 * tt + 12 * ts, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(W.xs, 0, sizeof(double) * tt, st);
-    if (e == cudaSuccess && P.trips > 0) {
-        sweep_pack_kernel<false><<<P.trips, kThreads, 0, st>>>(W.trip, W.valmap, src, cnt, nullptr, W.slab);
+    SIGB_CUDA(cudaMemsetAsync(W.slab, 0, 9 * tt + 12 * ts, st));
+    SIGB_CUDA(cudaMemsetAsync(W.xs, 0, sizeof(double) * tt, st));
+    if (P.trips > 0) {
+        sweep_slots_kernel<<<P.trips, kThreads, 0, st>>>(sweep_args(W), ptr1_dev, node1_dev, W.valmap);
         count_launch();
-        e = cudaGetLastError();
+        SIGB_CUDA(cudaGetLastError());
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);    // the plan's host vectors go out of scope in the caller
-    cudaFree(src);
-    cudaFree(cnt);
-    if (e != cudaSuccess) return cuda_fail(e, "ldu sweep plan upload", __FILE__, __LINE__);
+    SIGB_CUDA(cudaStreamSynchronize(st));    // the plan's trip table goes out of scope in the caller
     W.on = true;
     return SIGB_OK;
 }
@@ -628,7 +654,7 @@ static int upload_sweep(const SweepPlan &P, SweepDev &W)
 static int pack_sweep(const SweepDev &W, const double *fac_part)
 {
     if (!W.on || W.total_s == 0 || W.trips == 0) return SIGB_OK;
-    sweep_pack_kernel<true><<<W.trips, kThreads, 0, ctx().stream>>>(W.trip, W.valmap, nullptr, nullptr, fac_part, W.slab);
+    sweep_pack_kernel<<<W.trips, kThreads, 0, ctx().stream>>>(W.trip, W.valmap, fac_part, W.slab);
     count_launch();
     SIGB_CUDA(cudaGetLastError());
     return SIGB_OK;
@@ -770,15 +796,6 @@ int ldu_setup_dev(sigb_solver_t s, sigb_matrix_t A)
             F->blev.assign(blev.begin(), blev.begin() + nb + 1);
             choose_chunking(F, Lptr, Lnode, Uptr, Unode);
             // statically scheduled sweeps where the pattern has a wavefront (both sweeps or neither)
-            if (env_int("SIGB_LDU_STATIC", 1) != 0) {
-                SweepPlan Pf, Pb;
-                build_sweep_plan(n, Lptr.data(), Lnode.data(), 0, (int64_t)nf, Pf);
-                if (Pf.eligible) build_sweep_plan(n, Uptr.data(), Unode.data(), 1, (int64_t)nb, Pb);
-                if (Pf.eligible && Pb.eligible) {
-                    rc = upload_sweep(Pf, F->fsw);
-                    if (rc == SIGB_OK) rc = upload_sweep(Pb, F->bsw);
-                }
-            }
             rc = upload(&F->Lptr, Lptr.data(), (size_t)n + 1);
             if (rc == SIGB_OK) rc = upload(&F->Uptr, Uptr.data(), (size_t)n + 1);
             if (rc == SIGB_OK) rc = upload(&F->Lnode, Lnode.data(), (size_t)F->nL);
@@ -786,6 +803,17 @@ int ldu_setup_dev(sigb_solver_t s, sigb_matrix_t A)
             if (rc == SIGB_OK) rc = upload(&F->dest, dest.data(), (size_t)ne);
             if (rc == SIGB_OK) rc = upload(&F->frows, frows.data(), (size_t)n);
             if (rc == SIGB_OK) rc = upload(&F->brows, brows.data(), (size_t)n);
+            // statically scheduled sweeps where the pattern has a wavefront (both sweeps or neither): schedules
+            // on the host, slots on the device from the patterns just uploaded
+            if (rc == SIGB_OK && env_int("SIGB_LDU_STATIC", 1) != 0) {
+                SweepPlan Pf, Pb;
+                build_sweep_plan(n, Lptr.data(), Lnode.data(), 0, (int64_t)nf, Pf, false);
+                if (Pf.eligible) build_sweep_plan(n, Uptr.data(), Unode.data(), 1, (int64_t)nb, Pb, false);
+                if (Pf.eligible && Pb.eligible) {
+                    rc = upload_sweep(Pf, F->Lptr, F->Lnode, F->fsw);
+                    if (rc == SIGB_OK) rc = upload_sweep(Pb, F->Uptr, F->Unode, F->bsw);
+                }
+            }
             if (rc == SIGB_OK) {
                 cudaError_t e2 = cudaMalloc((void **)&F->fac, sizeof(double) * (size_t)(F->nL + F->nU + n + 1));
                 if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(st);   // the host vectors go out of scope below

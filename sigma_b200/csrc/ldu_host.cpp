@@ -111,7 +111,7 @@ int sigb_ldu_symbolic(int32_t n, const int32_t *ptr1, const int32_t *node1, int3
 namespace sigb {
 
 void build_sweep_plan(int32_t n, const int32_t *ptr1, const int32_t *node1, int backward, int64_t levels,
-                      SweepPlan &P)
+                      SweepPlan &P, bool fill_slots)
 {
     P = SweepPlan();
     P.n = n;
@@ -232,7 +232,12 @@ void build_sweep_plan(int32_t n, const int32_t *ptr1, const int32_t *node1, int 
     P.stage_bytes = (int32_t)stage;
     P.threads = (int32_t)std::min<int64_t>(1024, (C + 31) & ~(int64_t)31);
 
-    // slots
+    // slots: ldu.cu fills them on the device from the device-resident factor pattern (sweep_slots_kernel, the
+    // same statements); the host copy is for the tests
+    if (!fill_slots) {
+        P.eligible = true;
+        return;
+    }
     P.src.assign((size_t)soff, 0);
     P.valmap.assign((size_t)soff, -1);
     P.cnt.assign((size_t)off, kSweepNoRow);
@@ -275,7 +280,7 @@ int sigb_debug_ldu_sweep_plan(int32_t n, const int32_t *ptr1, const int32_t *nod
     SIGB_REQUIRE(n >= 0 && ptr1 && info && (n == 0 || ptr1[n] == 1 || node1), SIGB_ERR_ARG,
                  "sigb_debug_ldu_sweep_plan: bad argument");
     SweepPlan P;
-    build_sweep_plan(n, ptr1, node1, backward, levels, P);
+    build_sweep_plan(n, ptr1, node1, backward, levels, P, true);
     const int32_t vals[16] = {P.eligible ? 1 : 0, P.R, P.sigma, P.C, P.trips, P.W, P.S_max, P.w16_max, P.nstage,
                               P.stage_bytes, P.threads, (int32_t)(P.total & 0xffffffff), (int32_t)(P.total >> 32),
                               (int32_t)(P.total_s & 0xffffffff), (int32_t)(P.total_s >> 32), P.has_far};

@@ -41,6 +41,7 @@ struct SweepPlan {
     std::vector<int32_t> src;      // >= 0: ring index (p' mod W) * C + v' ; < 0: -(1 + index into the trip-ordered x)
     std::vector<uint8_t> cnt;      // entries of the row; 0xFF: no row at this (trip, chunk)
     std::vector<int64_t> valmap;   // entry of the factor's value array behind every slot, -1 = padding
+                                   // (src / cnt / valmap: filled on request only -- the device builds its own)
 };
 
 constexpr int kSweepMaxChunks = 4096;
@@ -49,7 +50,8 @@ constexpr uint8_t kSweepNoRow = 0xFF;
 
 // ptr1 / node1: the rows of the strictly triangular factor (1-based).  backward = 0: positions are rows
 // ascending (L); 1: rows descending (U).  levels: depth of the level schedule of the same sweep.
+// fill_slots = false: schedule and trip table only (src / cnt / valmap stay empty).
 void build_sweep_plan(int32_t n, const int32_t *ptr1, const int32_t *node1, int backward, int64_t levels,
-                      SweepPlan &P);
+                      SweepPlan &P, bool fill_slots);
 
 }  // namespace sigb
