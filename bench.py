@@ -533,7 +533,7 @@ def run_ours(args):
             "parity": parity,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic,
-                         "kernel": "csr_tma_kernel<MODE_SET,NDOT=1,HALO=%d> (q = A p fused with p.q)" % (1 if world > 1 else 0),
+                         "kernel": "csr_tma_kernel<MODE_SET,NDOT=1,HALO=%d,TileCfg<2048>> (q = A p fused with p.q)" % (1 if world > 1 else 0),
                          "bytes_per_launch": bytes_spmv, "us_per_launch": ms_spmv_dot * 1e3,
                          "peak_source": peak_src},
             "spmv": {"gbs": bytes_spmv / (ms_spmv * 1e-3) / 1e9 * (world if world > 1 else 1),
