@@ -93,22 +93,18 @@ ldu_scatter_kernel(const double *__restrict__ aval, const int64_t *__restrict__ 
         fac[dest[e]] = aval[e];
 }
 
-// M%get_value(i, j) on a csr pattern: last hit wins, 0 when absent (cs_matrices.f90:709-724).
-// L2: the values are read at L2 (rows finished by other threads of a running kernel, see factor_row).
-template <bool L2>
+// M%get_value(i, j) on a csr pattern: last hit wins, 0 when absent (cs_matrices.f90:709-724)
 __device__ __forceinline__ double get_value(const int32_t *ptr1, const int32_t *node1, const double *val, int32_t i,
                                             int32_t j)
 {
     double z = 0.0;
     for (int32_t k = ptr1[i - 1] - 1; k < ptr1[i] - 1; k++)
-        if (node1[k] == j) z = L2 ? __ldcg(val + k) : val[k];
+        if (node1[k] == j) z = val[k];
     return z;
 }
 
-// One row of the elimination (:331-381).  Reads rows k < i of U and D(k) for the lower neighbours k of i --
-// finished by an earlier launch (L2 = false: one launch per level) or by another thread of the SAME launch in
-// an earlier trip (L2 = true: those values are read at L2, the row's own entries through the normal path).
-template <bool L2>
+// One row of the elimination (:331-381).  Reads rows k < i of U and D(k) for the lower neighbours k of i,
+// finished by an earlier launch.
 __device__ __forceinline__ void factor_row(int32_t i, const int32_t *__restrict__ Lptr, const int32_t *__restrict__ Lnode,
                                            double *Lval, const int32_t *__restrict__ Uptr,
                                            const int32_t *__restrict__ Unode, double *Uval, double *D)
@@ -118,22 +114,22 @@ __device__ __forceinline__ void factor_row(int32_t i, const int32_t *__restrict_
     for (int32_t ind1 = 0; ind1 < dl; ind1++) {
         const int32_t k = Lnode[lb + ind1];
         double Lik = Lval[lb + ind1];                                  // L%get_value(i, k)   :342
-        const double Uki = get_value<L2>(Uptr, Unode, Uval, k, i);     // :343
-        const double Dk = L2 ? __ldcg(D + (k - 1)) : D[k - 1];
+        const double Uki = get_value(Uptr, Unode, Uval, k, i);     // :343
+        const double Dk = D[k - 1];
         Lik = Lik / Dk;                                                // :345-346
         Lval[lb + ind1] = Lik;
         const double LikDk = mul(Lik, Dk);
         for (int32_t ind2 = 0; ind2 < dl; ind2++) {                    // :350-358
             const int32_t j = Lnode[lb + ind2];
             if (j > k) {
-                const double Ukj = get_value<L2>(Uptr, Unode, Uval, k, j);
+                const double Ukj = get_value(Uptr, Unode, Uval, k, j);
                 Lval[lb + ind2] = add(Lval[lb + ind2], -mul(LikDk, Ukj));
             }
         }
         D[i - 1] = sub(D[i - 1], mul(LikDk, Uki));                     // :361
         for (int32_t ind2 = 0; ind2 < du; ind2++) {                    // :364-368
             const int32_t j = Unode[ub + ind2];
-            const double Ukj = get_value<L2>(Uptr, Unode, Uval, k, j);
+            const double Ukj = get_value(Uptr, Unode, Uval, k, j);
             Uval[ub + ind2] = add(Uval[ub + ind2], -mul(LikDk, Ukj));
         }
     }
@@ -148,26 +144,7 @@ ldu_factor_level_kernel(const int32_t *__restrict__ rows, int32_t count, const i
                         const int32_t *__restrict__ Unode, double *Uval, double *D)
 {
     for (int32_t t = blockIdx.x * kThreads + threadIdx.x; t < count; t += gridDim.x * kThreads)
-        factor_row<false>(rows[t], Lptr, Lnode, Lval, Uptr, Unode, Uval, D);
-}
-
-// The elimination on the schedule of the statically scheduled FORWARD sweep (ldu_sweep.h): row i needs the
-// rows k < i among its lower neighbours -- exactly the dependencies that schedule was proven for -- so ONE CTA
-// runs all rows, thread v taking the row at position t - sigma * v of chunk v in trip t, a barrier per trip
-// (which also makes the finished rows visible to the CTA).  2 N - 1 trips instead of 2 N - 1 launches.
-__global__ void __launch_bounds__(1024, 1)
-ldu_factor_static_kernel(int32_t n, int32_t R, int32_t sigma, int32_t C, int32_t trips, const int32_t *__restrict__ Lptr,
-                         const int32_t *__restrict__ Lnode, double *Lval, const int32_t *__restrict__ Uptr,
-                         const int32_t *__restrict__ Unode, double *Uval, double *D)
-{
-    for (int32_t t = 0; t < trips; t++) {
-        const int32_t vlo = max(0, (t - (R - 1) + sigma - 1) / sigma), vhi = min(C - 1, t / sigma);
-        for (int32_t v = vlo + (int32_t)threadIdx.x; v <= vhi; v += (int32_t)blockDim.x) {
-            const long long q = (long long)v * R + (t - (long long)sigma * v);
-            if (q < n) factor_row<true>((int32_t)q + 1, Lptr, Lnode, Lval, Uptr, Unode, Uval, D);
-        }
-        __syncthreads();
-    }
+        factor_row(rows[t], Lptr, Lnode, Lval, Uptr, Unode, Uval, D);
 }
 
 // rows of one level of lower_/upper_triangular_solve (:226-235, :254-263):
@@ -865,17 +842,10 @@ int ldu_setup_dev(sigb_solver_t s, sigb_matrix_t A)
         ldu_scatter_kernel<<<grid_for(F->ne), kThreads, 0, st>>>(R->val, F->dest, F->ne, F->fac);
         count_launch();
     }
-    // the elimination: on the forward sweep's static schedule where the pattern has one (one launch), else
-    // level by level
-    const bool factor_static = F->fsw.on && env_int("SIGB_LDU_STATIC_FACTOR", 1) != 0;
-    if (factor_static) {
-        const SweepDev &W = F->fsw;
-        ldu_factor_static_kernel<<<1, std::max(32, std::min(W.threads, 1024)), 0, st>>>(n, W.R, W.sigma, W.C, W.trips, F->Lptr,
-                                                                                       F->Lnode, F->Lval(), F->Uptr, F->Unode,
-                                                                                       F->Uval(), F->D());
-        count_launch();
-    }
-    const int nlev = factor_static ? 0 : (int)F->flev.size() - 1;
+    // the elimination, level by level.  (Run on the forward sweep's static schedule as ONE CTA -- the same
+    // dependencies -- it was no faster: 29.8 vs 28.4 ms at 1024^2, 113 vs 62 ms at 2048^2, a row of the
+    // elimination being ~10x the instructions of a row of the sweep on one SM; visit r2y.)
+    const int nlev = (int)F->flev.size() - 1;
     for (int l = 0; l < nlev; l++) {
         const int32_t b = F->flev[(size_t)l], cnt = F->flev[(size_t)l + 1] - b;
         ldu_factor_level_kernel<<<grid_for(cnt), kThreads, 0, st>>>(F->frows + b, cnt, F->Lptr, F->Lnode, F->Lval(),
