@@ -494,7 +494,12 @@ SIGB_API int sigb_comm_info(sigb_comm_t comm, int *rank, int *nranks,
  * MPI_Alltoallv ...; sigma_b200/distributed.py shows it) -- "graph-derived"
  * index work, no values involved.  The library splits the rows into interior
  * and boundary tiles and mirrors the renumbered local CSR on the device.
- * Values are uploaded with sigb_matrix_set_values (the block's val slice). */
+ * Values are uploaded with sigb_matrix_set_values (the block's val slice).
+ * The resulting operator takes the vectors' OWNED slices in sigb_matvec /
+ * sigb_matvec_add, sigb_solver_* (cg, bicgstab, jacobi), sigb_lanczos[_dev] and
+ * sigb_eigensolve (the sign convention V(1, i) > 0 is taken from the rank that owns
+ * global row 1); matvec_t, copies, expressions and ldu refuse it
+ * (SIGB_ERR_UNSUPPORTED). */
 SIGB_API int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global,
                                   const int32_t *part, const int32_t *ptr_blk1,
                                   const int32_t *node_glob1,

@@ -931,7 +931,7 @@ static int lanczos_common(sigb_matrix_t A, int32_t n, const double *q1, uint64_t
         LZ_TRY(dev_alloc(&V2, (size_t)nr * n));
         LZ_TRY(dev_alloc(&small, (size_t)n * n + n));
         LZ_CUDA(cudaMemcpyAsync(small, Z.data(), sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, st));
-        LZ_TRY(ritz_vectors_dev(Qd, V2, small, nr, n, B ? nullptr : small + (size_t)n * n));
+        LZ_TRY(ritz_vectors_dev(A, Qd, V2, small, nr, n, B ? nullptr : small + (size_t)n * n));
         if (lambda) memcpy(lambda, d.data(), sizeof(double) * (size_t)n);
     }
     if (Q) LZ_CUDA(cudaMemcpyAsync(Q, Qd, sizeof(double) * (size_t)nr * n, cudaMemcpyDeviceToHost, st));
@@ -984,7 +984,6 @@ int sigb_eigensolve(sigb_matrix_t A, int32_t n, const double *q1, uint64_t seed,
 {
     if (A && A->mg) { ::sigb::set_error("sigb_eigensolve: not available for a single-process multi-GPU operator"); return SIGB_ERR_UNSUPPORTED; }
     SIGB_REQUIRE(lambda && V, SIGB_ERR_ARG, "sigb_eigensolve: lambda and V are required");
-    SIGB_REQUIRE(!(A && A->dist), SIGB_ERR_UNSUPPORTED, "sigb_eigensolve on a row-sharded operator");
     return lanczos_common(A, n, q1, seed, nullptr, V, lambda, true);
 }
 

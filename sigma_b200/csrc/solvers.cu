@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include "krylov.cuh"
+#include "dist.h"
 #include "solvers.h"
 
 namespace sigb {
@@ -1305,7 +1306,10 @@ int tridiag_eig_host(int n, double *d, double *e, double *Z)
 
 size_t kstate_bytes() { return sizeof(KState); }
 
-int ritz_vectors_dev(double *V, double *V2, const double *Qm_dev, int64_t nr, int32_t n,
+// A: the operator the vectors belong to -- on a row-sharded operator the first row of V lives on the rank
+// that owns global row 1; the other ranks contribute zeros and the n entries are summed across the ranks
+// (exact: x + 0), so that every rank scales by the same signs.
+int ritz_vectors_dev(sigb_matrix_t A, double *V, double *V2, const double *Qm_dev, int64_t nr, int32_t n,
                      double *first_row_dev)
 {
     cudaStream_t st = ctx().stream;
@@ -1317,9 +1321,17 @@ int ritz_vectors_dev(double *V, double *V2, const double *Qm_dev, int64_t nr, in
     SIGB_CUDA(cudaMemcpyAsync(V, V2, sizeof(double) * (size_t)nr * n, cudaMemcpyDeviceToDevice, st));
     count_launch(1);
     if (first_row_dev) {   // sign normalisation of eigensolve (:178-180); generalized_eigensolve has none
-        grab_first_row_kernel<<<1, 128, 0, st>>>(V, nr, n, first_row_dev);
+        const bool sharded = A != nullptr && A->dist != nullptr;
+        if (sharded && (dist_row_offset(A) != 0 || nr == 0)) {
+            SIGB_CUDA(cudaMemsetAsync(first_row_dev, 0, sizeof(double) * (size_t)n, st));
+        } else {
+            grab_first_row_kernel<<<1, 128, 0, st>>>(V, nr, n, first_row_dev);
+            count_launch();
+        }
+        if (sharded)
+            for (int32_t c = 0; c < n; c += 3) SIGB_CHECK(dist_allreduce(A, first_row_dev + c, std::min(3, n - c), nullptr));
         sign_kernel<<<ew_grid(nr), kThreads, 0, st>>>(V, nr, n, first_row_dev);
-        count_launch(2);
+        count_launch(1);
     }
     SIGB_CUDA(cudaGetLastError());
     return SIGB_OK;

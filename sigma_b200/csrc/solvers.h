@@ -58,7 +58,7 @@ int generalized_lanczos_dev(sigb_matrix_t A, sigb_matrix_t B, sigb_solver_t bs, 
                             const double *q1, uint64_t seed, int64_t row_offset, double *T, double *Q, double *w,
                             double *v, double *zbuf, KState *st);
 int tridiag_eig_host(int n, double *d, double *e, double *Z);
-int ritz_vectors_dev(double *V, double *V2, const double *Qm_dev, int64_t nr, int32_t n,
+int ritz_vectors_dev(sigb_matrix_t A, double *V, double *V2, const double *Qm_dev, int64_t nr, int32_t n,
                      double *first_row_dev);
 size_t kstate_bytes();
 

@@ -53,7 +53,8 @@ inline void sigb_check(int stat)
 }
 
 // Single-process multi-GPU mode.  After sigma::use_gpus(ndev) (ndev <= 0: all visible GPUs) every
-// square csr_matrix is mirrored as one row block per GPU (sigb_mgpu_csr_create): A%matvec, A%matvec_add
+// square csr_matrix / csc_matrix / ellpack_matrix is mirrored as one row block per GPU (sigb_mgpu_csr_create;
+// csc and ellpack through their rows in the order their own matvec loops accumulate them): A%matvec, A%matvec_add
 // and solver%solve(A, x, b [, pc]) with cg / bicgstab / jacobi run on all of them, with the caller's
 // whole vectors and no change to the calling program.  What a multi-GPU mirror cannot do (matvec_t,
 // copies, expressions, ldu, the eigensolvers) is what the library refuses for it.
@@ -350,10 +351,20 @@ struct device_matrix : linear_operator {
     }
     void zero() { for (dp &v : val) v = 0.0; dirty = true; }
     void scalar_multiply(dp alpha) { for (dp &v : val) v *= alpha; dirty = true; }
+    // multi-GPU mirrors of csc / ellpack matrices hold the ROWS of the matrix (the sharded path takes csr
+    // blocks): mg_perm[k] = stored index of the k-th entry in row order, mg_val the values in that order
+    std::vector<int64_t> mg_perm;
+    std::vector<dp> mg_val;
     void upload()
     {
         if (dirty) {
-            sigb_check(sigb_matrix_set_values(mirror, val.data(), (int64_t)val.size()));
+            if (!mg_perm.empty()) {
+                mg_val.resize(mg_perm.size());
+                for (size_t k = 0; k < mg_perm.size(); k++) mg_val[k] = val[(size_t)mg_perm[k]];
+                sigb_check(sigb_matrix_set_values(mirror, mg_val.data(), (int64_t)mg_val.size()));
+            } else {
+                sigb_check(sigb_matrix_set_values(mirror, val.data(), (int64_t)val.size()));
+            }
             dirty = false;
         }
     }
@@ -457,6 +468,29 @@ struct cs_matrix : device_matrix {
             // multi-GPU mode: the pattern goes in whole, the library shards it (row blocks, halo and
             // send lists derived from the graph)
             sigb_check(sigb_mgpu_csr_create(g->n, g->ptr.data(), g->node.data(), &mirror));
+            dirty = true;
+        }
+        if (!mirror && COL && gpus_in_use() > 0 && g->n == g->m) {
+            // a csc_matrix in multi-GPU mode: its rows, each in the order csc_matvec_add reaches it (columns
+            // ascending, a column's entries in stored order -- the stable transpose the one-GPU path builds
+            // on the device, cs_matrices.f90:627-647), sharded like a csr_matrix
+            const int n = g->n;
+            std::vector<int32_t> rptr((size_t)n + 2, 0), rnode((size_t)g->ne);
+            for (int q = 0; q < g->ne; q++) rptr[(size_t)g->node[(size_t)q] + 1]++;
+            rptr[0] = 1;
+            rptr[1] = 1;
+            for (int i = 1; i <= n; i++) rptr[(size_t)i + 1] += rptr[(size_t)i];
+            std::vector<int32_t> fill(rptr.begin() + 1, rptr.end());     // fill[i-1] = next free slot of row i (1-based)
+            mg_perm.assign((size_t)g->ne, 0);
+            for (int j = 1; j <= n; j++)
+                for (int q = g->ptr[(size_t)j - 1] - 1; q < g->ptr[(size_t)j] - 1; q++) {
+                    const int i = g->node[(size_t)q];
+                    const int32_t slot = fill[(size_t)i - 1]++;
+                    rnode[(size_t)slot - 1] = j;
+                    mg_perm[(size_t)slot - 1] = q;
+                }
+            std::vector<int32_t> ptr1(rptr.begin() + 1, rptr.end());
+            sigb_check(sigb_mgpu_csr_create(n, ptr1.data(), rnode.data(), &mirror));
             dirty = true;
         }
         if (!mirror) {
@@ -605,6 +639,22 @@ struct ellpack_matrix : device_matrix {
 
     void sync_mirror() override
     {
+        if (!mirror && gpus_in_use() > 0 && g->n == g->m) {
+            // an ellpack_matrix in multi-GPU mode: its rows without the padding slots (their values are zero:
+            // ellpack_matvec_add adds 0 * x for them, ellpack_matrices.f90:655-658), sharded like a csr_matrix
+            const int n = g->n;
+            std::vector<int32_t> ptr1((size_t)n + 1, 1), rnode;
+            mg_perm.clear();
+            for (int i = 1; i <= n; i++) {
+                for (int k = 0; k < g->degrees[(size_t)i - 1]; k++) {
+                    rnode.push_back(g->node[(size_t)(i - 1) * g->max_d + k]);
+                    mg_perm.push_back((int64_t)(i - 1) * g->max_d + k);
+                }
+                ptr1[(size_t)i] = (int32_t)rnode.size() + 1;
+            }
+            sigb_check(sigb_mgpu_csr_create(n, ptr1.data(), rnode.data(), &mirror));
+            dirty = true;
+        }
         if (!mirror) {
             if (!g->mirror) {
                 g->mirror = std::make_shared<graph_mirror>();

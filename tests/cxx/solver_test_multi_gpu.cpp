@@ -37,6 +37,60 @@ static void build_poisson(int N, csr_matrix &A)
         for (int32_t j : g.get_neighbors(k)) A.set_value(k, j, j == k ? 4.0 : -1.0);
 }
 
+// the same stencil with nonsymmetric values (so that a row / column mix-up cannot hide), in any format
+template <class M>
+static void build_nonsymmetric(int N, M &A)
+{
+    const int n = N * N;
+    ll_graph g;
+    g.init(n);
+    for (int ix = 0; ix < N; ix++)
+        for (int iy = 0; iy < N; iy++) {
+            const int k = N * ix + iy + 1;
+            g.add_edge(k, k);
+            if (iy + 1 < N) { g.add_edge(k, k + 1); g.add_edge(k + 1, k); }
+            if (ix + 1 < N) { g.add_edge(k, k + N); g.add_edge(k + N, k); }
+        }
+    A.init(n, n);
+    A.copy_graph(g);
+    A.zero();
+    for (int k = 1; k <= n; k++)
+        for (int32_t j : g.get_neighbors(k)) A.set_value(k, j, j == k ? 4.0 : (j > k ? -1.25 : -0.75));
+}
+
+// csc_matrix / ellpack_matrix in multi-GPU mode: sharded through their rows in the order their own matvec
+// loops accumulate them, so the product must equal the one-GPU product of the same format bit for bit
+template <class M>
+static int other_format(const char *name, int N, const std::vector<dp> &xs, const std::vector<dp> &y_one_gpu,
+                        const std::vector<dp> &x_one_gpu, long it_one_gpu, dp tol, bool verbose)
+{
+    const int n = N * N;
+    M A;
+    build_nonsymmetric(N, A);
+    std::vector<dp> y(n), f(n), x(n, 0.0);
+    A.matvec(xs.data(), y.data());
+    for (int i = 0; i < n; i++)
+        if (y[i] != y_one_gpu[i]) { std::printf(" multi-GPU %s matvec differs from the one-GPU result at row %d\n", name, i + 1); return 1; }
+    f = y;
+    linear_solver *s = bicgstab(tol);
+    s->setup(A);
+    s->set_max_iterations(20 * N);
+    s->solve(A, x.data(), f.data());
+    const long slack = std::max(1L, (long)std::ceil(0.05 * it_one_gpu));
+    if (s->capped() || std::labs((long)s->iterations - it_one_gpu) > slack) {
+        std::printf(" multi-GPU %s bicgstab: %ld iterations, %ld on one GPU\n", name, (long)s->iterations, it_one_gpu);
+        return 1;
+    }
+    dp num = 0.0, den = 0.0;
+    for (int i = 0; i < n; i++) { num += (x[i] - x_one_gpu[i]) * (x[i] - x_one_gpu[i]); den += x_one_gpu[i] * x_one_gpu[i]; }
+    // (two bicgstab runs to the same |r| <= tol whose dot products are summed in different orders: they agree
+    //  to the tolerance times the condition number, not to rounding -- 6.7e-9 at this size)
+    if (std::sqrt(num / den) > 1e-7) { std::printf(" multi-GPU %s bicgstab solution differs by %g\n", name, std::sqrt(num / den)); return 1; }
+    if (verbose) std::printf(" o %s_matrix sharded through its rows: matvec bit-identical, bicgstab %ld iterations (one GPU: %ld)\n", name,
+                             (long)s->iterations, it_one_gpu);
+    return 0;
+}
+
 static dp rel_diff(const std::vector<dp> &a, const std::vector<dp> &b)
 {
     dp num = 0.0, den = 0.0;
@@ -68,6 +122,30 @@ int main(int argc, char **argv)
     const long it1 = (long)s1->iterations;
     if (s1->capped()) { std::printf(" one-GPU cg hit the safety cap\n"); return 1; }
     y1 = b;
+
+    // one-GPU products and solves of the csc / ellpack forms of a nonsymmetric variant (compared below)
+    std::vector<dp> yc1(n), ye1(n), xc1(n, 0.0), xe1(n, 0.0);
+    long itc1 = 0, ite1 = 0;
+    const dp tol_ns = 1e-10 * std::sqrt((dp)n);
+    {
+        csc_matrix C1;
+        build_nonsymmetric(N, C1);
+        C1.matvec(xs.data(), yc1.data());
+        linear_solver *sc = bicgstab(tol_ns);
+        sc->setup(C1);
+        sc->set_max_iterations(20 * N);
+        sc->solve(C1, xc1.data(), yc1.data());
+        itc1 = (long)sc->iterations;
+        ellpack_matrix E1;
+        build_nonsymmetric(N, E1);
+        E1.matvec(xs.data(), ye1.data());
+        linear_solver *se = bicgstab(tol_ns);
+        se->setup(E1);
+        se->set_max_iterations(20 * N);
+        se->solve(E1, xe1.data(), ye1.data());
+        ite1 = (long)se->iterations;
+        if (sc->capped() || se->capped()) { std::printf(" one-GPU bicgstab on the nonsymmetric variant hit the safety cap\n"); return 1; }
+    }
 
     // ---- all visible GPUs, same program ---------------------------------------
     const int ndev = use_gpus(want_gpus);
@@ -126,5 +204,7 @@ int main(int argc, char **argv)
         return 1;
     }
     if (verbose) std::printf(" o bicgstab on %d GPU(s): %ld iterations\n", ndev, (long)s3->iterations);
+    if (other_format<csc_matrix>("csc", N, xs, yc1, xc1, itc1, tol_ns, verbose)) return 1;
+    if (other_format<ellpack_matrix>("ellpack", N, xs, ye1, xe1, ite1, tol_ns, verbose)) return 1;
     return 0;
 }

@@ -138,6 +138,15 @@ def main():
     assert np.allclose(T, To, rtol=1e-9, atol=1e-11)
     V = np.concatenate([None] * 0 + [gather(np.ascontiguousarray(Vl[:, j])) for j in range(nq)]).reshape(nq, n).T
     assert np.sqrt(((V.T @ V - np.eye(nq)) ** 2).sum()) / nq <= 1e-14
+    # eigensolve on the sharded operator: Ritz values against the oracle, vectors with the reference's sign
+    # convention V(1, i) > 0 -- the first row lives on rank 0, every rank must scale by the same signs
+    lam, Wl = sb.eigensolve(A, nq, q1[lo:hi])
+    info, lamo, Wo = orc.eigensolve(O, nq, q1)
+    assert info == 0 and np.allclose(lam, lamo, rtol=1e-9, atol=1e-10)
+    W = np.concatenate([gather(np.ascontiguousarray(Wl[:, j])) for j in range(nq)]).reshape(nq, n).T
+    assert np.all(W[0, :] > 0)
+    for j in (0, nq - 1):           # extremal pairs: same vector as the serial oracle, sign included
+        assert np.allclose(W[:, j], Wo[:, j], atol=1e-7), j
     # library-drawn start vector does not depend on the sharding
     T1, V1l = sb.lanczos(A, nq, None, seed=5)
     V1 = gather(np.ascontiguousarray(V1l[:, 0]))
