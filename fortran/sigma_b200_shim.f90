@@ -232,6 +232,17 @@ interface                                                                  !
         integer(c_int) :: stat
     end function
 
+    function sigb_generalized_eigensolve(A, B, b_solver, b_pc, n, q1, seed, lambda, V) &
+            & bind(c, name='sigb_generalized_eigensolve') result(stat)
+        import :: c_int, c_int32_t, c_int64_t, c_double, c_ptr
+        type(c_ptr), value :: A, B, b_solver, b_pc   ! b_pc = c_null_ptr: none attached
+        integer(c_int32_t), value :: n
+        type(c_ptr), value :: q1
+        integer(c_int64_t), value :: seed
+        real(c_double), intent(out) :: lambda(*), V(*)
+        integer(c_int) :: stat
+    end function
+
     ! operator expressions: every constructor returns another operator handle
     ! that sigb_matvec*, sigb_solver_* and sigb_lanczos* accept unchanged
     function sigb_operator_sum(A, B, C) bind(c, name='sigb_operator_sum') result(stat)
@@ -595,6 +606,10 @@ end module sigma_b200_shim
 !         call sigb_check( sigb_generalized_lanczos(A%device_handle(), B%device_handle(), &
 !                 & B%solver%dev, pc_or_null, size(T, 2), c_loc(Q(1,1)), 0_c_int64_t, T, Q) )
 !     where B%solver is what `call B%set_solver(...)` attached (:134 runs it).
+!
+! --- src/eigensolver.f90, generalized_eigensolve (:189-208):
+!         call sigb_check( sigb_generalized_eigensolve(A%device_handle(), B%device_handle(), &
+!                 & B%solver%dev, pc_or_null, size(lambda), c_null_ptr, 0_c_int64_t, lambda, V) )
 !
 ! --- src/matrix/formats/cs_matrices.f90, cs_matrix_copy_matrix (:294-322):
 !         h = B%device_handle()
