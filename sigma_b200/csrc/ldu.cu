@@ -359,7 +359,9 @@ tri_chunked_kernel(int32_t n, int32_t chunk_rows, int32_t nchunks, const int32_t
 // ~120 waiting for the stage), so rows of at most two entries without far reads -- every stencil-like
 // factor -- take a straight-line body, and the producer issues one copy per trip instead of four.
 // The right-hand side and the solution live in trip order (coalesced in the sweep); two tiled transposes
-// convert from and to the natural order.
+// convert from and to the natural order.  (Measured and dropped: bulk stores through shared memory instead of
+// plain stores in front of the barrier, L2 prefetch of the slabs 8 / 24 trips ahead -- no effect or slower,
+// profiles/r2_visit_s_1gpu_summary.txt, r2_visit_pf_1gpu_summary.txt.)
 // ---------------------------------------------------------------------------
 struct SweepArgs {
     int32_t n, backward, R, sigma, C, trips, W, S_max, w16_max, nstage, stage_bytes;
