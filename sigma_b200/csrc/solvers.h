@@ -90,7 +90,14 @@ int solver_matvec(sigb_matrix_t A, const double *x, double *y, const DotSpec &do
                   bool x_has_halo);
 // Sum `count` contiguous device doubles over all ranks (no-op on one GPU).
 // skip_flag: device int; when non-zero at execution time the reduction is a
-// no-op (iterations launched past the stopping test), on every rank alike.
+// no-op (iterations launched past the stopping test), on every rank alike -- on the
+// peer-memory transport.  On the NCCL transport the collective cannot be skipped by a
+// device flag (every rank has to enter it), so past the latch it sums the already
+// reduced words once more: the Krylov scalars (pq, rr, rho ...) are UNDEFINED after
+// the latch there.  Nothing reads them: iters, final_res2, capped and done[] are
+// latched by the kernel that evaluates the stopping test, a new solve starts from
+// push_state, and the persistent kernel (the only form that resumes from rr) is not
+// used with that transport.
 bool dist_red_fuse(sigb_matrix_t A, RedFuse *rf);   // peer-memory transport: reductions finished inside their producers (comm.cu)
 int dist_allreduce(sigb_matrix_t A, double *vals, int count, const int *skip_flag = nullptr);
 int dist_allreduce2(sigb_matrix_t A, double *a, double *b, const int *skip_flag = nullptr);
