@@ -462,6 +462,29 @@ struct cs_matrix : device_matrix {
     void get_row(std::vector<int32_t> &nodes, std::vector<dp> &slice, int k) const { if (COL) cross_slice(k, nodes, slice); else line_slice(k, nodes, slice); }
     void get_column(std::vector<int32_t> &nodes, std::vector<dp> &slice, int k) const { if (COL) line_slice(k, nodes, slice); else cross_slice(k, nodes, slice); }
 
+    // The ROWS of a csc_matrix, each in the order csc_matvec_add reaches it (columns ascending, a column's
+    // entries in stored order: cs_matrices.f90:627-647 -- the stable transpose the one-GPU path builds on the
+    // device), with perm[k] = stored index of the k-th entry in row order.  Host-side index work.
+    void rows_in_matvec_order(std::vector<int32_t> &ptr1, std::vector<int32_t> &rnode, std::vector<int64_t> &perm) const
+    {
+        const int nlines = g->n, nrows = COL ? g->m : g->n;
+        ptr1.assign((size_t)nrows + 1, 0);
+        std::vector<int32_t> count((size_t)nrows + 1, 0);
+        for (int q = 0; q < g->ne; q++) count[(size_t)g->node[(size_t)q]]++;
+        ptr1[0] = 1;
+        for (int i = 1; i <= nrows; i++) ptr1[(size_t)i] = ptr1[(size_t)i - 1] + count[(size_t)i];
+        std::vector<int32_t> fill(ptr1.begin(), ptr1.end() - 1);                  // next free slot of row i at fill[i-1]
+        rnode.assign((size_t)g->ne, 0);
+        perm.assign((size_t)g->ne, 0);
+        for (int j = 1; j <= nlines; j++)
+            for (int q = g->ptr[(size_t)j - 1] - 1; q < g->ptr[(size_t)j] - 1; q++) {
+                const int i = g->node[(size_t)q];
+                const int32_t slot = fill[(size_t)i - 1]++;
+                rnode[(size_t)slot - 1] = j;
+                perm[(size_t)slot - 1] = q;
+            }
+    }
+
     void sync_mirror() override
     {
         if (!mirror && !COL && gpus_in_use() > 0 && g->n == g->m) {
@@ -471,26 +494,10 @@ struct cs_matrix : device_matrix {
             dirty = true;
         }
         if (!mirror && COL && gpus_in_use() > 0 && g->n == g->m) {
-            // a csc_matrix in multi-GPU mode: its rows, each in the order csc_matvec_add reaches it (columns
-            // ascending, a column's entries in stored order -- the stable transpose the one-GPU path builds
-            // on the device, cs_matrices.f90:627-647), sharded like a csr_matrix
-            const int n = g->n;
-            std::vector<int32_t> rptr((size_t)n + 2, 0), rnode((size_t)g->ne);
-            for (int q = 0; q < g->ne; q++) rptr[(size_t)g->node[(size_t)q] + 1]++;
-            rptr[0] = 1;
-            rptr[1] = 1;
-            for (int i = 1; i <= n; i++) rptr[(size_t)i + 1] += rptr[(size_t)i];
-            std::vector<int32_t> fill(rptr.begin() + 1, rptr.end());     // fill[i-1] = next free slot of row i (1-based)
-            mg_perm.assign((size_t)g->ne, 0);
-            for (int j = 1; j <= n; j++)
-                for (int q = g->ptr[(size_t)j - 1] - 1; q < g->ptr[(size_t)j] - 1; q++) {
-                    const int i = g->node[(size_t)q];
-                    const int32_t slot = fill[(size_t)i - 1]++;
-                    rnode[(size_t)slot - 1] = j;
-                    mg_perm[(size_t)slot - 1] = q;
-                }
-            std::vector<int32_t> ptr1(rptr.begin() + 1, rptr.end());
-            sigb_check(sigb_mgpu_csr_create(n, ptr1.data(), rnode.data(), &mirror));
+            // a csc_matrix in multi-GPU mode is sharded like a csr_matrix, through its rows (rows_in_matvec_order)
+            std::vector<int32_t> ptr1, rnode;
+            rows_in_matvec_order(ptr1, rnode, mg_perm);
+            sigb_check(sigb_mgpu_csr_create(g->n, ptr1.data(), rnode.data(), &mirror));
             dirty = true;
         }
         if (!mirror) {
@@ -640,19 +647,10 @@ struct ellpack_matrix : device_matrix {
     void sync_mirror() override
     {
         if (!mirror && gpus_in_use() > 0 && g->n == g->m) {
-            // an ellpack_matrix in multi-GPU mode: its rows without the padding slots (their values are zero:
-            // ellpack_matvec_add adds 0 * x for them, ellpack_matrices.f90:655-658), sharded like a csr_matrix
-            const int n = g->n;
-            std::vector<int32_t> ptr1((size_t)n + 1, 1), rnode;
-            mg_perm.clear();
-            for (int i = 1; i <= n; i++) {
-                for (int k = 0; k < g->degrees[(size_t)i - 1]; k++) {
-                    rnode.push_back(g->node[(size_t)(i - 1) * g->max_d + k]);
-                    mg_perm.push_back((int64_t)(i - 1) * g->max_d + k);
-                }
-                ptr1[(size_t)i] = (int32_t)rnode.size() + 1;
-            }
-            sigb_check(sigb_mgpu_csr_create(n, ptr1.data(), rnode.data(), &mirror));
+            // an ellpack_matrix in multi-GPU mode is sharded like a csr_matrix, through its rows without padding
+            std::vector<int32_t> ptr1, rnode;
+            rows_without_padding(ptr1, rnode, mg_perm);
+            sigb_check(sigb_mgpu_csr_create(g->n, ptr1.data(), rnode.data(), &mirror));
             dirty = true;
         }
         if (!mirror) {
@@ -665,6 +663,23 @@ struct ellpack_matrix : device_matrix {
             dirty = true;
         }
         upload();
+    }
+
+    // The rows of an ellpack_matrix without the padding slots (their values are zero: ellpack_matvec_add adds
+    // 0 * x for them, ellpack_matrices.f90:655-658), with perm[k] = index into val of the k-th entry.
+    void rows_without_padding(std::vector<int32_t> &ptr1, std::vector<int32_t> &rnode, std::vector<int64_t> &perm) const
+    {
+        const int n = g->n;
+        ptr1.assign((size_t)n + 1, 1);
+        rnode.clear();
+        perm.clear();
+        for (int i = 1; i <= n; i++) {
+            for (int k = 0; k < g->degrees[(size_t)i - 1]; k++) {
+                rnode.push_back(g->node[(size_t)(i - 1) * g->max_d + k]);
+                perm.push_back((int64_t)(i - 1) * g->max_d + k);
+            }
+            ptr1[(size_t)i] = (int32_t)rnode.size() + 1;
+        }
     }
 
     // call A%copy_matrix(B, trans)   (ellpack_matrix_copy_matrix :169-198), on the device

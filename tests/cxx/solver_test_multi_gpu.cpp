@@ -91,6 +91,64 @@ static int other_format(const char *name, int N, const std::vector<dp> &xs, cons
     return 0;
 }
 
+// Host-only check of the row forms a multi-GPU mirror is built from: the csr row loop over
+// (ptr1, rnode, val[perm]) must give, bit for bit, what the format's OWN reference loop gives
+// (csc_matvec_add cs_matrices.f90:627-647: y(node(k)) += val(k) * x(j), columns ascending;
+//  ellpack_matvec_add ellpack_matrices.f90:640-665: every slot of the row, padding included).
+static int host_side_row_forms(int N, bool verbose)
+{
+    const int n = N * N;
+    rng64 rnd(11);
+    std::vector<dp> x(n);
+    for (dp &v : x) v = rnd.next() - 0.5;
+    auto row_loop = [&](const std::vector<int32_t> &ptr1, const std::vector<int32_t> &rnode, const std::vector<int64_t> &perm,
+                        const std::vector<dp> &val, std::vector<dp> &y) {
+        for (int i = 0; i < n; i++) {
+            dp z = 0.0;
+            for (int k = ptr1[(size_t)i] - 1; k < ptr1[(size_t)i + 1] - 1; k++) z = z + val[(size_t)perm[(size_t)k]] * x[(size_t)rnode[(size_t)k] - 1];
+            y[(size_t)i] = 0.0 + z;
+        }
+    };
+    std::vector<int32_t> ptr1, rnode;
+    std::vector<int64_t> perm;
+    std::vector<dp> y(n), yr(n);
+    {
+        csc_matrix C;
+        build_nonsymmetric(N, C);
+        std::fill(y.begin(), y.end(), 0.0);
+        for (int j = 1; j <= n; j++) {
+            const dp z = x[(size_t)j - 1];
+            for (int k = C.g->ptr[(size_t)j - 1] - 1; k < C.g->ptr[(size_t)j] - 1; k++) y[(size_t)C.g->node[(size_t)k] - 1] += C.val[(size_t)k] * z;
+        }
+        C.rows_in_matvec_order(ptr1, rnode, perm);
+        row_loop(ptr1, rnode, perm, C.val, yr);
+        for (int i = 0; i < n; i++)
+            if (y[(size_t)i] != yr[(size_t)i]) { std::printf(" csc rows: row %d differs from csc_matvec_add\n", i + 1); return 1; }
+        // a nonsymmetric matrix: the row form must not be the column form
+        if (rnode == C.g->node && C.val[(size_t)perm[1]] == C.val[1] && n > 4) {
+            bool same = true;
+            for (size_t k = 0; k < perm.size() && same; k++) same = C.val[(size_t)perm[k]] == C.val[k];
+            if (same) { std::printf(" csc rows: the permutation is the identity on a nonsymmetric matrix\n"); return 1; }
+        }
+    }
+    {
+        ellpack_matrix E;
+        build_nonsymmetric(N, E);
+        for (int i = 1; i <= n; i++) {
+            dp z = 0.0;
+            for (int k = 0; k < E.g->max_d; k++) z = z + E.val[(size_t)(i - 1) * E.g->max_d + k] * x[(size_t)E.g->node[(size_t)(i - 1) * E.g->max_d + k] - 1];
+            y[(size_t)i - 1] = 0.0 + z;
+        }
+        E.rows_without_padding(ptr1, rnode, perm);
+        row_loop(ptr1, rnode, perm, E.val, yr);
+        for (int i = 0; i < n; i++)
+            if (y[(size_t)i] != yr[(size_t)i]) { std::printf(" ellpack rows: row %d differs from ellpack_matvec_add\n", i + 1); return 1; }
+        if ((int)rnode.size() != E.g->ne) { std::printf(" ellpack rows: %zu entries, graph has %d\n", rnode.size(), E.g->ne); return 1; }
+    }
+    if (verbose) std::printf(" o row forms of csc / ellpack matrices reproduce their own matvec loops bit for bit (host only)\n");
+    return 0;
+}
+
 static dp rel_diff(const std::vector<dp> &a, const std::vector<dp> &b)
 {
     dp num = 0.0, den = 0.0;
@@ -101,6 +159,8 @@ static dp rel_diff(const std::vector<dp> &a, const std::vector<dp> &b)
 int main(int argc, char **argv)
 {
     const bool verbose = argc > 1 && !strcmp(argv[1], "-v");
+    if (argc > 2 && !strcmp(argv[2], "--host-only")) return host_side_row_forms(96, verbose);
+    if (host_side_row_forms(64, false)) return 1;
     int want_gpus = 0;
     if (argc > 2) want_gpus = atoi(argv[2]);
     const int N = 512, n = N * N;

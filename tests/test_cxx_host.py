@@ -70,3 +70,14 @@ def test_strategy_host_side():
                        capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("entries, rows and columns work") == 3
+
+
+def test_multi_gpu_row_forms_host_side():
+    """A csc_matrix / ellpack_matrix in multi-GPU mode is sharded through its rows (sigma.hpp
+    rows_in_matvec_order / rows_without_padding): the csr row loop over those rows must reproduce the format's
+    own reference matvec loop bit for bit -- host-side index work, checked here without a GPU."""
+    build()
+    r = subprocess.run([os.path.join(CXX, "_build", "solver_test_multi_gpu"), "-v", "--host-only"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "row forms of csc / ellpack matrices reproduce their own matvec loops" in r.stdout
