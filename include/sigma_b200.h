@@ -527,8 +527,9 @@ SIGB_API int sigb_dist_csr_create(sigb_comm_t comm, int32_t n_global,
  * The handle is then used with WHOLE host arrays in sigb_matrix_set_values,
  * sigb_matvec, sigb_matvec_add, sigb_matrix_get_dims, sigb_solver_setup (cg,
  * bicgstab, jacobi), sigb_solver_solve (pc: jacobi), sigb_solver_get_info,
- * sigb_solver_get_vector and the destroy calls; the *_dev entry points, matvec_t,
- * copies, expressions, ldu and the eigensolvers return SIGB_ERR_UNSUPPORTED for it. */
+ * sigb_solver_get_vector, sigb_lanczos, sigb_eigensolve and the destroy calls; the
+ * *_dev entry points, matvec_t, copies, expressions, ldu and the generalized
+ * eigensolvers return SIGB_ERR_UNSUPPORTED for it. */
 SIGB_API int sigb_mgpu_init(int ndev);
 SIGB_API int sigb_mgpu_finalize(void);
 SIGB_API int sigb_mgpu_device_count(int *ndev);

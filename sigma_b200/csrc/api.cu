@@ -944,8 +944,8 @@ static int lanczos_common(sigb_matrix_t A, int32_t n, const double *q1, uint64_t
 
 int sigb_lanczos(sigb_matrix_t A, int32_t n, const double *q1, uint64_t seed, double *T, double *Q)
 {
-    if (A && A->mg) { ::sigb::set_error("sigb_lanczos: not available for a single-process multi-GPU operator"); return SIGB_ERR_UNSUPPORTED; }
     SIGB_REQUIRE(T && Q, SIGB_ERR_ARG, "sigb_lanczos: T and Q are required");
+    if (A && A->mg) return mgpu_lanczos(A, n, q1, seed, T, Q, nullptr, false);
     return lanczos_common(A, n, q1, seed, T, Q, nullptr, false);
 }
 
@@ -982,8 +982,8 @@ int sigb_lanczos_dev(sigb_matrix_t A, int32_t n, const double *q1_dev, uint64_t 
 
 int sigb_eigensolve(sigb_matrix_t A, int32_t n, const double *q1, uint64_t seed, double *lambda, double *V)
 {
-    if (A && A->mg) { ::sigb::set_error("sigb_eigensolve: not available for a single-process multi-GPU operator"); return SIGB_ERR_UNSUPPORTED; }
     SIGB_REQUIRE(lambda && V, SIGB_ERR_ARG, "sigb_eigensolve: lambda and V are required");
+    if (A && A->mg) return mgpu_lanczos(A, n, q1, seed, nullptr, V, lambda, true);
     return lanczos_common(A, n, q1, seed, nullptr, V, lambda, true);
 }
 

@@ -213,6 +213,37 @@ int mgpu_solver_solve(sigb_solver_t s, sigb_matrix_t A, double *x, const double 
     return SIGB_OK;
 }
 
+// lanczos / eigensolve on every GPU: each worker runs the row-sharded form on its block (identical T and Ritz
+// values on every rank: the dot products are all-reduced bit-identically), writing its rows of the basis into
+// a buffer of its own; the columns are then gathered into the caller's nrow x n column-major array.
+int mgpu_lanczos(sigb_matrix_t A, int32_t n, const double *q1, uint64_t seed, double *T, double *Q, double *lambda,
+                 bool ritz)
+{
+    MgpuMatrix *G = A->mg;
+    const int ndev = mg().ndev;
+    std::vector<std::vector<double>> Qr((size_t)ndev), Tr((size_t)ndev);
+    SIGB_CHECK(run_all([&](int r) {
+        const int32_t lo = G->part[(size_t)r], nloc = G->part[(size_t)r + 1] - lo;
+        Qr[(size_t)r].assign((size_t)std::max(nloc, 1) * n, 0.0);
+        Tr[(size_t)r].assign((size_t)3 * n, 0.0);
+        sigb_matrix_t S = G->shard[(size_t)r];
+        return ritz ? sigb_eigensolve(S, n, q1 ? q1 + lo : nullptr, seed, Tr[(size_t)r].data(), Qr[(size_t)r].data())
+                    : sigb_lanczos(S, n, q1 ? q1 + lo : nullptr, seed, Tr[(size_t)r].data(), Qr[(size_t)r].data());
+    }));
+    if (ritz) {
+        if (lambda) memcpy(lambda, Tr[0].data(), sizeof(double) * (size_t)n);     // sigb_eigensolve returns lambda there
+    } else if (T) {
+        memcpy(T, Tr[0].data(), sizeof(double) * 3 * (size_t)n);
+    }
+    if (Q)
+        for (int r = 0; r < ndev; r++) {
+            const int32_t lo = G->part[(size_t)r], nloc = G->part[(size_t)r + 1] - lo;
+            for (int32_t j = 0; j < n; j++)
+                memcpy(Q + (size_t)j * G->n + lo, Qr[(size_t)r].data() + (size_t)j * nloc, sizeof(double) * (size_t)nloc);
+        }
+    return SIGB_OK;
+}
+
 int mgpu_solver_get_vector(sigb_solver_t s, const char *name, double *out)
 {
     MgpuMatrix *G = s->A ? s->A->mg : nullptr;

@@ -66,6 +66,8 @@ size_t kstate_bytes();
 int mgpu_solver_setup(sigb_solver_t s, sigb_matrix_t A);
 int mgpu_solver_solve(sigb_solver_t s, sigb_matrix_t A, double *x, const double *b, sigb_solver_t pc);
 int mgpu_solver_get_vector(sigb_solver_t s, const char *name, double *out);
+int mgpu_lanczos(sigb_matrix_t A, int32_t n, const double *q1, uint64_t seed, double *T, double *Q, double *lambda,
+                 bool ritz);
 void mgpu_solver_free(sigb_solver_t s);
 
 // ---- persistent cooperative CG kernel (cg_persistent.cu) -------------------

@@ -55,9 +55,9 @@ inline void sigb_check(int stat)
 // Single-process multi-GPU mode.  After sigma::use_gpus(ndev) (ndev <= 0: all visible GPUs) every
 // square csr_matrix / csc_matrix / ellpack_matrix is mirrored as one row block per GPU (sigb_mgpu_csr_create;
 // csc and ellpack through their rows in the order their own matvec loops accumulate them): A%matvec, A%matvec_add
-// and solver%solve(A, x, b [, pc]) with cg / bicgstab / jacobi run on all of them, with the caller's
-// whole vectors and no change to the calling program.  What a multi-GPU mirror cannot do (matvec_t,
-// copies, expressions, ldu, the eigensolvers) is what the library refuses for it.
+// solver%solve(A, x, b [, pc]) with cg / bicgstab / jacobi, lanczos and eigensolve run on all of them, with
+// the caller's whole vectors and no change to the calling program.  What a multi-GPU mirror cannot do
+// (matvec_t, copies, expressions, ldu, the generalized eigensolvers) is what the library refuses for it.
 inline int &gpus_in_use() { static int n = 0; return n; }
 inline int use_gpus(int ndev = 0)
 {

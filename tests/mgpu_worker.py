@@ -114,6 +114,24 @@ def main():
         assert np.linalg.norm(u - uo) / np.linalg.norm(uo) <= 1e-10
     A.destroy()
 
+    # ---- Lanczos / eigensolve: whole vectors in and out, every GPU runs its row block ----------------
+    n, nq = 4096, 12
+    ptr, node, val = G.erdos_renyi_csr(n, seed=41, shift=0.0)
+    O = orc.Matrix(orc.CSR, n, n, node, val, ptr=ptr)
+    q1 = 2 * np.random.default_rng(3).random(n) - 1
+    A = sb.mgpu_csr_matrix(n, ptr, node, val)
+    T, V = sb.lanczos(A, nq, q1)
+    To, Vo = orc.lanczos(O, nq, q1)
+    assert np.allclose(T, To, rtol=1e-9, atol=1e-11)
+    assert np.sqrt(((V.T @ V - np.eye(nq)) ** 2).sum()) / nq <= 1e-14
+    lam, W = sb.eigensolve(A, nq, q1)
+    info, lamo, Wo = orc.eigensolve(O, nq, q1)
+    assert info == 0 and np.allclose(lam, lamo, rtol=1e-9, atol=1e-10)
+    assert np.all(W[0, :] > 0)
+    for j in (0, nq - 1):
+        assert np.allclose(W[:, j], Wo[:, j], atol=1e-7), j
+    A.destroy()
+
     # bad input is refused before anything is sharded
     try:
         sb.mgpu_csr_matrix(3, [1, 2, 3, 4], [1, 2, 9], [1.0, 1.0, 1.0])
