@@ -10,9 +10,11 @@
 // dot products that directly follow a matvec (cg_solvers.f90:134-135,
 // bicgstab_solvers.f90:159-160,163-164, eigensolver.f90:68-69).
 //
-// CSR kernel ("stream" layout).  Rows are grouped on the host into tiles of at
-// most kTileCap stored entries and kTileRows rows.  A persistent CTA walks its
-// tiles round-robin; per tile (spmv_device.cuh has the pipeline)
+// CSR kernel ("stream" layout).  Rows are grouped into tiles of at most 2045 stored
+// entries and 512 rows -- 1021 and 256 for patterns with >= 12 entries per row, whose
+// SpMV is bound by uncoalesced gathers and wants the L1, not deep stages (the two
+// tile shapes, spmv_device.cuh TileCfg).  A persistent CTA walks its tiles
+// round-robin; per tile (spmv_device.cuh has the pipeline)
 //   stage   : the tile's slices of val / node / ptr are brought into shared
 //             memory by the TMA engine (cp.async.bulk, 1-D, completion on an
 //             mbarrier), double-buffered, so no register or thread is tied up
